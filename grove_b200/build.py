@@ -1,0 +1,45 @@
+"""In-tree build of libgrove_place.so (nvcc, sm_100a only)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libgrove_place.so")
+SOURCES = ["engine.cu"]
+DEPS = ["engine.cu", "kernels.cuh", os.path.join("..", "..", "include", "grove_place.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "shared",
+]
+
+
+def nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or stale():
+        cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        env = dict(os.environ)
+        env.pop("CC", None); env.pop("CXX", None)  # /opt/gcc wrappers in this image lack libgomp specs
+        subprocess.check_call(cmd, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,641 @@
+// engine.cu -- libgrove_place.so: host side of the placement engine and the C ABI of
+// include/grove_place.h.  Everything that computes a placement runs in the kernels of kernels.cuh;
+// the host sorts the topology once per label change, validates and uploads tables, and drives the
+// optimistic rounds.  There is no CPU fallback: without a CUDA device the engine cannot be created.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace grove;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = std::max<size_t>(n, 1); else p = nullptr;
+    return e;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = std::max<size_t>(n, 1); else p = nullptr;
+    return e;
+  }
+};
+
+uint32_t fmix32(uint32_t x) {
+  x = x * 0x9E3779B1u + 0x7F4A7C15u;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+
+}  // namespace
+
+struct grove_engine {
+  grove_config_t cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10]{};
+
+  // ---- topology (static until labels change) ----
+  uint32_t N = 0, Npad = 0, L = 0, words = 0;
+  std::vector<uint32_t> raw_dom;      // caller order, N * MAX_LEVELS: cache key
+  std::vector<uint32_t> perm, inv;    // sorted <-> caller
+  std::vector<uint32_t> tdom;         // sorted order, N * MAX_LEVELS tree-ified ids
+  std::vector<uint8_t> vdepth;
+  std::vector<uint32_t> dom_lo[GROVE_MAX_LEVELS], dom_hi[GROVE_MAX_LEVELS];
+  uint32_t n_dom[GROVE_MAX_LEVELS]{}, unit[GROVE_MAX_LEVELS]{};
+  DevBuf<grove_node_t> d_nodes_in;    // caller order, as loaded
+  DevBuf<uint4> d_nres, d_ndom;
+  DevBuf<uint32_t> d_perm, d_inv;
+  DevBuf<uint8_t> d_vdepth;
+  DevBuf<uint32_t> d_dom_lo[GROVE_MAX_LEVELS], d_dom_hi[GROVE_MAX_LEVELS], d_next_dom[GROVE_MAX_LEVELS];
+  bool nodes_loaded = false;
+
+  // ---- gang tables ----
+  uint32_t G = 0, Q = 0, S = 0, P = 0;
+  std::vector<grove_gang_t> gangs;
+  std::vector<grove_clique_t> cliques;
+  std::vector<grove_scope_t> scopes;
+  std::vector<GangInfo> ginfo;
+  std::vector<CliqueInfo> cinfo;
+  bool gangs_loaded = false, ginfo_dirty = true;
+  DevBuf<grove_gang_t> d_gangs;
+  DevBuf<grove_clique_t> d_cliques;
+  DevBuf<grove_scope_t> d_scopes;
+  DevBuf<GangInfo> d_ginfo;
+  DevBuf<CliqueInfo> d_cinfo;
+
+  // ---- round state ----
+  DevBuf<uint8_t> d_state, d_round, d_spec_ok, d_spec_score, d_T;
+  DevBuf<uint16_t> d_spec_n, d_ent_meta;
+  DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
+  DevBuf<grove_gang_status_t> d_status;
+  DevBuf<grove_placement_t> d_out;
+  DevBuf<uint32_t> d_upd_idx;
+  DevBuf<grove_node_t> d_upd_recs;
+  PinBuf<uint32_t> h_counters;
+  PinBuf<grove_gang_status_t> h_status;
+  PinBuf<grove_placement_t> h_out;
+  PinBuf<grove_node_t> h_stage_nodes;
+  uint32_t n_out = 0;
+  bool have_results = false;
+  grove_cycle_stats_t last{};
+
+  // stepping state (multi-GPU)
+  uint32_t round_no = 0;
+  bool in_cycle = false;
+  uint64_t pairs = 0, launches = 0;
+};
+
+#define CU_TRY(e, expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t _c = (expr);                                                                  \
+    if (_c != cudaSuccess) {                                                                  \
+      (e)->err = std::string(#expr) + ": " + cudaGetErrorString(_c);                          \
+      return _c == cudaErrorMemoryAllocation ? GROVE_ERR_OOM : GROVE_ERR_CUDA;                \
+    }                                                                                         \
+  } while (0)
+
+static int32_t fail(grove_engine* e, int32_t code, const char* msg) { e->err = msg; return code; }
+
+// ---------------------------------------------------------------------------------------------
+// topology: sort by label path, tree-ify ids, domain ranges.  Host side; runs only when labels change.
+// Restates what the reference hands a scheduler as the ordered level list
+// (operator/internal/scheduler/kai/topology.go:103-135) plus the per-node label values.
+// ---------------------------------------------------------------------------------------------
+static int32_t build_topology(grove_engine* e, const grove_node_t* nodes, uint32_t n) {
+  const uint32_t L = e->L;
+  e->N = n;
+  e->Npad = (n + 1023u) & ~1023u;
+  e->words = e->Npad / 32;
+  e->raw_dom.resize(size_t(n) * GROVE_MAX_LEVELS);
+  for (uint32_t i = 0; i < n; ++i) std::memcpy(&e->raw_dom[size_t(i) * GROVE_MAX_LEVELS], nodes[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS);
+  e->perm.resize(n); e->inv.resize(n);
+  std::iota(e->perm.begin(), e->perm.end(), 0u);
+  const uint32_t* rd = e->raw_dom.data();
+  std::sort(e->perm.begin(), e->perm.end(), [rd, L](uint32_t a, uint32_t b) {
+    const uint32_t* x = rd + size_t(a) * GROVE_MAX_LEVELS; const uint32_t* y = rd + size_t(b) * GROVE_MAX_LEVELS;
+    for (uint32_t l = 0; l < L; ++l) if (x[l] != y[l]) return x[l] < y[l];
+    return a < b;
+  });
+  for (uint32_t i = 0; i < n; ++i) e->inv[e->perm[i]] = i;
+  e->tdom.assign(size_t(e->Npad) * GROVE_MAX_LEVELS, GROVE_DOM_ABSENT);
+  e->vdepth.assign(e->Npad, 0);
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) { e->dom_lo[l].clear(); e->dom_hi[l].clear(); e->n_dom[l] = 0; e->unit[l] = 0; }
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t* cur = rd + size_t(e->perm[i]) * GROVE_MAX_LEVELS;
+    const uint32_t* prv = i ? rd + size_t(e->perm[i - 1]) * GROVE_MAX_LEVELS : nullptr;
+    bool same_path = prv != nullptr;  // do cur and prv agree (and exist) on every level above l?
+    uint32_t depth = 0;
+    for (uint32_t l = 0; l < L; ++l) {
+      if (cur[l] == GROVE_DOM_ABSENT) break;  // deeper labels are ignored once one is missing
+      bool same = same_path && e->vdepth[i - 1] > l && prv[l] == cur[l];
+      if (same) {
+        uint32_t id = e->tdom[size_t(i - 1) * GROVE_MAX_LEVELS + l];
+        e->tdom[size_t(i) * GROVE_MAX_LEVELS + l] = id;
+        e->dom_hi[l][id] = i + 1;
+      } else {
+        e->tdom[size_t(i) * GROVE_MAX_LEVELS + l] = uint32_t(e->dom_lo[l].size());
+        e->dom_lo[l].push_back(i); e->dom_hi[l].push_back(i + 1);
+      }
+      same_path = same;
+      depth = l + 1;
+    }
+    e->vdepth[i] = uint8_t(depth);
+  }
+  for (uint32_t l = 0; l < L; ++l) {
+    e->n_dom[l] = uint32_t(e->dom_lo[l].size());
+    bool u = e->n_dom[l] > 0;
+    for (uint32_t d = 0; d < e->n_dom[l] && u; ++d) u = (e->dom_hi[l][d] - e->dom_lo[l][d]) == 1;
+    e->unit[l] = u ? 1u : 0u;
+  }
+  // upload static tables
+  CU_TRY(e, e->d_perm.ensure(n)); CU_TRY(e, e->d_inv.ensure(n));
+  CU_TRY(e, e->d_ndom.ensure(e->Npad)); CU_TRY(e, e->d_nres.ensure(e->Npad)); CU_TRY(e, e->d_vdepth.ensure(e->Npad));
+  CU_TRY(e, cudaMemcpyAsync(e->d_perm.p, e->perm.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_inv.p, e->inv.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_ndom.p, e->tdom.data(), sizeof(uint4) * e->Npad, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_vdepth.p, e->vdepth.data(), e->Npad, cudaMemcpyHostToDevice, e->stream));
+  std::vector<uint32_t> nxt(size_t(n) + 1);
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t nd = e->n_dom[l];
+    CU_TRY(e, e->d_dom_lo[l].ensure(nd)); CU_TRY(e, e->d_dom_hi[l].ensure(nd)); CU_TRY(e, e->d_next_dom[l].ensure(size_t(n) + 1));
+    if (nd) {
+      CU_TRY(e, cudaMemcpyAsync(e->d_dom_lo[l].p, e->dom_lo[l].data(), sizeof(uint32_t) * nd, cudaMemcpyHostToDevice, e->stream));
+      CU_TRY(e, cudaMemcpyAsync(e->d_dom_hi[l].p, e->dom_hi[l].data(), sizeof(uint32_t) * nd, cudaMemcpyHostToDevice, e->stream));
+    }
+    uint32_t d = 0;
+    for (uint32_t i = 0; i <= n; ++i) {  // first domain whose lo >= i
+      while (d < nd && e->dom_lo[l][d] < i) ++d;
+      nxt[i] = d;
+    }
+    CU_TRY(e, cudaMemcpyAsync(e->d_next_dom[l].p, nxt.data(), sizeof(uint32_t) * (size_t(n) + 1), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));  // nxt is reused
+  }
+  e->ginfo_dirty = true;
+  return GROVE_OK;
+}
+
+static Topo make_topo(grove_engine* e) {
+  Topo t{};
+  t.nres = e->d_nres.p; t.ndom = e->d_ndom.p;
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+    t.dom_lo[l] = e->d_dom_lo[l].p; t.dom_hi[l] = e->d_dom_hi[l].p; t.next_dom[l] = e->d_next_dom[l].p;
+    t.n_dom[l] = e->n_dom[l]; t.unit[l] = e->unit[l];
+  }
+  t.n = e->N; t.npad = e->Npad; t.L = e->L; t.words = e->words;
+  return t;
+}
+
+static Tables make_tables(grove_engine* e) {
+  Tables t{};
+  t.gangs = e->d_gangs.p; t.cliques = e->d_cliques.p; t.scopes = e->d_scopes.p;
+  t.ginfo = e->d_ginfo.p; t.cinfo = e->d_cinfo.p; t.G = e->G; t.Q = e->Q;
+  return t;
+}
+
+static RoundBufs make_bufs(grove_engine* e) {
+  RoundBufs r{};
+  r.state = e->d_state.p; r.round = e->d_round.p; r.active = e->d_active.p; r.rows = e->d_rows.p;
+  r.counters = e->d_counters.p; r.spec_ok = e->d_spec_ok.p; r.spec_score = e->d_spec_score.p;
+  r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
+  r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p; r.cand = nullptr; r.cand_words = 0;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t grove_abi_version(void) { return GROVE_ABI_VERSION; }
+
+const char* grove_last_error(grove_engine_t* e) { return e ? e->err.c_str() : "null engine"; }
+
+int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
+  if (!cfg || !out) return GROVE_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->abi_version != GROVE_ABI_VERSION) return GROVE_ERR_INVALID_ARG;
+  if (cfg->n_levels < 1 || cfg->n_levels > GROVE_MAX_LEVELS) return GROVE_ERR_INVALID_ARG;
+  if (cfg->world > 1 && cfg->rank >= cfg->world) return GROVE_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GROVE_ERR_NO_DEVICE;  // no CPU fallback
+  if (cfg->device < 0 || cfg->device >= ndev) return GROVE_ERR_NO_DEVICE;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return GROVE_ERR_NO_DEVICE;
+  grove_engine* e = new (std::nothrow) grove_engine();
+  if (!e) return GROVE_ERR_OOM;
+  e->cfg = *cfg; e->L = cfg->n_levels;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  if (e->h_counters.ensure(4) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
+  *out = e;
+  return GROVE_OK;
+}
+
+void grove_engine_destroy(grove_engine_t* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes, const void* dev_nodes, uint32_t n) {
+  if (n == 0 || n > GROVE_MAX_NODES) return fail(e, GROVE_ERR_INVALID_ARG, "node count out of range");
+  if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  if (host_nodes) {
+    bool same = e->nodes_loaded && n == e->N;
+    if (same) {
+      const uint32_t* rd = e->raw_dom.data();
+      for (uint32_t i = 0; i < n && same; ++i)
+        same = std::memcmp(rd + size_t(i) * GROVE_MAX_LEVELS, host_nodes[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS) == 0;
+    }
+    if (!same) { int32_t rc = build_topology(e, host_nodes, n); if (rc) return rc; }
+    CU_TRY(e, e->d_nodes_in.ensure(n));
+    CU_TRY(e, e->h_stage_nodes.ensure(n));
+    std::memcpy(e->h_stage_nodes.p, host_nodes, sizeof(grove_node_t) * n);  // caller buffer is not retained
+    CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p, e->h_stage_nodes.p, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    if (!e->nodes_loaded || n != e->N) return fail(e, GROVE_ERR_STATE, "device load needs a prior host load with the same labels");
+    CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p, dev_nodes, sizeof(grove_node_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+  }
+  k_gather<<<(e->Npad + 255) / 256, 256, 0, e->stream>>>(e->d_nodes_in.p, e->d_perm.p, e->d_vdepth.p, e->d_nres.p, e->N, e->Npad);
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  e->nodes_loaded = true;
+  return GROVE_OK;
+}
+
+int32_t grove_load_nodes(grove_engine_t* e, const grove_node_t* nodes, uint32_t n) {
+  if (!e || !nodes) return GROVE_ERR_INVALID_ARG;
+  return load_nodes_common(e, nodes, nullptr, n);
+}
+
+int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n) {
+  if (!e || !d_nodes) return GROVE_ERR_INVALID_ARG;
+  return load_nodes_common(e, nullptr, d_nodes, n);
+}
+
+int32_t grove_update_nodes(grove_engine_t* e, const uint32_t* idx, const grove_node_t* recs, uint32_t n) {
+  if (!e || (n && (!idx || !recs))) return GROVE_ERR_INVALID_ARG;
+  if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
+  if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
+  if (n == 0) return GROVE_OK;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  std::vector<uint32_t> sidx(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (idx[i] >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "node index out of range");
+    if (std::memcmp(&e->raw_dom[size_t(idx[i]) * GROVE_MAX_LEVELS], recs[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS) != 0)
+      return fail(e, GROVE_ERR_INVALID_ARG, "grove_update_nodes cannot change labels; reload the snapshot");
+    sidx[i] = e->inv[idx[i]];
+  }
+  CU_TRY(e, e->d_upd_idx.ensure(n)); CU_TRY(e, e->d_upd_recs.ensure(n));
+  CU_TRY(e, cudaMemcpyAsync(e->d_upd_idx.p, sidx.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_upd_recs.p, recs, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
+  k_update<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_upd_idx.p, e->d_upd_recs.p, e->d_vdepth.p, e->d_nres.p, n);
+  CU_TRY(e, cudaGetLastError());
+  // keep the caller-order mirror coherent for grove_get_nodes
+  for (uint32_t i = 0; i < n; ++i)
+    CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p + idx[i], recs + i, sizeof(grove_node_t), cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return GROVE_OK;
+}
+
+int32_t grove_get_nodes(grove_engine_t* e, grove_node_t* out, uint32_t cap) {
+  if (!e || !out) return GROVE_ERR_INVALID_ARG;
+  if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
+  if (cap < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  DevBuf<grove_node_t> tmp;
+  CU_TRY(e, tmp.ensure(e->N));
+  k_scatter<<<(e->N + 255) / 256, 256, 0, e->stream>>>(tmp.p, e->d_nodes_in.p, e->d_perm.p, e->d_nres.p, e->N);
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaMemcpyAsync(out, tmp.p, sizeof(grove_node_t) * e->N, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return GROVE_OK;
+}
+
+// same structural rules as the PodGang admission webhook guarantees
+// (operator/internal/webhook/admission/pcs/validation/topologyconstraints.go:195-280)
+static int32_t validate(grove_engine* e, const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                        const grove_scope_t* scopes, uint32_t S) {
+  const uint32_t L = e->L;
+  for (uint32_t gi = 0; gi < G; ++gi) {
+    const grove_gang_t& g = gangs[gi];
+    if (g.n_cliques == 0 || g.n_cliques > GROVE_MAX_GANG_CLIQUES) return fail(e, GROVE_ERR_LIMIT, "gang clique count out of range");
+    if (g.n_scopes == 0 || g.n_scopes > GROVE_MAX_GANG_SCOPES) return fail(e, GROVE_ERR_LIMIT, "gang scope count out of range");
+    if (uint64_t(g.clique_off) + g.n_cliques > Q || uint64_t(g.scope_off) + g.n_scopes > S) return fail(e, GROVE_ERR_INVALID_ARG, "gang table offsets out of range");
+    if (g.level != GROVE_LEVEL_NONE && g.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "gang level out of range");
+    if (g.preferred != GROVE_LEVEL_NONE) return fail(e, GROVE_ERR_INVALID_ARG, "preferred level is reserved");
+    if (g.anchor_node != GROVE_NONE_U32 && e->nodes_loaded && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
+    if (g.base_gang != GROVE_NONE_U32 && (g.base_gang >= G || g.base_gang == gi)) return fail(e, GROVE_ERR_INVALID_ARG, "base gang out of range");
+    uint32_t pods = 0, next = 0;
+    for (uint32_t si = 0; si < g.n_scopes; ++si) {
+      const grove_scope_t& s = scopes[g.scope_off + si];
+      if (s.first_clique != next || s.n_cliques == 0) return fail(e, GROVE_ERR_INVALID_ARG, "scopes must tile the gang's cliques in order");
+      if (s.level != GROVE_LEVEL_NONE && s.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "scope level out of range");
+      if (next + s.n_cliques > g.n_cliques) return fail(e, GROVE_ERR_INVALID_ARG, "scope exceeds gang");
+      for (uint32_t i = 0; i < s.n_cliques; ++i) {
+        const grove_clique_t& q = cliques[g.clique_off + next + i];
+        if (q.scope != si) return fail(e, GROVE_ERR_INVALID_ARG, "clique.scope does not match its scope");
+        if (q.level != GROVE_LEVEL_NONE && q.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "clique level out of range");
+        if (q.replicas < q.min_replicas) return fail(e, GROVE_ERR_INVALID_ARG, "replicas < min_replicas");
+        pods += q.replicas;
+      }
+      next += s.n_cliques;
+    }
+    if (next != g.n_cliques) return fail(e, GROVE_ERR_INVALID_ARG, "scopes do not cover the gang");
+    if (pods > GROVE_MAX_GANG_PODS) return fail(e, GROVE_ERR_LIMIT, "gang exceeds GROVE_MAX_GANG_PODS");
+  }
+  return GROVE_OK;
+}
+
+int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_t n_gangs, const grove_clique_t* cliques,
+                           uint32_t n_cliques, const grove_scope_t* scopes, uint32_t n_scopes) {
+  if (!e || (n_gangs && (!gangs || !cliques || !scopes))) return GROVE_ERR_INVALID_ARG;
+  if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
+  if (n_gangs >= (1u << 24)) return fail(e, GROVE_ERR_LIMIT, "too many gangs");
+  int32_t rc = validate(e, gangs, n_gangs, cliques, n_cliques, scopes, n_scopes);
+  if (rc) return rc;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  e->G = n_gangs; e->Q = n_cliques; e->S = n_scopes;
+  e->gangs.assign(gangs, gangs + n_gangs);
+  e->cliques.assign(cliques, cliques + n_cliques);
+  e->scopes.assign(scopes, scopes + n_scopes);
+  e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
+  CU_TRY(e, e->d_gangs.ensure(n_gangs)); CU_TRY(e, e->d_cliques.ensure(n_cliques)); CU_TRY(e, e->d_scopes.ensure(n_scopes));
+  if (n_gangs) CU_TRY(e, cudaMemcpyAsync(e->d_gangs.p, e->gangs.data(), sizeof(grove_gang_t) * n_gangs, cudaMemcpyHostToDevice, e->stream));
+  if (n_cliques) CU_TRY(e, cudaMemcpyAsync(e->d_cliques.p, e->cliques.data(), sizeof(grove_clique_t) * n_cliques, cudaMemcpyHostToDevice, e->stream));
+  if (n_scopes) CU_TRY(e, cudaMemcpyAsync(e->d_scopes.p, e->scopes.data(), sizeof(grove_scope_t) * n_scopes, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return GROVE_OK;
+}
+
+// derived per-gang / per-clique tables: order rank, anchor (sorted index + ancestor ranges), entry slots
+static int32_t build_ginfo(grove_engine* e) {
+  const uint32_t G = e->G, Q = e->Q;
+  e->ginfo.assign(G, GangInfo{});
+  e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0});
+  std::vector<uint32_t> ord(G);
+  std::iota(ord.begin(), ord.end(), 0u);
+  std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
+  uint32_t pod_off = 0;
+  for (uint32_t r = 0; r < G; ++r) e->ginfo[ord[r]].order = r;
+  for (uint32_t gi = 0; gi < G; ++gi) {
+    const grove_gang_t& g = e->gangs[gi];
+    GangInfo& in = e->ginfo[gi];
+    if (g.anchor_node != GROVE_NONE_U32 && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
+    const uint32_t a = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
+    in.anchor = a; in.pod_off = pod_off;
+    for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+      uint32_t d = l < e->L ? e->tdom[size_t(a) * GROVE_MAX_LEVELS + l] : GROVE_DOM_ABSENT;
+      if (d == GROVE_DOM_ABSENT) { in.anc_lo[l] = a; in.anc_hi[l] = a; }
+      else { in.anc_lo[l] = e->dom_lo[l][d]; in.anc_hi[l] = e->dom_hi[l][d]; }
+    }
+    uint32_t pods = 0;
+    for (uint32_t si = 0; si < g.n_scopes; ++si) {
+      const grove_scope_t& s = e->scopes[g.scope_off + si];
+      for (uint32_t i = 0; i < s.n_cliques; ++i) {
+        const uint32_t qi = g.clique_off + s.first_clique + i;
+        const grove_clique_t& q = e->cliques[qi];
+        uint32_t nd = 0;
+        if (g.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(g.level) + 1);
+        if (s.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(s.level) + 1);
+        if (q.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(q.level) + 1);
+        if (e->cinfo[qi].gang != GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique rows shared between gangs");
+        e->cinfo[qi] = CliqueInfo{gi, nd};
+        pods += q.replicas;
+      }
+    }
+    pod_off += pods;
+  }
+  e->P = pod_off;
+  for (uint32_t qi = 0; qi < Q; ++qi)
+    if (e->cinfo[qi].gang == GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique row owned by no gang");
+  CU_TRY(e, e->d_ginfo.ensure(G)); CU_TRY(e, e->d_cinfo.ensure(Q));
+  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo.data(), sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
+  if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo.data(), sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
+  e->ginfo_dirty = false;
+  return GROVE_OK;
+}
+
+int32_t grove_cycle_begin(grove_engine_t* e) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
+  if (!e->gangs_loaded) return fail(e, GROVE_ERR_STATE, "no gangs submitted");
+  if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  if (e->ginfo_dirty) { int32_t rc = build_ginfo(e); if (rc) return rc; }
+  const uint32_t G = e->G, Q = e->Q;
+  CU_TRY(e, e->d_state.ensure(G)); CU_TRY(e, e->d_round.ensure(G)); CU_TRY(e, e->d_active.ensure(G)); CU_TRY(e, e->d_rows.ensure(Q));
+  CU_TRY(e, e->d_counters.ensure(4)); CU_TRY(e, e->d_spec_ok.ensure(G)); CU_TRY(e, e->d_spec_score.ensure(G));
+  CU_TRY(e, e->d_spec_n.ensure(G)); CU_TRY(e, e->d_spec_top.ensure(G)); CU_TRY(e, e->d_ent_node.ensure(e->P)); CU_TRY(e, e->d_ent_meta.ensure(e->P));
+  CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
+  CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
+  CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
+  // the Q x N matrices
+  {
+    const size_t fw = size_t(Q) * e->words, tb = size_t(Q) * e->Npad;
+    if (e->d_F.ensure(fw) != cudaSuccess || e->d_T.ensure(tb) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(e, GROVE_ERR_OOM, "fit/score matrices do not fit in device memory");
+    }
+  }
+  // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
+  std::vector<uint8_t> st(G, GROVE_GANG_PENDING);
+  for (uint32_t g = 0; g < G; ++g) if (e->gangs[g].flags & GROVE_GANG_GATED) st[g] = GROVE_GANG_GATED_SKIP;
+  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_state.p, st.data(), G, cudaMemcpyHostToDevice, e->stream));
+  if (G) CU_TRY(e, cudaMemsetAsync(e->d_round.p, 0, G, e->stream));
+  if (G) CU_TRY(e, cudaMemsetAsync(e->d_spec_n.p, 0, sizeof(uint16_t) * G, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));  // st is a local
+  e->round_no = 0; e->pairs = 0; e->launches = 0; e->in_cycle = true; e->have_results = false;
+  std::memset(&e->last, 0, sizeof(e->last));
+  return GROVE_OK;
+}
+
+// one optimistic round on this handle's share of the gangs; returns via h_counters
+static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
+  e->round_no++;
+  k_prepare<<<1, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  e->launches += 1;
+  const uint32_t na = e->h_counters.p[0], nr = e->h_counters.p[1];
+  if (na == 0) return GROVE_OK;
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
+  dim3 gfit(e->Npad / 1024, (nr + kFitTile - 1) / kFitTile);
+  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
+  {
+    const uint64_t total = uint64_t(nr) * (e->Npad >> 4);
+    const uint32_t blocks = uint32_t(std::min<uint64_t>((total + 255) / 256, 148u * 64u));
+    k_score<<<blocks, 256, 0, e->stream>>>(tp, tb, rb, nr);
+  }
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
+  k_admit<<<(na + kAdmitWarps - 1) / kAdmitWarps, kAdmitWarps * 32, 0, e->stream>>>(tp, tb, rb);
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
+  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0xFF, sizeof(uint32_t) * e->N, e->stream));
+  k_claim<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 4;
+  e->pairs += uint64_t(nr) * e->N;
+  (void)ms;
+  return GROVE_OK;
+}
+
+static int32_t round_commit_local(grove_engine* e, bool timed) {
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
+  const uint32_t na = e->h_counters.p[0];
+  if (na == 0) return GROVE_OK;
+  k_commit<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tp, tb, rb, e->d_nres.p, e->round_no);
+  CU_TRY(e, cudaGetLastError());
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
+  e->launches += 1;
+  return GROVE_OK;
+}
+
+static int32_t finish_cycle(grove_engine* e, grove_cycle_stats_t* stats) {
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
+  k_finalize<<<1, 1024, 0, e->stream>>>(tp, tb, rb, e->d_perm.p, e->d_status.p, e->d_out.p, e->d_totals.p);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_totals.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (e->G) CU_TRY(e, cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(grove_gang_status_t) * e->G, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  e->n_out = e->h_counters.p[0];
+  if (e->n_out) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->n_out, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  e->last.rounds = e->round_no; e->last.gangs_admitted = e->h_counters.p[1]; e->last.gangs_rejected = e->h_counters.p[2];
+  e->last.pods_bound = e->n_out; e->last.pairs_evaluated = e->pairs; e->last.kernel_launches = e->launches;
+  e->have_results = true; e->in_cycle = false;
+  if (stats) *stats = e->last;
+  return GROVE_OK;
+}
+
+int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  if (e->cfg.world > 1) return fail(e, GROVE_ERR_STATE, "sharded handle: drive the cycle with grove_round_* and reduce between steps");
+  int32_t rc = grove_cycle_begin(e);
+  if (rc) return rc;
+  float ms_fit = 0, ms_score = 0, ms_admit = 0, ms_commit = 0;
+  CU_TRY(e, cudaEventRecord(e->ev[8], e->stream));
+  for (;;) {
+    if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) break;
+    rc = round_eval(e, true, nullptr);
+    if (rc) { e->in_cycle = false; return rc; }
+    const uint32_t na = e->h_counters.p[0], unres = e->h_counters.p[2];
+    if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; break; }  // nothing left (and nothing propagated): not a round
+    if (na == 0) {  // dependency cycle / unreachable base
+      k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
+      e->launches += 1;
+      break;
+    }
+    rc = round_commit_local(e, true);
+    if (rc) { e->in_cycle = false; return rc; }
+    CU_TRY(e, cudaEventSynchronize(e->ev[4]));
+    float t;
+    cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); ms_fit += t;
+    cudaEventElapsedTime(&t, e->ev[1], e->ev[2]); ms_score += t;
+    cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_admit += t;
+    cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_commit += t;
+  }
+  CU_TRY(e, cudaEventRecord(e->ev[9], e->stream));
+  rc = finish_cycle(e, nullptr);
+  if (rc) { e->in_cycle = false; return rc; }
+  float tot = 0; cudaEventElapsedTime(&tot, e->ev[8], e->ev[9]);
+  e->last.ms_fit = ms_fit; e->last.ms_score = ms_score; e->last.ms_admit = ms_admit; e->last.ms_commit = ms_commit; e->last.ms_total = tot;
+  if (stats) *stats = e->last;
+  return GROVE_OK;
+}
+
+int32_t grove_get_placements(grove_engine_t* e, grove_placement_t* out, uint32_t cap, uint32_t* n_out) {
+  if (!e || !n_out) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results) return fail(e, GROVE_ERR_STATE, "no completed cycle");
+  *n_out = e->n_out;
+  if (!out) return GROVE_OK;
+  if (cap < e->n_out) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  std::memcpy(out, e->h_out.p, sizeof(grove_placement_t) * e->n_out);
+  return GROVE_OK;
+}
+
+int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint32_t cap) {
+  if (!e || !out) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results) return fail(e, GROVE_ERR_STATE, "no completed cycle");
+  if (cap < e->G) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  std::memcpy(out, e->h_status.p, sizeof(grove_gang_status_t) * e->G);
+  return GROVE_OK;
+}
+
+// ---- multi-GPU stepping (filled in with the sharded path) ----
+int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+}
+int32_t grove_round_commit(grove_engine_t* e, void** d_delta_words, uint32_t* n_delta_words) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+}
+int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining_local) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+}
+int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+}
+
+// ---- introspection for parity tests ----
+int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap) {
+  if (!e || !sorted_to_caller) return GROVE_ERR_INVALID_ARG;
+  if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
+  if (cap < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  std::memcpy(sorted_to_caller, e->perm.data(), sizeof(uint32_t) * e->N);
+  return GROVE_OK;
+}
+
+int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* words, uint32_t cap_words) {
+  if (!e || !words) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
+  const uint32_t w = (e->N + 31) / 32;
+  if (cap_words < w) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaMemcpy(words, e->d_F.p + size_t(clique) * e->words, sizeof(uint32_t) * w, cudaMemcpyDeviceToHost));
+  return GROVE_OK;
+}
+
+int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* bytes, uint32_t cap_bytes) {
+  if (!e || !bytes) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
+  if (cap_bytes < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaMemcpy(bytes, e->d_T.p + size_t(clique) * e->Npad, e->N, cudaMemcpyDeviceToHost));
+  return GROVE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,654 @@
+// kernels.cuh -- sm_100a kernels of the gang-placement cycle.
+//
+//   k_fit     K1  node x clique resource-fit bitmap          (Filter; oracle: fit(), grove_oracle.c)
+//   k_score   K2  topology-distance score matrix, u8         (Score;  oracle: closeness())
+//   k_admit   K3  per-gang all-or-nothing admission: first feasible domain in score order, pods
+//                 packed by warp ballot / prefix sums over the fit words
+//   k_claim / k_commit   optimistic conflict resolution between gangs of one round
+//   k_prepare / k_finalize / k_gather / k_scatter   round bookkeeping and table (un)packing
+//
+// Semantics are DESIGN.md "Placement semantics"; the reference contract they restate is cited in
+// include/grove_place.h.  Integer / compare work only: no tensor cores, no floating point.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/grove_place.h"
+
+namespace grove {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kMaxPieces = 2 * GROVE_MAX_LEVELS + 3;
+
+struct GangInfo {     // 48 B, built on the host at submit time
+  uint32_t anchor;    // sorted node index
+  uint32_t order;     // rank by (priority desc, index asc)
+  uint32_t pod_off;   // first slot in the entry arrays
+  uint32_t pad;
+  uint32_t anc_lo[GROVE_MAX_LEVELS];  // node range of the anchor's domain per level; [a,a) if label absent
+  uint32_t anc_hi[GROVE_MAX_LEVELS];
+};
+
+struct CliqueInfo {   // 8 B
+  uint32_t gang;
+  uint32_t need_depth;  // labels a candidate node must carry (deepest binding Required level + 1)
+};
+
+struct Topo {
+  const uint4* nres;       // [npad] dynamic: free_cpu, free_mem, free_gpu | free_pods << 16, flags | vdepth << 16
+  const uint4* ndom;       // [npad] static: tree-ified domain index per level
+  const uint32_t* dom_lo[GROVE_MAX_LEVELS];
+  const uint32_t* dom_hi[GROVE_MAX_LEVELS];
+  const uint32_t* next_dom[GROVE_MAX_LEVELS];  // [n+1] first level-l domain starting at or after node i
+  uint32_t n_dom[GROVE_MAX_LEVELS];
+  uint32_t unit[GROVE_MAX_LEVELS];             // every domain of the level is a single node
+  uint32_t n, npad, L, words;                  // words = npad / 32 (row stride of the fit bitmap)
+};
+
+struct Tables {
+  const grove_gang_t* gangs;
+  const grove_clique_t* cliques;
+  const grove_scope_t* scopes;
+  const GangInfo* ginfo;
+  const CliqueInfo* cinfo;
+  uint32_t G, Q;
+};
+
+struct RoundBufs {
+  uint8_t* state;        // [G] GROVE_GANG_*
+  uint8_t* round;        // [G]
+  uint32_t* active;      // [G] gangs evaluated this round
+  uint32_t* rows;        // [Q] clique rows evaluated this round
+  uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated by this prepare
+  uint8_t* spec_ok;      // [G]
+  uint8_t* spec_score;   // [G]
+  uint16_t* spec_n;      // [G] entries incl. surplus
+  uint32_t* spec_top;    // [G]
+  uint32_t* ent_node;    // [P]
+  uint16_t* ent_meta;    // [P] clique_rel | score << 8
+  uint32_t* claim;       // [n]
+  uint32_t* F;           // [Q][words]
+  uint8_t* T;            // [Q][npad]
+  uint32_t* cand;        // [G][cand_words] necessary-condition bits over gang-level domains
+  uint32_t cand_words;
+};
+
+// ------------------------------------------------------------------------------------------------
+// table packing
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather(const grove_node_t* __restrict__ in, const uint32_t* __restrict__ perm,
+                         const uint8_t* __restrict__ vdepth, uint4* __restrict__ nres, uint32_t n, uint32_t npad) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (i < n) {
+    const uint4* p = reinterpret_cast<const uint4*>(in + perm[i]);  // first 16 B of the 32 B record
+    uint4 a = __ldg(p);
+    r.x = a.x; r.y = a.y; r.z = a.z;                                // gpu | pods << 16 is already packed
+    r.w = (a.w & 0xFFFFu) | (uint32_t(vdepth[i]) << 16);
+  }
+  nres[i] = r;
+}
+
+__global__ void k_scatter(grove_node_t* __restrict__ out, const grove_node_t* __restrict__ orig,
+                          const uint32_t* __restrict__ perm, const uint4* __restrict__ nres, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c = perm[i];
+  grove_node_t nd = orig[c];
+  uint4 r = nres[i];
+  nd.free_cpu_milli = r.x; nd.free_mem_mib = r.y; nd.free_gpu = uint16_t(r.z & 0xFFFFu); nd.free_pods = uint16_t(r.z >> 16);
+  out[c] = nd;
+}
+
+__global__ void k_update(const uint32_t* __restrict__ idx_sorted, const grove_node_t* __restrict__ recs,
+                         const uint8_t* __restrict__ vdepth, uint4* __restrict__ nres, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  uint32_t s = idx_sorted[i];
+  grove_node_t nd = recs[i];
+  nres[s] = make_uint4(nd.free_cpu_milli, nd.free_mem_mib, uint32_t(nd.free_gpu) | (uint32_t(nd.free_pods) << 16),
+                       (nd.flags & 0xFFFFu) | (uint32_t(vdepth[s]) << 16));
+}
+
+// ------------------------------------------------------------------------------------------------
+// round bookkeeping: which gangs are evaluated this round, and their clique rows
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(kFull, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+
+// single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint32_t round_no, uint32_t rank, uint32_t world) {
+  __shared__ int s_changed;
+  __shared__ uint32_t s_warp_a[32], s_warp_r[32];
+  __shared__ uint32_t s_na, s_nr, s_unres, s_tot_a, s_tot_r, s_prop;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
+  // scaled gangs of a rejected / skipped base gang are rejected with it (transitively)
+  if (tid == 0) s_prop = 0;
+  do {
+    __syncthreads();
+    if (tid == 0) s_changed = 0;
+    __syncthreads();
+    for (uint32_t g = tid; g < tb.G; g += 1024) {
+      if (rb.state[g] != GROVE_GANG_PENDING) continue;
+      uint32_t b = tb.gangs[g].base_gang;
+      if (b == GROVE_NONE_U32) continue;
+      uint8_t bs = rb.state[b];
+      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
+        rb.state[g] = GROVE_GANG_BASE_REJECTED; rb.round[g] = r8; s_changed = 1; s_prop = 1;
+      }
+    }
+    __syncthreads();
+  } while (s_changed);
+  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; }
+  __syncthreads();
+  for (uint32_t base = 0; base < tb.G; base += 1024) {
+    uint32_t g = base + tid;
+    uint32_t act = 0, ncl = 0, unres = 0, coff = 0;
+    if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
+      unres = 1;
+      grove_gang_t gg = tb.gangs[g];
+      bool ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
+      bool mine = world <= 1 || (g % world) == rank;
+      if (ready && mine) { act = 1; ncl = gg.n_cliques; coff = gg.clique_off; }
+    }
+    uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
+    uint32_t un = __popc(__ballot_sync(kFull, unres));
+    if (lane == 31) { s_warp_a[warp] = ia; s_warp_r[warp] = ir; }
+    if (lane == 0 && un) atomicAdd(&s_unres, un);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t va = s_warp_a[lane], vr = s_warp_r[lane];
+      uint32_t sa = warp_incl_scan(va, lane), sr = warp_incl_scan(vr, lane);
+      s_warp_a[lane] = sa - va; s_warp_r[lane] = sr - vr;  // exclusive per-warp offsets
+      if (lane == 31) { s_tot_a = sa; s_tot_r = sr; }
+    }
+    __syncthreads();
+    uint32_t oa = s_na + s_warp_a[warp] + ia - act;
+    uint32_t orr = s_nr + s_warp_r[warp] + ir - ncl;
+    if (act) {
+      rb.active[oa] = g;
+      for (uint32_t i = 0; i < ncl; ++i) rb.rows[orr + i] = coff + i;
+    }
+    __syncthreads();
+    if (tid == 0) { s_na += s_tot_a; s_nr += s_tot_r; }
+    __syncthreads();
+  }
+  if (tid == 0) { rb.counters[0] = s_na; rb.counters[1] = s_nr; rb.counters[2] = s_unres; rb.counters[3] = s_prop; }
+}
+
+// dependency cycle or unreachable base: nothing can become active any more
+__global__ void k_reject_rest(Tables tb, RoundBufs rb, uint32_t round_no) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
+    rb.state[g] = GROVE_GANG_BASE_REJECTED;
+    rb.round[g] = uint8_t(round_no > 255 ? 255 : round_no);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: node x clique resource-fit bitmap.
+// CTA = 1024 nodes (lane = node, record in registers) x a tile of kFitTile clique rows whose
+// requirements are staged in shared memory.  One __ballot_sync per (warp, clique) yields the 32-bit
+// fit word; words are staged in shared memory and written back as full 128-byte lines per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFitTile = 128;
+
+__global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) {
+  __shared__ uint4 s_prm[kFitTile];
+  __shared__ uint32_t s_row[kFitTile];
+  __shared__ uint32_t s_out[kFitTile][32];
+  const uint32_t n_rows = rb.counters[1];
+  const uint32_t r0 = blockIdx.y * kFitTile;
+  if (r0 >= n_rows) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kFitTile) {
+    uint32_t r = r0 + tid;
+    uint4 p = make_uint4(kFull, kFull, kFull, 0);  // never fits
+    uint32_t q = 0;
+    if (r < n_rows) {
+      q = rb.rows[r];
+      grove_clique_t c = tb.cliques[q];
+      p = make_uint4(c.req_cpu_milli, c.req_mem_mib, c.req_gpu, uint32_t(c.class_mask) | (tb.cinfo[q].need_depth << 16));
+    }
+    s_prm[tid] = p; s_row[tid] = q;
+  }
+  __syncthreads();
+  const uint32_t node = blockIdx.x * 1024 + tid;           // npad is a multiple of 1024
+  const uint4 r = __ldg(tp.nres + node);
+  const uint32_t gpu = r.z & 0xFFFFu, pods = r.z >> 16;
+  const uint32_t depth = (r.w >> 16) & 0xFu;
+  const uint32_t onehot = ((r.w & GROVE_NODE_SCHEDULABLE) && pods >= 1) ? (1u << ((r.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) : 0u;
+#pragma unroll 4
+  for (int c = 0; c < kFitTile; ++c) {
+    const uint4 p = s_prm[c];
+    bool ok = (r.x >= p.x) & (r.y >= p.y) & (gpu >= p.z) & ((p.w & onehot) != 0) & (depth >= (p.w >> 16));
+    uint32_t b = __ballot_sync(kFull, ok);
+    if (lane == 0) s_out[c][warp] = b;
+  }
+  __syncthreads();
+  for (int c = warp; c < kFitTile; c += 32) {
+    if (r0 + c < n_rows) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: topology-distance score matrix.  T[q][n] = fit ? 1 + #levels at which n shares the anchor's
+// domain : 0.  Nodes are stored in topology order, so the anchor's domains are index ranges and the
+// score is piecewise constant: a thread owns 16 consecutive nodes of one row, expands its 16 fit bits
+// to bytes and writes one 128-bit store; only chunks straddling an ancestor boundary go per byte.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {  // 4 bits -> 4 bytes of 0/1
+  return (nib * 0x00204081u) & 0x01010101u;
+}
+
+__global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb, uint32_t n_rows) {
+  const uint32_t cpr = tp.npad >> 4;  // 16-node chunks per row
+  const uint64_t total = uint64_t(n_rows) * cpr;
+  for (uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; id < total; id += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t r = uint32_t(id / cpr), ch = uint32_t(id - uint64_t(r) * cpr);
+    const uint32_t q = __ldg(rb.rows + r);
+    const uint32_t n0 = ch << 4;
+    const uint32_t bits = (__ldg(rb.F + size_t(q) * tp.words + (n0 >> 5)) >> (n0 & 16)) & 0xFFFFu;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (bits) {
+      const GangInfo* gi = tb.ginfo + __ldg(&tb.cinfo[q].gang);
+      const uint4 alo = __ldg(reinterpret_cast<const uint4*>(gi->anc_lo));
+      const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(gi->anc_hi));
+      const uint32_t lo[4] = {alo.x, alo.y, alo.z, alo.w}, hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
+      uint32_t inside = 0; bool uniform = true;
+#pragma unroll
+      for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
+        if (l < (int)tp.L) {
+          bool in = n0 >= lo[l] && n0 + 16 <= hi[l];
+          bool outl = n0 + 16 <= lo[l] || n0 >= hi[l];
+          inside += in; uniform &= (in | outl);
+        }
+      }
+      if (uniform) {
+        const uint32_t v = inside + 1;
+        out.x = spread4(bits & 0xF) * v; out.y = spread4((bits >> 4) & 0xF) * v;
+        out.z = spread4((bits >> 8) & 0xF) * v; out.w = spread4(bits >> 12) * v;
+      } else {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((bits >> j) & 1u) {
+            uint32_t n = n0 + j, c = 1;
+#pragma unroll
+            for (int l = 0; l < GROVE_MAX_LEVELS; ++l) c += (l < (int)tp.L && n >= lo[l] && n < hi[l]);
+            w[j >> 2] |= c << ((j & 3) * 8);
+          }
+        }
+        out = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    *reinterpret_cast<uint4*>(rb.T + size_t(q) * tp.npad + n0) = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: gang admission.  One warp per active gang.
+// ------------------------------------------------------------------------------------------------
+struct WarpCtx {
+  uint32_t ent_node[GROVE_MAX_GANG_PODS];
+  uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel | score << 8
+  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
+  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
+};
+
+struct GangRegs {   // warp-uniform registers
+  uint32_t a, L, n, np;
+  uint32_t anc_lo[GROVE_MAX_LEVELS], anc_hi[GROVE_MAX_LEVELS];
+  uint32_t clique_off;
+};
+
+// Ordered pieces of [lo,hi): descending score, ties by ascending rotated index (n - anchor) mod N.
+// from == L: node granularity (ring l = anc_l \ anc_{l+1}, upper part then lower part);
+// from <  L: level-`from` domain granularity (the anchor's own domain whole, then the rings).
+__device__ __forceinline__ int make_pieces(const GangRegs& g, uint32_t lo, uint32_t hi, uint32_t from,
+                                           uint32_t* plo, uint32_t* phi) {
+  int k = 0;
+  if (g.a < lo || g.a >= hi) { plo[0] = lo; phi[0] = hi; return hi > lo ? 1 : 0; }
+  uint32_t prev_lo = g.a, prev_hi = g.a;
+  if (from < g.L) {
+    prev_lo = max(g.anc_lo[from], lo); prev_hi = min(g.anc_hi[from], hi);
+    if (prev_hi > prev_lo) { plo[k] = prev_lo; phi[k] = prev_hi; ++k; }
+  }
+  for (int l = int(min(from, g.L)) - 1; l >= 0; --l) {
+    uint32_t cl = max(g.anc_lo[l], lo), ch = min(g.anc_hi[l], hi);
+    if (ch > prev_hi) { plo[k] = prev_hi; phi[k] = ch; ++k; }
+    if (prev_lo > cl) { plo[k] = cl; phi[k] = prev_lo; ++k; }
+    prev_lo = min(cl, prev_lo); prev_hi = max(ch, prev_hi);
+  }
+  if (hi > prev_hi) { plo[k] = prev_hi; phi[k] = hi; ++k; }
+  if (prev_lo > lo) { plo[k] = lo; phi[k] = prev_lo; ++k; }
+  return k;
+}
+
+// pods of clique cr that still fit on node n, given what this gang has already put there
+__device__ __forceinline__ uint32_t cap_now(const Topo& tp, const WarpCtx& cx, uint32_t np, uint32_t cr, uint32_t n) {
+  const uint4 r = __ldg(tp.nres + n);
+  uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
+  for (uint32_t i = 0; i < np; ++i) {
+    if (cx.ent_node[i] == n) {
+      const uint4 o = cx.clq[cx.ent_meta[i] & 0xFFu];
+      cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
+    }
+  }
+  const uint4 q = cx.clq[cr];
+  uint32_t c = pods;
+  if (q.x) c = min(c, cpu / q.x);
+  if (q.y) c = min(c, mem / q.y);
+  if (q.z) c = min(c, gpu / q.z);
+  return c;
+}
+
+// Put up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed.
+__device__ uint32_t take(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
+                         uint32_t lo, uint32_t hi, uint32_t want, uint32_t lane) {
+  if (want == 0 || hi <= lo) return 0;
+  const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+  const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+  uint32_t plo[kMaxPieces], phi[kMaxPieces];
+  const int np_ = make_pieces(g, lo, hi, g.L, plo, phi);
+  uint32_t placed = 0;
+  for (int p = 0; p < np_ && placed < want; ++p) {
+    const uint32_t a = plo[p], b = phi[p];
+    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (uint32_t wb = w0; wb <= w1 && placed < want; wb += 32) {
+      // 32 fit words at a time, one per lane
+      uint32_t myw = 0;
+      if (wb + lane <= w1) {
+        myw = __ldg(Frow + wb + lane);
+        if (wb + lane == w0) myw &= kFull << (a & 31);
+        if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
+      }
+      uint32_t nz = __ballot_sync(kFull, myw != 0);
+      while (nz && placed < want) {
+        const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
+        const uint32_t bits = __shfl_sync(kFull, myw, src);
+        const uint32_t n = ((wb + src) << 5) + lane;
+        const bool mine = (bits >> lane) & 1u;
+        const uint32_t c = mine ? cap_now(tp, cx, g.np, cr, n) : 0u;
+        const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
+        const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
+        const uint32_t tincl = warp_incl_scan(t, lane);
+        if (t) {
+          const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+          const uint32_t pos = g.np + tincl - t;
+          for (uint32_t j = 0; j < t; ++j) { cx.ent_node[pos + j] = n; cx.ent_meta[pos + j] = meta; }
+        }
+        const uint32_t tot = __shfl_sync(kFull, tincl, 31);
+        g.np += tot; placed += tot;
+        __syncwarp();
+      }
+    }
+  }
+  return placed;
+}
+
+__device__ __forceinline__ bool fill_min(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
+                                         uint32_t lo, uint32_t hi, uint32_t lane) {
+  const uint32_t m = cx.clq[cr].w & 0xFFu;
+  const uint32_t mark = g.np;
+  if (take(tp, rb, cx, g, cr, lo, hi, m, lane) < m) { g.np = mark; return false; }
+  if (lane == 0) { cx.Hlo[cr] = lo; cx.Hhi[cr] = hi; }
+  __syncwarp();
+  return true;
+}
+
+// clique whose own Required level is a unit level (one node per domain, e.g. hostname): first node of
+// [lo,hi) in score order that takes all m pods
+__device__ bool find_unit(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
+                          uint32_t lo, uint32_t hi, uint32_t lane) {
+  const uint32_t m = cx.clq[cr].w & 0xFFu;
+  const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+  const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+  uint32_t plo[kMaxPieces], phi[kMaxPieces];
+  const int np_ = make_pieces(g, lo, hi, g.L, plo, phi);
+  for (int p = 0; p < np_; ++p) {
+    const uint32_t a = plo[p], b = phi[p];
+    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (uint32_t wb = w0; wb <= w1; wb += 32) {
+      uint32_t myw = 0;
+      if (wb + lane <= w1) {
+        myw = __ldg(Frow + wb + lane);
+        if (wb + lane == w0) myw &= kFull << (a & 31);
+        if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
+      }
+      uint32_t nz = __ballot_sync(kFull, myw != 0);
+      while (nz) {
+        const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
+        const uint32_t bits = __shfl_sync(kFull, myw, src);
+        const uint32_t n = ((wb + src) << 5) + lane;
+        const bool mine = (bits >> lane) & 1u;
+        const uint32_t c = mine ? cap_now(tp, cx, g.np, cr, n) : 0u;
+        const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
+        if (okb) {
+          const uint32_t first = __ffs(okb) - 1;
+          const uint32_t nn = ((wb + src) << 5) + first;
+          const uint16_t meta = uint16_t(cr | (uint32_t(Trow[nn]) << 8));
+          for (uint32_t j = lane; j < m; j += 32) { cx.ent_node[g.np + j] = nn; cx.ent_meta[g.np + j] = meta; }
+          if (lane == 0) { cx.Hlo[cr] = nn; cx.Hhi[cr] = nn + 1; }
+          g.np += m;
+          __syncwarp();
+          return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+__device__ bool place_scope(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, const grove_scope_t& s,
+                            uint32_t lo, uint32_t hi, int lvl, uint32_t lane) {
+  const uint32_t mark = g.np;
+  for (uint32_t i = 0; i < s.n_cliques; ++i) {
+    const uint32_t cr = s.first_clique + i;
+    const uint32_t w = cx.clq[cr].w;
+    const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
+    bool ok = false;
+    if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
+      if (tp.unit[ql] && m >= 1) {
+        ok = find_unit(tp, rb, cx, g, cr, lo, hi, lane);
+      } else {
+        uint32_t plo[kMaxPieces], phi[kMaxPieces];
+        const int np_ = make_pieces(g, lo, hi, ql, plo, phi);
+        for (int p = 0; p < np_ && !ok; ++p) {
+          const uint32_t d0 = __ldg(tp.next_dom[ql] + plo[p]), d1 = __ldg(tp.next_dom[ql] + phi[p]);
+          for (uint32_t d = d0; d < d1 && !ok; ++d)
+            ok = fill_min(tp, rb, cx, g, cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d), lane);
+        }
+      }
+    } else {
+      ok = fill_min(tp, rb, cx, g, cr, lo, hi, lane);
+    }
+    if (!ok) { g.np = mark; return false; }
+  }
+  return true;
+}
+
+__device__ bool place_in(const Topo& tp, const Tables& tb, const RoundBufs& rb, WarpCtx& cx, GangRegs& g,
+                         const grove_gang_t& gg, uint32_t lo, uint32_t hi, int lvl, uint32_t lane) {
+  g.np = 0;
+  for (uint32_t si = 0; si < gg.n_scopes; ++si) {
+    const grove_scope_t s = tb.scopes[gg.scope_off + si];
+    bool ok = false;
+    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
+      uint32_t plo[kMaxPieces], phi[kMaxPieces];
+      const int np_ = make_pieces(g, lo, hi, s.level, plo, phi);
+      for (int p = 0; p < np_ && !ok; ++p) {
+        const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
+        for (uint32_t d = d0; d < d1 && !ok; ++d)
+          ok = place_scope(tp, rb, cx, g, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), lane);
+      }
+    } else {
+      ok = place_scope(tp, rb, cx, g, s, lo, hi, lvl, lane);
+    }
+    if (!ok) { g.np = 0; return false; }
+  }
+  return true;
+}
+
+constexpr int kAdmitWarps = 4;
+
+__global__ void __launch_bounds__(kAdmitWarps * 32) k_admit(Topo tp, Tables tb, RoundBufs rb) {
+  __shared__ WarpCtx s_cx[kAdmitWarps];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ai = blockIdx.x * kAdmitWarps + warp;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t gi = rb.active[ai];
+  const grove_gang_t gg = tb.gangs[gi];
+  const GangInfo info = tb.ginfo[gi];
+  WarpCtx& cx = s_cx[warp];
+  GangRegs g;
+  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.np = 0; g.clique_off = gg.clique_off;
+#pragma unroll
+  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
+  for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
+    const grove_clique_t q = tb.cliques[gg.clique_off + c];
+    cx.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
+                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
+    cx.Hlo[c] = 0; cx.Hhi[c] = 0;
+  }
+  __syncwarp();
+  bool ok = false; uint32_t top = GROVE_NONE_U32;
+  if (gg.level == GROVE_LEVEL_NONE) {
+    ok = place_in(tp, tb, rb, cx, g, gg, 0, tp.n, -1, lane);
+    if (ok) top = 0;
+  } else {
+    const uint32_t gl = gg.level;
+    const uint32_t* cand = rb.cand ? rb.cand + size_t(gi) * rb.cand_words : nullptr;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int np_ = make_pieces(g, 0, tp.n, gl, plo, phi);
+    for (int p = 0; p < np_ && !ok; ++p) {
+      const uint32_t d0 = __ldg(tp.next_dom[gl] + plo[p]), d1 = __ldg(tp.next_dom[gl] + phi[p]);
+      for (uint32_t d = d0; d < d1 && !ok; ++d) {
+        if (cand && !((__ldg(cand + (d >> 5)) >> (d & 31)) & 1u)) continue;  // necessary condition failed
+        const uint32_t dl = __ldg(tp.dom_lo[gl] + d), dh = __ldg(tp.dom_hi[gl] + d);
+        ok = place_in(tp, tb, rb, cx, g, gg, dl, dh, int(gl), lane);
+        if (ok) top = dl;
+      }
+    }
+  }
+  uint32_t n_min = g.np;
+  uint32_t min_score = tp.L + 1;
+  if (ok) {
+    for (uint32_t i = lane; i < n_min; i += 32) min_score = min(min_score, uint32_t(cx.ent_meta[i] >> 8));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) min_score = min(min_score, __shfl_xor_sync(kFull, min_score, d));
+    // best-effort surplus beyond MinReplicas inside the domain each clique was packed into
+    for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
+      const uint32_t w = cx.clq[cr].w;
+      const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
+      if (rp > mn) take(tp, rb, cx, g, cr, cx.Hlo[cr], cx.Hhi[cr], rp - mn, lane);
+    }
+    for (uint32_t i = lane; i < g.np; i += 32) {
+      rb.ent_node[info.pod_off + i] = cx.ent_node[i];
+      rb.ent_meta[info.pod_off + i] = cx.ent_meta[i];
+    }
+  }
+  if (lane == 0) {
+    rb.spec_ok[gi] = ok ? 1 : 0;
+    rb.spec_n[gi] = uint16_t(ok ? g.np : 0);
+    rb.spec_score[gi] = uint8_t(min_score);
+    rb.spec_top[gi] = top;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conflict resolution: lowest order rank wins a node; a gang commits iff it holds all its nodes
+// ------------------------------------------------------------------------------------------------
+__global__ void k_claim(Tables tb, RoundBufs rb) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t gi = rb.active[ai];
+  if (!rb.spec_ok[gi]) return;
+  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
+  for (uint32_t i = lane; i < n; i += 32) atomicMin(rb.claim + rb.ent_node[off + i], order);
+}
+
+__global__ void k_commit(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t gi = rb.active[ai];
+  const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
+  if (!rb.spec_ok[gi]) {
+    if (lane == 0) { rb.state[gi] = GROVE_GANG_REJECTED; rb.round[gi] = r8; }
+    return;
+  }
+  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
+  bool win = true;
+  for (uint32_t i = lane; i < n; i += 32) win &= rb.claim[rb.ent_node[off + i]] == order;
+  if (!__all_sync(kFull, win)) return;  // retry next round against the new state
+  const uint32_t coff = tb.gangs[gi].clique_off;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const grove_clique_t q = tb.cliques[coff + (rb.ent_meta[off + i] & 0xFFu)];
+    uint32_t* r = reinterpret_cast<uint32_t*>(nres + rb.ent_node[off + i]);
+    // winners own their nodes exclusively this round; atomics only order this gang's own pods
+    if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
+    if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
+    atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
+  }
+  if (lane == 0) { rb.state[gi] = GROVE_GANG_ADMITTED; rb.round[gi] = r8; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs: compact the admitted gangs' entries into caller order / caller node indices
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_finalize(Topo tp, Tables tb, RoundBufs rb, const uint32_t* __restrict__ perm,
+                                                   grove_gang_status_t* status, grove_placement_t* out, uint32_t* totals) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_run, s_tot, s_adm, s_rej;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_run = 0; s_adm = 0; s_rej = 0; }
+  __syncthreads();
+  for (uint32_t base = 0; base < tb.G; base += 1024) {
+    const uint32_t g = base + tid;
+    uint32_t cnt = 0; uint8_t st = 0;
+    if (g < tb.G) { st = rb.state[g]; if (st == GROVE_GANG_ADMITTED) cnt = rb.spec_n[g]; }
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    const uint32_t na = __popc(__ballot_sync(kFull, st == GROVE_GANG_ADMITTED));
+    const uint32_t nr = __popc(__ballot_sync(kFull, st == GROVE_GANG_REJECTED || st == GROVE_GANG_BASE_REJECTED));
+    if (lane == 0) { if (na) atomicAdd(&s_adm, na); if (nr) atomicAdd(&s_rej, nr); }
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t v = s_warp[lane];
+      const uint32_t s = warp_incl_scan(v, lane);
+      s_warp[lane] = s - v;
+      if (lane == 31) s_tot = s;
+    }
+    __syncthreads();
+    const uint32_t off = s_run + s_warp[warp] + incl - cnt;
+    if (g < tb.G) {
+      grove_gang_status_t o;
+      o.state = st; o.round = rb.round[g]; o.n_pods = cnt; o.placement_off = off;
+      o.score_num = 0; o.score_den = 0; o.top_domain_lo = GROVE_NONE_U32;
+      if (st == GROVE_GANG_ADMITTED) { o.score_num = rb.spec_score[g]; o.score_den = uint8_t(tp.L + 1); o.top_domain_lo = rb.spec_top[g]; }
+      status[g] = o;
+      const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
+      for (uint32_t i = 0; i < cnt; ++i) {
+        grove_placement_t p;
+        p.clique = coff + (rb.ent_meta[po + i] & 0xFFu);
+        p.node = perm[rb.ent_node[po + i]];
+        out[off + i] = p;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_run += s_tot;
+    __syncthreads();
+  }
+  if (tid == 0) { totals[0] = s_run; totals[1] = s_adm; totals[2] = s_rej; }
+}
+
+}  // namespace grove

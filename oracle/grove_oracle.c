@@ -1,0 +1,640 @@
+/*
+ * grove_oracle.c -- CPU restatement of the gang-placement cycle.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (libgrove_place.so) never links, loads or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" at node level.  The reference tree (ai-dynamo/grove @ 08ad3b37)
+ * contains no scheduler: placement is done by KAI-Scheduler v0.14.0 (operator/go.mod:11), which is
+ * not vendored, and there is no Go toolchain in this image.  What the reference does pin -- and
+ * what tests/test_oracle_e2e_properties.py checks this file against -- is
+ *   * the input schema             scheduler/api/core/v1alpha1/podgang.go:51-131
+ *   * MinReplicas = gang guarantee, surplus best effort                      podgang.go:80-83
+ *   * Required pack constraint = all pods of the scope share one label value podgang.go:101-109
+ *   * nodes lacking the label are not candidates      docs/proposals/244-topology-aware-scheduling/README.md:65
+ *   * level index 0 is the broadest                                          ibid. :143
+ *   * scope nesting gang >= group-config >= pod-group   operator/internal/webhook/admission/pcs/validation/topologyconstraints.go:195-202
+ *   * all-or-nothing admission               operator/internal/controller/podclique/components/pod/syncflow.go:319-358
+ *   * scaled gangs gated behind their base gang                              ibid. :255-314
+ *   * the outcome properties of the live-cluster e2e suites GS1-GS12 / TAS2-TAS17
+ *     (operator/e2e/tests/gang_scheduling_test.go, topology_test.go).
+ * Everything below those (which node, which domain among feasible ones, the score value) is
+ * defined by DESIGN.md "Placement semantics"; this file is its executable form, written as plain
+ * scalar loops that derive every ordering from the score matrix itself (no piece iterator, no
+ * warp tricks) so that it shares no code or shortcut with the CUDA path.
+ *
+ * Build: make -C oracle   (gcc -O2 -fopenmp -shared)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/grove_place.h"
+
+#define VDEPTH_SHIFT 16u /* internal: valid label depth in flags bits 16..19 */
+
+typedef struct oracle_stats {
+  uint32_t rounds;
+  uint32_t gangs_admitted;
+  uint32_t gangs_rejected;
+  uint32_t pods_bound;
+  uint64_t pairs_evaluated;
+  double seconds_eval;   /* fit+score+admit per-gang evaluation, all rounds */
+  double seconds_total;
+  uint32_t non_tree_labels; /* raw label ids that appeared under more than one parent */
+  uint32_t threads;
+} oracle_stats_t;
+
+typedef struct topo {
+  uint32_t n, L;
+  uint32_t* perm; /* sorted -> caller */
+  uint32_t* inv;  /* caller -> sorted */
+  grove_node_t* nodes; /* sorted; dom[] tree-ified; flags |= vdepth << 16 */
+  uint32_t n_dom[GROVE_MAX_LEVELS];
+  uint32_t* dom_lo[GROVE_MAX_LEVELS];
+  uint32_t* dom_hi[GROVE_MAX_LEVELS];
+  uint32_t non_tree;
+} topo_t;
+
+static const grove_node_t* g_sort_nodes;
+static uint32_t g_sort_L;
+static int cmp_nodes(const void* pa, const void* pb) {
+  uint32_t a = *(const uint32_t*)pa, b = *(const uint32_t*)pb;
+  for (uint32_t l = 0; l < g_sort_L; ++l) {
+    uint32_t x = g_sort_nodes[a].dom[l], y = g_sort_nodes[b].dom[l];
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+static void topo_free(topo_t* t) {
+  free(t->perm); free(t->inv); free(t->nodes);
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) { free(t->dom_lo[l]); free(t->dom_hi[l]); }
+  memset(t, 0, sizeof(*t));
+}
+
+/* Sort nodes by label path (absent labels last), then make every level's domain id the index of the
+ * distinct PATH prefix ("tree-ify"): two nodes are in the same level-l domain iff their labels agree
+ * on levels 0..l and are all present.  KWOK's 28/20/7 arithmetic (kwok.py:64-68) is not nested; path
+ * semantics splits such a block per zone and counts it in non_tree. */
+static int topo_build(topo_t* t, const grove_node_t* in, uint32_t n, uint32_t L) {
+  memset(t, 0, sizeof(*t));
+  t->n = n; t->L = L;
+  t->perm = malloc(sizeof(uint32_t) * (n ? n : 1));
+  t->inv = malloc(sizeof(uint32_t) * (n ? n : 1));
+  t->nodes = malloc(sizeof(grove_node_t) * (n ? n : 1));
+  if (!t->perm || !t->inv || !t->nodes) return -1;
+  for (uint32_t i = 0; i < n; ++i) t->perm[i] = i;
+  g_sort_nodes = in; g_sort_L = L;
+  qsort(t->perm, n, sizeof(uint32_t), cmp_nodes);
+  for (uint32_t i = 0; i < n; ++i) { t->inv[t->perm[i]] = i; t->nodes[i] = in[t->perm[i]]; }
+  for (uint32_t l = 0; l < L; ++l) {
+    t->dom_lo[l] = malloc(sizeof(uint32_t) * (n ? n : 1));
+    t->dom_hi[l] = malloc(sizeof(uint32_t) * (n ? n : 1));
+    if (!t->dom_lo[l] || !t->dom_hi[l]) return -1;
+  }
+  /* raw label -> first parent seen, to count non-tree label sets (diagnostic only) */
+  uint32_t cnt[GROVE_MAX_LEVELS] = {0, 0, 0, 0};
+  uint32_t prev_raw[GROVE_MAX_LEVELS], prev_id[GROVE_MAX_LEVELS];
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t depth = 0;
+    int parent_same = 1; /* is the tree-ified parent the same as the previous node's? */
+    uint32_t raw[GROVE_MAX_LEVELS];
+    for (uint32_t l = 0; l < L; ++l) raw[l] = in[t->perm[i]].dom[l];
+    int alive = 1;
+    for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+      if (l >= L || !alive || raw[l] == GROVE_DOM_ABSENT) {
+        alive = 0;
+        t->nodes[i].dom[l] = GROVE_DOM_ABSENT;
+        if (l < L) { prev_raw[l] = GROVE_DOM_ABSENT; prev_id[l] = GROVE_DOM_ABSENT; }
+        parent_same = 0;
+        continue;
+      }
+      int same = (i > 0) && parent_same && prev_id[l] != GROVE_DOM_ABSENT && prev_raw[l] == raw[l];
+      uint32_t id;
+      if (same) {
+        id = prev_id[l];
+        t->dom_hi[l][id] = i + 1;
+      } else {
+        id = cnt[l]++;
+        t->dom_lo[l][id] = i;
+        t->dom_hi[l][id] = i + 1;
+      }
+      t->nodes[i].dom[l] = id;
+      prev_raw[l] = raw[l]; prev_id[l] = id;
+      parent_same = same;
+      depth = l + 1;
+    }
+    t->nodes[i].flags = (t->nodes[i].flags & 0xFFFFu) | (depth << VDEPTH_SHIFT);
+  }
+  for (uint32_t l = 0; l < L; ++l) t->n_dom[l] = cnt[l];
+  /* non-tree diagnostic: a raw id at level l>0 owned by >1 tree domain */
+  t->non_tree = 0;
+  for (uint32_t l = 1; l < L; ++l) {
+    /* collect (raw) of every domain's first node, sort, count duplicates */
+    uint32_t m = cnt[l];
+    if (m < 2) continue;
+    uint32_t* raws = malloc(sizeof(uint32_t) * m);
+    if (!raws) return -1;
+    for (uint32_t d = 0; d < m; ++d) raws[d] = in[t->perm[t->dom_lo[l][d]]].dom[l];
+    /* shell sort (keeps this file free of a second comparator) */
+    for (uint32_t gap = m / 2; gap > 0; gap /= 2)
+      for (uint32_t x = gap; x < m; ++x) {
+        uint32_t v = raws[x]; uint32_t y = x;
+        while (y >= gap && raws[y - gap] > v) { raws[y] = raws[y - gap]; y -= gap; }
+        raws[y] = v;
+      }
+    for (uint32_t x = 1; x < m; ++x) if (raws[x] == raws[x - 1]) t->non_tree++;
+    free(raws);
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct ctx {
+  topo_t T;
+  uint32_t G, Q, S;
+  const grove_gang_t* gangs;
+  const grove_clique_t* cliques;
+  const grove_scope_t* scopes;
+  uint32_t* order;   /* gang -> rank by (priority desc, index asc) */
+  uint32_t* anchor;  /* gang -> sorted node index */
+  uint32_t* pod_off; /* gang -> first slot */
+} ctx_t;
+
+typedef struct entry { uint32_t node; uint8_t clique_rel; uint8_t score; } entry_t;
+
+typedef struct spec { /* speculative result of one gang in one round */
+  int ok;
+  uint32_t n_entries;
+  uint32_t n_min_entries;
+  uint8_t min_score;
+  uint32_t top_lo;
+  entry_t e[GROVE_MAX_GANG_PODS];
+} spec_t;
+
+static uint32_t fmix32(uint32_t x) {
+  x = x * 0x9E3779B1u + 0x7F4A7C15u;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+
+static inline uint32_t node_vdepth(const grove_node_t* nd) { return (nd->flags >> VDEPTH_SHIFT) & 0xFu; }
+static inline uint32_t node_class(const grove_node_t* nd) { return (nd->flags & GROVE_NODE_CLASS_MASK) >> GROVE_NODE_CLASS_SHIFT; }
+
+/* deepest Required level that binds clique q (its own, its scope's, its gang's) + 1; 0 if none.
+ * A node must carry labels down to that depth to be a candidate (GREP-244 README.md:65). */
+static uint32_t need_depth(const grove_gang_t* g, const grove_scope_t* s, const grove_clique_t* q) {
+  uint32_t d = 0;
+  if (g->level != GROVE_LEVEL_NONE && g->level + 1u > d) d = g->level + 1u;
+  if (s->level != GROVE_LEVEL_NONE && s->level + 1u > d) d = s->level + 1u;
+  if (q->level != GROVE_LEVEL_NONE && q->level + 1u > d) d = q->level + 1u;
+  return d;
+}
+
+static int static_ok(const grove_node_t* nd, const grove_clique_t* q, uint32_t nd_need) {
+  if (!(nd->flags & GROVE_NODE_SCHEDULABLE)) return 0;
+  if (!((q->class_mask >> node_class(nd)) & 1u)) return 0;
+  if (node_vdepth(nd) < nd_need) return 0;
+  return 1;
+}
+
+/* K1 semantics: can node nd host at least one pod of q right now? */
+static int fit(const grove_node_t* nd, const grove_clique_t* q, uint32_t nd_need) {
+  return static_ok(nd, q, nd_need) && nd->free_cpu_milli >= q->req_cpu_milli &&
+         nd->free_mem_mib >= q->req_mem_mib && nd->free_gpu >= q->req_gpu && nd->free_pods >= 1;
+}
+
+/* K2 semantics: number of levels at which n and the anchor share a (tree-ified) domain */
+static uint32_t closeness(const topo_t* T, uint32_t n, uint32_t a) {
+  uint32_t c = 0;
+  for (uint32_t l = 0; l < T->L; ++l) {
+    uint32_t x = T->nodes[n].dom[l];
+    if (x != GROVE_DOM_ABSENT && x == T->nodes[a].dom[l]) c++;
+  }
+  return c;
+}
+
+typedef struct geval {
+  const ctx_t* C;
+  uint32_t g;
+  uint32_t a;
+  uint8_t* Trow[GROVE_MAX_GANG_CLIQUES]; /* score rows of this gang's cliques, round-start state */
+  uint32_t ndepth[GROVE_MAX_GANG_CLIQUES];
+  entry_t st[GROVE_MAX_GANG_PODS];
+  uint32_t np;
+  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
+} geval_t;
+
+/* how many more pods of clique cr fit on node n given the pods this gang already put there */
+static uint32_t cap_now(const geval_t* E, uint32_t cr, uint32_t n) {
+  const ctx_t* C = E->C;
+  const grove_gang_t* g = &C->gangs[E->g];
+  const grove_clique_t* q = &C->cliques[g->clique_off + cr];
+  const grove_node_t* nd = &C->T.nodes[n];
+  if (!static_ok(nd, q, E->ndepth[cr])) return 0;
+  uint64_t ucpu = 0, umem = 0, ugpu = 0, upods = 0;
+  for (uint32_t i = 0; i < E->np; ++i)
+    if (E->st[i].node == n) {
+      const grove_clique_t* o = &C->cliques[g->clique_off + E->st[i].clique_rel];
+      ucpu += o->req_cpu_milli; umem += o->req_mem_mib; ugpu += o->req_gpu; upods += 1;
+    }
+  if (nd->free_cpu_milli < ucpu || nd->free_mem_mib < umem || nd->free_gpu < ugpu || nd->free_pods < upods) return 0;
+  uint64_t c = nd->free_pods - upods;
+  if (q->req_cpu_milli) { uint64_t k = (nd->free_cpu_milli - ucpu) / q->req_cpu_milli; if (k < c) c = k; }
+  if (q->req_mem_mib) { uint64_t k = (nd->free_mem_mib - umem) / q->req_mem_mib; if (k < c) c = k; }
+  if (q->req_gpu) { uint64_t k = (nd->free_gpu - ugpu) / q->req_gpu; if (k < c) c = k; }
+  return (uint32_t)c;
+}
+
+/* Put up to `want` pods of clique cr on the fit nodes of [lo,hi), visiting them in descending score,
+ * ties by ascending rotated index (n - anchor) mod N.  Returns pods placed. */
+static uint32_t take(geval_t* E, uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+  const topo_t* T = &E->C->T;
+  uint32_t placed = 0;
+  if (want == 0 || hi <= lo) return 0;
+  uint32_t len = hi - lo;
+  uint32_t start = (E->a >= lo && E->a < hi) ? E->a - lo : 0; /* ascending rot == ascending from the anchor, wrapping */
+  for (uint32_t s = T->L + 1; s >= 1 && placed < want; --s) {
+    for (uint32_t k = 0; k < len && placed < want; ++k) {
+      uint32_t n = lo + (start + k) % len;
+      if (E->Trow[cr][n] != s) continue;
+      uint32_t c = cap_now(E, cr, n);
+      uint32_t t = c < (want - placed) ? c : (want - placed);
+      for (uint32_t j = 0; j < t; ++j) {
+        E->st[E->np].node = n; E->st[E->np].clique_rel = (uint8_t)cr; E->st[E->np].score = (uint8_t)s;
+        E->np++;
+      }
+      placed += t;
+    }
+  }
+  return placed;
+}
+
+static int fill_min(geval_t* E, uint32_t cr, uint32_t lo, uint32_t hi) {
+  const grove_gang_t* g = &E->C->gangs[E->g];
+  uint32_t m = E->C->cliques[g->clique_off + cr].min_replicas;
+  uint32_t mark = E->np;
+  if (take(E, cr, lo, hi, m) < m) { E->np = mark; return 0; }
+  E->Hlo[cr] = lo; E->Hhi[cr] = hi;
+  return 1;
+}
+
+typedef struct cand { uint32_t sc; uint32_t rot; uint32_t lo, hi; } cand_t;
+static int cmp_cand(const void* pa, const void* pb) {
+  const cand_t* a = pa; const cand_t* b = pb;
+  if (a->sc != b->sc) return a->sc > b->sc ? -1 : 1;
+  if (a->rot != b->rot) return a->rot < b->rot ? -1 : 1;
+  return 0;
+}
+
+/* Level-l domains inside [lo,hi), ordered by descending score of the domain (closeness of its nodes
+ * to the anchor, which is uniform outside the anchor's own level-l domain and capped at l+1 inside
+ * it), ties by ascending rotated index of the domain's first node. */
+static cand_t* subdomains(const geval_t* E, uint32_t l, uint32_t lo, uint32_t hi, uint32_t* n_out) {
+  const topo_t* T = &E->C->T;
+  uint32_t cnt = 0;
+  for (uint32_t n = lo; n < hi; ++n) {
+    uint32_t d = T->nodes[n].dom[l];
+    if (d != GROVE_DOM_ABSENT && T->dom_lo[l][d] == n) cnt++;
+  }
+  cand_t* v = malloc(sizeof(cand_t) * (cnt ? cnt : 1));
+  uint32_t k = 0;
+  for (uint32_t n = lo; n < hi; ++n) {
+    uint32_t d = T->nodes[n].dom[l];
+    if (d == GROVE_DOM_ABSENT || T->dom_lo[l][d] != n) continue;
+    uint32_t c = closeness(T, n, E->a);
+    v[k].sc = c < l + 1 ? c : l + 1;
+    v[k].rot = (n + T->n - E->a) % T->n;
+    v[k].lo = n; v[k].hi = T->dom_hi[l][d];
+    k++;
+  }
+  qsort(v, cnt, sizeof(cand_t), cmp_cand);
+  *n_out = cnt;
+  return v;
+}
+
+/* cliques of one scope inside range E_=[lo,hi) whose level is `lvl` (-1 = ROOT) */
+static int place_scope(geval_t* E, const grove_scope_t* s, uint32_t lo, uint32_t hi, int lvl) {
+  const grove_gang_t* g = &E->C->gangs[E->g];
+  uint32_t mark = E->np;
+  for (uint32_t i = 0; i < s->n_cliques; ++i) {
+    uint32_t cr = s->first_clique + i;
+    const grove_clique_t* q = &E->C->cliques[g->clique_off + cr];
+    int ok = 0;
+    if (q->level != GROVE_LEVEL_NONE && (int)q->level > lvl) {
+      uint32_t nc; cand_t* v = subdomains(E, q->level, lo, hi, &nc);
+      for (uint32_t k = 0; k < nc && !ok; ++k) ok = fill_min(E, cr, v[k].lo, v[k].hi);
+      free(v);
+    } else {
+      ok = fill_min(E, cr, lo, hi);
+    }
+    if (!ok) { E->np = mark; return 0; }
+  }
+  return 1;
+}
+
+static int place_in(geval_t* E, uint32_t lo, uint32_t hi, int lvl) {
+  const ctx_t* C = E->C;
+  const grove_gang_t* g = &C->gangs[E->g];
+  E->np = 0;
+  for (uint32_t si = 0; si < g->n_scopes; ++si) {
+    const grove_scope_t* s = &C->scopes[g->scope_off + si];
+    int ok = 0;
+    if (s->level != GROVE_LEVEL_NONE && (int)s->level > lvl) {
+      uint32_t nc; cand_t* v = subdomains(E, s->level, lo, hi, &nc);
+      for (uint32_t k = 0; k < nc && !ok; ++k) ok = place_scope(E, s, v[k].lo, v[k].hi, (int)s->level);
+      free(v);
+    } else {
+      ok = place_scope(E, s, lo, hi, lvl);
+    }
+    if (!ok) { E->np = 0; return 0; }
+  }
+  return 1;
+}
+
+/* one gang against the round-start state: first feasible gang-level domain in score order */
+static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, spec_t* out) {
+  geval_t* E = malloc(sizeof(geval_t));
+  memset(E, 0, sizeof(*E));
+  const grove_gang_t* g = &C->gangs[gi];
+  E->C = C; E->g = gi; E->a = C->anchor[gi];
+  for (uint32_t si = 0; si < g->n_scopes; ++si) {
+    const grove_scope_t* s = &C->scopes[g->scope_off + si];
+    for (uint32_t i = 0; i < s->n_cliques; ++i) {
+      uint32_t cr = s->first_clique + i;
+      E->ndepth[cr] = need_depth(g, s, &C->cliques[g->clique_off + cr]);
+    }
+  }
+  for (uint32_t cr = 0; cr < g->n_cliques; ++cr) E->Trow[cr] = Trow[cr];
+  int ok = 0; uint32_t top_lo = GROVE_NONE_U32;
+  if (g->level == GROVE_LEVEL_NONE) {
+    ok = place_in(E, 0, C->T.n, -1);
+    if (ok) top_lo = 0;
+  } else {
+    uint32_t nc; cand_t* v = subdomains(E, g->level, 0, C->T.n, &nc);
+    for (uint32_t k = 0; k < nc && !ok; ++k) {
+      ok = place_in(E, v[k].lo, v[k].hi, (int)g->level);
+      if (ok) top_lo = v[k].lo;
+    }
+    free(v);
+  }
+  out->ok = ok; out->n_entries = 0; out->n_min_entries = 0; out->min_score = (uint8_t)(C->T.L + 1); out->top_lo = top_lo;
+  if (ok) {
+    out->n_min_entries = E->np;
+    for (uint32_t i = 0; i < E->np; ++i) if (E->st[i].score < out->min_score) out->min_score = E->st[i].score;
+    /* best-effort surplus beyond MinReplicas, inside the domain each clique was packed into (podgang.go:80-83) */
+    for (uint32_t cr = 0; cr < g->n_cliques; ++cr) {
+      const grove_clique_t* q = &C->cliques[g->clique_off + cr];
+      uint32_t extra = q->replicas > q->min_replicas ? (uint32_t)(q->replicas - q->min_replicas) : 0;
+      if (extra) {
+        take(E, cr, E->Hlo[cr], E->Hhi[cr], extra);
+      }
+    }
+    out->n_entries = E->np;
+    memcpy(out->e, E->st, sizeof(entry_t) * E->np);
+  }
+  free(E);
+}
+
+static double now_s(void) {
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return 0.0;
+#endif
+}
+
+typedef struct ord { int32_t pr; uint32_t g; } ord_t;
+static int cmp_ord(const void* pa, const void* pb) {
+  const ord_t* a = pa; const ord_t* b = pb;
+  if (a->pr != b->pr) return a->pr > b->pr ? -1 : 1;
+  return a->g < b->g ? -1 : (a->g > b->g ? 1 : 0);
+}
+
+int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                        const grove_scope_t* scopes, uint32_t S, uint32_t L, uint32_t n_nodes) {
+  if (L < 1 || L > GROVE_MAX_LEVELS) return GROVE_ERR_INVALID_ARG;
+  for (uint32_t gi = 0; gi < G; ++gi) {
+    const grove_gang_t* g = &gangs[gi];
+    if (g->n_cliques == 0 || g->n_cliques > GROVE_MAX_GANG_CLIQUES) return GROVE_ERR_LIMIT;
+    if (g->n_scopes == 0 || g->n_scopes > GROVE_MAX_GANG_SCOPES) return GROVE_ERR_LIMIT;
+    if ((uint64_t)g->clique_off + g->n_cliques > Q || (uint64_t)g->scope_off + g->n_scopes > S) return GROVE_ERR_INVALID_ARG;
+    if (g->level != GROVE_LEVEL_NONE && g->level >= L) return GROVE_ERR_INVALID_ARG;
+    if (g->preferred != GROVE_LEVEL_NONE) return GROVE_ERR_INVALID_ARG;
+    if (g->anchor_node != GROVE_NONE_U32 && g->anchor_node >= n_nodes) return GROVE_ERR_INVALID_ARG;
+    if (g->base_gang != GROVE_NONE_U32 && (g->base_gang >= G || g->base_gang == gi)) return GROVE_ERR_INVALID_ARG;
+    uint32_t pods = 0, next = 0;
+    for (uint32_t si = 0; si < g->n_scopes; ++si) {
+      const grove_scope_t* s = &scopes[g->scope_off + si];
+      if (s->first_clique != next || s->n_cliques == 0) return GROVE_ERR_INVALID_ARG; /* scopes tile the gang's cliques in order */
+      if (s->level != GROVE_LEVEL_NONE && s->level >= L) return GROVE_ERR_INVALID_ARG;
+      for (uint32_t i = 0; i < s->n_cliques; ++i) {
+        if (next + i >= g->n_cliques) return GROVE_ERR_INVALID_ARG;
+        const grove_clique_t* q = &cliques[g->clique_off + next + i];
+        if (q->scope != si) return GROVE_ERR_INVALID_ARG;
+        if (q->level != GROVE_LEVEL_NONE && q->level >= L) return GROVE_ERR_INVALID_ARG;
+        if (q->replicas < q->min_replicas) return GROVE_ERR_INVALID_ARG;
+        pods += q->replicas;
+      }
+      next += s->n_cliques;
+    }
+    if (next != g->n_cliques) return GROVE_ERR_INVALID_ARG;
+    if (pods > GROVE_MAX_GANG_PODS) return GROVE_ERR_LIMIT;
+  }
+  return GROVE_OK;
+}
+
+/*
+ * One scheduling cycle.  Optimistic rounds (DESIGN.md "Cycle"):
+ *   round: every active gang is evaluated against the round-start node state (fit -> score ->
+ *   first feasible domain); each successful gang claims its nodes with its order rank (min wins);
+ *   a gang that holds every node it claimed commits, the others retry next round; a gang with no
+ *   feasible domain is rejected for the cycle.
+ * Outputs are in caller node indices.  out_fit/out_score (nullable) receive the round-1 rows of all
+ * cliques in SORTED node order (row stride words = ceil(n/32) and n bytes).
+ */
+int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
+                         const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, int32_t threads,
+                         grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
+                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm,
+                         uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
+  int32_t rc = oracle_validate(gangs, G, cliques, Q, scopes, S, L, n);
+  if (rc != GROVE_OK) return rc;
+  if (n == 0 || n > GROVE_MAX_NODES) return GROVE_ERR_INVALID_ARG;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+  double t0 = now_s(), t_eval = 0;
+  ctx_t C; memset(&C, 0, sizeof(C));
+  if (topo_build(&C.T, nodes_in, n, L)) return GROVE_ERR_OOM;
+  C.G = G; C.Q = Q; C.S = S; C.gangs = gangs; C.cliques = cliques; C.scopes = scopes;
+  C.order = malloc(sizeof(uint32_t) * (G ? G : 1));
+  C.anchor = malloc(sizeof(uint32_t) * (G ? G : 1));
+  C.pod_off = malloc(sizeof(uint32_t) * (G + 1));
+  ord_t* ov = malloc(sizeof(ord_t) * (G ? G : 1));
+  for (uint32_t g = 0; g < G; ++g) { ov[g].pr = gangs[g].priority; ov[g].g = g; }
+  qsort(ov, G, sizeof(ord_t), cmp_ord);
+  for (uint32_t r = 0; r < G; ++r) C.order[ov[r].g] = r;
+  free(ov);
+  for (uint32_t g = 0; g < G; ++g)
+    C.anchor[g] = gangs[g].anchor_node != GROVE_NONE_U32 ? C.T.inv[gangs[g].anchor_node] : fmix32(g) % n;
+
+  uint8_t* state = calloc(G ? G : 1, 1);
+  uint8_t* rnd = calloc(G ? G : 1, 1);
+  spec_t* specs = calloc(G ? G : 1, sizeof(spec_t));
+  uint32_t* claim = malloc(sizeof(uint32_t) * n);
+  uint32_t words = (n + 31) / 32;
+  uint64_t pairs = 0;
+  uint32_t round = 0, unresolved = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    if (gangs[g].flags & GROVE_GANG_GATED) state[g] = GROVE_GANG_GATED_SKIP; else unresolved++;
+  }
+  uint32_t* active = malloc(sizeof(uint32_t) * (G ? G : 1));
+  while (unresolved > 0 && (max_rounds == 0 || round < max_rounds)) {
+    round++;
+    /* scaled gangs become active once their base gang is admitted (pod/syncflow.go:319-358) */
+    uint32_t na = 0;
+    int changed = 1;
+    while (changed) { /* propagate base rejections transitively */
+      changed = 0;
+      for (uint32_t g = 0; g < G; ++g) {
+        if (state[g] != GROVE_GANG_PENDING || gangs[g].base_gang == GROVE_NONE_U32) continue;
+        uint8_t bs = state[gangs[g].base_gang];
+        if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
+          state[g] = GROVE_GANG_BASE_REJECTED; rnd[g] = (uint8_t)(round > 255 ? 255 : round); unresolved--; changed = 1;
+        }
+      }
+    }
+    for (uint32_t g = 0; g < G; ++g) {
+      if (state[g] != GROVE_GANG_PENDING) continue;
+      if (gangs[g].base_gang != GROVE_NONE_U32 && state[gangs[g].base_gang] != GROVE_GANG_ADMITTED) continue;
+      active[na++] = g;
+    }
+    if (na == 0) { /* dependency cycle: nothing can ever become active */
+      for (uint32_t g = 0; g < G; ++g)
+        if (state[g] == GROVE_GANG_PENDING) { state[g] = GROVE_GANG_BASE_REJECTED; rnd[g] = (uint8_t)(round > 255 ? 255 : round); unresolved--; }
+      break;
+    }
+    double te0 = now_s();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : pairs)
+    for (uint32_t ai = 0; ai < na; ++ai) {
+      uint32_t gi = active[ai];
+      const grove_gang_t* g = &gangs[gi];
+      uint8_t* Trow[GROVE_MAX_GANG_CLIQUES];
+      uint32_t* Frow = malloc(sizeof(uint32_t) * words);
+      for (uint32_t si = 0; si < g->n_scopes; ++si) {
+        const grove_scope_t* s = &scopes[g->scope_off + si];
+        for (uint32_t i = 0; i < s->n_cliques; ++i) {
+          uint32_t cr = s->first_clique + i;
+          const grove_clique_t* q = &cliques[g->clique_off + cr];
+          uint32_t ndp = need_depth(g, s, q);
+          Trow[cr] = malloc(n);
+          memset(Frow, 0, sizeof(uint32_t) * words);
+          /* K1: fit bitmap row */
+          for (uint32_t nn = 0; nn < n; ++nn)
+            if (fit(&C.T.nodes[nn], q, ndp)) Frow[nn >> 5] |= 1u << (nn & 31);
+          /* K2: score row = fit ? closeness + 1 : 0 */
+          for (uint32_t nn = 0; nn < n; ++nn)
+            Trow[cr][nn] = ((Frow[nn >> 5] >> (nn & 31)) & 1u) ? (uint8_t)(closeness(&C.T, nn, C.anchor[gi]) + 1) : 0;
+          pairs += n;
+          if (round == 1 && out_fit) memcpy(out_fit + (size_t)(g->clique_off + cr) * words, Frow, sizeof(uint32_t) * words);
+          if (round == 1 && out_score) memcpy(out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
+        }
+      }
+      eval_gang(&C, gi, Trow, &specs[gi]);
+      for (uint32_t cr = 0; cr < g->n_cliques; ++cr) free(Trow[cr]);
+      free(Frow);
+    }
+    t_eval += now_s() - te0;
+    /* claims: lowest order rank wins each node */
+    for (uint32_t i = 0; i < n; ++i) claim[i] = GROVE_NONE_U32;
+    for (uint32_t ai = 0; ai < na; ++ai) {
+      uint32_t gi = active[ai];
+      if (!specs[gi].ok) continue;
+      for (uint32_t i = 0; i < specs[gi].n_entries; ++i) {
+        uint32_t nd = specs[gi].e[i].node;
+        if (C.order[gi] < claim[nd]) claim[nd] = C.order[gi];
+      }
+    }
+    for (uint32_t ai = 0; ai < na; ++ai) {
+      uint32_t gi = active[ai];
+      uint8_t r8 = (uint8_t)(round > 255 ? 255 : round);
+      if (!specs[gi].ok) { state[gi] = GROVE_GANG_REJECTED; rnd[gi] = r8; unresolved--; continue; }
+      int win = 1;
+      for (uint32_t i = 0; i < specs[gi].n_entries && win; ++i) win = claim[specs[gi].e[i].node] == C.order[gi];
+      if (!win) continue;
+      for (uint32_t i = 0; i < specs[gi].n_entries; ++i) {
+        grove_node_t* nd = &C.T.nodes[specs[gi].e[i].node];
+        const grove_clique_t* q = &cliques[gangs[gi].clique_off + specs[gi].e[i].clique_rel];
+        nd->free_cpu_milli -= q->req_cpu_milli; nd->free_mem_mib -= q->req_mem_mib;
+        nd->free_gpu -= q->req_gpu; nd->free_pods -= 1;
+      }
+      state[gi] = GROVE_GANG_ADMITTED; rnd[gi] = r8; unresolved--;
+    }
+  }
+  /* outputs */
+  uint32_t np = 0, adm = 0, rej = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    grove_gang_status_t st; memset(&st, 0, sizeof(st));
+    st.state = state[g]; st.round = rnd[g]; st.top_domain_lo = GROVE_NONE_U32; st.placement_off = np;
+    if (state[g] == GROVE_GANG_ADMITTED) {
+      adm++;
+      st.score_num = specs[g].min_score; st.score_den = (uint8_t)(L + 1);
+      st.n_pods = specs[g].n_entries; st.top_domain_lo = specs[g].top_lo;
+      for (uint32_t i = 0; i < specs[g].n_entries; ++i) {
+        if (out_pl && np < cap_pl) { out_pl[np].clique = gangs[g].clique_off + specs[g].e[i].clique_rel; out_pl[np].node = C.T.perm[specs[g].e[i].node]; }
+        np++;
+      }
+    } else if (state[g] == GROVE_GANG_REJECTED || state[g] == GROVE_GANG_BASE_REJECTED) rej++;
+    if (out_status) out_status[g] = st;
+  }
+  if (n_pl) *n_pl = np;
+  if (out_nodes)
+    for (uint32_t i = 0; i < n; ++i) {
+      grove_node_t nd = nodes_in[C.T.perm[i]];
+      nd.free_cpu_milli = C.T.nodes[i].free_cpu_milli; nd.free_mem_mib = C.T.nodes[i].free_mem_mib;
+      nd.free_gpu = C.T.nodes[i].free_gpu; nd.free_pods = C.T.nodes[i].free_pods;
+      out_nodes[C.T.perm[i]] = nd;
+    }
+  if (out_perm) memcpy(out_perm, C.T.perm, sizeof(uint32_t) * n);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rounds = round; stats->gangs_admitted = adm; stats->gangs_rejected = rej; stats->pods_bound = np;
+    stats->pairs_evaluated = pairs; stats->seconds_eval = t_eval; stats->seconds_total = now_s() - t0;
+    stats->non_tree_labels = C.T.non_tree;
+#ifdef _OPENMP
+    stats->threads = (uint32_t)omp_get_max_threads();
+#else
+    stats->threads = 1;
+#endif
+  }
+  int32_t ret = (out_pl && np > cap_pl) ? GROVE_ERR_LIMIT : GROVE_OK;
+  free(active); free(claim); free(specs); free(rnd); free(state);
+  free(C.order); free(C.anchor); free(C.pod_off);
+  topo_free(&C.T);
+  return ret;
+}
+
+/* topology preprocessing alone, for tests of the engine's host-side sort: perm + tree-ified dom ids */
+int32_t oracle_topology(const grove_node_t* nodes_in, uint32_t n, uint32_t L, uint32_t* out_perm,
+                        uint32_t* out_dom /* n * GROVE_MAX_LEVELS, sorted order */, uint32_t* out_n_dom /* L */,
+                        uint32_t* out_non_tree) {
+  topo_t T;
+  if (L < 1 || L > GROVE_MAX_LEVELS || n == 0) return GROVE_ERR_INVALID_ARG;
+  if (topo_build(&T, nodes_in, n, L)) return GROVE_ERR_OOM;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (out_perm) out_perm[i] = T.perm[i];
+    if (out_dom) for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) out_dom[i * GROVE_MAX_LEVELS + l] = T.nodes[i].dom[l];
+  }
+  if (out_n_dom) for (uint32_t l = 0; l < L; ++l) out_n_dom[l] = T.n_dom[l];
+  if (out_non_tree) *out_non_tree = T.non_tree;
+  topo_free(&T);
+  return GROVE_OK;
+}
+
+uint32_t oracle_abi_version(void) { return GROVE_ABI_VERSION; }
