@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- PodGang placements/sec on the 50k-node / 10k-gang synthetic snapshot (BASELINE.json).
+
+A "step" is one scheduling cycle: every pending PodGang of the snapshot goes through
+fit -> score -> admit -> commit (optimistic rounds) until it is admitted or rejected.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
+
+`value`       whole-job admitted gangs / second, node table already resident in HBM (per step:
+              device->device reset of the node table, then the cycle).
+`e2e`         the same metric through the C ABI with HOST buffers every step: grove_load_nodes +
+              grove_submit_gangs + grove_run_cycle + grove_get_placements + grove_get_gang_status.
+`roofline`    the dominant kernel (K2 score matrix): algorithmic bytes / CUDA-event time, against the
+              measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline`/--impl reference   the CPU oracle (oracle/, a C restatement: the reference tree holds no
+              scheduler and there is no Go toolchain) on this box's host cores, same snapshot.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from grove_b200 import synth, tables as T  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(name: str):
+    cfg = synth.CONFIGS[name]()
+    g, c, s = cfg["tables"]
+    return cfg["nodes"], cfg["n_levels"], g, c, s
+
+
+def workload_desc(name, nodes, g, c, dev_note):
+    return {"workload": f"{name}: {len(nodes)} nodes / {len(g)} PodGangs / {len(c)} PodCliques, "
+                        + {"C4": "4-level tree zone/block/rack/host, hierarchical PCSG gangs (base + scaled)",
+                           "C3": "3-level tree, prefill+decode cliques", "C2": "flat", "C1": "simple1.yaml"}[name],
+            "nodes": int(len(nodes)), "gangs": int(len(g)), "cliques": int(len(c)),
+            "pairs_per_full_pass": int(len(nodes)) * int(len(c)),
+            "l2": dev_note}
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle, all host cores, full workload per step."""
+    from oracle import oracle_py as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nodes, L, g, c, s = make_workload(args.config)
+    cores = os.cpu_count() or 1
+    O.build()
+    for _ in range(args.warmup):
+        O.run_cycle(nodes, L, g, c, s, threads=cores)
+    t0 = time.perf_counter()
+    adm = 0
+    for _ in range(args.steps):
+        r = O.run_cycle(nodes, L, g, c, s, threads=cores)
+        adm = r["stats"]["gangs_admitted"]
+    dt = (time.perf_counter() - t0) / args.steps
+    val = adm / dt
+    line = {
+        "impl": "reference", "metric": "podgang_placements_per_sec", "value": val, "unit": "gangs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_desc(args.config, nodes, g, c, "n/a (CPU)"),
+        "cpu_baseline": {"value": val, "unit": "gangs/s", "cores": cores, "kind": "port",
+                         "sample": f"full {args.config} cycle per step, OpenMP over gangs; C restatement (no scheduler in the "
+                                   "reference tree, Go toolchain absent)"},
+        "e2e": {"value": val, "unit": "gangs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    from grove_b200 import build
+    from grove_b200.engine import PlacementEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU oracle)")
+    build.build()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    nodes, L, g, c, s = make_workload(args.config)
+    eng = PlacementEngine(L, device=local, rank=rank, world=world)
+    eng.load_nodes(nodes)
+    eng.submit_gangs(g, c, s)
+    d_nodes = torch.from_numpy(nodes.view(np.uint8).reshape(-1)).cuda()  # pristine snapshot, resident in HBM
+    h2d = nodes.nbytes + g.nbytes + c.nbytes + s.nbytes
+
+    if world > 1:
+        from grove_b200.sharded import run_sharded_cycle
+        def step_dev():
+            eng.load_nodes_device(d_nodes.data_ptr(), len(nodes))
+            return run_sharded_cycle(eng, dist)
+        def step_e2e():
+            eng.load_nodes(nodes); eng.submit_gangs(g, c, s)
+            st = run_sharded_cycle(eng, dist)
+            return st, eng.placements(), eng.gang_status()
+    else:
+        def step_dev():
+            eng.load_nodes_device(d_nodes.data_ptr(), len(nodes))
+            return eng.run_cycle()
+        def step_e2e():
+            eng.load_nodes(nodes); eng.submit_gangs(g, c, s)
+            st = eng.run_cycle()
+            return st, eng.placements(), eng.gang_status()
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync()
+    t0 = time.perf_counter()
+    acc = {k: 0.0 for k in ("ms_fit", "ms_score", "ms_admit", "ms_commit", "ms_total")}
+    launches = 0
+    for _ in range(args.steps):
+        st = step_dev()
+        for k in acc:
+            acc[k] += st[k]
+        launches += st["kernel_launches"] + 1  # + k_gather of the node-table reset
+    sync()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e through the C ABI with host buffers
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    sync()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        st_e, pl, gs = step_e2e()
+    sync()
+    dt_e = time.perf_counter() - t1
+    if dist is not None:
+        tt = torch.tensor([dt, dt_e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e = tt.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    adm = st["gangs_admitted"]
+    resolved = st["gangs_admitted"] + st["gangs_rejected"]
+    ms_step = dt / args.steps * 1e3
+    ms_e2e = dt_e / args.steps * 1e3
+    peak, peak_src = peaks()
+    # K2 (score matrix): per (clique,node) pair it reads 1 fit bit and writes 1 score byte
+    pairs = st["pairs_evaluated"]
+    k2_bytes = pairs * (1.0 + 1.0 / 8.0)
+    k2_ms = acc["ms_score"] / args.steps
+    achieved = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    d2h = pl.nbytes + gs.nbytes
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_py as O
+        cores = os.cpu_count() or 1
+        O.build()
+        tc = time.perf_counter()
+        r = O.run_cycle(nodes, L, g, c, s, threads=cores)
+        tcpu = time.perf_counter() - tc
+        same = bool(np.array_equal(r["placements"], pl) and np.array_equal(r["status"]["state"], gs["state"]))
+        cpu = {"value": r["stats"]["gangs_admitted"] / tcpu, "unit": "gangs/s", "cores": cores, "kind": "port",
+               "sample": f"one full {args.config} cycle ({r['stats']['pairs_evaluated']} pairs, {r['stats']['rounds']} rounds, {tcpu:.2f} s); "
+                         "C restatement timed on this box (reference tree has no scheduler; Go toolchain absent)",
+               "placements_identical_to_gpu": same}
+    line = {
+        "metric": "podgang_placements_per_sec", "value": adm / (ms_step * 1e-3), "unit": "gangs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {**workload_desc(args.config, nodes, g, c, "fit+score matrices (%.2f GB) exceed the 126 MB L2; no flush needed"
+                                   % ((len(c) * eng_npad(len(nodes)) * 1.125) / 1e9)),
+                   "gangs_resolved_per_sec": resolved / (ms_step * 1e-3), "rounds": st["rounds"],
+                   "admitted": adm, "rejected": st["gangs_rejected"], "pods_bound": st["pods_bound"],
+                   "parallelism": "gang rows sharded over %d GPU(s)" % world},
+        "clocks": clocks,
+        "e2e": {"value": adm / (ms_e2e * 1e-3), "unit": "gangs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_score (K2 topology-distance score matrix)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": k2_bytes, "ms_per_step": k2_ms},
+        "kernel_ms_per_step": {k: v / args.steps for k, v in acc.items()},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def eng_npad(n):
+    return (n + 1023) // 1024 * 1024
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C4", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
