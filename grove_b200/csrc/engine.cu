@@ -498,7 +498,7 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
     k_score<<<blocks, 256, 0, e->stream>>>(tp, tb, rb, nr);
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
-  k_admit<<<(na + kAdmitWarps - 1) / kAdmitWarps, kAdmitWarps * 32, 0, e->stream>>>(tp, tb, rb);
+  k_admit<<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
   CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0xFF, sizeof(uint32_t) * e->N, e->stream));
   k_claim<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb);

@@ -294,19 +294,32 @@ __global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: gang admission.  One warp per active gang.
+// K3: gang admission.  One CTA (4 warps) per active gang.
+//
+// A gang with a Required level tries the domains of that level in score order and takes the first
+// one in which every PodClique's MinReplicas can be packed (all-or-nothing).  Candidate domains are
+// independent of each other, so they are evaluated in parallel: one LANE per candidate domain runs
+// the greedy packing as scalar code (ScalarEv), the warp ballots the outcomes and the first feasible
+// candidate in order wins.  Step 0 uses warp 0 only (32 candidates, the common case succeeds on the
+// first); further steps use all 128 lanes.  A gang without a gang-level constraint has a single
+// candidate (the whole cluster): warp 0 packs it cooperatively (CoopEv), lanes = nodes of a fit
+// word, prefix sums over the per-node capacities.
+// Both evaluators implement the same DESIGN.md semantics and are checked against the oracle.
 // ------------------------------------------------------------------------------------------------
-struct WarpCtx {
+struct GangRegs {   // per-gang constants
+  uint32_t a, L, n;
+  uint32_t anc_lo[GROVE_MAX_LEVELS], anc_hi[GROVE_MAX_LEVELS];
+  uint32_t clique_off;
+};
+
+struct GangShared {
+  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
+  grove_scope_t scopes[GROVE_MAX_GANG_SCOPES];
+  // cooperative evaluator state (warp 0)
   uint32_t ent_node[GROVE_MAX_GANG_PODS];
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel | score << 8
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
-  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
-};
-
-struct GangRegs {   // warp-uniform registers
-  uint32_t a, L, n, np;
-  uint32_t anc_lo[GROVE_MAX_LEVELS], anc_hi[GROVE_MAX_LEVELS];
-  uint32_t clique_off;
+  uint32_t best;                           // lowest successful candidate index of the current step
 };
 
 // Ordered pieces of [lo,hi): descending score, ties by ascending rotated index (n - anchor) mod N.
@@ -332,17 +345,7 @@ __device__ __forceinline__ int make_pieces(const GangRegs& g, uint32_t lo, uint3
   return k;
 }
 
-// pods of clique cr that still fit on node n, given what this gang has already put there
-__device__ __forceinline__ uint32_t cap_now(const Topo& tp, const WarpCtx& cx, uint32_t np, uint32_t cr, uint32_t n) {
-  const uint4 r = __ldg(tp.nres + n);
-  uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-  for (uint32_t i = 0; i < np; ++i) {
-    if (cx.ent_node[i] == n) {
-      const uint4 o = cx.clq[cx.ent_meta[i] & 0xFFu];
-      cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
-    }
-  }
-  const uint4 q = cx.clq[cr];
+__device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_t gpu, uint32_t pods, const uint4& q) {
   uint32_t c = pods;
   if (q.x) c = min(c, cpu / q.x);
   if (q.y) c = min(c, mem / q.y);
@@ -350,216 +353,364 @@ __device__ __forceinline__ uint32_t cap_now(const Topo& tp, const WarpCtx& cx, u
   return c;
 }
 
-// Put up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed.
-__device__ uint32_t take(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
-                         uint32_t lo, uint32_t hi, uint32_t want, uint32_t lane) {
-  if (want == 0 || hi <= lo) return 0;
-  const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
-  const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int np_ = make_pieces(g, lo, hi, g.L, plo, phi);
-  uint32_t placed = 0;
-  for (int p = 0; p < np_ && placed < want; ++p) {
-    const uint32_t a = plo[p], b = phi[p];
-    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-    for (uint32_t wb = w0; wb <= w1 && placed < want; wb += 32) {
-      // 32 fit words at a time, one per lane
-      uint32_t myw = 0;
-      if (wb + lane <= w1) {
-        myw = __ldg(Frow + wb + lane);
-        if (wb + lane == w0) myw &= kFull << (a & 31);
-        if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
-      }
-      uint32_t nz = __ballot_sync(kFull, myw != 0);
-      while (nz && placed < want) {
-        const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
-        const uint32_t bits = __shfl_sync(kFull, myw, src);
-        const uint32_t n = ((wb + src) << 5) + lane;
-        const bool mine = (bits >> lane) & 1u;
-        const uint32_t c = mine ? cap_now(tp, cx, g.np, cr, n) : 0u;
-        const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
-        const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
-        const uint32_t tincl = warp_incl_scan(t, lane);
-        if (t) {
-          const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
-          const uint32_t pos = g.np + tincl - t;
-          for (uint32_t j = 0; j < t; ++j) { cx.ent_node[pos + j] = n; cx.ent_meta[pos + j] = meta; }
-        }
-        const uint32_t tot = __shfl_sync(kFull, tincl, 31);
-        g.np += tot; placed += tot;
-        __syncwarp();
+// ---- cooperative evaluator: the whole warp packs ONE candidate range -----------------------------
+struct CoopEv {
+  const Topo& tp; const RoundBufs& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
+  uint32_t np;
+  __device__ CoopEv(const Topo& t, const RoundBufs& r, GangShared& s, const GangRegs& gr, uint32_t ln)
+      : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
+
+  __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
+    const uint4 r = __ldg(tp.nres + n);
+    uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
+    for (uint32_t i = 0; i < np; ++i) {
+      if (sh.ent_node[i] == n) {
+        const uint4 o = sh.clq[sh.ent_meta[i] & 0xFFu];
+        cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
       }
     }
+    return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
   }
-  return placed;
-}
 
-__device__ __forceinline__ bool fill_min(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
-                                         uint32_t lo, uint32_t hi, uint32_t lane) {
-  const uint32_t m = cx.clq[cr].w & 0xFFu;
-  const uint32_t mark = g.np;
-  if (take(tp, rb, cx, g, cr, lo, hi, m, lane) < m) { g.np = mark; return false; }
-  if (lane == 0) { cx.Hlo[cr] = lo; cx.Hhi[cr] = hi; }
-  __syncwarp();
-  return true;
-}
-
-// clique whose own Required level is a unit level (one node per domain, e.g. hostname): first node of
-// [lo,hi) in score order that takes all m pods
-__device__ bool find_unit(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, uint32_t cr,
-                          uint32_t lo, uint32_t hi, uint32_t lane) {
-  const uint32_t m = cx.clq[cr].w & 0xFFu;
-  const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
-  const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int np_ = make_pieces(g, lo, hi, g.L, plo, phi);
-  for (int p = 0; p < np_; ++p) {
-    const uint32_t a = plo[p], b = phi[p];
-    const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-    for (uint32_t wb = w0; wb <= w1; wb += 32) {
-      uint32_t myw = 0;
-      if (wb + lane <= w1) {
-        myw = __ldg(Frow + wb + lane);
-        if (wb + lane == w0) myw &= kFull << (a & 31);
-        if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
-      }
-      uint32_t nz = __ballot_sync(kFull, myw != 0);
-      while (nz) {
-        const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
-        const uint32_t bits = __shfl_sync(kFull, myw, src);
-        const uint32_t n = ((wb + src) << 5) + lane;
-        const bool mine = (bits >> lane) & 1u;
-        const uint32_t c = mine ? cap_now(tp, cx, g.np, cr, n) : 0u;
-        const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
-        if (okb) {
-          const uint32_t first = __ffs(okb) - 1;
-          const uint32_t nn = ((wb + src) << 5) + first;
-          const uint16_t meta = uint16_t(cr | (uint32_t(Trow[nn]) << 8));
-          for (uint32_t j = lane; j < m; j += 32) { cx.ent_node[g.np + j] = nn; cx.ent_meta[g.np + j] = meta; }
-          if (lane == 0) { cx.Hlo[cr] = nn; cx.Hhi[cr] = nn + 1; }
-          g.np += m;
+  // up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed
+  __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+    if (want == 0 || hi <= lo) return 0;
+    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    uint32_t placed = 0;
+    for (int p = 0; p < npc && placed < want; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+      for (uint32_t wb = w0; wb <= w1 && placed < want; wb += 32) {
+        uint32_t myw = 0;  // 32 fit words at a time, one per lane
+        if (wb + lane <= w1) {
+          myw = __ldg(Frow + wb + lane);
+          if (wb + lane == w0) myw &= kFull << (a & 31);
+          if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
+        }
+        uint32_t nz = __ballot_sync(kFull, myw != 0);
+        while (nz && placed < want) {
+          const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
+          const uint32_t bits = __shfl_sync(kFull, myw, src);
+          const uint32_t n = ((wb + src) << 5) + lane;
+          const bool mine = (bits >> lane) & 1u;
+          const uint32_t c = mine ? cap_now(cr, n) : 0u;
+          const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
+          const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
+          const uint32_t tincl = warp_incl_scan(t, lane);
+          if (t) {
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint32_t pos = np + tincl - t;
+            for (uint32_t j = 0; j < t; ++j) { sh.ent_node[pos + j] = n; sh.ent_meta[pos + j] = meta; }
+          }
+          const uint32_t tot = __shfl_sync(kFull, tincl, 31);
+          np += tot; placed += tot;
           __syncwarp();
-          return true;
         }
       }
     }
+    return placed;
   }
-  return false;
-}
 
-__device__ bool place_scope(const Topo& tp, const RoundBufs& rb, WarpCtx& cx, GangRegs& g, const grove_scope_t& s,
-                            uint32_t lo, uint32_t hi, int lvl, uint32_t lane) {
-  const uint32_t mark = g.np;
+  __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint32_t mark = np;
+    if (take(cr, lo, hi, m) < m) { np = mark; return false; }
+    if (lane == 0) { sh.Hlo[cr] = lo; sh.Hhi[cr] = hi; }
+    __syncwarp();
+    return true;
+  }
+
+  // clique whose own Required level is a unit level (one node per domain, e.g. hostname):
+  // first node of [lo,hi) in score order that takes all m pods
+  __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    for (int p = 0; p < npc; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+      for (uint32_t wb = w0; wb <= w1; wb += 32) {
+        uint32_t myw = 0;
+        if (wb + lane <= w1) {
+          myw = __ldg(Frow + wb + lane);
+          if (wb + lane == w0) myw &= kFull << (a & 31);
+          if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
+        }
+        uint32_t nz = __ballot_sync(kFull, myw != 0);
+        while (nz) {
+          const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
+          const uint32_t bits = __shfl_sync(kFull, myw, src);
+          const uint32_t n = ((wb + src) << 5) + lane;
+          const bool mine = (bits >> lane) & 1u;
+          const uint32_t c = mine ? cap_now(cr, n) : 0u;
+          const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
+          if (okb) {
+            const uint32_t nn = ((wb + src) << 5) + (__ffs(okb) - 1);
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[nn]) << 8));
+            for (uint32_t j = lane; j < m; j += 32) { sh.ent_node[np + j] = nn; sh.ent_meta[np + j] = meta; }
+            if (lane == 0) { sh.Hlo[cr] = nn; sh.Hhi[cr] = nn + 1; }
+            np += m;
+            __syncwarp();
+            return true;
+          }
+        }
+      }
+    }
+    return false;
+  }
+};
+
+// ---- scalar evaluator: ONE lane packs one candidate range (lanes of a warp hold different candidates)
+struct ScalarEv {
+  const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
+  uint32_t np;
+  uint32_t ent_node[GROVE_MAX_GANG_PODS];
+  uint16_t ent_meta[GROVE_MAX_GANG_PODS];
+  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
+  __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr)
+      : tp(t), rb(r), sh(s), g(gr), np(0) {}
+
+  __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
+    const uint4 r = __ldg(tp.nres + n);
+    uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
+    for (uint32_t i = 0; i < np; ++i) {
+      if (ent_node[i] == n) {
+        const uint4 o = sh.clq[ent_meta[i] & 0xFFu];
+        cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
+      }
+    }
+    return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
+  }
+
+  __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+    if (want == 0 || hi <= lo) return 0;
+    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    uint32_t placed = 0;
+    for (int p = 0; p < npc && placed < want; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+      for (uint32_t w = w0; w <= w1 && placed < want; ++w) {
+        uint32_t bits = __ldg(Frow + w);
+        if (w == w0) bits &= kFull << (a & 31);
+        if (w == w1 && (b & 31)) bits &= (1u << (b & 31)) - 1u;
+        while (bits && placed < want) {
+          const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
+          const uint32_t c = cap_now(cr, n);
+          const uint32_t t = min(c, want - placed);
+          if (t) {
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            for (uint32_t j = 0; j < t; ++j) { ent_node[np + j] = n; ent_meta[np + j] = meta; }
+            np += t; placed += t;
+          }
+        }
+      }
+    }
+    return placed;
+  }
+
+  __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint32_t mark = np;
+    if (take(cr, lo, hi, m) < m) { np = mark; return false; }
+    Hlo[cr] = lo; Hhi[cr] = hi;
+    return true;
+  }
+
+  __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    for (int p = 0; p < npc; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+      for (uint32_t w = w0; w <= w1; ++w) {
+        uint32_t bits = __ldg(Frow + w);
+        if (w == w0) bits &= kFull << (a & 31);
+        if (w == w1 && (b & 31)) bits &= (1u << (b & 31)) - 1u;
+        while (bits) {
+          const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
+          if (cap_now(cr, n) >= m) {
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            for (uint32_t j = 0; j < m; ++j) { ent_node[np + j] = n; ent_meta[np + j] = meta; }
+            np += m; Hlo[cr] = n; Hhi[cr] = n + 1;
+            return true;
+          }
+        }
+      }
+    }
+    return false;
+  }
+};
+
+template <class Ev>
+__device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
+  const Topo& tp = ev.tp;
+  const uint32_t mark = ev.np;
   for (uint32_t i = 0; i < s.n_cliques; ++i) {
     const uint32_t cr = s.first_clique + i;
-    const uint32_t w = cx.clq[cr].w;
+    const uint32_t w = ev.sh.clq[cr].w;
     const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
     bool ok = false;
     if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
       if (tp.unit[ql] && m >= 1) {
-        ok = find_unit(tp, rb, cx, g, cr, lo, hi, lane);
+        ok = ev.find_unit(cr, lo, hi);
       } else {
         uint32_t plo[kMaxPieces], phi[kMaxPieces];
-        const int np_ = make_pieces(g, lo, hi, ql, plo, phi);
-        for (int p = 0; p < np_ && !ok; ++p) {
+        const int npc = make_pieces(ev.g, lo, hi, ql, plo, phi);
+        for (int p = 0; p < npc && !ok; ++p) {
           const uint32_t d0 = __ldg(tp.next_dom[ql] + plo[p]), d1 = __ldg(tp.next_dom[ql] + phi[p]);
           for (uint32_t d = d0; d < d1 && !ok; ++d)
-            ok = fill_min(tp, rb, cx, g, cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d), lane);
+            ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
         }
       }
     } else {
-      ok = fill_min(tp, rb, cx, g, cr, lo, hi, lane);
+      ok = ev.fill_min(cr, lo, hi);
     }
-    if (!ok) { g.np = mark; return false; }
+    if (!ok) { ev.np = mark; return false; }
   }
   return true;
 }
 
-__device__ bool place_in(const Topo& tp, const Tables& tb, const RoundBufs& rb, WarpCtx& cx, GangRegs& g,
-                         const grove_gang_t& gg, uint32_t lo, uint32_t hi, int lvl, uint32_t lane) {
-  g.np = 0;
-  for (uint32_t si = 0; si < gg.n_scopes; ++si) {
-    const grove_scope_t s = tb.scopes[gg.scope_off + si];
+template <class Ev>
+__device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
+  const Topo& tp = ev.tp;
+  ev.np = 0;
+  for (uint32_t si = 0; si < n_scopes; ++si) {
+    const grove_scope_t s = ev.sh.scopes[si];
     bool ok = false;
     if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
       uint32_t plo[kMaxPieces], phi[kMaxPieces];
-      const int np_ = make_pieces(g, lo, hi, s.level, plo, phi);
-      for (int p = 0; p < np_ && !ok; ++p) {
+      const int npc = make_pieces(ev.g, lo, hi, s.level, plo, phi);
+      for (int p = 0; p < npc && !ok; ++p) {
         const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
         for (uint32_t d = d0; d < d1 && !ok; ++d)
-          ok = place_scope(tp, rb, cx, g, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), lane);
+          ok = place_scope(ev, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level));
       }
     } else {
-      ok = place_scope(tp, rb, cx, g, s, lo, hi, lvl, lane);
+      ok = place_scope(ev, s, lo, hi, lvl);
     }
-    if (!ok) { g.np = 0; return false; }
+    if (!ok) { ev.np = 0; return false; }
   }
   return true;
 }
 
-constexpr int kAdmitWarps = 4;
+// surplus beyond MinReplicas (best effort) + publication of the speculative placement
+template <class Ev>
+__device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* ent_meta, const uint32_t* Hlo,
+                            const uint32_t* Hhi, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
+  n_min = ev.np;
+  min_score = ev.tp.L + 1;
+  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ent_meta[i] >> 8));
+  for (uint32_t cr = 0; cr < n_cliques; ++cr) {
+    const uint32_t w = ev.sh.clq[cr].w;
+    const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
+    if (rp > mn) ev.take(cr, Hlo[cr], Hhi[cr], rp - mn);
+  }
+}
 
-__global__ void __launch_bounds__(kAdmitWarps * 32) k_admit(Topo tp, Tables tb, RoundBufs rb) {
-  __shared__ WarpCtx s_cx[kAdmitWarps];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ai = blockIdx.x * kAdmitWarps + warp;
+constexpr int kAdmitThreads = 128;
+
+__global__ void __launch_bounds__(kAdmitThreads) k_admit(Topo tp, Tables tb, RoundBufs rb) {
+  __shared__ GangShared sh;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ai = blockIdx.x;
   if (ai >= rb.counters[0]) return;
   const uint32_t gi = rb.active[ai];
   const grove_gang_t gg = tb.gangs[gi];
   const GangInfo info = tb.ginfo[gi];
-  WarpCtx& cx = s_cx[warp];
   GangRegs g;
-  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.np = 0; g.clique_off = gg.clique_off;
+  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
 #pragma unroll
   for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-  for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
+  for (uint32_t c = tid; c < gg.n_cliques; c += kAdmitThreads) {
     const grove_clique_t q = tb.cliques[gg.clique_off + c];
-    cx.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
+    sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
                            uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
-    cx.Hlo[c] = 0; cx.Hhi[c] = 0;
+    sh.Hlo[c] = 0; sh.Hhi[c] = 0;
   }
-  __syncwarp();
-  bool ok = false; uint32_t top = GROVE_NONE_U32;
+  for (uint32_t si = tid; si < gg.n_scopes; si += kAdmitThreads) sh.scopes[si] = tb.scopes[gg.scope_off + si];
+  if (tid == 0) sh.best = GROVE_NONE_U32;
+  __syncthreads();
+
   if (gg.level == GROVE_LEVEL_NONE) {
-    ok = place_in(tp, tb, rb, cx, g, gg, 0, tp.n, -1, lane);
-    if (ok) top = 0;
-  } else {
-    const uint32_t gl = gg.level;
-    const uint32_t* cand = rb.cand ? rb.cand + size_t(gi) * rb.cand_words : nullptr;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int np_ = make_pieces(g, 0, tp.n, gl, plo, phi);
-    for (int p = 0; p < np_ && !ok; ++p) {
-      const uint32_t d0 = __ldg(tp.next_dom[gl] + plo[p]), d1 = __ldg(tp.next_dom[gl] + phi[p]);
-      for (uint32_t d = d0; d < d1 && !ok; ++d) {
-        if (cand && !((__ldg(cand + (d >> 5)) >> (d & 31)) & 1u)) continue;  // necessary condition failed
-        const uint32_t dl = __ldg(tp.dom_lo[gl] + d), dh = __ldg(tp.dom_hi[gl] + d);
-        ok = place_in(tp, tb, rb, cx, g, gg, dl, dh, int(gl), lane);
-        if (ok) top = dl;
+    // single candidate: the whole cluster, packed cooperatively by warp 0
+    if (warp != 0) return;
+    CoopEv ev(tp, rb, sh, g, lane);
+    const bool ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
+    uint32_t n_min = 0, min_score = tp.L + 1;
+    if (ok) {
+      n_min = ev.np;
+      for (uint32_t i = lane; i < n_min; i += 32) min_score = min(min_score, uint32_t(sh.ent_meta[i] >> 8));
+#pragma unroll
+      for (int d = 16; d; d >>= 1) min_score = min(min_score, __shfl_xor_sync(kFull, min_score, d));
+      for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
+        const uint32_t w = sh.clq[cr].w;
+        const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
+        if (rp > mn) ev.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn);
+      }
+      for (uint32_t i = lane; i < ev.np; i += 32) {
+        rb.ent_node[info.pod_off + i] = sh.ent_node[i];
+        rb.ent_meta[info.pod_off + i] = sh.ent_meta[i];
       }
     }
-  }
-  uint32_t n_min = g.np;
-  uint32_t min_score = tp.L + 1;
-  if (ok) {
-    for (uint32_t i = lane; i < n_min; i += 32) min_score = min(min_score, uint32_t(cx.ent_meta[i] >> 8));
-#pragma unroll
-    for (int d = 16; d; d >>= 1) min_score = min(min_score, __shfl_xor_sync(kFull, min_score, d));
-    // best-effort surplus beyond MinReplicas inside the domain each clique was packed into
-    for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
-      const uint32_t w = cx.clq[cr].w;
-      const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-      if (rp > mn) take(tp, rb, cx, g, cr, cx.Hlo[cr], cx.Hhi[cr], rp - mn, lane);
+    if (lane == 0) {
+      rb.spec_ok[gi] = ok ? 1 : 0; rb.spec_n[gi] = uint16_t(ok ? ev.np : 0);
+      rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = ok ? 0u : GROVE_NONE_U32;
     }
-    for (uint32_t i = lane; i < g.np; i += 32) {
-      rb.ent_node[info.pod_off + i] = cx.ent_node[i];
-      rb.ent_meta[info.pod_off + i] = cx.ent_meta[i];
-    }
+    return;
   }
-  if (lane == 0) {
-    rb.spec_ok[gi] = ok ? 1 : 0;
-    rb.spec_n[gi] = uint16_t(ok ? g.np : 0);
-    rb.spec_score[gi] = uint8_t(min_score);
-    rb.spec_top[gi] = top;
+
+  // candidate domains of the gang's level in score order: up to kMaxPieces ranges of domain indices
+  const uint32_t gl = gg.level;
+  uint32_t plo[kMaxPieces], phi[kMaxPieces];
+  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
+  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
+  for (int p = 0; p < npc; ++p) {
+    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
+    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
+    D += rcnt[p];
+  }
+  ScalarEv ev(tp, rb, sh, g);
+  for (uint32_t base = 0, step = 0; base < D; ++step) {
+    const uint32_t width = step == 0 ? 32u : uint32_t(kAdmitThreads);
+    bool ok = false; uint32_t k = GROVE_NONE_U32, dl = 0, dh = 0;
+    if (tid < width && base + tid < D) {
+      k = base + tid;
+      uint32_t rem = k, d = 0;
+      for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
+      dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+      ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
+      if (ok) atomicMin(&sh.best, k);
+    }
+    __syncthreads();
+    const uint32_t best = sh.best;
+    if (best != GROVE_NONE_U32) {
+      if (k == best) {  // this lane holds the winning packing
+        uint32_t n_min, min_score;
+        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+        for (uint32_t i = 0; i < ev.np; ++i) {
+          rb.ent_node[info.pod_off + i] = ev.ent_node[i];
+          rb.ent_meta[info.pod_off + i] = ev.ent_meta[i];
+        }
+        rb.spec_ok[gi] = 1; rb.spec_n[gi] = uint16_t(ev.np);
+        rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = dl;
+      }
+      return;
+    }
+    base += width;
+  }
+  if (tid == 0) {
+    rb.spec_ok[gi] = 0; rb.spec_n[gi] = 0; rb.spec_score[gi] = uint8_t(tp.L + 1); rb.spec_top[gi] = GROVE_NONE_U32;
   }
 }
 
