@@ -4,7 +4,9 @@
 // optimistic rounds.  There is no CPU fallback: without a CUDA device the engine cannot be created.
 #include <algorithm>
 #include <cstdio>
+#include <array>
 #include <cstring>
+#include <map>
 #include <new>
 #include <numeric>
 #include <string>
@@ -82,12 +84,16 @@ struct grove_engine {
   std::vector<grove_scope_t> scopes;
   std::vector<GangInfo> ginfo;
   std::vector<CliqueInfo> cinfo;
+  std::vector<uint4> sigs;
+  uint32_t n_sigs = 0;
   bool gangs_loaded = false, ginfo_dirty = true;
   DevBuf<grove_gang_t> d_gangs;
   DevBuf<grove_clique_t> d_cliques;
   DevBuf<grove_scope_t> d_scopes;
   DevBuf<GangInfo> d_ginfo;
   DevBuf<CliqueInfo> d_cinfo;
+  DevBuf<uint4> d_sigs;
+  DevBuf<uint32_t> d_sig_stamp, d_sig_list;
 
   // ---- round state ----
   DevBuf<uint8_t> d_state, d_round, d_spec_ok, d_spec_score, d_T;
@@ -214,7 +220,7 @@ static Topo make_topo(grove_engine* e) {
 static Tables make_tables(grove_engine* e) {
   Tables t{};
   t.gangs = e->d_gangs.p; t.cliques = e->d_cliques.p; t.scopes = e->d_scopes.p;
-  t.ginfo = e->d_ginfo.p; t.cinfo = e->d_cinfo.p; t.G = e->G; t.Q = e->Q;
+  t.ginfo = e->d_ginfo.p; t.cinfo = e->d_cinfo.p; t.sigs = e->d_sigs.p; t.G = e->G; t.Q = e->Q; t.S = e->n_sigs;
   return t;
 }
 
@@ -223,6 +229,7 @@ static RoundBufs make_bufs(grove_engine* e) {
   r.state = e->d_state.p; r.round = e->d_round.p; r.active = e->d_active.p; r.rows = e->d_rows.p;
   r.counters = e->d_counters.p; r.spec_ok = e->d_spec_ok.p; r.spec_score = e->d_spec_score.p;
   r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
+  r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
   r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p; r.cand = nullptr; r.cand_words = 0;
   return r;
 }
@@ -249,7 +256,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   e->cfg = *cfg; e->L = cfg->n_levels;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
-  if (e->h_counters.ensure(4) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
+  if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
   *out = e;
   return GROVE_OK;
 }
@@ -399,7 +406,9 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
 static int32_t build_ginfo(grove_engine* e) {
   const uint32_t G = e->G, Q = e->Q;
   e->ginfo.assign(G, GangInfo{});
-  e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0});
+  e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0, 0, 0});
+  e->sigs.clear();
+  std::map<std::array<uint32_t, 5>, uint32_t> sig_of;
   std::vector<uint32_t> ord(G);
   std::iota(ord.begin(), ord.end(), 0u);
   std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
@@ -427,7 +436,15 @@ static int32_t build_ginfo(grove_engine* e) {
         if (s.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(s.level) + 1);
         if (q.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(q.level) + 1);
         if (e->cinfo[qi].gang != GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique rows shared between gangs");
-        e->cinfo[qi] = CliqueInfo{gi, nd};
+        // PodCliques stamped from one template (PCS / PCSG replicas) share requests, selector class and
+        // binding depth: they share one fit-bitmap row
+        const std::array<uint32_t, 5> key{q.req_cpu_milli, q.req_mem_mib, q.req_gpu, q.class_mask, nd};
+        auto it = sig_of.find(key);
+        if (it == sig_of.end()) {
+          it = sig_of.emplace(key, uint32_t(e->sigs.size())).first;
+          e->sigs.push_back(make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu, uint32_t(q.class_mask) | (nd << 16)));
+        }
+        e->cinfo[qi] = CliqueInfo{gi, nd, it->second, 0};
         pods += q.replicas;
       }
     }
@@ -436,7 +453,10 @@ static int32_t build_ginfo(grove_engine* e) {
   e->P = pod_off;
   for (uint32_t qi = 0; qi < Q; ++qi)
     if (e->cinfo[qi].gang == GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique row owned by no gang");
-  CU_TRY(e, e->d_ginfo.ensure(G)); CU_TRY(e, e->d_cinfo.ensure(Q));
+  e->n_sigs = uint32_t(e->sigs.size());
+  CU_TRY(e, e->d_ginfo.ensure(G)); CU_TRY(e, e->d_cinfo.ensure(Q)); CU_TRY(e, e->d_sigs.ensure(e->n_sigs));
+  CU_TRY(e, e->d_sig_stamp.ensure(e->n_sigs)); CU_TRY(e, e->d_sig_list.ensure(e->n_sigs));
+  if (e->n_sigs) CU_TRY(e, cudaMemcpyAsync(e->d_sigs.p, e->sigs.data(), sizeof(uint4) * e->n_sigs, cudaMemcpyHostToDevice, e->stream));
   if (G) CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo.data(), sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
   if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo.data(), sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
   e->ginfo_dirty = false;
@@ -452,14 +472,14 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   if (e->ginfo_dirty) { int32_t rc = build_ginfo(e); if (rc) return rc; }
   const uint32_t G = e->G, Q = e->Q;
   CU_TRY(e, e->d_state.ensure(G)); CU_TRY(e, e->d_round.ensure(G)); CU_TRY(e, e->d_active.ensure(G)); CU_TRY(e, e->d_rows.ensure(Q));
-  CU_TRY(e, e->d_counters.ensure(4)); CU_TRY(e, e->d_spec_ok.ensure(G)); CU_TRY(e, e->d_spec_score.ensure(G));
+  CU_TRY(e, e->d_counters.ensure(8)); CU_TRY(e, e->d_spec_ok.ensure(G)); CU_TRY(e, e->d_spec_score.ensure(G));
   CU_TRY(e, e->d_spec_n.ensure(G)); CU_TRY(e, e->d_spec_top.ensure(G)); CU_TRY(e, e->d_ent_node.ensure(e->P)); CU_TRY(e, e->d_ent_meta.ensure(e->P));
   CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
   CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
   CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
   // the Q x N matrices
   {
-    const size_t fw = size_t(Q) * e->words, tb = size_t(Q) * e->Npad;
+    const size_t fw = size_t(e->n_sigs) * e->words, tb = size_t(Q) * e->Npad;
     if (e->d_F.ensure(fw) != cudaSuccess || e->d_T.ensure(tb) != cudaSuccess) {
       (void)cudaGetLastError();
       return fail(e, GROVE_ERR_OOM, "fit/score matrices do not fit in device memory");
@@ -471,6 +491,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   if (G) CU_TRY(e, cudaMemcpyAsync(e->d_state.p, st.data(), G, cudaMemcpyHostToDevice, e->stream));
   if (G) CU_TRY(e, cudaMemsetAsync(e->d_round.p, 0, G, e->stream));
   if (G) CU_TRY(e, cudaMemsetAsync(e->d_spec_n.p, 0, sizeof(uint16_t) * G, e->stream));
+  if (e->n_sigs) CU_TRY(e, cudaMemsetAsync(e->d_sig_stamp.p, 0, sizeof(uint32_t) * e->n_sigs, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));  // st is a local
   e->round_no = 0; e->pairs = 0; e->launches = 0; e->in_cycle = true; e->have_results = false;
   std::memset(&e->last, 0, sizeof(e->last));
@@ -483,22 +504,25 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
   e->round_no++;
   k_prepare<<<1, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
   CU_TRY(e, cudaGetLastError());
-  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   e->launches += 1;
   const uint32_t na = e->h_counters.p[0], nr = e->h_counters.p[1];
   if (na == 0) return GROVE_OK;
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  dim3 gfit(e->Npad / 1024, (nr + kFitTile - 1) / kFitTile);
+  const uint32_t ns = e->h_counters.p[4];
+  dim3 gfit(e->Npad / 1024, std::min<uint32_t>((ns + kFitTile - 1) / kFitTile, 65535u));
   k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
   {
-    const uint64_t total = uint64_t(nr) * (e->Npad >> 4);
-    const uint32_t blocks = uint32_t(std::min<uint64_t>((total + 255) / 256, 148u * 64u));
-    k_score<<<blocks, 256, 0, e->stream>>>(tp, tb, rb, nr);
+    const uint32_t cpr = e->Npad >> 4;
+    (void)cpr;
+    dim3 gs(1, std::min<uint32_t>(nr, 65535u));  // one CTA per row, looping over its chunks
+    k_score<<<gs, 256, 0, e->stream>>>(tp, tb, rb, nr);
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
-  k_admit<<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+  if (na >= 148u * 4u) k_admit<kAdmitThreads><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+  else k_admit<kAdmitThreadsWide><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
   CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0xFF, sizeof(uint32_t) * e->N, e->stream));
   k_claim<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb);
@@ -625,7 +649,7 @@ int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* wo
   const uint32_t w = (e->N + 31) / 32;
   if (cap_words < w) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  CU_TRY(e, cudaMemcpy(words, e->d_F.p + size_t(clique) * e->words, sizeof(uint32_t) * w, cudaMemcpyDeviceToHost));
+  CU_TRY(e, cudaMemcpy(words, e->d_F.p + size_t(e->cinfo[clique].sig) * e->words, sizeof(uint32_t) * w, cudaMemcpyDeviceToHost));
   return GROVE_OK;
 }
 

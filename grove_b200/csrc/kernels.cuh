@@ -28,9 +28,11 @@ struct GangInfo {     // 48 B, built on the host at submit time
   uint32_t anc_hi[GROVE_MAX_LEVELS];
 };
 
-struct CliqueInfo {   // 8 B
+struct CliqueInfo {   // 16 B
   uint32_t gang;
   uint32_t need_depth;  // labels a candidate node must carry (deepest binding Required level + 1)
+  uint32_t sig;         // fit signature: cliques with identical (requests, class mask, need_depth) share a fit row
+  uint32_t pad;
 };
 
 struct Topo {
@@ -50,7 +52,8 @@ struct Tables {
   const grove_scope_t* scopes;
   const GangInfo* ginfo;
   const CliqueInfo* cinfo;
-  uint32_t G, Q;
+  const uint4* sigs;     // [S] req_cpu, req_mem, req_gpu, class_mask | need_depth << 16
+  uint32_t G, Q, S;
 };
 
 struct RoundBufs {
@@ -58,7 +61,9 @@ struct RoundBufs {
   uint8_t* round;        // [G]
   uint32_t* active;      // [G] gangs evaluated this round
   uint32_t* rows;        // [Q] clique rows evaluated this round
-  uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated by this prepare
+  uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated [4] n_sigs
+  uint32_t* sig_stamp;   // [S] last round in which the signature was active
+  uint32_t* sig_list;    // [S] signatures needed this round
   uint8_t* spec_ok;      // [G]
   uint8_t* spec_score;   // [G]
   uint16_t* spec_n;      // [G] entries incl. surplus
@@ -66,7 +71,7 @@ struct RoundBufs {
   uint32_t* ent_node;    // [P]
   uint16_t* ent_meta;    // [P] clique_rel | score << 8
   uint32_t* claim;       // [n]
-  uint32_t* F;           // [Q][words]
+  uint32_t* F;           // [S][words] fit bitmap, one row per signature
   uint8_t* T;            // [Q][npad]
   uint32_t* cand;        // [G][cand_words] necessary-condition bits over gang-level domains
   uint32_t cand_words;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     }
     __syncthreads();
   } while (s_changed);
-  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; }
+  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; rb.counters[4] = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < tb.G; base += 1024) {
     uint32_t g = base + tid;
@@ -174,7 +179,11 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     uint32_t orr = s_nr + s_warp_r[warp] + ir - ncl;
     if (act) {
       rb.active[oa] = g;
-      for (uint32_t i = 0; i < ncl; ++i) rb.rows[orr + i] = coff + i;
+      for (uint32_t i = 0; i < ncl; ++i) {
+        rb.rows[orr + i] = coff + i;
+        const uint32_t sg = tb.cinfo[coff + i].sig;
+        if (atomicExch(rb.sig_stamp + sg, round_no) != round_no) rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
+      }
     }
     __syncthreads();
     if (tid == 0) { s_na += s_tot_a; s_nr += s_tot_r; }
@@ -204,37 +213,32 @@ __global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) 
   __shared__ uint4 s_prm[kFitTile];
   __shared__ uint32_t s_row[kFitTile];
   __shared__ uint32_t s_out[kFitTile][32];
-  const uint32_t n_rows = rb.counters[1];
-  const uint32_t r0 = blockIdx.y * kFitTile;
-  if (r0 >= n_rows) return;
+  const uint32_t n_rows = rb.counters[4];                 // active signatures
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < kFitTile) {
-    uint32_t r = r0 + tid;
-    uint4 p = make_uint4(kFull, kFull, kFull, 0);  // never fits
-    uint32_t q = 0;
-    if (r < n_rows) {
-      q = rb.rows[r];
-      grove_clique_t c = tb.cliques[q];
-      p = make_uint4(c.req_cpu_milli, c.req_mem_mib, c.req_gpu, uint32_t(c.class_mask) | (tb.cinfo[q].need_depth << 16));
-    }
-    s_prm[tid] = p; s_row[tid] = q;
-  }
-  __syncthreads();
   const uint32_t node = blockIdx.x * 1024 + tid;           // npad is a multiple of 1024
   const uint4 r = __ldg(tp.nres + node);
   const uint32_t gpu = r.z & 0xFFFFu, pods = r.z >> 16;
   const uint32_t depth = (r.w >> 16) & 0xFu;
   const uint32_t onehot = ((r.w & GROVE_NODE_SCHEDULABLE) && pods >= 1) ? (1u << ((r.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) : 0u;
+  for (uint32_t r0 = blockIdx.y * kFitTile; r0 < n_rows; r0 += gridDim.y * kFitTile) {
+    __syncthreads();
+    if (tid < kFitTile) {
+      uint4 p = make_uint4(kFull, kFull, kFull, 0);  // never fits
+      uint32_t sg = 0;
+      if (r0 + tid < n_rows) { sg = rb.sig_list[r0 + tid]; p = tb.sigs[sg]; }
+      s_prm[tid] = p; s_row[tid] = sg;
+    }
+    __syncthreads();
+    const int cnt = int(min(uint32_t(kFitTile), n_rows - r0));
 #pragma unroll 4
-  for (int c = 0; c < kFitTile; ++c) {
-    const uint4 p = s_prm[c];
-    bool ok = (r.x >= p.x) & (r.y >= p.y) & (gpu >= p.z) & ((p.w & onehot) != 0) & (depth >= (p.w >> 16));
-    uint32_t b = __ballot_sync(kFull, ok);
-    if (lane == 0) s_out[c][warp] = b;
-  }
-  __syncthreads();
-  for (int c = warp; c < kFitTile; c += 32) {
-    if (r0 + c < n_rows) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
+    for (int c = 0; c < cnt; ++c) {
+      const uint4 p = s_prm[c];
+      bool ok = (r.x >= p.x) & (r.y >= p.y) & (gpu >= p.z) & ((p.w & onehot) != 0) & (depth >= (p.w >> 16));
+      uint32_t b = __ballot_sync(kFull, ok);
+      if (lane == 0) s_out[c][warp] = b;
+    }
+    __syncthreads();
+    for (int c = warp; c < cnt; c += 32) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
   }
 }
 
@@ -250,46 +254,49 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {  // 4 bits -> 4 byte
 
 __global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb, uint32_t n_rows) {
   const uint32_t cpr = tp.npad >> 4;  // 16-node chunks per row
-  const uint64_t total = uint64_t(n_rows) * cpr;
-  for (uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; id < total; id += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t r = uint32_t(id / cpr), ch = uint32_t(id - uint64_t(r) * cpr);
+  for (uint32_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
     const uint32_t q = __ldg(rb.rows + r);
-    const uint32_t n0 = ch << 4;
-    const uint32_t bits = (__ldg(rb.F + size_t(q) * tp.words + (n0 >> 5)) >> (n0 & 16)) & 0xFFFFu;
-    uint4 out = make_uint4(0, 0, 0, 0);
-    if (bits) {
-      const GangInfo* gi = tb.ginfo + __ldg(&tb.cinfo[q].gang);
-      const uint4 alo = __ldg(reinterpret_cast<const uint4*>(gi->anc_lo));
-      const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(gi->anc_hi));
-      const uint32_t lo[4] = {alo.x, alo.y, alo.z, alo.w}, hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
-      uint32_t inside = 0; bool uniform = true;
+    const CliqueInfo ci = tb.cinfo[q];
+    const GangInfo* gi = tb.ginfo + ci.gang;
+    const uint4 alo = __ldg(reinterpret_cast<const uint4*>(gi->anc_lo));
+    const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(gi->anc_hi));
+    const uint32_t lo[4] = {alo.x, alo.y, alo.z, alo.w}, hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
+    const uint32_t* Frow = rb.F + size_t(ci.sig) * tp.words;
+    uint8_t* Trow = rb.T + size_t(q) * tp.npad;
+    for (uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch < cpr; ch += gridDim.x * blockDim.x) {
+      const uint32_t n0 = ch << 4;
+      const uint32_t bits = (__ldg(Frow + (n0 >> 5)) >> (n0 & 16)) & 0xFFFFu;
+      uint4 out = make_uint4(0, 0, 0, 0);
+      if (bits) {
+        uint32_t inside = 0; bool uniform = true;
 #pragma unroll
-      for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
-        if (l < (int)tp.L) {
-          bool in = n0 >= lo[l] && n0 + 16 <= hi[l];
-          bool outl = n0 + 16 <= lo[l] || n0 >= hi[l];
-          inside += in; uniform &= (in | outl);
-        }
-      }
-      if (uniform) {
-        const uint32_t v = inside + 1;
-        out.x = spread4(bits & 0xF) * v; out.y = spread4((bits >> 4) & 0xF) * v;
-        out.z = spread4((bits >> 8) & 0xF) * v; out.w = spread4(bits >> 12) * v;
-      } else {
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if ((bits >> j) & 1u) {
-            uint32_t n = n0 + j, c = 1;
-#pragma unroll
-            for (int l = 0; l < GROVE_MAX_LEVELS; ++l) c += (l < (int)tp.L && n >= lo[l] && n < hi[l]);
-            w[j >> 2] |= c << ((j & 3) * 8);
+        for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
+          if (l < (int)tp.L) {
+            bool in = n0 >= lo[l] && n0 + 16 <= hi[l];
+            bool outl = n0 + 16 <= lo[l] || n0 >= hi[l];
+            inside += in; uniform &= (in | outl);
           }
         }
-        out = make_uint4(w[0], w[1], w[2], w[3]);
+        if (uniform) {
+          const uint32_t v = inside + 1;
+          out.x = spread4(bits & 0xF) * v; out.y = spread4((bits >> 4) & 0xF) * v;
+          out.z = spread4((bits >> 8) & 0xF) * v; out.w = spread4(bits >> 12) * v;
+        } else {
+          uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if ((bits >> j) & 1u) {
+              uint32_t n = n0 + j, c = 1;
+#pragma unroll
+              for (int l = 0; l < GROVE_MAX_LEVELS; ++l) c += (l < (int)tp.L && n >= lo[l] && n < hi[l]);
+              w[j >> 2] |= c << ((j & 3) * 8);
+            }
+          }
+          out = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
+      *reinterpret_cast<uint4*>(Trow + n0) = out;
     }
-    *reinterpret_cast<uint4*>(rb.T + size_t(q) * tp.npad + n0) = out;
   }
 }
 
@@ -315,6 +322,7 @@ struct GangRegs {   // per-gang constants
 struct GangShared {
   uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
   grove_scope_t scopes[GROVE_MAX_GANG_SCOPES];
+  uint32_t sig[GROVE_MAX_GANG_CLIQUES];    // fit-bitmap row of each clique
   // cooperative evaluator state (warp 0)
   uint32_t ent_node[GROVE_MAX_GANG_PODS];
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel | score << 8
@@ -357,6 +365,7 @@ __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_
 struct CoopEv {
   const Topo& tp; const RoundBufs& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
   uint32_t np;
+  __device__ __forceinline__ bool moot() const { return false; }
   __device__ CoopEv(const Topo& t, const RoundBufs& r, GangShared& s, const GangRegs& gr, uint32_t ln)
       : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
 
@@ -375,7 +384,7 @@ struct CoopEv {
   // up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed
   __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
-    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     uint32_t plo[kMaxPieces], phi[kMaxPieces];
     const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
@@ -427,7 +436,7 @@ struct CoopEv {
   // first node of [lo,hi) in score order that takes all m pods
   __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     uint32_t plo[kMaxPieces], phi[kMaxPieces];
     const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
@@ -469,11 +478,13 @@ struct CoopEv {
 struct ScalarEv {
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
+  uint32_t k;   // candidate index of this lane; a lower successful candidate makes this attempt moot
+  __device__ __forceinline__ bool moot() const { return *reinterpret_cast<const volatile uint32_t*>(&sh.best) < k; }
   uint32_t ent_node[GROVE_MAX_GANG_PODS];
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
   __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr)
-      : tp(t), rb(r), sh(s), g(gr), np(0) {}
+      : tp(t), rb(r), sh(s), g(gr), np(0), k(0) {}
 
   __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
     const uint4 r = __ldg(tp.nres + n);
@@ -489,7 +500,7 @@ struct ScalarEv {
 
   __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
-    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     uint32_t plo[kMaxPieces], phi[kMaxPieces];
     const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
@@ -526,7 +537,7 @@ struct ScalarEv {
 
   __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t* Frow = rb.F + size_t(g.clique_off + cr) * tp.words;
+    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     uint32_t plo[kMaxPieces], phi[kMaxPieces];
     const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
@@ -593,8 +604,10 @@ __device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, in
       const int npc = make_pieces(ev.g, lo, hi, s.level, plo, phi);
       for (int p = 0; p < npc && !ok; ++p) {
         const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
-        for (uint32_t d = d0; d < d1 && !ok; ++d)
+        for (uint32_t d = d0; d < d1 && !ok; ++d) {
+          if (ev.moot()) { ev.np = 0; return false; }
           ok = place_scope(ev, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level));
+        }
       }
     } else {
       ok = place_scope(ev, s, lo, hi, lvl);
@@ -618,9 +631,11 @@ __device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* en
   }
 }
 
-constexpr int kAdmitThreads = 128;
+constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
+constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
 
-__global__ void __launch_bounds__(kAdmitThreads) k_admit(Topo tp, Tables tb, RoundBufs rb) {
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ai = blockIdx.x;
@@ -632,13 +647,13 @@ __global__ void __launch_bounds__(kAdmitThreads) k_admit(Topo tp, Tables tb, Rou
   g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
 #pragma unroll
   for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-  for (uint32_t c = tid; c < gg.n_cliques; c += kAdmitThreads) {
+  for (uint32_t c = tid; c < gg.n_cliques; c += blockDim.x) {
     const grove_clique_t q = tb.cliques[gg.clique_off + c];
     sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
                            uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
-    sh.Hlo[c] = 0; sh.Hhi[c] = 0;
+    sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
   }
-  for (uint32_t si = tid; si < gg.n_scopes; si += kAdmitThreads) sh.scopes[si] = tb.scopes[gg.scope_off + si];
+  for (uint32_t si = tid; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
   if (tid == 0) sh.best = GROVE_NONE_U32;
   __syncthreads();
 
@@ -682,13 +697,14 @@ __global__ void __launch_bounds__(kAdmitThreads) k_admit(Topo tp, Tables tb, Rou
   }
   ScalarEv ev(tp, rb, sh, g);
   for (uint32_t base = 0, step = 0; base < D; ++step) {
-    const uint32_t width = step == 0 ? 32u : uint32_t(kAdmitThreads);
+    const uint32_t width = (step == 0 && blockDim.x == kAdmitThreads) ? 32u : blockDim.x;
     bool ok = false; uint32_t k = GROVE_NONE_U32, dl = 0, dh = 0;
     if (tid < width && base + tid < D) {
       k = base + tid;
       uint32_t rem = k, d = 0;
       for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
       dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+      ev.k = k;
       ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
       if (ok) atomicMin(&sh.best, k);
     }
