@@ -200,12 +200,10 @@ int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats);
 
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */
 int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap);
-/* round-1 matrices of the last cycle: fit bitmap row (ceil(n/32) words) and score row (n bytes) */
+/* matrices as the last round left them (create the engine with max_rounds = 1 to read round 1):
+ * fit bitmap row (ceil(n/32) words) and score row (n bytes) of one clique */
 int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* words, uint32_t cap_words);
 int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* bytes, uint32_t cap_bytes);
-/* keep round-1 matrices intact for the getters above (later rounds then use scratch rows) */
-int32_t grove_debug_set_keep_round1(grove_engine_t* e, int32_t keep);
-
 #ifdef __cplusplus
 }
 #endif
