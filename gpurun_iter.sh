@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -5
+python -m pytest tests -x -q -m gpu 2>&1 | tail -8
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; tail -3 gpurun_out/bench_iter.err
 python - <<'PY'
 import json

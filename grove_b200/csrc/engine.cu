@@ -101,6 +101,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
   DevBuf<grove_gang_status_t> d_status;
   DevBuf<grove_placement_t> d_out;
+  DevBuf<uint32_t> d_delta, d_final;
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
   PinBuf<uint32_t> h_counters;
@@ -524,7 +525,7 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
   if (na >= 148u * 4u) k_admit<kAdmitThreads><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
   else k_admit<kAdmitThreadsWide><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
-  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0xFF, sizeof(uint32_t) * e->N, e->stream));
+  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
   k_claim<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb);
   CU_TRY(e, cudaGetLastError());
   e->launches += 4;
@@ -616,22 +617,93 @@ int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint3
   return GROVE_OK;
 }
 
-// ---- multi-GPU stepping (filled in with the sharded path) ----
-int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
-  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+// ---- stepping API (multi-GPU hosts reduce the returned buffers between the calls) ----
+int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words, uint32_t* go) {
+  if (!e || !d_claim_words || !n_claim_words || !go) return GROVE_ERR_INVALID_ARG;
+  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  *go = 0; *d_claim_words = e->d_claim.p; *n_claim_words = e->N;
+  if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) return GROVE_OK;
+  // the prepare pass sees the replicated gang state, so its verdicts are identical on every rank
+  int32_t rc = round_eval(e, false, nullptr);
+  if (rc) return rc;
+  const uint32_t unres = e->h_counters.p[2], glob = e->h_counters.p[5];
+  if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; return GROVE_OK; }
+  if (glob == 0) {
+    k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
+    CU_TRY(e, cudaGetLastError());
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    e->launches += 1;
+    return GROVE_OK;
+  }
+  if (e->h_counters.p[0] == 0)  // this rank has no active gang this round: its claims are all "none"
+    CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  *go = 1;
+  return GROVE_OK;
 }
+
 int32_t grove_round_commit(grove_engine_t* e, void** d_delta_words, uint32_t* n_delta_words) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
-  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+  if (!e || !d_delta_words || !n_delta_words) return GROVE_ERR_INVALID_ARG;
+  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  const size_t words = 4 * size_t(e->N) + e->G;
+  CU_TRY(e, e->d_delta.ensure(words));
+  CU_TRY(e, cudaMemsetAsync(e->d_delta.p, 0, sizeof(uint32_t) * words, e->stream));
+  const uint32_t na = e->h_counters.p[0];
+  if (na) {
+    k_commit_sharded<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(make_topo(e), make_tables(e), make_bufs(e), e->d_delta.p);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 1;
+  }
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  *d_delta_words = e->d_delta.p; *n_delta_words = uint32_t(words);
+  return GROVE_OK;
 }
-int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining_local) {
+
+int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining) {
   if (!e) return GROVE_ERR_INVALID_ARG;
-  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  const uint32_t m = std::max(e->N, e->G);
+  k_apply<<<(m + 255) / 256, 256, 0, e->stream>>>(make_topo(e), make_tables(e), make_bufs(e), e->d_nres.p, e->d_delta.p, e->round_no);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  const uint32_t unres_before = e->h_counters.p[2];
+  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (remaining) *remaining = unres_before - e->h_counters.p[6];
+  return GROVE_OK;
 }
+
+int32_t grove_cycle_gather(grove_engine_t* e, void** d_final_words, uint32_t* n_final_words) {
+  if (!e || !d_final_words || !n_final_words) return GROVE_ERR_INVALID_ARG;
+  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  const size_t words = 2 * size_t(e->P) + 3 * size_t(e->G);
+  CU_TRY(e, e->d_final.ensure(words));
+  CU_TRY(e, cudaMemsetAsync(e->d_final.p, 0, sizeof(uint32_t) * std::max<size_t>(words, 1), e->stream));
+  if (e->G) {
+    k_pack_final<<<(e->G + 127) / 128, 128, 0, e->stream>>>(make_tables(e), make_bufs(e), e->d_final.p, e->P, e->cfg.rank, e->cfg.world);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 1;
+  }
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  *d_final_words = e->d_final.p; *n_final_words = uint32_t(words);
+  return GROVE_OK;
+}
+
 int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e) return GROVE_ERR_INVALID_ARG;
-  return fail(e, GROVE_ERR_STATE, "sharded stepping not built yet");
+  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
+  if (e->d_final.cap < 2 * size_t(e->P) + 3 * size_t(e->G)) return fail(e, GROVE_ERR_STATE, "grove_cycle_gather first");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  if (e->G) {
+    k_unpack_final<<<(e->G + 127) / 128, 128, 0, e->stream>>>(make_tables(e), make_bufs(e), e->d_final.p, e->P);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 1;
+  }
+  return finish_cycle(e, stats);
 }
 
 // ---- introspection for parity tests ----

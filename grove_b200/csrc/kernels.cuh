@@ -62,6 +62,7 @@ struct RoundBufs {
   uint32_t* active;      // [G] gangs evaluated this round
   uint32_t* rows;        // [Q] clique rows evaluated this round
   uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated [4] n_sigs
+                         // [5] active gangs over all ranks [6] gangs resolved by this round's apply
   uint32_t* sig_stamp;   // [S] last round in which the signature was active
   uint32_t* sig_list;    // [S] signatures needed this round
   uint8_t* spec_ok;      // [G]
@@ -131,7 +132,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint32_t round_no, uint32_t rank, uint32_t world) {
   __shared__ int s_changed;
   __shared__ uint32_t s_warp_a[32], s_warp_r[32];
-  __shared__ uint32_t s_na, s_nr, s_unres, s_tot_a, s_tot_r, s_prop;
+  __shared__ uint32_t s_na, s_nr, s_unres, s_tot_a, s_tot_r, s_prop, s_glob;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
   // scaled gangs of a rejected / skipped base gang are rejected with it (transitively)
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     }
     __syncthreads();
   } while (s_changed);
-  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; rb.counters[4] = 0; }
+  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; s_glob = 0; rb.counters[4] = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < tb.G; base += 1024) {
     uint32_t g = base + tid;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
       grove_gang_t gg = tb.gangs[g];
       bool ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
       bool mine = world <= 1 || (g % world) == rank;
+      if (ready) atomicAdd(&s_glob, 1u);
       if (ready && mine) { act = 1; ncl = gg.n_cliques; coff = gg.clique_off; }
     }
     uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     if (tid == 0) { s_na += s_tot_a; s_nr += s_tot_r; }
     __syncthreads();
   }
-  if (tid == 0) { rb.counters[0] = s_na; rb.counters[1] = s_nr; rb.counters[2] = s_unres; rb.counters[3] = s_prop; }
+  if (tid == 0) { rb.counters[0] = s_na; rb.counters[1] = s_nr; rb.counters[2] = s_unres; rb.counters[3] = s_prop; rb.counters[5] = s_glob; rb.counters[6] = 0; }
 }
 
 // dependency cycle or unreachable base: nothing can become active any more
@@ -767,6 +769,76 @@ __global__ void k_commit(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t
     atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
   }
   if (lane == 0) { rb.state[gi] = GROVE_GANG_ADMITTED; rb.round[gi] = r8; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded cycle (gang rows dealt g % world to ranks; node table and gang state replicated):
+// winners write deltas instead of touching the node table; after the SUM all-reduce every rank applies
+// the same deltas.  Layouts: delta = [4 * n] resource usage per node + [G] new gang state;
+// final = [P] entry node + [P] entry meta + [G] entries + [G] min score + [G] top domain.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_commit_sharded(Topo tp, Tables tb, RoundBufs rb, uint32_t* delta) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t gi = rb.active[ai];
+  uint32_t* dstate = delta + 4 * size_t(tp.n);
+  if (!rb.spec_ok[gi]) { if (lane == 0) dstate[gi] = GROVE_GANG_REJECTED; return; }
+  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
+  bool win = true;
+  for (uint32_t i = lane; i < n; i += 32) win &= rb.claim[rb.ent_node[off + i]] == order;
+  if (!__all_sync(kFull, win)) return;
+  const uint32_t coff = tb.gangs[gi].clique_off;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const grove_clique_t q = tb.cliques[coff + (rb.ent_meta[off + i] & 0xFFu)];
+    uint32_t* d = delta + 4 * size_t(rb.ent_node[off + i]);
+    if (q.req_cpu_milli) atomicAdd(d + 0, q.req_cpu_milli);
+    if (q.req_mem_mib) atomicAdd(d + 1, q.req_mem_mib);
+    if (q.req_gpu) atomicAdd(d + 2, uint32_t(q.req_gpu));
+    atomicAdd(d + 3, 1u);
+  }
+  if (lane == 0) dstate[gi] = GROVE_GANG_ADMITTED;
+}
+
+__global__ void k_apply(Topo tp, Tables tb, RoundBufs rb, uint4* nres, const uint32_t* __restrict__ delta, uint32_t round_no) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tp.n) {
+    const uint4 d = *reinterpret_cast<const uint4*>(delta + 4 * size_t(i));
+    if (d.x | d.y | d.z | d.w) {
+      uint4 r = nres[i];
+      r.x -= d.x; r.y -= d.y; r.z -= d.z | (d.w << 16);
+      nres[i] = r;
+    }
+  }
+  if (i < tb.G) {
+    const uint32_t s = delta[4 * size_t(tp.n) + i];
+    if (s) {
+      rb.state[i] = uint8_t(s); rb.round[i] = uint8_t(round_no > 255 ? 255 : round_no);
+      atomicAdd(rb.counters + 6, 1u);
+    }
+  }
+}
+
+__global__ void k_pack_final(Tables tb, RoundBufs rb, uint32_t* fin, uint32_t P, uint32_t rank, uint32_t world) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= tb.G) return;
+  if (rb.state[g] != GROVE_GANG_ADMITTED || (world > 1 && g % world != rank)) return;
+  const uint32_t po = tb.ginfo[g].pod_off, n = rb.spec_n[g];
+  for (uint32_t i = 0; i < n; ++i) { fin[po + i] = rb.ent_node[po + i]; fin[P + po + i] = rb.ent_meta[po + i]; }
+  fin[2 * size_t(P) + g] = n;
+  fin[2 * size_t(P) + tb.G + g] = rb.spec_score[g];
+  fin[2 * size_t(P) + 2 * size_t(tb.G) + g] = rb.spec_top[g];
+}
+
+__global__ void k_unpack_final(Tables tb, RoundBufs rb, const uint32_t* __restrict__ fin, uint32_t P) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= tb.G) return;
+  if (rb.state[g] != GROVE_GANG_ADMITTED) { rb.spec_n[g] = 0; return; }
+  const uint32_t po = tb.ginfo[g].pod_off, n = fin[2 * size_t(P) + g];
+  for (uint32_t i = 0; i < n; ++i) { rb.ent_node[po + i] = fin[po + i]; rb.ent_meta[po + i] = uint16_t(fin[P + po + i]); }
+  rb.spec_n[g] = uint16_t(n);
+  rb.spec_score[g] = uint8_t(fin[2 * size_t(P) + tb.G + g]);
+  rb.spec_top[g] = fin[2 * size_t(P) + 2 * size_t(tb.G) + g];
 }
 
 // ------------------------------------------------------------------------------------------------

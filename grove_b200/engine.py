@@ -24,7 +24,7 @@ SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_load_nodes_device", "grove_cycle_begin",
-    "grove_round_eval", "grove_round_commit", "grove_round_apply", "grove_cycle_end",
+    "grove_round_eval", "grove_round_commit", "grove_round_apply", "grove_cycle_gather", "grove_cycle_end",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -124,6 +124,36 @@ class PlacementEngine:
     def run_cycle(self) -> dict:
         st = np.zeros(1, dtype=T.stats_dt)
         self._check(self.lib.grove_run_cycle(self.h, _p(st)))
+        return {k: st[k][0].item() for k in T.stats_dt.names}
+
+    # ---- stepping (multi-GPU hosts reduce the returned device buffers between the calls) ----
+    def cycle_begin(self):
+        self._check(self.lib.grove_cycle_begin(self.h))
+
+    def round_eval(self):
+        """-> (device pointer, int32 words, go)"""
+        p, n, go = C.c_void_p(), C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.grove_round_eval(self.h, C.byref(p), C.byref(n), C.byref(go)))
+        return p.value, n.value, bool(go.value)
+
+    def round_commit(self):
+        p, n = C.c_void_p(), C.c_uint32(0)
+        self._check(self.lib.grove_round_commit(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def round_apply(self) -> int:
+        r = C.c_uint32(0)
+        self._check(self.lib.grove_round_apply(self.h, C.byref(r)))
+        return r.value
+
+    def cycle_gather(self):
+        p, n = C.c_void_p(), C.c_uint32(0)
+        self._check(self.lib.grove_cycle_gather(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def cycle_end(self) -> dict:
+        st = np.zeros(1, dtype=T.stats_dt)
+        self._check(self.lib.grove_cycle_end(self.h, _p(st)))
         return {k: st[k][0].item() for k in T.stats_dt.names}
 
     # ---- outputs ----

@@ -187,15 +187,26 @@ int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint3
 /* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load */
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);
 
-/* ---- multi-GPU stepping: one handle per rank, gang rows sharded, node table replicated -------- */
-/* A sharded cycle is: begin; repeat { round_eval; <all-reduce MIN over claim words>;
- * round_commit; <all-reduce SUM over delta words>; round_apply } until remaining == 0; end.
- * Buffers are device pointers owned by the engine; the host (torch.distributed / NCCL) reduces
- * them in place between the calls.  With world <= 1 grove_run_cycle does all of this itself. */
+/* ---- multi-GPU stepping: one handle per rank (cfg.rank / cfg.world) -------------------------------
+ * Gang rows are dealt g % world to ranks; the node table and the gang states are replicated, so every
+ * rank takes the same decisions and the results are bit-identical for every world size.  The buffers
+ * returned are DEVICE pointers owned by the engine, int32 words; the host (torch.distributed / NCCL)
+ * reduces them in place across ranks between the calls:
+ *
+ *   grove_cycle_begin
+ *   loop: grove_round_eval(&claim,&n,&go); if (!go) break;      all-reduce MIN  over claim[n]
+ *         grove_round_commit(&delta,&m);                        all-reduce SUM  over delta[m]
+ *         grove_round_apply(&remaining);
+ *   grove_cycle_gather(&fin,&k);                                all-reduce SUM  over fin[k]
+ *   grove_cycle_end(&stats)
+ *
+ * Every call is synchronous (its kernels are complete on return).  With world <= 1 the same sequence
+ * is valid without any reduction, and grove_run_cycle is a faster fused form of it. */
 int32_t grove_cycle_begin(grove_engine_t* e);
-int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words);
+int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words, uint32_t* go);
 int32_t grove_round_commit(grove_engine_t* e, void** d_delta_words, uint32_t* n_delta_words);
-int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining_local);
+int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining);
+int32_t grove_cycle_gather(grove_engine_t* e, void** d_final_words, uint32_t* n_final_words);
 int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats);
 
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */

@@ -454,159 +454,270 @@ int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_cliqu
  *   first feasible domain); each successful gang claims its nodes with its order rank (min wins);
  *   a gang that holds every node it claimed commits, the others retry next round; a gang with no
  *   feasible domain is rejected for the cycle.
- * Outputs are in caller node indices.  out_fit/out_score (nullable) receive the round-1 rows of all
- * cliques in SORTED node order (row stride words = ceil(n/32) and n bytes).
+ *
+ * The cycle is written as steps over a shard context so that the multi-rank protocol (gang rows
+ * dealt g % world to ranks, node table and gang state replicated, claims reduced with MIN, commit
+ * deltas with SUM -- DESIGN.md section 7) can be exercised on CPU with gloo:
+ *   begin; repeat { eval -> [all-reduce MIN claim] -> commit -> [all-reduce SUM delta] -> apply }
+ *   until nothing is unresolved; gather -> [all-reduce SUM] -> end.
+ * oracle_run_cycle is the same steps with world = 1 and no reductions.
  */
-int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
-                         const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
-                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, int32_t threads,
-                         grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
-                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm,
-                         uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
+#define CLAIM_NONE 0x7F7F7F7F /* > any order rank (< 2^24), positive as int32 */
+
+typedef struct oshard {
+  ctx_t C;
+  uint32_t n, L, G, Q, S, P;
+  const grove_node_t* nodes_in;
+  uint32_t rank, world, max_rounds;
+  uint8_t* state; uint8_t* rnd;
+  spec_t* specs;
+  uint32_t* active; uint32_t na_local;
+  uint32_t round, unresolved;
+  uint64_t pairs;
+  double t0, t_eval;
+  uint32_t* out_fit; uint8_t* out_score;
+} oshard_t;
+
+static void shard_free(oshard_t* h) {
+  if (!h) return;
+  free(h->active); free(h->specs); free(h->rnd); free(h->state);
+  free(h->C.order); free(h->C.anchor); free(h->C.pod_off);
+  topo_free(&h->C.T);
+  free(h);
+}
+
+void oracle_shard_abort(oshard_t* h) { shard_free(h); }
+
+int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L, const grove_gang_t* gangs, uint32_t G,
+                           const grove_clique_t* cliques, uint32_t Q, const grove_scope_t* scopes, uint32_t S,
+                           uint32_t max_rounds, int32_t threads, uint32_t rank, uint32_t world,
+                           uint32_t* out_fit, uint8_t* out_score, oshard_t** out) {
   int32_t rc = oracle_validate(gangs, G, cliques, Q, scopes, S, L, n);
   if (rc != GROVE_OK) return rc;
-  if (n == 0 || n > GROVE_MAX_NODES) return GROVE_ERR_INVALID_ARG;
+  if (n == 0 || n > GROVE_MAX_NODES || !out) return GROVE_ERR_INVALID_ARG;
+  if (world == 0) world = 1;
+  if (rank >= world) return GROVE_ERR_INVALID_ARG;
 #ifdef _OPENMP
   if (threads > 0) omp_set_num_threads(threads);
 #endif
-  double t0 = now_s(), t_eval = 0;
-  ctx_t C; memset(&C, 0, sizeof(C));
-  if (topo_build(&C.T, nodes_in, n, L)) return GROVE_ERR_OOM;
-  C.G = G; C.Q = Q; C.S = S; C.gangs = gangs; C.cliques = cliques; C.scopes = scopes;
-  C.order = malloc(sizeof(uint32_t) * (G ? G : 1));
-  C.anchor = malloc(sizeof(uint32_t) * (G ? G : 1));
-  C.pod_off = malloc(sizeof(uint32_t) * (G + 1));
+  oshard_t* h = calloc(1, sizeof(oshard_t));
+  if (!h) return GROVE_ERR_OOM;
+  h->t0 = now_s();
+  if (topo_build(&h->C.T, nodes_in, n, L)) { shard_free(h); return GROVE_ERR_OOM; }
+  h->n = n; h->L = L; h->G = G; h->Q = Q; h->S = S; h->nodes_in = nodes_in;
+  h->rank = rank; h->world = world; h->max_rounds = max_rounds; h->out_fit = out_fit; h->out_score = out_score;
+  ctx_t* C = &h->C;
+  C->G = G; C->Q = Q; C->S = S; C->gangs = gangs; C->cliques = cliques; C->scopes = scopes;
+  C->order = malloc(sizeof(uint32_t) * (G ? G : 1));
+  C->anchor = malloc(sizeof(uint32_t) * (G ? G : 1));
+  C->pod_off = malloc(sizeof(uint32_t) * (G + 1));
   ord_t* ov = malloc(sizeof(ord_t) * (G ? G : 1));
   for (uint32_t g = 0; g < G; ++g) { ov[g].pr = gangs[g].priority; ov[g].g = g; }
   qsort(ov, G, sizeof(ord_t), cmp_ord);
-  for (uint32_t r = 0; r < G; ++r) C.order[ov[r].g] = r;
+  for (uint32_t r = 0; r < G; ++r) C->order[ov[r].g] = r;
   free(ov);
-  for (uint32_t g = 0; g < G; ++g)
-    C.anchor[g] = gangs[g].anchor_node != GROVE_NONE_U32 ? C.T.inv[gangs[g].anchor_node] : fmix32(g) % n;
-
-  uint8_t* state = calloc(G ? G : 1, 1);
-  uint8_t* rnd = calloc(G ? G : 1, 1);
-  spec_t* specs = calloc(G ? G : 1, sizeof(spec_t));
-  uint32_t* claim = malloc(sizeof(uint32_t) * n);
-  uint32_t words = (n + 31) / 32;
-  uint64_t pairs = 0;
-  uint32_t round = 0, unresolved = 0;
+  uint32_t po = 0;
   for (uint32_t g = 0; g < G; ++g) {
-    if (gangs[g].flags & GROVE_GANG_GATED) state[g] = GROVE_GANG_GATED_SKIP; else unresolved++;
+    C->anchor[g] = gangs[g].anchor_node != GROVE_NONE_U32 ? C->T.inv[gangs[g].anchor_node] : fmix32(g) % n;
+    C->pod_off[g] = po;
+    for (uint32_t c = 0; c < gangs[g].n_cliques; ++c) po += cliques[gangs[g].clique_off + c].replicas;
   }
-  uint32_t* active = malloc(sizeof(uint32_t) * (G ? G : 1));
-  while (unresolved > 0 && (max_rounds == 0 || round < max_rounds)) {
-    round++;
-    /* scaled gangs become active once their base gang is admitted (pod/syncflow.go:319-358) */
-    uint32_t na = 0;
-    int changed = 1;
-    while (changed) { /* propagate base rejections transitively */
-      changed = 0;
-      for (uint32_t g = 0; g < G; ++g) {
-        if (state[g] != GROVE_GANG_PENDING || gangs[g].base_gang == GROVE_NONE_U32) continue;
-        uint8_t bs = state[gangs[g].base_gang];
-        if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
-          state[g] = GROVE_GANG_BASE_REJECTED; rnd[g] = (uint8_t)(round > 255 ? 255 : round); unresolved--; changed = 1;
-        }
-      }
-    }
+  C->pod_off[G] = po; h->P = po;
+  h->state = calloc(G ? G : 1, 1);
+  h->rnd = calloc(G ? G : 1, 1);
+  h->specs = calloc(G ? G : 1, sizeof(spec_t));
+  h->active = malloc(sizeof(uint32_t) * (G ? G : 1));
+  for (uint32_t g = 0; g < G; ++g) {
+    if (gangs[g].flags & GROVE_GANG_GATED) h->state[g] = GROVE_GANG_GATED_SKIP; else h->unresolved++;
+  }
+  *out = h;
+  return GROVE_OK;
+}
+
+uint32_t oracle_shard_claim_words(const oshard_t* h) { return h->n; }
+uint32_t oracle_shard_delta_words(const oshard_t* h) { return 4 * h->n + h->G; }
+uint32_t oracle_shard_final_words(const oshard_t* h) { return 2 * h->P + 3 * h->G; }
+
+/* Step 1: decide who is active (replicated state => identical on every rank), evaluate this rank's
+ * share, write this rank's claims.  *go = 0 when the cycle is over (nothing was evaluated). */
+int32_t oracle_shard_eval(oshard_t* h, int32_t* claim, uint32_t* go) {
+  ctx_t* C = &h->C;
+  const grove_gang_t* gangs = C->gangs; const grove_clique_t* cliques = C->cliques; const grove_scope_t* scopes = C->scopes;
+  const uint32_t G = h->G, n = h->n;
+  *go = 0; h->na_local = 0;
+  if (h->unresolved == 0 || (h->max_rounds && h->round >= h->max_rounds)) return GROVE_OK;
+  h->round++;
+  const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
+  /* scaled gangs become active once their base gang is admitted (pod/syncflow.go:319-358) */
+  int changed = 1;
+  while (changed) { /* propagate base rejections transitively */
+    changed = 0;
     for (uint32_t g = 0; g < G; ++g) {
-      if (state[g] != GROVE_GANG_PENDING) continue;
-      if (gangs[g].base_gang != GROVE_NONE_U32 && state[gangs[g].base_gang] != GROVE_GANG_ADMITTED) continue;
-      active[na++] = g;
-    }
-    if (na == 0) { /* dependency cycle: nothing can ever become active */
-      for (uint32_t g = 0; g < G; ++g)
-        if (state[g] == GROVE_GANG_PENDING) { state[g] = GROVE_GANG_BASE_REJECTED; rnd[g] = (uint8_t)(round > 255 ? 255 : round); unresolved--; }
-      break;
-    }
-    double te0 = now_s();
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : pairs)
-    for (uint32_t ai = 0; ai < na; ++ai) {
-      uint32_t gi = active[ai];
-      const grove_gang_t* g = &gangs[gi];
-      uint8_t* Trow[GROVE_MAX_GANG_CLIQUES];
-      uint32_t* Frow = malloc(sizeof(uint32_t) * words);
-      for (uint32_t si = 0; si < g->n_scopes; ++si) {
-        const grove_scope_t* s = &scopes[g->scope_off + si];
-        for (uint32_t i = 0; i < s->n_cliques; ++i) {
-          uint32_t cr = s->first_clique + i;
-          const grove_clique_t* q = &cliques[g->clique_off + cr];
-          uint32_t ndp = need_depth(g, s, q);
-          Trow[cr] = malloc(n);
-          memset(Frow, 0, sizeof(uint32_t) * words);
-          /* K1: fit bitmap row */
-          for (uint32_t nn = 0; nn < n; ++nn)
-            if (fit(&C.T.nodes[nn], q, ndp)) Frow[nn >> 5] |= 1u << (nn & 31);
-          /* K2: score row = fit ? closeness + 1 : 0 */
-          for (uint32_t nn = 0; nn < n; ++nn)
-            Trow[cr][nn] = ((Frow[nn >> 5] >> (nn & 31)) & 1u) ? (uint8_t)(closeness(&C.T, nn, C.anchor[gi]) + 1) : 0;
-          pairs += n;
-          if (round == 1 && out_fit) memcpy(out_fit + (size_t)(g->clique_off + cr) * words, Frow, sizeof(uint32_t) * words);
-          if (round == 1 && out_score) memcpy(out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
-        }
+      if (h->state[g] != GROVE_GANG_PENDING || gangs[g].base_gang == GROVE_NONE_U32) continue;
+      uint8_t bs = h->state[gangs[g].base_gang];
+      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
+        h->state[g] = GROVE_GANG_BASE_REJECTED; h->rnd[g] = r8; h->unresolved--; changed = 1;
       }
-      eval_gang(&C, gi, Trow, &specs[gi]);
-      for (uint32_t cr = 0; cr < g->n_cliques; ++cr) free(Trow[cr]);
-      free(Frow);
-    }
-    t_eval += now_s() - te0;
-    /* claims: lowest order rank wins each node */
-    for (uint32_t i = 0; i < n; ++i) claim[i] = GROVE_NONE_U32;
-    for (uint32_t ai = 0; ai < na; ++ai) {
-      uint32_t gi = active[ai];
-      if (!specs[gi].ok) continue;
-      for (uint32_t i = 0; i < specs[gi].n_entries; ++i) {
-        uint32_t nd = specs[gi].e[i].node;
-        if (C.order[gi] < claim[nd]) claim[nd] = C.order[gi];
-      }
-    }
-    for (uint32_t ai = 0; ai < na; ++ai) {
-      uint32_t gi = active[ai];
-      uint8_t r8 = (uint8_t)(round > 255 ? 255 : round);
-      if (!specs[gi].ok) { state[gi] = GROVE_GANG_REJECTED; rnd[gi] = r8; unresolved--; continue; }
-      int win = 1;
-      for (uint32_t i = 0; i < specs[gi].n_entries && win; ++i) win = claim[specs[gi].e[i].node] == C.order[gi];
-      if (!win) continue;
-      for (uint32_t i = 0; i < specs[gi].n_entries; ++i) {
-        grove_node_t* nd = &C.T.nodes[specs[gi].e[i].node];
-        const grove_clique_t* q = &cliques[gangs[gi].clique_off + specs[gi].e[i].clique_rel];
-        nd->free_cpu_milli -= q->req_cpu_milli; nd->free_mem_mib -= q->req_mem_mib;
-        nd->free_gpu -= q->req_gpu; nd->free_pods -= 1;
-      }
-      state[gi] = GROVE_GANG_ADMITTED; rnd[gi] = r8; unresolved--;
     }
   }
-  /* outputs */
+  uint32_t na_global = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    if (h->state[g] != GROVE_GANG_PENDING) continue;
+    if (gangs[g].base_gang != GROVE_NONE_U32 && h->state[gangs[g].base_gang] != GROVE_GANG_ADMITTED) continue;
+    na_global++;
+    if (g % h->world == h->rank) h->active[h->na_local++] = g;
+  }
+  if (na_global == 0) { /* dependency cycle: nothing can ever become active */
+    for (uint32_t g = 0; g < G; ++g)
+      if (h->state[g] == GROVE_GANG_PENDING) { h->state[g] = GROVE_GANG_BASE_REJECTED; h->rnd[g] = r8; h->unresolved--; }
+    return GROVE_OK;
+  }
+  *go = 1;
+  const uint32_t words = (n + 31) / 32;
+  uint64_t pairs = 0;
+  double te0 = now_s();
+  const uint32_t na = h->na_local;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : pairs)
+  for (uint32_t ai = 0; ai < na; ++ai) {
+    uint32_t gi = h->active[ai];
+    const grove_gang_t* g = &gangs[gi];
+    uint8_t* Trow[GROVE_MAX_GANG_CLIQUES];
+    uint32_t* Frow = malloc(sizeof(uint32_t) * words);
+    for (uint32_t si = 0; si < g->n_scopes; ++si) {
+      const grove_scope_t* s = &scopes[g->scope_off + si];
+      for (uint32_t i = 0; i < s->n_cliques; ++i) {
+        uint32_t cr = s->first_clique + i;
+        const grove_clique_t* q = &cliques[g->clique_off + cr];
+        uint32_t ndp = need_depth(g, s, q);
+        Trow[cr] = malloc(n);
+        memset(Frow, 0, sizeof(uint32_t) * words);
+        /* K1: fit bitmap row */
+        for (uint32_t nn = 0; nn < n; ++nn)
+          if (fit(&C->T.nodes[nn], q, ndp)) Frow[nn >> 5] |= 1u << (nn & 31);
+        /* K2: score row = fit ? closeness + 1 : 0 */
+        for (uint32_t nn = 0; nn < n; ++nn)
+          Trow[cr][nn] = ((Frow[nn >> 5] >> (nn & 31)) & 1u) ? (uint8_t)(closeness(&C->T, nn, C->anchor[gi]) + 1) : 0;
+        pairs += n;
+        if (h->round == 1 && h->out_fit) memcpy(h->out_fit + (size_t)(g->clique_off + cr) * words, Frow, sizeof(uint32_t) * words);
+        if (h->round == 1 && h->out_score) memcpy(h->out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
+      }
+    }
+    eval_gang(C, gi, Trow, &h->specs[gi]);
+    for (uint32_t cr = 0; cr < g->n_cliques; ++cr) free(Trow[cr]);
+    free(Frow);
+  }
+  h->pairs += pairs;
+  h->t_eval += now_s() - te0;
+  /* claims: lowest order rank wins each node */
+  for (uint32_t i = 0; i < n; ++i) claim[i] = CLAIM_NONE;
+  for (uint32_t ai = 0; ai < na; ++ai) {
+    uint32_t gi = h->active[ai];
+    if (!h->specs[gi].ok) continue;
+    for (uint32_t i = 0; i < h->specs[gi].n_entries; ++i) {
+      uint32_t nd = h->specs[gi].e[i].node;
+      if ((int32_t)C->order[gi] < claim[nd]) claim[nd] = (int32_t)C->order[gi];
+    }
+  }
+  return GROVE_OK;
+}
+
+/* Step 2 (claims reduced over ranks): this rank's winners -> resource deltas per node and new gang states */
+int32_t oracle_shard_commit(oshard_t* h, const int32_t* claim, int32_t* delta) {
+  ctx_t* C = &h->C;
+  const uint32_t n = h->n;
+  memset(delta, 0, sizeof(int32_t) * (4 * (size_t)n + h->G));
+  for (uint32_t ai = 0; ai < h->na_local; ++ai) {
+    uint32_t gi = h->active[ai];
+    if (!h->specs[gi].ok) { delta[4 * (size_t)n + gi] = GROVE_GANG_REJECTED; continue; }
+    int win = 1;
+    for (uint32_t i = 0; i < h->specs[gi].n_entries && win; ++i) win = claim[h->specs[gi].e[i].node] == (int32_t)C->order[gi];
+    if (!win) continue;
+    for (uint32_t i = 0; i < h->specs[gi].n_entries; ++i) {
+      uint32_t nd = h->specs[gi].e[i].node;
+      const grove_clique_t* q = &C->cliques[C->gangs[gi].clique_off + h->specs[gi].e[i].clique_rel];
+      delta[4 * (size_t)nd + 0] += (int32_t)q->req_cpu_milli; delta[4 * (size_t)nd + 1] += (int32_t)q->req_mem_mib;
+      delta[4 * (size_t)nd + 2] += (int32_t)q->req_gpu; delta[4 * (size_t)nd + 3] += 1;
+    }
+    delta[4 * (size_t)n + gi] = GROVE_GANG_ADMITTED;
+  }
+  return GROVE_OK;
+}
+
+/* Step 3 (deltas reduced over ranks): every rank applies the same commits */
+int32_t oracle_shard_apply(oshard_t* h, const int32_t* delta, uint32_t* remaining) {
+  ctx_t* C = &h->C;
+  const uint32_t n = h->n;
+  const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
+  for (uint32_t i = 0; i < n; ++i) {
+    grove_node_t* nd = &C->T.nodes[i];
+    nd->free_cpu_milli -= (uint32_t)delta[4 * (size_t)i + 0]; nd->free_mem_mib -= (uint32_t)delta[4 * (size_t)i + 1];
+    nd->free_gpu = (uint16_t)(nd->free_gpu - (uint32_t)delta[4 * (size_t)i + 2]);
+    nd->free_pods = (uint16_t)(nd->free_pods - (uint32_t)delta[4 * (size_t)i + 3]);
+  }
+  for (uint32_t g = 0; g < h->G; ++g) {
+    int32_t s = delta[4 * (size_t)n + g];
+    if (s) { h->state[g] = (uint8_t)s; h->rnd[g] = r8; h->unresolved--; }
+  }
+  if (remaining) *remaining = h->unresolved;
+  return GROVE_OK;
+}
+
+/* Step 4: placements of the gangs this rank admitted, for the final exchange (zeros elsewhere) */
+int32_t oracle_shard_gather(oshard_t* h, int32_t* fin) {
+  const uint32_t P = h->P, G = h->G;
+  memset(fin, 0, sizeof(int32_t) * (2 * (size_t)P + 3 * (size_t)G));
+  for (uint32_t g = 0; g < G; ++g) {
+    if (h->state[g] != GROVE_GANG_ADMITTED || g % h->world != h->rank) continue;
+    const spec_t* sp = &h->specs[g];
+    for (uint32_t i = 0; i < sp->n_entries; ++i) {
+      fin[h->C.pod_off[g] + i] = (int32_t)sp->e[i].node;
+      fin[P + h->C.pod_off[g] + i] = (int32_t)((uint32_t)sp->e[i].clique_rel | ((uint32_t)sp->e[i].score << 8));
+    }
+    fin[2 * (size_t)P + g] = (int32_t)sp->n_entries;
+    fin[2 * (size_t)P + G + g] = (int32_t)sp->min_score;
+    fin[2 * (size_t)P + 2 * (size_t)G + g] = (int32_t)sp->top_lo;
+  }
+  return GROVE_OK;
+}
+
+/* Step 5 (final words reduced over ranks): outputs in caller node indices; frees the context */
+int32_t oracle_shard_end(oshard_t* h, const int32_t* fin, grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
+                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm, oracle_stats_t* stats) {
+  ctx_t* C = &h->C;
+  const uint32_t P = h->P, G = h->G, n = h->n;
   uint32_t np = 0, adm = 0, rej = 0;
   for (uint32_t g = 0; g < G; ++g) {
     grove_gang_status_t st; memset(&st, 0, sizeof(st));
-    st.state = state[g]; st.round = rnd[g]; st.top_domain_lo = GROVE_NONE_U32; st.placement_off = np;
-    if (state[g] == GROVE_GANG_ADMITTED) {
+    st.state = h->state[g]; st.round = h->rnd[g]; st.top_domain_lo = GROVE_NONE_U32; st.placement_off = np;
+    if (h->state[g] == GROVE_GANG_ADMITTED) {
       adm++;
-      st.score_num = specs[g].min_score; st.score_den = (uint8_t)(L + 1);
-      st.n_pods = specs[g].n_entries; st.top_domain_lo = specs[g].top_lo;
-      for (uint32_t i = 0; i < specs[g].n_entries; ++i) {
-        if (out_pl && np < cap_pl) { out_pl[np].clique = gangs[g].clique_off + specs[g].e[i].clique_rel; out_pl[np].node = C.T.perm[specs[g].e[i].node]; }
+      uint32_t cnt = (uint32_t)fin[2 * (size_t)P + g];
+      st.score_num = (uint8_t)fin[2 * (size_t)P + G + g]; st.score_den = (uint8_t)(h->L + 1);
+      st.n_pods = cnt; st.top_domain_lo = (uint32_t)fin[2 * (size_t)P + 2 * (size_t)G + g];
+      for (uint32_t i = 0; i < cnt; ++i) {
+        if (out_pl && np < cap_pl) {
+          out_pl[np].clique = C->gangs[g].clique_off + ((uint32_t)fin[P + C->pod_off[g] + i] & 0xFFu);
+          out_pl[np].node = C->T.perm[(uint32_t)fin[C->pod_off[g] + i]];
+        }
         np++;
       }
-    } else if (state[g] == GROVE_GANG_REJECTED || state[g] == GROVE_GANG_BASE_REJECTED) rej++;
+    } else if (h->state[g] == GROVE_GANG_REJECTED || h->state[g] == GROVE_GANG_BASE_REJECTED) rej++;
     if (out_status) out_status[g] = st;
   }
   if (n_pl) *n_pl = np;
   if (out_nodes)
     for (uint32_t i = 0; i < n; ++i) {
-      grove_node_t nd = nodes_in[C.T.perm[i]];
-      nd.free_cpu_milli = C.T.nodes[i].free_cpu_milli; nd.free_mem_mib = C.T.nodes[i].free_mem_mib;
-      nd.free_gpu = C.T.nodes[i].free_gpu; nd.free_pods = C.T.nodes[i].free_pods;
-      out_nodes[C.T.perm[i]] = nd;
+      grove_node_t nd = h->nodes_in[C->T.perm[i]];
+      nd.free_cpu_milli = C->T.nodes[i].free_cpu_milli; nd.free_mem_mib = C->T.nodes[i].free_mem_mib;
+      nd.free_gpu = C->T.nodes[i].free_gpu; nd.free_pods = C->T.nodes[i].free_pods;
+      out_nodes[C->T.perm[i]] = nd;
     }
-  if (out_perm) memcpy(out_perm, C.T.perm, sizeof(uint32_t) * n);
+  if (out_perm) memcpy(out_perm, C->T.perm, sizeof(uint32_t) * n);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->rounds = round; stats->gangs_admitted = adm; stats->gangs_rejected = rej; stats->pods_bound = np;
-    stats->pairs_evaluated = pairs; stats->seconds_eval = t_eval; stats->seconds_total = now_s() - t0;
-    stats->non_tree_labels = C.T.non_tree;
+    stats->rounds = h->round; stats->gangs_admitted = adm; stats->gangs_rejected = rej; stats->pods_bound = np;
+    stats->pairs_evaluated = h->pairs; stats->seconds_eval = h->t_eval; stats->seconds_total = now_s() - h->t0;
+    stats->non_tree_labels = C->T.non_tree;
 #ifdef _OPENMP
     stats->threads = (uint32_t)omp_get_max_threads();
 #else
@@ -614,10 +725,36 @@ int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
 #endif
   }
   int32_t ret = (out_pl && np > cap_pl) ? GROVE_ERR_LIMIT : GROVE_OK;
-  free(active); free(claim); free(specs); free(rnd); free(state);
-  free(C.order); free(C.anchor); free(C.pod_off);
-  topo_free(&C.T);
+  shard_free(h);
   return ret;
+}
+
+/* Outputs are in caller node indices.  out_fit/out_score (nullable) receive the round-1 rows of all
+ * cliques in SORTED node order (row stride words = ceil(n/32) and n bytes). */
+int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
+                         const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, int32_t threads,
+                         grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
+                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm,
+                         uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
+  oshard_t* h = NULL;
+  int32_t rc = oracle_shard_begin(nodes_in, n, L, gangs, G, cliques, Q, scopes, S, max_rounds, threads, 0, 1, out_fit, out_score, &h);
+  if (rc != GROVE_OK) return rc;
+  int32_t* claim = malloc(sizeof(int32_t) * n);
+  int32_t* delta = malloc(sizeof(int32_t) * (4 * (size_t)n + G));
+  int32_t* fin = malloc(sizeof(int32_t) * (2 * (size_t)h->P + 3 * (size_t)G + 1));
+  if (!claim || !delta || !fin) { free(claim); free(delta); free(fin); shard_free(h); return GROVE_ERR_OOM; }
+  for (;;) {
+    uint32_t go = 0;
+    oracle_shard_eval(h, claim, &go);
+    if (!go) break;
+    oracle_shard_commit(h, claim, delta);
+    oracle_shard_apply(h, delta, NULL);
+  }
+  oracle_shard_gather(h, fin);
+  rc = oracle_shard_end(h, fin, out_pl, cap_pl, n_pl, out_status, out_nodes, out_perm, stats);
+  free(claim); free(delta); free(fin);
+  return rc;
 }
 
 /* topology preprocessing alone, for tests of the engine's host-side sort: perm + tree-ified dom ids */

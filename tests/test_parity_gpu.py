@@ -61,3 +61,139 @@ def test_c4_reduced(built_lib, oracle):
     ref = oracle.run_cycle(c["nodes"], c["n_levels"], g, cl, sc, threads=8)
     gpu = _run_engine(c["nodes"], c["n_levels"], c["tables"])
     assert_same(gpu, ref)
+
+
+class _LocalGroup:
+    """stand-in for torch.distributed inside one process: reduces the buffers of several engines that
+    live on the same GPU (the sharded protocol without NCCL)."""
+
+    class ReduceOp:
+        MIN, SUM = "min", "sum"
+
+
+def _run_sharded_local(nodes, L, tabs, world):
+    import torch
+    from grove_b200.engine import PlacementEngine
+    from grove_b200.sharded import as_tensor
+    g, c, s = tabs
+    engs = [PlacementEngine(L, rank=r, world=world) for r in range(world)]
+    try:
+        for e in engs:
+            e.load_nodes(nodes); e.submit_gangs(g, c, s); e.cycle_begin()
+
+        def reduce(bufs, op):
+            ts = [as_tensor(p, n) for p, n in bufs]
+            if not ts or ts[0].numel() == 0:
+                return
+            acc = ts[0].clone()
+            for t in ts[1:]:
+                acc = torch.minimum(acc, t) if op == "min" else acc + t
+            for t in ts:
+                t.copy_(acc)
+            torch.cuda.synchronize()
+
+        while True:
+            ev = [e.round_eval() for e in engs]
+            gos = {go for _, _, go in ev}
+            assert len(gos) == 1  # replicated state: every rank takes the same decision
+            if not gos.pop():
+                break
+            reduce([(p, n) for p, n, _ in ev], "min")
+            reduce([e.round_commit() for e in engs], "sum")
+            rem = {e.round_apply() for e in engs}
+            assert len(rem) == 1
+        reduce([e.cycle_gather() for e in engs], "sum")
+        outs = []
+        for e in engs:
+            st = e.cycle_end()
+            outs.append(dict(stats=st, placements=e.placements(), status=e.gang_status(), nodes_after=e.nodes(), perm=e.debug_perm()))
+        return outs
+    finally:
+        for e in engs:
+            e.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_engine_is_world_size_invariant(built_lib, oracle, world):
+    c = synth.config_c4(n=5040, g=1000)
+    g, cl, sc = c["tables"]
+    ref = oracle.run_cycle(c["nodes"], c["n_levels"], g, cl, sc, threads=8)
+    for out in _run_sharded_local(c["nodes"], c["n_levels"], c["tables"], world):
+        assert_same(out, ref)
+
+
+def test_update_nodes_and_second_cycle(built_lib, oracle):
+    """churn: after a cycle, free some nodes through grove_update_nodes and run the next cycle on the
+    committed state; the oracle follows with the same inputs."""
+    from grove_b200.engine import PlacementEngine
+    c = synth.config_c3(n=756, g=150)
+    g, cl, sc = c["tables"]
+    with PlacementEngine(c["n_levels"]) as e:
+        e.load_nodes(c["nodes"]); e.submit_gangs(g, cl, sc)
+        e.run_cycle()
+        after = e.nodes()
+        ref1 = oracle.run_cycle(c["nodes"], c["n_levels"], g, cl, sc)
+        assert np.array_equal(after, ref1["nodes_after"])
+        idx = np.arange(0, 756, 7, dtype=np.uint32)
+        recs = c["nodes"][idx].copy()  # these nodes drained back to their initial free state
+        e.update_nodes(idx, recs)
+        state2 = after.copy(); state2[idx] = recs
+        assert np.array_equal(e.nodes(), state2)
+        e.submit_gangs(g, cl, sc)
+        e.run_cycle()
+        ref2 = oracle.run_cycle(state2, c["n_levels"], g, cl, sc)
+        assert np.array_equal(e.placements(), ref2["placements"])
+        assert np.array_equal(e.gang_status(), ref2["status"])
+        assert np.array_equal(e.nodes(), ref2["nodes_after"])
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE.json's full C4 size, through size-independent properties (no oracle needed):
+    no node is over-committed, every admitted gang has all its MinReplicas, every scope's pods share its
+    Required domain, rejected gangs bound nothing, and resources are conserved."""
+    from grove_b200.engine import PlacementEngine
+    c = synth.config_c4()
+    g, cl, sc = c["tables"]
+    nodes = c["nodes"]
+    with PlacementEngine(c["n_levels"]) as e:
+        e.load_nodes(nodes); e.submit_gangs(g, cl, sc)
+        st = e.run_cycle()
+        pl, gs, after = e.placements(), e.gang_status(), e.nodes()
+    assert st["gangs_admitted"] + st["gangs_rejected"] == len(g)
+    # conservation: free_before - free_after == sum of requests bound per node
+    for f, req in (("free_cpu_milli", "req_cpu_milli"), ("free_mem_mib", "req_mem_mib"), ("free_gpu", "req_gpu")):
+        used = np.bincount(pl["node"], weights=cl[req][pl["clique"]].astype(np.float64), minlength=len(nodes))
+        assert np.array_equal(nodes[f].astype(np.int64) - after[f].astype(np.int64), used.astype(np.int64)), f
+    pods = np.bincount(pl["node"], minlength=len(nodes))
+    assert np.array_equal(nodes["free_pods"].astype(np.int64) - after["free_pods"].astype(np.int64), pods)
+    assert (after["free_cpu_milli"] <= nodes["free_cpu_milli"]).all() and (after["free_gpu"] <= nodes["free_gpu"]).all()
+    assert (nodes["flags"][pl["node"]] & T.NODE_SCHEDULABLE).all()
+    cls = (nodes["flags"][pl["node"]] >> T.NODE_CLASS_SHIFT) & 0xF
+    assert ((cl["class_mask"][pl["clique"]] >> cls) & 1).all()
+    per_clique = np.bincount(pl["clique"], minlength=len(cl))
+    clique_gang = np.repeat(np.arange(len(g)), g["n_cliques"])
+    adm = gs["state"][clique_gang] == T.GANG_ADMITTED
+    assert (per_clique[adm] >= cl["min_replicas"][adm]).all() and (per_clique[adm] <= cl["replicas"][adm]).all()
+    assert (per_clique[~adm] == 0).all()
+    # Required domains: gang -> block (level 1), scaling-group scope -> rack (2), leader -> host (3)
+    dom = nodes["dom"][pl["node"]]
+    gang_of = clique_gang[pl["clique"]]
+    for lvl_field, lvl_src, key in (("gang", g["level"][gang_of], gang_of),):
+        lv = lvl_src.astype(np.int64)
+        sel = lv != T.LEVEL_NONE
+        val = dom[np.arange(len(pl)), np.where(sel, lv, 0)]
+        first = {}
+        for k, v, ok in zip(key.tolist(), val.tolist(), sel.tolist()):
+            if ok:
+                assert first.setdefault(k, v) == v
+    scope_id = np.repeat(np.arange(len(sc)), sc["n_cliques"])  # scopes tile the clique table in order
+    lv = sc["level"][scope_id[pl["clique"]]].astype(np.int64)
+    first = {}
+    for k, l, row in zip(scope_id[pl["clique"]].tolist(), lv.tolist(), dom.tolist()):
+        if l != T.LEVEL_NONE:
+            assert first.setdefault(k, row[l]) == row[l]
+    lv = cl["level"][pl["clique"]].astype(np.int64)
+    first = {}
+    for k, l, row in zip(pl["clique"].tolist(), lv.tolist(), dom.tolist()):
+        if l != T.LEVEL_NONE:
+            assert first.setdefault(k, row[l]) == row[l]
