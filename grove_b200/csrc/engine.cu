@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -101,7 +102,12 @@ struct grove_engine {
   DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
   DevBuf<grove_gang_status_t> d_status;
   DevBuf<grove_placement_t> d_out;
-  DevBuf<uint32_t> d_delta, d_final;
+  DevBuf<uint32_t> d_delta, d_final, d_capsum, d_capmax;
+  DevBuf<uint8_t> d_cap8;
+  uint32_t cap_off[GROVE_MAX_LEVELS]{}, cap_stride = 0;
+  bool prefilter = false;
+  int tune_prefilter = 1;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
+  uint32_t tune_width0 = 32;
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
   PinBuf<uint32_t> h_counters;
@@ -180,6 +186,11 @@ static int32_t build_topology(grove_engine* e, const grove_node_t* nodes, uint32
     for (uint32_t d = 0; d < e->n_dom[l] && u; ++d) u = (e->dom_hi[l][d] - e->dom_lo[l][d]) == 1;
     e->unit[l] = u ? 1u : 0u;
   }
+  e->cap_stride = 0;
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+    e->cap_off[l] = e->cap_stride;
+    if (l < L && !e->unit[l]) e->cap_stride += e->n_dom[l];
+  }
   // upload static tables
   CU_TRY(e, e->d_perm.ensure(n)); CU_TRY(e, e->d_inv.ensure(n));
   CU_TRY(e, e->d_ndom.ensure(e->Npad)); CU_TRY(e, e->d_nres.ensure(e->Npad)); CU_TRY(e, e->d_vdepth.ensure(e->Npad));
@@ -215,6 +226,8 @@ static Topo make_topo(grove_engine* e) {
     t.n_dom[l] = e->n_dom[l]; t.unit[l] = e->unit[l];
   }
   t.n = e->N; t.npad = e->Npad; t.L = e->L; t.words = e->words;
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) t.cap_off[l] = e->cap_off[l];
+  t.cap_stride = e->cap_stride;
   return t;
 }
 
@@ -231,7 +244,9 @@ static RoundBufs make_bufs(grove_engine* e) {
   r.counters = e->d_counters.p; r.spec_ok = e->d_spec_ok.p; r.spec_score = e->d_spec_score.p;
   r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
   r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
-  r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p; r.cand = nullptr; r.cand_words = 0;
+  r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
+  r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
+  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0;
   return r;
 }
 
@@ -255,6 +270,8 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   grove_engine* e = new (std::nothrow) grove_engine();
   if (!e) return GROVE_ERR_OOM;
   e->cfg = *cfg; e->L = cfg->n_levels;
+  if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
+  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = std::min(32, std::max(1, std::atoi(v)));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
@@ -486,6 +503,14 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
       return fail(e, GROVE_ERR_OOM, "fit/score matrices do not fit in device memory");
     }
   }
+  // capacity tables for the candidate pre-filter: worth building only while signatures are few
+  e->prefilter = false;
+  if (e->tune_prefilter && e->n_sigs && uint64_t(e->n_sigs) * e->Npad <= (64ull << 20) && e->cap_stride > 0) {
+    const size_t tw = size_t(e->n_sigs) * e->cap_stride;
+    if (e->d_cap8.ensure(size_t(e->n_sigs) * e->Npad) == cudaSuccess && e->d_capsum.ensure(tw) == cudaSuccess &&
+        e->d_capmax.ensure(tw) == cudaSuccess) e->prefilter = true;
+    else (void)cudaGetLastError();
+  }
   // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
   std::vector<uint8_t> st(G, GROVE_GANG_PENDING);
   for (uint32_t g = 0; g < G; ++g) if (e->gangs[g].flags & GROVE_GANG_GATED) st[g] = GROVE_GANG_GATED_SKIP;
@@ -503,7 +528,8 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
 static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
   const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
   e->round_no++;
-  k_prepare<<<1, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
+  CU_TRY(e, cudaMemsetAsync(e->d_counters.p, 0, sizeof(uint32_t) * 8, e->stream));
+  k_prepare<<<(e->G + 1023) / 1024, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
   CU_TRY(e, cudaGetLastError());
   CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -514,6 +540,11 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
   const uint32_t ns = e->h_counters.p[4];
   dim3 gfit(e->Npad / 1024, std::min<uint32_t>((ns + kFitTile - 1) / kFitTile, 65535u));
   k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
+  if (e->prefilter && ns) {
+    k_cap8<<<dim3(e->Npad / 256, ns), 256, 0, e->stream>>>(tp, tb, rb, e->d_cap8.p);
+    k_capsum<<<dim3((e->cap_stride * 32 + 255) / 256, ns), 256, 0, e->stream>>>(tp, rb, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+    e->launches += 2;
+  }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
   {
     const uint32_t cpr = e->Npad >> 4;

@@ -44,6 +44,8 @@ struct Topo {
   uint32_t n_dom[GROVE_MAX_LEVELS];
   uint32_t unit[GROVE_MAX_LEVELS];             // every domain of the level is a single node
   uint32_t n, npad, L, words;                  // words = npad / 32 (row stride of the fit bitmap)
+  uint32_t cap_off[GROVE_MAX_LEVELS];          // column offset of level l in a capacity-table row (non-unit levels)
+  uint32_t cap_stride;                         // columns per signature row = sum of n_dom over non-unit levels
 };
 
 struct Tables {
@@ -74,8 +76,11 @@ struct RoundBufs {
   uint32_t* claim;       // [n]
   uint32_t* F;           // [S][words] fit bitmap, one row per signature
   uint8_t* T;            // [Q][npad]
-  uint32_t* cand;        // [G][cand_words] necessary-condition bits over gang-level domains
-  uint32_t cand_words;
+  const uint8_t* cap8;   // [S][npad] pods of the signature that fit on the node now (saturating), or null
+  const uint32_t* capsum; // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
+  const uint32_t* capmax; // [S][cap_stride] per-domain max of cap8
+  uint32_t caps_in_attempts;  // 1: the scalar evaluator packs from cap8 bytes, 0: from fit words + node records
+  uint32_t width0;            // candidates attempted in the very first step of a gang (1..32)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -128,70 +133,66 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
   return v;
 }
 
-// single CTA of 1024 threads
+// grid of 1024-thread CTAs over the gangs; counters must be zeroed before the launch.
+// Order inside active[] / rows[] depends on CTA arrival order; no result depends on it.
 __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint32_t round_no, uint32_t rank, uint32_t world) {
-  __shared__ int s_changed;
   __shared__ uint32_t s_warp_a[32], s_warp_r[32];
-  __shared__ uint32_t s_na, s_nr, s_unres, s_tot_a, s_tot_r, s_prop, s_glob;
+  __shared__ uint32_t s_base_a, s_base_r;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
-  // scaled gangs of a rejected / skipped base gang are rejected with it (transitively)
-  if (tid == 0) s_prop = 0;
-  do {
-    __syncthreads();
-    if (tid == 0) s_changed = 0;
-    __syncthreads();
-    for (uint32_t g = tid; g < tb.G; g += 1024) {
-      if (rb.state[g] != GROVE_GANG_PENDING) continue;
-      uint32_t b = tb.gangs[g].base_gang;
-      if (b == GROVE_NONE_U32) continue;
-      uint8_t bs = rb.state[b];
-      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
-        rb.state[g] = GROVE_GANG_BASE_REJECTED; rb.round[g] = r8; s_changed = 1; s_prop = 1;
-      }
+  const uint32_t g = blockIdx.x * 1024 + tid;
+  uint32_t act = 0, ncl = 0, unres = 0, coff = 0, ready = 0, prop = 0;
+  if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
+    const grove_gang_t gg = tb.gangs[g];
+    // walk the base chain: a scaled gang is rejected with any rejected / skipped ancestor (transitively),
+    // and is ready once its direct base gang is admitted (pod/syncflow.go:319-358)
+    bool dead = false;
+    uint32_t b = gg.base_gang;
+    for (int hop = 0; hop < 64 && b != GROVE_NONE_U32; ++hop) {
+      const uint8_t bs = rb.state[b];
+      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) { dead = true; break; }
+      if (bs == GROVE_GANG_ADMITTED) break;
+      b = tb.gangs[b].base_gang;
     }
-    __syncthreads();
-  } while (s_changed);
-  if (tid == 0) { s_na = 0; s_nr = 0; s_unres = 0; s_glob = 0; rb.counters[4] = 0; }
-  __syncthreads();
-  for (uint32_t base = 0; base < tb.G; base += 1024) {
-    uint32_t g = base + tid;
-    uint32_t act = 0, ncl = 0, unres = 0, coff = 0;
-    if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
+    if (dead) {
+      rb.state[g] = GROVE_GANG_BASE_REJECTED; rb.round[g] = r8; prop = 1;
+    } else {
       unres = 1;
-      grove_gang_t gg = tb.gangs[g];
-      bool ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
-      bool mine = world <= 1 || (g % world) == rank;
-      if (ready) atomicAdd(&s_glob, 1u);
+      ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
+      const bool mine = world <= 1 || (g % world) == rank;
       if (ready && mine) { act = 1; ncl = gg.n_cliques; coff = gg.clique_off; }
     }
-    uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
-    uint32_t un = __popc(__ballot_sync(kFull, unres));
-    if (lane == 31) { s_warp_a[warp] = ia; s_warp_r[warp] = ir; }
-    if (lane == 0 && un) atomicAdd(&s_unres, un);
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t va = s_warp_a[lane], vr = s_warp_r[lane];
-      uint32_t sa = warp_incl_scan(va, lane), sr = warp_incl_scan(vr, lane);
-      s_warp_a[lane] = sa - va; s_warp_r[lane] = sr - vr;  // exclusive per-warp offsets
-      if (lane == 31) { s_tot_a = sa; s_tot_r = sr; }
-    }
-    __syncthreads();
-    uint32_t oa = s_na + s_warp_a[warp] + ia - act;
-    uint32_t orr = s_nr + s_warp_r[warp] + ir - ncl;
-    if (act) {
-      rb.active[oa] = g;
-      for (uint32_t i = 0; i < ncl; ++i) {
-        rb.rows[orr + i] = coff + i;
-        const uint32_t sg = tb.cinfo[coff + i].sig;
-        if (atomicExch(rb.sig_stamp + sg, round_no) != round_no) rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) { s_na += s_tot_a; s_nr += s_tot_r; }
-    __syncthreads();
   }
-  if (tid == 0) { rb.counters[0] = s_na; rb.counters[1] = s_nr; rb.counters[2] = s_unres; rb.counters[3] = s_prop; rb.counters[5] = s_glob; rb.counters[6] = 0; }
+  const uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
+  const uint32_t un = __popc(__ballot_sync(kFull, unres)), rd = __popc(__ballot_sync(kFull, ready));
+  const uint32_t pr = __ballot_sync(kFull, prop);
+  if (lane == 31) { s_warp_a[warp] = ia; s_warp_r[warp] = ir; }
+  if (lane == 0) {
+    if (un) atomicAdd(rb.counters + 2, un);
+    if (rd) atomicAdd(rb.counters + 5, rd);
+    if (pr) atomicOr(rb.counters + 3, 1u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t va = s_warp_a[lane], vr = s_warp_r[lane];
+    const uint32_t sa = warp_incl_scan(va, lane), sr = warp_incl_scan(vr, lane);
+    s_warp_a[lane] = sa - va; s_warp_r[lane] = sr - vr;  // exclusive per-warp offsets
+    if (lane == 31) {
+      s_base_a = sa ? atomicAdd(rb.counters + 0, sa) : 0u;
+      s_base_r = sr ? atomicAdd(rb.counters + 1, sr) : 0u;
+    }
+  }
+  __syncthreads();
+  if (act) {
+    const uint32_t oa = s_base_a + s_warp_a[warp] + ia - act;
+    const uint32_t orr = s_base_r + s_warp_r[warp] + ir - ncl;
+    rb.active[oa] = g;
+    for (uint32_t i = 0; i < ncl; ++i) {
+      rb.rows[orr + i] = coff + i;
+      const uint32_t sg = tb.cinfo[coff + i].sig;
+      if (atomicExch(rb.sig_stamp + sg, round_no) != round_no) rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
+    }
+  }
 }
 
 // dependency cycle or unreachable base: nothing can become active any more
@@ -242,6 +243,50 @@ __global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) 
     __syncthreads();
     for (int c = warp; c < cnt; c += 32) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Capacity tables for K3's candidate pre-filter (only built while the active signatures are few):
+// cap8[sig][n] = whole pods of the signature that fit on node n (0 if unfit, saturating at 255) and
+// its per-domain sum / max.  "sum over the fill domain >= MinReplicas" is a necessary condition for a
+// clique to be packable there, so domains failing it can be skipped without changing any result.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cap8(Topo tp, Tables tb, RoundBufs rb, uint8_t* cap8) {
+  const uint32_t sg = rb.sig_list[blockIdx.y];
+  const uint32_t n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= tp.npad) return;
+  uint32_t c = 0;
+  if ((__ldg(rb.F + size_t(sg) * tp.words + (n >> 5)) >> (n & 31)) & 1u) {
+    const uint4 r = __ldg(tp.nres + n);
+    const uint4 q = tb.sigs[sg];
+    c = r.z >> 16;
+    if (q.x) c = min(c, r.x / q.x);
+    if (q.y) c = min(c, r.y / q.y);
+    if (q.z) c = min(c, (r.z & 0xFFFFu) / q.z);
+    c = min(c, 255u);
+  }
+  cap8[size_t(sg) * tp.npad + n] = uint8_t(c);
+}
+
+// one warp per (active signature, non-unit domain)
+__global__ void __launch_bounds__(256) k_capsum(Topo tp, RoundBufs rb, const uint8_t* __restrict__ cap8,
+                                                uint32_t* capsum, uint32_t* capmax) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t j = (blockIdx.x * 256 + threadIdx.x) >> 5;   // column in the table row
+  if (j >= tp.cap_stride) return;
+  const uint32_t sg = rb.sig_list[blockIdx.y];
+  uint32_t l = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < GROVE_MAX_LEVELS; ++k)
+    if (k < tp.L && !tp.unit[k] && j >= tp.cap_off[k]) l = k;
+  const uint32_t d = j - tp.cap_off[l];
+  const uint32_t lo = __ldg(tp.dom_lo[l] + d), hi = __ldg(tp.dom_hi[l] + d);
+  const uint8_t* row = cap8 + size_t(sg) * tp.npad;
+  uint32_t sum = 0, mx = 0;
+  for (uint32_t n = lo + lane; n < hi; n += 32) { const uint32_t c = row[n]; sum += c; mx = max(mx, c); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(kFull, sum, o); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
+  if (lane == 0) { capsum[size_t(sg) * tp.cap_stride + j] = sum; capmax[size_t(sg) * tp.cap_stride + j] = mx; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,8 +545,90 @@ struct ScalarEv {
     return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
   }
 
+  // has this gang already put pods on node n?
+  __device__ __forceinline__ bool touched(uint32_t n) const {
+    for (uint32_t i = 0; i < np; ++i) if (ent_node[i] == n) return true;
+    return false;
+  }
+
+  // 32 capacity bytes [base, base+32) of one signature row as 8 independent word loads; returns the
+  // mask of nodes in [a,b) whose capacity byte is non-zero
+  __device__ __forceinline__ uint32_t load_caps(const uint8_t* row, uint32_t base, uint32_t a, uint32_t b, uint32_t* w) const {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t v = (base + 4u * i < b) ? __ldg(reinterpret_cast<const uint32_t*>(row + base) + i) : 0u;
+      w[i] = v;
+      const uint32_t nz = ((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u) >> 7;   // bit 0 of each byte = byte != 0
+      mask |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);                             // gather the 4 flags, byte 0 first
+    }
+    if (a > base) mask &= kFull << (a - base);
+    if (b < base + 32u) mask &= (1u << (b - base)) - 1u;
+    return mask;
+  }
+
+  // capacity-table path: per-node capacities come as bytes (computed once per round for the signature);
+  // only nodes this gang already touched, or saturated bytes, are recomputed from the node record
+  __device__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+    const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    uint32_t placed = 0;
+    for (int p = 0; p < npc && placed < want; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      for (uint32_t base = a & ~3u; base < b && placed < want; base += 32) {
+        uint32_t w[8];
+        uint32_t mask = load_caps(row, base, a, b, w);
+        while (mask && placed < want) {
+          const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
+          const uint32_t n = base + j;
+          uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          if (c == 255u || touched(n)) c = cap_now(cr, n);
+          const uint32_t t = min(c, want - placed);
+          if (t) {
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            for (uint32_t x = 0; x < t; ++x) { ent_node[np + x] = n; ent_meta[np + x] = meta; }
+            np += t; placed += t;
+          }
+        }
+      }
+    }
+    return placed;
+  }
+
+  __device__ bool find_unit_caps(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
+    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    for (int p = 0; p < npc; ++p) {
+      const uint32_t a = plo[p], b = phi[p];
+      for (uint32_t base = a & ~3u; base < b; base += 32) {
+        uint32_t w[8];
+        uint32_t mask = load_caps(row, base, a, b, w);
+        while (mask) {
+          const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
+          const uint32_t n = base + j;
+          uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          if (c < m && c != 255u) continue;   // capacities only shrink inside an attempt
+          if (c == 255u || touched(n)) c = cap_now(cr, n);
+          if (c >= m) {
+            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            for (uint32_t x = 0; x < m; ++x) { ent_node[np + x] = n; ent_meta[np + x] = meta; }
+            np += m; Hlo[cr] = n; Hhi[cr] = n + 1;
+            return true;
+          }
+        }
+      }
+    }
+    return false;
+  }
+
   __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
+    if (rb.cap8 && rb.caps_in_attempts) return take_caps(cr, lo, hi, want);
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     uint32_t plo[kMaxPieces], phi[kMaxPieces];
@@ -538,6 +665,7 @@ struct ScalarEv {
   }
 
   __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+    if (rb.cap8 && rb.caps_in_attempts) return find_unit_caps(cr, lo, hi);
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
@@ -633,6 +761,60 @@ __device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* en
   }
 }
 
+// ---- candidate pre-filter: a NECESSARY condition for place_in(lo, hi) to succeed ------------------
+// (each clique alone must find MinReplicas worth of capacity in a domain it could be packed into, and
+// the cliques of a scope must find it inside one common scope domain).  Reads only the small
+// per-signature capacity tables.
+__device__ bool clique_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t cr,
+                                 uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
+  const uint32_t w = sh.clq[cr].w;
+  const uint32_t m = w & 0xFFu, ql = (w >> 16) & 0xFFu;
+  if (m == 0) return true;
+  const size_t row = size_t(sh.sig[cr]);
+  const bool tabled = lvl >= 0 && !tp.unit[lvl];
+  if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
+    if (tp.unit[ql]) {  // all m pods on one node
+      if (tabled) return __ldg(rb.capmax + row * tp.cap_stride + tp.cap_off[lvl] + dE) >= m;
+      for (uint32_t n = lo; n < hi; ++n) if (__ldg(rb.cap8 + row * tp.npad + n) >= m) return true;
+      return false;
+    }
+    const uint32_t d0 = __ldg(tp.next_dom[ql] + lo), d1 = __ldg(tp.next_dom[ql] + hi);
+    uint32_t any = 0;  // no early exit: the look-ups are independent and overlap
+    for (uint32_t d = d0; d < d1; ++d) any |= __ldg(rb.capsum + row * tp.cap_stride + tp.cap_off[ql] + d) >= m;
+    return any != 0;
+  }
+  if (tabled) return __ldg(rb.capsum + row * tp.cap_stride + tp.cap_off[lvl] + dE) >= m;
+  uint32_t sum = 0;
+  for (uint32_t n = lo; n < hi && sum < m; ++n) sum += __ldg(rb.cap8 + row * tp.npad + n);
+  return sum >= m;
+}
+
+__device__ bool scope_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, const grove_scope_t& s,
+                                uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
+  uint32_t all = 1;
+  for (uint32_t i = 0; i < s.n_cliques; ++i) all &= clique_plausible(tp, rb, sh, s.first_clique + i, lo, hi, lvl, dE);
+  return all != 0;
+}
+
+__device__ bool gang_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t n_scopes,
+                               uint32_t lo, uint32_t hi, int lvl, uint32_t dD) {
+  for (uint32_t si = 0; si < n_scopes; ++si) {
+    const grove_scope_t s = sh.scopes[si];
+    bool ok = false;
+    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
+      const uint32_t d0 = __ldg(tp.next_dom[s.level] + lo), d1 = __ldg(tp.next_dom[s.level] + hi);
+      uint32_t any = 0;  // no early exit: children are independent table look-ups
+      for (uint32_t d = d0; d < d1; ++d)
+        any |= scope_plausible(tp, rb, sh, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), d);
+      ok = any != 0;
+    } else {
+      ok = scope_plausible(tp, rb, sh, s, lo, hi, lvl, dD);
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
 constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
 constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
 
@@ -698,34 +880,52 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
     D += rcnt[p];
   }
   ScalarEv ev(tp, rb, sh, g);
-  for (uint32_t base = 0, step = 0; base < D; ++step) {
-    const uint32_t width = (step == 0 && blockDim.x == kAdmitThreads) ? 32u : blockDim.x;
-    bool ok = false; uint32_t k = GROVE_NONE_U32, dl = 0, dh = 0;
-    if (tid < width && base + tid < D) {
-      k = base + tid;
-      uint32_t rem = k, d = 0;
+  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
+  const uint32_t nwarp = blockDim.x >> 5;
+  // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
+  // then run the packing only on the plausible ones -- the first 32 of them first, since in an
+  // uncongested cluster the very first candidate already fits
+  for (uint32_t base = 0; base < D; base += blockDim.x) {
+    const uint32_t k = base + tid;
+    uint32_t d = 0, dl = 0, dh = 0;
+    bool plaus = false;
+    if (k < D) {
+      uint32_t rem = k;
       for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
       dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-      ev.k = k;
-      ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
-      if (ok) atomicMin(&sh.best, k);
+      plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
     }
+    const uint32_t pb = __ballot_sync(kFull, plaus);
+    if (lane == 0) s_wcnt[warp] = __popc(pb);
     __syncthreads();
-    const uint32_t best = sh.best;
-    if (best != GROVE_NONE_U32) {
-      if (k == best) {  // this lane holds the winning packing
-        uint32_t n_min, min_score;
-        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
-        for (uint32_t i = 0; i < ev.np; ++i) {
-          rb.ent_node[info.pod_off + i] = ev.ent_node[i];
-          rb.ent_meta[info.pod_off + i] = ev.ent_meta[i];
-        }
-        rb.spec_ok[gi] = 1; rb.spec_n[gi] = uint16_t(ev.np);
-        rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = dl;
+    uint32_t rank = __popc(pb & ((1u << lane) - 1u)), total = 0;
+    for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wcnt[w]; if (w < warp) rank += c; total += c; }
+    for (uint32_t abase = 0; abase < total;) {
+      const uint32_t width = (base == 0 && abase == 0 && blockDim.x == kAdmitThreads) ? rb.width0 : blockDim.x;
+      bool ok = false;
+      if (plaus && rank >= abase && rank < abase + width) {
+        ev.k = k;
+        ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
+        if (ok) atomicMin(&sh.best, k);
       }
-      return;
+      __syncthreads();
+      const uint32_t best = sh.best;
+      if (best != GROVE_NONE_U32) {
+        if (k == best) {  // this lane holds the winning packing
+          uint32_t n_min, min_score;
+          finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+          for (uint32_t i = 0; i < ev.np; ++i) {
+            rb.ent_node[info.pod_off + i] = ev.ent_node[i];
+            rb.ent_meta[info.pod_off + i] = ev.ent_meta[i];
+          }
+          rb.spec_ok[gi] = 1; rb.spec_n[gi] = uint16_t(ev.np);
+          rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = dl;
+        }
+        return;
+      }
+      abase += width;
     }
-    base += width;
+    __syncthreads();  // s_wcnt is rewritten by the next chunk
   }
   if (tid == 0) {
     rb.spec_ok[gi] = 0; rb.spec_n[gi] = 0; rb.spec_score[gi] = uint8_t(tp.L + 1); rb.spec_top[gi] = GROVE_NONE_U32;
