@@ -76,6 +76,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the captured k_score launch (round 1: 12 500 rows), from the committed
+    `ncu --set full` capture; None when the capture is absent."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r1_ncu_k_score_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(name)
+            tot += float(vals[i].replace(",", "")) * scale[units[i]]
+        return tot
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def make_workload(name: str):
     cfg = synth.CONFIGS[name]()
     g, c, s = cfg["tables"]
@@ -243,7 +261,11 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_score (K2 topology-distance score matrix)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic() if args.config == "C4" else None,
+                     "traffic_note": "DRAM read+write of the round-1 k_score launch (12 500 rows x 50 176 B; algorithmic 703 MB) from "
+                                     "profiles/r1_ncu_k_score_raw.csv; write-only ceiling on this box = 3.93 TB/s (torch memset), "
+                                     "i.e. 0.60 of the copy peak used as denominator",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_step": k2_bytes, "ms_per_step": k2_ms},
         "kernel_ms_per_step": {k: v / args.steps for k, v in acc.items()},
         "cpu_baseline": cpu,

@@ -106,7 +106,9 @@ struct grove_engine {
   DevBuf<uint8_t> d_cap8;
   uint32_t cap_off[GROVE_MAX_LEVELS]{}, cap_stride = 0;
   bool prefilter = false;
-  int tune_prefilter = 1;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
+  bool dbg_on = false;
+  DevBuf<uint32_t> d_dbg;
+  int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
   uint32_t tune_width0 = 32;
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
@@ -246,7 +248,7 @@ static RoundBufs make_bufs(grove_engine* e) {
   r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
   r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
   r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
-  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0;
+  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0; r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
 }
 
@@ -271,6 +273,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (!e) return GROVE_ERR_OOM;
   e->cfg = *cfg; e->L = cfg->n_levels;
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
+  if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = std::min(32, std::max(1, std::atoi(v)));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
@@ -511,6 +514,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
         e->d_capmax.ensure(tw) == cudaSuccess) e->prefilter = true;
     else (void)cudaGetLastError();
   }
+  if (e->dbg_on) CU_TRY(e, e->d_dbg.ensure(size_t(G) * 4));
   // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
   std::vector<uint8_t> st(G, GROVE_GANG_PENDING);
   for (uint32_t g = 0; g < G; ++g) if (e->gangs[g].flags & GROVE_GANG_GATED) st[g] = GROVE_GANG_GATED_SKIP;
@@ -553,6 +557,7 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
     k_score<<<gs, 256, 0, e->stream>>>(tp, tb, rb, nr);
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
+  if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   if (na >= 148u * 4u) k_admit<kAdmitThreads><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
   else k_admit<kAdmitThreadsWide><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
@@ -614,6 +619,16 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     }
     rc = round_commit_local(e, true);
     if (rc) { e->in_cycle = false; return rc; }
+    if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr
+      std::vector<uint32_t> h(size_t(e->G) * 4); std::vector<uint32_t> act(na);
+      cudaStreamSynchronize(e->stream);
+      cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(act.data(), e->d_active.p, na * 4, cudaMemcpyDeviceToHost);
+      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0;
+      for (uint32_t i = 0; i < na; ++i) { const uint32_t* d = &h[size_t(act[i]) * 4]; sp += d[1]; sa += d[2]; maxa = std::max<uint64_t>(maxa, d[2]); if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; } }
+      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) winners %llu mean winning k %.1f\n", e->round_no, na,
+                   double(sp) / na, double(sa) / na, (unsigned long long)maxa, (unsigned long long)won, won ? double(sk) / won : 0.0);
+    }
     CU_TRY(e, cudaEventSynchronize(e->ev[4]));
     float t;
     cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); ms_fit += t;

@@ -81,6 +81,7 @@ struct RoundBufs {
   const uint32_t* capmax; // [S][cap_stride] per-domain max of cap8
   uint32_t caps_in_attempts;  // 1: the scalar evaluator packs from cap8 bytes, 0: from fit words + node records
   uint32_t width0;            // candidates attempted in the very first step of a gang (1..32)
+  uint32_t* dbg;              // [G][4] optional: candidates, plausible, attempts, winning candidate
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -693,74 +694,6 @@ struct ScalarEv {
   }
 };
 
-template <class Ev>
-__device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
-  const Topo& tp = ev.tp;
-  const uint32_t mark = ev.np;
-  for (uint32_t i = 0; i < s.n_cliques; ++i) {
-    const uint32_t cr = s.first_clique + i;
-    const uint32_t w = ev.sh.clq[cr].w;
-    const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
-    bool ok = false;
-    if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
-      if (tp.unit[ql] && m >= 1) {
-        ok = ev.find_unit(cr, lo, hi);
-      } else {
-        uint32_t plo[kMaxPieces], phi[kMaxPieces];
-        const int npc = make_pieces(ev.g, lo, hi, ql, plo, phi);
-        for (int p = 0; p < npc && !ok; ++p) {
-          const uint32_t d0 = __ldg(tp.next_dom[ql] + plo[p]), d1 = __ldg(tp.next_dom[ql] + phi[p]);
-          for (uint32_t d = d0; d < d1 && !ok; ++d)
-            ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
-        }
-      }
-    } else {
-      ok = ev.fill_min(cr, lo, hi);
-    }
-    if (!ok) { ev.np = mark; return false; }
-  }
-  return true;
-}
-
-template <class Ev>
-__device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
-  const Topo& tp = ev.tp;
-  ev.np = 0;
-  for (uint32_t si = 0; si < n_scopes; ++si) {
-    const grove_scope_t s = ev.sh.scopes[si];
-    bool ok = false;
-    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      uint32_t plo[kMaxPieces], phi[kMaxPieces];
-      const int npc = make_pieces(ev.g, lo, hi, s.level, plo, phi);
-      for (int p = 0; p < npc && !ok; ++p) {
-        const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
-        for (uint32_t d = d0; d < d1 && !ok; ++d) {
-          if (ev.moot()) { ev.np = 0; return false; }
-          ok = place_scope(ev, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level));
-        }
-      }
-    } else {
-      ok = place_scope(ev, s, lo, hi, lvl);
-    }
-    if (!ok) { ev.np = 0; return false; }
-  }
-  return true;
-}
-
-// surplus beyond MinReplicas (best effort) + publication of the speculative placement
-template <class Ev>
-__device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* ent_meta, const uint32_t* Hlo,
-                            const uint32_t* Hhi, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
-  n_min = ev.np;
-  min_score = ev.tp.L + 1;
-  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ent_meta[i] >> 8));
-  for (uint32_t cr = 0; cr < n_cliques; ++cr) {
-    const uint32_t w = ev.sh.clq[cr].w;
-    const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-    if (rp > mn) ev.take(cr, Hlo[cr], Hhi[cr], rp - mn);
-  }
-}
-
 // ---- candidate pre-filter: a NECESSARY condition for place_in(lo, hi) to succeed ------------------
 // (each clique alone must find MinReplicas worth of capacity in a domain it could be packed into, and
 // the cliques of a scope must find it inside one common scope domain).  Reads only the small
@@ -813,6 +746,82 @@ __device__ bool gang_plausible(const Topo& tp, const RoundBufs& rb, const GangSh
     if (!ok) return false;
   }
   return true;
+}
+
+template <class Ev>
+__device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
+  const Topo& tp = ev.tp;
+  const uint32_t mark = ev.np;
+  for (uint32_t i = 0; i < s.n_cliques; ++i) {
+    const uint32_t cr = s.first_clique + i;
+    const uint32_t w = ev.sh.clq[cr].w;
+    const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
+    bool ok = false;
+    if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
+      if (tp.unit[ql] && m >= 1) {
+        ok = ev.find_unit(cr, lo, hi);
+      } else {
+        uint32_t plo[kMaxPieces], phi[kMaxPieces];
+        const int npc = make_pieces(ev.g, lo, hi, ql, plo, phi);
+        for (int p = 0; p < npc && !ok; ++p) {
+          const uint32_t d0 = __ldg(tp.next_dom[ql] + plo[p]), d1 = __ldg(tp.next_dom[ql] + phi[p]);
+          for (uint32_t d = d0; d < d1 && !ok; ++d)
+            ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
+        }
+      }
+    } else {
+      ok = ev.fill_min(cr, lo, hi);
+    }
+    if (!ok) { ev.np = mark; return false; }
+  }
+  return true;
+}
+
+template <class Ev>
+__device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
+  const Topo& tp = ev.tp;
+  ev.np = 0;
+  for (uint32_t si = 0; si < n_scopes; ++si) {
+    const grove_scope_t s = ev.sh.scopes[si];
+    bool ok = false;
+    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
+      uint32_t plo[kMaxPieces], phi[kMaxPieces];
+      const int npc = make_pieces(ev.g, lo, hi, s.level, plo, phi);
+      for (int p = 0; p < npc && !ok; ++p) {
+        const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
+        for (uint32_t d = d0; d < d1 && !ok; ++d) {
+          if (ev.moot()) { ev.np = 0; return false; }
+          const uint32_t el = __ldg(tp.dom_lo[s.level] + d), eh = __ldg(tp.dom_hi[s.level] + d);
+          // round-start capacities are an upper bound: a scope domain that lacks them cannot be packed
+          if (ev.rb.cap8 && !scope_plausible(tp, ev.rb, ev.sh, s, el, eh, int(s.level), d)) continue;
+          ok = place_scope(ev, s, el, eh, int(s.level));
+        }
+      }
+    } else {
+      ok = place_scope(ev, s, lo, hi, lvl);
+    }
+    if (!ok) { ev.np = 0; return false; }
+  }
+  return true;
+}
+
+// surplus beyond MinReplicas (best effort) + publication of the speculative placement
+template <class Ev>
+__device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* ent_meta, const uint32_t* Hlo,
+                            const uint32_t* Hhi, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
+  n_min = ev.np;
+  min_score = ev.tp.L + 1;
+  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ent_meta[i] >> 8));
+  for (uint32_t cr = 0; cr < n_cliques; ++cr) {
+    const uint32_t w = ev.sh.clq[cr].w;
+    const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
+    if (rp > mn) ev.take(cr, Hlo[cr], Hhi[cr], rp - mn);
+  }
+}
+
+__global__ void k_dbg_init(uint32_t* dbg, uint32_t G) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) dbg[g * 4 + 3] = GROVE_NONE_U32;
 }
 
 constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
@@ -900,6 +909,7 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
     __syncthreads();
     uint32_t rank = __popc(pb & ((1u << lane) - 1u)), total = 0;
     for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wcnt[w]; if (w < warp) rank += c; total += c; }
+    if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
     for (uint32_t abase = 0; abase < total;) {
       const uint32_t width = (base == 0 && abase == 0 && blockDim.x == kAdmitThreads) ? rb.width0 : blockDim.x;
       bool ok = false;
@@ -907,6 +917,7 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
         ev.k = k;
         ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
         if (ok) atomicMin(&sh.best, k);
+        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
       }
       __syncthreads();
       const uint32_t best = sh.best;
@@ -920,6 +931,7 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
           }
           rb.spec_ok[gi] = 1; rb.spec_n[gi] = uint16_t(ev.np);
           rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = dl;
+          if (rb.dbg) rb.dbg[gi * 4 + 3] = k;
         }
         return;
       }
