@@ -102,7 +102,11 @@ struct grove_engine {
   DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
   DevBuf<grove_gang_status_t> d_status;
   DevBuf<grove_placement_t> d_out;
-  DevBuf<uint32_t> d_delta, d_final, d_capsum, d_capmax;
+  DevBuf<uint32_t> d_xbuf, d_active_all, d_flags, d_capsum, d_capmax;
+  DevBuf<uint8_t> d_taken, d_cur, d_prop;
+  uint32_t K = GROVE_MAX_ALTERNATIVES;
+  int resolve_blocks_per_sm = 0;
+  uint32_t n_sm = 148;
   DevBuf<uint8_t> d_cap8;
   uint32_t cap_off[GROVE_MAX_LEVELS]{}, cap_stride = 0;
   bool prefilter = false;
@@ -246,6 +250,13 @@ static RoundBufs make_bufs(grove_engine* e) {
   r.counters = e->d_counters.p; r.spec_ok = e->d_spec_ok.p; r.spec_score = e->d_spec_score.p;
   r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
   r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
+  r.active_all = e->d_active_all.p; r.taken = e->d_taken.p; r.cur = e->d_cur.p; r.prop = e->d_prop.p; r.flags = e->d_flags.p;
+  {
+    const size_t KP = size_t(e->K) * e->P, GK = size_t(e->G) * e->K;
+    uint32_t* x = e->d_xbuf.p;
+    r.alt_node = x; r.alt_meta = x + KP; r.alt_n = x + 2 * KP; r.alt_score = x + 2 * KP + GK; r.alt_top = x + 2 * KP + 2 * GK;
+    r.nalt = x + 2 * KP + 3 * GK; r.K = e->K; r.P = e->P;
+  }
   r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
   r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
   r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0; r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
@@ -265,6 +276,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (cfg->abi_version != GROVE_ABI_VERSION) return GROVE_ERR_INVALID_ARG;
   if (cfg->n_levels < 1 || cfg->n_levels > GROVE_MAX_LEVELS) return GROVE_ERR_INVALID_ARG;
   if (cfg->world > 1 && cfg->rank >= cfg->world) return GROVE_ERR_INVALID_ARG;
+  if (cfg->alternatives > GROVE_MAX_ALTERNATIVES) return GROVE_ERR_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GROVE_ERR_NO_DEVICE;  // no CPU fallback
   if (cfg->device < 0 || cfg->device >= ndev) return GROVE_ERR_NO_DEVICE;
@@ -272,6 +284,10 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   grove_engine* e = new (std::nothrow) grove_engine();
   if (!e) return GROVE_ERR_OOM;
   e->cfg = *cfg; e->L = cfg->n_levels;
+  e->K = cfg->alternatives ? cfg->alternatives : GROVE_MAX_ALTERNATIVES;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resolve_blocks_per_sm, k_resolve, 256, 0);
+  if (e->resolve_blocks_per_sm < 1) e->resolve_blocks_per_sm = 1;
+  { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = std::min(32, std::max(1, std::atoi(v)));
@@ -496,6 +512,10 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   CU_TRY(e, e->d_counters.ensure(8)); CU_TRY(e, e->d_spec_ok.ensure(G)); CU_TRY(e, e->d_spec_score.ensure(G));
   CU_TRY(e, e->d_spec_n.ensure(G)); CU_TRY(e, e->d_spec_top.ensure(G)); CU_TRY(e, e->d_ent_node.ensure(e->P)); CU_TRY(e, e->d_ent_meta.ensure(e->P));
   CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
+  CU_TRY(e, e->d_taken.ensure(e->N)); CU_TRY(e, e->d_cur.ensure(G)); CU_TRY(e, e->d_prop.ensure(G)); CU_TRY(e, e->d_flags.ensure(GROVE_SUBROUNDS));
+  CU_TRY(e, e->d_active_all.ensure(G));
+  CU_TRY(e, e->d_xbuf.ensure(2 * size_t(e->K) * e->P + 3 * size_t(G) * e->K + G));
+  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // k_resolve withdraws its claims itself
   CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
   CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
   // the Q x N matrices
@@ -528,8 +548,11 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   return GROVE_OK;
 }
 
-// one optimistic round on this handle's share of the gangs; returns via h_counters
-static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
+static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P + 3 * size_t(e->G) * e->K + e->G; }
+
+// evaluation half of a round on this handle's share of the gangs: prepare -> fit -> (capacity tables)
+// -> score -> admit.  Counters land in h_counters.
+static int32_t round_eval(grove_engine* e, bool timed) {
   const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
   e->round_no++;
   CU_TRY(e, cudaMemsetAsync(e->d_counters.p, 0, sizeof(uint32_t) * 8, e->stream));
@@ -538,10 +561,11 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
   CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   e->launches += 1;
-  const uint32_t na = e->h_counters.p[0], nr = e->h_counters.p[1];
+  const uint32_t na = e->h_counters.p[0], nr = e->h_counters.p[1], ns = e->h_counters.p[4];
+  if (e->cfg.world > 1 && e->h_counters.p[5])  // all-reduce SUM payload: everything this rank does not own stays zero
+    CU_TRY(e, cudaMemsetAsync(e->d_xbuf.p, 0, sizeof(uint32_t) * xbuf_words(e), e->stream));
   if (na == 0) return GROVE_OK;
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  const uint32_t ns = e->h_counters.p[4];
   dim3 gfit(e->Npad / 1024, std::min<uint32_t>((ns + kFitTile - 1) / kFitTile, 65535u));
   k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
   if (e->prefilter && ns) {
@@ -550,32 +574,30 @@ static int32_t round_eval(grove_engine* e, bool timed, float* ms) {
     e->launches += 2;
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
-  {
-    const uint32_t cpr = e->Npad >> 4;
-    (void)cpr;
-    dim3 gs(1, std::min<uint32_t>(nr, 65535u));  // one CTA per row, looping over its chunks
-    k_score<<<gs, 256, 0, e->stream>>>(tp, tb, rb, nr);
-  }
+  k_score<<<dim3(1, std::min<uint32_t>(nr, 65535u)), 256, 0, e->stream>>>(tp, tb, rb, nr);  // one CTA per row
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   if (na >= 148u * 4u) k_admit<kAdmitThreads><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
   else k_admit<kAdmitThreadsWide><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
-  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
-  k_claim<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb);
   CU_TRY(e, cudaGetLastError());
-  e->launches += 4;
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
+  e->launches += 3;
   e->pairs += uint64_t(nr) * e->N;
-  (void)ms;
   return GROVE_OK;
 }
 
-static int32_t round_commit_local(grove_engine* e, bool timed) {
-  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
-  const uint32_t na = e->h_counters.p[0];
-  if (na == 0) return GROVE_OK;
-  k_commit<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(tp, tb, rb, e->d_nres.p, e->round_no);
-  CU_TRY(e, cudaGetLastError());
+// resolution half: sub-rounds over the alternatives of every rank's active gangs (replicated), commits
+static int32_t round_resolve(grove_engine* e, bool timed) {
+  const uint32_t na_all = e->h_counters.p[5];
+  if (na_all == 0) return GROVE_OK;
+  Topo tp = make_topo(e); Tables tb = make_tables(e); RoundBufs rb = make_bufs(e);
+  CU_TRY(e, cudaMemsetAsync(e->d_taken.p, 0, e->N, e->stream));
+  CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));
+  uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
+  const uint32_t want = (na_all * 32 + 255) / 256;
+  const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, uint32_t(e->resolve_blocks_per_sm) * e->n_sm));
+  void* args[] = {&tp, &tb, &rb, &nres, &rn};
+  CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(256), args, 0, e->stream));
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
   e->launches += 1;
   return GROVE_OK;
@@ -599,42 +621,55 @@ static int32_t finish_cycle(grove_engine* e, grove_cycle_stats_t* stats) {
   return GROVE_OK;
 }
 
+// what the prepare pass decided (identical on every rank: it sees the replicated gang state):
+//  1 = a round is on, 0 = the cycle is over
+static int32_t after_prepare(grove_engine* e, uint32_t* go) {
+  *go = 0;
+  const uint32_t unres = e->h_counters.p[2], glob = e->h_counters.p[5];
+  if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; return GROVE_OK; }  // nothing left (and nothing propagated): not a round
+  if (glob == 0) {  // dependency cycle / unreachable base: nothing can ever become active
+    k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 1;
+    return GROVE_OK;
+  }
+  *go = 1;
+  return GROVE_OK;
+}
+
 int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e) return GROVE_ERR_INVALID_ARG;
-  if (e->cfg.world > 1) return fail(e, GROVE_ERR_STATE, "sharded handle: drive the cycle with grove_round_* and reduce between steps");
+  if (e->cfg.world > 1) return fail(e, GROVE_ERR_STATE, "sharded handle: drive the cycle with grove_round_* and reduce between the steps");
   int32_t rc = grove_cycle_begin(e);
   if (rc) return rc;
   float ms_fit = 0, ms_score = 0, ms_admit = 0, ms_commit = 0;
   CU_TRY(e, cudaEventRecord(e->ev[8], e->stream));
   for (;;) {
     if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) break;
-    rc = round_eval(e, true, nullptr);
+    rc = round_eval(e, true);
     if (rc) { e->in_cycle = false; return rc; }
-    const uint32_t na = e->h_counters.p[0], unres = e->h_counters.p[2];
-    if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; break; }  // nothing left (and nothing propagated): not a round
-    if (na == 0) {  // dependency cycle / unreachable base
-      k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
-      e->launches += 1;
-      break;
-    }
-    rc = round_commit_local(e, true);
+    uint32_t go = 0;
+    rc = after_prepare(e, &go);
     if (rc) { e->in_cycle = false; return rc; }
-    if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr
-      std::vector<uint32_t> h(size_t(e->G) * 4); std::vector<uint32_t> act(na);
-      cudaStreamSynchronize(e->stream);
-      cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
-      cudaMemcpy(act.data(), e->d_active.p, na * 4, cudaMemcpyDeviceToHost);
-      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0;
-      for (uint32_t i = 0; i < na; ++i) { const uint32_t* d = &h[size_t(act[i]) * 4]; sp += d[1]; sa += d[2]; maxa = std::max<uint64_t>(maxa, d[2]); if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; } }
-      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) winners %llu mean winning k %.1f\n", e->round_no, na,
-                   double(sp) / na, double(sa) / na, (unsigned long long)maxa, (unsigned long long)won, won ? double(sk) / won : 0.0);
-    }
+    if (!go) break;
+    const uint32_t na = e->h_counters.p[0];
+    rc = round_resolve(e, true);
+    if (rc) { e->in_cycle = false; return rc; }
     CU_TRY(e, cudaEventSynchronize(e->ev[4]));
     float t;
     cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); ms_fit += t;
     cudaEventElapsedTime(&t, e->ev[1], e->ev[2]); ms_score += t;
     cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_admit += t;
     cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_commit += t;
+    if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr
+      std::vector<uint32_t> h(size_t(e->G) * 4); std::vector<uint32_t> act(na);
+      cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(act.data(), e->d_active.p, na * 4, cudaMemcpyDeviceToHost);
+      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0;
+      for (uint32_t i = 0; i < na; ++i) { const uint32_t* d = &h[size_t(act[i]) * 4]; sp += d[1]; sa += d[2]; maxa = std::max<uint64_t>(maxa, d[2]); if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; } }
+      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) feasible %llu mean first feasible k %.1f\n", e->round_no, na,
+                   double(sp) / na, double(sa) / na, (unsigned long long)maxa, (unsigned long long)won, won ? double(sk) / won : 0.0);
+    }
   }
   CU_TRY(e, cudaEventRecord(e->ev[9], e->stream));
   rc = finish_cycle(e, nullptr);
@@ -663,92 +698,36 @@ int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint3
   return GROVE_OK;
 }
 
-// ---- stepping API (multi-GPU hosts reduce the returned buffers between the calls) ----
-int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words, uint32_t* go) {
-  if (!e || !d_claim_words || !n_claim_words || !go) return GROVE_ERR_INVALID_ARG;
+// ---- stepping API (multi-GPU hosts reduce the returned buffer between the two calls of a round) ----
+int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, uint32_t* go) {
+  if (!e || !d_words || !n_words || !go) return GROVE_ERR_INVALID_ARG;
   if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  *go = 0; *d_claim_words = e->d_claim.p; *n_claim_words = e->N;
+  *go = 0; *d_words = e->d_xbuf.p; *n_words = uint32_t(xbuf_words(e));
   if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) return GROVE_OK;
-  // the prepare pass sees the replicated gang state, so its verdicts are identical on every rank
-  int32_t rc = round_eval(e, false, nullptr);
+  int32_t rc = round_eval(e, false);
   if (rc) return rc;
-  const uint32_t unres = e->h_counters.p[2], glob = e->h_counters.p[5];
-  if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; return GROVE_OK; }
-  if (glob == 0) {
-    k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
-    CU_TRY(e, cudaGetLastError());
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
-    e->launches += 1;
-    return GROVE_OK;
-  }
-  if (e->h_counters.p[0] == 0)  // this rank has no active gang this round: its claims are all "none"
-    CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
+  rc = after_prepare(e, go);
+  if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->stream));
-  *go = 1;
   return GROVE_OK;
 }
 
-int32_t grove_round_commit(grove_engine_t* e, void** d_delta_words, uint32_t* n_delta_words) {
-  if (!e || !d_delta_words || !n_delta_words) return GROVE_ERR_INVALID_ARG;
-  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  CU_TRY(e, cudaSetDevice(e->cfg.device));
-  const size_t words = 4 * size_t(e->N) + e->G;
-  CU_TRY(e, e->d_delta.ensure(words));
-  CU_TRY(e, cudaMemsetAsync(e->d_delta.p, 0, sizeof(uint32_t) * words, e->stream));
-  const uint32_t na = e->h_counters.p[0];
-  if (na) {
-    k_commit_sharded<<<(na * 32 + 255) / 256, 256, 0, e->stream>>>(make_topo(e), make_tables(e), make_bufs(e), e->d_delta.p);
-    CU_TRY(e, cudaGetLastError());
-    e->launches += 1;
-  }
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  *d_delta_words = e->d_delta.p; *n_delta_words = uint32_t(words);
-  return GROVE_OK;
-}
-
-int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining) {
+int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining) {
   if (!e) return GROVE_ERR_INVALID_ARG;
   if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  const uint32_t m = std::max(e->N, e->G);
-  k_apply<<<(m + 255) / 256, 256, 0, e->stream>>>(make_topo(e), make_tables(e), make_bufs(e), e->d_nres.p, e->d_delta.p, e->round_no);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 1;
-  const uint32_t unres_before = e->h_counters.p[2];
-  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
+  int32_t rc = round_resolve(e, false);
+  if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->stream));
-  if (remaining) *remaining = unres_before - e->h_counters.p[6];
-  return GROVE_OK;
-}
-
-int32_t grove_cycle_gather(grove_engine_t* e, void** d_final_words, uint32_t* n_final_words) {
-  if (!e || !d_final_words || !n_final_words) return GROVE_ERR_INVALID_ARG;
-  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  CU_TRY(e, cudaSetDevice(e->cfg.device));
-  const size_t words = 2 * size_t(e->P) + 3 * size_t(e->G);
-  CU_TRY(e, e->d_final.ensure(words));
-  CU_TRY(e, cudaMemsetAsync(e->d_final.p, 0, sizeof(uint32_t) * std::max<size_t>(words, 1), e->stream));
-  if (e->G) {
-    k_pack_final<<<(e->G + 127) / 128, 128, 0, e->stream>>>(make_tables(e), make_bufs(e), e->d_final.p, e->P, e->cfg.rank, e->cfg.world);
-    CU_TRY(e, cudaGetLastError());
-    e->launches += 1;
-  }
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  *d_final_words = e->d_final.p; *n_final_words = uint32_t(words);
+  if (remaining) *remaining = e->h_counters.p[2];  // unresolved before this round's commits (upper bound)
   return GROVE_OK;
 }
 
 int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e) return GROVE_ERR_INVALID_ARG;
   if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  if (e->d_final.cap < 2 * size_t(e->P) + 3 * size_t(e->G)) return fail(e, GROVE_ERR_STATE, "grove_cycle_gather first");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  if (e->G) {
-    k_unpack_final<<<(e->G + 127) / 128, 128, 0, e->stream>>>(make_tables(e), make_bufs(e), e->d_final.p, e->P);
-    CU_TRY(e, cudaGetLastError());
-    e->launches += 1;
-  }
   return finish_cycle(e, stats);
 }
 

@@ -10,6 +10,7 @@
 // Semantics are DESIGN.md "Placement semantics"; the reference contract they restate is cited in
 // include/grove_place.h.  Integer / compare work only: no tensor cores, no floating point.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/grove_place.h"
@@ -73,7 +74,20 @@ struct RoundBufs {
   uint32_t* spec_top;    // [G]
   uint32_t* ent_node;    // [P]
   uint16_t* ent_meta;    // [P] clique_rel | score << 8
+  uint32_t* active_all;  // [G] active gangs of every rank (replicated decision)
   uint32_t* claim;       // [n]
+  uint8_t* taken;        // [n] node received a commit in this round
+  uint8_t* cur;          // [G] next alternative a gang will propose
+  uint8_t* prop;         // [G] sub-round (1-based) of the gang's last proposal
+  uint32_t* flags;       // [GROVE_SUBROUNDS] any proposal in sub-round s
+  // exchange buffer of the round (also the all-reduce payload of the sharded cycle), u32 words:
+  uint32_t* alt_node;    // [K][P] entry i of alternative a of gang g at a*P + pod_off[g] + i
+  uint32_t* alt_meta;    // [K][P] clique_rel | score << 8
+  uint32_t* alt_n;       // [G][K] entries incl. surplus
+  uint32_t* alt_score;   // [G][K]
+  uint32_t* alt_top;     // [G][K]
+  uint32_t* nalt;        // [G]
+  uint32_t K, P;
   uint32_t* F;           // [S][words] fit bitmap, one row per signature
   uint8_t* T;            // [Q][npad]
   const uint8_t* cap8;   // [S][npad] pods of the signature that fit on the node now (saturating), or null
@@ -142,7 +156,8 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
   const uint32_t g = blockIdx.x * 1024 + tid;
-  uint32_t act = 0, ncl = 0, unres = 0, coff = 0, ready = 0, prop = 0;
+  uint32_t act = 0, ncl = 0, unres = 0, coff = 0, prop = 0;
+  bool ready = false;
   if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
     const grove_gang_t gg = tb.gangs[g];
     // walk the base chain: a scaled gang is rejected with any rejected / skipped ancestor (transitively),
@@ -160,17 +175,17 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     } else {
       unres = 1;
       ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
+      if (ready) rb.active_all[atomicAdd(rb.counters + 5, 1u)] = g;
       const bool mine = world <= 1 || (g % world) == rank;
       if (ready && mine) { act = 1; ncl = gg.n_cliques; coff = gg.clique_off; }
     }
   }
   const uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
-  const uint32_t un = __popc(__ballot_sync(kFull, unres)), rd = __popc(__ballot_sync(kFull, ready));
+  const uint32_t un = __popc(__ballot_sync(kFull, unres));
   const uint32_t pr = __ballot_sync(kFull, prop);
   if (lane == 31) { s_warp_a[warp] = ia; s_warp_r[warp] = ir; }
   if (lane == 0) {
     if (un) atomicAdd(rb.counters + 2, un);
-    if (rd) atomicAdd(rb.counters + 5, rd);
     if (pr) atomicOr(rb.counters + 3, 1u);
   }
   __syncthreads();
@@ -527,7 +542,7 @@ struct ScalarEv {
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
   uint32_t k;   // candidate index of this lane; a lower successful candidate makes this attempt moot
-  __device__ __forceinline__ bool moot() const { return *reinterpret_cast<const volatile uint32_t*>(&sh.best) < k; }
+  __device__ __forceinline__ bool moot() const { return false; }  // every attempt may become one of the K alternatives
   uint32_t ent_node[GROVE_MAX_GANG_PODS];
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
@@ -850,8 +865,9 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
   if (tid == 0) sh.best = GROVE_NONE_U32;
   __syncthreads();
 
+  const uint32_t K = rb.K, P = rb.P;
   if (gg.level == GROVE_LEVEL_NONE) {
-    // single candidate: the whole cluster, packed cooperatively by warp 0
+    // single candidate: the whole cluster, packed cooperatively by warp 0 (one alternative at most)
     if (warp != 0) return;
     CoopEv ev(tp, rb, sh, g, lane);
     const bool ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
@@ -867,13 +883,15 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
         if (rp > mn) ev.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn);
       }
       for (uint32_t i = lane; i < ev.np; i += 32) {
-        rb.ent_node[info.pod_off + i] = sh.ent_node[i];
-        rb.ent_meta[info.pod_off + i] = sh.ent_meta[i];
+        rb.alt_node[info.pod_off + i] = sh.ent_node[i];
+        rb.alt_meta[info.pod_off + i] = sh.ent_meta[i];
       }
     }
     if (lane == 0) {
-      rb.spec_ok[gi] = ok ? 1 : 0; rb.spec_n[gi] = uint16_t(ok ? ev.np : 0);
-      rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = ok ? 0u : GROVE_NONE_U32;
+      rb.nalt[gi] = ok ? 1u : 0u;
+      rb.alt_n[size_t(gi) * K] = ok ? ev.np : 0u;
+      rb.alt_score[size_t(gi) * K] = min_score;
+      rb.alt_top[size_t(gi) * K] = 0u;
     }
     return;
   }
@@ -889,12 +907,14 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
     D += rcnt[p];
   }
   ScalarEv ev(tp, rb, sh, g);
-  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
+  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32], s_wsucc[kAdmitThreadsWide / 32];
   const uint32_t nwarp = blockDim.x >> 5;
+  uint32_t nsucc = 0;  // feasible candidates found so far (block-uniform)
   // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
   // then run the packing only on the plausible ones -- the first 32 of them first, since in an
-  // uncongested cluster the very first candidate already fits
-  for (uint32_t base = 0; base < D; base += blockDim.x) {
+  // uncongested cluster the very first candidates already fit.  The first K feasible candidates in
+  // order become the gang's alternatives.
+  for (uint32_t base = 0; base < D && nsucc < K; base += blockDim.x) {
     const uint32_t k = base + tid;
     uint32_t d = 0, dl = 0, dh = 0;
     bool plaus = false;
@@ -910,147 +930,123 @@ __global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBuf
     uint32_t rank = __popc(pb & ((1u << lane) - 1u)), total = 0;
     for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wcnt[w]; if (w < warp) rank += c; total += c; }
     if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
-    for (uint32_t abase = 0; abase < total;) {
+    for (uint32_t abase = 0; abase < total && nsucc < K;) {
       const uint32_t width = (base == 0 && abase == 0 && blockDim.x == kAdmitThreads) ? rb.width0 : blockDim.x;
       bool ok = false;
       if (plaus && rank >= abase && rank < abase + width) {
         ev.k = k;
         ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
-        if (ok) atomicMin(&sh.best, k);
         if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
       }
+      const uint32_t sb = __ballot_sync(kFull, ok);
+      if (lane == 0) s_wsucc[warp] = __popc(sb);
       __syncthreads();
-      const uint32_t best = sh.best;
-      if (best != GROVE_NONE_U32) {
-        if (k == best) {  // this lane holds the winning packing
-          uint32_t n_min, min_score;
-          finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
-          for (uint32_t i = 0; i < ev.np; ++i) {
-            rb.ent_node[info.pod_off + i] = ev.ent_node[i];
-            rb.ent_meta[info.pod_off + i] = ev.ent_meta[i];
-          }
-          rb.spec_ok[gi] = 1; rb.spec_n[gi] = uint16_t(ev.np);
-          rb.spec_score[gi] = uint8_t(min_score); rb.spec_top[gi] = dl;
-          if (rb.dbg) rb.dbg[gi * 4 + 3] = k;
-        }
-        return;
+      uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u)), stot = 0;
+      for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wsucc[w]; if (w < warp) srank += c; stot += c; }
+      if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
+        uint32_t n_min, min_score;
+        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+        const size_t o = size_t(srank) * P + info.pod_off;
+        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.ent_node[i]; rb.alt_meta[o + i] = ev.ent_meta[i]; }
+        rb.alt_n[size_t(gi) * K + srank] = ev.np;
+        rb.alt_score[size_t(gi) * K + srank] = min_score;
+        rb.alt_top[size_t(gi) * K + srank] = dl;
+        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
       }
+      nsucc += stot;
       abase += width;
+      __syncthreads();  // s_wsucc is rewritten by the next window
     }
     __syncthreads();  // s_wcnt is rewritten by the next chunk
   }
-  if (tid == 0) {
-    rb.spec_ok[gi] = 0; rb.spec_n[gi] = 0; rb.spec_score[gi] = uint8_t(tp.L + 1); rb.spec_top[gi] = GROVE_NONE_U32;
-  }
+  if (tid == 0) rb.nalt[gi] = min(nsucc, K);
 }
 
 // ------------------------------------------------------------------------------------------------
-// conflict resolution: lowest order rank wins a node; a gang commits iff it holds all its nodes
+// Conflict resolution of one round (cooperative launch: grid-wide barriers between the phases).
+// Up to GROVE_SUBROUNDS passes over the alternatives computed by k_admit: every undecided gang
+// proposes its first alternative that touches no node committed earlier in this round; proposals
+// claim their nodes with the gang's order rank (atomicMin); a gang that holds every node it claimed
+// (warp ballot) commits: node table decremented, nodes marked taken, placement copied to the final
+// arrays.  Gangs without any alternative are rejected.  One warp per gang, strided over the grid; a
+// gang is always handled by the same warp, so its cur/prop bytes need no cross-CTA visibility; taken,
+// claim and flags do and are read with ld.cg / volatile.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_claim(Tables tb, RoundBufs rb) {
+__global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t gi = rb.active[ai];
-  if (!rb.spec_ok[gi]) return;
-  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
-  for (uint32_t i = lane; i < n; i += 32) atomicMin(rb.claim + rb.ent_node[off + i], order);
-}
-
-__global__ void k_commit(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t gi = rb.active[ai];
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t na = rb.counters[5];
   const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
-  if (!rb.spec_ok[gi]) {
-    if (lane == 0) { rb.state[gi] = GROVE_GANG_REJECTED; rb.round[gi] = r8; }
-    return;
-  }
-  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
-  bool win = true;
-  for (uint32_t i = lane; i < n; i += 32) win &= rb.claim[rb.ent_node[off + i]] == order;
-  if (!__all_sync(kFull, win)) return;  // retry next round against the new state
-  const uint32_t coff = tb.gangs[gi].clique_off;
-  for (uint32_t i = lane; i < n; i += 32) {
-    const grove_clique_t q = tb.cliques[coff + (rb.ent_meta[off + i] & 0xFFu)];
-    uint32_t* r = reinterpret_cast<uint32_t*>(nres + rb.ent_node[off + i]);
-    // winners own their nodes exclusively this round; atomics only order this gang's own pods
-    if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
-    if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
-    atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
-  }
-  if (lane == 0) { rb.state[gi] = GROVE_GANG_ADMITTED; rb.round[gi] = r8; }
-}
-
-// ------------------------------------------------------------------------------------------------
-// sharded cycle (gang rows dealt g % world to ranks; node table and gang state replicated):
-// winners write deltas instead of touching the node table; after the SUM all-reduce every rank applies
-// the same deltas.  Layouts: delta = [4 * n] resource usage per node + [G] new gang state;
-// final = [P] entry node + [P] entry meta + [G] entries + [G] min score + [G] top domain.
-// ------------------------------------------------------------------------------------------------
-__global__ void k_commit_sharded(Topo tp, Tables tb, RoundBufs rb, uint32_t* delta) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t gi = rb.active[ai];
-  uint32_t* dstate = delta + 4 * size_t(tp.n);
-  if (!rb.spec_ok[gi]) { if (lane == 0) dstate[gi] = GROVE_GANG_REJECTED; return; }
-  const uint32_t off = tb.ginfo[gi].pod_off, order = tb.ginfo[gi].order, n = rb.spec_n[gi];
-  bool win = true;
-  for (uint32_t i = lane; i < n; i += 32) win &= rb.claim[rb.ent_node[off + i]] == order;
-  if (!__all_sync(kFull, win)) return;
-  const uint32_t coff = tb.gangs[gi].clique_off;
-  for (uint32_t i = lane; i < n; i += 32) {
-    const grove_clique_t q = tb.cliques[coff + (rb.ent_meta[off + i] & 0xFFu)];
-    uint32_t* d = delta + 4 * size_t(rb.ent_node[off + i]);
-    if (q.req_cpu_milli) atomicAdd(d + 0, q.req_cpu_milli);
-    if (q.req_mem_mib) atomicAdd(d + 1, q.req_mem_mib);
-    if (q.req_gpu) atomicAdd(d + 2, uint32_t(q.req_gpu));
-    atomicAdd(d + 3, 1u);
-  }
-  if (lane == 0) dstate[gi] = GROVE_GANG_ADMITTED;
-}
-
-__global__ void k_apply(Topo tp, Tables tb, RoundBufs rb, uint4* nres, const uint32_t* __restrict__ delta, uint32_t round_no) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < tp.n) {
-    const uint4 d = *reinterpret_cast<const uint4*>(delta + 4 * size_t(i));
-    if (d.x | d.y | d.z | d.w) {
-      uint4 r = nres[i];
-      r.x -= d.x; r.y -= d.y; r.z -= d.z | (d.w << 16);
-      nres[i] = r;
+  const uint32_t K = rb.K, P = rb.P;
+  const volatile uint32_t* vflags = rb.flags;
+  for (uint32_t ai = gw; ai < na; ai += nw) {
+    const uint32_t g = rb.active_all[ai];
+    if (lane == 0) {
+      rb.cur[g] = 0; rb.prop[g] = 0;
+      if (rb.nalt[g] == 0) { rb.state[g] = GROVE_GANG_REJECTED; rb.round[g] = r8; }
     }
   }
-  if (i < tb.G) {
-    const uint32_t s = delta[4 * size_t(tp.n) + i];
-    if (s) {
-      rb.state[i] = uint8_t(s); rb.round[i] = uint8_t(round_no > 255 ? 255 : round_no);
-      atomicAdd(rb.counters + 6, 1u);
+  __syncwarp();
+  for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
+    // ---- propose ----
+    for (uint32_t ai = gw; ai < na; ai += nw) {
+      const uint32_t g = rb.active_all[ai];
+      if (rb.state[g] != GROVE_GANG_PENDING) continue;
+      const uint32_t nalt = rb.nalt[g], po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order;
+      uint32_t c = rb.cur[g], cnt = 0;
+      while (c < nalt) {  // first alternative that touches no node committed earlier in this round
+        cnt = rb.alt_n[size_t(g) * K + c];
+        bool hit = false;
+        for (uint32_t i = lane; i < cnt; i += 32) hit |= __ldcg(rb.taken + rb.alt_node[size_t(c) * P + po + i]) != 0;
+        if (!__any_sync(kFull, hit)) break;
+        ++c;
+      }
+      if (lane == 0) rb.cur[g] = uint8_t(c);
+      if (c >= nalt) continue;  // nothing left to propose: re-evaluated next round
+      for (uint32_t i = lane; i < cnt; i += 32) atomicMin(rb.claim + rb.alt_node[size_t(c) * P + po + i], order);
+      if (lane == 0) { rb.prop[g] = uint8_t(sub + 1); rb.flags[sub] = 1u; }
     }
+    grid.sync();
+    if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
+    // ---- decide ----
+    for (uint32_t ai = gw; ai < na; ai += nw) {
+      const uint32_t g = rb.active_all[ai];
+      if (rb.prop[g] != sub + 1 || rb.state[g] != GROVE_GANG_PENDING) continue;
+      const uint32_t po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order, c = rb.cur[g];
+      const uint32_t cnt = rb.alt_n[size_t(g) * K + c];
+      bool win = true;
+      for (uint32_t i = lane; i < cnt; i += 32) win &= __ldcg(rb.claim + rb.alt_node[size_t(c) * P + po + i]) == order;
+      if (!__all_sync(kFull, win)) continue;
+      const uint32_t coff = tb.gangs[g].clique_off;
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint32_t nd = rb.alt_node[size_t(c) * P + po + i], meta = rb.alt_meta[size_t(c) * P + po + i];
+        const grove_clique_t q = tb.cliques[coff + (meta & 0xFFu)];
+        uint32_t* r = reinterpret_cast<uint32_t*>(nres + nd);
+        // winners own their nodes exclusively in a sub-round; atomics only order this gang's own pods
+        if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
+        if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
+        atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
+        rb.taken[nd] = 1;
+        rb.ent_node[po + i] = nd; rb.ent_meta[po + i] = uint16_t(meta);
+      }
+      if (lane == 0) {
+        rb.spec_n[g] = uint16_t(cnt); rb.spec_score[g] = uint8_t(rb.alt_score[size_t(g) * K + c]);
+        rb.spec_top[g] = rb.alt_top[size_t(g) * K + c];
+        rb.state[g] = GROVE_GANG_ADMITTED; rb.round[g] = r8;
+      }
+    }
+    grid.sync();
+    // ---- withdraw this sub-round's claims ----
+    for (uint32_t ai = gw; ai < na; ai += nw) {
+      const uint32_t g = rb.active_all[ai];
+      if (rb.prop[g] != sub + 1) continue;
+      const uint32_t po = tb.ginfo[g].pod_off, c = rb.cur[g], cnt = rb.alt_n[size_t(g) * K + c];
+      for (uint32_t i = lane; i < cnt; i += 32) rb.claim[rb.alt_node[size_t(c) * P + po + i]] = 0x7F7F7F7Fu;
+    }
+    grid.sync();
   }
-}
-
-__global__ void k_pack_final(Tables tb, RoundBufs rb, uint32_t* fin, uint32_t P, uint32_t rank, uint32_t world) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= tb.G) return;
-  if (rb.state[g] != GROVE_GANG_ADMITTED || (world > 1 && g % world != rank)) return;
-  const uint32_t po = tb.ginfo[g].pod_off, n = rb.spec_n[g];
-  for (uint32_t i = 0; i < n; ++i) { fin[po + i] = rb.ent_node[po + i]; fin[P + po + i] = rb.ent_meta[po + i]; }
-  fin[2 * size_t(P) + g] = n;
-  fin[2 * size_t(P) + tb.G + g] = rb.spec_score[g];
-  fin[2 * size_t(P) + 2 * size_t(tb.G) + g] = rb.spec_top[g];
-}
-
-__global__ void k_unpack_final(Tables tb, RoundBufs rb, const uint32_t* __restrict__ fin, uint32_t P) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= tb.G) return;
-  if (rb.state[g] != GROVE_GANG_ADMITTED) { rb.spec_n[g] = 0; return; }
-  const uint32_t po = tb.ginfo[g].pod_off, n = fin[2 * size_t(P) + g];
-  for (uint32_t i = 0; i < n; ++i) { rb.ent_node[po + i] = fin[po + i]; rb.ent_meta[po + i] = uint16_t(fin[P + po + i]); }
-  rb.spec_n[g] = uint16_t(n);
-  rb.spec_score[g] = uint8_t(fin[2 * size_t(P) + tb.G + g]);
-  rb.spec_top[g] = fin[2 * size_t(P) + 2 * size_t(tb.G) + g];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_load_nodes_device", "grove_cycle_begin",
-    "grove_round_eval", "grove_round_commit", "grove_round_apply", "grove_cycle_gather", "grove_cycle_end",
+    "grove_round_eval", "grove_round_resolve", "grove_cycle_end",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -61,12 +61,13 @@ def _p(a):
 class PlacementEngine:
     """One scheduler session on one GPU (not thread-safe; one cycle in flight)."""
 
-    def __init__(self, n_levels: int, device: int = 0, max_rounds: int = 0, rank: int = 0, world: int = 1):
+    def __init__(self, n_levels: int, device: int = 0, max_rounds: int = 0, rank: int = 0, world: int = 1,
+                 alternatives: int = 0):
         self.lib = load_library()
         cfg = np.zeros(1, dtype=T.config_dt)
         cfg["abi_version"] = ABI_VERSION
         cfg["device"], cfg["n_levels"], cfg["max_rounds"] = device, n_levels, max_rounds
-        cfg["rank"], cfg["world"] = rank, world
+        cfg["rank"], cfg["world"], cfg["alternatives"] = rank, world, alternatives
         self.h = C.c_void_p()
         rc = self.lib.grove_engine_create(_p(cfg), C.byref(self.h))
         if rc != 0:
@@ -136,20 +137,10 @@ class PlacementEngine:
         self._check(self.lib.grove_round_eval(self.h, C.byref(p), C.byref(n), C.byref(go)))
         return p.value, n.value, bool(go.value)
 
-    def round_commit(self):
-        p, n = C.c_void_p(), C.c_uint32(0)
-        self._check(self.lib.grove_round_commit(self.h, C.byref(p), C.byref(n)))
-        return p.value, n.value
-
-    def round_apply(self) -> int:
+    def round_resolve(self) -> int:
         r = C.c_uint32(0)
-        self._check(self.lib.grove_round_apply(self.h, C.byref(r)))
+        self._check(self.lib.grove_round_resolve(self.h, C.byref(r)))
         return r.value
-
-    def cycle_gather(self):
-        p, n = C.c_void_p(), C.c_uint32(0)
-        self._check(self.lib.grove_cycle_gather(self.h, C.byref(p), C.byref(n)))
-        return p.value, n.value
 
     def cycle_end(self) -> dict:
         st = np.zeros(1, dtype=T.stats_dt)

@@ -15,6 +15,8 @@ NONE_U32 = 0xFFFFFFFF
 MAX_GANG_PODS = 128
 MAX_GANG_CLIQUES = 32
 MAX_GANG_SCOPES = 32
+MAX_ALTERNATIVES = 8
+SUBROUNDS = 8
 
 NODE_SCHEDULABLE = 0x1
 NODE_CLASS_SHIFT = 8
@@ -46,7 +48,7 @@ status_dt = np.dtype([
 ])
 config_dt = np.dtype([
     ("abi_version", "<u4"), ("device", "<i4"), ("n_levels", "<u4"), ("max_rounds", "<u4"),
-    ("rank", "<u4"), ("world", "<u4"), ("reserved", "<u4", (2,)),
+    ("rank", "<u4"), ("world", "<u4"), ("alternatives", "<u4"), ("reserved", "<u4"),
 ])
 stats_dt = np.dtype([
     ("rounds", "<u4"), ("gangs_admitted", "<u4"), ("gangs_rejected", "<u4"), ("pods_bound", "<u4"),

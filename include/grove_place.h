@@ -51,6 +51,8 @@ extern "C" {
 #define GROVE_MAX_GANG_CLIQUES 32u
 #define GROVE_MAX_GANG_SCOPES 32u
 #define GROVE_MAX_NODES (1u << 24)
+#define GROVE_MAX_ALTERNATIVES 8u    /* feasible placements kept per gang per round */
+#define GROVE_SUBROUNDS 8u           /* conflict-resolution passes over the alternatives per round */
 
 /* error codes (all entry points return 0 on success, <0 on error) */
 #define GROVE_OK 0
@@ -141,7 +143,8 @@ typedef struct grove_config {
   uint32_t max_rounds;   /* 0 = default (unbounded until every gang is resolved) */
   uint32_t rank;         /* gang-row sharding: this handle evaluates gangs g with g % world == rank */
   uint32_t world;        /* 0 or 1 = unsharded */
-  uint32_t reserved[2];
+  uint32_t alternatives; /* 1..GROVE_MAX_ALTERNATIVES, 0 = default (GROVE_MAX_ALTERNATIVES) */
+  uint32_t reserved;
 } grove_config_t;
 
 typedef struct grove_cycle_stats {
@@ -188,25 +191,23 @@ int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint3
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);
 
 /* ---- multi-GPU stepping: one handle per rank (cfg.rank / cfg.world) -------------------------------
- * Gang rows are dealt g % world to ranks; the node table and the gang states are replicated, so every
- * rank takes the same decisions and the results are bit-identical for every world size.  The buffers
- * returned are DEVICE pointers owned by the engine, int32 words; the host (torch.distributed / NCCL)
- * reduces them in place across ranks between the calls:
+ * Gang rows are dealt g % world to ranks; the node table and the gang states are replicated.  A round
+ * has two halves: each rank EVALUATES its own gangs (fit -> score -> up to `alternatives` feasible
+ * placements per gang) into an exchange buffer that is zero for gangs it does not own; after one
+ * all-reduce SUM over that buffer every rank RESOLVES the conflicts and commits identically.  Results
+ * are bit-identical for every world size.  The buffer is a DEVICE pointer owned by the engine, int32
+ * words; the host (torch.distributed / NCCL) reduces it in place:
  *
  *   grove_cycle_begin
- *   loop: grove_round_eval(&claim,&n,&go); if (!go) break;      all-reduce MIN  over claim[n]
- *         grove_round_commit(&delta,&m);                        all-reduce SUM  over delta[m]
- *         grove_round_apply(&remaining);
- *   grove_cycle_gather(&fin,&k);                                all-reduce SUM  over fin[k]
+ *   loop: grove_round_eval(&buf,&n,&go); if (!go) break;     all-reduce SUM over buf[n]
+ *         grove_round_resolve(&remaining);
  *   grove_cycle_end(&stats)
  *
  * Every call is synchronous (its kernels are complete on return).  With world <= 1 the same sequence
- * is valid without any reduction, and grove_run_cycle is a faster fused form of it. */
+ * is valid without the reduction, and grove_run_cycle is the fused form of it. */
 int32_t grove_cycle_begin(grove_engine_t* e);
-int32_t grove_round_eval(grove_engine_t* e, void** d_claim_words, uint32_t* n_claim_words, uint32_t* go);
-int32_t grove_round_commit(grove_engine_t* e, void** d_delta_words, uint32_t* n_delta_words);
-int32_t grove_round_apply(grove_engine_t* e, uint32_t* remaining);
-int32_t grove_cycle_gather(grove_engine_t* e, void** d_final_words, uint32_t* n_final_words);
+int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, uint32_t* go);
+int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining);
 int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats);
 
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */

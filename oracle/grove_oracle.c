@@ -167,14 +167,18 @@ typedef struct ctx {
 
 typedef struct entry { uint32_t node; uint8_t clique_rel; uint8_t score; } entry_t;
 
-typedef struct spec { /* speculative result of one gang in one round */
-  int ok;
-  uint32_t n_entries;
-  uint32_t n_min_entries;
-  uint8_t min_score;
-  uint32_t top_lo;
-  entry_t e[GROVE_MAX_GANG_PODS];
-} spec_t;
+/* Exchange buffer of one round (int32 words; also the all-reduce payload of the multi-rank protocol):
+ *   [0, K*P)          alt_node   entry i of alternative a of gang g at a*P + pod_off[g] + i (sorted node index)
+ *   [K*P, 2*K*P)      alt_meta   clique_rel | score << 8
+ *   then G*K words each: alt_n (entries incl. surplus), alt_score (min score over MinReplicas pods),
+ *   alt_top (first sorted node of the gang domain); then G words nalt. */
+typedef struct xlay { size_t node, meta, n, score, top, nalt, words; uint32_t K; } xlay_t;
+static xlay_t xlayout(uint32_t K, uint32_t P, uint32_t G) {
+  xlay_t x; x.K = K;
+  x.node = 0; x.meta = (size_t)K * P; x.n = 2 * (size_t)K * P; x.score = x.n + (size_t)G * K; x.top = x.score + (size_t)G * K;
+  x.nalt = x.top + (size_t)G * K; x.words = x.nalt + G;
+  return x;
+}
 
 static uint32_t fmix32(uint32_t x) {
   x = x * 0x9E3779B1u + 0x7F4A7C15u;
@@ -356,8 +360,29 @@ static int place_in(geval_t* E, uint32_t lo, uint32_t hi, int lvl) {
   return 1;
 }
 
-/* one gang against the round-start state: first feasible gang-level domain in score order */
-static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, spec_t* out) {
+/* surplus beyond MinReplicas (best effort, podgang.go:80-83) and publication of one alternative */
+static void emit_alt(geval_t* E, const xlay_t* X, int32_t* xb, uint32_t P, uint32_t pod_off, uint32_t a, uint32_t top_lo) {
+  const ctx_t* C = E->C;
+  const grove_gang_t* g = &C->gangs[E->g];
+  uint32_t min_score = C->T.L + 1;
+  for (uint32_t i = 0; i < E->np; ++i) if (E->st[i].score < min_score) min_score = E->st[i].score;
+  for (uint32_t cr = 0; cr < g->n_cliques; ++cr) {
+    const grove_clique_t* q = &C->cliques[g->clique_off + cr];
+    uint32_t extra = q->replicas > q->min_replicas ? (uint32_t)(q->replicas - q->min_replicas) : 0;
+    if (extra) take(E, cr, E->Hlo[cr], E->Hhi[cr], extra);
+  }
+  for (uint32_t i = 0; i < E->np; ++i) {
+    xb[X->node + (size_t)a * P + pod_off + i] = (int32_t)E->st[i].node;
+    xb[X->meta + (size_t)a * P + pod_off + i] = (int32_t)((uint32_t)E->st[i].clique_rel | ((uint32_t)E->st[i].score << 8));
+  }
+  xb[X->n + (size_t)E->g * X->K + a] = (int32_t)E->np;
+  xb[X->score + (size_t)E->g * X->K + a] = (int32_t)min_score;
+  xb[X->top + (size_t)E->g * X->K + a] = (int32_t)top_lo;
+}
+
+/* one gang against the round-start state: its first K feasible gang-level domains in score order, each
+ * packed independently ("alternatives"); a gang without a gang-level constraint has one candidate */
+static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, const xlay_t* X, int32_t* xb, uint32_t P) {
   geval_t* E = malloc(sizeof(geval_t));
   memset(E, 0, sizeof(*E));
   const grove_gang_t* g = &C->gangs[gi];
@@ -370,33 +395,16 @@ static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, spec_t*
     }
   }
   for (uint32_t cr = 0; cr < g->n_cliques; ++cr) E->Trow[cr] = Trow[cr];
-  int ok = 0; uint32_t top_lo = GROVE_NONE_U32;
+  uint32_t na = 0;
   if (g->level == GROVE_LEVEL_NONE) {
-    ok = place_in(E, 0, C->T.n, -1);
-    if (ok) top_lo = 0;
+    if (place_in(E, 0, C->T.n, -1)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, 0);
   } else {
     uint32_t nc; cand_t* v = subdomains(E, g->level, 0, C->T.n, &nc);
-    for (uint32_t k = 0; k < nc && !ok; ++k) {
-      ok = place_in(E, v[k].lo, v[k].hi, (int)g->level);
-      if (ok) top_lo = v[k].lo;
-    }
+    for (uint32_t k = 0; k < nc && na < X->K; ++k)
+      if (place_in(E, v[k].lo, v[k].hi, (int)g->level)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, v[k].lo);
     free(v);
   }
-  out->ok = ok; out->n_entries = 0; out->n_min_entries = 0; out->min_score = (uint8_t)(C->T.L + 1); out->top_lo = top_lo;
-  if (ok) {
-    out->n_min_entries = E->np;
-    for (uint32_t i = 0; i < E->np; ++i) if (E->st[i].score < out->min_score) out->min_score = E->st[i].score;
-    /* best-effort surplus beyond MinReplicas, inside the domain each clique was packed into (podgang.go:80-83) */
-    for (uint32_t cr = 0; cr < g->n_cliques; ++cr) {
-      const grove_clique_t* q = &C->cliques[g->clique_off + cr];
-      uint32_t extra = q->replicas > q->min_replicas ? (uint32_t)(q->replicas - q->min_replicas) : 0;
-      if (extra) {
-        take(E, cr, E->Hlo[cr], E->Hhi[cr], extra);
-      }
-    }
-    out->n_entries = E->np;
-    memcpy(out->e, E->st, sizeof(entry_t) * E->np);
-  }
+  xb[X->nalt + gi] = (int32_t)na;
   free(E);
 }
 
@@ -450,28 +458,30 @@ int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_cliqu
 
 /*
  * One scheduling cycle.  Optimistic rounds (DESIGN.md "Cycle"):
- *   round: every active gang is evaluated against the round-start node state (fit -> score ->
- *   first feasible domain); each successful gang claims its nodes with its order rank (min wins);
- *   a gang that holds every node it claimed commits, the others retry next round; a gang with no
- *   feasible domain is rejected for the cycle.
+ *   round: every active gang is evaluated against the round-start node state (fit -> score -> its
+ *   first K feasible domains, each packed = K alternatives); then up to GROVE_SUBROUNDS sub-rounds
+ *   resolve conflicts without re-evaluating: every undecided gang proposes its first alternative
+ *   that touches no node committed earlier in this round, proposals claim their nodes with the gang's
+ *   order rank (min wins), a gang that holds every node it claimed commits.  Gangs left undecided are
+ *   re-evaluated next round; a gang with no feasible domain is rejected for the cycle.
  *
- * The cycle is written as steps over a shard context so that the multi-rank protocol (gang rows
- * dealt g % world to ranks, node table and gang state replicated, claims reduced with MIN, commit
- * deltas with SUM -- DESIGN.md section 7) can be exercised on CPU with gloo:
- *   begin; repeat { eval -> [all-reduce MIN claim] -> commit -> [all-reduce SUM delta] -> apply }
- *   until nothing is unresolved; gather -> [all-reduce SUM] -> end.
- * oracle_run_cycle is the same steps with world = 1 and no reductions.
+ * Written as steps over a shard context so that the multi-rank protocol (gang rows dealt g % world
+ * to ranks, node table and gang state replicated -- DESIGN.md section 7) can be exercised on CPU:
+ *   begin; repeat { eval (own gangs -> exchange buffer) -> [all-reduce SUM] -> resolve (replicated) }; end.
+ * oracle_run_cycle is the same steps with world = 1 and no reduction.
  */
-#define CLAIM_NONE 0x7F7F7F7F /* > any order rank (< 2^24), positive as int32 */
+#define CLAIM_NONE 0x7F7F7F7F /* > any order rank (< 2^24) */
 
 typedef struct oshard {
   ctx_t C;
-  uint32_t n, L, G, Q, S, P;
+  uint32_t n, L, G, Q, S, P, K;
+  xlay_t X;
   const grove_node_t* nodes_in;
   uint32_t rank, world, max_rounds;
   uint8_t* state; uint8_t* rnd;
-  spec_t* specs;
-  uint32_t* active; uint32_t na_local;
+  uint32_t* active; uint32_t na_local;        /* this rank's share of the round */
+  uint32_t* active_all; uint32_t na_all;      /* every rank's (replicated decision) */
+  int32_t* fin_node; int32_t* fin_meta; uint32_t* fin_n; uint8_t* fin_score; uint32_t* fin_top;
   uint32_t round, unresolved;
   uint64_t pairs;
   double t0, t_eval;
@@ -480,7 +490,8 @@ typedef struct oshard {
 
 static void shard_free(oshard_t* h) {
   if (!h) return;
-  free(h->active); free(h->specs); free(h->rnd); free(h->state);
+  free(h->active); free(h->active_all); free(h->rnd); free(h->state);
+  free(h->fin_node); free(h->fin_meta); free(h->fin_n); free(h->fin_score); free(h->fin_top);
   free(h->C.order); free(h->C.anchor); free(h->C.pod_off);
   topo_free(&h->C.T);
   free(h);
@@ -490,11 +501,13 @@ void oracle_shard_abort(oshard_t* h) { shard_free(h); }
 
 int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L, const grove_gang_t* gangs, uint32_t G,
                            const grove_clique_t* cliques, uint32_t Q, const grove_scope_t* scopes, uint32_t S,
-                           uint32_t max_rounds, int32_t threads, uint32_t rank, uint32_t world,
+                           uint32_t max_rounds, uint32_t alternatives, int32_t threads, uint32_t rank, uint32_t world,
                            uint32_t* out_fit, uint8_t* out_score, oshard_t** out) {
   int32_t rc = oracle_validate(gangs, G, cliques, Q, scopes, S, L, n);
   if (rc != GROVE_OK) return rc;
   if (n == 0 || n > GROVE_MAX_NODES || !out) return GROVE_ERR_INVALID_ARG;
+  if (alternatives == 0) alternatives = GROVE_MAX_ALTERNATIVES;
+  if (alternatives > GROVE_MAX_ALTERNATIVES) return GROVE_ERR_INVALID_ARG;
   if (world == 0) world = 1;
   if (rank >= world) return GROVE_ERR_INVALID_ARG;
 #ifdef _OPENMP
@@ -504,7 +517,7 @@ int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
   if (!h) return GROVE_ERR_OOM;
   h->t0 = now_s();
   if (topo_build(&h->C.T, nodes_in, n, L)) { shard_free(h); return GROVE_ERR_OOM; }
-  h->n = n; h->L = L; h->G = G; h->Q = Q; h->S = S; h->nodes_in = nodes_in;
+  h->n = n; h->L = L; h->G = G; h->Q = Q; h->S = S; h->nodes_in = nodes_in; h->K = alternatives;
   h->rank = rank; h->world = world; h->max_rounds = max_rounds; h->out_fit = out_fit; h->out_score = out_score;
   ctx_t* C = &h->C;
   C->G = G; C->Q = Q; C->S = S; C->gangs = gangs; C->cliques = cliques; C->scopes = scopes;
@@ -523,10 +536,13 @@ int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
     for (uint32_t c = 0; c < gangs[g].n_cliques; ++c) po += cliques[gangs[g].clique_off + c].replicas;
   }
   C->pod_off[G] = po; h->P = po;
+  h->X = xlayout(h->K, h->P, G);
   h->state = calloc(G ? G : 1, 1);
   h->rnd = calloc(G ? G : 1, 1);
-  h->specs = calloc(G ? G : 1, sizeof(spec_t));
   h->active = malloc(sizeof(uint32_t) * (G ? G : 1));
+  h->active_all = malloc(sizeof(uint32_t) * (G ? G : 1));
+  h->fin_node = calloc(po ? po : 1, sizeof(int32_t)); h->fin_meta = calloc(po ? po : 1, sizeof(int32_t));
+  h->fin_n = calloc(G ? G : 1, sizeof(uint32_t)); h->fin_score = calloc(G ? G : 1, 1); h->fin_top = calloc(G ? G : 1, sizeof(uint32_t));
   for (uint32_t g = 0; g < G; ++g) {
     if (gangs[g].flags & GROVE_GANG_GATED) h->state[g] = GROVE_GANG_GATED_SKIP; else h->unresolved++;
   }
@@ -534,17 +550,15 @@ int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
   return GROVE_OK;
 }
 
-uint32_t oracle_shard_claim_words(const oshard_t* h) { return h->n; }
-uint32_t oracle_shard_delta_words(const oshard_t* h) { return 4 * h->n + h->G; }
-uint32_t oracle_shard_final_words(const oshard_t* h) { return 2 * h->P + 3 * h->G; }
+uint32_t oracle_shard_xbuf_words(const oshard_t* h) { return (uint32_t)h->X.words; }
 
 /* Step 1: decide who is active (replicated state => identical on every rank), evaluate this rank's
- * share, write this rank's claims.  *go = 0 when the cycle is over (nothing was evaluated). */
-int32_t oracle_shard_eval(oshard_t* h, int32_t* claim, uint32_t* go) {
+ * share into the exchange buffer (zero elsewhere).  *go = 0 when the cycle is over. */
+int32_t oracle_shard_eval(oshard_t* h, int32_t* xb, uint32_t* go) {
   ctx_t* C = &h->C;
   const grove_gang_t* gangs = C->gangs; const grove_clique_t* cliques = C->cliques; const grove_scope_t* scopes = C->scopes;
   const uint32_t G = h->G, n = h->n;
-  *go = 0; h->na_local = 0;
+  *go = 0; h->na_local = 0; h->na_all = 0;
   if (h->unresolved == 0 || (h->max_rounds && h->round >= h->max_rounds)) return GROVE_OK;
   h->round++;
   const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
@@ -560,19 +574,19 @@ int32_t oracle_shard_eval(oshard_t* h, int32_t* claim, uint32_t* go) {
       }
     }
   }
-  uint32_t na_global = 0;
   for (uint32_t g = 0; g < G; ++g) {
     if (h->state[g] != GROVE_GANG_PENDING) continue;
     if (gangs[g].base_gang != GROVE_NONE_U32 && h->state[gangs[g].base_gang] != GROVE_GANG_ADMITTED) continue;
-    na_global++;
+    h->active_all[h->na_all++] = g;
     if (g % h->world == h->rank) h->active[h->na_local++] = g;
   }
-  if (na_global == 0) { /* dependency cycle: nothing can ever become active */
+  if (h->na_all == 0) { /* dependency cycle: nothing can ever become active */
     for (uint32_t g = 0; g < G; ++g)
       if (h->state[g] == GROVE_GANG_PENDING) { h->state[g] = GROVE_GANG_BASE_REJECTED; h->rnd[g] = r8; h->unresolved--; }
     return GROVE_OK;
   }
   *go = 1;
+  memset(xb, 0, sizeof(int32_t) * h->X.words);
   const uint32_t words = (n + 31) / 32;
   uint64_t pairs = 0;
   double te0 = now_s();
@@ -602,102 +616,97 @@ int32_t oracle_shard_eval(oshard_t* h, int32_t* claim, uint32_t* go) {
         if (h->round == 1 && h->out_score) memcpy(h->out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
       }
     }
-    eval_gang(C, gi, Trow, &h->specs[gi]);
+    eval_gang(C, gi, Trow, &h->X, xb, h->P);
     for (uint32_t cr = 0; cr < g->n_cliques; ++cr) free(Trow[cr]);
     free(Frow);
   }
   h->pairs += pairs;
   h->t_eval += now_s() - te0;
-  /* claims: lowest order rank wins each node */
-  for (uint32_t i = 0; i < n; ++i) claim[i] = CLAIM_NONE;
-  for (uint32_t ai = 0; ai < na; ++ai) {
-    uint32_t gi = h->active[ai];
-    if (!h->specs[gi].ok) continue;
-    for (uint32_t i = 0; i < h->specs[gi].n_entries; ++i) {
-      uint32_t nd = h->specs[gi].e[i].node;
-      if ((int32_t)C->order[gi] < claim[nd]) claim[nd] = (int32_t)C->order[gi];
-    }
-  }
   return GROVE_OK;
 }
 
-/* Step 2 (claims reduced over ranks): this rank's winners -> resource deltas per node and new gang states */
-int32_t oracle_shard_commit(oshard_t* h, const int32_t* claim, int32_t* delta) {
+/* Step 2 (exchange buffer summed over ranks): conflict resolution and commits, identical on every rank */
+int32_t oracle_shard_resolve(oshard_t* h, const int32_t* xb, uint32_t* remaining) {
   ctx_t* C = &h->C;
-  const uint32_t n = h->n;
-  memset(delta, 0, sizeof(int32_t) * (4 * (size_t)n + h->G));
-  for (uint32_t ai = 0; ai < h->na_local; ++ai) {
-    uint32_t gi = h->active[ai];
-    if (!h->specs[gi].ok) { delta[4 * (size_t)n + gi] = GROVE_GANG_REJECTED; continue; }
-    int win = 1;
-    for (uint32_t i = 0; i < h->specs[gi].n_entries && win; ++i) win = claim[h->specs[gi].e[i].node] == (int32_t)C->order[gi];
-    if (!win) continue;
-    for (uint32_t i = 0; i < h->specs[gi].n_entries; ++i) {
-      uint32_t nd = h->specs[gi].e[i].node;
-      const grove_clique_t* q = &C->cliques[C->gangs[gi].clique_off + h->specs[gi].e[i].clique_rel];
-      delta[4 * (size_t)nd + 0] += (int32_t)q->req_cpu_milli; delta[4 * (size_t)nd + 1] += (int32_t)q->req_mem_mib;
-      delta[4 * (size_t)nd + 2] += (int32_t)q->req_gpu; delta[4 * (size_t)nd + 3] += 1;
-    }
-    delta[4 * (size_t)n + gi] = GROVE_GANG_ADMITTED;
-  }
-  return GROVE_OK;
-}
-
-/* Step 3 (deltas reduced over ranks): every rank applies the same commits */
-int32_t oracle_shard_apply(oshard_t* h, const int32_t* delta, uint32_t* remaining) {
-  ctx_t* C = &h->C;
-  const uint32_t n = h->n;
+  const xlay_t* X = &h->X;
+  const uint32_t n = h->n, P = h->P, K = h->K;
   const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
-  for (uint32_t i = 0; i < n; ++i) {
-    grove_node_t* nd = &C->T.nodes[i];
-    nd->free_cpu_milli -= (uint32_t)delta[4 * (size_t)i + 0]; nd->free_mem_mib -= (uint32_t)delta[4 * (size_t)i + 1];
-    nd->free_gpu = (uint16_t)(nd->free_gpu - (uint32_t)delta[4 * (size_t)i + 2]);
-    nd->free_pods = (uint16_t)(nd->free_pods - (uint32_t)delta[4 * (size_t)i + 3]);
+  uint8_t* taken = calloc(n, 1);
+  int32_t* claim = malloc(sizeof(int32_t) * n);
+  uint32_t* cur = calloc(h->na_all ? h->na_all : 1, sizeof(uint32_t));
+  uint8_t* prop = calloc(h->na_all ? h->na_all : 1, 1);
+  for (uint32_t ai = 0; ai < h->na_all; ++ai) {
+    uint32_t g = h->active_all[ai];
+    if (xb[X->nalt + g] == 0) { h->state[g] = GROVE_GANG_REJECTED; h->rnd[g] = r8; h->unresolved--; }
   }
-  for (uint32_t g = 0; g < h->G; ++g) {
-    int32_t s = delta[4 * (size_t)n + g];
-    if (s) { h->state[g] = (uint8_t)s; h->rnd[g] = r8; h->unresolved--; }
+  for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
+    for (uint32_t i = 0; i < n; ++i) claim[i] = CLAIM_NONE;
+    uint32_t nprop = 0;
+    for (uint32_t ai = 0; ai < h->na_all; ++ai) {
+      uint32_t g = h->active_all[ai];
+      prop[ai] = 0;
+      if (h->state[g] != GROVE_GANG_PENDING) continue;
+      const uint32_t nalt = (uint32_t)xb[X->nalt + g], po = C->pod_off[g];
+      while (cur[ai] < nalt) { /* first alternative that touches no node committed earlier in this round */
+        const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a];
+        int hit = 0;
+        for (uint32_t i = 0; i < cnt && !hit; ++i) hit = taken[(uint32_t)xb[X->node + (size_t)a * P + po + i]];
+        if (!hit) break;
+        cur[ai]++;
+      }
+      if (cur[ai] >= nalt) continue; /* nothing left to propose: re-evaluated next round */
+      prop[ai] = 1; nprop++;
+      const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a];
+      for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t nd = (uint32_t)xb[X->node + (size_t)a * P + po + i];
+        if ((int32_t)C->order[g] < claim[nd]) claim[nd] = (int32_t)C->order[g];
+      }
+    }
+    if (nprop == 0) break;
+    for (uint32_t ai = 0; ai < h->na_all; ++ai) {
+      if (!prop[ai]) continue;
+      uint32_t g = h->active_all[ai];
+      const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a], po = C->pod_off[g];
+      int win = 1;
+      for (uint32_t i = 0; i < cnt && win; ++i) win = claim[(uint32_t)xb[X->node + (size_t)a * P + po + i]] == (int32_t)C->order[g];
+      if (!win) continue;
+      for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t nd = (uint32_t)xb[X->node + (size_t)a * P + po + i];
+        int32_t meta = xb[X->meta + (size_t)a * P + po + i];
+        const grove_clique_t* q = &C->cliques[C->gangs[g].clique_off + ((uint32_t)meta & 0xFFu)];
+        grove_node_t* node = &C->T.nodes[nd];
+        node->free_cpu_milli -= q->req_cpu_milli; node->free_mem_mib -= q->req_mem_mib;
+        node->free_gpu -= q->req_gpu; node->free_pods -= 1;
+        taken[nd] = 1;
+        h->fin_node[po + i] = (int32_t)nd; h->fin_meta[po + i] = meta;
+      }
+      h->fin_n[g] = cnt; h->fin_score[g] = (uint8_t)xb[X->score + (size_t)g * K + a]; h->fin_top[g] = (uint32_t)xb[X->top + (size_t)g * K + a];
+      h->state[g] = GROVE_GANG_ADMITTED; h->rnd[g] = r8; h->unresolved--;
+    }
   }
+  free(taken); free(claim); free(cur); free(prop);
   if (remaining) *remaining = h->unresolved;
   return GROVE_OK;
 }
 
-/* Step 4: placements of the gangs this rank admitted, for the final exchange (zeros elsewhere) */
-int32_t oracle_shard_gather(oshard_t* h, int32_t* fin) {
-  const uint32_t P = h->P, G = h->G;
-  memset(fin, 0, sizeof(int32_t) * (2 * (size_t)P + 3 * (size_t)G));
-  for (uint32_t g = 0; g < G; ++g) {
-    if (h->state[g] != GROVE_GANG_ADMITTED || g % h->world != h->rank) continue;
-    const spec_t* sp = &h->specs[g];
-    for (uint32_t i = 0; i < sp->n_entries; ++i) {
-      fin[h->C.pod_off[g] + i] = (int32_t)sp->e[i].node;
-      fin[P + h->C.pod_off[g] + i] = (int32_t)((uint32_t)sp->e[i].clique_rel | ((uint32_t)sp->e[i].score << 8));
-    }
-    fin[2 * (size_t)P + g] = (int32_t)sp->n_entries;
-    fin[2 * (size_t)P + G + g] = (int32_t)sp->min_score;
-    fin[2 * (size_t)P + 2 * (size_t)G + g] = (int32_t)sp->top_lo;
-  }
-  return GROVE_OK;
-}
-
-/* Step 5 (final words reduced over ranks): outputs in caller node indices; frees the context */
-int32_t oracle_shard_end(oshard_t* h, const int32_t* fin, grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
+/* Step 3: outputs in caller node indices; frees the context */
+int32_t oracle_shard_end(oshard_t* h, grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
                          grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm, oracle_stats_t* stats) {
   ctx_t* C = &h->C;
-  const uint32_t P = h->P, G = h->G, n = h->n;
+  const uint32_t G = h->G, n = h->n;
   uint32_t np = 0, adm = 0, rej = 0;
   for (uint32_t g = 0; g < G; ++g) {
     grove_gang_status_t st; memset(&st, 0, sizeof(st));
     st.state = h->state[g]; st.round = h->rnd[g]; st.top_domain_lo = GROVE_NONE_U32; st.placement_off = np;
     if (h->state[g] == GROVE_GANG_ADMITTED) {
       adm++;
-      uint32_t cnt = (uint32_t)fin[2 * (size_t)P + g];
-      st.score_num = (uint8_t)fin[2 * (size_t)P + G + g]; st.score_den = (uint8_t)(h->L + 1);
-      st.n_pods = cnt; st.top_domain_lo = (uint32_t)fin[2 * (size_t)P + 2 * (size_t)G + g];
+      uint32_t cnt = h->fin_n[g];
+      st.score_num = h->fin_score[g]; st.score_den = (uint8_t)(h->L + 1);
+      st.n_pods = cnt; st.top_domain_lo = h->fin_top[g];
       for (uint32_t i = 0; i < cnt; ++i) {
         if (out_pl && np < cap_pl) {
-          out_pl[np].clique = C->gangs[g].clique_off + ((uint32_t)fin[P + C->pod_off[g] + i] & 0xFFu);
-          out_pl[np].node = C->T.perm[(uint32_t)fin[C->pod_off[g] + i]];
+          out_pl[np].clique = C->gangs[g].clique_off + ((uint32_t)h->fin_meta[C->pod_off[g] + i] & 0xFFu);
+          out_pl[np].node = C->T.perm[(uint32_t)h->fin_node[C->pod_off[g] + i]];
         }
         np++;
       }
@@ -733,27 +742,24 @@ int32_t oracle_shard_end(oshard_t* h, const int32_t* fin, grove_placement_t* out
  * cliques in SORTED node order (row stride words = ceil(n/32) and n bytes). */
 int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
                          const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
-                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, int32_t threads,
+                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, uint32_t alternatives, int32_t threads,
                          grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
                          grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm,
                          uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
   oshard_t* h = NULL;
-  int32_t rc = oracle_shard_begin(nodes_in, n, L, gangs, G, cliques, Q, scopes, S, max_rounds, threads, 0, 1, out_fit, out_score, &h);
+  int32_t rc = oracle_shard_begin(nodes_in, n, L, gangs, G, cliques, Q, scopes, S, max_rounds, alternatives, threads, 0, 1,
+                                  out_fit, out_score, &h);
   if (rc != GROVE_OK) return rc;
-  int32_t* claim = malloc(sizeof(int32_t) * n);
-  int32_t* delta = malloc(sizeof(int32_t) * (4 * (size_t)n + G));
-  int32_t* fin = malloc(sizeof(int32_t) * (2 * (size_t)h->P + 3 * (size_t)G + 1));
-  if (!claim || !delta || !fin) { free(claim); free(delta); free(fin); shard_free(h); return GROVE_ERR_OOM; }
+  int32_t* xb = malloc(sizeof(int32_t) * (h->X.words ? h->X.words : 1));
+  if (!xb) { shard_free(h); return GROVE_ERR_OOM; }
   for (;;) {
     uint32_t go = 0;
-    oracle_shard_eval(h, claim, &go);
+    oracle_shard_eval(h, xb, &go);
     if (!go) break;
-    oracle_shard_commit(h, claim, delta);
-    oracle_shard_apply(h, delta, NULL);
+    oracle_shard_resolve(h, xb, NULL);
   }
-  oracle_shard_gather(h, fin);
-  rc = oracle_shard_end(h, fin, out_pl, cap_pl, n_pl, out_status, out_nodes, out_perm, stats);
-  free(claim); free(delta); free(fin);
+  rc = oracle_shard_end(h, out_pl, cap_pl, n_pl, out_status, out_nodes, out_perm, stats);
+  free(xb);
   return rc;
 }
 

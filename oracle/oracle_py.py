@@ -48,7 +48,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, want_matrices=False):
+def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, want_matrices=False, alternatives=0):
     """Returns dict(placements, status, nodes_after, perm, stats[, fit, score])."""
     from grove_b200 import tables as T
 
@@ -69,7 +69,7 @@ def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, 
     stats = OracleStats()
     rc = lib().oracle_run_cycle(
         _p(nodes), C.c_uint32(n), C.c_uint32(n_levels), _p(gangs), C.c_uint32(G), _p(cliques), C.c_uint32(Q),
-        _p(scopes), C.c_uint32(S), C.c_uint32(max_rounds), C.c_int32(threads), _p(pl), C.c_uint32(len(pl)),
+        _p(scopes), C.c_uint32(S), C.c_uint32(max_rounds), C.c_uint32(alternatives), C.c_int32(threads), _p(pl), C.c_uint32(len(pl)),
         C.byref(n_pl), _p(st), _p(nodes_after), _p(perm), _p(fit), _p(score), C.byref(stats))
     if rc != 0:
         raise RuntimeError(f"oracle_run_cycle failed: {rc}")
@@ -100,21 +100,19 @@ class OracleStepper:
     """CPU stand-in for PlacementEngine's stepping interface (same protocol, numpy buffers), used by the
     world_size-2 gloo test of grove_b200.sharded.run_sharded_cycle."""
 
-    def __init__(self, nodes, n_levels, gangs, cliques, scopes, rank, world, threads=1):
+    def __init__(self, nodes, n_levels, gangs, cliques, scopes, rank, world, threads=1, alternatives=0):
         from grove_b200 import tables as T
         self.T = T
         self.nodes = np.ascontiguousarray(nodes, dtype=T.node_dt)
         self.gangs = np.ascontiguousarray(gangs, dtype=T.gang_dt)
         self.cliques = np.ascontiguousarray(cliques, dtype=T.clique_dt)
         self.scopes = np.ascontiguousarray(scopes, dtype=T.scope_dt)
-        self.L, self.rank, self.world, self.threads = n_levels, rank, world, threads
+        self.L, self.rank, self.world, self.threads, self.alternatives = n_levels, rank, world, threads, alternatives
         self.h = None
         L = lib()
-        for f in ("oracle_shard_begin", "oracle_shard_eval", "oracle_shard_commit", "oracle_shard_apply",
-                  "oracle_shard_gather", "oracle_shard_end"):
+        for f in ("oracle_shard_begin", "oracle_shard_eval", "oracle_shard_resolve", "oracle_shard_end"):
             getattr(L, f).restype = C.c_int32
-        for f in ("oracle_shard_claim_words", "oracle_shard_delta_words", "oracle_shard_final_words"):
-            getattr(L, f).restype = C.c_uint32
+        L.oracle_shard_xbuf_words.restype = C.c_uint32
 
     def _chk(self, rc):
         if rc != 0:
@@ -125,29 +123,20 @@ class OracleStepper:
         self._chk(lib().oracle_shard_begin(
             _p(self.nodes), C.c_uint32(len(self.nodes)), C.c_uint32(self.L), _p(self.gangs), C.c_uint32(len(self.gangs)),
             _p(self.cliques), C.c_uint32(len(self.cliques)), _p(self.scopes), C.c_uint32(len(self.scopes)),
-            C.c_uint32(0), C.c_int32(self.threads), C.c_uint32(self.rank), C.c_uint32(self.world), None, None, C.byref(self.h)))
-        self.claim = np.zeros(lib().oracle_shard_claim_words(self.h), dtype=np.int32)
-        self.delta = np.zeros(lib().oracle_shard_delta_words(self.h), dtype=np.int32)
-        self.fin = np.zeros(max(lib().oracle_shard_final_words(self.h), 1), dtype=np.int32)
-        self.n_fin = lib().oracle_shard_final_words(self.h)
+            C.c_uint32(0), C.c_uint32(self.alternatives), C.c_int32(self.threads), C.c_uint32(self.rank),
+            C.c_uint32(self.world), None, None, C.byref(self.h)))
+        self.n_x = lib().oracle_shard_xbuf_words(self.h)
+        self.xbuf = np.zeros(max(self.n_x, 1), dtype=np.int32)
 
     def round_eval(self):
         go = C.c_uint32(0)
-        self._chk(lib().oracle_shard_eval(self.h, _p(self.claim), C.byref(go)))
-        return self.claim, len(self.claim), bool(go.value)
+        self._chk(lib().oracle_shard_eval(self.h, _p(self.xbuf), C.byref(go)))
+        return self.xbuf, self.n_x, bool(go.value)
 
-    def round_commit(self):
-        self._chk(lib().oracle_shard_commit(self.h, _p(self.claim), _p(self.delta)))
-        return self.delta, len(self.delta)
-
-    def round_apply(self):
+    def round_resolve(self):
         r = C.c_uint32(0)
-        self._chk(lib().oracle_shard_apply(self.h, _p(self.delta), C.byref(r)))
+        self._chk(lib().oracle_shard_resolve(self.h, _p(self.xbuf), C.byref(r)))
         return r.value
-
-    def cycle_gather(self):
-        self._chk(lib().oracle_shard_gather(self.h, _p(self.fin)))
-        return self.fin, self.n_fin
 
     def cycle_end(self):
         T = self.T
@@ -157,7 +146,7 @@ class OracleStepper:
         after = np.zeros(len(self.nodes), dtype=T.node_dt)
         n_pl = C.c_uint32(0)
         stats = OracleStats()
-        self._chk(lib().oracle_shard_end(self.h, _p(self.fin), _p(pl), C.c_uint32(len(pl)), C.byref(n_pl), _p(st), _p(after),
+        self._chk(lib().oracle_shard_end(self.h, _p(pl), C.c_uint32(len(pl)), C.byref(n_pl), _p(st), _p(after),
                                          None, C.byref(stats)))
         self.h = None
         self.result = dict(placements=pl[: n_pl.value].copy(), status=st[: len(self.gangs)].copy(), nodes_after=after)

@@ -98,11 +98,9 @@ def _run_sharded_local(nodes, L, tabs, world):
             assert len(gos) == 1  # replicated state: every rank takes the same decision
             if not gos.pop():
                 break
-            reduce([(p, n) for p, n, _ in ev], "min")
-            reduce([e.round_commit() for e in engs], "sum")
-            rem = {e.round_apply() for e in engs}
-            assert len(rem) == 1
-        reduce([e.cycle_gather() for e in engs], "sum")
+            reduce([(p, n) for p, n, _ in ev], "sum")
+            for e in engs:
+                e.round_resolve()
         outs = []
         for e in engs:
             st = e.cycle_end()
