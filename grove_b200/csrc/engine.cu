@@ -3,11 +3,12 @@
 // the host sorts the topology once per label change, validates and uploads tables, and drives the
 // optimistic rounds.  There is no CPU fallback: without a CUDA device the engine cannot be created.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <array>
 #include <cstdlib>
 #include <cstring>
-#include <map>
+#include <functional>
 #include <new>
 #include <numeric>
 #include <string>
@@ -422,7 +423,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
                            uint32_t n_cliques, const grove_scope_t* scopes, uint32_t n_scopes) {
   if (!e || (n_gangs && (!gangs || !cliques || !scopes))) return GROVE_ERR_INVALID_ARG;
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
-  if (n_gangs >= (1u << 24)) return fail(e, GROVE_ERR_LIMIT, "too many gangs");
+  if (n_gangs >= (1u << 24)) return fail(e, GROVE_ERR_LIMIT, "too many gangs");  // order rank + sub-round tag share a claim word
   int32_t rc = validate(e, gangs, n_gangs, cliques, n_cliques, scopes, n_scopes);
   if (rc) return rc;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
@@ -442,13 +443,35 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
 // derived per-gang / per-clique tables: order rank, anchor (sorted index + ancestor ranges), entry slots
 static int32_t build_ginfo(grove_engine* e) {
   const uint32_t G = e->G, Q = e->Q;
+  const auto t_b0 = std::chrono::steady_clock::now();
   e->ginfo.assign(G, GangInfo{});
   e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0, 0, 0});
   e->sigs.clear();
-  std::map<std::array<uint32_t, 5>, uint32_t> sig_of;
+  // open-addressing table over (req_cpu, req_mem, req_gpu, class_mask, need_depth): templates repeat, so it stays tiny
+  std::vector<std::array<uint32_t, 6>> tab(1024, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
+  auto hash5 = [](const std::array<uint32_t, 5>& k) { uint32_t h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA6Bu ^ (k[2] << 20) ^ (k[3] << 4) ^ k[4]; return h ^ (h >> 15); };
+  std::array<uint32_t, 5> last_key{GROVE_NONE_U32, 0, 0, 0, 0};
+  uint32_t last_sig = 0;
+  // order rank = position by (priority desc, index asc): a stable bucket pass over the distinct priorities
   std::vector<uint32_t> ord(G);
-  std::iota(ord.begin(), ord.end(), 0u);
-  std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
+  {
+    std::vector<int32_t> pr;
+    for (uint32_t g = 0; g < G; ++g) if (pr.empty() || e->gangs[g].priority != pr.back()) pr.push_back(e->gangs[g].priority);
+    std::sort(pr.begin(), pr.end(), std::greater<int32_t>());
+    pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+    if (pr.size() <= 1) {
+      std::iota(ord.begin(), ord.end(), 0u);
+    } else if (pr.size() <= 64) {
+      std::vector<uint32_t> cnt(pr.size() + 1, 0);
+      auto bucket = [&pr](int32_t p) { return uint32_t(std::lower_bound(pr.begin(), pr.end(), p, std::greater<int32_t>()) - pr.begin()); };
+      for (uint32_t g = 0; g < G; ++g) cnt[bucket(e->gangs[g].priority) + 1]++;
+      for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+      for (uint32_t g = 0; g < G; ++g) ord[cnt[bucket(e->gangs[g].priority)]++] = g;
+    } else {
+      std::iota(ord.begin(), ord.end(), 0u);
+      std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
+    }
+  }
   uint32_t pod_off = 0;
   for (uint32_t r = 0; r < G; ++r) e->ginfo[ord[r]].order = r;
   for (uint32_t gi = 0; gi < G; ++gi) {
@@ -457,11 +480,6 @@ static int32_t build_ginfo(grove_engine* e) {
     if (g.anchor_node != GROVE_NONE_U32 && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
     const uint32_t a = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
     in.anchor = a; in.pod_off = pod_off;
-    for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
-      uint32_t d = l < e->L ? e->tdom[size_t(a) * GROVE_MAX_LEVELS + l] : GROVE_DOM_ABSENT;
-      if (d == GROVE_DOM_ABSENT) { in.anc_lo[l] = a; in.anc_hi[l] = a; }
-      else { in.anc_lo[l] = e->dom_lo[l][d]; in.anc_hi[l] = e->dom_hi[l][d]; }
-    }
     uint32_t pods = 0;
     for (uint32_t si = 0; si < g.n_scopes; ++si) {
       const grove_scope_t& s = e->scopes[g.scope_off + si];
@@ -476,27 +494,50 @@ static int32_t build_ginfo(grove_engine* e) {
         // PodCliques stamped from one template (PCS / PCSG replicas) share requests, selector class and
         // binding depth: they share one fit-bitmap row
         const std::array<uint32_t, 5> key{q.req_cpu_milli, q.req_mem_mib, q.req_gpu, q.class_mask, nd};
-        auto it = sig_of.find(key);
-        if (it == sig_of.end()) {
-          it = sig_of.emplace(key, uint32_t(e->sigs.size())).first;
+        if (key == last_key) { e->cinfo[qi] = CliqueInfo{gi, nd, last_sig, 0}; pods += q.replicas; continue; }
+        if (e->sigs.size() * 2 >= tab.size()) {  // grow and re-insert
+          std::vector<std::array<uint32_t, 6>> nt(tab.size() * 4, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
+          for (const auto& r : tab) if (r[5] != GROVE_NONE_U32) {
+            size_t h = hash5({r[0], r[1], r[2], r[3], r[4]}) & (nt.size() - 1);
+            while (nt[h][5] != GROVE_NONE_U32) h = (h + 1) & (nt.size() - 1);
+            nt[h] = r;
+          }
+          tab.swap(nt);
+        }
+        size_t h = hash5(key) & (tab.size() - 1);
+        while (tab[h][5] != GROVE_NONE_U32 && !(tab[h][0] == key[0] && tab[h][1] == key[1] && tab[h][2] == key[2] && tab[h][3] == key[3] && tab[h][4] == key[4]))
+          h = (h + 1) & (tab.size() - 1);
+        if (tab[h][5] == GROVE_NONE_U32) {
+          tab[h] = {key[0], key[1], key[2], key[3], key[4], uint32_t(e->sigs.size())};
           e->sigs.push_back(make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu, uint32_t(q.class_mask) | (nd << 16)));
         }
-        e->cinfo[qi] = CliqueInfo{gi, nd, it->second, 0};
+        e->cinfo[qi] = CliqueInfo{gi, nd, tab[h][5], 0};
+        last_key = key; last_sig = tab[h][5];
         pods += q.replicas;
       }
     }
     pod_off += pods;
   }
   e->P = pod_off;
+  const auto t_b1 = std::chrono::steady_clock::now();
   for (uint32_t qi = 0; qi < Q; ++qi)
     if (e->cinfo[qi].gang == GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique row owned by no gang");
   e->n_sigs = uint32_t(e->sigs.size());
   CU_TRY(e, e->d_ginfo.ensure(G)); CU_TRY(e, e->d_cinfo.ensure(Q)); CU_TRY(e, e->d_sigs.ensure(e->n_sigs));
   CU_TRY(e, e->d_sig_stamp.ensure(e->n_sigs)); CU_TRY(e, e->d_sig_list.ensure(e->n_sigs));
   if (e->n_sigs) CU_TRY(e, cudaMemcpyAsync(e->d_sigs.p, e->sigs.data(), sizeof(uint4) * e->n_sigs, cudaMemcpyHostToDevice, e->stream));
-  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo.data(), sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
+  if (G) {
+    CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo.data(), sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
+    k_anchor<<<(G + 255) / 256, 256, 0, e->stream>>>(make_topo(e), e->d_ginfo.p, G);  // ancestor ranges from the device-resident tree
+    CU_TRY(e, cudaGetLastError());
+  }
   if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo.data(), sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
   e->ginfo_dirty = false;
+  if (std::getenv("GROVE_DEBUG_HOST")) {
+    const auto t_b2 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    std::fprintf(stderr, "build_ginfo: tables %ld us, upload %ld us\n", us(t_b0, t_b1), us(t_b1, t_b2));
+  }
   return GROVE_OK;
 }
 
@@ -593,8 +634,9 @@ static int32_t round_resolve(grove_engine* e, bool timed) {
   Topo tp = make_topo(e); Tables tb = make_tables(e); RoundBufs rb = make_bufs(e);
   CU_TRY(e, cudaMemsetAsync(e->d_taken.p, 0, e->N, e->stream));
   CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));
+  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // claims are sub-round tagged; reset once per round
   uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
-  const uint32_t want = (na_all * 32 + 255) / 256;
+  const uint32_t want = na_all <= 64u ? 1u : (na_all * 32 + 255) / 256;  // few gangs: one CTA, grid barriers are then nearly free
   const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, uint32_t(e->resolve_blocks_per_sm) * e->n_sm));
   void* args[] = {&tp, &tb, &rb, &nres, &rn};
   CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(256), args, 0, e->stream));
@@ -605,9 +647,10 @@ static int32_t round_resolve(grove_engine* e, bool timed) {
 
 static int32_t finish_cycle(grove_engine* e, grove_cycle_stats_t* stats) {
   const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
-  k_finalize<<<1, 1024, 0, e->stream>>>(tp, tb, rb, e->d_perm.p, e->d_status.p, e->d_out.p, e->d_totals.p);
+  k_finalize<<<1, 1024, 0, e->stream>>>(tp, tb, rb, e->d_status.p, e->d_totals.p);
+  if (e->G) k_emit<<<(e->G * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb, e->d_perm.p, e->d_status.p, e->d_out.p);
   CU_TRY(e, cudaGetLastError());
-  e->launches += 1;
+  e->launches += 2;
   CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_totals.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
   if (e->G) CU_TRY(e, cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(grove_gang_status_t) * e->G, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -640,7 +683,9 @@ static int32_t after_prepare(grove_engine* e, uint32_t* go) {
 int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e) return GROVE_ERR_INVALID_ARG;
   if (e->cfg.world > 1) return fail(e, GROVE_ERR_STATE, "sharded handle: drive the cycle with grove_round_* and reduce between the steps");
+  const auto t_h0 = std::chrono::steady_clock::now();
   int32_t rc = grove_cycle_begin(e);
+  const auto t_h1 = std::chrono::steady_clock::now();
   if (rc) return rc;
   float ms_fit = 0, ms_score = 0, ms_admit = 0, ms_commit = 0;
   CU_TRY(e, cudaEventRecord(e->ev[8], e->stream));
@@ -672,7 +717,13 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     }
   }
   CU_TRY(e, cudaEventRecord(e->ev[9], e->stream));
+  const auto t_h2 = std::chrono::steady_clock::now();
   rc = finish_cycle(e, nullptr);
+  if (std::getenv("GROVE_DEBUG_HOST")) {
+    const auto t_h3 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    std::fprintf(stderr, "host: begin %ld us, rounds %ld us, finish %ld us\n", us(t_h0, t_h1), us(t_h1, t_h2), us(t_h2, t_h3));
+  }
   if (rc) { e->in_cycle = false; return rc; }
   float tot = 0; cudaEventElapsedTime(&tot, e->ev[8], e->ev[9]);
   e->last.ms_fit = ms_fit; e->last.ms_score = ms_score; e->last.ms_admit = ms_admit; e->last.ms_commit = ms_commit; e->last.ms_total = tot;

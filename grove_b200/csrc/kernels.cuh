@@ -136,6 +136,21 @@ __global__ void k_update(const uint32_t* __restrict__ idx_sorted, const grove_no
                        (nd.flags & 0xFFFFu) | (uint32_t(vdepth[s]) << 16));
 }
 
+// anchor ancestors: node range of the anchor's domain at every level ([a,a) where its label is absent)
+__global__ void k_anchor(Topo tp, GangInfo* ginfo, uint32_t G) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const uint32_t a = ginfo[g].anchor;
+  const uint4 dm = tp.ndom[a];
+  const uint32_t d[4] = {dm.x, dm.y, dm.z, dm.w};
+#pragma unroll
+  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
+    uint32_t lo = a, hi = a;
+    if (l < (int)tp.L && d[l] != GROVE_DOM_ABSENT) { lo = tp.dom_lo[l][d[l]]; hi = tp.dom_hi[l][d[l]]; }
+    ginfo[g].anc_lo[l] = lo; ginfo[g].anc_hi[l] = hi;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // round bookkeeping: which gangs are evaluated this round, and their clique rows
 // ------------------------------------------------------------------------------------------------
@@ -839,11 +854,14 @@ __global__ void k_dbg_init(uint32_t* dbg, uint32_t G) {
   if (g < G) dbg[g * 4 + 3] = GROVE_NONE_U32;
 }
 
+#ifndef GROVE_ADMIT_MINBLOCKS
+#define GROVE_ADMIT_MINBLOCKS 6
+#endif
 constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
 constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads) k_admit(Topo tp, Tables tb, RoundBufs rb) {
+__global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ai = blockIdx.x;
@@ -990,11 +1008,14 @@ __global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs r
   }
   __syncwarp();
   for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
+    // claims carry the sub-round in their top bits so that a later sub-round always beats stale claims of
+    // an earlier one (atomicMin): nothing has to be withdrawn between sub-rounds
+    const uint32_t tag = (GROVE_SUBROUNDS - 1u - sub) << 24;
     // ---- propose ----
     for (uint32_t ai = gw; ai < na; ai += nw) {
       const uint32_t g = rb.active_all[ai];
       if (rb.state[g] != GROVE_GANG_PENDING) continue;
-      const uint32_t nalt = rb.nalt[g], po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order;
+      const uint32_t nalt = rb.nalt[g], po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order | tag;
       uint32_t c = rb.cur[g], cnt = 0;
       while (c < nalt) {  // first alternative that touches no node committed earlier in this round
         cnt = rb.alt_n[size_t(g) * K + c];
@@ -1014,7 +1035,7 @@ __global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs r
     for (uint32_t ai = gw; ai < na; ai += nw) {
       const uint32_t g = rb.active_all[ai];
       if (rb.prop[g] != sub + 1 || rb.state[g] != GROVE_GANG_PENDING) continue;
-      const uint32_t po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order, c = rb.cur[g];
+      const uint32_t po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order | tag, c = rb.cur[g];
       const uint32_t cnt = rb.alt_n[size_t(g) * K + c];
       bool win = true;
       for (uint32_t i = lane; i < cnt; i += 32) win &= __ldcg(rb.claim + rb.alt_node[size_t(c) * P + po + i]) == order;
@@ -1038,22 +1059,13 @@ __global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs r
       }
     }
     grid.sync();
-    // ---- withdraw this sub-round's claims ----
-    for (uint32_t ai = gw; ai < na; ai += nw) {
-      const uint32_t g = rb.active_all[ai];
-      if (rb.prop[g] != sub + 1) continue;
-      const uint32_t po = tb.ginfo[g].pod_off, c = rb.cur[g], cnt = rb.alt_n[size_t(g) * K + c];
-      for (uint32_t i = lane; i < cnt; i += 32) rb.claim[rb.alt_node[size_t(c) * P + po + i]] = 0x7F7F7F7Fu;
-    }
-    grid.sync();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // outputs: compact the admitted gangs' entries into caller order / caller node indices
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_finalize(Topo tp, Tables tb, RoundBufs rb, const uint32_t* __restrict__ perm,
-                                                   grove_gang_status_t* status, grove_placement_t* out, uint32_t* totals) {
+__global__ void __launch_bounds__(1024) k_finalize(Topo tp, Tables tb, RoundBufs rb, grove_gang_status_t* status, uint32_t* totals) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_run, s_tot, s_adm, s_rej;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1076,26 +1088,35 @@ __global__ void __launch_bounds__(1024) k_finalize(Topo tp, Tables tb, RoundBufs
       if (lane == 31) s_tot = s;
     }
     __syncthreads();
-    const uint32_t off = s_run + s_warp[warp] + incl - cnt;
     if (g < tb.G) {
       grove_gang_status_t o;
-      o.state = st; o.round = rb.round[g]; o.n_pods = cnt; o.placement_off = off;
+      o.state = st; o.round = rb.round[g]; o.n_pods = cnt; o.placement_off = s_run + s_warp[warp] + incl - cnt;
       o.score_num = 0; o.score_den = 0; o.top_domain_lo = GROVE_NONE_U32;
       if (st == GROVE_GANG_ADMITTED) { o.score_num = rb.spec_score[g]; o.score_den = uint8_t(tp.L + 1); o.top_domain_lo = rb.spec_top[g]; }
       status[g] = o;
-      const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
-      for (uint32_t i = 0; i < cnt; ++i) {
-        grove_placement_t p;
-        p.clique = coff + (rb.ent_meta[po + i] & 0xFFu);
-        p.node = perm[rb.ent_node[po + i]];
-        out[off + i] = p;
-      }
     }
     __syncthreads();
     if (tid == 0) s_run += s_tot;
     __syncthreads();
   }
   if (tid == 0) { totals[0] = s_run; totals[1] = s_adm; totals[2] = s_rej; }
+}
+
+// one warp per gang: its entries -> caller node indices, at the offset k_finalize assigned
+__global__ void k_emit(Tables tb, RoundBufs rb, const uint32_t* __restrict__ perm, const grove_gang_status_t* __restrict__ status,
+                       grove_placement_t* out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= tb.G) return;
+  const grove_gang_status_t st = status[g];
+  if (st.state != GROVE_GANG_ADMITTED) return;
+  const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
+  for (uint32_t i = lane; i < st.n_pods; i += 32) {
+    grove_placement_t p;
+    p.clique = coff + (rb.ent_meta[po + i] & 0xFFu);
+    p.node = perm[rb.ent_node[po + i]];
+    out[st.placement_off + i] = p;
+  }
 }
 
 }  // namespace grove
