@@ -1,0 +1,346 @@
+// grove_host.cpp -- see grove_host.hpp.  Host-side mirror of the reference interfaces around the
+// placement hot path; the placement itself happens behind the C ABI (libgrove_place.so).
+#include "grove_host.hpp"
+
+#include <algorithm>
+#include <set>
+
+namespace grove::host {
+
+static Error mkerr(const char* code, const char* op, std::string msg) { return Error{code, op, std::move(msg)}; }
+
+// ---- namegen.go ------------------------------------------------------------------------------------
+std::string GeneratePodCliqueName(const std::string& owner, int replica, const std::string& t) {
+  return owner + "-" + std::to_string(replica) + "-" + t;
+}
+std::string GeneratePodCliqueScalingGroupName(const std::string& pcs, int replica, const std::string& name) {
+  return pcs + "-" + std::to_string(replica) + "-" + name;
+}
+std::string GenerateBasePodGangName(const std::string& pcs, int replica) { return pcs + "-" + std::to_string(replica); }
+std::string CreatePodGangNameFromPCSGFQN(const std::string& pcsgFQN, int idx) { return pcsgFQN + "-" + std::to_string(idx); }
+
+// ---- producer: syncflow.go:145-371 -------------------------------------------------------------------
+// createTopologyPackConstraint (syncflow.go:349-371): packDomain -> node-label key through the ordered
+// ClusterTopology levels; TAS disabled, no constraint, or an unknown domain => nil.  Only Required is set.
+static std::optional<TopologyConstraint> createTopologyPackConstraint(const std::vector<TopologyLevel>& levels, bool tas,
+                                                                      const std::optional<PackDomain>& req) {
+  if (!tas || !req) return std::nullopt;
+  for (const auto& l : levels)
+    if (l.Domain == req->packDomain) {
+      TopologyConstraint tc;
+      tc.PackConstraint = TopologyPackConstraint{l.Key, std::nullopt};
+      return tc;
+    }
+  return std::nullopt;  // stale domain: the reference logs and nullifies the constraint
+}
+
+static const PodCliqueTemplateSpec* findClique(const PodCliqueSet& pcs, const std::string& name) {
+  for (const auto& c : pcs.Cliques) if (c.Name == name) return &c;
+  return nullptr;
+}
+static const PodCliqueScalingGroupConfig* findScalingGroupForClique(const PodCliqueSet& pcs, const std::string& clique) {
+  for (const auto& g : pcs.PodCliqueScalingGroupConfigs)
+    if (std::find(g.CliqueNames.begin(), g.CliqueNames.end(), clique) != g.CliqueNames.end()) return &g;
+  return nullptr;
+}
+
+// buildPodCliqueInfo (syncflow.go:335-345); MinAvailable defaulted as the webhook does (defaulting/podcliqueset.go:74-83)
+static PclqInfo buildPodCliqueInfo(const std::vector<TopologyLevel>& levels, bool tas, const PodCliqueTemplateSpec& t, const std::string& fqn) {
+  PclqInfo p;
+  p.fqn = fqn; p.replicas = t.Replicas; p.minAvailable = t.MinAvailable.value_or(t.Replicas); p.templateName = t.Name;
+  p.topologyConstraint = createTopologyPackConstraint(levels, tas, t.Topology);
+  return p;
+}
+
+Err ComputeExpectedPodGangs(const PodCliqueSet& pcs, const std::vector<TopologyLevel>& levels, bool tas, std::vector<PodGangInfo>* out) {
+  out->clear();
+  // base PodGang per PCS replica: standalone cliques + PCSG replicas [0, minAvailable) (syncflow.go:172-275)
+  for (int r = 0; r < pcs.Replicas; ++r) {
+    PodGangInfo pg;
+    pg.fqn = GenerateBasePodGangName(pcs.Name, r);
+    pg.topologyConstraint = createTopologyPackConstraint(levels, tas, pcs.Topology);
+    for (const auto& t : pcs.Cliques)
+      if (!findScalingGroupForClique(pcs, t.Name))
+        pg.pclqs.push_back(buildPodCliqueInfo(levels, tas, t, GeneratePodCliqueName(pcs.Name, r, t.Name)));
+    for (const auto& cfg : pcs.PodCliqueScalingGroupConfigs) {
+      const int minAvailable = cfg.MinAvailable.value_or(1);
+      const std::string pcsgFQN = GeneratePodCliqueScalingGroupName(pcs.Name, r, cfg.Name);
+      for (int ri = 0; ri < minAvailable; ++ri) {
+        std::vector<std::string> fqns;
+        for (const auto& cn : cfg.CliqueNames) {
+          const PodCliqueTemplateSpec* t = findClique(pcs, cn);
+          if (!t) return mkerr("ERR_SYNC_PODGANG", "ComputeExpectedPodGangs",
+                               "PodCliqueScalingGroup \"" + cfg.Name + "\" references a PodClique \"" + cn + "\" that does not exist in the PodCliqueSet");
+          const std::string fqn = GeneratePodCliqueName(pcsgFQN, ri, cn);
+          pg.pclqs.push_back(buildPodCliqueInfo(levels, tas, *t, fqn));
+          fqns.push_back(fqn);
+        }
+        if (tas && cfg.Topology) {  // one TopologyConstraintGroupConfig per PCSG replica (syncflow.go:262-271)
+          TopologyConstraintGroupConfig gc;
+          gc.Name = pcsgFQN + "-" + std::to_string(ri);
+          gc.PodGroupNames = fqns;
+          gc.Topology = createTopologyPackConstraint(levels, tas, cfg.Topology);
+          pg.pcsgTopologyConstraints.push_back(std::move(gc));
+        }
+      }
+    }
+    out->push_back(std::move(pg));
+  }
+  // scaled PodGang per PCSG replica >= minAvailable (syncflow.go:277-333)
+  for (int r = 0; r < pcs.Replicas; ++r)
+    for (const auto& cfg : pcs.PodCliqueScalingGroupConfigs) {
+      const std::string pcsgFQN = GeneratePodCliqueScalingGroupName(pcs.Name, r, cfg.Name);
+      const int replicas = cfg.Replicas.value_or(1), minAvailable = cfg.MinAvailable.value_or(1);
+      for (int idx = 0, pr = minAvailable; idx < replicas - minAvailable; ++idx, ++pr) {
+        PodGangInfo pg;
+        pg.fqn = CreatePodGangNameFromPCSGFQN(pcsgFQN, idx);
+        pg.baseFqn = GenerateBasePodGangName(pcs.Name, r);
+        for (const auto& cn : cfg.CliqueNames) {
+          const PodCliqueTemplateSpec* t = findClique(pcs, cn);
+          if (!t) return mkerr("ERR_SYNC_PODGANG", "ComputeExpectedPodGangs", "PodCliqueScalingGroup references unknown PodClique \"" + cn + "\"");
+          pg.pclqs.push_back(buildPodCliqueInfo(levels, tas, *t, GeneratePodCliqueName(pcsgFQN, pr, cn)));
+        }
+        // PCSG constraint if set, else fall back to the PCS constraint (syncflow.go:311-324)
+        if (tas) pg.topologyConstraint = cfg.Topology ? createTopologyPackConstraint(levels, tas, cfg.Topology)
+                                                      : createTopologyPackConstraint(levels, tas, pcs.Topology);
+        out->push_back(std::move(pg));
+      }
+    }
+  return std::nullopt;
+}
+
+PodGang BuildPodGang(const PodCliqueSet& pcs, const PodGangInfo& info) {
+  PodGang pg;
+  pg.Namespace = pcs.Namespace; pg.Name = info.fqn;
+  pg.Labels["grove.io/scheduler-name"] = GpuBackend::kName;
+  pg.Spec.Topology = info.topologyConstraint;
+  pg.Spec.TopologyConstraintGroupConfigs = info.pcsgTopologyConstraints;
+  pg.Spec.PriorityClassName = pcs.PriorityClassName;
+  pg.BasePodGangName = info.baseFqn;
+  for (const auto& p : info.pclqs) {  // createPodGroupsForPodGang (podgang.go:165-186)
+    PodGroup g;
+    g.Name = p.fqn; g.MinReplicas = p.minAvailable; g.Topology = p.topologyConstraint;
+    for (int i = 0; i < p.replicas; ++i) g.PodReferences.push_back({pcs.Namespace, p.fqn + "-" + std::to_string(i)});
+    std::sort(g.PodReferences.begin(), g.PodReferences.end(), [](const NamespacedName& a, const NamespacedName& b) { return a.Name < b.Name; });
+    pg.Spec.PodGroups.push_back(std::move(g));
+    if (const PodCliqueTemplateSpec* t = findClique(pcs, p.templateName)) pg.PodGroupRequests[p.fqn] = t->Requests;
+  }
+  return pg;
+}
+
+// ---- GpuBackend ----------------------------------------------------------------------------------------
+GpuBackend::GpuBackend(int device, std::string classLabelKey) : device_(device), classKey_(std::move(classLabelKey)) {}
+GpuBackend::~GpuBackend() { if (engine_) grove_engine_destroy(engine_); }
+
+Err GpuBackend::Init() {
+  if (levels_.empty()) return std::nullopt;  // the engine is created once the topology is known (SyncTopology)
+  if (engine_ && engineLevels_ == levels_.size()) return std::nullopt;
+  if (engine_) { grove_engine_destroy(engine_); engine_ = nullptr; }
+  grove_config_t cfg{};
+  cfg.abi_version = GROVE_ABI_VERSION; cfg.device = device_; cfg.n_levels = uint32_t(levels_.size());
+  const int32_t rc = grove_engine_create(&cfg, &engine_);
+  if (rc != GROVE_OK) { engine_ = nullptr; return mkerr("ERR_INIT_BACKEND", "Init", "grove_engine_create failed with " + std::to_string(rc) + " (there is no CPU fallback)"); }
+  engineLevels_ = uint32_t(levels_.size());
+  return std::nullopt;
+}
+
+Err GpuBackend::SyncTopology(const std::vector<TopologyLevel>& levels) {
+  if (levels.empty() || levels.size() > GROVE_MAX_LEVELS)
+    return mkerr("ERR_SYNC_TOPOLOGY", "SyncTopology", "the engine supports 1.." + std::to_string(GROVE_MAX_LEVELS) + " topology levels");
+  levels_ = levels;  // ordered broadest -> narrowest, as desiredKAITopologyLevels hands them over (kai/topology.go:103-135)
+  return std::nullopt;
+}
+Err GpuBackend::OnTopologyDelete() { levels_.clear(); return std::nullopt; }
+std::pair<bool, std::string> GpuBackend::CheckTopologyDrift(const std::vector<TopologyLevel>& levels) const {
+  if (levels.size() != levels_.size()) return {false, "level count differs"};
+  for (size_t i = 0; i < levels.size(); ++i)
+    if (levels[i].Key != levels_[i].Key) return {false, "level " + std::to_string(i) + " key " + levels_[i].Key + " != " + levels[i].Key};
+  return {true, ""};
+}
+
+Err GpuBackend::ValidatePodCliqueSet(const PodCliqueSet& pcs) const {
+  std::vector<PodGangInfo> infos;
+  if (auto e = ComputeExpectedPodGangs(pcs, levels_, true, &infos)) return e;
+  for (const auto& pg : infos) {
+    int pods = 0;
+    for (const auto& p : pg.pclqs) pods += p.replicas;
+    if (pg.pclqs.size() > GROVE_MAX_GANG_CLIQUES || pods > int(GROVE_MAX_GANG_PODS) || pg.pcsgTopologyConstraints.size() + 1 > GROVE_MAX_GANG_SCOPES)
+      return mkerr("ERR_VALIDATE_PCS", "ValidatePodCliqueSet", "PodGang " + pg.fqn + " exceeds the gpu-scheduler limits (32 PodCliques / 32 constraint groups / 128 pods per PodGang)");
+  }
+  return std::nullopt;
+}
+
+Err GpuBackend::SyncPodGang(const PodGang& podGang) {
+  pending_[podGang.Namespace + "/" + podGang.Name] = podGang;  // a copy: the cache-owned object is neither mutated nor retained
+  return std::nullopt;
+}
+Err GpuBackend::OnPodGangDelete(const PodGang& podGang) { pending_.erase(podGang.Namespace + "/" + podGang.Name); return std::nullopt; }
+
+Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
+  *out = Tables{};
+  if (levels_.empty()) return mkerr("ERR_SYNC_PODGANG", "Encode", "no ClusterTopology levels synced");
+  const uint32_t L = uint32_t(levels_.size());
+  // nodes: interned label value per level; selector class from one label key; taints per class
+  std::vector<std::map<std::string, uint32_t>> intern(L);
+  std::map<std::string, uint32_t> classOf;  // label value -> class id (0 = label absent)
+  std::vector<std::set<std::string>> classTaints(1);
+  std::vector<std::string> classValue(1, "");
+  out->nodes.resize(nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    const Node& n = nodes[i];
+    grove_node_t& r = out->nodes[i];
+    r.free_cpu_milli = n.alloc_cpu_milli > n.used_cpu_milli ? n.alloc_cpu_milli - n.used_cpu_milli : 0;
+    r.free_mem_mib = n.alloc_mem_mib > n.used_mem_mib ? n.alloc_mem_mib - n.used_mem_mib : 0;
+    r.free_gpu = uint16_t(n.alloc_gpu > n.used_gpu ? n.alloc_gpu - n.used_gpu : 0);
+    r.free_pods = uint16_t(n.alloc_pods > n.used_pods ? n.alloc_pods - n.used_pods : 0);
+    uint32_t cls = 0;
+    if (auto it = n.Labels.find(classKey_); it != n.Labels.end()) {
+      auto [ci, fresh] = classOf.emplace(it->second, uint32_t(classOf.size() + 1));
+      if (fresh) { classTaints.emplace_back(); classValue.push_back(it->second); }
+      cls = ci->second;
+      if (cls > 15) return mkerr("ERR_SYNC_PODGANG", "Encode", "more than 15 values of the selector-class label " + classKey_);
+    }
+    for (const auto& t : n.TaintKeys) classTaints[cls].insert(t);
+    r.flags = (n.Unschedulable ? 0u : GROVE_NODE_SCHEDULABLE) | (cls << GROVE_NODE_CLASS_SHIFT);
+    for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+      r.dom[l] = GROVE_DOM_ABSENT;
+      if (l >= L) continue;
+      if (auto it = n.Labels.find(levels_[l].Key); it != n.Labels.end())
+        r.dom[l] = intern[l].emplace(it->second, uint32_t(intern[l].size())).first->second;
+    }
+  }
+  auto levelOf = [this](const std::optional<TopologyConstraint>& tc, uint8_t* lvl) -> Err {
+    *lvl = GROVE_LEVEL_NONE;
+    if (!tc || !tc->PackConstraint || !tc->PackConstraint->Required) return std::nullopt;
+    for (size_t l = 0; l < levels_.size(); ++l) if (levels_[l].Key == *tc->PackConstraint->Required) { *lvl = uint8_t(l); return std::nullopt; }
+    return mkerr("ERR_SYNC_PODGANG", "Encode", "Required topology key " + *tc->PackConstraint->Required + " is not a level of the synced ClusterTopology");
+  };
+  std::map<std::string, uint32_t> row;  // PodGang key -> gang row
+  for (const auto& kv : pending_) row.emplace(kv.first, uint32_t(row.size()));
+  std::map<std::string, uint32_t> nodeIndex;
+  for (size_t i = 0; i < nodes.size(); ++i) nodeIndex[nodes[i].Name] = uint32_t(i);
+  for (const auto& [key, pg] : pending_) {
+    grove_gang_t g{};
+    g.clique_off = uint32_t(out->cliques.size()); g.scope_off = uint32_t(out->scopes.size());
+    g.anchor_node = GROVE_NONE_U32; g.base_gang = GROVE_NONE_U32; g.preferred = GROVE_LEVEL_NONE;
+    g.flags = pg.Gated ? GROVE_GANG_GATED : 0;
+    if (auto e = levelOf(pg.Spec.Topology, &g.level)) return e;
+    if (auto it = priorityClasses_.find(pg.Spec.PriorityClassName); it != priorityClasses_.end()) g.priority = it->second;
+    if (!pg.BasePodGangName.empty())
+      if (auto it = row.find(pg.Namespace + "/" + pg.BasePodGangName); it != row.end()) g.base_gang = it->second;
+    if (pg.Spec.ReuseReservationRef) {  // locality hint: score distance against where that PodGang was placed
+      auto it = lastNode_.find(pg.Spec.ReuseReservationRef->Namespace + "/" + pg.Spec.ReuseReservationRef->Name);
+      if (it != lastNode_.end()) if (auto nt = nodeIndex.find(it->second); nt != nodeIndex.end()) g.anchor_node = nt->second;
+    }
+    // scopes: the loose PodGroups first (one implicit scope), then one scope per TopologyConstraintGroupConfig
+    std::set<std::string> grouped;
+    for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) for (const auto& n : gc.PodGroupNames) grouped.insert(n);
+    std::vector<std::pair<uint8_t, std::vector<uint32_t>>> scopes;  // (level, PodGroup indices)
+    std::vector<uint32_t> loose;
+    for (uint32_t i = 0; i < pg.Spec.PodGroups.size(); ++i) if (!grouped.count(pg.Spec.PodGroups[i].Name)) loose.push_back(i);
+    if (!loose.empty()) scopes.push_back({uint8_t(GROVE_LEVEL_NONE), loose});
+    for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) {
+      uint8_t lvl; if (auto e = levelOf(gc.Topology, &lvl)) return e;
+      std::vector<uint32_t> members;
+      for (const auto& n : gc.PodGroupNames) {
+        auto it = std::find_if(pg.Spec.PodGroups.begin(), pg.Spec.PodGroups.end(), [&n](const PodGroup& p) { return p.Name == n; });
+        if (it == pg.Spec.PodGroups.end()) return mkerr("ERR_SYNC_PODGANG", "Encode", "group config " + gc.Name + " names unknown PodGroup " + n);
+        members.push_back(uint32_t(it - pg.Spec.PodGroups.begin()));
+      }
+      if (!members.empty()) scopes.push_back({lvl, members});
+    }
+    uint32_t rel = 0, pods = 0;
+    for (size_t si = 0; si < scopes.size(); ++si) {
+      grove_scope_t s{}; s.first_clique = uint16_t(rel); s.n_cliques = uint16_t(scopes[si].second.size()); s.level = scopes[si].first;
+      out->scopes.push_back(s);
+      for (uint32_t gi : scopes[si].second) {
+        const PodGroup& p = pg.Spec.PodGroups[gi];
+        grove_clique_t c{};
+        PodGang::Requests rq;
+        if (auto it = pg.PodGroupRequests.find(p.Name); it != pg.PodGroupRequests.end()) rq = it->second;
+        c.req_cpu_milli = rq.cpu_milli; c.req_mem_mib = rq.mem_mib; c.req_gpu = rq.gpu;
+        if (p.MinReplicas < 0 || p.MinReplicas > 255 || p.PodReferences.size() > 255 || size_t(p.MinReplicas) > p.PodReferences.size())
+          return mkerr("ERR_SYNC_PODGANG", "Encode", "PodGroup " + p.Name + ": MinReplicas / PodReferences out of range");
+        c.min_replicas = uint8_t(p.MinReplicas); c.replicas = uint8_t(p.PodReferences.size());
+        if (auto e = levelOf(p.Topology, &c.level)) return e;
+        c.scope = uint8_t(si);
+        // class mask: classes whose label value satisfies the nodeSelector and whose taints are all tolerated
+        uint16_t mask = 0;
+        auto sel = rq.nodeSelector.find(classKey_);
+        for (uint32_t cl = 0; cl < classValue.size(); ++cl) {
+          if (sel != rq.nodeSelector.end() && (cl == 0 || classValue[cl] != sel->second)) continue;
+          bool tolerated = true;
+          for (const auto& t : classTaints[cl]) tolerated &= std::find(rq.tolerationKeys.begin(), rq.tolerationKeys.end(), t) != rq.tolerationKeys.end();
+          if (tolerated) mask |= uint16_t(1u << cl);
+        }
+        c.class_mask = mask;
+        out->cliques.push_back(c);
+        out->cliqueOf.push_back({uint32_t(out->gangs.size()), gi});
+        pods += c.replicas; ++rel;
+      }
+    }
+    if (rel == 0 || rel > GROVE_MAX_GANG_CLIQUES || scopes.size() > GROVE_MAX_GANG_SCOPES || pods > GROVE_MAX_GANG_PODS)
+      return mkerr("ERR_SYNC_PODGANG", "Encode", "PodGang " + key + " exceeds the gpu-scheduler limits");
+    g.n_cliques = uint16_t(rel); g.n_scopes = uint16_t(scopes.size());
+    out->gangs.push_back(g);
+    out->gangNames.push_back(key);
+  }
+  return std::nullopt;
+}
+
+Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* bindings, std::map<std::string, PodGangStatus>* statuses,
+                         grove_cycle_stats_t* stats) {
+  bindings->clear(); statuses->clear();
+  if (pending_.empty()) return std::nullopt;
+  if (auto e = Init()) return e;
+  if (!engine_) return mkerr("ERR_SYNC_PODGANG", "RunCycle", "no ClusterTopology synced");
+  Tables t;
+  if (auto e = Encode(nodes, &t)) return e;
+  auto chk = [this](int32_t rc, const char* what) -> Err {
+    if (rc == GROVE_OK) return std::nullopt;
+    return mkerr("ERR_SYNC_PODGANG", what, std::string(grove_last_error(engine_)) + " (" + std::to_string(rc) + ")");
+  };
+  if (auto e = chk(grove_load_nodes(engine_, t.nodes.data(), uint32_t(t.nodes.size())), "grove_load_nodes")) return e;
+  if (auto e = chk(grove_submit_gangs(engine_, t.gangs.data(), uint32_t(t.gangs.size()), t.cliques.data(), uint32_t(t.cliques.size()),
+                                      t.scopes.data(), uint32_t(t.scopes.size())), "grove_submit_gangs")) return e;
+  grove_cycle_stats_t st{};
+  if (auto e = chk(grove_run_cycle(engine_, &st), "grove_run_cycle")) return e;
+  if (stats) *stats = st;
+  std::vector<grove_placement_t> pl(st.pods_bound + 1);
+  uint32_t n = 0;
+  if (auto e = chk(grove_get_placements(engine_, pl.data(), uint32_t(pl.size()), &n), "grove_get_placements")) return e;
+  std::vector<grove_gang_status_t> gs(t.gangs.size());
+  if (auto e = chk(grove_get_gang_status(engine_, gs.data(), uint32_t(gs.size())), "grove_get_gang_status")) return e;
+  std::vector<uint32_t> seen(t.cliques.size(), 0);  // the r-th entry of a clique binds its r-th PodReference
+  for (uint32_t i = 0; i < n; ++i) {
+    const auto [grow, pgi] = t.cliqueOf[pl[i].clique];
+    const PodGang& pg = pending_.at(t.gangNames[grow]);
+    const PodGroup& grp = pg.Spec.PodGroups[pgi];
+    const NamespacedName& pod = grp.PodReferences[seen[pl[i].clique]++];
+    bindings->push_back({pod.Namespace, pod.Name, nodes[pl[i].node].Name});
+  }
+  for (size_t g = 0; g < gs.size(); ++g) {
+    PodGangStatus s;
+    switch (gs[g].state) {
+      case GROVE_GANG_ADMITTED:
+        s.Phase = PodGangPhase::Starting; s.Scheduled = true;
+        s.PlacementScore = double(gs[g].score_num) / double(gs[g].score_den);
+        break;
+      case GROVE_GANG_REJECTED: s.ScheduledReason = "Unschedulable"; break;
+      case GROVE_GANG_BASE_REJECTED: s.ScheduledReason = "BaseNotScheduled"; break;
+      case GROVE_GANG_GATED_SKIP: s.ScheduledReason = "Gated"; break;
+      default: s.ScheduledReason = "Pending"; break;
+    }
+    (*statuses)[t.gangNames[g]] = s;
+  }
+  // scheduled PodGangs leave the pending set; remember where they landed for ReuseReservationRef hints
+  for (uint32_t i = 0, at = 0; i < gs.size(); ++i) {
+    if (gs[i].state != GROVE_GANG_ADMITTED) continue;
+    if (gs[i].n_pods) lastNode_[t.gangNames[i]] = nodes[pl[gs[i].placement_off].node].Name;
+    pending_.erase(t.gangNames[i]);
+    (void)at;
+  }
+  return std::nullopt;
+}
+
+}  // namespace grove::host

@@ -1,0 +1,246 @@
+// Host-side mirror tests.  The producer cases are the reference's own table-driven vectors
+// (/root/reference operator/internal/controller/podcliqueset/components/podgang/syncflow_test.go:740-953
+// TestComputeExpectedPodGangs and :965-1420 TestComputeExpectedPodGangsWithTopologyConstraints),
+// transcribed: same inputs, same expected PodGang names, counts and topology keys.
+//   test_host cpu   producer + encoder (no GPU)        test_host gpu   + GpuBackend cycles on cuda:0
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+
+#include "../../grove_b200/csrc/host/grove_host.hpp"
+
+using namespace grove::host;
+
+static int g_fail = 0;
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "FAIL %s:%d %s\n", __FILE__, __LINE__, #c); ++g_fail; } } while (0)
+
+static PodCliqueTemplateSpec clq(const char* name, int replicas, int minAvail, const char* pack = nullptr) {
+  PodCliqueTemplateSpec t; t.Name = name; t.Replicas = replicas; t.MinAvailable = minAvail;
+  if (pack) t.Topology = PackDomain{pack};
+  return t;
+}
+static PodCliqueScalingGroupConfig sg(const char* name, int replicas, int minAvail, std::vector<std::string> cliques, const char* pack = nullptr) {
+  PodCliqueScalingGroupConfig g; g.Name = name; g.Replicas = replicas; g.MinAvailable = minAvail; g.CliqueNames = std::move(cliques);
+  if (pack) g.Topology = PackDomain{pack};
+  return g;
+}
+static std::set<std::string> names(const std::vector<PodGangInfo>& v, bool scaled) {
+  std::set<std::string> s; for (const auto& p : v) if (p.baseFqn.empty() != scaled) s.insert(p.fqn); return s;
+}
+static std::string key(const std::optional<TopologyConstraint>& tc) {
+  return (tc && tc->PackConstraint && tc->PackConstraint->Required) ? *tc->PackConstraint->Required : std::string();
+}
+
+static void test_compute_expected_podgangs() {  // syncflow_test.go:740-953
+  struct Case { const char* name; int pcsReplicas; std::vector<PodCliqueTemplateSpec> pclqs; std::vector<PodCliqueScalingGroupConfig> pcsgs;
+                size_t n; std::set<std::string> base, scaled; };
+  std::vector<Case> cases = {
+    {"Simple PCS with standalone PCLQs only", 2, {clq("worker", 3, 2)}, {}, 2, {"test-pcs-0", "test-pcs-1"}, {}},
+    {"PCS with PCSG having minAvailable=1", 1, {clq("sg-worker", 2, 2)}, {sg("scaling-group", 3, 1, {"sg-worker"})}, 3, {"test-pcs-0"},
+     {"test-pcs-0-scaling-group-0", "test-pcs-0-scaling-group-1"}},
+    {"PCS with mixed standalone PCLQ and PCSG", 1, {clq("standalone", 2, 1), clq("scalable", 3, 2)}, {sg("sg", 4, 2, {"scalable"})}, 3,
+     {"test-pcs-0"}, {"test-pcs-0-sg-0", "test-pcs-0-sg-1"}},
+    {"Multiple PCS replicas with PCSG", 2, {clq("worker", 2, 1)}, {sg("worker-sg", 2, 1, {"worker"})}, 4, {"test-pcs-0", "test-pcs-1"},
+     {"test-pcs-0-worker-sg-0", "test-pcs-1-worker-sg-0"}},
+    {"PCSG with minAvailable equals replicas", 1, {clq("worker", 2, 2)}, {sg("sg", 2, 2, {"worker"})}, 1, {"test-pcs-0"}, {}},
+    {"Multiple PCSGs in one PCS replica", 1, {clq("worker-a", 2, 2), clq("worker-b", 2, 2)},
+     {sg("sg-a", 3, 1, {"worker-a"}), sg("sg-b", 2, 1, {"worker-b"})}, 4, {"test-pcs-0"},
+     {"test-pcs-0-sg-a-0", "test-pcs-0-sg-a-1", "test-pcs-0-sg-b-0"}},
+    {"Multiple cliques in one PCSG", 1, {clq("worker", 2, 2), clq("helper", 1, 1)}, {sg("sg", 3, 1, {"worker", "helper"})}, 3, {"test-pcs-0"},
+     {"test-pcs-0-sg-0", "test-pcs-0-sg-1"}},
+  };
+  for (const auto& c : cases) {
+    PodCliqueSet pcs; pcs.Name = "test-pcs"; pcs.Replicas = c.pcsReplicas; pcs.Cliques = c.pclqs; pcs.PodCliqueScalingGroupConfigs = c.pcsgs;
+    std::vector<PodGangInfo> out;
+    CHECK(!ComputeExpectedPodGangs(pcs, {}, false, &out));
+    CHECK(out.size() == c.n);
+    CHECK(names(out, false) == c.base);
+    CHECK(names(out, true) == c.scaled);
+    if (g_fail) std::fprintf(stderr, "  in case: %s\n", c.name);
+  }
+}
+
+static void test_topology_constraints() {  // syncflow_test.go:965-1420
+  const std::vector<TopologyLevel> levels = {{"zone", "topology.kubernetes.io/zone"}, {"rack", "topology.kubernetes.io/rack"}, {"host", "kubernetes.io/hostname"}};
+  const std::string Z = levels[0].Key, R = levels[1].Key, H = levels[2].Key;
+  auto run = [&](bool tas, const char* pcsPack, std::vector<PodCliqueTemplateSpec> pclqs, std::vector<PodCliqueScalingGroupConfig> pcsgs) {
+    PodCliqueSet pcs; pcs.Name = "test-pcs"; pcs.Cliques = std::move(pclqs); pcs.PodCliqueScalingGroupConfigs = std::move(pcsgs);
+    if (pcsPack) pcs.Topology = PackDomain{pcsPack};
+    std::vector<PodGangInfo> out;
+    CHECK(!ComputeExpectedPodGangs(pcs, levels, tas, &out));
+    return out;
+  };
+  auto find = [](const std::vector<PodGangInfo>& v, const std::string& fqn) -> const PodGangInfo* { for (auto& p : v) if (p.fqn == fqn) return &p; return nullptr; };
+  auto pclqKey = [](const PodGangInfo& pg, const std::string& fqn) { for (auto& p : pg.pclqs) if (p.fqn == fqn) return key(p.topologyConstraint); return std::string("<missing>"); };
+  auto pcsgKey = [](const PodGangInfo& pg, const std::string& n) { for (auto& g : pg.pcsgTopologyConstraints) if (g.Name == n) return key(g.Topology); return std::string("<missing>"); };
+  {  // no constraints anywhere
+    auto o = run(true, nullptr, {clq("worker", 3, 2)}, {});
+    CHECK(o.size() == 1 && key(o[0].topologyConstraint).empty() && o[0].pcsgTopologyConstraints.empty());
+  }
+  {  // PCS only
+    auto o = run(true, "zone", {clq("worker", 3, 2)}, {});
+    CHECK(o.size() == 1 && key(find(o, "test-pcs-0")->topologyConstraint) == Z);
+  }
+  {  // one of the PCLQs
+    auto o = run(true, nullptr, {clq("router", 3, 2), clq("worker", 2, 1, "host")}, {});
+    CHECK(o.size() == 1 && key(o[0].topologyConstraint).empty());
+    CHECK(pclqKey(o[0], "test-pcs-0-worker") == H && pclqKey(o[0], "test-pcs-0-router").empty());
+  }
+  {  // all levels, standalone
+    auto o = run(true, "zone", {clq("router", 3, 2, "zone"), clq("worker", 2, 1, "host")}, {});
+    CHECK(key(o[0].topologyConstraint) == Z && pclqKey(o[0], "test-pcs-0-worker") == H && pclqKey(o[0], "test-pcs-0-router") == Z);
+  }
+  const std::vector<PodCliqueTemplateSpec> decode = {clq("decode-leader", 1, 1, "host"), clq("decode-worker", 5, 1, "host")};
+  {  // PCS + PCSG
+    auto o = run(true, "zone", decode, {sg("scaling-group", 2, 1, {"decode-leader", "decode-worker"}, "rack")});
+    CHECK(o.size() == 2);
+    const PodGangInfo* b = find(o, "test-pcs-0"); const PodGangInfo* s = find(o, "test-pcs-0-scaling-group-0");
+    CHECK(b && s);
+    if (b && s) {
+      CHECK(key(b->topologyConstraint) == Z);
+      CHECK(pclqKey(*b, "test-pcs-0-scaling-group-0-decode-leader") == H && pclqKey(*b, "test-pcs-0-scaling-group-0-decode-worker") == H);
+      CHECK(pcsgKey(*b, "test-pcs-0-scaling-group-0") == R);
+      CHECK(key(s->topologyConstraint) == R);  // scaled PodGang carries the PCSG constraint
+      CHECK(pclqKey(*s, "test-pcs-0-scaling-group-1-decode-leader") == H && pclqKey(*s, "test-pcs-0-scaling-group-1-decode-worker") == H);
+      CHECK(s->pcsgTopologyConstraints.empty());
+    }
+  }
+  {  // standalone + PCSG, all levels
+    std::vector<PodCliqueTemplateSpec> all = {clq("router", 1, 1, "zone")}; all.insert(all.end(), decode.begin(), decode.end());
+    auto o = run(true, "zone", all, {sg("scaling-group", 2, 1, {"decode-leader", "decode-worker"}, "rack")});
+    const PodGangInfo* b = find(o, "test-pcs-0");
+    CHECK(o.size() == 2 && b && pclqKey(*b, "test-pcs-0-router") == Z && pcsgKey(*b, "test-pcs-0-scaling-group-0") == R);
+  }
+  {  // TAS disabled: nothing set anywhere
+    std::vector<PodCliqueTemplateSpec> all = {clq("router", 1, 1, "zone")}; all.insert(all.end(), decode.begin(), decode.end());
+    auto o = run(false, "zone", all, {sg("scaling-group", 2, 1, {"decode-leader", "decode-worker"}, "rack")});
+    CHECK(o.size() == 2);
+    for (const auto& pg : o) {
+      CHECK(key(pg.topologyConstraint).empty() && pg.pcsgTopologyConstraints.empty());
+      for (const auto& p : pg.pclqs) CHECK(key(p.topologyConstraint).empty());
+    }
+  }
+  {  // PCSG without constraint: scaled PodGang falls back to the PCS constraint
+    auto o = run(true, "zone", decode, {sg("scaling-group", 2, 1, {"decode-leader", "decode-worker"})});
+    const PodGangInfo* b = find(o, "test-pcs-0"); const PodGangInfo* s = find(o, "test-pcs-0-scaling-group-0");
+    CHECK(b && s && key(b->topologyConstraint) == Z && key(s->topologyConstraint) == Z && b->pcsgTopologyConstraints.empty());
+  }
+}
+
+static std::vector<Node> e2e_nodes(int n, int cordoned = 0) {  // hack/e2e.yaml: 150 MiB nodes; zone 28 / block 14 / rack 7 / host
+  std::vector<Node> v(n);
+  for (int i = 0; i < n; ++i) {
+    Node& nd = v[i];
+    nd.Name = "kwok-node-" + std::to_string(i);
+    nd.Labels = {{"topology.kubernetes.io/zone", "zone-" + std::to_string(i / 28)}, {"topology.kubernetes.io/block", "block-" + std::to_string(i / 14)},
+                 {"topology.kubernetes.io/rack", "rack-" + std::to_string(i / 7)}, {"kubernetes.io/hostname", nd.Name},
+                 {"node_role.e2e.grove.nvidia.com", "agent"}};
+    nd.alloc_cpu_milli = 4000; nd.alloc_mem_mib = 150; nd.alloc_pods = 110;
+    nd.TaintKeys = {"node_role.e2e.grove.nvidia.com"};
+    nd.Unschedulable = i >= n - cordoned;
+  }
+  return v;
+}
+static const std::vector<TopologyLevel> kLevels = {{"zone", "topology.kubernetes.io/zone"}, {"block", "topology.kubernetes.io/block"},
+                                                   {"rack", "topology.kubernetes.io/rack"}, {"host", "kubernetes.io/hostname"}};
+
+static PodCliqueSet workload1() {  // e2e/yaml/workload1.yaml
+  PodCliqueSet pcs; pcs.Name = "workload1";
+  PodGang::Requests rq; rq.mem_mib = 80; rq.nodeSelector = {{"node_role.e2e.grove.nvidia.com", "agent"}}; rq.tolerationKeys = {"node_role.e2e.grove.nvidia.com"};
+  for (auto [n, r] : std::vector<std::pair<const char*, int>>{{"pc-a", 2}, {"pc-b", 1}, {"pc-c", 3}}) { auto c = clq(n, r, r); c.Requests = rq; pcs.Cliques.push_back(c); }
+  pcs.PodCliqueScalingGroupConfigs = {sg("sg-x", 2, 2, {"pc-b", "pc-c"})};
+  return pcs;
+}
+
+static void test_encode() {
+  GpuBackend be;
+  CHECK(be.Name() == "gpu-scheduler");
+  std::string sched; be.PreparePod(&sched); CHECK(sched == "gpu-scheduler");
+  CHECK(!be.SyncTopology(kLevels));
+  CHECK(be.CheckTopologyDrift(kLevels).first);
+  auto drift = kLevels; drift[2].Key = "example.com/nvlink-domain";
+  CHECK(!be.CheckTopologyDrift(drift).first);
+  PodCliqueSet pcs = workload1(); pcs.Topology = PackDomain{"block"}; pcs.PodCliqueScalingGroupConfigs[0].Topology = PackDomain{"rack"};
+  CHECK(!be.ValidatePodCliqueSet(pcs));
+  std::vector<PodGangInfo> infos; CHECK(!ComputeExpectedPodGangs(pcs, kLevels, true, &infos));
+  CHECK(infos.size() == 1);
+  for (const auto& i : infos) CHECK(!be.SyncPodGang(BuildPodGang(pcs, i)));
+  CHECK(be.Pending() == 1);
+  Tables t; CHECK(!be.Encode(e2e_nodes(10, 1), &t));
+  CHECK(t.nodes.size() == 10 && t.gangs.size() == 1 && t.cliques.size() == 5 && t.scopes.size() == 3);
+  CHECK(t.gangs[0].level == 1 && t.gangs[0].n_cliques == 5 && t.gangs[0].n_scopes == 3 && t.gangs[0].base_gang == GROVE_NONE_U32);
+  CHECK(t.scopes[0].level == GROVE_LEVEL_NONE && t.scopes[0].n_cliques == 1);            // pc-a, loose
+  CHECK(t.scopes[1].level == 2 && t.scopes[1].n_cliques == 2 && t.scopes[2].level == 2);  // sg-x replicas 0 and 1 -> rack
+  CHECK(t.cliques[0].min_replicas == 2 && t.cliques[0].replicas == 2 && t.cliques[0].req_mem_mib == 80);
+  CHECK(t.cliques[2].min_replicas == 3 && t.cliques[1].scope == 1 && t.cliques[4].scope == 2);
+  CHECK(t.cliques[0].class_mask == 0x2);  // only the "agent" class, whose taint the pods tolerate
+  CHECK((t.nodes[0].flags & GROVE_NODE_SCHEDULABLE) && !(t.nodes[9].flags & GROVE_NODE_SCHEDULABLE));
+  CHECK(t.nodes[0].dom[0] == t.nodes[9].dom[0] && t.nodes[0].dom[2] != t.nodes[7].dom[2] && t.nodes[0].free_mem_mib == 150);
+  // a Required key that is not a level of the synced topology is an error, like a stale ClusterTopology
+  PodGang bad = BuildPodGang(pcs, infos[0]); bad.Name = "bad"; bad.Spec.Topology = TopologyConstraint{TopologyPackConstraint{std::string("example.com/nope"), std::nullopt}};
+  CHECK(!be.SyncPodGang(bad));
+  CHECK(be.Encode(e2e_nodes(10), &t).has_value());
+  CHECK(!be.OnPodGangDelete(bad));
+  // engine limits surface in ValidatePodCliqueSet
+  PodCliqueSet big; big.Name = "big"; big.Cliques = {clq("w", 200, 200)};
+  CHECK(be.ValidatePodCliqueSet(big).has_value());
+}
+
+static void test_gpu_cycles() {
+  GpuBackend be;
+  CHECK(!be.SyncTopology(kLevels));
+  CHECK(!be.Init());
+  PodCliqueSet pcs = workload1();
+  std::vector<PodGangInfo> infos; CHECK(!ComputeExpectedPodGangs(pcs, kLevels, true, &infos));
+  std::vector<Binding> b; std::map<std::string, PodGangStatus> st;
+  // GS1 (gang_scheduling_test.go:34-74): 9 schedulable nodes -> nothing bound; 10 -> 10 pods on 10 distinct nodes
+  for (const auto& i : infos) CHECK(!be.SyncPodGang(BuildPodGang(pcs, i)));
+  CHECK(!be.RunCycle(e2e_nodes(10, 1), &b, &st));
+  CHECK(b.empty() && st.size() == 1 && !st.begin()->second.Scheduled && st.begin()->second.ScheduledReason == "Unschedulable");
+  CHECK(be.Pending() == 1);  // still pending: retried next cycle
+  CHECK(!be.RunCycle(e2e_nodes(10), &b, &st));
+  CHECK(b.size() == 10 && st.begin()->second.Scheduled && st.begin()->second.Phase == PodGangPhase::Starting);
+  std::set<std::string> nodes, pods; for (auto& x : b) { nodes.insert(x.NodeName); pods.insert(x.PodName); }
+  CHECK(nodes.size() == 10 && pods.size() == 10 && be.Pending() == 0);
+  CHECK(st.begin()->second.PlacementScore && *st.begin()->second.PlacementScore > 0.0 && *st.begin()->second.PlacementScore <= 1.0);
+  // TAS8 (topology_test.go:501-578): block -> rack -> host on 8 nodes
+  PodCliqueSet tas; tas.Name = "tas-hierarchy"; tas.Topology = PackDomain{"block"};
+  PodGang::Requests rq; rq.mem_mib = 40; rq.tolerationKeys = {"node_role.e2e.grove.nvidia.com"};
+  for (const char* n : {"prefill", "decode"}) { auto c = clq(n, 2, 2, "host"); c.Requests = rq; tas.Cliques.push_back(c); }
+  tas.PodCliqueScalingGroupConfigs = {sg("inference-group", 2, 2, {"prefill", "decode"}, "rack")};
+  CHECK(!ComputeExpectedPodGangs(tas, kLevels, true, &infos));
+  for (const auto& i : infos) CHECK(!be.SyncPodGang(BuildPodGang(tas, i)));
+  auto n8 = e2e_nodes(8);
+  CHECK(!be.RunCycle(n8, &b, &st));
+  CHECK(b.size() == 8 && st.begin()->second.Scheduled);
+  std::map<std::string, std::set<std::string>> hostsOfClique, racksOfReplica;
+  for (auto& x : b) {
+    const std::string clique = x.PodName.substr(0, x.PodName.rfind('-'));  // <pclq fqn>-<ordinal>
+    hostsOfClique[clique].insert(x.NodeName);
+    const int idx = std::atoi(x.NodeName.c_str() + std::strlen("kwok-node-"));
+    racksOfReplica[clique.substr(0, clique.rfind('-'))].insert(n8[idx].Labels.at("topology.kubernetes.io/rack"));
+  }
+  CHECK(hostsOfClique.size() == 4);
+  for (auto& kv : hostsOfClique) CHECK(kv.second.size() == 1);   // every PodClique on one host
+  CHECK(racksOfReplica.size() == 2);
+  for (auto& kv : racksOfReplica) CHECK(kv.second.size() == 1);  // every PCSG replica in one rack
+}
+
+int main(int argc, char** argv) {
+  const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+  test_compute_expected_podgangs();
+  test_topology_constraints();
+  test_encode();
+  if (gpu) test_gpu_cycles();
+  else {  // without a CUDA device Init must fail loudly, never fall back
+    GpuBackend be; be.SyncTopology(kLevels);
+    auto e = be.Init();
+    if (!e) std::fprintf(stderr, "note: a CUDA device is present; Init succeeded\n");
+    else CHECK(e->message.find("no CPU fallback") != std::string::npos);
+  }
+  if (g_fail) { std::fprintf(stderr, "%d check(s) failed\n", g_fail); return 1; }
+  std::printf("host tests ok (%s)\n", gpu ? "cpu+gpu" : "cpu");
+  return 0;
+}
