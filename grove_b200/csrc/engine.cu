@@ -106,6 +106,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_xbuf, d_active_all, d_flags, d_capsum, d_capmax;
   DevBuf<uint8_t> d_taken, d_cur, d_prop;
   uint32_t K = GROVE_MAX_ALTERNATIVES;
+  uint32_t n_constrained = 0, n_unconstrained = 0;  // gangs with / without a gang-level Required level
   int resolve_blocks_per_sm = 0;
   uint32_t n_sm = 148;
   DevBuf<uint8_t> d_cap8;
@@ -114,7 +115,7 @@ struct grove_engine {
   bool dbg_on = false;
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
-  uint32_t tune_width0 = 32;
+  uint32_t tune_width0 = 16;
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
   PinBuf<uint32_t> h_counters;
@@ -291,7 +292,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
-  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = std::min(32, std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(128, std::max(4, std::atoi(v)))) & ~3u;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
@@ -432,6 +433,8 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   e->cliques.assign(cliques, cliques + n_cliques);
   e->scopes.assign(scopes, scopes + n_scopes);
   e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
+  e->n_constrained = e->n_unconstrained = 0;
+  for (uint32_t g = 0; g < n_gangs; ++g) (gangs[g].level == GROVE_LEVEL_NONE ? e->n_unconstrained : e->n_constrained)++;
   CU_TRY(e, e->d_gangs.ensure(n_gangs)); CU_TRY(e, e->d_cliques.ensure(n_cliques)); CU_TRY(e, e->d_scopes.ensure(n_scopes));
   if (n_gangs) CU_TRY(e, cudaMemcpyAsync(e->d_gangs.p, e->gangs.data(), sizeof(grove_gang_t) * n_gangs, cudaMemcpyHostToDevice, e->stream));
   if (n_cliques) CU_TRY(e, cudaMemcpyAsync(e->d_cliques.p, e->cliques.data(), sizeof(grove_clique_t) * n_cliques, cudaMemcpyHostToDevice, e->stream));
@@ -618,11 +621,16 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   k_score<<<dim3(1, std::min<uint32_t>(nr, 65535u)), 256, 0, e->stream>>>(tp, tb, rb, nr);  // one CTA per row
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
-  if (na >= 148u * 4u) k_admit<kAdmitThreads><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-  else k_admit<kAdmitThreadsWide><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+  const bool caps = e->prefilter && e->tune_prefilter >= 2;
+  if (e->n_constrained) {
+    if (na >= 148u * 4u) { if (caps) k_admit<kAdmitThreads, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); else k_admit<kAdmitThreads, 1><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); }
+    else { if (caps) k_admit<kAdmitThreadsWide, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); else k_admit<kAdmitThreadsWide, 1><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); }
+    e->launches += 1;
+  }
+  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
   CU_TRY(e, cudaGetLastError());
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
-  e->launches += 3;
+  e->launches += 2;
   e->pairs += uint64_t(nr) * e->N;
   return GROVE_OK;
 }

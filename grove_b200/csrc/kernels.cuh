@@ -431,6 +431,42 @@ __device__ __forceinline__ int make_pieces(const GangRegs& g, uint32_t lo, uint3
   return k;
 }
 
+// The same ordered pieces as make_pieces, produced one at a time from a few registers (no per-thread
+// arrays: the scalar evaluator runs one attempt per LANE and every local-memory word costs a cache line
+// per warp).
+struct PieceIt {
+  uint32_t lo, hi, prev_lo, prev_hi, first_lo, first_hi;
+  int l, stage;  // stage: 0 first piece pending, 1 rings (upper), 2 rings (lower), 3 tail upper, 4 tail lower, 5 done
+  bool outside;
+  __device__ __forceinline__ void init(const GangRegs& g, uint32_t lo_, uint32_t hi_, uint32_t from) {
+    lo = lo_; hi = hi_;
+    outside = g.a < lo || g.a >= hi;
+    stage = 0; prev_lo = g.a; prev_hi = g.a; first_lo = first_hi = 0;
+    l = int(min(from, g.L)) - 1;
+    if (!outside && from < g.L) {
+      first_lo = max(g.anc_lo[from], lo); first_hi = min(g.anc_hi[from], hi);
+      prev_lo = first_lo; prev_hi = first_hi;
+    }
+  }
+  __device__ __forceinline__ bool next(const GangRegs& g, uint32_t& a, uint32_t& b) {
+    if (outside) { if (stage == 0 && hi > lo) { stage = 5; a = lo; b = hi; return true; } return false; }
+    if (stage == 0) { stage = 1; if (first_hi > first_lo) { a = first_lo; b = first_hi; return true; } }
+    while (stage == 1 || stage == 2) {
+      if (l < 0) { stage = 3; break; }
+      const uint32_t cl = max(g.anc_lo[l], lo), ch = min(g.anc_hi[l], hi);
+      if (stage == 1) { stage = 2; if (ch > prev_hi) { a = prev_hi; b = ch; return true; } }
+      // stage 2: lower part of ring l, then move one level out
+      const uint32_t pl = prev_lo;
+      prev_lo = min(cl, prev_lo); prev_hi = max(ch, prev_hi);
+      --l; stage = 1;
+      if (pl > cl) { a = cl; b = pl; return true; }
+    }
+    if (stage == 3) { stage = 4; if (hi > prev_hi) { a = prev_hi; b = hi; return true; } }
+    if (stage == 4) { stage = 5; if (prev_lo > lo) { a = lo; b = prev_lo; return true; } }
+    return false;
+  }
+};
+
 __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_t gpu, uint32_t pods, const uint4& q) {
   uint32_t c = pods;
   if (q.x) c = min(c, cpu / q.x);
@@ -464,11 +500,9 @@ struct CoopEv {
     if (want == 0 || hi <= lo) return 0;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
-    for (int p = 0; p < npc && placed < want; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
       for (uint32_t wb = w0; wb <= w1 && placed < want; wb += 32) {
         uint32_t myw = 0;  // 32 fit words at a time, one per lane
@@ -516,10 +550,8 @@ struct CoopEv {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
-    for (int p = 0; p < npc; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    PieceIt pit; pit.init(g, lo, hi, g.L);
+    for (uint32_t a, b; pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
       for (uint32_t wb = w0; wb <= w1; wb += 32) {
         uint32_t myw = 0;
@@ -553,6 +585,7 @@ struct CoopEv {
 };
 
 // ---- scalar evaluator: ONE lane packs one candidate range (lanes of a warp hold different candidates)
+template <bool kCaps>
 struct ScalarEv {
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
@@ -603,11 +636,9 @@ struct ScalarEv {
   __device__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
-    for (int p = 0; p < npc && placed < want; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
       for (uint32_t base = a & ~3u; base < b && placed < want; base += 32) {
         uint32_t w[8];
         uint32_t mask = load_caps(row, base, a, b, w);
@@ -632,10 +663,8 @@ struct ScalarEv {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
-    for (int p = 0; p < npc; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    PieceIt pit; pit.init(g, lo, hi, g.L);
+    for (uint32_t a, b; pit.next(g, a, b);) {
       for (uint32_t base = a & ~3u; base < b; base += 32) {
         uint32_t w[8];
         uint32_t mask = load_caps(row, base, a, b, w);
@@ -659,14 +688,12 @@ struct ScalarEv {
 
   __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
-    if (rb.cap8 && rb.caps_in_attempts) return take_caps(cr, lo, hi, want);
+    if constexpr (kCaps) return take_caps(cr, lo, hi, want);
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
+    PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
-    for (int p = 0; p < npc && placed < want; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
       for (uint32_t w = w0; w <= w1 && placed < want; ++w) {
         uint32_t bits = __ldg(Frow + w);
@@ -696,14 +723,12 @@ struct ScalarEv {
   }
 
   __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
-    if (rb.cap8 && rb.caps_in_attempts) return find_unit_caps(cr, lo, hi);
+    if constexpr (kCaps) return find_unit_caps(cr, lo, hi);
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
-    uint32_t plo[kMaxPieces], phi[kMaxPieces];
-    const int npc = make_pieces(g, lo, hi, g.L, plo, phi);
-    for (int p = 0; p < npc; ++p) {
-      const uint32_t a = plo[p], b = phi[p];
+    PieceIt pit; pit.init(g, lo, hi, g.L);
+    for (uint32_t a, b; pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
       for (uint32_t w = w0; w <= w1; ++w) {
         uint32_t bits = __ldg(Frow + w);
@@ -791,10 +816,9 @@ __device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_
       if (tp.unit[ql] && m >= 1) {
         ok = ev.find_unit(cr, lo, hi);
       } else {
-        uint32_t plo[kMaxPieces], phi[kMaxPieces];
-        const int npc = make_pieces(ev.g, lo, hi, ql, plo, phi);
-        for (int p = 0; p < npc && !ok; ++p) {
-          const uint32_t d0 = __ldg(tp.next_dom[ql] + plo[p]), d1 = __ldg(tp.next_dom[ql] + phi[p]);
+        PieceIt pit; pit.init(ev.g, lo, hi, ql);
+        for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
+          const uint32_t d0 = __ldg(tp.next_dom[ql] + pa), d1 = __ldg(tp.next_dom[ql] + pb);
           for (uint32_t d = d0; d < d1 && !ok; ++d)
             ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
         }
@@ -815,10 +839,9 @@ __device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, in
     const grove_scope_t s = ev.sh.scopes[si];
     bool ok = false;
     if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      uint32_t plo[kMaxPieces], phi[kMaxPieces];
-      const int npc = make_pieces(ev.g, lo, hi, s.level, plo, phi);
-      for (int p = 0; p < npc && !ok; ++p) {
-        const uint32_t d0 = __ldg(tp.next_dom[s.level] + plo[p]), d1 = __ldg(tp.next_dom[s.level] + phi[p]);
+      PieceIt pit; pit.init(ev.g, lo, hi, s.level);
+      for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
+        const uint32_t d0 = __ldg(tp.next_dom[s.level] + pa), d1 = __ldg(tp.next_dom[s.level] + pb);
         for (uint32_t d = d0; d < d1 && !ok; ++d) {
           if (ev.moot()) { ev.np = 0; return false; }
           const uint32_t el = __ldg(tp.dom_lo[s.level] + d), eh = __ldg(tp.dom_hi[s.level] + d);
@@ -860,7 +883,10 @@ __global__ void k_dbg_init(uint32_t* dbg, uint32_t G) {
 constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
 constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
 
-template <int kThreads>
+// kMode 0: gangs with a gang-level constraint, packing from capacity bytes; 1: same, packing from fit
+// words + node records (no capacity tables this cycle); 2: gangs without a gang-level constraint
+// (cooperative).  Each instantiation skips the gangs of the other kind.
+template <int kThreads, int kMode>
 __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -868,6 +894,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   if (ai >= rb.counters[0]) return;
   const uint32_t gi = rb.active[ai];
   const grove_gang_t gg = tb.gangs[gi];
+  if ((gg.level == GROVE_LEVEL_NONE) != (kMode == 2)) return;  // handled by the other instantiation
   const GangInfo info = tb.ginfo[gi];
   GangRegs g;
   g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
@@ -884,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   __syncthreads();
 
   const uint32_t K = rb.K, P = rb.P;
-  if (gg.level == GROVE_LEVEL_NONE) {
+  if constexpr (kMode == 2) {
     // single candidate: the whole cluster, packed cooperatively by warp 0 (one alternative at most)
     if (warp != 0) return;
     CoopEv ev(tp, rb, sh, g, lane);
@@ -912,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
       rb.alt_top[size_t(gi) * K] = 0u;
     }
     return;
-  }
+  } else {
 
   // candidate domains of the gang's level in score order: up to kMaxPieces ranges of domain indices
   const uint32_t gl = gg.level;
@@ -924,43 +951,62 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
     D += rcnt[p];
   }
-  ScalarEv ev(tp, rb, sh, g);
-  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32], s_wsucc[kAdmitThreadsWide / 32];
+  ScalarEv<kMode == 0> ev(tp, rb, sh, g);
+  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
+  __shared__ uint32_t s_okmask[kAdmitThreadsWide / 32];
+  __shared__ uint32_t s_ck[kAdmitThreadsWide], s_cl[kAdmitThreadsWide], s_ch[kAdmitThreadsWide];  // plausible candidates of the chunk, in order
   const uint32_t nwarp = blockDim.x >> 5;
   uint32_t nsucc = 0;  // feasible candidates found so far (block-uniform)
   // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
-  // then run the packing only on the plausible ones -- the first 32 of them first, since in an
-  // uncongested cluster the very first candidates already fit.  The first K feasible candidates in
-  // order become the gang's alternatives.
+  // compact the plausible ones, then run the packing on them one lane per candidate.  The first window
+  // is narrow (2 K candidates, in an uncongested cluster the first ones already fit) and spread over
+  // all warps so that the divergent attempts serialise as little as possible.  The first K feasible
+  // candidates in order become the gang's alternatives.
   for (uint32_t base = 0; base < D && nsucc < K; base += blockDim.x) {
-    const uint32_t k = base + tid;
-    uint32_t d = 0, dl = 0, dh = 0;
-    bool plaus = false;
-    if (k < D) {
-      uint32_t rem = k;
-      for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
-      dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-      plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
-    }
-    const uint32_t pb = __ballot_sync(kFull, plaus);
-    if (lane == 0) s_wcnt[warp] = __popc(pb);
-    __syncthreads();
-    uint32_t rank = __popc(pb & ((1u << lane) - 1u)), total = 0;
-    for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wcnt[w]; if (w < warp) rank += c; total += c; }
-    if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
-    for (uint32_t abase = 0; abase < total && nsucc < K;) {
-      const uint32_t width = (base == 0 && abase == 0 && blockDim.x == kAdmitThreads) ? rb.width0 : blockDim.x;
-      bool ok = false;
-      if (plaus && rank >= abase && rank < abase + width) {
-        ev.k = k;
-        ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
-        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
+    {
+      const uint32_t k = base + tid;
+      uint32_t d = 0, dl = 0, dh = 0;
+      bool plaus = false;
+      if (k < D) {
+        uint32_t rem = k;
+        for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
+        dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+        plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
       }
-      const uint32_t sb = __ballot_sync(kFull, ok);
-      if (lane == 0) s_wsucc[warp] = __popc(sb);
+      const uint32_t pb = __ballot_sync(kFull, plaus);
+      if (lane == 0) s_wcnt[warp] = __popc(pb);
       __syncthreads();
-      uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u)), stot = 0;
-      for (uint32_t w = 0; w < nwarp; ++w) { const uint32_t c = s_wsucc[w]; if (w < warp) srank += c; stot += c; }
+      uint32_t rank = __popc(pb & ((1u << lane) - 1u));
+      for (uint32_t w = 0; w < warp; ++w) rank += s_wcnt[w];
+      if (plaus) { s_ck[rank] = k; s_cl[rank] = dl; s_ch[rank] = dh; }
+    }
+    uint32_t total = 0;
+    for (uint32_t w = 0; w < nwarp; ++w) total += s_wcnt[w];
+    if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
+    __syncthreads();
+    for (uint32_t abase = 0; abase < total && nsucc < K;) {
+      const bool narrow = base == 0 && abase == 0 && blockDim.x == kAdmitThreads;
+      const uint32_t width = narrow ? rb.width0 : blockDim.x;
+      // slot of this thread inside the window: narrow windows put width/nwarp slots on each warp
+      const uint32_t per = width / nwarp;
+      const uint32_t slot = narrow ? (lane < per ? warp * per + lane : GROVE_NONE_U32) : tid;
+      if (tid < (kAdmitThreadsWide / 32)) s_okmask[tid] = 0;
+      __syncthreads();
+      bool ok = false; uint32_t k = 0, dl = 0;
+      if (slot != GROVE_NONE_U32 && abase + slot < total) {
+        k = s_ck[abase + slot]; dl = s_cl[abase + slot];
+        ev.k = k;
+        ok = place_in(ev, gg.n_scopes, dl, s_ch[abase + slot], int(gl));
+        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
+        if (ok) atomicOr(&s_okmask[slot >> 5], 1u << (slot & 31));
+      }
+      __syncthreads();
+      uint32_t stot = 0, srank = nsucc;
+      for (uint32_t w = 0; w < (kAdmitThreadsWide / 32); ++w) {
+        const uint32_t m = s_okmask[w];
+        stot += __popc(m);
+        if (ok) { if (w < (slot >> 5)) srank += __popc(m); else if (w == (slot >> 5)) srank += __popc(m & ((1u << (slot & 31)) - 1u)); }
+      }
       if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
         uint32_t n_min, min_score;
         finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
@@ -973,11 +1019,12 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
       }
       nsucc += stot;
       abase += width;
-      __syncthreads();  // s_wsucc is rewritten by the next window
+      __syncthreads();  // s_okmask is rewritten by the next window
     }
-    __syncthreads();  // s_wcnt is rewritten by the next chunk
+    __syncthreads();  // the candidate list is rewritten by the next chunk
   }
   if (tid == 0) rb.nalt[gi] = min(nsucc, K);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
