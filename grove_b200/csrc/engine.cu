@@ -116,6 +116,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
   uint32_t tune_width0 = 16;
+  uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
   PinBuf<uint32_t> h_counters;
@@ -292,6 +293,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
+  if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(128, std::max(4, std::atoi(v)))) & ~3u;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
@@ -645,7 +647,7 @@ static int32_t round_resolve(grove_engine* e, bool timed) {
   CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // claims are sub-round tagged; reset once per round
   uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
   const uint32_t want = na_all <= 64u ? 1u : (na_all * 32 + 255) / 256;  // few gangs: one CTA, grid barriers are then nearly free
-  const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, uint32_t(e->resolve_blocks_per_sm) * e->n_sm));
+  const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, std::min<uint32_t>(uint32_t(e->resolve_blocks_per_sm), e->tune_resolve_bps) * e->n_sm));
   void* args[] = {&tp, &tb, &rb, &nres, &rn};
   CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(256), args, 0, e->stream));
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
