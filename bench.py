@@ -173,7 +173,7 @@ def run_gpu(args):
         def step_e2e():
             eng.load_nodes(nodes); eng.submit_gangs(g, c, s)
             st = run_sharded_cycle(eng, dist)
-            return st, eng.placements(), eng.gang_status()
+            return st, eng.placements(copy=False), eng.gang_status(copy=False)
     else:
         def step_dev():
             eng.load_nodes_device(d_nodes.data_ptr(), len(nodes))
@@ -181,7 +181,7 @@ def run_gpu(args):
         def step_e2e():
             eng.load_nodes(nodes); eng.submit_gangs(g, c, s)
             st = eng.run_cycle()
-            return st, eng.placements(), eng.gang_status()
+            return st, eng.placements(copy=False), eng.gang_status(copy=False)
 
     def sync():
         torch.cuda.synchronize()

@@ -11,7 +11,7 @@ SOURCES = ["engine.cu"]
 DEPS = ["engine.cu", "kernels.cuh", os.path.join("..", "..", "include", "grove_place.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-fopenmp", "-shared", "-cudart", "shared", "-lgomp",
 ]
 
 

@@ -2,6 +2,8 @@
 // include/grove_place.h.  Everything that computes a placement runs in the kernels of kernels.cuh;
 // the host sorts the topology once per label change, validates and uploads tables, and drives the
 // optimistic rounds.  There is no CPU fallback: without a CUDA device the engine cannot be created.
+#include <omp.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -452,77 +454,111 @@ static int32_t build_ginfo(grove_engine* e) {
   e->ginfo.assign(G, GangInfo{});
   e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0, 0, 0});
   e->sigs.clear();
-  // open-addressing table over (req_cpu, req_mem, req_gpu, class_mask, need_depth): templates repeat, so it stays tiny
-  std::vector<std::array<uint32_t, 6>> tab(1024, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
-  auto hash5 = [](const std::array<uint32_t, 5>& k) { uint32_t h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA6Bu ^ (k[2] << 20) ^ (k[3] << 4) ^ k[4]; return h ^ (h >> 15); };
-  std::array<uint32_t, 5> last_key{GROVE_NONE_U32, 0, 0, 0, 0};
-  uint32_t last_sig = 0;
   // order rank = position by (priority desc, index asc): a stable bucket pass over the distinct priorities
   std::vector<uint32_t> ord(G);
   {
-    std::vector<int32_t> pr;
-    for (uint32_t g = 0; g < G; ++g) if (pr.empty() || e->gangs[g].priority != pr.back()) pr.push_back(e->gangs[g].priority);
-    std::sort(pr.begin(), pr.end(), std::greater<int32_t>());
-    pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
-    if (pr.size() <= 1) {
-      std::iota(ord.begin(), ord.end(), 0u);
-    } else if (pr.size() <= 64) {
-      std::vector<uint32_t> cnt(pr.size() + 1, 0);
-      auto bucket = [&pr](int32_t p) { return uint32_t(std::lower_bound(pr.begin(), pr.end(), p, std::greater<int32_t>()) - pr.begin()); };
-      for (uint32_t g = 0; g < G; ++g) cnt[bucket(e->gangs[g].priority) + 1]++;
-      for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
-      for (uint32_t g = 0; g < G; ++g) ord[cnt[bucket(e->gangs[g].priority)]++] = g;
-    } else {
+    std::vector<int32_t> pr;          // distinct priorities (PriorityClasses are few)
+    std::vector<uint8_t> bkt(G, 0);   // bucket of each gang in first-seen order, remapped below
+    bool many = false;
+    for (uint32_t g = 0; g < G && !many; ++g) {
+      const int32_t p = e->gangs[g].priority;
+      size_t i = 0;
+      while (i < pr.size() && pr[i] != p) ++i;
+      if (i == pr.size()) { if (pr.size() == 64) { many = true; break; } pr.push_back(p); }
+      bkt[g] = uint8_t(i);
+    }
+    if (many) {
       std::iota(ord.begin(), ord.end(), 0u);
       std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
+    } else if (pr.size() <= 1) {
+      std::iota(ord.begin(), ord.end(), 0u);
+    } else {
+      std::vector<uint8_t> rank_of(pr.size());  // first-seen bucket -> position in descending priority order
+      std::vector<uint32_t> idx(pr.size());
+      std::iota(idx.begin(), idx.end(), 0u);
+      std::sort(idx.begin(), idx.end(), [&pr](uint32_t a, uint32_t b) { return pr[a] > pr[b]; });
+      for (size_t r = 0; r < idx.size(); ++r) rank_of[idx[r]] = uint8_t(r);
+      std::vector<uint32_t> cnt(pr.size() + 1, 0);
+      for (uint32_t g = 0; g < G; ++g) cnt[rank_of[bkt[g]] + 1]++;
+      for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+      for (uint32_t g = 0; g < G; ++g) ord[cnt[rank_of[bkt[g]]]++] = g;
     }
   }
-  uint32_t pod_off = 0;
+  const auto t_m1 = std::chrono::steady_clock::now();
   for (uint32_t r = 0; r < G; ++r) e->ginfo[ord[r]].order = r;
   for (uint32_t gi = 0; gi < G; ++gi) {
     const grove_gang_t& g = e->gangs[gi];
-    GangInfo& in = e->ginfo[gi];
     if (g.anchor_node != GROVE_NONE_U32 && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
-    const uint32_t a = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
-    in.anchor = a; in.pod_off = pod_off;
-    uint32_t pods = 0;
-    for (uint32_t si = 0; si < g.n_scopes; ++si) {
-      const grove_scope_t& s = e->scopes[g.scope_off + si];
-      for (uint32_t i = 0; i < s.n_cliques; ++i) {
-        const uint32_t qi = g.clique_off + s.first_clique + i;
-        const grove_clique_t& q = e->cliques[qi];
-        uint32_t nd = 0;
-        if (g.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(g.level) + 1);
-        if (s.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(s.level) + 1);
-        if (q.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(q.level) + 1);
-        if (e->cinfo[qi].gang != GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique rows shared between gangs");
-        // PodCliques stamped from one template (PCS / PCSG replicas) share requests, selector class and
-        // binding depth: they share one fit-bitmap row
-        const std::array<uint32_t, 5> key{q.req_cpu_milli, q.req_mem_mib, q.req_gpu, q.class_mask, nd};
-        if (key == last_key) { e->cinfo[qi] = CliqueInfo{gi, nd, last_sig, 0}; pods += q.replicas; continue; }
-        if (e->sigs.size() * 2 >= tab.size()) {  // grow and re-insert
-          std::vector<std::array<uint32_t, 6>> nt(tab.size() * 4, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
-          for (const auto& r : tab) if (r[5] != GROVE_NONE_U32) {
-            size_t h = hash5({r[0], r[1], r[2], r[3], r[4]}) & (nt.size() - 1);
-            while (nt[h][5] != GROVE_NONE_U32) h = (h + 1) & (nt.size() - 1);
-            nt[h] = r;
-          }
-          tab.swap(nt);
-        }
-        size_t h = hash5(key) & (tab.size() - 1);
-        while (tab[h][5] != GROVE_NONE_U32 && !(tab[h][0] == key[0] && tab[h][1] == key[1] && tab[h][2] == key[2] && tab[h][3] == key[3] && tab[h][4] == key[4]))
-          h = (h + 1) & (tab.size() - 1);
-        if (tab[h][5] == GROVE_NONE_U32) {
-          tab[h] = {key[0], key[1], key[2], key[3], key[4], uint32_t(e->sigs.size())};
-          e->sigs.push_back(make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu, uint32_t(q.class_mask) | (nd << 16)));
-        }
-        e->cinfo[qi] = CliqueInfo{gi, nd, tab[h][5], 0};
-        last_key = key; last_sig = tab[h][5];
-        pods += q.replicas;
-      }
-    }
-    pod_off += pods;
+    e->ginfo[gi].anchor = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
   }
+  // per-clique derived data + signature interning.  PodCliques stamped from one template (PCS / PCSG
+  // replicas) share requests, selector class and binding depth: they share one fit-bitmap row.  Gang
+  // ranges are processed by a few host threads with thread-local signature tables, merged afterwards.
+  const auto t_m2 = std::chrono::steady_clock::now();
+  struct SigTab {
+    std::vector<std::array<uint32_t, 6>> tab = std::vector<std::array<uint32_t, 6>>(256, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
+    std::vector<std::array<uint32_t, 5>> keys;
+    static uint32_t hash5(const std::array<uint32_t, 5>& k) { uint32_t h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA6Bu ^ (k[2] << 20) ^ (k[3] << 4) ^ k[4]; return h ^ (h >> 15); }
+    uint32_t intern(const std::array<uint32_t, 5>& key) {
+      if (keys.size() * 2 >= tab.size()) {
+        std::vector<std::array<uint32_t, 6>> nt(tab.size() * 4, std::array<uint32_t, 6>{0, 0, 0, 0, 0, GROVE_NONE_U32});
+        for (const auto& r : tab) if (r[5] != GROVE_NONE_U32) {
+          size_t h = hash5({r[0], r[1], r[2], r[3], r[4]}) & (nt.size() - 1);
+          while (nt[h][5] != GROVE_NONE_U32) h = (h + 1) & (nt.size() - 1);
+          nt[h] = r;
+        }
+        tab.swap(nt);
+      }
+      size_t h = hash5(key) & (tab.size() - 1);
+      while (tab[h][5] != GROVE_NONE_U32 && !(tab[h][0] == key[0] && tab[h][1] == key[1] && tab[h][2] == key[2] && tab[h][3] == key[3] && tab[h][4] == key[4]))
+        h = (h + 1) & (tab.size() - 1);
+      if (tab[h][5] == GROVE_NONE_U32) { tab[h] = {key[0], key[1], key[2], key[3], key[4], uint32_t(keys.size())}; keys.push_back(key); }
+      return tab[h][5];
+    }
+  };
+  const int T = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+  std::vector<SigTab> local(T);
+  std::vector<uint32_t> gang_pods(G, 0);
+  int shared_rows = 0;
+#pragma omp parallel num_threads(T) reduction(+ : shared_rows)
+  {
+    const int t = omp_get_thread_num();
+    const uint32_t g0 = uint32_t(uint64_t(G) * t / T), g1 = uint32_t(uint64_t(G) * (t + 1) / T);
+    SigTab& st = local[t];
+    for (uint32_t gi = g0; gi < g1; ++gi) {
+      const grove_gang_t& g = e->gangs[gi];
+      uint32_t pods = 0;
+      for (uint32_t si = 0; si < g.n_scopes; ++si) {
+        const grove_scope_t& s = e->scopes[g.scope_off + si];
+        for (uint32_t i = 0; i < s.n_cliques; ++i) {
+          const uint32_t qi = g.clique_off + s.first_clique + i;
+          const grove_clique_t& q = e->cliques[qi];
+          uint32_t nd = 0;
+          if (g.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(g.level) + 1);
+          if (s.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(s.level) + 1);
+          if (q.level != GROVE_LEVEL_NONE) nd = std::max(nd, uint32_t(q.level) + 1);
+          if (e->cinfo[qi].gang != GROVE_NONE_U32) shared_rows++;  // rows of different threads never overlap unless the tables are malformed
+          e->cinfo[qi] = CliqueInfo{gi, nd, st.intern({q.req_cpu_milli, q.req_mem_mib, q.req_gpu, q.class_mask, nd}), uint32_t(t)};
+          pods += q.replicas;
+        }
+      }
+      gang_pods[gi] = pods;
+    }
+  }
+  const auto t_m3 = std::chrono::steady_clock::now();
+  if (shared_rows) return fail(e, GROVE_ERR_INVALID_ARG, "clique rows shared between gangs");
+  SigTab global;
+  std::vector<std::vector<uint32_t>> remap(T);
+  for (int t = 0; t < T; ++t) { remap[t].resize(local[t].keys.size()); for (size_t k = 0; k < local[t].keys.size(); ++k) remap[t][k] = global.intern(local[t].keys[k]); }
+  e->sigs.resize(global.keys.size());
+  for (size_t k = 0; k < global.keys.size(); ++k) { const auto& key = global.keys[k]; e->sigs[k] = make_uint4(key[0], key[1], key[2], key[3] | (key[4] << 16)); }
+  if (T > 1 || true) {
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (uint32_t qi = 0; qi < Q; ++qi)
+      if (e->cinfo[qi].gang != GROVE_NONE_U32) { e->cinfo[qi].sig = remap[e->cinfo[qi].pad][e->cinfo[qi].sig]; e->cinfo[qi].pad = 0; }
+  }
+  uint32_t pod_off = 0;
+  for (uint32_t gi = 0; gi < G; ++gi) { e->ginfo[gi].pod_off = pod_off; pod_off += gang_pods[gi]; }
   e->P = pod_off;
   const auto t_b1 = std::chrono::steady_clock::now();
   for (uint32_t qi = 0; qi < Q; ++qi)
@@ -541,7 +577,7 @@ static int32_t build_ginfo(grove_engine* e) {
   if (std::getenv("GROVE_DEBUG_HOST")) {
     const auto t_b2 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
-    std::fprintf(stderr, "build_ginfo: tables %ld us, upload %ld us\n", us(t_b0, t_b1), us(t_b1, t_b2));
+    std::fprintf(stderr, "build_ginfo: tables %ld us (order %ld, anchors %ld, cliques %ld, merge %ld), upload %ld us\n", us(t_b0, t_b1), us(t_b0, t_m1), us(t_m1, t_m2), us(t_m2, t_m3), us(t_m3, t_b1), us(t_b1, t_b2));
   }
   return GROVE_OK;
 }

@@ -76,6 +76,7 @@ class PlacementEngine:
         self.n_levels = n_levels
         self.n = self.G = self.Q = 0
         self._cap_pods = 0
+        self._pl_buf = self._st_buf = None
 
     def _check(self, rc: int):
         if rc != 0:
@@ -148,16 +149,23 @@ class PlacementEngine:
         return {k: st[k][0].item() for k in T.stats_dt.names}
 
     # ---- outputs ----
-    def placements(self) -> np.ndarray:
-        out = np.zeros(max(self._cap_pods, 1), dtype=T.placement_dt)
+    def placements(self, copy: bool = True) -> np.ndarray:
+        """copy=False returns a view into a buffer the wrapper reuses (valid until the next call)."""
+        cap = max(self._cap_pods, 1)
+        if self._pl_buf is None or len(self._pl_buf) < cap:
+            self._pl_buf = np.empty(cap, dtype=T.placement_dt)
         n = C.c_uint32(0)
-        self._check(self.lib.grove_get_placements(self.h, _p(out), C.c_uint32(len(out)), C.byref(n)))
-        return out[: n.value].copy()
+        self._check(self.lib.grove_get_placements(self.h, _p(self._pl_buf), C.c_uint32(len(self._pl_buf)), C.byref(n)))
+        out = self._pl_buf[: n.value]
+        return out.copy() if copy else out
 
-    def gang_status(self) -> np.ndarray:
-        out = np.zeros(max(self.G, 1), dtype=T.status_dt)
-        self._check(self.lib.grove_get_gang_status(self.h, _p(out), C.c_uint32(len(out))))
-        return out[: self.G].copy()
+    def gang_status(self, copy: bool = True) -> np.ndarray:
+        cap = max(self.G, 1)
+        if self._st_buf is None or len(self._st_buf) < cap:
+            self._st_buf = np.empty(cap, dtype=T.status_dt)
+        self._check(self.lib.grove_get_gang_status(self.h, _p(self._st_buf), C.c_uint32(len(self._st_buf))))
+        out = self._st_buf[: self.G]
+        return out.copy() if copy else out
 
     def nodes(self) -> np.ndarray:
         out = np.zeros(self.n, dtype=T.node_dt)
