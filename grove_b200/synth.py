@@ -190,4 +190,74 @@ def config_c4(n=50000, g=10000, seed=SEED_BASE + 4, max_used_pct=90):
     return dict(name="C4", n_levels=4, nodes=nodes, tables=b.build())
 
 
+class ChurnC5:
+    """BASELINE.json config 5: steady-state churn on the C4 cluster.  Every tick (100 ms of scheduler
+    time) `arrivals` new PodGangs join the gangs still pending from earlier ticks, one cycle runs, and
+    the pods of ~`release_pct` % of the running gangs finish (their resources return to their nodes
+    through grove_update_nodes).  Deterministic from the seed; the oracle and the engine are driven
+    with identical inputs tick by tick."""
+
+    def __init__(self, n=50000, arrivals=100, seed=SEED_BASE + 5, release_pct=1, max_used_pct=60):
+        self.n, self.arrivals, self.seed, self.release_pct = n, arrivals, seed, release_pct
+        self.nodes = kwok_nodes(n, [2520, 126, 18, 1])
+        pre_use(self.nodes, seed, max_used_pct)
+        self.n_levels = 4
+        self.tick = 0
+        self.pending = []   # gang specs carried over: (uid, scopes, level, priority)
+        self.running = []   # (uid, placements ndarray, clique table rows) of admitted gangs
+        self.next_uid = 0
+
+    def _new_gangs(self):
+        t = self.tick
+        w_ = _rand_below(self.seed + t, 1, self.arrivals, 4)
+        pr = _rand_below(self.seed + t, 2, self.arrivals, 3)
+        out = []
+        for i in range(self.arrivals):
+            w = 1 << int(w_[i])
+            lead = dict(cpu=2000, mem=16384, gpu=1, min=1, level=3)
+            work = dict(cpu=1000 * w, mem=8192 * w, gpu=w, min=4)
+            out.append((self.next_uid, [(2, [lead, work])], 1, int(pr[i])))
+            self.next_uid += 1
+        return out
+
+    def begin_tick(self):
+        """-> (gang specs of this tick in submission order, packed tables)"""
+        specs = self.pending + self._new_gangs()
+        b = T.GangTableBuilder()
+        for uid, scopes, level, prio in specs:
+            b.add_gang(scopes, level=level, priority=prio, anchor=int(splitmix64(self.seed, np.array([uid]))[0] % np.uint64(self.n)))
+        return specs, b.build()
+
+    def end_tick(self, specs, tables, status, placements, nodes_after):
+        """Book-keeping after the cycle: rejected gangs stay pending, admitted ones run; then some
+        running gangs finish.  Returns (idx, recs) for grove_update_nodes and the new node table."""
+        g, c, s = tables
+        self.pending = []
+        for i, sp in enumerate(specs):
+            st = int(status["state"][i])
+            if st == T.GANG_ADMITTED:
+                pl = placements[status["placement_off"][i]: status["placement_off"][i] + status["n_pods"][i]]
+                self.running.append((sp[0], pl["node"].copy(), c[pl["clique"]].copy()))
+            else:
+                self.pending.append(sp)
+        nodes = nodes_after.copy()
+        touched = set()
+        keep = []
+        for k, (uid, pnodes, pcl) in enumerate(self.running):
+            h = int(splitmix64(self.seed * 7919 + self.tick, np.array([uid]))[0] % np.uint64(100))
+            if h < self.release_pct:
+                np.add.at(nodes["free_cpu_milli"], pnodes, pcl["req_cpu_milli"])
+                np.add.at(nodes["free_mem_mib"], pnodes, pcl["req_mem_mib"])
+                np.add.at(nodes["free_gpu"], pnodes, pcl["req_gpu"])
+                np.add.at(nodes["free_pods"], pnodes, 1)
+                touched.update(pnodes.tolist())
+            else:
+                keep.append((uid, pnodes, pcl))
+        self.running = keep
+        self.tick += 1
+        idx = np.array(sorted(touched), dtype=np.uint32)
+        self.nodes = nodes
+        return idx, nodes[idx]
+
+
 CONFIGS = {"C1": config_c1, "C2": config_c2, "C3": config_c3, "C4": config_c4}

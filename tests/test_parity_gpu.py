@@ -195,3 +195,29 @@ def test_full_size_properties(built_lib):
     for k, l, row in zip(pl["clique"].tolist(), lv.tolist(), dom.tolist()):
         if l != T.LEVEL_NONE:
             assert first.setdefault(k, row[l]) == row[l]
+
+
+def test_c5_churn_matches_oracle_tick_by_tick(built_lib, oracle):
+    """BASELINE.json config 5 (steady-state churn): arrivals every tick, pending gangs carried over,
+    finished gangs release their nodes through grove_update_nodes; the engine keeps its node table
+    across ticks, the oracle is re-fed the same table; every tick must match bit for bit."""
+    from grove_b200.engine import PlacementEngine
+    ch = synth.ChurnC5(n=50000, arrivals=100, release_pct=5)
+    with PlacementEngine(ch.n_levels) as e:
+        e.load_nodes(ch.nodes)
+        for tick in range(12):
+            specs, tabs = ch.begin_tick()
+            g, c, s = tabs
+            before = ch.nodes
+            e.submit_gangs(g, c, s)
+            e.run_cycle()
+            pl, st, after = e.placements(), e.gang_status(), e.nodes()
+            ref = oracle.run_cycle(before, ch.n_levels, g, c, s, threads=8)
+            assert np.array_equal(pl, ref["placements"]), tick
+            assert np.array_equal(st, ref["status"]), tick
+            assert np.array_equal(after, ref["nodes_after"]), tick
+            idx, recs = ch.end_tick(specs, tabs, st, pl, after)
+            if len(idx):
+                e.update_nodes(idx, recs)
+            assert np.array_equal(e.nodes(), ch.nodes), tick
+        assert ch.tick == 12 and len(ch.running) > 0
