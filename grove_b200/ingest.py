@@ -1,0 +1,119 @@
+"""Kubernetes manifests -> packed tables (the data formats either side of the hot path).
+
+* Node manifests in the shape the reference's KWOK generator emits
+  (/root/reference operator/hack/infra_manager/kwok.py:74-117): allocatable {cpu, memory, pods[, nvidia.com/gpu]},
+  topology labels, NoSchedule taints, spec.unschedulable.
+* PodGang manifests in the CRD's shape (scheduler/api/core/v1alpha1/podgang.go:51-131,
+  crds/scheduler.grove.io_podgangs.yaml): podgroups[].{name, podReferences, minReplicas,
+  topologyConstraint.packConstraint.required}, topologyConstraint, topologyConstraintGroupConfigs,
+  priorityClassName.  What a PodGroup's pods request is not in the CRD (a scheduler reads the Pods); it is
+  passed alongside as {podGroupName: {"cpu": "...", "memory": "...", "nvidia.com/gpu": n}}.
+
+The C++ host mirror (grove_b200/csrc/host) does the same from structs; this module is the file-format
+counterpart used by tools and tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import tables as T
+
+_BIN = {"Ki": 2 ** 10, "Mi": 2 ** 20, "Gi": 2 ** 30, "Ti": 2 ** 40, "Pi": 2 ** 50}
+_DEC = {"k": 10 ** 3, "M": 10 ** 6, "G": 10 ** 9, "T": 10 ** 12}
+
+
+def parse_cpu_milli(q) -> int:
+    """Kubernetes CPU quantity -> millicores ("64" -> 64000, "500m" -> 500, 0.5 -> 500)."""
+    s = str(q).strip()
+    if s.endswith("m"):
+        return int(s[:-1])
+    return int(round(float(s) * 1000))
+
+
+def parse_mem_mib(q) -> int:
+    """Kubernetes memory quantity -> MiB, rounded down ("512Gi" -> 524288, "150Mi" -> 150)."""
+    s = str(q).strip()
+    for suf, mul in _BIN.items():
+        if s.endswith(suf):
+            return int(float(s[: -len(suf)]) * mul) // 2 ** 20
+    for suf, mul in _DEC.items():
+        if s.endswith(suf):
+            return int(float(s[: -len(suf)]) * mul) // 2 ** 20
+    return int(float(s)) // 2 ** 20
+
+
+def nodes_from_manifests(manifests, level_keys, class_key=None, used=None):
+    """Node manifests -> (node table, node names, per-level label interning, class values).
+
+    level_keys: ordered label keys, broadest first (ClusterTopology.spec.levels[].key).
+    class_key:  label whose value partitions nodes into selector classes (class 0 = label absent).
+    used:       optional {node name: {"cpu": q, "memory": q, "nvidia.com/gpu": n, "pods": n}} already requested.
+    """
+    if len(level_keys) > T.MAX_LEVELS:
+        raise ValueError("at most %d topology levels" % T.MAX_LEVELS)
+    nodes = T.make_nodes(len(manifests))
+    names, intern, classes = [], [dict() for _ in level_keys], {}
+    for i, m in enumerate(manifests):
+        meta, spec, status = m.get("metadata", {}), m.get("spec", {}) or {}, m.get("status", {}) or {}
+        names.append(meta.get("name", f"node-{i}"))
+        alloc = status.get("allocatable") or status.get("capacity") or {}
+        u = (used or {}).get(names[-1], {})
+        nodes["free_cpu_milli"][i] = max(0, parse_cpu_milli(alloc.get("cpu", 0)) - parse_cpu_milli(u.get("cpu", 0)))
+        nodes["free_mem_mib"][i] = max(0, parse_mem_mib(alloc.get("memory", 0)) - parse_mem_mib(u.get("memory", 0)))
+        nodes["free_gpu"][i] = max(0, int(alloc.get("nvidia.com/gpu", 0)) - int(u.get("nvidia.com/gpu", 0)))
+        nodes["free_pods"][i] = max(0, int(alloc.get("pods", 110)) - int(u.get("pods", 0)))
+        labels = meta.get("labels", {}) or {}
+        cls = 0
+        if class_key is not None and class_key in labels:
+            cls = classes.setdefault(labels[class_key], len(classes) + 1)
+            if cls > 15:
+                raise ValueError("more than 15 selector classes")
+        sched = not spec.get("unschedulable", False)
+        nodes["flags"][i] = (T.NODE_SCHEDULABLE if sched else 0) | (cls << T.NODE_CLASS_SHIFT)
+        for l, key in enumerate(level_keys):
+            if key in labels:
+                nodes["dom"][i, l] = intern[l].setdefault(labels[key], len(intern[l]))
+    return nodes, names, intern, classes
+
+
+def _level(tc, level_keys):
+    req = (((tc or {}).get("packConstraint") or {}).get("required"))
+    if req is None:
+        return None
+    if req not in level_keys:
+        raise ValueError(f"required topology key {req!r} is not a level of the cluster topology")
+    return level_keys.index(req)
+
+
+def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=None, class_mask=0xFFFF, base_of=None):
+    """PodGang manifests -> (gangs, cliques, scopes, clique_names) with clique_names[row] = (gang name, PodGroup name).
+
+    Cliques of one TopologyConstraintGroupConfig are made adjacent (one scope each); PodGroups in no group form
+    the implicit first scope.  base_of: optional {scaled gang name: base gang name} (gating, syncflow.go:319-358).
+    """
+    b = T.GangTableBuilder()
+    names, row_of = [], {pg["metadata"]["name"]: i for i, pg in enumerate(podgangs)}
+    for pg in podgangs:
+        spec = pg["spec"]
+        groups = {g["name"]: g for g in spec["podgroups"]}
+        grouped = [n for gc in spec.get("topologyConstraintGroupConfigs") or [] for n in gc["podGroupNames"]]
+        scopes = []
+
+        def clique(g):
+            rq = requests.get(g["name"], {})
+            names.append((pg["metadata"]["name"], g["name"]))
+            return dict(cpu=parse_cpu_milli(rq.get("cpu", 0)), mem=parse_mem_mib(rq.get("memory", 0)),
+                        gpu=int(rq.get("nvidia.com/gpu", 0)), min=int(g["minReplicas"]), replicas=len(g["podReferences"]),
+                        level=_level(g.get("topologyConstraint"), level_keys), class_mask=class_mask)
+
+        loose = [g for g in spec["podgroups"] if g["name"] not in grouped]
+        if loose:
+            scopes.append((None, [clique(g) for g in loose]))
+        for gc in spec.get("topologyConstraintGroupConfigs") or []:
+            scopes.append((_level(gc.get("topologyConstraint"), level_keys), [clique(groups[n]) for n in gc["podGroupNames"]]))
+        base = (base_of or {}).get(pg["metadata"]["name"])
+        b.add_gang(scopes, level=_level(spec.get("topologyConstraint"), level_keys),
+                   priority=(priority_classes or {}).get(spec.get("priorityClassName", ""), 0),
+                   base=row_of[base] if base in row_of else None)
+    g, c, s = b.build()
+    return g, c, s, names

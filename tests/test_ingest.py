@@ -1,0 +1,103 @@
+"""Manifests -> tables, pinned on output of the reference's own KWOK node generator
+(tests/golden/kwok_nodes_60.json, made by tests/golden/make_kwok_fixture.py importing
+/root/reference operator/hack/infra_manager/kwok.py in the build container)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from grove_b200 import ingest, synth, tables as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def kwok():
+    with open(os.path.join(HERE, "golden", "kwok_nodes_60.json")) as f:
+        return json.load(f)
+
+
+def test_quantities():
+    assert ingest.parse_cpu_milli("64") == 64000 and ingest.parse_cpu_milli("500m") == 500 and ingest.parse_cpu_milli(4) == 4000
+    assert ingest.parse_mem_mib("512Gi") == 524288 and ingest.parse_mem_mib("150Mi") == 150 and ingest.parse_mem_mib("80Mi") == 80
+    assert ingest.parse_mem_mib("1G") == 953
+
+
+def test_reference_kwok_manifests_match_the_synthetic_generator(kwok):
+    """our label arithmetic (synth.kwok_nodes) == what the reference generator labels its nodes with"""
+    keys = [kwok["label_keys"][k] for k in ("zone", "block", "rack", "host")]
+    nodes, names, intern, classes = ingest.nodes_from_manifests(kwok["manifests"], keys, class_key="node_role.e2e.grove.nvidia.com")
+    per = kwok["nodes_per"]
+    assert (per["zone"], per["block"], per["rack"]) == (28, 20, 7)  # constants.py:65-67
+    ours = synth.kwok_nodes(60, [per["zone"], per["block"], per["rack"], 1], cpu_milli=64000, mem_mib=524288, gpu=0, pods=110, node_class=1)
+    assert names[57] == "kwok-node-57"
+    for f in ("free_cpu_milli", "free_mem_mib", "free_gpu", "free_pods", "flags"):
+        assert np.array_equal(nodes[f], ours[f]), f
+    # interning assigns ids in first-seen order == the integer division for this generator
+    assert np.array_equal(nodes["dom"], ours["dom"])
+    assert classes == {"agent": 1}
+
+
+def test_reference_e2e_preset(kwok):
+    keys = [kwok["label_keys"][k] for k in ("zone", "block", "rack", "host")]
+    nodes, *_ = ingest.nodes_from_manifests(kwok["manifests_e2e"], keys)
+    assert (nodes["free_cpu_milli"] == 4000).all() and (nodes["free_mem_mib"] == 150).all() and (nodes["free_pods"] == 110).all()
+
+
+def test_reference_labels_are_not_a_tree(kwok, oracle):
+    """28/20/7: block-1 straddles zone-0 and zone-1 (20 does not divide 28); path semantics splits it"""
+    keys = [kwok["label_keys"][k] for k in ("zone", "block", "rack", "host")]
+    nodes, *_ = ingest.nodes_from_manifests(kwok["manifests"], keys)
+    perm, dom, ndom, non_tree = oracle.topology(nodes, 4)
+    assert non_tree > 0 and ndom[0] == 3 and ndom[1] > 3
+
+
+def test_used_and_cordon_and_missing_labels(kwok):
+    ms = json.loads(json.dumps(kwok["manifests"][:4]))
+    ms[1]["spec"]["unschedulable"] = True
+    del ms[2]["metadata"]["labels"][kwok["label_keys"]["rack"]]
+    keys = [kwok["label_keys"][k] for k in ("zone", "block", "rack", "host")]
+    nodes, names, *_ = ingest.nodes_from_manifests(ms, keys, used={"kwok-node-0": {"cpu": "1500m", "memory": "2Gi", "pods": 3}})
+    assert nodes["free_cpu_milli"][0] == 62500 and nodes["free_mem_mib"][0] == 524288 - 2048 and nodes["free_pods"][0] == 107
+    assert not nodes["flags"][1] & T.NODE_SCHEDULABLE and nodes["flags"][0] & T.NODE_SCHEDULABLE
+    assert nodes["dom"][2, 2] == T.DOM_ABSENT and nodes["dom"][2, 3] != T.DOM_ABSENT
+
+
+def _podgang(name, groups, gang_key=None, configs=()):
+    tc = lambda k: {"packConstraint": {"required": k}} if k else None  # noqa: E731
+    spec = {"podgroups": [dict(name=n, podReferences=[{"namespace": "default", "name": f"{n}-{i}"} for i in range(r)], minReplicas=m,
+                               **({"topologyConstraint": tc(k)} if k else {})) for n, r, m, k in groups]}
+    if gang_key:
+        spec["topologyConstraint"] = tc(gang_key)
+    if configs:
+        spec["topologyConstraintGroupConfigs"] = [dict(name=cn, podGroupNames=list(members), topologyConstraint=tc(k)) for cn, members, k in configs]
+    return {"apiVersion": "scheduler.grove.io/v1alpha1", "kind": "PodGang", "metadata": {"name": name, "namespace": "default"}, "spec": spec}
+
+
+def test_podgang_manifest_to_tables_and_oracle(kwok, oracle):
+    """tas-hierarchy.yaml as the operator would emit it: PCS block -> PCSG replica rack -> PCLQ host"""
+    Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
+    pg = _podgang("tas-hierarchy-0",
+                  [("r0-prefill", 2, 2, H), ("r0-decode", 2, 2, H), ("r1-prefill", 2, 2, H), ("r1-decode", 2, 2, H), ("router", 1, 1, None)],
+                  gang_key=B, configs=[("ig-0", ("r0-prefill", "r0-decode"), R), ("ig-1", ("r1-prefill", "r1-decode"), R)])
+    req = {n: {"memory": "40Mi"} for n in ("r0-prefill", "r0-decode", "r1-prefill", "r1-decode", "router")}
+    g, c, s, names = ingest.podgangs_from_manifests([pg], req, [Z, B, R, H])
+    assert len(g) == 1 and g["level"][0] == 1 and g["n_scopes"][0] == 3 and g["n_cliques"][0] == 5
+    assert names[0] == ("tas-hierarchy-0", "router") and s["level"].tolist() == [T.LEVEL_NONE, 2, 2]
+    assert c["level"].tolist() == [T.LEVEL_NONE, 3, 3, 3, 3] and c["req_mem_mib"].tolist() == [40] * 5
+    # 14/7 arithmetic nests (unlike 28/20/7): relabel a 14-node block of the reference manifests accordingly
+    ms = json.loads(json.dumps(kwok["manifests_e2e"][:14]))
+    for i, m in enumerate(ms):
+        m["metadata"]["labels"][B] = f"block-{i // 14}"
+    nodes, node_names, *_ = ingest.nodes_from_manifests(ms, [Z, B, R, H])
+    r = oracle.run_cycle(nodes, 4, g, c, s)
+    assert r["status"]["state"][0] == T.GANG_ADMITTED and r["status"]["n_pods"][0] == 9
+    pl = r["placements"]
+    for row in range(1, 5):
+        assert len(set(pl["node"][pl["clique"] == row])) == 1        # each clique on one host
+    for rows in ((1, 2), (3, 4)):
+        racks = {int(nodes["dom"][n, 2]) for n in pl["node"][np.isin(pl["clique"], rows)]}
+        assert len(racks) == 1                                        # each PCSG replica in one rack
+    with pytest.raises(ValueError):
+        ingest.podgangs_from_manifests([_podgang("x", [("a", 1, 1, "example.com/nope")])], {}, [Z, B, R, H])
