@@ -189,11 +189,11 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_dev()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # sampled from the warm-up on: a cycle is milliseconds, nvidia-smi samples every 100 ms
+    for _ in range(args.warmup):
+        step_dev()
     sync()
     t0 = time.perf_counter()
     acc = {k: 0.0 for k in ("ms_fit", "ms_score", "ms_admit", "ms_commit", "ms_total")}
@@ -205,7 +205,6 @@ def run_gpu(args):
         launches += st["kernel_launches"] + 1  # + k_gather of the node-table reset
     sync()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     # e2e through the C ABI with host buffers
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -215,6 +214,7 @@ def run_gpu(args):
         st_e, pl, gs = step_e2e()
     sync()
     dt_e = time.perf_counter() - t1
+    clocks = sampler.stop() if rank == 0 else None  # covers warm-up, the timed steps and the e2e steps
     if dist is not None:
         tt = torch.tensor([dt, dt_e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -282,7 +282,7 @@ def eng_npad(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C4", choices=sorted(synth.CONFIGS))
     ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
