@@ -1,3 +1,5 @@
+# Round-end capture on the GPU box: /usr/local/graft/bin/gpurun --timeout 1200 -- "bash scripts/gpu_capture.sh"
+# (tests, smoke, bench, reference arm, ncu launch list + full captures of k_score / k_admit / k_resolve into gpurun_out/)
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
 python __graft_entry__.py --smoke 2>&1 | tail -1

@@ -221,3 +221,28 @@ def test_c5_churn_matches_oracle_tick_by_tick(built_lib, oracle):
                 e.update_nodes(idx, recs)
             assert np.array_equal(e.nodes(), ch.nodes), tick
         assert ch.tick == 12 and len(ch.running) > 0
+
+
+@pytest.mark.parametrize("env", [{"GROVE_TUNE_PREFILTER": "0"}, {"GROVE_TUNE_PREFILTER": "1"}, {"GROVE_TUNE_WIDTH0": "4"}])
+def test_other_admit_paths_match_too(built_lib, oracle, env):
+    """k_admit has a path that packs from fit words + node records (used when the capacity tables are not
+    built: many distinct signatures) and tuning knobs; all must give the oracle's answer."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from grove_b200 import synth
+        from grove_b200.engine import PlacementEngine
+        from oracle import oracle_py as O
+        for cfg in (synth.config_c3(n=2016, g=300), synth.config_c4(n=5040, g=800), synth.config_c2(n=500, g=80)):
+            g, c, s = cfg["tables"]
+            ref = O.run_cycle(cfg["nodes"], cfg["n_levels"], g, c, s, threads=4)
+            with PlacementEngine(cfg["n_levels"]) as e:
+                e.load_nodes(cfg["nodes"]); e.submit_gangs(g, c, s); e.run_cycle()
+                assert np.array_equal(e.placements(), ref["placements"])
+                assert np.array_equal(e.gang_status(), ref["status"])
+                assert np.array_equal(e.nodes(), ref["nodes_after"])
+        print("ok")
+    ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, **env})
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
