@@ -117,7 +117,7 @@ struct grove_engine {
   bool dbg_on = false;
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
-  uint32_t tune_width0 = 16;
+  uint32_t tune_width0 = 12;  // packing attempts per window in the warp-per-gang kernel
   uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
@@ -296,7 +296,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
   if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(128, std::max(4, std::atoi(v)))) & ~3u;
+  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
@@ -661,7 +661,10 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
   if (e->n_constrained) {
-    if (na >= 148u * 4u) { if (caps) k_admit<kAdmitThreads, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); else k_admit<kAdmitThreads, 1><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); }
+    if (na >= 148u * 4u) {  // throughput round: a warp per gang
+      const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
+      if (caps) k_admit_warp<true><<<nb, kAdmitWarpGangs * 32, 0, e->stream>>>(tp, tb, rb); else k_admit_warp<false><<<nb, kAdmitWarpGangs * 32, 0, e->stream>>>(tp, tb, rb);
+    }
     else { if (caps) k_admit<kAdmitThreadsWide, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); else k_admit<kAdmitThreadsWide, 1><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); }
     e->launches += 1;
   }

@@ -1028,6 +1028,91 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3, throughput form: ONE WARP per gang (4 gangs per CTA), used while a round has many gangs.  The
+// packing of one gang is a chain of dependent L2 look-ups (latency-bound), so what matters is how many
+// gangs are in flight per SM: a warp per gang keeps 24 of them resident instead of 6 with a CTA per
+// gang, and every intra-gang barrier is a __syncwarp.  Same semantics as k_admit: candidates in chunks
+// of 32 (one lane each), pre-filter, packing attempts on the plausible lanes in windows of `width0`,
+// ballots rank the successes, the first K in order are published as alternatives.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAdmitWarpGangs = 4;
+
+template <bool kCaps>
+__global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k_admit_warp(Topo tp, Tables tb, RoundBufs rb) {
+  __shared__ GangShared shs[kAdmitWarpGangs];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ai = blockIdx.x * kAdmitWarpGangs + warp;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t gi = rb.active[ai];
+  const grove_gang_t gg = tb.gangs[gi];
+  if (gg.level == GROVE_LEVEL_NONE) return;  // unconstrained gangs: k_admit<.,2>
+  GangShared& sh = shs[warp];
+  const GangInfo info = tb.ginfo[gi];
+  GangRegs g;
+  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
+#pragma unroll
+  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
+  for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
+    const grove_clique_t q = tb.cliques[gg.clique_off + c];
+    sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
+                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
+    sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
+  }
+  for (uint32_t si = lane; si < gg.n_scopes; si += 32) sh.scopes[si] = tb.scopes[gg.scope_off + si];
+  __syncwarp();
+  const uint32_t K = rb.K, P = rb.P, gl = gg.level;
+  uint32_t plo[kMaxPieces], phi[kMaxPieces];
+  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
+  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
+  for (int p = 0; p < npc; ++p) {
+    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
+    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
+    D += rcnt[p];
+  }
+  ScalarEv<kCaps> ev(tp, rb, sh, g);
+  uint32_t nsucc = 0;
+  for (uint32_t base = 0; base < D && nsucc < K; base += 32) {
+    const uint32_t k = base + lane;
+    uint32_t d = 0, dl = 0, dh = 0;
+    bool plaus = false;
+    if (k < D) {
+      uint32_t rem = k;
+      for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
+      dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+      plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
+    }
+    uint32_t todo = __ballot_sync(kFull, plaus);
+    if (rb.dbg && lane == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, __popc(todo)); }
+    while (todo && nsucc < K) {
+      uint32_t sel = 0, t = todo;
+      for (uint32_t i = 0; i < rb.width0 && t; ++i) { const uint32_t b = t & (0u - t); sel |= b; t ^= b; }
+      todo &= ~sel;
+      bool ok = false;
+      if ((sel >> lane) & 1u) {
+        ev.k = k;
+        ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
+        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
+      }
+      const uint32_t sb = __ballot_sync(kFull, ok);
+      const uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u));
+      if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
+        uint32_t n_min, min_score;
+        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+        const size_t o = size_t(srank) * P + info.pod_off;
+        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.ent_node[i]; rb.alt_meta[o + i] = ev.ent_meta[i]; }
+        rb.alt_n[size_t(gi) * K + srank] = ev.np;
+        rb.alt_score[size_t(gi) * K + srank] = min_score;
+        rb.alt_top[size_t(gi) * K + srank] = dl;
+        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
+      }
+      nsucc += __popc(sb);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) rb.nalt[gi] = min(nsucc, K);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Conflict resolution of one round (cooperative launch: grid-wide barriers between the phases).
 // Up to GROVE_SUBROUNDS passes over the alternatives computed by k_admit: every undecided gang
 // proposes its first alternative that touches no node committed earlier in this round; proposals
