@@ -109,6 +109,7 @@ struct grove_engine {
   DevBuf<uint8_t> d_taken, d_cur, d_prop;
   uint32_t K = GROVE_MAX_ALTERNATIVES;
   uint32_t n_constrained = 0, n_unconstrained = 0;  // gangs with / without a gang-level Required level
+  uint32_t max_gang_pods = 0;
   int resolve_blocks_per_sm = 0;
   uint32_t n_sm = 148;
   DevBuf<uint8_t> d_cap8;
@@ -558,7 +559,8 @@ static int32_t build_ginfo(grove_engine* e) {
       if (e->cinfo[qi].gang != GROVE_NONE_U32) { e->cinfo[qi].sig = remap[e->cinfo[qi].pad][e->cinfo[qi].sig]; e->cinfo[qi].pad = 0; }
   }
   uint32_t pod_off = 0;
-  for (uint32_t gi = 0; gi < G; ++gi) { e->ginfo[gi].pod_off = pod_off; pod_off += gang_pods[gi]; }
+  e->max_gang_pods = 0;
+  for (uint32_t gi = 0; gi < G; ++gi) { e->ginfo[gi].pod_off = pod_off; pod_off += gang_pods[gi]; e->max_gang_pods = std::max(e->max_gang_pods, gang_pods[gi]); }
   e->P = pod_off;
   const auto t_b1 = std::chrono::steady_clock::now();
   for (uint32_t qi = 0; qi < Q; ++qi)
@@ -660,15 +662,24 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
+  const bool small = e->max_gang_pods <= kEntSmem;  // per-lane entry stacks fit the shared-memory form
   if (e->n_constrained) {
     if (na >= 148u * 4u) {  // throughput round: a warp per gang
       const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
-      if (caps) k_admit_warp<true><<<nb, kAdmitWarpGangs * 32, 0, e->stream>>>(tp, tb, rb); else k_admit_warp<false><<<nb, kAdmitWarpGangs * 32, 0, e->stream>>>(tp, tb, rb);
+      const int th = kAdmitWarpGangs * 32;
+      if (caps && small) k_admit_warp<true, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit_warp<true, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit_warp<false, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else k_admit_warp<false, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+    } else {                // latency round: a CTA per gang
+      if (caps && small) k_admit<kAdmitThreadsWide, 0, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit<kAdmitThreadsWide, 0, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit<kAdmitThreadsWide, 1, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else k_admit<kAdmitThreadsWide, 1, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
     }
-    else { if (caps) k_admit<kAdmitThreadsWide, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); else k_admit<kAdmitThreadsWide, 1><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb); }
     e->launches += 1;
   }
-  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
+  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
   CU_TRY(e, cudaGetLastError());
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
   e->launches += 2;

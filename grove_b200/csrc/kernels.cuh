@@ -585,24 +585,36 @@ struct CoopEv {
 };
 
 // ---- scalar evaluator: ONE lane packs one candidate range (lanes of a warp hold different candidates)
-template <bool kCaps>
+// kEnt > 0: the per-lane entry stack (pods placed so far) lives in shared memory, kEnt entries per lane,
+// laid out [entry][thread] -- per-thread local arrays are what made this kernel thrash L1 (every local
+// word is a 128 B line per warp).  kEnt == 0: local arrays sized for the largest legal gang.
+template <bool kCaps, int kEnt>
 struct ScalarEv {
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
-  uint32_t k;   // candidate index of this lane; a lower successful candidate makes this attempt moot
+  uint32_t k;   // candidate index of this lane
   __device__ __forceinline__ bool moot() const { return false; }  // every attempt may become one of the K alternatives
-  uint32_t ent_node[GROVE_MAX_GANG_PODS];
-  uint16_t ent_meta[GROVE_MAX_GANG_PODS];
-  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
-  __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr)
-      : tp(t), rb(r), sh(s), g(gr), np(0), k(0) {}
+  uint32_t* sen; uint16_t* sem; uint32_t stride;
+  uint32_t ent_node_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
+  uint16_t ent_meta_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
+  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];  // written only for cliques with surplus replicas
+  __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr, uint32_t* sen_, uint16_t* sem_, uint32_t stride_)
+      : tp(t), rb(r), sh(s), g(gr), np(0), k(0), sen(sen_), sem(sem_), stride(stride_) {}
+  __device__ __forceinline__ uint32_t& en(uint32_t i) { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
+  __device__ __forceinline__ uint16_t& em(uint32_t i) { if constexpr (kEnt > 0) return sem[i * stride]; else return ent_meta_l[i]; }
+  __device__ __forceinline__ uint32_t en(uint32_t i) const { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
+  __device__ __forceinline__ uint16_t em(uint32_t i) const { if constexpr (kEnt > 0) return sem[i * stride]; else return ent_meta_l[i]; }
+  __device__ __forceinline__ void note_domain(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t w = sh.clq[cr].w;
+    if (((w >> 8) & 0xFFu) > (w & 0xFFu)) { Hlo[cr] = lo; Hhi[cr] = hi; }
+  }
 
   __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
     const uint4 r = __ldg(tp.nres + n);
     uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
     for (uint32_t i = 0; i < np; ++i) {
-      if (ent_node[i] == n) {
-        const uint4 o = sh.clq[ent_meta[i] & 0xFFu];
+      if (en(i) == n) {
+        const uint4 o = sh.clq[em(i) & 0xFFu];
         cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
       }
     }
@@ -611,18 +623,17 @@ struct ScalarEv {
 
   // has this gang already put pods on node n?
   __device__ __forceinline__ bool touched(uint32_t n) const {
-    for (uint32_t i = 0; i < np; ++i) if (ent_node[i] == n) return true;
+    for (uint32_t i = 0; i < np; ++i) if (en(i) == n) return true;
     return false;
   }
 
   // 32 capacity bytes [base, base+32) of one signature row as 8 independent word loads; returns the
   // mask of nodes in [a,b) whose capacity byte is non-zero
-  __device__ __forceinline__ uint32_t load_caps(const uint8_t* row, uint32_t base, uint32_t a, uint32_t b, uint32_t* w) const {
+  __device__ __forceinline__ uint32_t load_caps(const uint8_t* row, uint32_t base, uint32_t a, uint32_t b) const {
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint32_t v = (base + 4u * i < b) ? __ldg(reinterpret_cast<const uint32_t*>(row + base) + i) : 0u;
-      w[i] = v;
       const uint32_t nz = ((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u) >> 7;   // bit 0 of each byte = byte != 0
       mask |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);                             // gather the 4 flags, byte 0 first
     }
@@ -640,17 +651,16 @@ struct ScalarEv {
     uint32_t placed = 0;
     for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
       for (uint32_t base = a & ~3u; base < b && placed < want; base += 32) {
-        uint32_t w[8];
-        uint32_t mask = load_caps(row, base, a, b, w);
+        uint32_t mask = load_caps(row, base, a, b);
         while (mask && placed < want) {
           const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
           const uint32_t n = base + j;
-          uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          uint32_t c = __ldg(row + n);  // the line was just fetched by load_caps
           if (c == 255u || touched(n)) c = cap_now(cr, n);
           const uint32_t t = min(c, want - placed);
           if (t) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
-            for (uint32_t x = 0; x < t; ++x) { ent_node[np + x] = n; ent_meta[np + x] = meta; }
+            for (uint32_t x = 0; x < t; ++x) { en(np + x) = n; em(np + x) = meta; }
             np += t; placed += t;
           }
         }
@@ -666,18 +676,17 @@ struct ScalarEv {
     PieceIt pit; pit.init(g, lo, hi, g.L);
     for (uint32_t a, b; pit.next(g, a, b);) {
       for (uint32_t base = a & ~3u; base < b; base += 32) {
-        uint32_t w[8];
-        uint32_t mask = load_caps(row, base, a, b, w);
+        uint32_t mask = load_caps(row, base, a, b);
         while (mask) {
           const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
           const uint32_t n = base + j;
-          uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          uint32_t c = __ldg(row + n);  // the line was just fetched by load_caps
           if (c < m && c != 255u) continue;   // capacities only shrink inside an attempt
           if (c == 255u || touched(n)) c = cap_now(cr, n);
           if (c >= m) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
-            for (uint32_t x = 0; x < m; ++x) { ent_node[np + x] = n; ent_meta[np + x] = meta; }
-            np += m; Hlo[cr] = n; Hhi[cr] = n + 1;
+            for (uint32_t x = 0; x < m; ++x) { en(np + x) = n; em(np + x) = meta; }
+            np += m; note_domain(cr, n, n + 1);
             return true;
           }
         }
@@ -705,7 +714,7 @@ struct ScalarEv {
           const uint32_t t = min(c, want - placed);
           if (t) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
-            for (uint32_t j = 0; j < t; ++j) { ent_node[np + j] = n; ent_meta[np + j] = meta; }
+            for (uint32_t j = 0; j < t; ++j) { en(np + j) = n; em(np + j) = meta; }
             np += t; placed += t;
           }
         }
@@ -718,7 +727,7 @@ struct ScalarEv {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t mark = np;
     if (take(cr, lo, hi, m) < m) { np = mark; return false; }
-    Hlo[cr] = lo; Hhi[cr] = hi;
+    note_domain(cr, lo, hi);
     return true;
   }
 
@@ -738,8 +747,8 @@ struct ScalarEv {
           const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
           if (cap_now(cr, n) >= m) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
-            for (uint32_t j = 0; j < m; ++j) { ent_node[np + j] = n; ent_meta[np + j] = meta; }
-            np += m; Hlo[cr] = n; Hhi[cr] = n + 1;
+            for (uint32_t j = 0; j < m; ++j) { en(np + j) = n; em(np + j) = meta; }
+            np += m; note_domain(cr, n, n + 1);
             return true;
           }
         }
@@ -858,17 +867,16 @@ __device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, in
   return true;
 }
 
-// surplus beyond MinReplicas (best effort) + publication of the speculative placement
+// surplus beyond MinReplicas (best effort) of a successful scalar attempt; min score over the MinReplicas pods
 template <class Ev>
-__device__ void finish_gang(Ev& ev, const uint32_t* ent_node, const uint16_t* ent_meta, const uint32_t* Hlo,
-                            const uint32_t* Hhi, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
+__device__ void finish_gang(Ev& ev, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
   n_min = ev.np;
   min_score = ev.tp.L + 1;
-  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ent_meta[i] >> 8));
+  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ev.em(i) >> 8));
   for (uint32_t cr = 0; cr < n_cliques; ++cr) {
     const uint32_t w = ev.sh.clq[cr].w;
     const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-    if (rp > mn) ev.take(cr, Hlo[cr], Hhi[cr], rp - mn);
+    if (rp > mn) ev.take(cr, ev.Hlo[cr], ev.Hhi[cr], rp - mn);
   }
 }
 
@@ -886,9 +894,11 @@ constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps p
 // kMode 0: gangs with a gang-level constraint, packing from capacity bytes; 1: same, packing from fit
 // words + node records (no capacity tables this cycle); 2: gangs without a gang-level constraint
 // (cooperative).  Each instantiation skips the gangs of the other kind.
-template <int kThreads, int kMode>
+template <int kThreads, int kMode, int kEnt>
 __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
+  __shared__ uint32_t s_en[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
+  __shared__ uint16_t s_em[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ai = blockIdx.x;
   if (ai >= rb.counters[0]) return;
@@ -951,7 +961,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
     D += rcnt[p];
   }
-  ScalarEv<kMode == 0> ev(tp, rb, sh, g);
+  ScalarEv<kMode == 0, kEnt> ev(tp, rb, sh, g, s_en + tid, s_em + tid, kThreads);
   __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
   __shared__ uint32_t s_okmask[kAdmitThreadsWide / 32];
   __shared__ uint32_t s_ck[kAdmitThreadsWide], s_cl[kAdmitThreadsWide], s_ch[kAdmitThreadsWide];  // plausible candidates of the chunk, in order
@@ -1009,9 +1019,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
       }
       if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
         uint32_t n_min, min_score;
-        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+        finish_gang(ev, gg.n_cliques, n_min, min_score);
         const size_t o = size_t(srank) * P + info.pod_off;
-        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.ent_node[i]; rb.alt_meta[o + i] = ev.ent_meta[i]; }
+        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
         rb.alt_score[size_t(gi) * K + srank] = min_score;
         rb.alt_top[size_t(gi) * K + srank] = dl;
@@ -1036,10 +1046,13 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
 // ballots rank the successes, the first K in order are published as alternatives.
 // ------------------------------------------------------------------------------------------------
 constexpr int kAdmitWarpGangs = 4;
+constexpr int kEntSmem = 16;  // per-lane entry stack depth of the shared-memory form (gangs of <= 16 pods)
 
-template <bool kCaps>
+template <bool kCaps, int kEnt>
 __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k_admit_warp(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared shs[kAdmitWarpGangs];
+  __shared__ uint32_t s_en[(kEnt ? kEnt : 1) * kAdmitWarpGangs * 32];
+  __shared__ uint16_t s_em[(kEnt ? kEnt : 1) * kAdmitWarpGangs * 32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ai = blockIdx.x * kAdmitWarpGangs + warp;
   if (ai >= rb.counters[0]) return;
@@ -1069,7 +1082,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
     rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
     D += rcnt[p];
   }
-  ScalarEv<kCaps> ev(tp, rb, sh, g);
+  ScalarEv<kCaps, kEnt> ev(tp, rb, sh, g, s_en + threadIdx.x, s_em + threadIdx.x, kAdmitWarpGangs * 32);
   uint32_t nsucc = 0;
   for (uint32_t base = 0; base < D && nsucc < K; base += 32) {
     const uint32_t k = base + lane;
@@ -1097,9 +1110,9 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       const uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u));
       if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
         uint32_t n_min, min_score;
-        finish_gang(ev, ev.ent_node, ev.ent_meta, ev.Hlo, ev.Hhi, gg.n_cliques, n_min, min_score);
+        finish_gang(ev, gg.n_cliques, n_min, min_score);
         const size_t o = size_t(srank) * P + info.pod_off;
-        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.ent_node[i]; rb.alt_meta[o + i] = ev.ent_meta[i]; }
+        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
         rb.alt_score[size_t(gi) * K + srank] = min_score;
         rb.alt_top[size_t(gi) * K + srank] = dl;
