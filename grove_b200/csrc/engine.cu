@@ -118,7 +118,7 @@ struct grove_engine {
   bool dbg_on = false;
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
-  uint32_t tune_width0 = 12;  // packing attempts per window in the warp-per-gang kernel
+  uint32_t tune_width0 = 24;  // packing attempts per window in the warp-per-gang kernel
   uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;

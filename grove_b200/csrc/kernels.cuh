@@ -479,6 +479,7 @@ __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_
 struct CoopEv {
   const Topo& tp; const RoundBufs& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
   uint32_t np;
+  uint32_t tmask = 0;
   __device__ __forceinline__ bool moot() const { return false; }
   __device__ CoopEv(const Topo& t, const RoundBufs& r, GangShared& s, const GangRegs& gr, uint32_t ln)
       : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
@@ -592,6 +593,7 @@ template <bool kCaps, int kEnt>
 struct ScalarEv {
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
+  uint32_t tmask;  // bit (n & 31) set for every node this attempt has put a pod on: quick 'untouched' test
   uint32_t k;   // candidate index of this lane
   __device__ __forceinline__ bool moot() const { return false; }  // every attempt may become one of the K alternatives
   uint32_t* sen; uint16_t* sem; uint32_t stride;
@@ -599,7 +601,7 @@ struct ScalarEv {
   uint16_t ent_meta_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];  // written only for cliques with surplus replicas
   __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr, uint32_t* sen_, uint16_t* sem_, uint32_t stride_)
-      : tp(t), rb(r), sh(s), g(gr), np(0), k(0), sen(sen_), sem(sem_), stride(stride_) {}
+      : tp(t), rb(r), sh(s), g(gr), np(0), tmask(0), k(0), sen(sen_), sem(sem_), stride(stride_) {}
   __device__ __forceinline__ uint32_t& en(uint32_t i) { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
   __device__ __forceinline__ uint16_t& em(uint32_t i) { if constexpr (kEnt > 0) return sem[i * stride]; else return ent_meta_l[i]; }
   __device__ __forceinline__ uint32_t en(uint32_t i) const { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
@@ -623,6 +625,7 @@ struct ScalarEv {
 
   // has this gang already put pods on node n?
   __device__ __forceinline__ bool touched(uint32_t n) const {
+    if (!((tmask >> (n & 31)) & 1u)) return false;
     for (uint32_t i = 0; i < np; ++i) if (en(i) == n) return true;
     return false;
   }
@@ -644,7 +647,7 @@ struct ScalarEv {
 
   // capacity-table path: per-node capacities come as bytes (computed once per round for the signature);
   // only nodes this gang already touched, or saturated bytes, are recomputed from the node record
-  __device__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+  __device__ __forceinline__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
@@ -661,6 +664,7 @@ struct ScalarEv {
           if (t) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
             for (uint32_t x = 0; x < t; ++x) { en(np + x) = n; em(np + x) = meta; }
+            tmask |= 1u << (n & 31);
             np += t; placed += t;
           }
         }
@@ -669,7 +673,7 @@ struct ScalarEv {
     return placed;
   }
 
-  __device__ bool find_unit_caps(uint32_t cr, uint32_t lo, uint32_t hi) {
+  __device__ __forceinline__ bool find_unit_caps(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
     const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
@@ -686,6 +690,7 @@ struct ScalarEv {
           if (c >= m) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
             for (uint32_t x = 0; x < m; ++x) { en(np + x) = n; em(np + x) = meta; }
+            tmask |= 1u << (n & 31);
             np += m; note_domain(cr, n, n + 1);
             return true;
           }
@@ -695,7 +700,7 @@ struct ScalarEv {
     return false;
   }
 
-  __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+  __device__ __forceinline__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
     if constexpr (kCaps) return take_caps(cr, lo, hi, want);
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
@@ -715,6 +720,7 @@ struct ScalarEv {
           if (t) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
             for (uint32_t j = 0; j < t; ++j) { en(np + j) = n; em(np + j) = meta; }
+            tmask |= 1u << (n & 31);
             np += t; placed += t;
           }
         }
@@ -723,7 +729,7 @@ struct ScalarEv {
     return placed;
   }
 
-  __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
+  __device__ __forceinline__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t mark = np;
     if (take(cr, lo, hi, m) < m) { np = mark; return false; }
@@ -731,7 +737,7 @@ struct ScalarEv {
     return true;
   }
 
-  __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+  __device__ __forceinline__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
     if constexpr (kCaps) return find_unit_caps(cr, lo, hi);
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
@@ -748,6 +754,7 @@ struct ScalarEv {
           if (cap_now(cr, n) >= m) {
             const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
             for (uint32_t j = 0; j < m; ++j) { en(np + j) = n; em(np + j) = meta; }
+            tmask |= 1u << (n & 31);
             np += m; note_domain(cr, n, n + 1);
             return true;
           }
@@ -762,7 +769,7 @@ struct ScalarEv {
 // (each clique alone must find MinReplicas worth of capacity in a domain it could be packed into, and
 // the cliques of a scope must find it inside one common scope domain).  Reads only the small
 // per-signature capacity tables.
-__device__ bool clique_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t cr,
+__device__ __forceinline__ bool clique_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t cr,
                                  uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
   const uint32_t w = sh.clq[cr].w;
   const uint32_t m = w & 0xFFu, ql = (w >> 16) & 0xFFu;
@@ -786,7 +793,7 @@ __device__ bool clique_plausible(const Topo& tp, const RoundBufs& rb, const Gang
   return sum >= m;
 }
 
-__device__ bool scope_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, const grove_scope_t& s,
+__device__ __forceinline__ bool scope_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, const grove_scope_t& s,
                                 uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
   uint32_t all = 1;
   for (uint32_t i = 0; i < s.n_cliques; ++i) all &= clique_plausible(tp, rb, sh, s.first_clique + i, lo, hi, lvl, dE);
@@ -813,7 +820,7 @@ __device__ bool gang_plausible(const Topo& tp, const RoundBufs& rb, const GangSh
 }
 
 template <class Ev>
-__device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
+__device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
   const uint32_t mark = ev.np;
   for (uint32_t i = 0; i < s.n_cliques; ++i) {
@@ -841,9 +848,9 @@ __device__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_
 }
 
 template <class Ev>
-__device__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
+__device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
-  ev.np = 0;
+  ev.np = 0; ev.tmask = 0;
   for (uint32_t si = 0; si < n_scopes; ++si) {
     const grove_scope_t s = ev.sh.scopes[si];
     bool ok = false;
