@@ -1103,9 +1103,14 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
     }
     uint32_t todo = __ballot_sync(kFull, plaus);
     if (rb.dbg && lane == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, __popc(todo)); }
+    bool first_window = base == 0;
     while (todo && nsucc < K) {
+      // first window: a few more candidates than alternatives wanted (in an uncongested cluster nearly all
+      // fit); if that was not enough the cluster is congested: take every plausible candidate of the chunk
       uint32_t sel = 0, t = todo;
-      for (uint32_t i = 0; i < rb.width0 && t; ++i) { const uint32_t b = t & (0u - t); sel |= b; t ^= b; }
+      const uint32_t wmax = first_window ? rb.width0 : 32u;
+      first_window = false;
+      for (uint32_t i = 0; i < wmax && t; ++i) { const uint32_t b = t & (0u - t); sel |= b; t ^= b; }
       todo &= ~sel;
       bool ok = false;
       if ((sel >> lane) & 1u) {
