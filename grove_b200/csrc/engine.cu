@@ -100,7 +100,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_sig_stamp, d_sig_list;
 
   // ---- round state ----
-  DevBuf<uint8_t> d_state, d_round, d_spec_ok, d_spec_score, d_T;
+  DevBuf<uint8_t> d_state, d_round, d_spec_score, d_T;
   DevBuf<uint16_t> d_spec_n, d_ent_meta;
   DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
   DevBuf<grove_gang_status_t> d_status;
@@ -253,7 +253,7 @@ static Tables make_tables(grove_engine* e) {
 static RoundBufs make_bufs(grove_engine* e) {
   RoundBufs r{};
   r.state = e->d_state.p; r.round = e->d_round.p; r.active = e->d_active.p; r.rows = e->d_rows.p;
-  r.counters = e->d_counters.p; r.spec_ok = e->d_spec_ok.p; r.spec_score = e->d_spec_score.p;
+  r.counters = e->d_counters.p; r.spec_score = e->d_spec_score.p;
   r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
   r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
   r.active_all = e->d_active_all.p; r.taken = e->d_taken.p; r.cur = e->d_cur.p; r.prop = e->d_prop.p; r.flags = e->d_flags.p;
@@ -593,7 +593,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   if (e->ginfo_dirty) { int32_t rc = build_ginfo(e); if (rc) return rc; }
   const uint32_t G = e->G, Q = e->Q;
   CU_TRY(e, e->d_state.ensure(G)); CU_TRY(e, e->d_round.ensure(G)); CU_TRY(e, e->d_active.ensure(G)); CU_TRY(e, e->d_rows.ensure(Q));
-  CU_TRY(e, e->d_counters.ensure(8)); CU_TRY(e, e->d_spec_ok.ensure(G)); CU_TRY(e, e->d_spec_score.ensure(G));
+  CU_TRY(e, e->d_counters.ensure(8)); CU_TRY(e, e->d_spec_score.ensure(G));
   CU_TRY(e, e->d_spec_n.ensure(G)); CU_TRY(e, e->d_spec_top.ensure(G)); CU_TRY(e, e->d_ent_node.ensure(e->P)); CU_TRY(e, e->d_ent_meta.ensure(e->P));
   CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
   CU_TRY(e, e->d_taken.ensure(e->N)); CU_TRY(e, e->d_cur.ensure(G)); CU_TRY(e, e->d_prop.ensure(G)); CU_TRY(e, e->d_flags.ensure(GROVE_SUBROUNDS));

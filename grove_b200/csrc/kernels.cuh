@@ -68,7 +68,6 @@ struct RoundBufs {
                          // [5] active gangs over all ranks [6] gangs resolved by this round's apply
   uint32_t* sig_stamp;   // [S] last round in which the signature was active
   uint32_t* sig_list;    // [S] signatures needed this round
-  uint8_t* spec_ok;      // [G]
   uint8_t* spec_score;   // [G]
   uint16_t* spec_n;      // [G] entries incl. surplus
   uint32_t* spec_top;    // [G]
@@ -405,7 +404,6 @@ struct GangShared {
   uint32_t ent_node[GROVE_MAX_GANG_PODS];
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel | score << 8
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
-  uint32_t best;                           // lowest successful candidate index of the current step
 };
 
 // Ordered pieces of [lo,hi): descending score, ties by ascending rotated index (n - anchor) mod N.
@@ -924,7 +922,6 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
   }
   for (uint32_t si = tid; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
-  if (tid == 0) sh.best = GROVE_NONE_U32;
   __syncthreads();
 
   const uint32_t K = rb.K, P = rb.P;
@@ -975,10 +972,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   const uint32_t nwarp = blockDim.x >> 5;
   uint32_t nsucc = 0;  // feasible candidates found so far (block-uniform)
   // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
-  // compact the plausible ones, then run the packing on them one lane per candidate.  The first window
-  // is narrow (2 K candidates, in an uncongested cluster the first ones already fit) and spread over
-  // all warps so that the divergent attempts serialise as little as possible.  The first K feasible
-  // candidates in order become the gang's alternatives.
+  // compact the plausible ones, then run the packing on them one lane per candidate.  The first K
+  // feasible candidates in order become the gang's alternatives.
   for (uint32_t base = 0; base < D && nsucc < K; base += blockDim.x) {
     {
       const uint32_t k = base + tid;
@@ -1002,11 +997,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
     __syncthreads();
     for (uint32_t abase = 0; abase < total && nsucc < K;) {
-      const bool narrow = base == 0 && abase == 0 && blockDim.x == kAdmitThreads;
-      const uint32_t width = narrow ? rb.width0 : blockDim.x;
-      // slot of this thread inside the window: narrow windows put width/nwarp slots on each warp
-      const uint32_t per = width / nwarp;
-      const uint32_t slot = narrow ? (lane < per ? warp * per + lane : GROVE_NONE_U32) : tid;
+      const uint32_t width = blockDim.x;  // every plausible candidate of the chunk at once (latency rounds)
+      const uint32_t slot = tid;
       if (tid < (kAdmitThreadsWide / 32)) s_okmask[tid] = 0;
       __syncthreads();
       bool ok = false; uint32_t k = 0, dl = 0;
