@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -191,7 +191,7 @@ def run_gpu(args):
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()  # sampled from the warm-up on: a cycle is milliseconds, nvidia-smi samples every 100 ms
+        sampler.start()  # sampled from the warm-up on: a cycle is milliseconds, nvidia-smi samples every 20 ms
     for _ in range(args.warmup):
         step_dev()
     sync()
