@@ -11,10 +11,10 @@ from grove_b200 import tables as T
 pytestmark = pytest.mark.gpu
 
 
-def random_case(seed):
+def random_case(seed, big=False):
     rng = np.random.default_rng(seed)
     L = int(rng.integers(1, 5))
-    n = int(rng.integers(1, 400))
+    n = int(rng.integers(1, 400)) if not big else int(rng.integers(1500, 4000))
     fan = [int(rng.integers(2, 9)) for _ in range(L)]
     nodes = T.make_nodes(n)
     idx = np.arange(n)
@@ -35,7 +35,7 @@ def random_case(seed):
     sched = rng.random(n) > 0.1
     nodes["flags"] = (sched * T.NODE_SCHEDULABLE) | (cls.astype(np.uint32) << T.NODE_CLASS_SHIFT)
     b = T.GangTableBuilder()
-    G = int(rng.integers(1, 40))
+    G = int(rng.integers(1, 40)) if not big else int(rng.integers(700, 1500))  # big: the warp-per-gang kernel (>= 592 active gangs)
     for gi in range(G):
         glevel = None if rng.random() < 0.35 else int(rng.integers(0, L))
         scopes, pods = [], 0
@@ -55,8 +55,8 @@ def random_case(seed):
                                     min=mn, replicas=rep, level=clevel, class_mask=int(rng.choice([0xFFFF, 0x1, 0x6, 0x8]))))
             scopes.append((slevel, cliques))
         base = None
-        if gi > 0 and rng.random() < 0.3:
-            base = int(rng.integers(0, gi))
+        if gi > 0 and rng.random() < (0.3 if not big else 0.05):
+            base = int(rng.integers(0, gi)) if not big else int(rng.integers(max(0, gi - 50), gi))
         b.add_gang(scopes, level=glevel, priority=int(rng.integers(0, 3)), anchor=None if rng.random() < 0.5 else int(rng.integers(0, n)),
                    base=base, gated=bool(rng.random() < 0.05))
     return nodes, L, b.build()
@@ -88,3 +88,17 @@ def test_random_snapshots_with_one_alternative(built_lib, oracle):
             e.load_nodes(nodes); e.submit_gangs(g, c, s); e.run_cycle()
             assert np.array_equal(e.gang_status(), ref["status"]), seed
             assert np.array_equal(e.placements(), ref["placements"]), seed
+
+
+def test_random_big_snapshots_hit_the_warp_per_gang_kernel(built_lib, oracle):
+    from grove_b200.engine import PlacementEngine
+    for seed in range(2000, 2006):
+        nodes, L, (g, c, s) = random_case(seed, big=True)
+        ref = oracle.run_cycle(nodes, L, g, c, s, threads=8)
+        with PlacementEngine(L) as e:
+            e.load_nodes(nodes); e.submit_gangs(g, c, s)
+            st = e.run_cycle()
+            assert st["rounds"] == ref["stats"]["rounds"], seed
+            assert np.array_equal(e.gang_status(), ref["status"]), seed
+            assert np.array_equal(e.placements(), ref["placements"]), seed
+            assert np.array_equal(e.nodes(), ref["nodes_after"]), seed
