@@ -64,6 +64,8 @@ struct grove_engine {
   grove_config_t cfg{};
   std::string err;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_score = nullptr;  // K2 runs beside K3 (they only share the fit data)
+  cudaEvent_t ev_fit = nullptr, ev_score = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   cudaEvent_t ev[10]{};
 
   // ---- topology (static until labels change) ----
@@ -119,6 +121,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
   uint32_t tune_width0 = 24;  // packing attempts per window in the warp-per-gang kernel
+  bool tune_overlap = true;      // K2 on a second stream beside K3 (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
   uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
@@ -261,7 +264,7 @@ static RoundBufs make_bufs(grove_engine* e) {
     const size_t KP = size_t(e->K) * e->P, GK = size_t(e->G) * e->K;
     uint32_t* x = e->d_xbuf.p;
     r.alt_node = x; r.alt_meta = x + KP; r.alt_n = x + 2 * KP; r.alt_score = x + 2 * KP + GK; r.alt_top = x + 2 * KP + 2 * GK;
-    r.nalt = x + 2 * KP + 3 * GK; r.K = e->K; r.P = e->P;
+    r.alt_nmin = x + 2 * KP + 3 * GK; r.nalt = x + 2 * KP + 4 * GK; r.K = e->K; r.P = e->P;
   }
   r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
   r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
@@ -296,9 +299,15 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
+  if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the latency-bound admission gets the SMs first
+  if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&e->stream_score, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  if (cudaEventCreateWithFlags(&e->ev_fit, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_score, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&e->ev_s0) != cudaSuccess || cudaEventCreate(&e->ev_s1) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
   *out = e;
@@ -310,6 +319,11 @@ void grove_engine_destroy(grove_engine_t* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->ev_s0) cudaEventDestroy(e->ev_s0);
+  if (e->ev_s1) cudaEventDestroy(e->ev_s1);
+  if (e->ev_fit) cudaEventDestroy(e->ev_fit);
+  if (e->ev_score) cudaEventDestroy(e->ev_score);
+  if (e->stream_score) cudaStreamDestroy(e->stream_score);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -598,7 +612,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
   CU_TRY(e, e->d_taken.ensure(e->N)); CU_TRY(e, e->d_cur.ensure(G)); CU_TRY(e, e->d_prop.ensure(G)); CU_TRY(e, e->d_flags.ensure(GROVE_SUBROUNDS));
   CU_TRY(e, e->d_active_all.ensure(G));
-  CU_TRY(e, e->d_xbuf.ensure(2 * size_t(e->K) * e->P + 3 * size_t(G) * e->K + G));
+  CU_TRY(e, e->d_xbuf.ensure(2 * size_t(e->K) * e->P + 4 * size_t(G) * e->K + G));
   CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // k_resolve withdraws its claims itself
   CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
   CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
@@ -632,7 +646,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   return GROVE_OK;
 }
 
-static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P + 3 * size_t(e->G) * e->K + e->G; }
+static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P + 4 * size_t(e->G) * e->K + e->G; }
 
 // evaluation half of a round on this handle's share of the gangs: prepare -> fit -> (capacity tables)
 // -> score -> admit.  Counters land in h_counters.
@@ -652,13 +666,22 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
   dim3 gfit(e->Npad / 1024, std::min<uint32_t>((ns + kFitTile - 1) / kFitTile, 65535u));
   k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
+  // fork: the score matrix goes to the second stream and overlaps the admission
+  cudaStream_t ss = e->tune_overlap ? e->stream_score : e->stream;
+  if (e->tune_overlap) {
+    CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream));
+    CU_TRY(e, cudaStreamWaitEvent(e->stream_score, e->ev_fit, 0));
+  }
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev_s0, ss));
+  k_score<<<dim3(1, std::min<uint32_t>(nr, 65535u)), 256, 0, ss>>>(tp, tb, rb, nr);  // one CTA per row
+  if (timed) CU_TRY(e, cudaEventRecord(e->ev_s1, ss));
+  if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_score, e->stream_score));
   if (e->prefilter && ns) {
     k_cap8<<<dim3(e->Npad / 256, ns), 256, 0, e->stream>>>(tp, tb, rb, e->d_cap8.p);
     k_capsum<<<dim3((e->cap_stride * 32 + 255) / 256, ns), 256, 0, e->stream>>>(tp, rb, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
     e->launches += 2;
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
-  k_score<<<dim3(1, std::min<uint32_t>(nr, 65535u)), 256, 0, e->stream>>>(tp, tb, rb, nr);  // one CTA per row
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
@@ -680,9 +703,12 @@ static int32_t round_eval(grove_engine* e, bool timed) {
     e->launches += 1;
   }
   if (e->n_unconstrained) { k_admit<kAdmitThreads, 2, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
+  // join: scores of the alternatives need both the score matrix and the alternatives
+  if (e->tune_overlap) CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_score, 0));
+  k_alt_scores<<<(na * e->K * 32 + 255) / 256, 256, 0, e->stream>>>(tp, tb, rb);
   CU_TRY(e, cudaGetLastError());
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
-  e->launches += 2;
+  e->launches += 3;
   e->pairs += uint64_t(nr) * e->N;
   return GROVE_OK;
 }
@@ -763,7 +789,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     CU_TRY(e, cudaEventSynchronize(e->ev[4]));
     float t;
     cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); ms_fit += t;
-    cudaEventElapsedTime(&t, e->ev[1], e->ev[2]); ms_score += t;
+    cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1); ms_score += t;  // on its own stream, overlapping the admission
     cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_admit += t;
     cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_commit += t;
     if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr

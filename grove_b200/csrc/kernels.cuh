@@ -83,7 +83,8 @@ struct RoundBufs {
   uint32_t* alt_node;    // [K][P] entry i of alternative a of gang g at a*P + pod_off[g] + i
   uint32_t* alt_meta;    // [K][P] clique_rel | score << 8
   uint32_t* alt_n;       // [G][K] entries incl. surplus
-  uint32_t* alt_score;   // [G][K]
+  uint32_t* alt_score;   // [G][K] min score over the MinReplicas entries (written by k_alt_scores)
+  uint32_t* alt_nmin;    // [G][K] entries of the MinReplicas phase (the rest is best-effort surplus)
   uint32_t* alt_top;     // [G][K]
   uint32_t* nalt;        // [G]
   uint32_t K, P;
@@ -498,7 +499,6 @@ struct CoopEv {
   __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
     for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
@@ -521,7 +521,7 @@ struct CoopEv {
           const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
           const uint32_t tincl = warp_incl_scan(t, lane);
           if (t) {
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint16_t meta = uint16_t(cr);
             const uint32_t pos = np + tincl - t;
             for (uint32_t j = 0; j < t; ++j) { sh.ent_node[pos + j] = n; sh.ent_meta[pos + j] = meta; }
           }
@@ -548,7 +548,6 @@ struct CoopEv {
   __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     for (uint32_t a, b; pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
@@ -569,7 +568,7 @@ struct CoopEv {
           const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
           if (okb) {
             const uint32_t nn = ((wb + src) << 5) + (__ffs(okb) - 1);
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[nn]) << 8));
+            const uint16_t meta = uint16_t(cr);
             for (uint32_t j = lane; j < m; j += 32) { sh.ent_node[np + j] = nn; sh.ent_meta[np + j] = meta; }
             if (lane == 0) { sh.Hlo[cr] = nn; sh.Hhi[cr] = nn + 1; }
             np += m;
@@ -647,7 +646,6 @@ struct ScalarEv {
   // only nodes this gang already touched, or saturated bytes, are recomputed from the node record
   __device__ __forceinline__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
     for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
@@ -660,7 +658,7 @@ struct ScalarEv {
           if (c == 255u || touched(n)) c = cap_now(cr, n);
           const uint32_t t = min(c, want - placed);
           if (t) {
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint16_t meta = uint16_t(cr);
             for (uint32_t x = 0; x < t; ++x) { en(np + x) = n; em(np + x) = meta; }
             tmask |= 1u << (n & 31);
             np += t; placed += t;
@@ -674,7 +672,6 @@ struct ScalarEv {
   __device__ __forceinline__ bool find_unit_caps(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     for (uint32_t a, b; pit.next(g, a, b);) {
       for (uint32_t base = a & ~3u; base < b; base += 32) {
@@ -686,7 +683,7 @@ struct ScalarEv {
           if (c < m && c != 255u) continue;   // capacities only shrink inside an attempt
           if (c == 255u || touched(n)) c = cap_now(cr, n);
           if (c >= m) {
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint16_t meta = uint16_t(cr);
             for (uint32_t x = 0; x < m; ++x) { en(np + x) = n; em(np + x) = meta; }
             tmask |= 1u << (n & 31);
             np += m; note_domain(cr, n, n + 1);
@@ -702,7 +699,6 @@ struct ScalarEv {
     if (want == 0 || hi <= lo) return 0;
     if constexpr (kCaps) return take_caps(cr, lo, hi, want);
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     uint32_t placed = 0;
     for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
@@ -716,7 +712,7 @@ struct ScalarEv {
           const uint32_t c = cap_now(cr, n);
           const uint32_t t = min(c, want - placed);
           if (t) {
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint16_t meta = uint16_t(cr);
             for (uint32_t j = 0; j < t; ++j) { en(np + j) = n; em(np + j) = meta; }
             tmask |= 1u << (n & 31);
             np += t; placed += t;
@@ -739,7 +735,6 @@ struct ScalarEv {
     if constexpr (kCaps) return find_unit_caps(cr, lo, hi);
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    const uint8_t* Trow = rb.T + size_t(g.clique_off + cr) * tp.npad;
     PieceIt pit; pit.init(g, lo, hi, g.L);
     for (uint32_t a, b; pit.next(g, a, b);) {
       const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
@@ -750,7 +745,7 @@ struct ScalarEv {
         while (bits) {
           const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
           if (cap_now(cr, n) >= m) {
-            const uint16_t meta = uint16_t(cr | (uint32_t(Trow[n]) << 8));
+            const uint16_t meta = uint16_t(cr);
             for (uint32_t j = 0; j < m; ++j) { en(np + j) = n; em(np + j) = meta; }
             tmask |= 1u << (n & 31);
             np += m; note_domain(cr, n, n + 1);
@@ -872,12 +867,10 @@ __device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo,
   return true;
 }
 
-// surplus beyond MinReplicas (best effort) of a successful scalar attempt; min score over the MinReplicas pods
+// surplus beyond MinReplicas (best effort) of a successful scalar attempt
 template <class Ev>
-__device__ void finish_gang(Ev& ev, uint32_t n_cliques, uint32_t& n_min, uint32_t& min_score) {
+__device__ void finish_gang(Ev& ev, uint32_t n_cliques, uint32_t& n_min) {
   n_min = ev.np;
-  min_score = ev.tp.L + 1;
-  for (uint32_t i = 0; i < n_min; ++i) min_score = min(min_score, uint32_t(ev.em(i) >> 8));
   for (uint32_t cr = 0; cr < n_cliques; ++cr) {
     const uint32_t w = ev.sh.clq[cr].w;
     const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
@@ -930,12 +923,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     if (warp != 0) return;
     CoopEv ev(tp, rb, sh, g, lane);
     const bool ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
-    uint32_t n_min = 0, min_score = tp.L + 1;
+    uint32_t n_min = 0;
     if (ok) {
       n_min = ev.np;
-      for (uint32_t i = lane; i < n_min; i += 32) min_score = min(min_score, uint32_t(sh.ent_meta[i] >> 8));
-#pragma unroll
-      for (int d = 16; d; d >>= 1) min_score = min(min_score, __shfl_xor_sync(kFull, min_score, d));
       for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
         const uint32_t w = sh.clq[cr].w;
         const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
@@ -949,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     if (lane == 0) {
       rb.nalt[gi] = ok ? 1u : 0u;
       rb.alt_n[size_t(gi) * K] = ok ? ev.np : 0u;
-      rb.alt_score[size_t(gi) * K] = min_score;
+      rb.alt_nmin[size_t(gi) * K] = n_min;
       rb.alt_top[size_t(gi) * K] = 0u;
     }
     return;
@@ -1017,12 +1007,12 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
         if (ok) { if (w < (slot >> 5)) srank += __popc(m); else if (w == (slot >> 5)) srank += __popc(m & ((1u << (slot & 31)) - 1u)); }
       }
       if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
-        uint32_t n_min, min_score;
-        finish_gang(ev, gg.n_cliques, n_min, min_score);
+        uint32_t n_min;
+        finish_gang(ev, gg.n_cliques, n_min);
         const size_t o = size_t(srank) * P + info.pod_off;
         for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
-        rb.alt_score[size_t(gi) * K + srank] = min_score;
+        rb.alt_nmin[size_t(gi) * K + srank] = n_min;
         rb.alt_top[size_t(gi) * K + srank] = dl;
         if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
       }
@@ -1113,12 +1103,12 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       const uint32_t sb = __ballot_sync(kFull, ok);
       const uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u));
       if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
-        uint32_t n_min, min_score;
-        finish_gang(ev, gg.n_cliques, n_min, min_score);
+        uint32_t n_min;
+        finish_gang(ev, gg.n_cliques, n_min);
         const size_t o = size_t(srank) * P + info.pod_off;
         for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
-        rb.alt_score[size_t(gi) * K + srank] = min_score;
+        rb.alt_nmin[size_t(gi) * K + srank] = n_min;
         rb.alt_top[size_t(gi) * K + srank] = dl;
         if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
       }
@@ -1127,6 +1117,36 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
     }
   }
   if (lane == 0) rb.nalt[gi] = min(nsucc, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scores of the alternatives.  The score matrix (K2) and the admission (K3) only share the fit data, so
+// they run concurrently on two streams (K2 is HBM-write-bound, K3 is latency-bound: they overlap almost
+// perfectly); this kernel joins them: one warp per (active gang, alternative) looks up T[clique row][node]
+// for every entry, stores it next to the entry and reduces the minimum over the MinReplicas entries --
+// the PlacementScore numerator (podgang.go:187-189).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_alt_scores(Topo tp, Tables tb, RoundBufs rb) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t K = rb.K, P = rb.P;
+  const uint32_t ai = w / K, a = w - ai * K;
+  if (ai >= rb.counters[0]) return;
+  const uint32_t g = rb.active[ai];
+  if (a >= rb.nalt[g]) return;
+  const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
+  const uint32_t cnt = rb.alt_n[size_t(g) * K + a], nmin = rb.alt_nmin[size_t(g) * K + a];
+  uint32_t mn = tp.L + 1;
+  for (uint32_t i = lane; i < cnt; i += 32) {
+    const size_t o = size_t(a) * P + po + i;
+    const uint32_t cr = rb.alt_meta[o] & 0xFFu;
+    const uint32_t sc = rb.T[size_t(coff + cr) * tp.npad + rb.alt_node[o]];
+    rb.alt_meta[o] = cr | (sc << 8);
+    if (i < nmin) mn = min(mn, sc);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) mn = min(mn, __shfl_xor_sync(kFull, mn, d));
+  if (lane == 0) rb.alt_score[size_t(g) * K + a] = mn;
 }
 
 // ------------------------------------------------------------------------------------------------
