@@ -246,3 +246,40 @@ def test_other_admit_paths_match_too(built_lib, oracle, env):
     ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, **env})
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_edge_cases(built_lib, oracle):
+    """empty submission, single node, everything gated, MinReplicas = 0 everywhere, API misuse"""
+    from grove_b200.engine import GroveError, PlacementEngine
+    nodes = synth.e2e_cluster(5)
+    with PlacementEngine(4) as e:
+        with pytest.raises(GroveError):
+            e.run_cycle()                      # nothing loaded yet
+        e.load_nodes(nodes)
+        with pytest.raises(GroveError):
+            e.run_cycle()                      # no gangs submitted
+        g, c, s = T.GangTableBuilder().build()
+        e.submit_gangs(g, c, s)                # empty submission is a valid (no-op) cycle
+        st = e.run_cycle()
+        assert st["rounds"] == 0 and st["gangs_admitted"] == 0 and len(e.placements()) == 0
+        b = T.GangTableBuilder()
+        b.add_gang([(None, [dict(mem=80, min=1, class_mask=synth.AGENT)])], gated=True)
+        b.add_gang([(None, [dict(mem=80, min=0, replicas=0, class_mask=synth.AGENT)])])
+        b.add_gang([(None, [dict(mem=80, min=0, replicas=3, class_mask=synth.AGENT)])], level=2)
+        g, c, s = b.build()
+        e.submit_gangs(g, c, s)
+        e.run_cycle()
+        ref = oracle.run_cycle(nodes, 4, g, c, s)
+        assert np.array_equal(e.gang_status(), ref["status"]) and np.array_equal(e.placements(), ref["placements"])
+        assert ref["status"]["state"].tolist() == [T.GANG_GATED_SKIP, T.GANG_ADMITTED, T.GANG_ADMITTED]
+        bad = g.copy(); bad["level"][2] = 9
+        with pytest.raises(GroveError):
+            e.submit_gangs(bad, c, s)
+        with pytest.raises(GroveError):
+            e.update_nodes(np.array([99], dtype=np.uint32), nodes[:1])
+    one = synth.e2e_cluster(1)
+    b = T.GangTableBuilder(); b.add_gang([(None, [dict(mem=80, min=1, class_mask=synth.AGENT)])], level=3)
+    g, c, s = b.build()
+    with PlacementEngine(4) as e:
+        e.load_nodes(one); e.submit_gangs(g, c, s); e.run_cycle()
+        assert e.gang_status()["state"][0] == T.GANG_ADMITTED and e.placements()["node"][0] == 0
