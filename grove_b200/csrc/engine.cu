@@ -653,6 +653,7 @@ static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P
 static int32_t round_eval(grove_engine* e, bool timed) {
   const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
   e->round_no++;
+  if (e->G == 0) { std::memset(e->h_counters.p, 0, sizeof(uint32_t) * 8); return GROVE_OK; }  // empty submission: nothing to launch
   CU_TRY(e, cudaMemsetAsync(e->d_counters.p, 0, sizeof(uint32_t) * 8, e->stream));
   k_prepare<<<(e->G + 1023) / 1024, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
   CU_TRY(e, cudaGetLastError());
