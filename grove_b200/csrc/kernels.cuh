@@ -1168,6 +1168,81 @@ __global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs r
   const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
   const uint32_t K = rb.K, P = rb.P;
   const volatile uint32_t* vflags = rb.flags;
+  if (na <= nw) {
+    // Fast path (the usual one: the grid is sized for it): a warp owns at most ONE gang for the whole round,
+    // so its constants and the nodes of its current alternative stay in registers and every phase is one
+    // level of look-ups (taken / claim) instead of a chain of six.
+    const bool have = gw < na;
+    uint32_t g = 0, nalt = 0, po = 0, order0 = 0, c = 0, cnt = 0;
+    uint32_t nd[4] = {GROVE_NONE_U32, GROVE_NONE_U32, GROVE_NONE_U32, GROVE_NONE_U32};
+    bool pending = false;
+    auto load_alt = [&]() {
+      cnt = rb.alt_n[size_t(g) * K + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const uint32_t i = lane + 32u * j; nd[j] = i < cnt ? rb.alt_node[size_t(c) * P + po + i] : GROVE_NONE_U32; }
+    };
+    if (have) {
+      g = rb.active_all[gw];
+      nalt = rb.nalt[g]; po = tb.ginfo[g].pod_off; order0 = tb.ginfo[g].order;
+      pending = nalt > 0;
+      if (!pending && lane == 0) { rb.state[g] = GROVE_GANG_REJECTED; rb.round[g] = r8; }
+      if (pending) load_alt();
+    }
+    for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
+      const uint32_t order = order0 | ((GROVE_SUBROUNDS - 1u - sub) << 24);
+      bool proposed = false;
+      if (pending) {
+        while (c < nalt) {  // first alternative that touches no node committed earlier in this round
+          bool hit = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) hit |= __ldcg(rb.taken + nd[j]) != 0;
+          if (!__any_sync(kFull, hit)) break;
+          if (++c < nalt) load_alt();
+        }
+        if (c < nalt) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) atomicMin(rb.claim + nd[j], order);
+          if (lane == 0) rb.flags[sub] = 1u;
+          proposed = true;
+        } else {
+          pending = false;  // nothing left to propose: re-evaluated next round
+        }
+      }
+      grid.sync();
+      if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
+      if (proposed) {
+        bool win = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) win &= __ldcg(rb.claim + nd[j]) == order;
+        if (__all_sync(kFull, win)) {
+          const uint32_t coff = tb.gangs[g].clique_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (nd[j] == GROVE_NONE_U32) continue;
+            const uint32_t i = lane + 32u * j;
+            const uint32_t meta = rb.alt_meta[size_t(c) * P + po + i];
+            const grove_clique_t q = tb.cliques[coff + (meta & 0xFFu)];
+            uint32_t* r = reinterpret_cast<uint32_t*>(nres + nd[j]);
+            // winners own their nodes exclusively in a sub-round; atomics only order this gang's own pods
+            if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
+            if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
+            atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
+            rb.taken[nd[j]] = 1;
+            rb.ent_node[po + i] = nd[j]; rb.ent_meta[po + i] = uint16_t(meta);
+          }
+          if (lane == 0) {
+            rb.spec_n[g] = uint16_t(cnt); rb.spec_score[g] = uint8_t(rb.alt_score[size_t(g) * K + c]);
+            rb.spec_top[g] = rb.alt_top[size_t(g) * K + c];
+            rb.state[g] = GROVE_GANG_ADMITTED; rb.round[g] = r8;
+          }
+          pending = false;
+        }
+      }
+      grid.sync();
+    }
+    return;
+  }
+  // generic path: more gangs than warps
   for (uint32_t ai = gw; ai < na; ai += nw) {
     const uint32_t g = rb.active_all[ai];
     if (lane == 0) {
