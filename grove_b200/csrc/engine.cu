@@ -121,6 +121,9 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
   uint32_t tune_width0 = 24;  // packing attempts per window in the warp-per-gang kernel
+  // admission kernel form by number of active gangs: >= 10 per SM a warp per gang (gangs in flight matter),
+  // >= 4 per SM a 4-warp CTA per gang, below that an 8-warp CTA per gang (latency of one gang matters)
+  uint32_t tune_warp_min = 1480, tune_wide_max = 592;
   bool tune_overlap = true;      // K2 on a second stream beside K3 (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
   uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
@@ -297,8 +300,12 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resolve_blocks_per_sm, k_resolve, 256, 0);
   if (e->resolve_blocks_per_sm < 1) e->resolve_blocks_per_sm = 1;
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
+  e->tune_warp_min = 10 * e->n_sm; e->tune_wide_max = 4 * e->n_sm;
+  if (const char* v = std::getenv("GROVE_TUNE_WARP_MIN")) e->tune_warp_min = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_WIDE_MAX")) e->tune_wide_max = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
+
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
@@ -688,14 +695,19 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
   const bool small = e->max_gang_pods <= kEntSmem;  // per-lane entry stacks fit the shared-memory form
   if (e->n_constrained) {
-    if (na >= 148u * 4u) {  // throughput round: a warp per gang
+    if (na >= e->tune_warp_min) {  // throughput round: a warp per gang
       const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
       const int th = kAdmitWarpGangs * 32;
       if (caps && small) k_admit_warp<true, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
       else if (caps) k_admit_warp<true, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
       else if (small) k_admit_warp<false, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
       else k_admit_warp<false, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-    } else {                // latency round: a CTA per gang
+    } else if (na >= e->tune_wide_max) {  // middle: a 4-warp CTA per gang
+      if (caps && small) k_admit<kAdmitThreads, 0, kEntSmem><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit<kAdmitThreads, 0, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit<kAdmitThreads, 1, kEntSmem><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else k_admit<kAdmitThreads, 1, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+    } else {                // latency round: an 8-warp CTA per gang
       if (caps && small) k_admit<kAdmitThreadsWide, 0, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
       else if (caps) k_admit<kAdmitThreadsWide, 0, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
       else if (small) k_admit<kAdmitThreadsWide, 1, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
