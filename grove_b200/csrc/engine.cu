@@ -88,8 +88,10 @@ struct grove_engine {
   std::vector<grove_gang_t> gangs;
   std::vector<grove_clique_t> cliques;
   std::vector<grove_scope_t> scopes;
-  std::vector<GangInfo> ginfo;
-  std::vector<CliqueInfo> cinfo;
+  PinBuf<GangInfo> ginfo_pin;      // derived tables are built straight into pinned memory: their upload is a plain DMA
+  PinBuf<CliqueInfo> cinfo_pin;
+  GangInfo* ginfo = nullptr;
+  CliqueInfo* cinfo = nullptr;
   std::vector<uint4> sigs;
   uint32_t n_sigs = 0;
   bool gangs_loaded = false, ginfo_dirty = true;
@@ -411,39 +413,56 @@ int32_t grove_get_nodes(grove_engine_t* e, grove_node_t* out, uint32_t cap) {
   return GROVE_OK;
 }
 
+// one gang; returns nullptr when it is well formed, else the reason (code through *code)
+static const char* validate_gang(const grove_engine* e, const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                                 const grove_scope_t* scopes, uint32_t S, uint32_t gi, int32_t* code) {
+  const uint32_t L = e->L;
+  const grove_gang_t& g = gangs[gi];
+  *code = GROVE_ERR_LIMIT;
+  if (g.n_cliques == 0 || g.n_cliques > GROVE_MAX_GANG_CLIQUES) return "gang clique count out of range";
+  if (g.n_scopes == 0 || g.n_scopes > GROVE_MAX_GANG_SCOPES) return "gang scope count out of range";
+  *code = GROVE_ERR_INVALID_ARG;
+  if (uint64_t(g.clique_off) + g.n_cliques > Q || uint64_t(g.scope_off) + g.n_scopes > S) return "gang table offsets out of range";
+  if (g.level != GROVE_LEVEL_NONE && g.level >= L) return "gang level out of range";
+  if (g.preferred != GROVE_LEVEL_NONE) return "preferred level is reserved";
+  if (g.anchor_node != GROVE_NONE_U32 && e->nodes_loaded && g.anchor_node >= e->N) return "anchor node out of range";
+  if (g.base_gang != GROVE_NONE_U32 && (g.base_gang >= G || g.base_gang == gi)) return "base gang out of range";
+  uint32_t pods = 0, next = 0;
+  for (uint32_t si = 0; si < g.n_scopes; ++si) {
+    const grove_scope_t& s = scopes[g.scope_off + si];
+    if (s.first_clique != next || s.n_cliques == 0) return "scopes must tile the gang's cliques in order";
+    if (s.level != GROVE_LEVEL_NONE && s.level >= L) return "scope level out of range";
+    if (next + s.n_cliques > g.n_cliques) return "scope exceeds gang";
+    for (uint32_t i = 0; i < s.n_cliques; ++i) {
+      const grove_clique_t& q = cliques[g.clique_off + next + i];
+      if (q.scope != si) return "clique.scope does not match its scope";
+      if (q.level != GROVE_LEVEL_NONE && q.level >= L) return "clique level out of range";
+      if (q.replicas < q.min_replicas) return "replicas < min_replicas";
+      pods += q.replicas;
+    }
+    next += s.n_cliques;
+  }
+  if (next != g.n_cliques) return "scopes do not cover the gang";
+  if (pods > GROVE_MAX_GANG_PODS) { *code = GROVE_ERR_LIMIT; return "gang exceeds GROVE_MAX_GANG_PODS"; }
+  return nullptr;
+}
+
 // same structural rules as the PodGang admission webhook guarantees
-// (operator/internal/webhook/admission/pcs/validation/topologyconstraints.go:195-280)
+// (operator/internal/webhook/admission/pcs/validation/topologyconstraints.go:195-280); the first offending gang
+// (lowest index) is reported whatever the thread count
 static int32_t validate(grove_engine* e, const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
                         const grove_scope_t* scopes, uint32_t S) {
-  const uint32_t L = e->L;
+  uint32_t first_bad = GROVE_NONE_U32;
+  const int T = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+#pragma omp parallel for num_threads(T) schedule(static) reduction(min : first_bad)
   for (uint32_t gi = 0; gi < G; ++gi) {
-    const grove_gang_t& g = gangs[gi];
-    if (g.n_cliques == 0 || g.n_cliques > GROVE_MAX_GANG_CLIQUES) return fail(e, GROVE_ERR_LIMIT, "gang clique count out of range");
-    if (g.n_scopes == 0 || g.n_scopes > GROVE_MAX_GANG_SCOPES) return fail(e, GROVE_ERR_LIMIT, "gang scope count out of range");
-    if (uint64_t(g.clique_off) + g.n_cliques > Q || uint64_t(g.scope_off) + g.n_scopes > S) return fail(e, GROVE_ERR_INVALID_ARG, "gang table offsets out of range");
-    if (g.level != GROVE_LEVEL_NONE && g.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "gang level out of range");
-    if (g.preferred != GROVE_LEVEL_NONE) return fail(e, GROVE_ERR_INVALID_ARG, "preferred level is reserved");
-    if (g.anchor_node != GROVE_NONE_U32 && e->nodes_loaded && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
-    if (g.base_gang != GROVE_NONE_U32 && (g.base_gang >= G || g.base_gang == gi)) return fail(e, GROVE_ERR_INVALID_ARG, "base gang out of range");
-    uint32_t pods = 0, next = 0;
-    for (uint32_t si = 0; si < g.n_scopes; ++si) {
-      const grove_scope_t& s = scopes[g.scope_off + si];
-      if (s.first_clique != next || s.n_cliques == 0) return fail(e, GROVE_ERR_INVALID_ARG, "scopes must tile the gang's cliques in order");
-      if (s.level != GROVE_LEVEL_NONE && s.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "scope level out of range");
-      if (next + s.n_cliques > g.n_cliques) return fail(e, GROVE_ERR_INVALID_ARG, "scope exceeds gang");
-      for (uint32_t i = 0; i < s.n_cliques; ++i) {
-        const grove_clique_t& q = cliques[g.clique_off + next + i];
-        if (q.scope != si) return fail(e, GROVE_ERR_INVALID_ARG, "clique.scope does not match its scope");
-        if (q.level != GROVE_LEVEL_NONE && q.level >= L) return fail(e, GROVE_ERR_INVALID_ARG, "clique level out of range");
-        if (q.replicas < q.min_replicas) return fail(e, GROVE_ERR_INVALID_ARG, "replicas < min_replicas");
-        pods += q.replicas;
-      }
-      next += s.n_cliques;
-    }
-    if (next != g.n_cliques) return fail(e, GROVE_ERR_INVALID_ARG, "scopes do not cover the gang");
-    if (pods > GROVE_MAX_GANG_PODS) return fail(e, GROVE_ERR_LIMIT, "gang exceeds GROVE_MAX_GANG_PODS");
+    int32_t code;
+    if (gi < first_bad && validate_gang(e, gangs, G, cliques, Q, scopes, S, gi, &code)) first_bad = gi;
   }
-  return GROVE_OK;
+  if (first_bad == GROVE_NONE_U32) return GROVE_OK;
+  int32_t code = GROVE_ERR_INVALID_ARG;
+  const char* why = validate_gang(e, gangs, G, cliques, Q, scopes, S, first_bad, &code);
+  return fail(e, code, why ? why : "malformed gang tables");
 }
 
 int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_t n_gangs, const grove_clique_t* cliques,
@@ -473,8 +492,10 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
 static int32_t build_ginfo(grove_engine* e) {
   const uint32_t G = e->G, Q = e->Q;
   const auto t_b0 = std::chrono::steady_clock::now();
-  e->ginfo.assign(G, GangInfo{});
-  e->cinfo.assign(Q, CliqueInfo{GROVE_NONE_U32, 0, 0, 0});
+  CU_TRY(e, e->ginfo_pin.ensure(G)); CU_TRY(e, e->cinfo_pin.ensure(Q));
+  e->ginfo = e->ginfo_pin.p; e->cinfo = e->cinfo_pin.p;
+  std::memset(e->ginfo, 0, sizeof(GangInfo) * G);
+  std::memset(e->cinfo, 0xFF, sizeof(CliqueInfo) * Q);  // gang == NONE marks a row no gang owns yet
   e->sigs.clear();
   // order rank = position by (priority desc, index asc): a stable bucket pass over the distinct priorities
   std::vector<uint32_t> ord(G);
@@ -591,11 +612,11 @@ static int32_t build_ginfo(grove_engine* e) {
   CU_TRY(e, e->d_sig_stamp.ensure(e->n_sigs)); CU_TRY(e, e->d_sig_list.ensure(e->n_sigs));
   if (e->n_sigs) CU_TRY(e, cudaMemcpyAsync(e->d_sigs.p, e->sigs.data(), sizeof(uint4) * e->n_sigs, cudaMemcpyHostToDevice, e->stream));
   if (G) {
-    CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo.data(), sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo, sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
     k_anchor<<<(G + 255) / 256, 256, 0, e->stream>>>(make_topo(e), e->d_ginfo.p, G);  // ancestor ranges from the device-resident tree
     CU_TRY(e, cudaGetLastError());
   }
-  if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo.data(), sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
+  if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo, sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
   e->ginfo_dirty = false;
   if (std::getenv("GROVE_DEBUG_HOST")) {
     const auto t_b2 = std::chrono::steady_clock::now();
