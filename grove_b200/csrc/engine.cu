@@ -141,6 +141,7 @@ struct grove_engine {
   // stepping state (multi-GPU)
   uint32_t round_no = 0;
   bool in_cycle = false;
+  bool stream_ordered = false;  // stepping calls return without the trailing host sync
   uint64_t pairs = 0, launches = 0;
 };
 
@@ -880,7 +881,7 @@ int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, u
   if (rc) return rc;
   rc = after_prepare(e, go);
   if (rc) return rc;
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (!e->stream_ordered) CU_TRY(e, cudaStreamSynchronize(e->stream));
   return GROVE_OK;
 }
 
@@ -890,7 +891,7 @@ int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining) {
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   int32_t rc = round_resolve(e, false);
   if (rc) return rc;
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (!e->stream_ordered) CU_TRY(e, cudaStreamSynchronize(e->stream));
   if (remaining) *remaining = e->h_counters.p[2];  // unresolved before this round's commits (upper bound)
   return GROVE_OK;
 }
@@ -900,6 +901,18 @@ int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   return finish_cycle(e, stats);
+}
+
+int32_t grove_engine_stream(grove_engine_t* e, void** stream) {
+  if (!e || !stream) return GROVE_ERR_INVALID_ARG;
+  *stream = e->stream;
+  return GROVE_OK;
+}
+
+int32_t grove_set_stream_ordered(grove_engine_t* e, int32_t on) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  e->stream_ordered = on != 0;
+  return GROVE_OK;
 }
 
 // ---- introspection for parity tests ----

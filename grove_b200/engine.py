@@ -24,7 +24,7 @@ SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_load_nodes_device", "grove_cycle_begin",
-    "grove_round_eval", "grove_round_resolve", "grove_cycle_end",
+    "grove_round_eval", "grove_round_resolve", "grove_cycle_end", "grove_engine_stream", "grove_set_stream_ordered",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -137,6 +137,15 @@ class PlacementEngine:
         p, n, go = C.c_void_p(), C.c_uint32(0), C.c_uint32(0)
         self._check(self.lib.grove_round_eval(self.h, C.byref(p), C.byref(n), C.byref(go)))
         return p.value, n.value, bool(go.value)
+
+    def stream(self) -> int:
+        """cudaStream_t of the engine (as an integer), e.g. for torch.cuda.ExternalStream"""
+        p = C.c_void_p()
+        self._check(self.lib.grove_engine_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def set_stream_ordered(self, on: bool):
+        self._check(self.lib.grove_set_stream_ordered(self.h, C.c_int32(1 if on else 0)))
 
     def round_resolve(self) -> int:
         r = C.c_uint32(0)

@@ -209,6 +209,12 @@ int32_t grove_cycle_begin(grove_engine_t* e);
 int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, uint32_t* go);
 int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining);
 int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats);
+/* The CUDA stream (cudaStream_t) every engine kernel runs on.  A host that enqueues its reduction ON THIS
+ * STREAM (ncclAllReduce(..., stream), or torch.cuda.ExternalStream) may switch the stepping calls to
+ * stream-ordered completion with grove_set_stream_ordered(e, 1): they then return without waiting for their
+ * kernels, and eval -> all-reduce -> resolve are ordered by the stream alone (no host synchronisation). */
+int32_t grove_engine_stream(grove_engine_t* e, void** stream);
+int32_t grove_set_stream_ordered(grove_engine_t* e, int32_t on);
 
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */
 int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap);
