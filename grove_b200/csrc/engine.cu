@@ -300,7 +300,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (!e) return GROVE_ERR_OOM;
   e->cfg = *cfg; e->L = cfg->n_levels;
   e->K = cfg->alternatives ? cfg->alternatives : GROVE_MAX_ALTERNATIVES;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resolve_blocks_per_sm, k_resolve, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resolve_blocks_per_sm, k_resolve, kResolveThreads, 0);
   if (e->resolve_blocks_per_sm < 1) e->resolve_blocks_per_sm = 1;
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   e->tune_warp_min = 10 * e->n_sm; e->tune_wide_max = 4 * e->n_sm;
@@ -757,10 +757,10 @@ static int32_t round_resolve(grove_engine* e, bool timed) {
   CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));
   CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // claims are sub-round tagged; reset once per round
   uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
-  const uint32_t want = na_all <= 64u ? 1u : (na_all * 32 + 255) / 256;  // few gangs: one CTA, grid barriers are then nearly free
+  const uint32_t want = (na_all * 32 + kResolveThreads - 1) / kResolveThreads;  // a warp per gang
   const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, std::min<uint32_t>(uint32_t(e->resolve_blocks_per_sm), e->tune_resolve_bps) * e->n_sm));
   void* args[] = {&tp, &tb, &rb, &nres, &rn};
-  CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(256), args, 0, e->stream));
+  CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(kResolveThreads), args, 0, e->stream));
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
   e->launches += 1;
   return GROVE_OK;

@@ -1159,7 +1159,9 @@ __global__ void __launch_bounds__(256) k_alt_scores(Topo tp, Tables tb, RoundBuf
 // gang is always handled by the same warp, so its cur/prop bytes need no cross-CTA visibility; taken,
 // claim and flags do and are read with ld.cg / volatile.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
+constexpr int kResolveThreads = 1024;  // few, fat CTAs: the grid barrier is what this kernel waits on
+
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const uint32_t lane = threadIdx.x & 31;
