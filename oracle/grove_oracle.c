@@ -605,12 +605,12 @@ int32_t oracle_shard_eval(oshard_t* h, int32_t* xb, uint32_t* go) {
         uint32_t ndp = need_depth(g, s, q);
         Trow[cr] = malloc(n);
         memset(Frow, 0, sizeof(uint32_t) * words);
-        /* K1: fit bitmap row */
-        for (uint32_t nn = 0; nn < n; ++nn)
-          if (fit(&C->T.nodes[nn], q, ndp)) Frow[nn >> 5] |= 1u << (nn & 31);
-        /* K2: score row = fit ? closeness + 1 : 0 */
-        for (uint32_t nn = 0; nn < n; ++nn)
-          Trow[cr][nn] = ((Frow[nn >> 5] >> (nn & 31)) & 1u) ? (uint8_t)(closeness(&C->T, nn, C->anchor[gi]) + 1) : 0;
+        /* K1: fit bitmap row; K2: score row = fit ? closeness + 1 : 0 (one pass over the node table) */
+        for (uint32_t nn = 0; nn < n; ++nn) {
+          const int f = fit(&C->T.nodes[nn], q, ndp);
+          if (f) Frow[nn >> 5] |= 1u << (nn & 31);
+          Trow[cr][nn] = f ? (uint8_t)(closeness(&C->T, nn, C->anchor[gi]) + 1) : 0;
+        }
         pairs += n;
         if (h->round == 1 && h->out_fit) memcpy(h->out_fit + (size_t)(g->clique_off + cr) * words, Frow, sizeof(uint32_t) * words);
         if (h->round == 1 && h->out_score) memcpy(h->out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
