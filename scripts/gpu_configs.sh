@@ -1,0 +1,8 @@
+# bench lines of the smaller BASELINE.json configs (parity-test cases; recorded for reference)
+mkdir -p gpurun_out
+for c in C1 C2 C3; do
+  python bench.py --config $c --steps 20 --warmup 3 > gpurun_out/bench_$c.json 2>/dev/null
+  python -c "
+import json
+d=json.loads(open('gpurun_out/bench_$c.json').read().strip().splitlines()[-1]); print('$c', round(d['ms_per_step'],3), 'ms', round(d['value']), 'gangs/s e2e', round(d['e2e']['ms_per_step'],3), 'ms rounds', d['config']['rounds'], 'cpu', round(d['cpu_baseline']['value']), d['cpu_baseline']['placements_identical_to_gpu'])"
+done
