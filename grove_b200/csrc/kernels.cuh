@@ -1,1368 +1,20 @@
-// kernels.cuh -- sm_100a kernels of the gang-placement cycle.
+// kernels.cuh -- sm_100a kernels of the gang-placement cycle (umbrella include).
 //
-//   k_fit     K1  node x clique resource-fit bitmap          (Filter; oracle: fit(), grove_oracle.c)
-//   k_score   K2  topology-distance score matrix, u8         (Score;  oracle: closeness())
-//   k_admit   K3  per-gang all-or-nothing admission: first feasible domain in score order, pods
-//                 packed by warp ballot / prefix sums over the fit words
-//   k_claim / k_commit   optimistic conflict resolution between gangs of one round
-//   k_prepare / k_finalize / k_gather / k_scatter   round bookkeeping and table (un)packing
+//   tables.cuh   k_gather / k_scatter / k_update / k_anchor / k_prepare   table (un)packing, round bookkeeping
+//   fit.cuh      k_fit  K1  node x clique-signature resource-fit bitmap   (Filter; oracle: fit())
+//                k_cap8 / k_capsum  per-signature pod capacities and their per-domain sum / max
+//   score.cuh    k_score K2 topology-distance score matrix, u8            (Score;  oracle: closeness())
+//                k_alt_scores       joins the K2 stream with K3: score of every alternative
+//   admit.cuh    k_admit_warp / k_admit  K3  per-gang all-or-nothing admission, K alternatives per gang
+//   resolve.cuh  k_resolve  conflict resolution + commit of one round (cooperative launch);
+//                k_finalize / k_emit  outputs
 //
 // Semantics are DESIGN.md "Placement semantics"; the reference contract they restate is cited in
 // include/grove_place.h.  Integer / compare work only: no tensor cores, no floating point.
 #pragma once
-#include <cooperative_groups.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include "../../include/grove_place.h"
-
-namespace grove {
-
-constexpr uint32_t kFull = 0xFFFFFFFFu;
-constexpr int kMaxPieces = 2 * GROVE_MAX_LEVELS + 3;
-
-struct GangInfo {     // 48 B, built on the host at submit time
-  uint32_t anchor;    // sorted node index
-  uint32_t order;     // rank by (priority desc, index asc)
-  uint32_t pod_off;   // first slot in the entry arrays
-  uint32_t pad;
-  uint32_t anc_lo[GROVE_MAX_LEVELS];  // node range of the anchor's domain per level; [a,a) if label absent
-  uint32_t anc_hi[GROVE_MAX_LEVELS];
-};
-
-struct CliqueInfo {   // 16 B
-  uint32_t gang;
-  uint32_t need_depth;  // labels a candidate node must carry (deepest binding Required level + 1)
-  uint32_t sig;         // fit signature: cliques with identical (requests, class mask, need_depth) share a fit row
-  uint32_t pad;
-};
-
-struct Topo {
-  const uint4* nres;       // [npad] dynamic: free_cpu, free_mem, free_gpu | free_pods << 16, flags | vdepth << 16
-  const uint4* ndom;       // [npad] static: tree-ified domain index per level
-  const uint32_t* dom_lo[GROVE_MAX_LEVELS];
-  const uint32_t* dom_hi[GROVE_MAX_LEVELS];
-  const uint32_t* next_dom[GROVE_MAX_LEVELS];  // [n+1] first level-l domain starting at or after node i
-  uint32_t n_dom[GROVE_MAX_LEVELS];
-  uint32_t unit[GROVE_MAX_LEVELS];             // every domain of the level is a single node
-  uint32_t n, npad, L, words;                  // words = npad / 32 (row stride of the fit bitmap)
-  uint32_t cap_off[GROVE_MAX_LEVELS];          // column offset of level l in a capacity-table row (non-unit levels)
-  uint32_t cap_stride;                         // columns per signature row = sum of n_dom over non-unit levels
-};
-
-struct Tables {
-  const grove_gang_t* gangs;
-  const grove_clique_t* cliques;
-  const grove_scope_t* scopes;
-  const GangInfo* ginfo;
-  const CliqueInfo* cinfo;
-  const uint4* sigs;     // [S] req_cpu, req_mem, req_gpu, class_mask | need_depth << 16
-  uint32_t G, Q, S;
-};
-
-struct RoundBufs {
-  uint8_t* state;        // [G] GROVE_GANG_*
-  uint8_t* round;        // [G]
-  uint32_t* active;      // [G] gangs evaluated this round
-  uint32_t* rows;        // [Q] clique rows evaluated this round
-  uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated [4] n_sigs
-                         // [5] active gangs over all ranks [6] gangs resolved by this round's apply
-  uint32_t* sig_stamp;   // [S] last round in which the signature was active
-  uint32_t* sig_list;    // [S] signatures needed this round
-  uint8_t* spec_score;   // [G]
-  uint16_t* spec_n;      // [G] entries incl. surplus
-  uint32_t* spec_top;    // [G]
-  uint32_t* ent_node;    // [P]
-  uint16_t* ent_meta;    // [P] clique_rel | score << 8
-  uint32_t* active_all;  // [G] active gangs of every rank (replicated decision)
-  uint32_t* claim;       // [n]
-  uint8_t* taken;        // [n] node received a commit in this round
-  uint8_t* cur;          // [G] next alternative a gang will propose
-  uint8_t* prop;         // [G] sub-round (1-based) of the gang's last proposal
-  uint32_t* flags;       // [GROVE_SUBROUNDS] any proposal in sub-round s
-  // exchange buffer of the round (also the all-reduce payload of the sharded cycle), u32 words:
-  uint32_t* alt_node;    // [K][P] entry i of alternative a of gang g at a*P + pod_off[g] + i
-  uint32_t* alt_meta;    // [K][P] clique_rel | score << 8
-  uint32_t* alt_n;       // [G][K] entries incl. surplus
-  uint32_t* alt_score;   // [G][K] min score over the MinReplicas entries (written by k_alt_scores)
-  uint32_t* alt_nmin;    // [G][K] entries of the MinReplicas phase (the rest is best-effort surplus)
-  uint32_t* alt_top;     // [G][K]
-  uint32_t* nalt;        // [G]
-  uint32_t K, P;
-  uint32_t* F;           // [S][words] fit bitmap, one row per signature
-  uint8_t* T;            // [Q][npad]
-  const uint8_t* cap8;   // [S][npad] pods of the signature that fit on the node now (saturating), or null
-  const uint32_t* capsum; // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
-  const uint32_t* capmax; // [S][cap_stride] per-domain max of cap8
-  uint32_t caps_in_attempts;  // 1: the scalar evaluator packs from cap8 bytes, 0: from fit words + node records
-  uint32_t width0;            // candidates attempted in the very first step of a gang (1..32)
-  uint32_t* dbg;              // [G][4] optional: candidates, plausible, attempts, winning candidate
-};
-
-// ------------------------------------------------------------------------------------------------
-// table packing
-// ------------------------------------------------------------------------------------------------
-__global__ void k_gather(const grove_node_t* __restrict__ in, const uint32_t* __restrict__ perm,
-                         const uint8_t* __restrict__ vdepth, uint4* __restrict__ nres, uint32_t n, uint32_t npad) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npad) return;
-  uint4 r = make_uint4(0, 0, 0, 0);
-  if (i < n) {
-    const uint4* p = reinterpret_cast<const uint4*>(in + perm[i]);  // first 16 B of the 32 B record
-    uint4 a = __ldg(p);
-    r.x = a.x; r.y = a.y; r.z = a.z;                                // gpu | pods << 16 is already packed
-    r.w = (a.w & 0xFFFFu) | (uint32_t(vdepth[i]) << 16);
-  }
-  nres[i] = r;
-}
-
-__global__ void k_scatter(grove_node_t* __restrict__ out, const grove_node_t* __restrict__ orig,
-                          const uint32_t* __restrict__ perm, const uint4* __restrict__ nres, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t c = perm[i];
-  grove_node_t nd = orig[c];
-  uint4 r = nres[i];
-  nd.free_cpu_milli = r.x; nd.free_mem_mib = r.y; nd.free_gpu = uint16_t(r.z & 0xFFFFu); nd.free_pods = uint16_t(r.z >> 16);
-  out[c] = nd;
-}
-
-__global__ void k_update(const uint32_t* __restrict__ idx_sorted, const grove_node_t* __restrict__ recs,
-                         const uint8_t* __restrict__ vdepth, uint4* __restrict__ nres, uint32_t m) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  uint32_t s = idx_sorted[i];
-  grove_node_t nd = recs[i];
-  nres[s] = make_uint4(nd.free_cpu_milli, nd.free_mem_mib, uint32_t(nd.free_gpu) | (uint32_t(nd.free_pods) << 16),
-                       (nd.flags & 0xFFFFu) | (uint32_t(vdepth[s]) << 16));
-}
-
-// anchor ancestors: node range of the anchor's domain at every level ([a,a) where its label is absent)
-__global__ void k_anchor(Topo tp, GangInfo* ginfo, uint32_t G) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  const uint32_t a = ginfo[g].anchor;
-  const uint4 dm = tp.ndom[a];
-  const uint32_t d[4] = {dm.x, dm.y, dm.z, dm.w};
-#pragma unroll
-  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
-    uint32_t lo = a, hi = a;
-    if (l < (int)tp.L && d[l] != GROVE_DOM_ABSENT) { lo = tp.dom_lo[l][d[l]]; hi = tp.dom_hi[l][d[l]]; }
-    ginfo[g].anc_lo[l] = lo; ginfo[g].anc_hi[l] = hi;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// round bookkeeping: which gangs are evaluated this round, and their clique rows
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(kFull, v, d);
-    if (lane >= (uint32_t)d) v += t;
-  }
-  return v;
-}
-
-// grid of 1024-thread CTAs over the gangs; counters must be zeroed before the launch.
-// Order inside active[] / rows[] depends on CTA arrival order; no result depends on it.
-__global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint32_t round_no, uint32_t rank, uint32_t world) {
-  __shared__ uint32_t s_warp_a[32], s_warp_r[32];
-  __shared__ uint32_t s_base_a, s_base_r;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
-  const uint32_t g = blockIdx.x * 1024 + tid;
-  uint32_t act = 0, ncl = 0, unres = 0, coff = 0, prop = 0;
-  bool ready = false;
-  if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
-    const grove_gang_t gg = tb.gangs[g];
-    // walk the base chain: a scaled gang is rejected with any rejected / skipped ancestor (transitively),
-    // and is ready once its direct base gang is admitted (pod/syncflow.go:319-358)
-    bool dead = false;
-    uint32_t b = gg.base_gang;
-    for (int hop = 0; hop < 64 && b != GROVE_NONE_U32; ++hop) {
-      const uint8_t bs = rb.state[b];
-      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) { dead = true; break; }
-      if (bs == GROVE_GANG_ADMITTED) break;
-      b = tb.gangs[b].base_gang;
-    }
-    if (dead) {
-      rb.state[g] = GROVE_GANG_BASE_REJECTED; rb.round[g] = r8; prop = 1;
-    } else {
-      unres = 1;
-      ready = gg.base_gang == GROVE_NONE_U32 || rb.state[gg.base_gang] == GROVE_GANG_ADMITTED;
-      if (ready) rb.active_all[atomicAdd(rb.counters + 5, 1u)] = g;
-      const bool mine = world <= 1 || (g % world) == rank;
-      if (ready && mine) { act = 1; ncl = gg.n_cliques; coff = gg.clique_off; }
-    }
-  }
-  const uint32_t ia = warp_incl_scan(act, lane), ir = warp_incl_scan(ncl, lane);
-  const uint32_t un = __popc(__ballot_sync(kFull, unres));
-  const uint32_t pr = __ballot_sync(kFull, prop);
-  if (lane == 31) { s_warp_a[warp] = ia; s_warp_r[warp] = ir; }
-  if (lane == 0) {
-    if (un) atomicAdd(rb.counters + 2, un);
-    if (pr) atomicOr(rb.counters + 3, 1u);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const uint32_t va = s_warp_a[lane], vr = s_warp_r[lane];
-    const uint32_t sa = warp_incl_scan(va, lane), sr = warp_incl_scan(vr, lane);
-    s_warp_a[lane] = sa - va; s_warp_r[lane] = sr - vr;  // exclusive per-warp offsets
-    if (lane == 31) {
-      s_base_a = sa ? atomicAdd(rb.counters + 0, sa) : 0u;
-      s_base_r = sr ? atomicAdd(rb.counters + 1, sr) : 0u;
-    }
-  }
-  __syncthreads();
-  if (act) {
-    const uint32_t oa = s_base_a + s_warp_a[warp] + ia - act;
-    const uint32_t orr = s_base_r + s_warp_r[warp] + ir - ncl;
-    rb.active[oa] = g;
-    for (uint32_t i = 0; i < ncl; ++i) {
-      rb.rows[orr + i] = coff + i;
-      const uint32_t sg = tb.cinfo[coff + i].sig;
-      if (atomicExch(rb.sig_stamp + sg, round_no) != round_no) rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
-    }
-  }
-}
-
-// dependency cycle or unreachable base: nothing can become active any more
-__global__ void k_reject_rest(Tables tb, RoundBufs rb, uint32_t round_no) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < tb.G && rb.state[g] == GROVE_GANG_PENDING) {
-    rb.state[g] = GROVE_GANG_BASE_REJECTED;
-    rb.round[g] = uint8_t(round_no > 255 ? 255 : round_no);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: node x clique resource-fit bitmap.
-// CTA = 1024 nodes (lane = node, record in registers) x a tile of kFitTile clique rows whose
-// requirements are staged in shared memory.  One __ballot_sync per (warp, clique) yields the 32-bit
-// fit word; words are staged in shared memory and written back as full 128-byte lines per row.
-// ------------------------------------------------------------------------------------------------
-constexpr int kFitTile = 128;
-
-__global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) {
-  __shared__ uint4 s_prm[kFitTile];
-  __shared__ uint32_t s_row[kFitTile];
-  __shared__ uint32_t s_out[kFitTile][32];
-  const uint32_t n_rows = rb.counters[4];                 // active signatures
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t node = blockIdx.x * 1024 + tid;           // npad is a multiple of 1024
-  const uint4 r = __ldg(tp.nres + node);
-  const uint32_t gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-  const uint32_t depth = (r.w >> 16) & 0xFu;
-  const uint32_t onehot = ((r.w & GROVE_NODE_SCHEDULABLE) && pods >= 1) ? (1u << ((r.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) : 0u;
-  for (uint32_t r0 = blockIdx.y * kFitTile; r0 < n_rows; r0 += gridDim.y * kFitTile) {
-    __syncthreads();
-    if (tid < kFitTile) {
-      uint4 p = make_uint4(kFull, kFull, kFull, 0);  // never fits
-      uint32_t sg = 0;
-      if (r0 + tid < n_rows) { sg = rb.sig_list[r0 + tid]; p = tb.sigs[sg]; }
-      s_prm[tid] = p; s_row[tid] = sg;
-    }
-    __syncthreads();
-    const int cnt = int(min(uint32_t(kFitTile), n_rows - r0));
-#pragma unroll 4
-    for (int c = 0; c < cnt; ++c) {
-      const uint4 p = s_prm[c];
-      bool ok = (r.x >= p.x) & (r.y >= p.y) & (gpu >= p.z) & ((p.w & onehot) != 0) & (depth >= (p.w >> 16));
-      uint32_t b = __ballot_sync(kFull, ok);
-      if (lane == 0) s_out[c][warp] = b;
-    }
-    __syncthreads();
-    for (int c = warp; c < cnt; c += 32) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Capacity tables for K3's candidate pre-filter (only built while the active signatures are few):
-// cap8[sig][n] = whole pods of the signature that fit on node n (0 if unfit, saturating at 255) and
-// its per-domain sum / max.  "sum over the fill domain >= MinReplicas" is a necessary condition for a
-// clique to be packable there, so domains failing it can be skipped without changing any result.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cap8(Topo tp, Tables tb, RoundBufs rb, uint8_t* cap8) {
-  const uint32_t sg = rb.sig_list[blockIdx.y];
-  const uint32_t n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= tp.npad) return;
-  uint32_t c = 0;
-  if ((__ldg(rb.F + size_t(sg) * tp.words + (n >> 5)) >> (n & 31)) & 1u) {
-    const uint4 r = __ldg(tp.nres + n);
-    const uint4 q = tb.sigs[sg];
-    c = r.z >> 16;
-    if (q.x) c = min(c, r.x / q.x);
-    if (q.y) c = min(c, r.y / q.y);
-    if (q.z) c = min(c, (r.z & 0xFFFFu) / q.z);
-    c = min(c, 255u);
-  }
-  cap8[size_t(sg) * tp.npad + n] = uint8_t(c);
-}
-
-// one warp per (active signature, non-unit domain)
-__global__ void __launch_bounds__(256) k_capsum(Topo tp, RoundBufs rb, const uint8_t* __restrict__ cap8,
-                                                uint32_t* capsum, uint32_t* capmax) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t j = (blockIdx.x * 256 + threadIdx.x) >> 5;   // column in the table row
-  if (j >= tp.cap_stride) return;
-  const uint32_t sg = rb.sig_list[blockIdx.y];
-  uint32_t l = 0;
-#pragma unroll
-  for (uint32_t k = 0; k < GROVE_MAX_LEVELS; ++k)
-    if (k < tp.L && !tp.unit[k] && j >= tp.cap_off[k]) l = k;
-  const uint32_t d = j - tp.cap_off[l];
-  const uint32_t lo = __ldg(tp.dom_lo[l] + d), hi = __ldg(tp.dom_hi[l] + d);
-  const uint8_t* row = cap8 + size_t(sg) * tp.npad;
-  uint32_t sum = 0, mx = 0;
-  for (uint32_t n = lo + lane; n < hi; n += 32) { const uint32_t c = row[n]; sum += c; mx = max(mx, c); }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(kFull, sum, o); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
-  if (lane == 0) { capsum[size_t(sg) * tp.cap_stride + j] = sum; capmax[size_t(sg) * tp.cap_stride + j] = mx; }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: topology-distance score matrix.  T[q][n] = fit ? 1 + #levels at which n shares the anchor's
-// domain : 0.  Nodes are stored in topology order, so the anchor's domains are index ranges and the
-// score is piecewise constant: a thread owns 16 consecutive nodes of one row, expands its 16 fit bits
-// to bytes and writes one 128-bit store; only chunks straddling an ancestor boundary go per byte.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spread4(uint32_t nib) {  // 4 bits -> 4 bytes of 0/1
-  return (nib * 0x00204081u) & 0x01010101u;
-}
-
-__global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb, uint32_t n_rows) {
-  const uint32_t cpr = tp.npad >> 4;  // 16-node chunks per row
-  for (uint32_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
-    const uint32_t q = __ldg(rb.rows + r);
-    const CliqueInfo ci = tb.cinfo[q];
-    const GangInfo* gi = tb.ginfo + ci.gang;
-    const uint4 alo = __ldg(reinterpret_cast<const uint4*>(gi->anc_lo));
-    const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(gi->anc_hi));
-    const uint32_t lo[4] = {alo.x, alo.y, alo.z, alo.w}, hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
-    const uint32_t* Frow = rb.F + size_t(ci.sig) * tp.words;
-    uint8_t* Trow = rb.T + size_t(q) * tp.npad;
-    for (uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch < cpr; ch += gridDim.x * blockDim.x) {
-      const uint32_t n0 = ch << 4;
-      const uint32_t bits = (__ldg(Frow + (n0 >> 5)) >> (n0 & 16)) & 0xFFFFu;
-      uint4 out = make_uint4(0, 0, 0, 0);
-      if (bits) {
-        uint32_t inside = 0; bool uniform = true;
-#pragma unroll
-        for (int l = 0; l < GROVE_MAX_LEVELS; ++l) {
-          if (l < (int)tp.L) {
-            bool in = n0 >= lo[l] && n0 + 16 <= hi[l];
-            bool outl = n0 + 16 <= lo[l] || n0 >= hi[l];
-            inside += in; uniform &= (in | outl);
-          }
-        }
-        if (uniform) {
-          const uint32_t v = inside + 1;
-          out.x = spread4(bits & 0xF) * v; out.y = spread4((bits >> 4) & 0xF) * v;
-          out.z = spread4((bits >> 8) & 0xF) * v; out.w = spread4(bits >> 12) * v;
-        } else {
-          uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if ((bits >> j) & 1u) {
-              uint32_t n = n0 + j, c = 1;
-#pragma unroll
-              for (int l = 0; l < GROVE_MAX_LEVELS; ++l) c += (l < (int)tp.L && n >= lo[l] && n < hi[l]);
-              w[j >> 2] |= c << ((j & 3) * 8);
-            }
-          }
-          out = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-      *reinterpret_cast<uint4*>(Trow + n0) = out;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: gang admission.  One CTA (4 warps) per active gang.
-//
-// A gang with a Required level tries the domains of that level in score order and takes the first
-// one in which every PodClique's MinReplicas can be packed (all-or-nothing).  Candidate domains are
-// independent of each other, so they are evaluated in parallel: one LANE per candidate domain runs
-// the greedy packing as scalar code (ScalarEv), the warp ballots the outcomes and the first feasible
-// candidate in order wins.  Step 0 uses warp 0 only (32 candidates, the common case succeeds on the
-// first); further steps use all 128 lanes.  A gang without a gang-level constraint has a single
-// candidate (the whole cluster): warp 0 packs it cooperatively (CoopEv), lanes = nodes of a fit
-// word, prefix sums over the per-node capacities.
-// Both evaluators implement the same DESIGN.md semantics and are checked against the oracle.
-// ------------------------------------------------------------------------------------------------
-struct GangRegs {   // per-gang constants
-  uint32_t a, L, n;
-  uint32_t anc_lo[GROVE_MAX_LEVELS], anc_hi[GROVE_MAX_LEVELS];
-  uint32_t clique_off;
-};
-
-struct GangShared {
-  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
-  grove_scope_t scopes[GROVE_MAX_GANG_SCOPES];
-  uint32_t sig[GROVE_MAX_GANG_CLIQUES];    // fit-bitmap row of each clique
-  // cooperative evaluator state (warp 0)
-  uint32_t ent_node[GROVE_MAX_GANG_PODS];
-  uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel | score << 8
-  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
-};
-
-// Ordered pieces of [lo,hi): descending score, ties by ascending rotated index (n - anchor) mod N.
-// from == L: node granularity (ring l = anc_l \ anc_{l+1}, upper part then lower part);
-// from <  L: level-`from` domain granularity (the anchor's own domain whole, then the rings).
-__device__ __forceinline__ int make_pieces(const GangRegs& g, uint32_t lo, uint32_t hi, uint32_t from,
-                                           uint32_t* plo, uint32_t* phi) {
-  int k = 0;
-  if (g.a < lo || g.a >= hi) { plo[0] = lo; phi[0] = hi; return hi > lo ? 1 : 0; }
-  uint32_t prev_lo = g.a, prev_hi = g.a;
-  if (from < g.L) {
-    prev_lo = max(g.anc_lo[from], lo); prev_hi = min(g.anc_hi[from], hi);
-    if (prev_hi > prev_lo) { plo[k] = prev_lo; phi[k] = prev_hi; ++k; }
-  }
-  for (int l = int(min(from, g.L)) - 1; l >= 0; --l) {
-    uint32_t cl = max(g.anc_lo[l], lo), ch = min(g.anc_hi[l], hi);
-    if (ch > prev_hi) { plo[k] = prev_hi; phi[k] = ch; ++k; }
-    if (prev_lo > cl) { plo[k] = cl; phi[k] = prev_lo; ++k; }
-    prev_lo = min(cl, prev_lo); prev_hi = max(ch, prev_hi);
-  }
-  if (hi > prev_hi) { plo[k] = prev_hi; phi[k] = hi; ++k; }
-  if (prev_lo > lo) { plo[k] = lo; phi[k] = prev_lo; ++k; }
-  return k;
-}
-
-// The same ordered pieces as make_pieces, produced one at a time from a few registers (no per-thread
-// arrays: the scalar evaluator runs one attempt per LANE and every local-memory word costs a cache line
-// per warp).
-struct PieceIt {
-  uint32_t lo, hi, prev_lo, prev_hi, first_lo, first_hi;
-  int l, stage;  // stage: 0 first piece pending, 1 rings (upper), 2 rings (lower), 3 tail upper, 4 tail lower, 5 done
-  bool outside;
-  __device__ __forceinline__ void init(const GangRegs& g, uint32_t lo_, uint32_t hi_, uint32_t from) {
-    lo = lo_; hi = hi_;
-    outside = g.a < lo || g.a >= hi;
-    stage = 0; prev_lo = g.a; prev_hi = g.a; first_lo = first_hi = 0;
-    l = int(min(from, g.L)) - 1;
-    if (!outside && from < g.L) {
-      first_lo = max(g.anc_lo[from], lo); first_hi = min(g.anc_hi[from], hi);
-      prev_lo = first_lo; prev_hi = first_hi;
-    }
-  }
-  __device__ __forceinline__ bool next(const GangRegs& g, uint32_t& a, uint32_t& b) {
-    if (outside) { if (stage == 0 && hi > lo) { stage = 5; a = lo; b = hi; return true; } return false; }
-    if (stage == 0) { stage = 1; if (first_hi > first_lo) { a = first_lo; b = first_hi; return true; } }
-    while (stage == 1 || stage == 2) {
-      if (l < 0) { stage = 3; break; }
-      const uint32_t cl = max(g.anc_lo[l], lo), ch = min(g.anc_hi[l], hi);
-      if (stage == 1) { stage = 2; if (ch > prev_hi) { a = prev_hi; b = ch; return true; } }
-      // stage 2: lower part of ring l, then move one level out
-      const uint32_t pl = prev_lo;
-      prev_lo = min(cl, prev_lo); prev_hi = max(ch, prev_hi);
-      --l; stage = 1;
-      if (pl > cl) { a = cl; b = pl; return true; }
-    }
-    if (stage == 3) { stage = 4; if (hi > prev_hi) { a = prev_hi; b = hi; return true; } }
-    if (stage == 4) { stage = 5; if (prev_lo > lo) { a = lo; b = prev_lo; return true; } }
-    return false;
-  }
-};
-
-__device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_t gpu, uint32_t pods, const uint4& q) {
-  uint32_t c = pods;
-  if (q.x) c = min(c, cpu / q.x);
-  if (q.y) c = min(c, mem / q.y);
-  if (q.z) c = min(c, gpu / q.z);
-  return c;
-}
-
-// ---- cooperative evaluator: the whole warp packs ONE candidate range -----------------------------
-struct CoopEv {
-  const Topo& tp; const RoundBufs& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
-  uint32_t np;
-  uint32_t tmask = 0;
-  __device__ __forceinline__ bool moot() const { return false; }
-  __device__ CoopEv(const Topo& t, const RoundBufs& r, GangShared& s, const GangRegs& gr, uint32_t ln)
-      : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
-
-  __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
-    const uint4 r = __ldg(tp.nres + n);
-    uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-    for (uint32_t i = 0; i < np; ++i) {
-      if (sh.ent_node[i] == n) {
-        const uint4 o = sh.clq[sh.ent_meta[i] & 0xFFu];
-        cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
-      }
-    }
-    return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
-  }
-
-  // up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed
-  __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
-    if (want == 0 || hi <= lo) return 0;
-    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    uint32_t placed = 0;
-    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
-      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-      for (uint32_t wb = w0; wb <= w1 && placed < want; wb += 32) {
-        uint32_t myw = 0;  // 32 fit words at a time, one per lane
-        if (wb + lane <= w1) {
-          myw = __ldg(Frow + wb + lane);
-          if (wb + lane == w0) myw &= kFull << (a & 31);
-          if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
-        }
-        uint32_t nz = __ballot_sync(kFull, myw != 0);
-        while (nz && placed < want) {
-          const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
-          const uint32_t bits = __shfl_sync(kFull, myw, src);
-          const uint32_t n = ((wb + src) << 5) + lane;
-          const bool mine = (bits >> lane) & 1u;
-          const uint32_t c = mine ? cap_now(cr, n) : 0u;
-          const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
-          const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
-          const uint32_t tincl = warp_incl_scan(t, lane);
-          if (t) {
-            const uint16_t meta = uint16_t(cr);
-            const uint32_t pos = np + tincl - t;
-            for (uint32_t j = 0; j < t; ++j) { sh.ent_node[pos + j] = n; sh.ent_meta[pos + j] = meta; }
-          }
-          const uint32_t tot = __shfl_sync(kFull, tincl, 31);
-          np += tot; placed += tot;
-          __syncwarp();
-        }
-      }
-    }
-    return placed;
-  }
-
-  __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
-    const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t mark = np;
-    if (take(cr, lo, hi, m) < m) { np = mark; return false; }
-    if (lane == 0) { sh.Hlo[cr] = lo; sh.Hhi[cr] = hi; }
-    __syncwarp();
-    return true;
-  }
-
-  // clique whose own Required level is a unit level (one node per domain, e.g. hostname):
-  // first node of [lo,hi) in score order that takes all m pods
-  __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
-    const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    for (uint32_t a, b; pit.next(g, a, b);) {
-      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-      for (uint32_t wb = w0; wb <= w1; wb += 32) {
-        uint32_t myw = 0;
-        if (wb + lane <= w1) {
-          myw = __ldg(Frow + wb + lane);
-          if (wb + lane == w0) myw &= kFull << (a & 31);
-          if (wb + lane == w1 && (b & 31)) myw &= (1u << (b & 31)) - 1u;
-        }
-        uint32_t nz = __ballot_sync(kFull, myw != 0);
-        while (nz) {
-          const uint32_t src = __ffs(nz) - 1; nz &= nz - 1;
-          const uint32_t bits = __shfl_sync(kFull, myw, src);
-          const uint32_t n = ((wb + src) << 5) + lane;
-          const bool mine = (bits >> lane) & 1u;
-          const uint32_t c = mine ? cap_now(cr, n) : 0u;
-          const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
-          if (okb) {
-            const uint32_t nn = ((wb + src) << 5) + (__ffs(okb) - 1);
-            const uint16_t meta = uint16_t(cr);
-            for (uint32_t j = lane; j < m; j += 32) { sh.ent_node[np + j] = nn; sh.ent_meta[np + j] = meta; }
-            if (lane == 0) { sh.Hlo[cr] = nn; sh.Hhi[cr] = nn + 1; }
-            np += m;
-            __syncwarp();
-            return true;
-          }
-        }
-      }
-    }
-    return false;
-  }
-};
-
-// ---- scalar evaluator: ONE lane packs one candidate range (lanes of a warp hold different candidates)
-// kEnt > 0: the per-lane entry stack (pods placed so far) lives in shared memory, kEnt entries per lane,
-// laid out [entry][thread] -- per-thread local arrays are what made this kernel thrash L1 (every local
-// word is a 128 B line per warp).  kEnt == 0: local arrays sized for the largest legal gang.
-template <bool kCaps, int kEnt>
-struct ScalarEv {
-  const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
-  uint32_t np;
-  uint32_t tmask;  // bit (n & 31) set for every node this attempt has put a pod on: quick 'untouched' test
-  uint32_t k;   // candidate index of this lane
-  __device__ __forceinline__ bool moot() const { return false; }  // every attempt may become one of the K alternatives
-  uint32_t* sen; uint16_t* sem; uint32_t stride;
-  uint32_t ent_node_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
-  uint16_t ent_meta_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
-  uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];  // written only for cliques with surplus replicas
-  __device__ ScalarEv(const Topo& t, const RoundBufs& r, const GangShared& s, const GangRegs& gr, uint32_t* sen_, uint16_t* sem_, uint32_t stride_)
-      : tp(t), rb(r), sh(s), g(gr), np(0), tmask(0), k(0), sen(sen_), sem(sem_), stride(stride_) {}
-  __device__ __forceinline__ uint32_t& en(uint32_t i) { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
-  __device__ __forceinline__ uint16_t& em(uint32_t i) { if constexpr (kEnt > 0) return sem[i * stride]; else return ent_meta_l[i]; }
-  __device__ __forceinline__ uint32_t en(uint32_t i) const { if constexpr (kEnt > 0) return sen[i * stride]; else return ent_node_l[i]; }
-  __device__ __forceinline__ uint16_t em(uint32_t i) const { if constexpr (kEnt > 0) return sem[i * stride]; else return ent_meta_l[i]; }
-  __device__ __forceinline__ void note_domain(uint32_t cr, uint32_t lo, uint32_t hi) {
-    const uint32_t w = sh.clq[cr].w;
-    if (((w >> 8) & 0xFFu) > (w & 0xFFu)) { Hlo[cr] = lo; Hhi[cr] = hi; }
-  }
-
-  __device__ __forceinline__ uint32_t cap_now(uint32_t cr, uint32_t n) const {
-    const uint4 r = __ldg(tp.nres + n);
-    uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-    for (uint32_t i = 0; i < np; ++i) {
-      if (en(i) == n) {
-        const uint4 o = sh.clq[em(i) & 0xFFu];
-        cpu -= o.x; mem -= o.y; gpu -= o.z; pods -= 1;
-      }
-    }
-    return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
-  }
-
-  // has this gang already put pods on node n?
-  __device__ __forceinline__ bool touched(uint32_t n) const {
-    if (!((tmask >> (n & 31)) & 1u)) return false;
-    for (uint32_t i = 0; i < np; ++i) if (en(i) == n) return true;
-    return false;
-  }
-
-  // 32 capacity bytes [base, base+32) of one signature row as 8 independent word loads; returns the
-  // mask of nodes in [a,b) whose capacity byte is non-zero
-  __device__ __forceinline__ uint32_t load_caps(const uint8_t* row, uint32_t base, uint32_t a, uint32_t b) const {
-    uint32_t mask = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t v = (base + 4u * i < b) ? __ldg(reinterpret_cast<const uint32_t*>(row + base) + i) : 0u;
-      const uint32_t nz = ((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u) >> 7;   // bit 0 of each byte = byte != 0
-      mask |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);                             // gather the 4 flags, byte 0 first
-    }
-    if (a > base) mask &= kFull << (a - base);
-    if (b < base + 32u) mask &= (1u << (b - base)) - 1u;
-    return mask;
-  }
-
-  // capacity-table path: per-node capacities come as bytes (computed once per round for the signature);
-  // only nodes this gang already touched, or saturated bytes, are recomputed from the node record
-  __device__ __forceinline__ uint32_t take_caps(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
-    const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    uint32_t placed = 0;
-    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
-      for (uint32_t base = a & ~3u; base < b && placed < want; base += 32) {
-        uint32_t mask = load_caps(row, base, a, b);
-        while (mask && placed < want) {
-          const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
-          const uint32_t n = base + j;
-          uint32_t c = __ldg(row + n);  // the line was just fetched by load_caps
-          if (c == 255u || touched(n)) c = cap_now(cr, n);
-          const uint32_t t = min(c, want - placed);
-          if (t) {
-            const uint16_t meta = uint16_t(cr);
-            for (uint32_t x = 0; x < t; ++x) { en(np + x) = n; em(np + x) = meta; }
-            tmask |= 1u << (n & 31);
-            np += t; placed += t;
-          }
-        }
-      }
-    }
-    return placed;
-  }
-
-  __device__ __forceinline__ bool find_unit_caps(uint32_t cr, uint32_t lo, uint32_t hi) {
-    const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint8_t* row = rb.cap8 + size_t(sh.sig[cr]) * tp.npad;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    for (uint32_t a, b; pit.next(g, a, b);) {
-      for (uint32_t base = a & ~3u; base < b; base += 32) {
-        uint32_t mask = load_caps(row, base, a, b);
-        while (mask) {
-          const uint32_t j = __ffs(mask) - 1; mask &= mask - 1;
-          const uint32_t n = base + j;
-          uint32_t c = __ldg(row + n);  // the line was just fetched by load_caps
-          if (c < m && c != 255u) continue;   // capacities only shrink inside an attempt
-          if (c == 255u || touched(n)) c = cap_now(cr, n);
-          if (c >= m) {
-            const uint16_t meta = uint16_t(cr);
-            for (uint32_t x = 0; x < m; ++x) { en(np + x) = n; em(np + x) = meta; }
-            tmask |= 1u << (n & 31);
-            np += m; note_domain(cr, n, n + 1);
-            return true;
-          }
-        }
-      }
-    }
-    return false;
-  }
-
-  __device__ __forceinline__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
-    if (want == 0 || hi <= lo) return 0;
-    if constexpr (kCaps) return take_caps(cr, lo, hi, want);
-    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    uint32_t placed = 0;
-    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
-      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-      for (uint32_t w = w0; w <= w1 && placed < want; ++w) {
-        uint32_t bits = __ldg(Frow + w);
-        if (w == w0) bits &= kFull << (a & 31);
-        if (w == w1 && (b & 31)) bits &= (1u << (b & 31)) - 1u;
-        while (bits && placed < want) {
-          const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
-          const uint32_t c = cap_now(cr, n);
-          const uint32_t t = min(c, want - placed);
-          if (t) {
-            const uint16_t meta = uint16_t(cr);
-            for (uint32_t j = 0; j < t; ++j) { en(np + j) = n; em(np + j) = meta; }
-            tmask |= 1u << (n & 31);
-            np += t; placed += t;
-          }
-        }
-      }
-    }
-    return placed;
-  }
-
-  __device__ __forceinline__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
-    const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t mark = np;
-    if (take(cr, lo, hi, m) < m) { np = mark; return false; }
-    note_domain(cr, lo, hi);
-    return true;
-  }
-
-  __device__ __forceinline__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
-    if constexpr (kCaps) return find_unit_caps(cr, lo, hi);
-    const uint32_t m = sh.clq[cr].w & 0xFFu;
-    const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
-    PieceIt pit; pit.init(g, lo, hi, g.L);
-    for (uint32_t a, b; pit.next(g, a, b);) {
-      const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
-      for (uint32_t w = w0; w <= w1; ++w) {
-        uint32_t bits = __ldg(Frow + w);
-        if (w == w0) bits &= kFull << (a & 31);
-        if (w == w1 && (b & 31)) bits &= (1u << (b & 31)) - 1u;
-        while (bits) {
-          const uint32_t n = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1;
-          if (cap_now(cr, n) >= m) {
-            const uint16_t meta = uint16_t(cr);
-            for (uint32_t j = 0; j < m; ++j) { en(np + j) = n; em(np + j) = meta; }
-            tmask |= 1u << (n & 31);
-            np += m; note_domain(cr, n, n + 1);
-            return true;
-          }
-        }
-      }
-    }
-    return false;
-  }
-};
-
-// ---- candidate pre-filter: a NECESSARY condition for place_in(lo, hi) to succeed ------------------
-// (each clique alone must find MinReplicas worth of capacity in a domain it could be packed into, and
-// the cliques of a scope must find it inside one common scope domain).  Reads only the small
-// per-signature capacity tables.
-__device__ __forceinline__ bool clique_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t cr,
-                                 uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
-  const uint32_t w = sh.clq[cr].w;
-  const uint32_t m = w & 0xFFu, ql = (w >> 16) & 0xFFu;
-  if (m == 0) return true;
-  const size_t row = size_t(sh.sig[cr]);
-  const bool tabled = lvl >= 0 && !tp.unit[lvl];
-  if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
-    if (tp.unit[ql]) {  // all m pods on one node
-      if (tabled) return __ldg(rb.capmax + row * tp.cap_stride + tp.cap_off[lvl] + dE) >= m;
-      for (uint32_t n = lo; n < hi; ++n) if (__ldg(rb.cap8 + row * tp.npad + n) >= m) return true;
-      return false;
-    }
-    const uint32_t d0 = __ldg(tp.next_dom[ql] + lo), d1 = __ldg(tp.next_dom[ql] + hi);
-    uint32_t any = 0;  // no early exit: the look-ups are independent and overlap
-    for (uint32_t d = d0; d < d1; ++d) any |= __ldg(rb.capsum + row * tp.cap_stride + tp.cap_off[ql] + d) >= m;
-    return any != 0;
-  }
-  if (tabled) return __ldg(rb.capsum + row * tp.cap_stride + tp.cap_off[lvl] + dE) >= m;
-  uint32_t sum = 0;
-  for (uint32_t n = lo; n < hi && sum < m; ++n) sum += __ldg(rb.cap8 + row * tp.npad + n);
-  return sum >= m;
-}
-
-__device__ __forceinline__ bool scope_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, const grove_scope_t& s,
-                                uint32_t lo, uint32_t hi, int lvl, uint32_t dE) {
-  uint32_t all = 1;
-  for (uint32_t i = 0; i < s.n_cliques; ++i) all &= clique_plausible(tp, rb, sh, s.first_clique + i, lo, hi, lvl, dE);
-  return all != 0;
-}
-
-__device__ bool gang_plausible(const Topo& tp, const RoundBufs& rb, const GangShared& sh, uint32_t n_scopes,
-                               uint32_t lo, uint32_t hi, int lvl, uint32_t dD) {
-  for (uint32_t si = 0; si < n_scopes; ++si) {
-    const grove_scope_t s = sh.scopes[si];
-    bool ok = false;
-    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      const uint32_t d0 = __ldg(tp.next_dom[s.level] + lo), d1 = __ldg(tp.next_dom[s.level] + hi);
-      uint32_t any = 0;  // no early exit: children are independent table look-ups
-      for (uint32_t d = d0; d < d1; ++d)
-        any |= scope_plausible(tp, rb, sh, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), d);
-      ok = any != 0;
-    } else {
-      ok = scope_plausible(tp, rb, sh, s, lo, hi, lvl, dD);
-    }
-    if (!ok) return false;
-  }
-  return true;
-}
-
-template <class Ev>
-__device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
-  const Topo& tp = ev.tp;
-  const uint32_t mark = ev.np;
-  for (uint32_t i = 0; i < s.n_cliques; ++i) {
-    const uint32_t cr = s.first_clique + i;
-    const uint32_t w = ev.sh.clq[cr].w;
-    const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
-    bool ok = false;
-    if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
-      if (tp.unit[ql] && m >= 1) {
-        ok = ev.find_unit(cr, lo, hi);
-      } else {
-        PieceIt pit; pit.init(ev.g, lo, hi, ql);
-        for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
-          const uint32_t d0 = __ldg(tp.next_dom[ql] + pa), d1 = __ldg(tp.next_dom[ql] + pb);
-          for (uint32_t d = d0; d < d1 && !ok; ++d)
-            ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
-        }
-      }
-    } else {
-      ok = ev.fill_min(cr, lo, hi);
-    }
-    if (!ok) { ev.np = mark; return false; }
-  }
-  return true;
-}
-
-template <class Ev>
-__device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
-  const Topo& tp = ev.tp;
-  ev.np = 0; ev.tmask = 0;
-  for (uint32_t si = 0; si < n_scopes; ++si) {
-    const grove_scope_t s = ev.sh.scopes[si];
-    bool ok = false;
-    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      PieceIt pit; pit.init(ev.g, lo, hi, s.level);
-      for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
-        const uint32_t d0 = __ldg(tp.next_dom[s.level] + pa), d1 = __ldg(tp.next_dom[s.level] + pb);
-        for (uint32_t d = d0; d < d1 && !ok; ++d) {
-          if (ev.moot()) { ev.np = 0; return false; }
-          const uint32_t el = __ldg(tp.dom_lo[s.level] + d), eh = __ldg(tp.dom_hi[s.level] + d);
-          // round-start capacities are an upper bound: a scope domain that lacks them cannot be packed
-          if (ev.rb.cap8 && !scope_plausible(tp, ev.rb, ev.sh, s, el, eh, int(s.level), d)) continue;
-          ok = place_scope(ev, s, el, eh, int(s.level));
-        }
-      }
-    } else {
-      ok = place_scope(ev, s, lo, hi, lvl);
-    }
-    if (!ok) { ev.np = 0; return false; }
-  }
-  return true;
-}
-
-// surplus beyond MinReplicas (best effort) of a successful scalar attempt
-template <class Ev>
-__device__ void finish_gang(Ev& ev, uint32_t n_cliques, uint32_t& n_min) {
-  n_min = ev.np;
-  for (uint32_t cr = 0; cr < n_cliques; ++cr) {
-    const uint32_t w = ev.sh.clq[cr].w;
-    const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-    if (rp > mn) ev.take(cr, ev.Hlo[cr], ev.Hhi[cr], rp - mn);
-  }
-}
-
-__global__ void k_dbg_init(uint32_t* dbg, uint32_t G) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) dbg[g * 4 + 3] = GROVE_NONE_U32;
-}
-
-#ifndef GROVE_ADMIT_MINBLOCKS
-#define GROVE_ADMIT_MINBLOCKS 6
-#endif
-constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
-constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
-
-// kMode 0: gangs with a gang-level constraint, packing from capacity bytes; 1: same, packing from fit
-// words + node records (no capacity tables this cycle); 2: gangs without a gang-level constraint
-// (cooperative).  Each instantiation skips the gangs of the other kind.
-template <int kThreads, int kMode, int kEnt>
-__global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
-  __shared__ GangShared sh;
-  __shared__ uint32_t s_en[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
-  __shared__ uint16_t s_em[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t ai = blockIdx.x;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t gi = rb.active[ai];
-  const grove_gang_t gg = tb.gangs[gi];
-  if ((gg.level == GROVE_LEVEL_NONE) != (kMode == 2)) return;  // handled by the other instantiation
-  const GangInfo info = tb.ginfo[gi];
-  GangRegs g;
-  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
-#pragma unroll
-  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-  for (uint32_t c = tid; c < gg.n_cliques; c += blockDim.x) {
-    const grove_clique_t q = tb.cliques[gg.clique_off + c];
-    sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
-                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
-    sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
-  }
-  for (uint32_t si = tid; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
-  __syncthreads();
-
-  const uint32_t K = rb.K, P = rb.P;
-  if constexpr (kMode == 2) {
-    // single candidate: the whole cluster, packed cooperatively by warp 0 (one alternative at most)
-    if (warp != 0) return;
-    CoopEv ev(tp, rb, sh, g, lane);
-    const bool ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
-    uint32_t n_min = 0;
-    if (ok) {
-      n_min = ev.np;
-      for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
-        const uint32_t w = sh.clq[cr].w;
-        const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-        if (rp > mn) ev.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn);
-      }
-      for (uint32_t i = lane; i < ev.np; i += 32) {
-        rb.alt_node[info.pod_off + i] = sh.ent_node[i];
-        rb.alt_meta[info.pod_off + i] = sh.ent_meta[i];
-      }
-    }
-    if (lane == 0) {
-      rb.nalt[gi] = ok ? 1u : 0u;
-      rb.alt_n[size_t(gi) * K] = ok ? ev.np : 0u;
-      rb.alt_nmin[size_t(gi) * K] = n_min;
-      rb.alt_top[size_t(gi) * K] = 0u;
-    }
-    return;
-  } else {
-
-  // candidate domains of the gang's level in score order: up to kMaxPieces ranges of domain indices
-  const uint32_t gl = gg.level;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
-  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
-  for (int p = 0; p < npc; ++p) {
-    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
-    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
-    D += rcnt[p];
-  }
-  ScalarEv<kMode == 0, kEnt> ev(tp, rb, sh, g, s_en + tid, s_em + tid, kThreads);
-  __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
-  __shared__ uint32_t s_okmask[kAdmitThreadsWide / 32];
-  __shared__ uint32_t s_ck[kAdmitThreadsWide], s_cl[kAdmitThreadsWide], s_ch[kAdmitThreadsWide];  // plausible candidates of the chunk, in order
-  const uint32_t nwarp = blockDim.x >> 5;
-  uint32_t nsucc = 0;  // feasible candidates found so far (block-uniform)
-  // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
-  // compact the plausible ones, then run the packing on them one lane per candidate.  The first K
-  // feasible candidates in order become the gang's alternatives.
-  for (uint32_t base = 0; base < D && nsucc < K; base += blockDim.x) {
-    {
-      const uint32_t k = base + tid;
-      uint32_t d = 0, dl = 0, dh = 0;
-      bool plaus = false;
-      if (k < D) {
-        uint32_t rem = k;
-        for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
-        dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-        plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
-      }
-      const uint32_t pb = __ballot_sync(kFull, plaus);
-      if (lane == 0) s_wcnt[warp] = __popc(pb);
-      __syncthreads();
-      uint32_t rank = __popc(pb & ((1u << lane) - 1u));
-      for (uint32_t w = 0; w < warp; ++w) rank += s_wcnt[w];
-      if (plaus) { s_ck[rank] = k; s_cl[rank] = dl; s_ch[rank] = dh; }
-    }
-    uint32_t total = 0;
-    for (uint32_t w = 0; w < nwarp; ++w) total += s_wcnt[w];
-    if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
-    __syncthreads();
-    for (uint32_t abase = 0; abase < total && nsucc < K;) {
-      const uint32_t width = blockDim.x;  // every plausible candidate of the chunk at once (latency rounds)
-      const uint32_t slot = tid;
-      if (tid < (kAdmitThreadsWide / 32)) s_okmask[tid] = 0;
-      __syncthreads();
-      bool ok = false; uint32_t k = 0, dl = 0;
-      if (slot != GROVE_NONE_U32 && abase + slot < total) {
-        k = s_ck[abase + slot]; dl = s_cl[abase + slot];
-        ev.k = k;
-        ok = place_in(ev, gg.n_scopes, dl, s_ch[abase + slot], int(gl));
-        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
-        if (ok) atomicOr(&s_okmask[slot >> 5], 1u << (slot & 31));
-      }
-      __syncthreads();
-      uint32_t stot = 0, srank = nsucc;
-      for (uint32_t w = 0; w < (kAdmitThreadsWide / 32); ++w) {
-        const uint32_t m = s_okmask[w];
-        stot += __popc(m);
-        if (ok) { if (w < (slot >> 5)) srank += __popc(m); else if (w == (slot >> 5)) srank += __popc(m & ((1u << (slot & 31)) - 1u)); }
-      }
-      if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
-        uint32_t n_min;
-        finish_gang(ev, gg.n_cliques, n_min);
-        const size_t o = size_t(srank) * P + info.pod_off;
-        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
-        rb.alt_n[size_t(gi) * K + srank] = ev.np;
-        rb.alt_nmin[size_t(gi) * K + srank] = n_min;
-        rb.alt_top[size_t(gi) * K + srank] = dl;
-        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
-      }
-      nsucc += stot;
-      abase += width;
-      __syncthreads();  // s_okmask is rewritten by the next window
-    }
-    __syncthreads();  // the candidate list is rewritten by the next chunk
-  }
-  if (tid == 0) rb.nalt[gi] = min(nsucc, K);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3, throughput form: ONE WARP per gang (4 gangs per CTA), used while a round has many gangs.  The
-// packing of one gang is a chain of dependent L2 look-ups (latency-bound), so what matters is how many
-// gangs are in flight per SM: a warp per gang keeps 24 of them resident instead of 6 with a CTA per
-// gang, and every intra-gang barrier is a __syncwarp.  Same semantics as k_admit: candidates in chunks
-// of 32 (one lane each), pre-filter, packing attempts on the plausible lanes in windows of `width0`,
-// ballots rank the successes, the first K in order are published as alternatives.
-// ------------------------------------------------------------------------------------------------
-constexpr int kAdmitWarpGangs = 4;
-constexpr int kEntSmem = 16;  // per-lane entry stack depth of the shared-memory form (gangs of <= 16 pods)
-
-template <bool kCaps, int kEnt>
-__global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k_admit_warp(Topo tp, Tables tb, RoundBufs rb) {
-  __shared__ GangShared shs[kAdmitWarpGangs];
-  __shared__ uint32_t s_en[(kEnt ? kEnt : 1) * kAdmitWarpGangs * 32];
-  __shared__ uint16_t s_em[(kEnt ? kEnt : 1) * kAdmitWarpGangs * 32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ai = blockIdx.x * kAdmitWarpGangs + warp;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t gi = rb.active[ai];
-  const grove_gang_t gg = tb.gangs[gi];
-  if (gg.level == GROVE_LEVEL_NONE) return;  // unconstrained gangs: k_admit<.,2>
-  GangShared& sh = shs[warp];
-  const GangInfo info = tb.ginfo[gi];
-  GangRegs g;
-  g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
-#pragma unroll
-  for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-  for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
-    const grove_clique_t q = tb.cliques[gg.clique_off + c];
-    sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
-                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
-    sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
-  }
-  for (uint32_t si = lane; si < gg.n_scopes; si += 32) sh.scopes[si] = tb.scopes[gg.scope_off + si];
-  __syncwarp();
-  const uint32_t K = rb.K, P = rb.P, gl = gg.level;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
-  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
-  for (int p = 0; p < npc; ++p) {
-    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
-    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
-    D += rcnt[p];
-  }
-  ScalarEv<kCaps, kEnt> ev(tp, rb, sh, g, s_en + threadIdx.x, s_em + threadIdx.x, kAdmitWarpGangs * 32);
-  uint32_t nsucc = 0;
-  for (uint32_t base = 0; base < D && nsucc < K; base += 32) {
-    const uint32_t k = base + lane;
-    uint32_t d = 0, dl = 0, dh = 0;
-    bool plaus = false;
-    if (k < D) {
-      uint32_t rem = k;
-      for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
-      dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-      plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
-    }
-    uint32_t todo = __ballot_sync(kFull, plaus);
-    if (rb.dbg && lane == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, __popc(todo)); }
-    bool first_window = base == 0;
-    while (todo && nsucc < K) {
-      // first window: a few more candidates than alternatives wanted (in an uncongested cluster nearly all
-      // fit); if that was not enough the cluster is congested: take every plausible candidate of the chunk
-      uint32_t sel = 0, t = todo;
-      const uint32_t wmax = first_window ? rb.width0 : 32u;
-      first_window = false;
-      for (uint32_t i = 0; i < wmax && t; ++i) { const uint32_t b = t & (0u - t); sel |= b; t ^= b; }
-      todo &= ~sel;
-      bool ok = false;
-      if ((sel >> lane) & 1u) {
-        ev.k = k;
-        ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
-        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
-      }
-      const uint32_t sb = __ballot_sync(kFull, ok);
-      const uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u));
-      if (ok && srank < K) {  // this lane holds the srank-th feasible candidate: publish it as an alternative
-        uint32_t n_min;
-        finish_gang(ev, gg.n_cliques, n_min);
-        const size_t o = size_t(srank) * P + info.pod_off;
-        for (uint32_t i = 0; i < ev.np; ++i) { rb.alt_node[o + i] = ev.en(i); rb.alt_meta[o + i] = ev.em(i); }
-        rb.alt_n[size_t(gi) * K + srank] = ev.np;
-        rb.alt_nmin[size_t(gi) * K + srank] = n_min;
-        rb.alt_top[size_t(gi) * K + srank] = dl;
-        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
-      }
-      nsucc += __popc(sb);
-      __syncwarp();
-    }
-  }
-  if (lane == 0) rb.nalt[gi] = min(nsucc, K);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Scores of the alternatives.  The score matrix (K2) and the admission (K3) only share the fit data, so
-// they run concurrently on two streams (K2 is HBM-write-bound, K3 is latency-bound: they overlap almost
-// perfectly); this kernel joins them: one warp per (active gang, alternative) looks up T[clique row][node]
-// for every entry, stores it next to the entry and reduces the minimum over the MinReplicas entries --
-// the PlacementScore numerator (podgang.go:187-189).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_alt_scores(Topo tp, Tables tb, RoundBufs rb) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t K = rb.K, P = rb.P;
-  const uint32_t ai = w / K, a = w - ai * K;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t g = rb.active[ai];
-  if (a >= rb.nalt[g]) return;
-  const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
-  const uint32_t cnt = rb.alt_n[size_t(g) * K + a], nmin = rb.alt_nmin[size_t(g) * K + a];
-  uint32_t mn = tp.L + 1;
-  for (uint32_t i = lane; i < cnt; i += 32) {
-    const size_t o = size_t(a) * P + po + i;
-    const uint32_t cr = rb.alt_meta[o] & 0xFFu;
-    const uint32_t sc = rb.T[size_t(coff + cr) * tp.npad + rb.alt_node[o]];
-    rb.alt_meta[o] = cr | (sc << 8);
-    if (i < nmin) mn = min(mn, sc);
-  }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) mn = min(mn, __shfl_xor_sync(kFull, mn, d));
-  if (lane == 0) rb.alt_score[size_t(g) * K + a] = mn;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Conflict resolution of one round (cooperative launch: grid-wide barriers between the phases).
-// Up to GROVE_SUBROUNDS passes over the alternatives computed by k_admit: every undecided gang
-// proposes its first alternative that touches no node committed earlier in this round; proposals
-// claim their nodes with the gang's order rank (atomicMin); a gang that holds every node it claimed
-// (warp ballot) commits: node table decremented, nodes marked taken, placement copied to the final
-// arrays.  Gangs without any alternative are rejected.  One warp per gang, strided over the grid; a
-// gang is always handled by the same warp, so its cur/prop bytes need no cross-CTA visibility; taken,
-// claim and flags do and are read with ld.cg / volatile.
-// ------------------------------------------------------------------------------------------------
-constexpr int kResolveThreads = 1024;  // few, fat CTAs: the grid barrier is what this kernel waits on
-
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t na = rb.counters[5];
-  const uint8_t r8 = uint8_t(round_no > 255 ? 255 : round_no);
-  const uint32_t K = rb.K, P = rb.P;
-  const volatile uint32_t* vflags = rb.flags;
-  if (na <= nw) {
-    // Fast path (the usual one: the grid is sized for it): a warp owns at most ONE gang for the whole round,
-    // so its constants and the nodes of its current alternative stay in registers and every phase is one
-    // level of look-ups (taken / claim) instead of a chain of six.
-    const bool have = gw < na;
-    uint32_t g = 0, nalt = 0, po = 0, order0 = 0, c = 0, cnt = 0;
-    uint32_t nd[4] = {GROVE_NONE_U32, GROVE_NONE_U32, GROVE_NONE_U32, GROVE_NONE_U32};
-    bool pending = false;
-    auto load_alt = [&]() {
-      cnt = rb.alt_n[size_t(g) * K + c];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const uint32_t i = lane + 32u * j; nd[j] = i < cnt ? rb.alt_node[size_t(c) * P + po + i] : GROVE_NONE_U32; }
-    };
-    if (have) {
-      g = rb.active_all[gw];
-      nalt = rb.nalt[g]; po = tb.ginfo[g].pod_off; order0 = tb.ginfo[g].order;
-      pending = nalt > 0;
-      if (!pending && lane == 0) { rb.state[g] = GROVE_GANG_REJECTED; rb.round[g] = r8; }
-      if (pending) load_alt();
-    }
-    for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
-      const uint32_t order = order0 | ((GROVE_SUBROUNDS - 1u - sub) << 24);
-      bool proposed = false;
-      if (pending) {
-        while (c < nalt) {  // first alternative that touches no node committed earlier in this round
-          bool hit = false;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) hit |= __ldcg(rb.taken + nd[j]) != 0;
-          if (!__any_sync(kFull, hit)) break;
-          if (++c < nalt) load_alt();
-        }
-        if (c < nalt) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) atomicMin(rb.claim + nd[j], order);
-          if (lane == 0) rb.flags[sub] = 1u;
-          proposed = true;
-        } else {
-          pending = false;  // nothing left to propose: re-evaluated next round
-        }
-      }
-      grid.sync();
-      if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
-      if (proposed) {
-        bool win = true;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) win &= __ldcg(rb.claim + nd[j]) == order;
-        if (__all_sync(kFull, win)) {
-          const uint32_t coff = tb.gangs[g].clique_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (nd[j] == GROVE_NONE_U32) continue;
-            const uint32_t i = lane + 32u * j;
-            const uint32_t meta = rb.alt_meta[size_t(c) * P + po + i];
-            const grove_clique_t q = tb.cliques[coff + (meta & 0xFFu)];
-            uint32_t* r = reinterpret_cast<uint32_t*>(nres + nd[j]);
-            // winners own their nodes exclusively in a sub-round; atomics only order this gang's own pods
-            if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
-            if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
-            atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
-            rb.taken[nd[j]] = 1;
-            rb.ent_node[po + i] = nd[j]; rb.ent_meta[po + i] = uint16_t(meta);
-          }
-          if (lane == 0) {
-            rb.spec_n[g] = uint16_t(cnt); rb.spec_score[g] = uint8_t(rb.alt_score[size_t(g) * K + c]);
-            rb.spec_top[g] = rb.alt_top[size_t(g) * K + c];
-            rb.state[g] = GROVE_GANG_ADMITTED; rb.round[g] = r8;
-          }
-          pending = false;
-        }
-      }
-      grid.sync();
-    }
-    return;
-  }
-  // generic path: more gangs than warps
-  for (uint32_t ai = gw; ai < na; ai += nw) {
-    const uint32_t g = rb.active_all[ai];
-    if (lane == 0) {
-      rb.cur[g] = 0; rb.prop[g] = 0;
-      if (rb.nalt[g] == 0) { rb.state[g] = GROVE_GANG_REJECTED; rb.round[g] = r8; }
-    }
-  }
-  __syncwarp();
-  for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
-    // claims carry the sub-round in their top bits so that a later sub-round always beats stale claims of
-    // an earlier one (atomicMin): nothing has to be withdrawn between sub-rounds
-    const uint32_t tag = (GROVE_SUBROUNDS - 1u - sub) << 24;
-    // ---- propose ----
-    for (uint32_t ai = gw; ai < na; ai += nw) {
-      const uint32_t g = rb.active_all[ai];
-      if (rb.state[g] != GROVE_GANG_PENDING) continue;
-      const uint32_t nalt = rb.nalt[g], po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order | tag;
-      uint32_t c = rb.cur[g], cnt = 0;
-      while (c < nalt) {  // first alternative that touches no node committed earlier in this round
-        cnt = rb.alt_n[size_t(g) * K + c];
-        bool hit = false;
-        for (uint32_t i = lane; i < cnt; i += 32) hit |= __ldcg(rb.taken + rb.alt_node[size_t(c) * P + po + i]) != 0;
-        if (!__any_sync(kFull, hit)) break;
-        ++c;
-      }
-      if (lane == 0) rb.cur[g] = uint8_t(c);
-      if (c >= nalt) continue;  // nothing left to propose: re-evaluated next round
-      for (uint32_t i = lane; i < cnt; i += 32) atomicMin(rb.claim + rb.alt_node[size_t(c) * P + po + i], order);
-      if (lane == 0) { rb.prop[g] = uint8_t(sub + 1); rb.flags[sub] = 1u; }
-    }
-    grid.sync();
-    if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
-    // ---- decide ----
-    for (uint32_t ai = gw; ai < na; ai += nw) {
-      const uint32_t g = rb.active_all[ai];
-      if (rb.prop[g] != sub + 1 || rb.state[g] != GROVE_GANG_PENDING) continue;
-      const uint32_t po = tb.ginfo[g].pod_off, order = tb.ginfo[g].order | tag, c = rb.cur[g];
-      const uint32_t cnt = rb.alt_n[size_t(g) * K + c];
-      bool win = true;
-      for (uint32_t i = lane; i < cnt; i += 32) win &= __ldcg(rb.claim + rb.alt_node[size_t(c) * P + po + i]) == order;
-      if (!__all_sync(kFull, win)) continue;
-      const uint32_t coff = tb.gangs[g].clique_off;
-      for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint32_t nd = rb.alt_node[size_t(c) * P + po + i], meta = rb.alt_meta[size_t(c) * P + po + i];
-        const grove_clique_t q = tb.cliques[coff + (meta & 0xFFu)];
-        uint32_t* r = reinterpret_cast<uint32_t*>(nres + nd);
-        // winners own their nodes exclusively in a sub-round; atomics only order this gang's own pods
-        if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
-        if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
-        atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
-        rb.taken[nd] = 1;
-        rb.ent_node[po + i] = nd; rb.ent_meta[po + i] = uint16_t(meta);
-      }
-      if (lane == 0) {
-        rb.spec_n[g] = uint16_t(cnt); rb.spec_score[g] = uint8_t(rb.alt_score[size_t(g) * K + c]);
-        rb.spec_top[g] = rb.alt_top[size_t(g) * K + c];
-        rb.state[g] = GROVE_GANG_ADMITTED; rb.round[g] = r8;
-      }
-    }
-    grid.sync();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// outputs: compact the admitted gangs' entries into caller order / caller node indices
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_finalize(Topo tp, Tables tb, RoundBufs rb, grove_gang_status_t* status, uint32_t* totals) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_run, s_tot, s_adm, s_rej;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_run = 0; s_adm = 0; s_rej = 0; }
-  __syncthreads();
-  for (uint32_t base = 0; base < tb.G; base += 1024) {
-    const uint32_t g = base + tid;
-    uint32_t cnt = 0; uint8_t st = 0;
-    if (g < tb.G) { st = rb.state[g]; if (st == GROVE_GANG_ADMITTED) cnt = rb.spec_n[g]; }
-    const uint32_t incl = warp_incl_scan(cnt, lane);
-    if (lane == 31) s_warp[warp] = incl;
-    const uint32_t na = __popc(__ballot_sync(kFull, st == GROVE_GANG_ADMITTED));
-    const uint32_t nr = __popc(__ballot_sync(kFull, st == GROVE_GANG_REJECTED || st == GROVE_GANG_BASE_REJECTED));
-    if (lane == 0) { if (na) atomicAdd(&s_adm, na); if (nr) atomicAdd(&s_rej, nr); }
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t v = s_warp[lane];
-      const uint32_t s = warp_incl_scan(v, lane);
-      s_warp[lane] = s - v;
-      if (lane == 31) s_tot = s;
-    }
-    __syncthreads();
-    if (g < tb.G) {
-      grove_gang_status_t o;
-      o.state = st; o.round = rb.round[g]; o.n_pods = cnt; o.placement_off = s_run + s_warp[warp] + incl - cnt;
-      o.score_num = 0; o.score_den = 0; o.top_domain_lo = GROVE_NONE_U32;
-      if (st == GROVE_GANG_ADMITTED) { o.score_num = rb.spec_score[g]; o.score_den = uint8_t(tp.L + 1); o.top_domain_lo = rb.spec_top[g]; }
-      status[g] = o;
-    }
-    __syncthreads();
-    if (tid == 0) s_run += s_tot;
-    __syncthreads();
-  }
-  if (tid == 0) { totals[0] = s_run; totals[1] = s_adm; totals[2] = s_rej; }
-}
-
-// one warp per gang: its entries -> caller node indices, at the offset k_finalize assigned
-__global__ void k_emit(Tables tb, RoundBufs rb, const uint32_t* __restrict__ perm, const grove_gang_status_t* __restrict__ status,
-                       grove_placement_t* out) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (g >= tb.G) return;
-  const grove_gang_status_t st = status[g];
-  if (st.state != GROVE_GANG_ADMITTED) return;
-  const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
-  for (uint32_t i = lane; i < st.n_pods; i += 32) {
-    grove_placement_t p;
-    p.clique = coff + (rb.ent_meta[po + i] & 0xFFu);
-    p.node = perm[rb.ent_node[po + i]];
-    out[st.placement_off + i] = p;
-  }
-}
-
-}  // namespace grove
+#include "common.cuh"
+#include "tables.cuh"
+#include "fit.cuh"
+#include "score.cuh"
+#include "admit.cuh"
+#include "resolve.cuh"
