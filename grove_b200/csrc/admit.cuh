@@ -24,7 +24,7 @@ struct GangRegs {   // per-gang constants
 };
 
 struct GangShared {
-  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16
+  uint4 clq[GROVE_MAX_GANG_CLIQUES];       // req_cpu, req_mem, req_gpu, min | replicas << 8 | level << 16 | preferred << 24
   grove_scope_t scopes[GROVE_MAX_GANG_SCOPES];
   uint32_t sig[GROVE_MAX_GANG_CLIQUES];    // fit-bitmap row of each clique
   // cooperative evaluator state (warp 0)
@@ -101,11 +101,12 @@ __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_
 }
 
 // ---- cooperative evaluator: the whole warp packs ONE candidate range -----------------------------
+template <bool kPref_>
 struct CoopEv {
+  static constexpr bool kPref = kPref_;
   const Topo& tp; const RoundBufs& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
   uint32_t np;
   uint32_t tmask = 0;
-  __device__ __forceinline__ bool moot() const { return false; }
   __device__ CoopEv(const Topo& t, const RoundBufs& r, GangShared& s, const GangRegs& gr, uint32_t ln)
       : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
 
@@ -212,13 +213,13 @@ struct CoopEv {
 // kEnt > 0: the per-lane entry stack (pods placed so far) lives in shared memory, kEnt entries per lane,
 // laid out [entry][thread] -- per-thread local arrays are what made this kernel thrash L1 (every local
 // word is a 128 B line per warp).  kEnt == 0: local arrays sized for the largest legal gang.
-template <bool kCaps, int kEnt>
+template <bool kCaps, int kEnt, bool kPref_>
 struct ScalarEv {
+  static constexpr bool kPref = kPref_;
   const Topo& tp; const RoundBufs& rb; const GangShared& sh; const GangRegs& g;
   uint32_t np;
   uint32_t tmask;  // bit (n & 31) set for every node this attempt has put a pod on: quick 'untouched' test
   uint32_t k;   // candidate index of this lane
-  __device__ __forceinline__ bool moot() const { return false; }  // every attempt may become one of the K alternatives
   uint32_t* sen; uint16_t* sem; uint32_t stride;
   uint32_t ent_node_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
   uint16_t ent_meta_l[kEnt ? 1 : GROVE_MAX_GANG_PODS];
@@ -438,6 +439,19 @@ __device__ bool gang_plausible(const Topo& tp, const RoundBufs& rb, const GangSh
   return true;
 }
 
+// Levels a unit (gang / scope / clique) with constraint (req, pref) is tried at inside a parent range of
+// level lvl (-1 = whole cluster): `first` down to the returned base.  base = the hard level (Required when
+// deeper than the parent's, else the parent range itself); a deeper Preferred level is tried first and
+// widened level by level up to base (podgang.go:110-117).  Oracle: level_span().  kPref = false: the submission
+// carries no Preferred level anywhere, the walk is the single step `base` (the kernels are instantiated both ways so
+// that Required-only workloads run the loop-free code).
+template <bool kPref>
+__device__ __forceinline__ int level_span(uint32_t req, uint32_t pref, int lvl, int& first) {
+  const int base = (req != GROVE_LEVEL_NONE && int(req) > lvl) ? int(req) : lvl;
+  first = (kPref && pref != GROVE_LEVEL_NONE && int(pref) > base) ? int(pref) : base;
+  return base;
+}
+
 template <class Ev>
 __device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
@@ -445,22 +459,29 @@ __device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint
   for (uint32_t i = 0; i < s.n_cliques; ++i) {
     const uint32_t cr = s.first_clique + i;
     const uint32_t w = ev.sh.clq[cr].w;
-    const uint32_t ql = (w >> 16) & 0xFFu, m = w & 0xFFu;
+    const uint32_t m = w & 0xFFu;
     bool ok = false;
-    if (ql != GROVE_LEVEL_NONE && int(ql) > lvl) {
-      if (tp.unit[ql] && m >= 1) {
-        ok = ev.find_unit(cr, lo, hi);
-      } else {
-        PieceIt pit; pit.init(ev.g, lo, hi, ql);
-        for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
-          const uint32_t d0 = __ldg(tp.next_dom[ql] + pa), d1 = __ldg(tp.next_dom[ql] + pb);
-          for (uint32_t d = d0; d < d1 && !ok; ++d)
-            ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
+    int first;
+    const int base = level_span<Ev::kPref>((w >> 16) & 0xFFu, w >> 24, lvl, first);
+    int ql = first;
+    do {
+      if (ql > lvl) {
+        // find_unit scans fit NODES: every fit node is a domain of a Required unit level (the fit row demands the
+        // labels down to it), but not of a Preferred one (ragged labels) -- those take the domain walk below
+        if (tp.unit[ql] && m >= 1 && ql == base) {
+          ok = ev.find_unit(cr, lo, hi);
+        } else {
+          PieceIt pit; pit.init(ev.g, lo, hi, uint32_t(ql));
+          for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
+            const uint32_t d0 = __ldg(tp.next_dom[ql] + pa), d1 = __ldg(tp.next_dom[ql] + pb);
+            for (uint32_t d = d0; d < d1 && !ok; ++d)
+              ok = ev.fill_min(cr, __ldg(tp.dom_lo[ql] + d), __ldg(tp.dom_hi[ql] + d));
+          }
         }
+      } else {
+        ok = ev.fill_min(cr, lo, hi);
       }
-    } else {
-      ok = ev.fill_min(cr, lo, hi);
-    }
+    } while (Ev::kPref && !ok && --ql >= base);
     if (!ok) { ev.np = mark; return false; }
   }
   return true;
@@ -473,21 +494,25 @@ __device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo,
   for (uint32_t si = 0; si < n_scopes; ++si) {
     const grove_scope_t s = ev.sh.scopes[si];
     bool ok = false;
-    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      PieceIt pit; pit.init(ev.g, lo, hi, s.level);
-      for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
-        const uint32_t d0 = __ldg(tp.next_dom[s.level] + pa), d1 = __ldg(tp.next_dom[s.level] + pb);
-        for (uint32_t d = d0; d < d1 && !ok; ++d) {
-          if (ev.moot()) { ev.np = 0; return false; }
-          const uint32_t el = __ldg(tp.dom_lo[s.level] + d), eh = __ldg(tp.dom_hi[s.level] + d);
-          // round-start capacities are an upper bound: a scope domain that lacks them cannot be packed
-          if (ev.rb.cap8 && !scope_plausible(tp, ev.rb, ev.sh, s, el, eh, int(s.level), d)) continue;
-          ok = place_scope(ev, s, el, eh, int(s.level));
+    int first;
+    const int base = level_span<Ev::kPref>(s.level, s.preferred1 ? uint32_t(s.preferred1) - 1u : uint32_t(GROVE_LEVEL_NONE), lvl, first);
+    int sl = first;
+    do {
+      if (sl > lvl) {
+        PieceIt pit; pit.init(ev.g, lo, hi, uint32_t(sl));
+        for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
+          const uint32_t d0 = __ldg(tp.next_dom[sl] + pa), d1 = __ldg(tp.next_dom[sl] + pb);
+          for (uint32_t d = d0; d < d1 && !ok; ++d) {
+            const uint32_t el = __ldg(tp.dom_lo[sl] + d), eh = __ldg(tp.dom_hi[sl] + d);
+            // round-start capacities are an upper bound: a scope domain that lacks them cannot be packed
+            if (ev.rb.cap8 && !scope_plausible(tp, ev.rb, ev.sh, s, el, eh, sl, d)) continue;
+            ok = place_scope(ev, s, el, eh, sl);
+          }
         }
+      } else {
+        ok = place_scope(ev, s, lo, hi, lvl);
       }
-    } else {
-      ok = place_scope(ev, s, lo, hi, lvl);
-    }
+    } while (Ev::kPref && !ok && --sl >= base);
     if (!ok) { ev.np = 0; return false; }
   }
   return true;
@@ -518,7 +543,7 @@ constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps p
 // kMode 0: gangs with a gang-level constraint, packing from capacity bytes; 1: same, packing from fit
 // words + node records (no capacity tables this cycle); 2: gangs without a gang-level constraint
 // (cooperative).  Each instantiation skips the gangs of the other kind.
-template <int kThreads, int kMode, int kEnt>
+template <int kThreads, int kMode, int kEnt, bool kPref>
 __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
   __shared__ uint32_t s_en[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
@@ -528,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   if (ai >= rb.counters[0]) return;
   const uint32_t gi = rb.active[ai];
   const grove_gang_t gg = tb.gangs[gi];
-  if ((gg.level == GROVE_LEVEL_NONE) != (kMode == 2)) return;  // handled by the other instantiation
+  if ((gg.level == GROVE_LEVEL_NONE && gg.preferred == GROVE_LEVEL_NONE) != (kMode == 2)) return;  // handled by the other instantiation
   const GangInfo info = tb.ginfo[gi];
   GangRegs g;
   g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.clique_off = gg.clique_off;
@@ -537,7 +562,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   for (uint32_t c = tid; c < gg.n_cliques; c += blockDim.x) {
     const grove_clique_t q = tb.cliques[gg.clique_off + c];
     sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
-                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
+                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16) |
+                               (GROVE_CLIQUE_PREFERRED(q.scope) << 24));
     sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
   }
   for (uint32_t si = tid; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
@@ -547,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   if constexpr (kMode == 2) {
     // single candidate: the whole cluster, packed cooperatively by warp 0 (one alternative at most)
     if (warp != 0) return;
-    CoopEv ev(tp, rb, sh, g, lane);
+    CoopEv<kPref> ev(tp, rb, sh, g, lane);
     const bool ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
     uint32_t n_min = 0;
     if (ok) {
@@ -571,22 +597,30 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     return;
   } else {
 
-  // candidate domains of the gang's level in score order: up to kMaxPieces ranges of domain indices
-  const uint32_t gl = gg.level;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
-  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
-  for (int p = 0; p < npc; ++p) {
-    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
-    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
-    D += rcnt[p];
-  }
-  ScalarEv<kMode == 0, kEnt> ev(tp, rb, sh, g, s_en + tid, s_em + tid, kThreads);
+  ScalarEv<kMode == 0, kEnt, kPref> ev(tp, rb, sh, g, s_en + tid, s_em + tid, kThreads);
   __shared__ uint32_t s_wcnt[kAdmitThreadsWide / 32];
   __shared__ uint32_t s_okmask[kAdmitThreadsWide / 32];
   __shared__ uint32_t s_ck[kAdmitThreadsWide], s_cl[kAdmitThreadsWide], s_ch[kAdmitThreadsWide];  // plausible candidates of the chunk, in order
   const uint32_t nwarp = blockDim.x >> 5;
   uint32_t nsucc = 0;  // feasible candidates found so far (block-uniform)
+  // candidate levels: the Preferred level first (if any), widened level by level up to the Required one
+  // (gl == -1: the whole cluster as a single candidate)
+  int gfirst;
+  const int gbase = level_span<kPref>(gg.level, gg.preferred, -1, gfirst);
+  int gl = gfirst;
+  do {
+  // candidate domains of level gl in score order: up to kMaxPieces ranges of domain indices
+  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
+  int npc = 1;
+  if (gl >= 0) {
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    npc = make_pieces(g, 0, tp.n, uint32_t(gl), plo, phi);
+    for (int p = 0; p < npc; ++p) {
+      r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
+      rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
+      D += rcnt[p];
+    }
+  } else { r0[0] = 0; rcnt[0] = 1; D = 1; }
   // chunks of blockDim.x candidates in order: pre-filter all of them in parallel (cheap table look-ups),
   // compact the plausible ones, then run the packing on them one lane per candidate.  The first K
   // feasible candidates in order become the gang's alternatives.
@@ -598,8 +632,10 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
       if (k < D) {
         uint32_t rem = k;
         for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
-        dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-        plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
+        if (gl >= 0) {
+          dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+          plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, gl, d);
+        } else { dl = 0; dh = tp.n; plaus = true; }
       }
       const uint32_t pb = __ballot_sync(kFull, plaus);
       if (lane == 0) s_wcnt[warp] = __popc(pb);
@@ -621,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
       if (slot != GROVE_NONE_U32 && abase + slot < total) {
         k = s_ck[abase + slot]; dl = s_cl[abase + slot];
         ev.k = k;
-        ok = place_in(ev, gg.n_scopes, dl, s_ch[abase + slot], int(gl));
+        ok = place_in(ev, gg.n_scopes, dl, s_ch[abase + slot], gl);
         if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
         if (ok) atomicOr(&s_okmask[slot >> 5], 1u << (slot & 31));
       }
@@ -648,6 +684,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     }
     __syncthreads();  // the candidate list is rewritten by the next chunk
   }
+  } while (kPref && nsucc < K && --gl >= gbase);  // candidate levels
   if (tid == 0) rb.nalt[gi] = min(nsucc, K);
   }
 }
@@ -663,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
 constexpr int kAdmitWarpGangs = 4;
 constexpr int kEntSmem = 16;  // per-lane entry stack depth of the shared-memory form (gangs of <= 16 pods)
 
-template <bool kCaps, int kEnt>
+template <bool kCaps, int kEnt, bool kPref>
 __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k_admit_warp(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared shs[kAdmitWarpGangs];
   __shared__ uint32_t s_en[(kEnt ? kEnt : 1) * kAdmitWarpGangs * 32];
@@ -673,7 +710,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
   if (ai >= rb.counters[0]) return;
   const uint32_t gi = rb.active[ai];
   const grove_gang_t gg = tb.gangs[gi];
-  if (gg.level == GROVE_LEVEL_NONE) return;  // unconstrained gangs: k_admit<.,2>
+  if (gg.level == GROVE_LEVEL_NONE && gg.preferred == GROVE_LEVEL_NONE) return;  // unconstrained gangs: k_admit<.,2>
   GangShared& sh = shs[warp];
   const GangInfo info = tb.ginfo[gi];
   GangRegs g;
@@ -683,22 +720,32 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
   for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
     const grove_clique_t q = tb.cliques[gg.clique_off + c];
     sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
-                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16));
+                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16) |
+                               (GROVE_CLIQUE_PREFERRED(q.scope) << 24));
     sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
   }
   for (uint32_t si = lane; si < gg.n_scopes; si += 32) sh.scopes[si] = tb.scopes[gg.scope_off + si];
   __syncwarp();
-  const uint32_t K = rb.K, P = rb.P, gl = gg.level;
-  uint32_t plo[kMaxPieces], phi[kMaxPieces];
-  const int npc = make_pieces(g, 0, tp.n, gl, plo, phi);
-  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
-  for (int p = 0; p < npc; ++p) {
-    r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
-    rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
-    D += rcnt[p];
-  }
-  ScalarEv<kCaps, kEnt> ev(tp, rb, sh, g, s_en + threadIdx.x, s_em + threadIdx.x, kAdmitWarpGangs * 32);
+  const uint32_t K = rb.K, P = rb.P;
+  ScalarEv<kCaps, kEnt, kPref> ev(tp, rb, sh, g, s_en + threadIdx.x, s_em + threadIdx.x, kAdmitWarpGangs * 32);
   uint32_t nsucc = 0;
+  // candidate levels: the Preferred level first (if any), widened level by level up to the Required one
+  // (gl == -1: the whole cluster as a single candidate)
+  int gfirst;
+  const int gbase = level_span<kPref>(gg.level, gg.preferred, -1, gfirst);
+  int gl = gfirst;
+  do {
+  uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
+  int npc = 1;
+  if (gl >= 0) {
+    uint32_t plo[kMaxPieces], phi[kMaxPieces];
+    npc = make_pieces(g, 0, tp.n, uint32_t(gl), plo, phi);
+    for (int p = 0; p < npc; ++p) {
+      r0[p] = __ldg(tp.next_dom[gl] + plo[p]);
+      rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p];
+      D += rcnt[p];
+    }
+  } else { r0[0] = 0; rcnt[0] = 1; D = 1; }
   for (uint32_t base = 0; base < D && nsucc < K; base += 32) {
     const uint32_t k = base + lane;
     uint32_t d = 0, dl = 0, dh = 0;
@@ -706,8 +753,10 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
     if (k < D) {
       uint32_t rem = k;
       for (int p = 0; p < npc; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
-      dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-      plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, int(gl), d);
+      if (gl >= 0) {
+        dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+        plaus = rb.cap8 == nullptr || gang_plausible(tp, rb, sh, gg.n_scopes, dl, dh, gl, d);
+      } else { dl = 0; dh = tp.n; plaus = true; }
     }
     uint32_t todo = __ballot_sync(kFull, plaus);
     if (rb.dbg && lane == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, __popc(todo)); }
@@ -723,7 +772,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       bool ok = false;
       if ((sel >> lane) & 1u) {
         ev.k = k;
-        ok = place_in(ev, gg.n_scopes, dl, dh, int(gl));
+        ok = place_in(ev, gg.n_scopes, dl, dh, gl);
         if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
       }
       const uint32_t sb = __ballot_sync(kFull, ok);
@@ -742,6 +791,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       __syncwarp();
     }
   }
+  } while (kPref && nsucc < K && --gl >= gbase);  // candidate levels
   if (lane == 0) rb.nalt[gi] = min(nsucc, K);
 }
 

@@ -112,7 +112,8 @@ struct grove_engine {
   DevBuf<uint32_t> d_xbuf, d_active_all, d_flags, d_capsum, d_capmax;
   DevBuf<uint8_t> d_taken, d_cur, d_prop;
   uint32_t K = GROVE_MAX_ALTERNATIVES;
-  uint32_t n_constrained = 0, n_unconstrained = 0;  // gangs with / without a gang-level Required level
+  bool any_preferred = false;  // some gang / scope / clique carries a Preferred level
+  uint32_t n_constrained = 0, n_unconstrained = 0;  // gangs with / without a gang-level Required or Preferred level
   uint32_t max_gang_pods = 0;
   int resolve_blocks_per_sm = 0;
   uint32_t n_sm = 148;
@@ -425,7 +426,8 @@ static const char* validate_gang(const grove_engine* e, const grove_gang_t* gang
   *code = GROVE_ERR_INVALID_ARG;
   if (uint64_t(g.clique_off) + g.n_cliques > Q || uint64_t(g.scope_off) + g.n_scopes > S) return "gang table offsets out of range";
   if (g.level != GROVE_LEVEL_NONE && g.level >= L) return "gang level out of range";
-  if (g.preferred != GROVE_LEVEL_NONE) return "preferred level is reserved";
+  if (g.preferred != GROVE_LEVEL_NONE && (g.preferred >= L || (g.level != GROVE_LEVEL_NONE && g.preferred <= g.level)))
+    return "gang preferred level must be a level deeper than the required one";
   if (g.anchor_node != GROVE_NONE_U32 && e->nodes_loaded && g.anchor_node >= e->N) return "anchor node out of range";
   if (g.base_gang != GROVE_NONE_U32 && (g.base_gang >= G || g.base_gang == gi)) return "base gang out of range";
   uint32_t pods = 0, next = 0;
@@ -433,11 +435,16 @@ static const char* validate_gang(const grove_engine* e, const grove_gang_t* gang
     const grove_scope_t& s = scopes[g.scope_off + si];
     if (s.first_clique != next || s.n_cliques == 0) return "scopes must tile the gang's cliques in order";
     if (s.level != GROVE_LEVEL_NONE && s.level >= L) return "scope level out of range";
+    if (s.preferred1 && (s.preferred1 > L || (s.level != GROVE_LEVEL_NONE && uint32_t(s.preferred1) - 1u <= s.level)))
+      return "scope preferred level must be a level deeper than the required one";
     if (next + s.n_cliques > g.n_cliques) return "scope exceeds gang";
     for (uint32_t i = 0; i < s.n_cliques; ++i) {
       const grove_clique_t& q = cliques[g.clique_off + next + i];
-      if (q.scope != si) return "clique.scope does not match its scope";
+      if (GROVE_CLIQUE_SCOPE(q.scope) != si) return "clique.scope does not match its scope";
       if (q.level != GROVE_LEVEL_NONE && q.level >= L) return "clique level out of range";
+      const uint32_t qp = GROVE_CLIQUE_PREFERRED(q.scope);
+      if (qp != GROVE_LEVEL_NONE && (qp >= L || (q.level != GROVE_LEVEL_NONE && qp <= q.level)))
+        return "clique preferred level must be a level deeper than the required one";
       if (q.replicas < q.min_replicas) return "replicas < min_replicas";
       pods += q.replicas;
     }
@@ -480,7 +487,14 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   e->scopes.assign(scopes, scopes + n_scopes);
   e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
   e->n_constrained = e->n_unconstrained = 0;
-  for (uint32_t g = 0; g < n_gangs; ++g) (gangs[g].level == GROVE_LEVEL_NONE ? e->n_unconstrained : e->n_constrained)++;
+  bool pref = false;
+  for (uint32_t g = 0; g < n_gangs; ++g) {
+    (gangs[g].level == GROVE_LEVEL_NONE && gangs[g].preferred == GROVE_LEVEL_NONE ? e->n_unconstrained : e->n_constrained)++;
+    pref |= gangs[g].preferred != GROVE_LEVEL_NONE;
+  }
+  for (uint32_t i = 0; i < n_scopes && !pref; ++i) pref |= scopes[i].preferred1 != 0;
+  for (uint32_t i = 0; i < n_cliques && !pref; ++i) pref |= (cliques[i].scope >> 5) != 0;
+  e->any_preferred = pref;
   CU_TRY(e, e->d_gangs.ensure(n_gangs)); CU_TRY(e, e->d_cliques.ensure(n_cliques)); CU_TRY(e, e->d_scopes.ensure(n_scopes));
   if (n_gangs) CU_TRY(e, cudaMemcpyAsync(e->d_gangs.p, e->gangs.data(), sizeof(grove_gang_t) * n_gangs, cudaMemcpyHostToDevice, e->stream));
   if (n_cliques) CU_TRY(e, cudaMemcpyAsync(e->d_cliques.p, e->cliques.data(), sizeof(grove_clique_t) * n_cliques, cudaMemcpyHostToDevice, e->stream));
@@ -677,6 +691,36 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
 
 static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P + 4 * size_t(e->G) * e->K + e->G; }
 
+// K3 launches of one round.  kPref: some gang / scope / clique of the submission carries a Preferred level
+// (the level walks are compiled in); otherwise the loop-free Required-only instantiations run.
+extern "C++" {
+template <bool kPref>
+static void launch_admit(grove_engine* e, const Topo& tp, const Tables& tb, const RoundBufs& rb, uint32_t na, bool caps, bool small) {
+  if (e->n_constrained) {
+    if (na >= e->tune_warp_min) {  // throughput round: a warp per gang
+      const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
+      const int th = kAdmitWarpGangs * 32;
+      if (caps && small) k_admit_warp<true, kEntSmem, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit_warp<true, 0, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit_warp<false, kEntSmem, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+      else k_admit_warp<false, 0, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
+    } else if (na >= e->tune_wide_max) {  // middle: a 4-warp CTA per gang
+      if (caps && small) k_admit<kAdmitThreads, 0, kEntSmem, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit<kAdmitThreads, 0, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit<kAdmitThreads, 1, kEntSmem, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+      else k_admit<kAdmitThreads, 1, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
+    } else {                // latency round: an 8-warp CTA per gang
+      if (caps && small) k_admit<kAdmitThreadsWide, 0, kEntSmem, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else if (caps) k_admit<kAdmitThreadsWide, 0, 0, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else if (small) k_admit<kAdmitThreadsWide, 1, kEntSmem, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+      else k_admit<kAdmitThreadsWide, 1, 0, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
+    }
+    e->launches += 1;
+  }
+  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
+}
+}  // extern "C++"
+
 // evaluation half of a round on this handle's share of the gangs: prepare -> fit -> (capacity tables)
 // -> score -> admit.  Counters land in h_counters.
 static int32_t round_eval(grove_engine* e, bool timed) {
@@ -716,28 +760,7 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
   const bool small = e->max_gang_pods <= kEntSmem;  // per-lane entry stacks fit the shared-memory form
-  if (e->n_constrained) {
-    if (na >= e->tune_warp_min) {  // throughput round: a warp per gang
-      const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
-      const int th = kAdmitWarpGangs * 32;
-      if (caps && small) k_admit_warp<true, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit_warp<true, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit_warp<false, kEntSmem><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else k_admit_warp<false, 0><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-    } else if (na >= e->tune_wide_max) {  // middle: a 4-warp CTA per gang
-      if (caps && small) k_admit<kAdmitThreads, 0, kEntSmem><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit<kAdmitThreads, 0, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit<kAdmitThreads, 1, kEntSmem><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else k_admit<kAdmitThreads, 1, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-    } else {                // latency round: an 8-warp CTA per gang
-      if (caps && small) k_admit<kAdmitThreadsWide, 0, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit<kAdmitThreadsWide, 0, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit<kAdmitThreadsWide, 1, kEntSmem><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else k_admit<kAdmitThreadsWide, 1, 0><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-    }
-    e->launches += 1;
-  }
-  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2, 0><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
+  if (e->any_preferred) launch_admit<true>(e, tp, tb, rb, na, caps, small); else launch_admit<false>(e, tp, tb, rb, na, caps, small);
   // join: scores of the alternatives need both the score matrix and the alternatives
   if (e->tune_overlap) CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_score, 0));
   k_alt_scores<<<(na * e->K * 32 + 255) / 256, 256, 0, e->stream>>>(tp, tb, rb);

@@ -209,11 +209,19 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
         r.dom[l] = intern[l].emplace(it->second, uint32_t(intern[l].size())).first->second;
     }
   }
-  auto levelOf = [this](const std::optional<TopologyConstraint>& tc, uint8_t* lvl) -> Err {
-    *lvl = GROVE_LEVEL_NONE;
-    if (!tc || !tc->PackConstraint || !tc->PackConstraint->Required) return std::nullopt;
-    for (size_t l = 0; l < levels_.size(); ++l) if (levels_[l].Key == *tc->PackConstraint->Required) { *lvl = uint8_t(l); return std::nullopt; }
-    return mkerr("ERR_SYNC_PODGANG", "Encode", "Required topology key " + *tc->PackConstraint->Required + " is not a level of the synced ClusterTopology");
+  // (Required, Preferred) label keys -> level indices; a Preferred level that is not deeper than the Required
+  // one adds nothing (best effort, podgang.go:110-117) and is dropped
+  auto levelOf = [this](const std::optional<TopologyConstraint>& tc, uint8_t* lvl, uint8_t* pref) -> Err {
+    *lvl = GROVE_LEVEL_NONE; *pref = GROVE_LEVEL_NONE;
+    if (!tc || !tc->PackConstraint) return std::nullopt;
+    auto find = [this](const std::string& key, const char* what, uint8_t* o) -> Err {
+      for (size_t l = 0; l < levels_.size(); ++l) if (levels_[l].Key == key) { *o = uint8_t(l); return std::nullopt; }
+      return mkerr("ERR_SYNC_PODGANG", "Encode", std::string(what) + " topology key " + key + " is not a level of the synced ClusterTopology");
+    };
+    if (tc->PackConstraint->Required) if (auto e = find(*tc->PackConstraint->Required, "Required", lvl)) return e;
+    if (tc->PackConstraint->Preferred) if (auto e = find(*tc->PackConstraint->Preferred, "Preferred", pref)) return e;
+    if (*pref != GROVE_LEVEL_NONE && *lvl != GROVE_LEVEL_NONE && *pref <= *lvl) *pref = GROVE_LEVEL_NONE;
+    return std::nullopt;
   };
   std::map<std::string, uint32_t> row;  // PodGang key -> gang row
   for (const auto& kv : pending_) row.emplace(kv.first, uint32_t(row.size()));
@@ -224,7 +232,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     g.clique_off = uint32_t(out->cliques.size()); g.scope_off = uint32_t(out->scopes.size());
     g.anchor_node = GROVE_NONE_U32; g.base_gang = GROVE_NONE_U32; g.preferred = GROVE_LEVEL_NONE;
     g.flags = pg.Gated ? GROVE_GANG_GATED : 0;
-    if (auto e = levelOf(pg.Spec.Topology, &g.level)) return e;
+    if (auto e = levelOf(pg.Spec.Topology, &g.level, &g.preferred)) return e;
     if (auto it = priorityClasses_.find(pg.Spec.PriorityClassName); it != priorityClasses_.end()) g.priority = it->second;
     if (!pg.BasePodGangName.empty())
       if (auto it = row.find(pg.Namespace + "/" + pg.BasePodGangName); it != row.end()) g.base_gang = it->second;
@@ -235,23 +243,25 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     // scopes: the loose PodGroups first (one implicit scope), then one scope per TopologyConstraintGroupConfig
     std::set<std::string> grouped;
     for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) for (const auto& n : gc.PodGroupNames) grouped.insert(n);
-    std::vector<std::pair<uint8_t, std::vector<uint32_t>>> scopes;  // (level, PodGroup indices)
+    struct ScopeRows { uint8_t first, pref; std::vector<uint32_t> second; };  // (Required level, Preferred level, PodGroup indices)
+    std::vector<ScopeRows> scopes;
     std::vector<uint32_t> loose;
     for (uint32_t i = 0; i < pg.Spec.PodGroups.size(); ++i) if (!grouped.count(pg.Spec.PodGroups[i].Name)) loose.push_back(i);
-    if (!loose.empty()) scopes.push_back({uint8_t(GROVE_LEVEL_NONE), loose});
+    if (!loose.empty()) scopes.push_back({uint8_t(GROVE_LEVEL_NONE), uint8_t(GROVE_LEVEL_NONE), loose});
     for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) {
-      uint8_t lvl; if (auto e = levelOf(gc.Topology, &lvl)) return e;
+      uint8_t lvl, pref; if (auto e = levelOf(gc.Topology, &lvl, &pref)) return e;
       std::vector<uint32_t> members;
       for (const auto& n : gc.PodGroupNames) {
         auto it = std::find_if(pg.Spec.PodGroups.begin(), pg.Spec.PodGroups.end(), [&n](const PodGroup& p) { return p.Name == n; });
         if (it == pg.Spec.PodGroups.end()) return mkerr("ERR_SYNC_PODGANG", "Encode", "group config " + gc.Name + " names unknown PodGroup " + n);
         members.push_back(uint32_t(it - pg.Spec.PodGroups.begin()));
       }
-      if (!members.empty()) scopes.push_back({lvl, members});
+      if (!members.empty()) scopes.push_back({lvl, pref, members});
     }
     uint32_t rel = 0, pods = 0;
     for (size_t si = 0; si < scopes.size(); ++si) {
       grove_scope_t s{}; s.first_clique = uint16_t(rel); s.n_cliques = uint16_t(scopes[si].second.size()); s.level = scopes[si].first;
+      s.preferred1 = scopes[si].pref == GROVE_LEVEL_NONE ? uint8_t(0) : uint8_t(scopes[si].pref + 1);
       out->scopes.push_back(s);
       for (uint32_t gi : scopes[si].second) {
         const PodGroup& p = pg.Spec.PodGroups[gi];
@@ -262,8 +272,9 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
         if (p.MinReplicas < 0 || p.MinReplicas > 255 || p.PodReferences.size() > 255 || size_t(p.MinReplicas) > p.PodReferences.size())
           return mkerr("ERR_SYNC_PODGANG", "Encode", "PodGroup " + p.Name + ": MinReplicas / PodReferences out of range");
         c.min_replicas = uint8_t(p.MinReplicas); c.replicas = uint8_t(p.PodReferences.size());
-        if (auto e = levelOf(p.Topology, &c.level)) return e;
-        c.scope = uint8_t(si);
+        uint8_t cpref;
+        if (auto e = levelOf(p.Topology, &c.level, &cpref)) return e;
+        c.scope = GROVE_CLIQUE_SCOPE_PREF(uint32_t(si), cpref);
         // class mask: classes whose label value satisfies the nodeSelector and whose taints are all tolerated
         uint16_t mask = 0;
         auto sel = rq.nodeSelector.find(classKey_);

@@ -76,13 +76,20 @@ def nodes_from_manifests(manifests, level_keys, class_key=None, used=None):
     return nodes, names, intern, classes
 
 
-def _level(tc, level_keys):
-    req = (((tc or {}).get("packConstraint") or {}).get("required"))
-    if req is None:
+def _level(tc, level_keys, which="required"):
+    key = (((tc or {}).get("packConstraint") or {}).get(which))
+    if key is None:
         return None
-    if req not in level_keys:
-        raise ValueError(f"required topology key {req!r} is not a level of the cluster topology")
-    return level_keys.index(req)
+    if key not in level_keys:
+        raise ValueError(f"{which} topology key {key!r} is not a level of the cluster topology")
+    return level_keys.index(key)
+
+
+def _preferred(tc, level_keys):
+    """packConstraint.preferred (podgang.go:110-117) as a level index; one that is not deeper than the
+    required level adds nothing (best effort) and is dropped"""
+    req, pref = _level(tc, level_keys), _level(tc, level_keys, "preferred")
+    return None if pref is None or (req is not None and pref <= req) else pref
 
 
 def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=None, class_mask=0xFFFF, base_of=None):
@@ -104,15 +111,18 @@ def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=Non
             names.append((pg["metadata"]["name"], g["name"]))
             return dict(cpu=parse_cpu_milli(rq.get("cpu", 0)), mem=parse_mem_mib(rq.get("memory", 0)),
                         gpu=int(rq.get("nvidia.com/gpu", 0)), min=int(g["minReplicas"]), replicas=len(g["podReferences"]),
-                        level=_level(g.get("topologyConstraint"), level_keys), class_mask=class_mask)
+                        level=_level(g.get("topologyConstraint"), level_keys),
+                        preferred=_preferred(g.get("topologyConstraint"), level_keys), class_mask=class_mask)
 
         loose = [g for g in spec["podgroups"] if g["name"] not in grouped]
         if loose:
             scopes.append((None, [clique(g) for g in loose]))
         for gc in spec.get("topologyConstraintGroupConfigs") or []:
-            scopes.append((_level(gc.get("topologyConstraint"), level_keys), [clique(groups[n]) for n in gc["podGroupNames"]]))
+            scopes.append((_level(gc.get("topologyConstraint"), level_keys), [clique(groups[n]) for n in gc["podGroupNames"]],
+                           _preferred(gc.get("topologyConstraint"), level_keys)))
         base = (base_of or {}).get(pg["metadata"]["name"])
         b.add_gang(scopes, level=_level(spec.get("topologyConstraint"), level_keys),
+                   preferred=_preferred(spec.get("topologyConstraint"), level_keys),
                    priority=(priority_classes or {}).get(spec.get("priorityClassName", ""), 0),
                    base=row_of[base] if base in row_of else None)
     g, c, s = b.build()

@@ -34,7 +34,7 @@ clique_dt = np.dtype([
     ("replicas", "u1"), ("class_mask", "<u2"), ("level", "u1"), ("scope", "u1"),
 ])
 scope_dt = np.dtype([
-    ("first_clique", "<u2"), ("n_cliques", "<u2"), ("level", "u1"), ("reserved", "u1", (3,)),
+    ("first_clique", "<u2"), ("n_cliques", "<u2"), ("level", "u1"), ("preferred1", "u1"), ("reserved", "u1", (2,)),
 ])
 gang_dt = np.dtype([
     ("clique_off", "<u4"), ("scope_off", "<u4"), ("n_cliques", "<u2"), ("n_scopes", "<u2"),
@@ -70,10 +70,11 @@ def make_nodes(n: int) -> np.ndarray:
 class GangTableBuilder:
     """Accumulates PodGangs into the three packed tables.
 
-    One `add_gang` call is one PodGang: `scopes` is a list of (level, [clique dict, ...]); a scope
-    with level None is the implicit scope of PodGroups that are in no TopologyConstraintGroupConfig.
-    Clique dict keys: cpu, mem, gpu (per-pod request), min, replicas (default = min), level,
-    class_mask (default 0xFFFF).
+    One `add_gang` call is one PodGang: `scopes` is a list of (level, [clique dict, ...]) or
+    (level, [clique dict, ...], preferred); a scope with level None is the implicit scope of PodGroups
+    that are in no TopologyConstraintGroupConfig.  Clique dict keys: cpu, mem, gpu (per-pod request),
+    min, replicas (default = min), level, preferred, class_mask (default 0xFFFF).  `preferred` is the
+    PackConstraint.Preferred level (podgang.go:110-117), deeper than the Required one.
     """
 
     def __init__(self) -> None:
@@ -85,22 +86,29 @@ class GangTableBuilder:
     def _lvl(level) -> int:
         return LEVEL_NONE if level is None else int(level)
 
-    def add_gang(self, scopes, level=None, priority=0, anchor=None, base=None, gated=False) -> int:
+    @staticmethod
+    def _pref1(level) -> int:
+        return 0 if level is None else int(level) + 1
+
+    def add_gang(self, scopes, level=None, priority=0, anchor=None, base=None, gated=False, preferred=None) -> int:
         clique_off, scope_off = len(self.cliques), len(self.scopes)
         rel = 0
-        for si, (slevel, cliques) in enumerate(scopes):
-            self.scopes.append((rel, len(cliques), self._lvl(slevel)))
+        for si, scope in enumerate(scopes):
+            slevel, cliques = scope[0], scope[1]
+            spref = scope[2] if len(scope) > 2 else None
+            self.scopes.append((rel, len(cliques), self._lvl(slevel), self._pref1(spref)))
             for c in cliques:
                 mn = int(c.get("min", 1))
                 self.cliques.append((
                     int(c.get("cpu", 0)), int(c.get("mem", 0)), int(c.get("gpu", 0)), mn,
-                    int(c.get("replicas", mn)), int(c.get("class_mask", 0xFFFF)), self._lvl(c.get("level")), si,
+                    int(c.get("replicas", mn)), int(c.get("class_mask", 0xFFFF)), self._lvl(c.get("level")),
+                    si | (self._pref1(c.get("preferred")) << 5),
                 ))
                 rel += 1
         self.gangs.append((
             clique_off, scope_off, rel, len(scopes), int(priority),
             NONE_U32 if anchor is None else int(anchor), NONE_U32 if base is None else int(base),
-            self._lvl(level), GANG_GATED if gated else 0,
+            self._lvl(level), GANG_GATED if gated else 0, self._lvl(preferred),
         ))
         return len(self.gangs) - 1
 
@@ -111,12 +119,11 @@ class GangTableBuilder:
         for i, g in enumerate(self.gangs):
             (gangs["clique_off"][i], gangs["scope_off"][i], gangs["n_cliques"][i], gangs["n_scopes"][i],
              gangs["priority"][i], gangs["anchor_node"][i], gangs["base_gang"][i], gangs["level"][i],
-             gangs["flags"][i]) = g
-        gangs["preferred"][:] = LEVEL_NONE
+             gangs["flags"][i], gangs["preferred"][i]) = g
         for i, c in enumerate(self.cliques):
             (cliques["req_cpu_milli"][i], cliques["req_mem_mib"][i], cliques["req_gpu"][i],
              cliques["min_replicas"][i], cliques["replicas"][i], cliques["class_mask"][i],
              cliques["level"][i], cliques["scope"][i]) = c
         for i, s in enumerate(self.scopes):
-            scopes["first_clique"][i], scopes["n_cliques"][i], scopes["level"][i] = s
+            scopes["first_clique"][i], scopes["n_cliques"][i], scopes["level"][i], scopes["preferred1"][i] = s
         return gangs, cliques, scopes

@@ -86,15 +86,22 @@ typedef struct grove_clique {
   uint8_t replicas;       /* len(PodReferences) >= min_replicas: surplus is best effort (podgang.go:80-83) */
   uint16_t class_mask;    /* bit c set <=> node selector class c is acceptable (nodeSelector+tolerations) */
   uint8_t level;          /* PodGroup.TopologyConstraint Required level index, or GROVE_LEVEL_NONE */
-  uint8_t scope;          /* index of the owning scope inside the gang (non-decreasing over the gang's cliques) */
+  uint8_t scope;          /* bits 0..4: index of the owning scope inside the gang (non-decreasing over the gang's
+                             cliques); bits 5..7: Preferred level index + 1, 0 = none (GROVE_CLIQUE_SCOPE_PREF) */
 } grove_clique_t;
+#define GROVE_CLIQUE_SCOPE(x) ((uint32_t)(x) & 0x1Fu)
+#define GROVE_CLIQUE_PREFERRED(x) ((((uint32_t)(x)) >> 5) ? (((uint32_t)(x)) >> 5) - 1u : (uint32_t)GROVE_LEVEL_NONE)
+#define GROVE_CLIQUE_SCOPE_PREF(scope, pref) \
+  ((uint8_t)(((scope) & 0x1Fu) | (((pref) == GROVE_LEVEL_NONE ? 0u : (uint32_t)(pref) + 1u) << 5)))
 
 /* one TopologyConstraintGroupConfig (podgang.go:120-131), or the implicit scope of loose PodGroups */
 typedef struct grove_scope {
   uint16_t first_clique;  /* relative to the gang's clique_off */
   uint16_t n_cliques;
   uint8_t level;          /* Required level index, or GROVE_LEVEL_NONE */
-  uint8_t reserved[3];
+  uint8_t preferred1;     /* Preferred level index + 1 (deeper than `level`), 0 = none: zero-filled records
+                             written against the earlier layout keep their meaning */
+  uint8_t reserved[2];
 } grove_scope_t;
 
 #define GROVE_GANG_GATED 0x1u /* pods still carry the grove.io/podgang-pending-creation gate: skip */
@@ -109,7 +116,8 @@ typedef struct grove_gang {
   uint32_t base_gang;     /* scaled gang: index of its base gang in this submission (gated behind it,
                              pod/syncflow.go:319-358), or GROVE_NONE_U32 */
   uint8_t level;          /* PodGangSpec.TopologyConstraint Required level index, or GROVE_LEVEL_NONE */
-  uint8_t preferred;      /* reserved (Preferred level); must be GROVE_LEVEL_NONE */
+  uint8_t preferred;      /* PackConstraint.Preferred level index (podgang.go:110-117): best effort, tried before
+                             falling back level by level up to `level`; deeper than `level`; or GROVE_LEVEL_NONE */
   uint16_t flags;
   uint32_t reserved;
 } grove_gang_t;

@@ -222,6 +222,18 @@ static uint32_t closeness(const topo_t* T, uint32_t n, uint32_t a) {
   return c;
 }
 
+/* Levels a unit (gang / scope / clique) with constraint (req, pref) is tried at inside a parent range of
+ * level `lvl` (-1 = the whole cluster): from *first down to the returned base.  base is the hard level
+ * (Required if it is deeper than the parent's, else the parent range itself); Preferred, when deeper than
+ * base, is tried first and widened level by level up to base (podgang.go:110-117: "Scheduler can fall back
+ * to higher topology levels (upto Required constraint) if preferred cannot be satisfied"). */
+static int level_span(uint32_t req, uint32_t pref, int lvl, int* first) {
+  int base = (req != GROVE_LEVEL_NONE && (int)req > lvl) ? (int)req : lvl;
+  *first = (pref != GROVE_LEVEL_NONE && (int)pref > base) ? (int)pref : base;
+  return base;
+}
+static inline uint32_t scope_pref(const grove_scope_t* s) { return s->preferred1 ? (uint32_t)s->preferred1 - 1u : GROVE_LEVEL_NONE; }
+
 typedef struct geval {
   const ctx_t* C;
   uint32_t g;
@@ -328,13 +340,15 @@ static int place_scope(geval_t* E, const grove_scope_t* s, uint32_t lo, uint32_t
   for (uint32_t i = 0; i < s->n_cliques; ++i) {
     uint32_t cr = s->first_clique + i;
     const grove_clique_t* q = &E->C->cliques[g->clique_off + cr];
-    int ok = 0;
-    if (q->level != GROVE_LEVEL_NONE && (int)q->level > lvl) {
-      uint32_t nc; cand_t* v = subdomains(E, q->level, lo, hi, &nc);
-      for (uint32_t k = 0; k < nc && !ok; ++k) ok = fill_min(E, cr, v[k].lo, v[k].hi);
-      free(v);
-    } else {
-      ok = fill_min(E, cr, lo, hi);
+    int ok = 0, first, base = level_span(q->level, GROVE_CLIQUE_PREFERRED(q->scope), lvl, &first);
+    for (int l = first; l >= base && !ok; --l) {
+      if (l > lvl) {
+        uint32_t nc; cand_t* v = subdomains(E, (uint32_t)l, lo, hi, &nc);
+        for (uint32_t k = 0; k < nc && !ok; ++k) ok = fill_min(E, cr, v[k].lo, v[k].hi);
+        free(v);
+      } else {
+        ok = fill_min(E, cr, lo, hi);
+      }
     }
     if (!ok) { E->np = mark; return 0; }
   }
@@ -347,13 +361,15 @@ static int place_in(geval_t* E, uint32_t lo, uint32_t hi, int lvl) {
   E->np = 0;
   for (uint32_t si = 0; si < g->n_scopes; ++si) {
     const grove_scope_t* s = &C->scopes[g->scope_off + si];
-    int ok = 0;
-    if (s->level != GROVE_LEVEL_NONE && (int)s->level > lvl) {
-      uint32_t nc; cand_t* v = subdomains(E, s->level, lo, hi, &nc);
-      for (uint32_t k = 0; k < nc && !ok; ++k) ok = place_scope(E, s, v[k].lo, v[k].hi, (int)s->level);
-      free(v);
-    } else {
-      ok = place_scope(E, s, lo, hi, lvl);
+    int ok = 0, first, base = level_span(s->level, scope_pref(s), lvl, &first);
+    for (int l = first; l >= base && !ok; --l) {
+      if (l > lvl) {
+        uint32_t nc; cand_t* v = subdomains(E, (uint32_t)l, lo, hi, &nc);
+        for (uint32_t k = 0; k < nc && !ok; ++k) ok = place_scope(E, s, v[k].lo, v[k].hi, l);
+        free(v);
+      } else {
+        ok = place_scope(E, s, lo, hi, lvl);
+      }
     }
     if (!ok) { E->np = 0; return 0; }
   }
@@ -381,7 +397,9 @@ static void emit_alt(geval_t* E, const xlay_t* X, int32_t* xb, uint32_t P, uint3
 }
 
 /* one gang against the round-start state: its first K feasible gang-level domains in score order, each
- * packed independently ("alternatives"); a gang without a gang-level constraint has one candidate */
+ * packed independently ("alternatives"); a gang without a gang-level constraint has one candidate (the
+ * whole cluster).  With a Preferred level the candidate list is the Preferred level's domains in score
+ * order, then each wider level's, down to the Required level (or the whole cluster). */
 static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, const xlay_t* X, int32_t* xb, uint32_t P) {
   geval_t* E = malloc(sizeof(geval_t));
   memset(E, 0, sizeof(*E));
@@ -396,13 +414,16 @@ static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, const x
   }
   for (uint32_t cr = 0; cr < g->n_cliques; ++cr) E->Trow[cr] = Trow[cr];
   uint32_t na = 0;
-  if (g->level == GROVE_LEVEL_NONE) {
-    if (place_in(E, 0, C->T.n, -1)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, 0);
-  } else {
-    uint32_t nc; cand_t* v = subdomains(E, g->level, 0, C->T.n, &nc);
-    for (uint32_t k = 0; k < nc && na < X->K; ++k)
-      if (place_in(E, v[k].lo, v[k].hi, (int)g->level)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, v[k].lo);
-    free(v);
+  int first, base = level_span(g->level, g->preferred, -1, &first);
+  for (int l = first; l >= base && na < X->K; --l) {
+    if (l < 0) {
+      if (place_in(E, 0, C->T.n, -1)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, 0);
+    } else {
+      uint32_t nc; cand_t* v = subdomains(E, (uint32_t)l, 0, C->T.n, &nc);
+      for (uint32_t k = 0; k < nc && na < X->K; ++k)
+        if (place_in(E, v[k].lo, v[k].hi, l)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, v[k].lo);
+      free(v);
+    }
   }
   xb[X->nalt + gi] = (int32_t)na;
   free(E);
@@ -432,7 +453,7 @@ int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_cliqu
     if (g->n_scopes == 0 || g->n_scopes > GROVE_MAX_GANG_SCOPES) return GROVE_ERR_LIMIT;
     if ((uint64_t)g->clique_off + g->n_cliques > Q || (uint64_t)g->scope_off + g->n_scopes > S) return GROVE_ERR_INVALID_ARG;
     if (g->level != GROVE_LEVEL_NONE && g->level >= L) return GROVE_ERR_INVALID_ARG;
-    if (g->preferred != GROVE_LEVEL_NONE) return GROVE_ERR_INVALID_ARG;
+    if (g->preferred != GROVE_LEVEL_NONE && (g->preferred >= L || (g->level != GROVE_LEVEL_NONE && g->preferred <= g->level))) return GROVE_ERR_INVALID_ARG;
     if (g->anchor_node != GROVE_NONE_U32 && g->anchor_node >= n_nodes) return GROVE_ERR_INVALID_ARG;
     if (g->base_gang != GROVE_NONE_U32 && (g->base_gang >= G || g->base_gang == gi)) return GROVE_ERR_INVALID_ARG;
     uint32_t pods = 0, next = 0;
@@ -440,11 +461,14 @@ int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_cliqu
       const grove_scope_t* s = &scopes[g->scope_off + si];
       if (s->first_clique != next || s->n_cliques == 0) return GROVE_ERR_INVALID_ARG; /* scopes tile the gang's cliques in order */
       if (s->level != GROVE_LEVEL_NONE && s->level >= L) return GROVE_ERR_INVALID_ARG;
+      if (s->preferred1 && (s->preferred1 > L || (s->level != GROVE_LEVEL_NONE && s->preferred1 - 1u <= s->level))) return GROVE_ERR_INVALID_ARG;
       for (uint32_t i = 0; i < s->n_cliques; ++i) {
         if (next + i >= g->n_cliques) return GROVE_ERR_INVALID_ARG;
         const grove_clique_t* q = &cliques[g->clique_off + next + i];
-        if (q->scope != si) return GROVE_ERR_INVALID_ARG;
+        if (GROVE_CLIQUE_SCOPE(q->scope) != si) return GROVE_ERR_INVALID_ARG;
         if (q->level != GROVE_LEVEL_NONE && q->level >= L) return GROVE_ERR_INVALID_ARG;
+        { uint32_t qp = GROVE_CLIQUE_PREFERRED(q->scope);
+          if (qp != GROVE_LEVEL_NONE && (qp >= L || (q->level != GROVE_LEVEL_NONE && qp <= q->level))) return GROVE_ERR_INVALID_ARG; }
         if (q->replicas < q->min_replicas) return GROVE_ERR_INVALID_ARG;
         pods += q->replicas;
       }

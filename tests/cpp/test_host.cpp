@@ -183,6 +183,19 @@ static void test_encode() {
   CHECK(!be.SyncPodGang(bad));
   CHECK(be.Encode(e2e_nodes(10), &t).has_value());
   CHECK(!be.OnPodGangDelete(bad));
+  // Preferred keys (podgang.go:110-117) become Preferred levels; one that is not deeper than Required is dropped
+  PodGang pref = BuildPodGang(pcs, infos[0]); pref.Name = "zz-pref";  // rows follow the PodGang key order: after workload1-0
+  pref.Spec.Topology = TopologyConstraint{TopologyPackConstraint{std::nullopt, kLevels[2].Key}};
+  pref.Spec.TopologyConstraintGroupConfigs[0].Topology = TopologyConstraint{TopologyPackConstraint{kLevels[1].Key, kLevels[2].Key}};
+  pref.Spec.TopologyConstraintGroupConfigs[1].Topology = TopologyConstraint{TopologyPackConstraint{kLevels[2].Key, kLevels[1].Key}};
+  pref.Spec.PodGroups[0].Topology = TopologyConstraint{TopologyPackConstraint{std::nullopt, kLevels[3].Key}};
+  CHECK(!be.SyncPodGang(pref));
+  CHECK(!be.Encode(e2e_nodes(10), &t));
+  CHECK(t.gangs.size() == 2 && t.gangs[1].level == GROVE_LEVEL_NONE && t.gangs[1].preferred == 2 && t.gangs[0].preferred == GROVE_LEVEL_NONE);
+  CHECK(t.scopes[3].preferred1 == 0 && t.scopes[4].level == 1 && t.scopes[4].preferred1 == 3 && t.scopes[5].level == 2 && t.scopes[5].preferred1 == 0);
+  CHECK(GROVE_CLIQUE_SCOPE(t.cliques[5].scope) == 0 && GROVE_CLIQUE_PREFERRED(t.cliques[5].scope) == 3);
+  CHECK(GROVE_CLIQUE_SCOPE(t.cliques[6].scope) == 1 && GROVE_CLIQUE_PREFERRED(t.cliques[6].scope) == GROVE_LEVEL_NONE);
+  CHECK(!be.OnPodGangDelete(pref));
   // engine limits surface in ValidatePodCliqueSet
   PodCliqueSet big; big.Name = "big"; big.Cliques = {clq("w", 200, 200)};
   CHECK(be.ValidatePodCliqueSet(big).has_value());

@@ -11,8 +11,12 @@ FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 
 
 def _load(path):
+    """The fixtures predate the Preferred fields: their records are reinterpreted byte for byte in the
+    current layout (the bytes that became `preferred1` were reserved zeros = "none"), never rewritten."""
+    from grove_b200 import tables as T
     z = np.load(path)
-    return z, (z["gangs"], z["cliques"], z["scopes"])
+    scopes = np.ascontiguousarray(z["scopes"]).view(np.uint8).view(T.scope_dt).reshape(-1)
+    return z, (z["gangs"], z["cliques"], scopes)
 
 
 def test_fixtures_exist():

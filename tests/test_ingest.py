@@ -101,3 +101,27 @@ def test_podgang_manifest_to_tables_and_oracle(kwok, oracle):
         assert len(racks) == 1                                        # each PCSG replica in one rack
     with pytest.raises(ValueError):
         ingest.podgangs_from_manifests([_podgang("x", [("a", 1, 1, "example.com/nope")])], {}, [Z, B, R, H])
+
+
+def test_preferred_keys_become_preferred_levels(kwok, oracle):
+    """packConstraint.preferred (podgang.go:110-117) at PodGang, group-config and PodGroup level"""
+    Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
+    pg = _podgang("p", [("a", 2, 2, None), ("b", 3, 3, None), ("c", 1, 1, None)], configs=[("cfg", ("b", "c"), B)])
+    pg["spec"]["topologyConstraint"] = {"packConstraint": {"preferred": R}}
+    pg["spec"]["podgroups"][0]["topologyConstraint"] = {"packConstraint": {"preferred": H}}
+    pg["spec"]["topologyConstraintGroupConfigs"][0]["topologyConstraint"]["packConstraint"]["preferred"] = R
+    pg["spec"]["podgroups"][1]["topologyConstraint"] = {"packConstraint": {"required": R, "preferred": B}}  # not deeper: dropped
+    g, c, s, _ = ingest.podgangs_from_manifests([pg], {n: {"memory": "40Mi"} for n in "abc"}, [Z, B, R, H])
+    assert g["level"][0] == T.LEVEL_NONE and g["preferred"][0] == 2
+    assert s["level"].tolist() == [T.LEVEL_NONE, 1] and s["preferred1"].tolist() == [0, 3]
+    assert (c["scope"] & 0x1F).tolist() == [0, 1, 1] and (c["scope"] >> 5).tolist() == [4, 0, 0]
+    assert c["level"].tolist() == [T.LEVEL_NONE, 2, T.LEVEL_NONE]
+    nodes, *_ = ingest.nodes_from_manifests(kwok["manifests_e2e"][:14], [Z, B, R, H])
+    r = oracle.run_cycle(nodes, 4, g, c, s)
+    assert r["status"]["state"][0] == T.GANG_ADMITTED
+    pl = r["placements"]
+    assert len(set(pl["node"][pl["clique"] == 0])) == 1                      # a: both pods on one host
+    assert len({int(nodes["dom"][n, 2]) for n in pl["node"]}) == 1           # the gang in one rack
+    with pytest.raises(ValueError):
+        bad = _podgang("x", [("a", 1, 1, None)]); bad["spec"]["topologyConstraint"] = {"packConstraint": {"preferred": "example.com/nope"}}
+        ingest.podgangs_from_manifests([bad], {}, [Z, B, R, H])

@@ -242,8 +242,17 @@ def test_other_admit_paths_match_too(built_lib, oracle, env):
                 assert np.array_equal(e.placements(), ref["placements"])
                 assert np.array_equal(e.gang_status(), ref["status"])
                 assert np.array_equal(e.nodes(), ref["nodes_after"])
+        sys.path.insert(0, %r)
+        from test_random_parity_gpu import random_case
+        for seed in list(range(3000, 3030)) + [4000]:   # Preferred levels through the same paths
+            nodes, L, (g, c, s) = random_case(seed, big=seed >= 4000, pref=True)
+            ref = O.run_cycle(nodes, L, g, c, s, threads=4)
+            with PlacementEngine(L) as e:
+                e.load_nodes(nodes); e.submit_gangs(g, c, s); e.run_cycle()
+                assert np.array_equal(e.placements(), ref["placements"]), seed
+                assert np.array_equal(e.gang_status(), ref["status"]), seed
         print("ok")
-    ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, **env})
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
@@ -283,3 +292,39 @@ def test_edge_cases(built_lib, oracle):
     with PlacementEngine(4) as e:
         e.load_nodes(one); e.submit_gangs(g, c, s); e.run_cycle()
         assert e.gang_status()["state"][0] == T.GANG_ADMITTED and e.placements()["node"][0] == 0
+
+
+def test_preferred_levels_match_the_oracle(built_lib, oracle):
+    """the scenarios of tests/test_oracle_preferred.py (fits at the Preferred level / widens one level at a time /
+    bounded by Required / whole-cluster fallback / clique- and scope-level), many gangs competing"""
+    from grove_b200.engine import GroveError, PlacementEngine
+    A = synth.AGENT
+    clq = lambda n, **kw: dict(mem=40, min=n, class_mask=A, **kw)
+    nodes = synth.e2e_cluster(112)
+    b = T.GangTableBuilder()
+    for i in range(12):
+        b.add_gang([(None, [clq(10), clq(8)])], preferred=2, anchor=(i * 9) % 112)
+        b.add_gang([(None, [clq(15), clq(15)])], preferred=2, level=1 if i % 2 else None)
+        b.add_gang([(None, [clq(25), clq(25)])], preferred=3)
+        b.add_gang([(None, [clq(3, preferred=3), clq(4, preferred=3)]), (None, [clq(6), clq(6)], 2), (1, [clq(12), clq(12)], 2)],
+                   priority=i % 3)
+    g, c, s = b.build()
+    ref = oracle.run_cycle(nodes, synth.E2E_LEVELS, g, c, s, threads=4)
+    assert (ref["status"]["state"] == T.GANG_ADMITTED).sum() > 5 and (ref["status"]["state"] == T.GANG_REJECTED).sum() > 5
+    with PlacementEngine(synth.E2E_LEVELS) as e:
+        e.load_nodes(nodes); e.submit_gangs(g, c, s)
+        st = e.run_cycle()
+        assert st["rounds"] == ref["stats"]["rounds"]
+        assert np.array_equal(e.gang_status(), ref["status"])
+        assert np.array_equal(e.placements(), ref["placements"])
+        assert np.array_equal(e.nodes(), ref["nodes_after"])
+        for kw in (dict(level=2, preferred=2), dict(level=2, preferred=1), dict(preferred=7)):
+            bad = T.GangTableBuilder(); bad.add_gang([(None, [clq(1)])], **kw)
+            with pytest.raises(GroveError):
+                e.submit_gangs(*bad.build())
+        bad = T.GangTableBuilder(); bad.add_gang([(2, [clq(1)], 1)])
+        with pytest.raises(GroveError):
+            e.submit_gangs(*bad.build())
+        bad = T.GangTableBuilder(); bad.add_gang([(None, [clq(1, level=2, preferred=2)])])
+        with pytest.raises(GroveError):
+            e.submit_gangs(*bad.build())

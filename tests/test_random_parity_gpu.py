@@ -1,8 +1,9 @@
 """-m gpu: differential test on seeded random snapshots that mix every feature of the table format:
 ragged topologies (absent labels at any level, non-tree label sets), cordoned nodes, selector classes,
 zero / partial requests, MinReplicas = 0, surplus replicas, nested Required levels at gang / scope /
-clique, priorities, explicit anchors, base-gang chains (incl. rejected and gated bases).  Every case
-must match the oracle bit for bit."""
+clique, Preferred levels at gang / scope / clique (with and without a Required level above them),
+priorities, explicit anchors, base-gang chains (incl. rejected and gated bases).  Every case must match
+the oracle bit for bit."""
 import numpy as np
 import pytest
 
@@ -11,8 +12,15 @@ from grove_b200 import tables as T
 pytestmark = pytest.mark.gpu
 
 
-def random_case(seed, big=False):
+def random_case(seed, big=False, pref=False):
     rng = np.random.default_rng(seed)
+    prng = np.random.default_rng(seed + 1_000_003)  # Preferred levels draw from their own stream: pref=False cases never change
+
+    def preferred(req):
+        """a level deeper than the unit's own Required one (it may be shallower than the parent's: then it is moot)"""
+        lo = 0 if req is None else req + 1
+        return int(prng.integers(lo, L)) if pref and lo < L and prng.random() < 0.45 else None
+
     L = int(rng.integers(1, 5))
     n = int(rng.integers(1, 400)) if not big else int(rng.integers(1500, 4000))
     fan = [int(rng.integers(2, 9)) for _ in range(L)]
@@ -52,13 +60,14 @@ def random_case(seed, big=False):
                 pods += rep
                 gpu = int(rng.choice([0, 1, 2, 4, 8]))
                 cliques.append(dict(cpu=int(rng.choice([0, 500, 2000, 16000])), mem=int(rng.choice([0, 1024, 65536])), gpu=gpu,
-                                    min=mn, replicas=rep, level=clevel, class_mask=int(rng.choice([0xFFFF, 0x1, 0x6, 0x8]))))
-            scopes.append((slevel, cliques))
+                                    min=mn, replicas=rep, level=clevel, preferred=preferred(clevel),
+                                    class_mask=int(rng.choice([0xFFFF, 0x1, 0x6, 0x8]))))
+            scopes.append((slevel, cliques, preferred(slevel)))
         base = None
         if gi > 0 and rng.random() < (0.3 if not big else 0.05):
             base = int(rng.integers(0, gi)) if not big else int(rng.integers(max(0, gi - 50), gi))
         b.add_gang(scopes, level=glevel, priority=int(rng.integers(0, 3)), anchor=None if rng.random() < 0.5 else int(rng.integers(0, n)),
-                   base=base, gated=bool(rng.random() < 0.05))
+                   base=base, gated=bool(rng.random() < 0.05), preferred=preferred(glevel))
     return nodes, L, b.build()
 
 
@@ -102,3 +111,40 @@ def test_random_big_snapshots_hit_the_warp_per_gang_kernel(built_lib, oracle):
             assert np.array_equal(e.gang_status(), ref["status"]), seed
             assert np.array_equal(e.placements(), ref["placements"]), seed
             assert np.array_equal(e.nodes(), ref["nodes_after"]), seed
+
+
+@pytest.mark.parametrize("block", range(10))
+def test_random_snapshots_with_preferred_levels(built_lib, oracle, block):
+    """Preferred levels (podgang.go:110-117) on all three kinds of unit; includes gangs with a Preferred but no
+    Required level, whose last candidate is the whole cluster packed by the scalar evaluator."""
+    from grove_b200.engine import PlacementEngine
+    seen = 0
+    for seed in range(3000 + block * 40, 3000 + block * 40 + 40):
+        nodes, L, (g, c, s) = random_case(seed, pref=True)
+        seen += int((g["preferred"] != T.LEVEL_NONE).sum() + (s["preferred1"] != 0).sum() + ((c["scope"] >> 5) != 0).sum())
+        ref = oracle.run_cycle(nodes, L, g, c, s, threads=1)
+        with PlacementEngine(L) as e:
+            e.load_nodes(nodes); e.submit_gangs(g, c, s)
+            st = e.run_cycle()
+            assert st["rounds"] == ref["stats"]["rounds"], seed
+            assert np.array_equal(e.gang_status(), ref["status"]), seed
+            assert np.array_equal(e.placements(), ref["placements"]), seed
+            assert np.array_equal(e.nodes(), ref["nodes_after"]), seed
+    assert seen > 100
+
+
+def test_random_big_snapshots_with_preferred_levels(built_lib, oracle):
+    from grove_b200.engine import PlacementEngine
+    for seed in range(4000, 4008):
+        nodes, L, (g, c, s) = random_case(seed, big=True, pref=True)
+        ref = oracle.run_cycle(nodes, L, g, c, s, threads=8)
+        for K in (0, 1):
+            if K:
+                ref = oracle.run_cycle(nodes, L, g, c, s, threads=8, alternatives=1)
+            with PlacementEngine(L, alternatives=K) as e:
+                e.load_nodes(nodes); e.submit_gangs(g, c, s)
+                st = e.run_cycle()
+                assert st["rounds"] == ref["stats"]["rounds"], seed
+                assert np.array_equal(e.gang_status(), ref["status"]), seed
+                assert np.array_equal(e.placements(), ref["placements"]), seed
+                assert np.array_equal(e.nodes(), ref["nodes_after"]), seed
