@@ -531,11 +531,14 @@ __device__ void finish_gang(Ev& ev, uint32_t n_cliques, uint32_t& n_min) {
 
 __global__ void k_dbg_init(uint32_t* dbg, uint32_t G) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) dbg[g * 4 + 3] = GROVE_NONE_U32;
+  if (g < G) dbg[g * 8 + 3] = GROVE_NONE_U32;
 }
 
 #ifndef GROVE_ADMIT_MINBLOCKS
 #define GROVE_ADMIT_MINBLOCKS 6
+#endif
+#ifndef GROVE_ADMIT_MINBLOCKS_WIDE
+#define GROVE_ADMIT_MINBLOCKS_WIDE 1   // 8-warp CTAs (2 per SM measured no faster: these rounds wait on their slowest gang)
 #endif
 constexpr int kAdmitThreads = 128;      // throughput rounds (many gangs): 4 warps per gang
 constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps per gang
@@ -544,7 +547,7 @@ constexpr int kAdmitThreadsWide = 256;  // latency rounds (few gangs): 8 warps p
 // words + node records (no capacity tables this cycle); 2: gangs without a gang-level constraint
 // (cooperative).  Each instantiation skips the gangs of the other kind.
 template <int kThreads, int kMode, int kEnt, bool kPref>
-__global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : 1) k_admit(Topo tp, Tables tb, RoundBufs rb) {
+__global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLOCKS : GROVE_ADMIT_MINBLOCKS_WIDE) k_admit(Topo tp, Tables tb, RoundBufs rb) {
   __shared__ GangShared sh;
   __shared__ uint32_t s_en[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
   __shared__ uint16_t s_em[(kEnt && kMode != 2 ? kEnt : 1) * kThreads];
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   __syncthreads();
 
   const uint32_t K = rb.K, P = rb.P;
+  const long long dbg_t0 = rb.dbg ? clock64() : 0;
   if constexpr (kMode == 2) {
     // single candidate: the whole cluster, packed cooperatively by warp 0 (one alternative at most)
     if (warp != 0) return;
@@ -646,19 +650,23 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
     }
     uint32_t total = 0;
     for (uint32_t w = 0; w < nwarp; ++w) total += s_wcnt[w];
-    if (rb.dbg && tid == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, total); }
+    if (rb.dbg && tid == 0) { atomicAdd(rb.dbg + gi * 8 + 1, total); atomicAdd(rb.dbg + gi * 8 + 5, 1u); }
     __syncthreads();
-    for (uint32_t abase = 0; abase < total && nsucc < K;) {
-      const uint32_t width = blockDim.x;  // every plausible candidate of the chunk at once (latency rounds)
-      const uint32_t slot = tid;
+    // attempt windows: `per_warp` candidates per warp, doubling (few attempts when the first candidates succeed,
+    // a logarithmic number of windows when they do not)
+    for (uint32_t abase = 0, per_warp = rb.width1; abase < total && nsucc < K; per_warp = min(32u, per_warp * 2u)) {
+      const uint32_t width = per_warp * nwarp;
+      // compacted candidate `slot` of the window goes to warp slot % nwarp: lanes of a warp run DIFFERENT packings
+      // (divergent, serialised), so a window of w candidates costs ~w / nwarp attempts per warp, not min(w, 32)
+      const uint32_t slot = lane * nwarp + warp;
       if (tid < (kAdmitThreadsWide / 32)) s_okmask[tid] = 0;
       __syncthreads();
       bool ok = false; uint32_t k = 0, dl = 0;
-      if (slot != GROVE_NONE_U32 && abase + slot < total) {
+      if (slot < width && abase + slot < total) {
         k = s_ck[abase + slot]; dl = s_cl[abase + slot];
         ev.k = k;
         ok = place_in(ev, gg.n_scopes, dl, s_ch[abase + slot], gl);
-        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
+        if (rb.dbg) { atomicAdd(rb.dbg + gi * 8 + 2, 1u); if (ok) atomicAdd(rb.dbg + gi * 8 + 0, 1u); }
         if (ok) atomicOr(&s_okmask[slot >> 5], 1u << (slot & 31));
       }
       __syncthreads();
@@ -676,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
         rb.alt_nmin[size_t(gi) * K + srank] = n_min;
         rb.alt_top[size_t(gi) * K + srank] = dl;
-        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
+        if (rb.dbg && srank == 0) rb.dbg[gi * 8 + 3] = k;
       }
       nsucc += stot;
       abase += width;
@@ -686,6 +694,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 128 ? GROVE_ADMIT_MINBLO
   }
   } while (kPref && nsucc < K && --gl >= gbase);  // candidate levels
   if (tid == 0) rb.nalt[gi] = min(nsucc, K);
+  if (rb.dbg && tid == 0) rb.dbg[gi * 8 + 4] = uint32_t(clock64() - dbg_t0);
   }
 }
 
@@ -727,6 +736,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
   for (uint32_t si = lane; si < gg.n_scopes; si += 32) sh.scopes[si] = tb.scopes[gg.scope_off + si];
   __syncwarp();
   const uint32_t K = rb.K, P = rb.P;
+  const long long dbg_t0 = rb.dbg ? clock64() : 0;
   ScalarEv<kCaps, kEnt, kPref> ev(tp, rb, sh, g, s_en + threadIdx.x, s_em + threadIdx.x, kAdmitWarpGangs * 32);
   uint32_t nsucc = 0;
   // candidate levels: the Preferred level first (if any), widened level by level up to the Required one
@@ -759,7 +769,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       } else { dl = 0; dh = tp.n; plaus = true; }
     }
     uint32_t todo = __ballot_sync(kFull, plaus);
-    if (rb.dbg && lane == 0) { rb.dbg[gi * 4 + 0] = D; atomicAdd(rb.dbg + gi * 4 + 1, __popc(todo)); }
+    if (rb.dbg && lane == 0) { atomicAdd(rb.dbg + gi * 8 + 1, __popc(todo)); atomicAdd(rb.dbg + gi * 8 + 5, 1u); }
     bool first_window = base == 0;
     while (todo && nsucc < K) {
       // first window: a few more candidates than alternatives wanted (in an uncongested cluster nearly all
@@ -773,7 +783,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
       if ((sel >> lane) & 1u) {
         ev.k = k;
         ok = place_in(ev, gg.n_scopes, dl, dh, gl);
-        if (rb.dbg) atomicAdd(rb.dbg + gi * 4 + 2, 1u);
+        if (rb.dbg) { atomicAdd(rb.dbg + gi * 8 + 2, 1u); if (ok) atomicAdd(rb.dbg + gi * 8 + 0, 1u); }
       }
       const uint32_t sb = __ballot_sync(kFull, ok);
       const uint32_t srank = nsucc + __popc(sb & ((1u << lane) - 1u));
@@ -785,7 +795,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
         rb.alt_n[size_t(gi) * K + srank] = ev.np;
         rb.alt_nmin[size_t(gi) * K + srank] = n_min;
         rb.alt_top[size_t(gi) * K + srank] = dl;
-        if (rb.dbg && srank == 0) rb.dbg[gi * 4 + 3] = k;
+        if (rb.dbg && srank == 0) rb.dbg[gi * 8 + 3] = k;
       }
       nsucc += __popc(sb);
       __syncwarp();
@@ -793,6 +803,7 @@ __global__ void __launch_bounds__(kAdmitWarpGangs * 32, GROVE_ADMIT_MINBLOCKS) k
   }
   } while (kPref && nsucc < K && --gl >= gbase);  // candidate levels
   if (lane == 0) rb.nalt[gi] = min(nsucc, K);
+  if (rb.dbg && lane == 0) rb.dbg[gi * 8 + 4] = uint32_t(clock64() - dbg_t0);
 }
 
 }  // namespace grove

@@ -85,8 +85,9 @@ struct RoundBufs {
   const uint32_t* capsum; // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
   const uint32_t* capmax; // [S][cap_stride] per-domain max of cap8
   uint32_t caps_in_attempts;  // 1: the scalar evaluator packs from cap8 bytes, 0: from fit words + node records
-  uint32_t width0;            // candidates attempted in the very first step of a gang (1..32)
-  uint32_t* dbg;              // [G][4] optional: candidates, plausible, attempts, winning candidate
+  uint32_t width0;            // candidates attempted in the very first step of a gang (1..32), warp-per-gang form
+  uint32_t width1;            // candidates per warp in the first attempt window of the CTA-per-gang forms (1..32)
+  uint32_t* dbg;              // [G][8] optional: successes, plausible, attempts, winning candidate, cycles, chunks
 };
 
 }  // namespace grove

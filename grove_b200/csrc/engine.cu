@@ -124,6 +124,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
   uint32_t tune_width0 = 24;  // packing attempts per window in the warp-per-gang kernel
+  uint32_t tune_width1 = 32;  // packing attempts per warp in the first window of the CTA-per-gang kernels (doubles per window)
   // admission kernel form by number of active gangs: >= 10 per SM a warp per gang (gangs in flight matter),
   // >= 4 per SM a 4-warp CTA per gang, below that an 8-warp CTA per gang (latency of one gang matters)
   uint32_t tune_warp_min = 1480, tune_wide_max = 592;
@@ -275,7 +276,7 @@ static RoundBufs make_bufs(grove_engine* e) {
   }
   r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
   r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
-  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0; r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
+  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0; r.width1 = e->tune_width1; r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
 }
 
@@ -313,6 +314,8 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
+  if (const char* v = std::getenv("GROVE_TUNE_ALTERNATIVES")) if (!cfg->alternatives) e->K = uint32_t(std::min<int>(GROVE_MAX_ALTERNATIVES, std::max(1, std::atoi(v))));
+  if (const char* v = std::getenv("GROVE_TUNE_WIDTH1")) e->tune_width1 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the latency-bound admission gets the SMs first
   if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
@@ -675,7 +678,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
         e->d_capmax.ensure(tw) == cudaSuccess) e->prefilter = true;
     else (void)cudaGetLastError();
   }
-  if (e->dbg_on) CU_TRY(e, e->d_dbg.ensure(size_t(G) * 4));
+  if (e->dbg_on) CU_TRY(e, e->d_dbg.ensure(size_t(G) * 8));
   // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
   std::vector<uint8_t> st(G, GROVE_GANG_PENDING);
   for (uint32_t g = 0; g < G; ++g) if (e->gangs[g].flags & GROVE_GANG_GATED) st[g] = GROVE_GANG_GATED_SKIP;
@@ -757,7 +760,7 @@ static int32_t round_eval(grove_engine* e, bool timed) {
   }
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
-  if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 16, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
+  if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 32, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
   const bool caps = e->prefilter && e->tune_prefilter >= 2;
   const bool small = e->max_gang_pods <= kEntSmem;  // per-lane entry stacks fit the shared-memory form
   if (e->any_preferred) launch_admit<true>(e, tp, tb, rb, na, caps, small); else launch_admit<false>(e, tp, tb, rb, na, caps, small);
@@ -851,13 +854,28 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_admit += t;
     cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_commit += t;
     if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr
-      std::vector<uint32_t> h(size_t(e->G) * 4); std::vector<uint32_t> act(na);
+      std::vector<uint32_t> h(size_t(e->G) * 8); std::vector<uint32_t> act(na);
       cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
       cudaMemcpy(act.data(), e->d_active.p, na * 4, cudaMemcpyDeviceToHost);
-      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0;
-      for (uint32_t i = 0; i < na; ++i) { const uint32_t* d = &h[size_t(act[i]) * 4]; sp += d[1]; sa += d[2]; maxa = std::max<uint64_t>(maxa, d[2]); if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; } }
-      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) feasible %llu mean first feasible k %.1f\n", e->round_no, na,
-                   double(sp) / na, double(sa) / na, (unsigned long long)maxa, (unsigned long long)won, won ? double(sk) / won : 0.0);
+      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0, ss = 0, full = 0;
+      for (uint32_t i = 0; i < na; ++i) {
+        const uint32_t* d = &h[size_t(act[i]) * 8]; sp += d[1]; sa += d[2]; ss += d[0]; maxa = std::max<uint64_t>(maxa, d[2]);
+        if (d[0] >= e->K) full++;
+        if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; }
+      }
+      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) successes/gang %.1f gangs with K %llu feasible %llu mean first feasible k %.1f\n",
+                   e->round_no, na, double(sp) / na, double(sa) / na, (unsigned long long)maxa, double(ss) / na, (unsigned long long)full, (unsigned long long)won,
+                   won ? double(sk) / won : 0.0);
+      // the slowest gangs of the round (SM cycles of their admission) and what they did
+      std::vector<uint32_t> idx(na); std::iota(idx.begin(), idx.end(), 0u);
+      std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return h[size_t(act[a]) * 8 + 4] > h[size_t(act[b]) * 8 + 4]; });
+      uint64_t cyc = 0; for (uint32_t i = 0; i < na; ++i) cyc += h[size_t(act[i]) * 8 + 4];
+      std::fprintf(stderr, "  mean cycles/gang %.0f, median %u; slowest:", double(cyc) / na, h[size_t(act[idx[na / 2]]) * 8 + 4]);
+      for (uint32_t i = 0; i < std::min(na, 6u); ++i) {
+        const uint32_t g = act[idx[i]]; const uint32_t* d = &h[size_t(g) * 8];
+        std::fprintf(stderr, " [g%u lvl%u cliques%u: %u cyc, %u chunks, %u plaus, %u att, %u succ]", g, unsigned(e->gangs[g].level), unsigned(e->gangs[g].n_cliques), d[4], d[5], d[1], d[2], d[0]);
+      }
+      std::fprintf(stderr, "\n");
     }
   }
   CU_TRY(e, cudaEventRecord(e->ev[9], e->stream));

@@ -42,6 +42,7 @@ def load_library(path: str = LIB_PATH):
     """dlopen the engine.  Raises (never falls back) when the shared library has not been built."""
     global _lib
     if _lib is None:
+        path = os.environ.get("GROVE_PLACE_LIB", path)  # experiments: another build of the same sources
         if not os.path.exists(path):
             raise GroveError(-2, f"{path} not built; run `python -m grove_b200.build` (needs nvcc)")
         lib = C.CDLL(path)

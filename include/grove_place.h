@@ -51,8 +51,12 @@ extern "C" {
 #define GROVE_MAX_GANG_CLIQUES 32u
 #define GROVE_MAX_GANG_SCOPES 32u
 #define GROVE_MAX_NODES (1u << 24)
+#ifndef GROVE_MAX_ALTERNATIVES
 #define GROVE_MAX_ALTERNATIVES 8u    /* feasible placements kept per gang per round */
+#endif
+#ifndef GROVE_SUBROUNDS
 #define GROVE_SUBROUNDS 8u           /* conflict-resolution passes over the alternatives per round */
+#endif
 
 /* error codes (all entry points return 0 on success, <0 on error) */
 #define GROVE_OK 0
