@@ -315,6 +315,74 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_churn(args):
+    """--config C5 (BASELINE.json config 5, steady-state churn): the C4 cluster, 100 PodGang arrivals per 100 ms tick
+    (1 000 /s) joining the gangs still pending, ~1 % of the running gangs finishing per tick (their resources come back
+    through grove_update_nodes).  A step is one tick: update_nodes + submit_gangs + run_cycle + results to host buffers,
+    all through the C ABI with host arrays (e2e); `value` counts the cycle alone (tables already resident)."""
+    import torch
+    from grove_b200 import build
+    from grove_b200.engine import PlacementEngine
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config C5 is a single-GPU line (the churn host loop is sequential)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    build.build()
+    ch = synth.ChurnC5(n=50000, arrivals=100, release_pct=1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_tick, t_cycle, adm, launches, pend, h2d, d2h = [], [], 0, 0, [], 0, 0
+    cpu_t, cpu_adm, same = 0.0, 0, True
+    idx = recs = None
+    with PlacementEngine(ch.n_levels) as e:
+        e.load_nodes(ch.nodes)
+        for tick in range(args.warmup + args.steps):
+            specs, tabs = ch.begin_tick()
+            g, c, s = tabs
+            before = ch.nodes
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if idx is not None and len(idx):
+                e.update_nodes(idx, recs)
+            e.submit_gangs(g, c, s)
+            st = e.run_cycle()
+            pl, gs = e.placements(), e.gang_status()
+            dt = time.perf_counter() - t0
+            if tick >= args.warmup:
+                t_tick.append(dt * 1e3); t_cycle.append(st["ms_total"]); adm += st["gangs_admitted"]
+                launches += st["kernel_launches"]; pend.append(len(g))
+                h2d += g.nbytes + c.nbytes + s.nbytes + (0 if idx is None else idx.nbytes + recs.nbytes); d2h += pl.nbytes + gs.nbytes
+            if not args.no_cpu_baseline and args.warmup <= tick < args.warmup + 5:   # bounded sample: five ticks on the host cores
+                from oracle import oracle_py as O
+                tc = time.perf_counter()
+                r = O.run_cycle(before, ch.n_levels, g, c, s, threads=os.cpu_count() or 1)
+                cpu_t += time.perf_counter() - tc; cpu_adm += r["stats"]["gangs_admitted"]
+                same &= bool(np.array_equal(r["placements"], pl) and np.array_equal(r["status"], gs))
+            idx, recs = ch.end_tick(specs, tabs, gs, pl, e.nodes())
+    clocks = sampler.stop()
+    ms_tick, ms_cyc = float(np.mean(t_tick)), float(np.mean(t_cycle))
+    line = {
+        "metric": "podgang_placements_per_sec", "value": adm / (sum(t_cycle) * 1e-3), "unit": "gangs/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_cyc, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "C5: steady-state churn on the C4 cluster (50000 nodes, 4-level tree): 100 PodGang arrivals per 100 ms tick "
+                               "+ carried-over pending gangs, ~1 % of running gangs finish per tick (grove_update_nodes)",
+                   "nodes": 50000, "arrivals_per_tick": 100, "tick_budget_ms": 100.0, "pending_per_tick_mean": float(np.mean(pend)),
+                   "pending_per_tick_last": int(pend[-1]), "admitted": int(adm), "tick_ms_mean": ms_tick, "tick_ms_max": float(np.max(t_tick)),
+                   "tick_budget_used": ms_tick / 100.0, "arrivals_per_sec_sustained_at_this_latency": 100.0 / (ms_tick * 1e-3),
+                   "l2": "per tick the score matrix is cliques x 50176 B (> 126 MB L2 from ~2500 pending cliques on); inputs change every tick"},
+        "clocks": clocks,
+        "e2e": {"value": adm / (sum(t_tick) * 1e-3), "unit": "gangs/s", "ms_per_step": ms_tick,
+                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps)},
+        "gpu_launches": int(launches),
+        "roofline": None,
+        "cpu_baseline": None if args.no_cpu_baseline else {
+            "value": cpu_adm / cpu_t if cpu_t else 0.0, "unit": "gangs/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "the first five timed ticks (same inputs, C restatement on this box's host cores)", "placements_identical_to_gpu": same},
+    }
+    print(json.dumps(line))
+
+
 def eng_npad(n):
     return (n + 1023) // 1024 * 1024
 
@@ -324,17 +392,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="C4", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--config", default="C4", choices=sorted(synth.CONFIGS) + ["C5"])
     ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
+        if args.config == "C5":
+            raise SystemExit("bench.py: the C5 line times the CPU oracle itself (cpu_baseline, five ticks); --impl reference covers C1-C4")
         run_reference(args)
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_gpu(args)
+        if args.config == "C5":
+            run_churn(args)
+        else:
+            run_gpu(args)
 
 
 if __name__ == "__main__":

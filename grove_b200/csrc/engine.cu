@@ -28,10 +28,16 @@ struct DevBuf {
   size_t cap = 0;  // elements
   ~DevBuf() { release(); }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // grows geometrically: a pending set that creeps up tick after tick (churn) must not pay a cudaFree + cudaMalloc
+  // of every table per cycle; falls back to the exact size when the padded one does not fit
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
+    const size_t want = std::max<size_t>(std::max<size_t>(n, 1), cap + cap / 2);
     release();
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) { cap = want; return e; }
+    (void)cudaGetLastError();
+    e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
     if (e == cudaSuccess) cap = std::max<size_t>(n, 1); else p = nullptr;
     return e;
   }
@@ -44,10 +50,11 @@ struct PinBuf {
   ~PinBuf() { if (p) cudaFreeHost(p); }
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
+    const size_t want = std::max<size_t>(std::max<size_t>(n, 1), cap + cap / 2);
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = std::max<size_t>(n, 1); else p = nullptr;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) cap = want; else p = nullptr;
     return e;
   }
 };
@@ -132,6 +139,7 @@ struct grove_engine {
   uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
+  DevBuf<grove_node_t> d_nodes_out;  // grove_get_nodes scratch
   PinBuf<uint32_t> h_counters;
   PinBuf<grove_gang_status_t> h_status;
   PinBuf<grove_placement_t> h_out;
@@ -395,12 +403,9 @@ int32_t grove_update_nodes(grove_engine_t* e, const uint32_t* idx, const grove_n
   CU_TRY(e, e->d_upd_idx.ensure(n)); CU_TRY(e, e->d_upd_recs.ensure(n));
   CU_TRY(e, cudaMemcpyAsync(e->d_upd_idx.p, sidx.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
   CU_TRY(e, cudaMemcpyAsync(e->d_upd_recs.p, recs, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
-  k_update<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_upd_idx.p, e->d_upd_recs.p, e->d_vdepth.p, e->d_nres.p, n);
+  k_update<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_upd_idx.p, e->d_upd_recs.p, e->d_vdepth.p, e->d_perm.p, e->d_nres.p, e->d_nodes_in.p, n);
   CU_TRY(e, cudaGetLastError());
-  // keep the caller-order mirror coherent for grove_get_nodes
-  for (uint32_t i = 0; i < n; ++i)
-    CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p + idx[i], recs + i, sizeof(grove_node_t), cudaMemcpyHostToDevice, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));  // sidx is a local, recs the caller's
   return GROVE_OK;
 }
 
@@ -409,11 +414,10 @@ int32_t grove_get_nodes(grove_engine_t* e, grove_node_t* out, uint32_t cap) {
   if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
   if (cap < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  DevBuf<grove_node_t> tmp;
-  CU_TRY(e, tmp.ensure(e->N));
-  k_scatter<<<(e->N + 255) / 256, 256, 0, e->stream>>>(tmp.p, e->d_nodes_in.p, e->d_perm.p, e->d_nres.p, e->N);
+  CU_TRY(e, e->d_nodes_out.ensure(e->N));
+  k_scatter<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->d_nodes_out.p, e->d_nodes_in.p, e->d_perm.p, e->d_nres.p, e->N);
   CU_TRY(e, cudaGetLastError());
-  CU_TRY(e, cudaMemcpyAsync(out, tmp.p, sizeof(grove_node_t) * e->N, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(out, e->d_nodes_out.p, sizeof(grove_node_t) * e->N, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   return GROVE_OK;
 }

@@ -31,14 +31,18 @@ __global__ void k_scatter(grove_node_t* __restrict__ out, const grove_node_t* __
   out[c] = nd;
 }
 
+// churn deltas: new records for a few nodes (labels unchanged); also kept in the caller-order mirror that
+// grove_get_nodes scatters back
 __global__ void k_update(const uint32_t* __restrict__ idx_sorted, const grove_node_t* __restrict__ recs,
-                         const uint8_t* __restrict__ vdepth, uint4* __restrict__ nres, uint32_t m) {
+                         const uint8_t* __restrict__ vdepth, const uint32_t* __restrict__ perm, uint4* __restrict__ nres,
+                         grove_node_t* __restrict__ nodes_in, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   uint32_t s = idx_sorted[i];
   grove_node_t nd = recs[i];
   nres[s] = make_uint4(nd.free_cpu_milli, nd.free_mem_mib, uint32_t(nd.free_gpu) | (uint32_t(nd.free_pods) << 16),
                        (nd.flags & 0xFFFFu) | (uint32_t(vdepth[s]) << 16));
+  nodes_in[perm[s]] = nd;
 }
 
 // anchor ancestors: node range of the anchor's domain at every level ([a,a) where its label is absent)
