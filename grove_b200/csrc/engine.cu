@@ -59,6 +59,31 @@ struct PinBuf {
   }
 };
 
+// a host table the engine owns, in pinned memory: the caller's array is copied in once (by a few threads when it is
+// large) and the upload from it is a plain asynchronous DMA
+template <typename T>
+struct PinVec {
+  PinBuf<T> b;
+  size_t n = 0;
+  T& operator[](size_t i) { return b.p[i]; }
+  const T& operator[](size_t i) const { return b.p[i]; }
+  T* data() { return b.p; }
+  cudaError_t assign(const T* src, size_t cnt) {
+    cudaError_t e = b.ensure(cnt);
+    if (e != cudaSuccess) return e;
+    n = cnt;
+    const size_t bytes = cnt * sizeof(T);
+    // one team size for every parallel region of the engine: libgomp re-creates its thread team whenever the size changes
+    const int T_ = bytes >= (256u << 10) ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+#pragma omp parallel for num_threads(T_) schedule(static)
+    for (int t = 0; t < T_; ++t) {
+      const size_t a = bytes * t / T_, z = bytes * (t + 1) / T_;
+      std::memcpy(reinterpret_cast<char*>(b.p) + a, reinterpret_cast<const char*>(src) + a, z - a);
+    }
+    return cudaSuccess;
+  }
+};
+
 uint32_t fmix32(uint32_t x) {
   x = x * 0x9E3779B1u + 0x7F4A7C15u;
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
@@ -92,9 +117,10 @@ struct grove_engine {
 
   // ---- gang tables ----
   uint32_t G = 0, Q = 0, S = 0, P = 0;
-  std::vector<grove_gang_t> gangs;
-  std::vector<grove_clique_t> cliques;
-  std::vector<grove_scope_t> scopes;
+  PinVec<grove_gang_t> gangs;
+  PinVec<grove_clique_t> cliques;
+  PinVec<grove_scope_t> scopes;
+  PinBuf<uint8_t> h_state0;        // initial gang states of a cycle
   PinBuf<GangInfo> ginfo_pin;      // derived tables are built straight into pinned memory: their upload is a plain DMA
   PinBuf<CliqueInfo> cinfo_pin;
   GangInfo* ginfo = nullptr;
@@ -354,17 +380,28 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
   if (n == 0 || n > GROVE_MAX_NODES) return fail(e, GROVE_ERR_INVALID_ARG, "node count out of range");
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));  // an earlier upload may still be reading the staging buffer
   if (host_nodes) {
-    bool same = e->nodes_loaded && n == e->N;
-    if (same) {
-      const uint32_t* rd = e->raw_dom.data();
-      for (uint32_t i = 0; i < n && same; ++i)
-        same = std::memcmp(rd + size_t(i) * GROVE_MAX_LEVELS, host_nodes[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS) == 0;
-    }
-    if (!same) { int32_t rc = build_topology(e, host_nodes, n); if (rc) return rc; }
     CU_TRY(e, e->d_nodes_in.ensure(n));
     CU_TRY(e, e->h_stage_nodes.ensure(n));
-    std::memcpy(e->h_stage_nodes.p, host_nodes, sizeof(grove_node_t) * n);  // caller buffer is not retained
+    // one pass over the caller's snapshot by a few threads: copy to the pinned staging buffer (the caller's array is
+    // not retained) and compare the labels with the cached topology's
+    const bool cached = e->nodes_loaded && n == e->N;
+    const int T = n >= 8192 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+    int differs = 0;
+#pragma omp parallel for num_threads(T) schedule(static) reduction(| : differs)
+    for (int t = 0; t < T; ++t) {
+      const uint32_t a = uint32_t(uint64_t(n) * t / T), z = uint32_t(uint64_t(n) * (t + 1) / T);
+      std::memcpy(e->h_stage_nodes.p + a, host_nodes + a, sizeof(grove_node_t) * (z - a));
+      if (cached) {
+        const uint32_t* rd = e->raw_dom.data();
+        int d = 0;
+        for (uint32_t i = a; i < z; ++i)
+          d |= std::memcmp(rd + size_t(i) * GROVE_MAX_LEVELS, host_nodes[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS) != 0;
+        differs |= d;
+      }
+    }
+    if (!cached || differs) { int32_t rc = build_topology(e, host_nodes, n); if (rc) return rc; }
     CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p, e->h_stage_nodes.p, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
   } else {
     if (!e->nodes_loaded || n != e->N) return fail(e, GROVE_ERR_STATE, "device load needs a prior host load with the same labels");
@@ -372,7 +409,7 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
   }
   k_gather<<<(e->Npad + 255) / 256, 256, 0, e->stream>>>(e->d_nodes_in.p, e->d_perm.p, e->d_vdepth.p, e->d_nres.p, e->N, e->Npad);
   CU_TRY(e, cudaGetLastError());
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (dev_nodes) CU_TRY(e, cudaStreamSynchronize(e->stream));  // the caller's device buffer is free again on return
   e->nodes_loaded = true;
   return GROVE_OK;
 }
@@ -488,10 +525,11 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   int32_t rc = validate(e, gangs, n_gangs, cliques, n_cliques, scopes, n_scopes);
   if (rc) return rc;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));  // an earlier upload may still be reading the pinned tables
   e->G = n_gangs; e->Q = n_cliques; e->S = n_scopes;
-  e->gangs.assign(gangs, gangs + n_gangs);
-  e->cliques.assign(cliques, cliques + n_cliques);
-  e->scopes.assign(scopes, scopes + n_scopes);
+  CU_TRY(e, e->gangs.assign(gangs, n_gangs));
+  CU_TRY(e, e->cliques.assign(cliques, n_cliques));
+  CU_TRY(e, e->scopes.assign(scopes, n_scopes));
   e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
   e->n_constrained = e->n_unconstrained = 0;
   bool pref = false;
@@ -506,8 +544,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   if (n_gangs) CU_TRY(e, cudaMemcpyAsync(e->d_gangs.p, e->gangs.data(), sizeof(grove_gang_t) * n_gangs, cudaMemcpyHostToDevice, e->stream));
   if (n_cliques) CU_TRY(e, cudaMemcpyAsync(e->d_cliques.p, e->cliques.data(), sizeof(grove_clique_t) * n_cliques, cudaMemcpyHostToDevice, e->stream));
   if (n_scopes) CU_TRY(e, cudaMemcpyAsync(e->d_scopes.p, e->scopes.data(), sizeof(grove_scope_t) * n_scopes, cudaMemcpyHostToDevice, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  return GROVE_OK;
+  return GROVE_OK;  // the uploads read engine-owned pinned memory: nothing of the caller's is referenced any more
 }
 
 // derived per-gang / per-clique tables: order rank, anchor (sorted index + ancestor ranges), entry slots
@@ -516,8 +553,15 @@ static int32_t build_ginfo(grove_engine* e) {
   const auto t_b0 = std::chrono::steady_clock::now();
   CU_TRY(e, e->ginfo_pin.ensure(G)); CU_TRY(e, e->cinfo_pin.ensure(Q));
   e->ginfo = e->ginfo_pin.p; e->cinfo = e->cinfo_pin.p;
-  std::memset(e->ginfo, 0, sizeof(GangInfo) * G);
-  std::memset(e->cinfo, 0xFF, sizeof(CliqueInfo) * Q);  // gang == NONE marks a row no gang owns yet
+  {  // ginfo zeroed, cinfo all-ones (gang == NONE marks a row no gang owns yet), by the engine's thread team
+    const int T0 = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+#pragma omp parallel for num_threads(T0) schedule(static)
+    for (int t = 0; t < T0; ++t) {
+      const size_t g0 = size_t(G) * t / T0, g1 = size_t(G) * (t + 1) / T0, q0 = size_t(Q) * t / T0, q1 = size_t(Q) * (t + 1) / T0;
+      std::memset(e->ginfo + g0, 0, sizeof(GangInfo) * (g1 - g0));
+      std::memset(e->cinfo + q0, 0xFF, sizeof(CliqueInfo) * (q1 - q0));
+    }
+  }
   e->sigs.clear();
   // order rank = position by (priority desc, index asc): a stable bucket pass over the distinct priorities
   std::vector<uint32_t> ord(G);
@@ -684,13 +728,13 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   }
   if (e->dbg_on) CU_TRY(e, e->d_dbg.ensure(size_t(G) * 8));
   // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
-  std::vector<uint8_t> st(G, GROVE_GANG_PENDING);
-  for (uint32_t g = 0; g < G; ++g) if (e->gangs[g].flags & GROVE_GANG_GATED) st[g] = GROVE_GANG_GATED_SKIP;
-  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_state.p, st.data(), G, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, e->h_state0.ensure(G));
+  uint8_t* st = e->h_state0.p;   // rewritten only by the next cycle_begin, long after this upload has been consumed
+  for (uint32_t g = 0; g < G; ++g) st[g] = (e->gangs[g].flags & GROVE_GANG_GATED) ? GROVE_GANG_GATED_SKIP : GROVE_GANG_PENDING;
+  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_state.p, st, G, cudaMemcpyHostToDevice, e->stream));
   if (G) CU_TRY(e, cudaMemsetAsync(e->d_round.p, 0, G, e->stream));
   if (G) CU_TRY(e, cudaMemsetAsync(e->d_spec_n.p, 0, sizeof(uint16_t) * G, e->stream));
   if (e->n_sigs) CU_TRY(e, cudaMemsetAsync(e->d_sig_stamp.p, 0, sizeof(uint32_t) * e->n_sigs, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));  // st is a local
   e->round_no = 0; e->pairs = 0; e->launches = 0; e->in_cycle = true; e->have_results = false;
   std::memset(&e->last, 0, sizeof(e->last));
   return GROVE_OK;
