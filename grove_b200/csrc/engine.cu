@@ -59,6 +59,19 @@ struct PinBuf {
   }
 };
 
+// Size of the engine's host thread team (table validation, signature interning, staging copies).  One size for every
+// parallel region: libgomp re-creates its team whenever the size changes.  Not taken from OMP_NUM_THREADS: launchers
+// such as torchrun export OMP_NUM_THREADS=1 for every rank, which would serialise the per-cycle host work; the knob is
+// GROVE_HOST_THREADS (default 8), capped by the processors this process may run on.
+int host_threads() {
+  static const int t = [] {
+    int want = 8;
+    if (const char* v = std::getenv("GROVE_HOST_THREADS")) want = std::atoi(v);
+    return std::max(1, std::min(want, omp_get_num_procs()));
+  }();
+  return t;
+}
+
 // a host table the engine owns, in pinned memory: the caller's array is copied in once (by a few threads when it is
 // large) and the upload from it is a plain asynchronous DMA
 template <typename T>
@@ -74,7 +87,7 @@ struct PinVec {
     n = cnt;
     const size_t bytes = cnt * sizeof(T);
     // one team size for every parallel region of the engine: libgomp re-creates its thread team whenever the size changes
-    const int T_ = bytes >= (256u << 10) ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+    const int T_ = bytes >= (256u << 10) ? host_threads() : 1;
 #pragma omp parallel for num_threads(T_) schedule(static)
     for (int t = 0; t < T_; ++t) {
       const size_t a = bytes * t / T_, z = bytes * (t + 1) / T_;
@@ -387,7 +400,7 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
     // one pass over the caller's snapshot by a few threads: copy to the pinned staging buffer (the caller's array is
     // not retained) and compare the labels with the cached topology's
     const bool cached = e->nodes_loaded && n == e->N;
-    const int T = n >= 8192 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+    const int T = n >= 8192 ? host_threads() : 1;
     int differs = 0;
 #pragma omp parallel for num_threads(T) schedule(static) reduction(| : differs)
     for (int t = 0; t < T; ++t) {
@@ -505,7 +518,7 @@ static const char* validate_gang(const grove_engine* e, const grove_gang_t* gang
 static int32_t validate(grove_engine* e, const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
                         const grove_scope_t* scopes, uint32_t S) {
   uint32_t first_bad = GROVE_NONE_U32;
-  const int T = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+  const int T = G >= 2048 ? host_threads() : 1;
 #pragma omp parallel for num_threads(T) schedule(static) reduction(min : first_bad)
   for (uint32_t gi = 0; gi < G; ++gi) {
     int32_t code;
@@ -554,7 +567,7 @@ static int32_t build_ginfo(grove_engine* e) {
   CU_TRY(e, e->ginfo_pin.ensure(G)); CU_TRY(e, e->cinfo_pin.ensure(Q));
   e->ginfo = e->ginfo_pin.p; e->cinfo = e->cinfo_pin.p;
   {  // ginfo zeroed, cinfo all-ones (gang == NONE marks a row no gang owns yet), by the engine's thread team
-    const int T0 = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+    const int T0 = G >= 2048 ? host_threads() : 1;
 #pragma omp parallel for num_threads(T0) schedule(static)
     for (int t = 0; t < T0; ++t) {
       const size_t g0 = size_t(G) * t / T0, g1 = size_t(G) * (t + 1) / T0, q0 = size_t(Q) * t / T0, q1 = size_t(Q) * (t + 1) / T0;
@@ -625,7 +638,7 @@ static int32_t build_ginfo(grove_engine* e) {
       return tab[h][5];
     }
   };
-  const int T = G >= 2048 ? std::max(1, std::min(8, omp_get_max_threads())) : 1;
+  const int T = G >= 2048 ? host_threads() : 1;
   std::vector<SigTab> local(T);
   std::vector<uint32_t> gang_pods(G, 0);
   int shared_rows = 0;
