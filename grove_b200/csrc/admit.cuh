@@ -147,6 +147,7 @@ struct CoopEv {
           const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
           const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
           const uint32_t tincl = warp_incl_scan(t, lane);
+          __syncwarp();  // every lane's cap_now scan of the entry stack (which may read one slot ahead) is over before it grows
           if (t) {
             const uint16_t meta = uint16_t(cr);
             const uint32_t pos = np + tincl - t;
@@ -193,6 +194,7 @@ struct CoopEv {
           const bool mine = (bits >> lane) & 1u;
           const uint32_t c = mine ? cap_now(cr, n) : 0u;
           const uint32_t okb = __ballot_sync(kFull, mine && c >= m);
+          __syncwarp();
           if (okb) {
             const uint32_t nn = ((wb + src) << 5) + (__ffs(okb) - 1);
             const uint16_t meta = uint16_t(cr);

@@ -8,6 +8,15 @@ for cfg in (synth.config_c3(n=756, g=120), synth.config_c2(n=200, g=30), synth.c
     g, c, s = cfg["tables"]
     with PlacementEngine(cfg["n_levels"]) as e:
         e.load_nodes(cfg["nodes"]); e.submit_gangs(g, c, s); st = e.run_cycle(); print(st["rounds"], st["gangs_admitted"])
+        import numpy as np
+        idx = np.arange(0, len(cfg["nodes"]), 7, dtype=np.uint32)   # churn path: update a few nodes, read the table back
+        e.update_nodes(idx, cfg["nodes"][idx]); e.nodes(); e.submit_gangs(g, c, s); e.run_cycle()
+sys.path.insert(0, 'tests')
+from test_random_parity_gpu import random_case
+for seed in (3001, 3007, 3012):   # Preferred levels at gang / scope / clique, incl. the whole-cluster fallback
+    nodes, L, (g, c, s) = random_case(seed, pref=True)
+    with PlacementEngine(L) as e:
+        e.load_nodes(nodes); e.submit_gangs(g, c, s); st = e.run_cycle(); print("pref", st["rounds"], st["gangs_admitted"])
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
