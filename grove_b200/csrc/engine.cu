@@ -674,11 +674,10 @@ static int32_t build_ginfo(grove_engine* e) {
   for (int t = 0; t < T; ++t) { remap[t].resize(local[t].keys.size()); for (size_t k = 0; k < local[t].keys.size(); ++k) remap[t][k] = global.intern(local[t].keys[k]); }
   e->sigs.resize(global.keys.size());
   for (size_t k = 0; k < global.keys.size(); ++k) { const auto& key = global.keys[k]; e->sigs[k] = make_uint4(key[0], key[1], key[2], key[3] | (key[4] << 16)); }
-  if (T > 1 || true) {
+  // thread-local signature ids -> global ids (pad carried the id of the thread that interned the row)
 #pragma omp parallel for num_threads(T) schedule(static)
-    for (uint32_t qi = 0; qi < Q; ++qi)
-      if (e->cinfo[qi].gang != GROVE_NONE_U32) { e->cinfo[qi].sig = remap[e->cinfo[qi].pad][e->cinfo[qi].sig]; e->cinfo[qi].pad = 0; }
-  }
+  for (uint32_t qi = 0; qi < Q; ++qi)
+    if (e->cinfo[qi].gang != GROVE_NONE_U32) { e->cinfo[qi].sig = remap[e->cinfo[qi].pad][e->cinfo[qi].sig]; e->cinfo[qi].pad = 0; }
   uint32_t pod_off = 0;
   e->max_gang_pods = 0;
   for (uint32_t gi = 0; gi < G; ++gi) { e->ginfo[gi].pod_off = pod_off; pod_off += gang_pods[gi]; e->max_gang_pods = std::max(e->max_gang_pods, gang_pods[gi]); }
