@@ -174,7 +174,11 @@ Err GpuBackend::SyncPodGang(const PodGang& podGang) {
   pending_[podGang.Namespace + "/" + podGang.Name] = podGang;  // a copy: the cache-owned object is neither mutated nor retained
   return std::nullopt;
 }
-Err GpuBackend::OnPodGangDelete(const PodGang& podGang) { pending_.erase(podGang.Namespace + "/" + podGang.Name); return std::nullopt; }
+Err GpuBackend::OnPodGangDelete(const PodGang& podGang) {
+  const std::string key = podGang.Namespace + "/" + podGang.Name;
+  pending_.erase(key); bound_.erase(key);
+  return std::nullopt;
+}
 
 Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
   *out = Tables{};
@@ -223,20 +227,42 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     if (*pref != GROVE_LEVEL_NONE && *lvl != GROVE_LEVEL_NONE && *pref <= *lvl) *pref = GROVE_LEVEL_NONE;
     return std::nullopt;
   };
-  std::map<std::string, uint32_t> row;  // PodGang key -> gang row
-  for (const auto& kv : pending_) row.emplace(kv.first, uint32_t(row.size()));
+  // Row order: PodGangs that still have to get their minimum (key order), then the REMAINDERS of scheduled PodGangs:
+  // pods that found no node when the gang was admitted stay Pending and are retried with MinReplicas 0 (the gang
+  // guarantee is met), after everybody's minimum -- what the e2e suites wait for step by step
+  // (gang_scheduling_test.go GS5-GS12).  A remainder carries no placement of its own, so it is only resubmitted for
+  // PodGangs without pack constraints (with constraints its pods would have to rejoin the domains chosen earlier).
+  auto constrained = [](const PodGang& pg) {
+    auto has = [](const std::optional<TopologyConstraint>& tc) { return tc && tc->PackConstraint && (tc->PackConstraint->Required || tc->PackConstraint->Preferred); };
+    if (has(pg.Spec.Topology)) return true;
+    for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) if (has(gc.Topology)) return true;
+    for (const auto& p : pg.Spec.PodGroups) if (has(p.Topology)) return true;
+    return false;
+  };
+  std::vector<const std::string*> order;
+  for (const auto& kv : pending_) if (!bound_.count(kv.first)) order.push_back(&kv.first);
+  const size_t nFull = order.size();
+  for (const auto& kv : pending_) if (bound_.count(kv.first) && !constrained(kv.second)) order.push_back(&kv.first);
+  std::map<std::string, uint32_t> row;  // PodGang key -> gang row (PodGangs still to be scheduled only: what a base_gang can name)
+  for (size_t i = 0; i < nFull; ++i) row.emplace(*order[i], uint32_t(i));
   std::map<std::string, uint32_t> nodeIndex;
   for (size_t i = 0; i < nodes.size(); ++i) nodeIndex[nodes[i].Name] = uint32_t(i);
-  for (const auto& [key, pg] : pending_) {
+  for (size_t oi = 0; oi < order.size(); ++oi) {
+    const std::string& key = *order[oi];
+    const PodGang& pg = pending_.at(key);
+    const bool remainder = oi >= nFull;
+    const std::vector<uint32_t>* done = remainder ? &bound_.at(key) : nullptr;   // pods already bound, per PodGroup
     grove_gang_t g{};
     g.clique_off = uint32_t(out->cliques.size()); g.scope_off = uint32_t(out->scopes.size());
     g.anchor_node = GROVE_NONE_U32; g.base_gang = GROVE_NONE_U32; g.preferred = GROVE_LEVEL_NONE;
     g.flags = pg.Gated ? GROVE_GANG_GATED : 0;
     if (auto e = levelOf(pg.Spec.Topology, &g.level, &g.preferred)) return e;
     if (auto it = priorityClasses_.find(pg.Spec.PriorityClassName); it != priorityClasses_.end()) g.priority = it->second;
-    if (!pg.BasePodGangName.empty())
+    if (!remainder && !pg.BasePodGangName.empty())   // a base that is already scheduled gates nothing
       if (auto it = row.find(pg.Namespace + "/" + pg.BasePodGangName); it != row.end()) g.base_gang = it->second;
-    if (pg.Spec.ReuseReservationRef) {  // locality hint: score distance against where that PodGang was placed
+    if (remainder) {  // stay close to where the gang landed
+      if (auto it = lastNode_.find(key); it != lastNode_.end()) if (auto nt = nodeIndex.find(it->second); nt != nodeIndex.end()) g.anchor_node = nt->second;
+    } else if (pg.Spec.ReuseReservationRef) {  // locality hint: score distance against where that PodGang was placed
       auto it = lastNode_.find(pg.Spec.ReuseReservationRef->Namespace + "/" + pg.Spec.ReuseReservationRef->Name);
       if (it != lastNode_.end()) if (auto nt = nodeIndex.find(it->second); nt != nodeIndex.end()) g.anchor_node = nt->second;
     }
@@ -246,7 +272,8 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     struct ScopeRows { uint8_t first, pref; std::vector<uint32_t> second; };  // (Required level, Preferred level, PodGroup indices)
     std::vector<ScopeRows> scopes;
     std::vector<uint32_t> loose;
-    for (uint32_t i = 0; i < pg.Spec.PodGroups.size(); ++i) if (!grouped.count(pg.Spec.PodGroups[i].Name)) loose.push_back(i);
+    auto left = [&](uint32_t i) { return pg.Spec.PodGroups[i].PodReferences.size() - (done ? (*done)[i] : 0u); };
+    for (uint32_t i = 0; i < pg.Spec.PodGroups.size(); ++i) if (!grouped.count(pg.Spec.PodGroups[i].Name) && (!remainder || left(i))) loose.push_back(i);
     if (!loose.empty()) scopes.push_back({uint8_t(GROVE_LEVEL_NONE), uint8_t(GROVE_LEVEL_NONE), loose});
     for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) {
       uint8_t lvl, pref; if (auto e = levelOf(gc.Topology, &lvl, &pref)) return e;
@@ -254,7 +281,8 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
       for (const auto& n : gc.PodGroupNames) {
         auto it = std::find_if(pg.Spec.PodGroups.begin(), pg.Spec.PodGroups.end(), [&n](const PodGroup& p) { return p.Name == n; });
         if (it == pg.Spec.PodGroups.end()) return mkerr("ERR_SYNC_PODGANG", "Encode", "group config " + gc.Name + " names unknown PodGroup " + n);
-        members.push_back(uint32_t(it - pg.Spec.PodGroups.begin()));
+        const uint32_t gi = uint32_t(it - pg.Spec.PodGroups.begin());
+        if (!remainder || left(gi)) members.push_back(gi);
       }
       if (!members.empty()) scopes.push_back({lvl, pref, members});
     }
@@ -272,6 +300,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
         if (p.MinReplicas < 0 || p.MinReplicas > 255 || p.PodReferences.size() > 255 || size_t(p.MinReplicas) > p.PodReferences.size())
           return mkerr("ERR_SYNC_PODGANG", "Encode", "PodGroup " + p.Name + ": MinReplicas / PodReferences out of range");
         c.min_replicas = uint8_t(p.MinReplicas); c.replicas = uint8_t(p.PodReferences.size());
+        if (remainder) { c.min_replicas = 0; c.replicas = uint8_t(left(gi)); }
         uint8_t cpref;
         if (auto e = levelOf(p.Topology, &c.level, &cpref)) return e;
         c.scope = GROVE_CLIQUE_SCOPE_PREF(uint32_t(si), cpref);
@@ -287,6 +316,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
         c.class_mask = mask;
         out->cliques.push_back(c);
         out->cliqueOf.push_back({uint32_t(out->gangs.size()), gi});
+        out->refBase.push_back(done ? (*done)[gi] : 0u);
         pods += c.replicas; ++rel;
       }
     }
@@ -295,6 +325,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     g.n_cliques = uint16_t(rel); g.n_scopes = uint16_t(scopes.size());
     out->gangs.push_back(g);
     out->gangNames.push_back(key);
+    out->remainder.push_back(remainder ? 1 : 0);
   }
   return std::nullopt;
 }
@@ -327,7 +358,7 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
     const auto [grow, pgi] = t.cliqueOf[pl[i].clique];
     const PodGang& pg = pending_.at(t.gangNames[grow]);
     const PodGroup& grp = pg.Spec.PodGroups[pgi];
-    const NamespacedName& pod = grp.PodReferences[seen[pl[i].clique]++];
+    const NamespacedName& pod = grp.PodReferences[t.refBase[pl[i].clique] + seen[pl[i].clique]++];
     bindings->push_back({pod.Namespace, pod.Name, nodes[pl[i].node].Name});
   }
   for (size_t g = 0; g < gs.size(); ++g) {
@@ -335,7 +366,7 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
     switch (gs[g].state) {
       case GROVE_GANG_ADMITTED:
         s.Phase = PodGangPhase::Starting; s.Scheduled = true;
-        s.PlacementScore = double(gs[g].score_num) / double(gs[g].score_den);
+        if (!t.remainder[g]) s.PlacementScore = double(gs[g].score_num) / double(gs[g].score_den);  // a remainder re-reports no score
         break;
       case GROVE_GANG_REJECTED: s.ScheduledReason = "Unschedulable"; break;
       case GROVE_GANG_BASE_REJECTED: s.ScheduledReason = "BaseNotScheduled"; break;
@@ -344,12 +375,19 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
     }
     (*statuses)[t.gangNames[g]] = s;
   }
-  // scheduled PodGangs leave the pending set; remember where they landed for ReuseReservationRef hints
-  for (uint32_t i = 0, at = 0; i < gs.size(); ++i) {
+  // a scheduled PodGang leaves the pending set once every PodReference is bound; until then its unbound pods are retried
+  // as a remainder (Encode).  Remember where gangs landed for ReuseReservationRef hints.
+  for (uint32_t i = 0; i < gs.size(); ++i) {
     if (gs[i].state != GROVE_GANG_ADMITTED) continue;
-    if (gs[i].n_pods) lastNode_[t.gangNames[i]] = nodes[pl[gs[i].placement_off].node].Name;
-    pending_.erase(t.gangNames[i]);
-    (void)at;
+    const std::string& key = t.gangNames[i];
+    const PodGang& pg = pending_.at(key);
+    if (gs[i].n_pods && !lastNode_.count(key)) lastNode_[key] = nodes[pl[gs[i].placement_off].node].Name;
+    std::vector<uint32_t>& done = bound_[key];
+    done.resize(pg.Spec.PodGroups.size(), 0u);
+    for (uint32_t c = t.gangs[i].clique_off; c < t.gangs[i].clique_off + t.gangs[i].n_cliques; ++c) done[t.cliqueOf[c].second] += seen[c];
+    bool all = true;
+    for (size_t k = 0; k < done.size(); ++k) all &= done[k] >= pg.Spec.PodGroups[k].PodReferences.size();
+    if (all) { pending_.erase(key); bound_.erase(key); }
   }
   return std::nullopt;
 }

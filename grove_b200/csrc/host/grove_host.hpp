@@ -164,6 +164,8 @@ struct Tables {
   std::vector<grove_scope_t> scopes;
   std::vector<std::string> gangNames;                 // row -> PodGang "<ns>/<name>"
   std::vector<std::pair<uint32_t, uint32_t>> cliqueOf; // clique row -> (gang row, PodGroup index in Spec.PodGroups)
+  std::vector<uint8_t> remainder;                       // gang row -> 1: unbound pods of an already scheduled PodGang (MinReplicas 0)
+  std::vector<uint32_t> refBase;                        // clique row -> first PodReference its placement entries bind (remainders)
 };
 
 // The `gpu` scheduler backend: the third case of newBackendForProfile (manager/manager.go:35-52).
@@ -188,7 +190,8 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   // one scheduling cycle: Encode -> grove_load_nodes / submit / run_cycle -> bindings + PodGang statuses
   Err RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* bindings, std::map<std::string, PodGangStatus>* statuses,
                grove_cycle_stats_t* stats = nullptr);
-  size_t Pending() const { return pending_.size(); }
+  size_t Pending() const { return pending_.size(); }       // PodGangs with unbound pods (unscheduled, or scheduled with a remainder)
+  size_t Unscheduled() const { return pending_.size() - bound_.size(); }
   void SetPriorityClass(const std::string& name, int32_t value) { priorityClasses_[name] = value; }
 
  private:
@@ -198,6 +201,7 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   std::map<std::string, PodGang> pending_;   // "<ns>/<name>" -> copy (the cache-owned object is never retained)
   std::map<std::string, int32_t> priorityClasses_;
   std::map<std::string, std::string> lastNode_;  // scheduled PodGang -> a node it landed on (ReuseReservationRef hint)
+  std::map<std::string, std::vector<uint32_t>> bound_;  // scheduled PodGang still pending with unbound pods -> pods bound per PodGroup
   grove_engine_t* engine_ = nullptr;
   uint32_t engineLevels_ = 0;
 };

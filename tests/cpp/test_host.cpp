@@ -241,12 +241,42 @@ static void test_gpu_cycles() {
   for (auto& kv : racksOfReplica) CHECK(kv.second.size() == 1);  // every PCSG replica in one rack
 }
 
+// GS5 + GS7 shape (gang_scheduling_test.go:277-285, 449-465) through the backend: workload2 (every minAvailable 1) while
+// nodes are uncordoned step by step.  Pods of a scheduled PodGang that found no node stay pending and are retried.
+static void test_gpu_min_replicas_then_remainder() {
+  GpuBackend be;
+  CHECK(!be.SyncTopology(kLevels));
+  CHECK(!be.Init());
+  PodCliqueSet pcs; pcs.Name = "workload2";
+  PodGang::Requests rq; rq.mem_mib = 80; rq.nodeSelector = {{"node_role.e2e.grove.nvidia.com", "agent"}}; rq.tolerationKeys = {"node_role.e2e.grove.nvidia.com"};
+  for (auto [n, r] : std::vector<std::pair<const char*, int>>{{"pc-a", 2}, {"pc-b", 1}, {"pc-c", 3}}) { auto c = clq(n, r, 1); c.Requests = rq; pcs.Cliques.push_back(c); }
+  pcs.PodCliqueScalingGroupConfigs = {sg("sg-x", 2, 1, {"pc-b", "pc-c"})};
+  std::vector<PodGangInfo> infos; CHECK(!ComputeExpectedPodGangs(pcs, kLevels, true, &infos));
+  CHECK(infos.size() == 2);   // base (pc-a + sg-x-0) and the scaled gang of sg-x-1
+  for (const auto& i : infos) CHECK(!be.SyncPodGang(BuildPodGang(pcs, i)));
+  std::map<std::string, std::string> podNode;   // every binding so far
+  auto cycle = [&](int cordoned) {
+    auto nodes = e2e_nodes(14, cordoned);
+    for (const auto& kv : podNode) for (auto& nd : nodes) if (nd.Name == kv.second) { nd.used_mem_mib += 80; nd.used_pods += 1; }
+    std::vector<Binding> b; std::map<std::string, PodGangStatus> st;
+    CHECK(!be.RunCycle(nodes, &b, &st));
+    for (const auto& x : b) { CHECK(!podNode.count(x.PodName)); podNode[x.PodName] = x.NodeName; }
+    return b.size();
+  };
+  CHECK(cycle(12) == 0 && be.Unscheduled() == 2);                 // 2 free nodes < 3 = sum of the base gang's MinReplicas
+  CHECK(cycle(11) == 3 && be.Unscheduled() == 1 && be.Pending() == 2);   // base scheduled with exactly its minimum; 3 of its pods wait
+  CHECK(cycle(9) == 2 && be.Unscheduled() == 0 && be.Pending() == 2);    // the scaled gang's minimum (pc-b 1 + pc-c 1) goes before anyone's surplus
+  CHECK(cycle(4) == 5 && be.Pending() == 0);                             // the five pods left over, as remainders
+  std::set<std::string> nodes; for (const auto& kv : podNode) nodes.insert(kv.second);
+  CHECK(podNode.size() == 10 && nodes.size() == 10);
+}
+
 int main(int argc, char** argv) {
   const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
   test_compute_expected_podgangs();
   test_topology_constraints();
   test_encode();
-  if (gpu) test_gpu_cycles();
+  if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); }
   else {  // without a CUDA device Init must fail loudly, never fall back
     GpuBackend be; be.SyncTopology(kLevels);
     auto e = be.Init();

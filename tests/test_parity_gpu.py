@@ -328,3 +328,21 @@ def test_preferred_levels_match_the_oracle(built_lib, oracle):
         bad = T.GangTableBuilder(); bad.add_gang([(None, [clq(1, level=2, preferred=2)])])
         with pytest.raises(GroveError):
             e.submit_gangs(*bad.build())
+
+
+def test_e2e_sequences_match_the_oracle_step_by_step(built_lib, oracle):
+    """the reference's multi-step suites (tests/test_oracle_e2e_sequences.py: GS2-GS12) through the engine: every
+    scheduling pass of every scenario must equal the oracle's, and the pod counts must be the suites'"""
+    from grove_b200.engine import PlacementEngine
+    from test_oracle_e2e_sequences import GS, replay
+    with PlacementEngine(synth.E2E_LEVELS) as e:
+        def place(nodes, g, c, s):
+            ref = oracle.run_cycle(nodes, synth.E2E_LEVELS, g, c, s)
+            e.load_nodes(nodes); e.submit_gangs(g, c, s); e.run_cycle()
+            out = dict(status=e.gang_status(), placements=e.placements(), nodes_after=e.nodes())
+            for k in out:
+                assert np.array_equal(out[k], ref[k]), k
+            return out
+        for name in GS:
+            sim = replay(place, GS[name])
+            assert sim.running() == sim.pods(), name
