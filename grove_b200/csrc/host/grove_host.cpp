@@ -158,7 +158,45 @@ std::pair<bool, std::string> GpuBackend::CheckTopologyDrift(const std::vector<To
   return {true, ""};
 }
 
+std::vector<FieldError> ValidateHierarchicalTopologyConstraints(const PodCliqueSet& pcs, const std::vector<std::string>& domains) {
+  std::vector<FieldError> errs;
+  auto index = [&domains](const std::string& d) { auto it = std::find(domains.begin(), domains.end(), d); return it == domains.end() ? -1 : int(it - domains.begin()); };
+  auto violation = [&index](const std::string& parent, const std::string& child) {   // hasHierarchyViolation :195-202
+    const int p = index(parent), c = index(child);
+    return p != -1 && c != -1 && p > c;
+  };
+  auto msg = [](const std::string& pd, const std::string& pkind, const std::string& pname, const std::string& cd, const std::string& ckind, const std::string& cname) {
+    const std::string who = pname.empty() ? pkind : pkind + " '" + pname + "'";
+    return who + " topology constraint domain '" + pd + "' is narrower than " + ckind + " '" + cname + "' topology constraint domain '" + cd + "'";
+  };
+  const std::string root = "spec.template";
+  if (pcs.Topology) {
+    const std::string& pd = pcs.Topology->packDomain;
+    for (const auto& c : pcs.Cliques)
+      if (c.Topology && violation(pd, c.Topology->packDomain))
+        errs.push_back({root + ".topologyConstraint", msg(pd, "PodCliqueSet", "", c.Topology->packDomain, "PodClique", c.Name)});
+    for (const auto& g : pcs.PodCliqueScalingGroupConfigs)
+      if (g.Topology && violation(pd, g.Topology->packDomain))
+        errs.push_back({root + ".topologyConstraint", msg(pd, "PodCliqueSet", "", g.Topology->packDomain, "PodCliqueScalingGroup", g.Name)});
+  }
+  for (size_t i = 0; i < pcs.PodCliqueScalingGroupConfigs.size(); ++i) {
+    const auto& g = pcs.PodCliqueScalingGroupConfigs[i];
+    if (!g.Topology) continue;
+    for (const auto& cn : g.CliqueNames) {
+      auto it = std::find_if(pcs.Cliques.begin(), pcs.Cliques.end(), [&cn](const PodCliqueTemplateSpec& t) { return t.Name == cn; });
+      if (it != pcs.Cliques.end() && it->Topology && violation(g.Topology->packDomain, it->Topology->packDomain))
+        errs.push_back({root + ".podCliqueScalingGroups[" + std::to_string(i) + "].topologyConstraint",
+                        msg(g.Topology->packDomain, "PodCliqueScalingGroup", g.Name, it->Topology->packDomain, "PodClique", it->Name)});
+    }
+  }
+  return errs;
+}
+
 Err GpuBackend::ValidatePodCliqueSet(const PodCliqueSet& pcs) const {
+  std::vector<std::string> domains;
+  for (const auto& l : levels_) domains.push_back(l.Domain);
+  if (auto errs = ValidateHierarchicalTopologyConstraints(pcs, domains); !errs.empty())
+    return mkerr("ERR_VALIDATE_PCS", "ValidatePodCliqueSet", errs[0].field + ": " + errs[0].message);
   std::vector<PodGangInfo> infos;
   if (auto e = ComputeExpectedPodGangs(pcs, levels_, true, &infos)) return e;
   for (const auto& pg : infos) {
@@ -174,6 +212,34 @@ Err GpuBackend::SyncPodGang(const PodGang& podGang) {
   pending_[podGang.Namespace + "/" + podGang.Name] = podGang;  // a copy: the cache-owned object is neither mutated nor retained
   return std::nullopt;
 }
+Err IsBasePodGangScheduled(const PodGang* base, const std::map<std::string, int32_t>& scheduledReplicas, bool* scheduled) {
+  *scheduled = false;
+  if (!base) return mkerr("ERR_GET_PODGANG", "Sync", "failed to get base PodGang");
+  for (const auto& g : base->Spec.PodGroups) {
+    auto it = scheduledReplicas.find(g.Name);
+    if (it == scheduledReplicas.end())
+      return mkerr("ERR_GET_PODCLIQUE", "Sync", "failed to get PodClique " + g.Name + " in namespace " + base->Namespace + " for base PodGang readiness check");
+    if (it->second < g.MinReplicas) return std::nullopt;  // not scheduled yet: a legitimate state, no error
+  }
+  *scheduled = true;
+  return std::nullopt;
+}
+
+Err CheckPodSchedulingGate(bool podHasGate, bool podListedInPodGang, const std::string& basePodGangName, const PodGang* base,
+                           const std::map<std::string, int32_t>& scheduledReplicas, bool* removed, bool* skipped) {
+  *removed = false; *skipped = false;
+  bool baseScheduled = true;   // computed once per PodClique, before any pod is looked at (syncflow.go:259-269)
+  if (!basePodGangName.empty()) {
+    if (auto e = IsBasePodGangScheduled(base, scheduledReplicas, &baseScheduled))
+      return mkerr("ERR_REMOVE_POD_SCHEDULING_GATE", "Sync", "failed to check if base PodGang is scheduled for PodClique: " + e->message);
+  }
+  if (!podHasGate) return std::nullopt;                                 // nothing to do, not a skip
+  if (!podListedInPodGang) { *skipped = true; return std::nullopt; }    // not yet in PodGang.Spec.PodGroups[].PodReferences
+  if (!baseScheduled) { *skipped = true; return std::nullopt; }         // scaled PodGang behind an unscheduled base
+  *removed = true;
+  return std::nullopt;
+}
+
 Err GpuBackend::OnPodGangDelete(const PodGang& podGang) {
   const std::string key = podGang.Namespace + "/" + podGang.Name;
   pending_.erase(key); bound_.erase(key);

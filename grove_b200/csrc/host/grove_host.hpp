@@ -7,6 +7,7 @@
 //   ComputeExpectedPodGangs (the producer)        operator/internal/controller/podcliqueset/components/podgang/syncflow.go:145-371
 //   name generation                               operator/api/common/namegen.go:70-117
 //   CreatePodGroupsForPodGang                     .../components/podgang/podgang.go:165-186
+//   isBasePodGangScheduled / scheduling gates     operator/internal/controller/podclique/components/pod/syncflow.go:255-358
 //
 // (all paths relative to /root/reference).  Error convention: Go returns `error`; here every fallible
 // call returns std::optional<Error> (nullopt == nil), and Error carries the GroveError fields
@@ -122,6 +123,27 @@ Err ComputeExpectedPodGangs(const PodCliqueSet& pcs, const std::vector<TopologyL
                             std::vector<PodGangInfo>* out);
 // buildResource + createPodGroupsForPodGang (podgang.go:128-186); pod names are <pclq>-<ordinal>, sorted
 PodGang BuildPodGang(const PodCliqueSet& pcs, const PodGangInfo& info);
+
+// ---- webhook rule the packing relies on (webhook/admission/pcs/validation/topologyconstraints.go:195-268) ----
+// A parent's pack domain must not be narrower than a child's (PodCliqueSet vs PodClique, PodCliqueSet vs
+// PodCliqueScalingGroup, PodCliqueScalingGroup vs its PodCliques); domains unknown to the ClusterTopology are skipped.
+// One FieldError per violating pair, in the reference's order, with the reference's field paths.
+struct FieldError { std::string field, message; };
+std::vector<FieldError> ValidateHierarchicalTopologyConstraints(const PodCliqueSet& pcs, const std::vector<std::string>& clusterTopologyDomains);
+
+// ---- the gang predicate (podclique/components/pod/syncflow.go:316-358) ---------------------------------------
+// A base PodGang is "scheduled" when every PodGroup has ScheduledReplicas >= MinReplicas; scaled PodGangs stay gated
+// until then.  base == nullptr (PodGang not found) and a PodGroup without a PodClique status are errors: the caller
+// requeues, as the reference does for every Get failure.  scheduledReplicas: PodClique name -> Status.ScheduledReplicas
+// (podclique/reconcilestatus.go:134-141).
+Err IsBasePodGangScheduled(const PodGang* base, const std::map<std::string, int32_t>& scheduledReplicas, bool* scheduled);
+
+// Which pods reach a scheduler at all (checkAndRemovePodSchedulingGates, pod/syncflow.go:255-312): a pod loses its
+// grove.io/podgang-pending-creation gate when it carries the gate, is already listed in its PodGang's PodReferences,
+// and its PodGang is a base PodGang or its base PodGang is scheduled.  basePodGangName empty = the pod's PodGang is a
+// base PodGang.  *removed: the gate is removed now; *skipped: the pod keeps its gate and is counted as skipped.
+Err CheckPodSchedulingGate(bool podHasGate, bool podListedInPodGang, const std::string& basePodGangName, const PodGang* base,
+                           const std::map<std::string, int32_t>& scheduledReplicas, bool* removed, bool* skipped);
 
 // ---- nodes ------------------------------------------------------------------------------------------
 struct Node {   // the slice of corev1.Node + bound Pods a scheduler snapshots; shape of kwok.py:74-117

@@ -154,6 +154,85 @@ static PodCliqueSet workload1() {  // e2e/yaml/workload1.yaml
   return pcs;
 }
 
+static void test_hierarchy_violations() {  // pcs/validation/topologyconstraints_test.go:228-357 (six vectors) and :410-457 (two)
+  const std::vector<std::string> dom = {"region", "zone", "rack", "host", "numa"};
+  const std::string PCS = "spec.template.topologyConstraint", SG0 = "spec.template.podCliqueScalingGroups[0].topologyConstraint";
+  struct Case { const char* name; const char* pcs; std::vector<PodCliqueTemplateSpec> cliques; std::vector<PodCliqueScalingGroupConfig> sgs; std::vector<std::string> fields; };
+  const std::vector<Case> cases = {
+    {"PCS broader than PodClique", "zone", {clq("worker", 1, 1, "host")}, {}, {}},
+    {"PCS narrower than PodClique", "host", {clq("worker", 1, 1, "zone")}, {}, {PCS}},
+    {"PCS narrower than PCSG", "numa", {}, {sg("sg1", 1, 1, {"worker"}, "rack")}, {PCS}},
+    {"PCSG narrower than PodClique", nullptr, {clq("worker", 1, 1, "zone")}, {sg("sg1", 1, 1, {"worker"}, "host")}, {SG0}},
+    {"same level", "zone", {clq("worker", 1, 1, "zone")}, {}, {}},
+    {"violations at several levels", "numa", {clq("worker1", 1, 1, "zone"), clq("worker2", 1, 1, "rack")}, {sg("sg1", 1, 1, {"worker1", "worker2"}, "host")},
+     {PCS, PCS, PCS, SG0, SG0}},
+  };
+  for (const auto& c : cases) {
+    PodCliqueSet pcs; pcs.Name = "t"; pcs.Cliques = c.cliques; pcs.PodCliqueScalingGroupConfigs = c.sgs;
+    if (c.pcs) pcs.Topology = PackDomain{c.pcs};
+    const auto errs = ValidateHierarchicalTopologyConstraints(pcs, dom);
+    CHECK(errs.size() == c.fields.size());
+    for (size_t i = 0; i < errs.size() && i < c.fields.size(); ++i) CHECK(errs[i].field == c.fields[i]);
+  }
+  const std::vector<std::string> custom = {"datacenter", "rack", "gpu-module", "host"};
+  PodCliqueSet ok; ok.Topology = PackDomain{"datacenter"}; ok.Cliques = {clq("worker", 1, 1, "host")};
+  CHECK(ValidateHierarchicalTopologyConstraints(ok, custom).empty());
+  PodCliqueSet bad; bad.Topology = PackDomain{"host"}; bad.Cliques = {clq("worker", 1, 1, "datacenter")};
+  CHECK(ValidateHierarchicalTopologyConstraints(bad, custom).size() == 1);
+  PodCliqueSet unknown; unknown.Topology = PackDomain{"nvl-domain"}; unknown.Cliques = {clq("worker", 1, 1, "datacenter")};   // unknown domain: check skipped
+  CHECK(ValidateHierarchicalTopologyConstraints(unknown, custom).empty());
+  GpuBackend be; CHECK(!be.SyncTopology(kLevels));
+  PodCliqueSet viol; viol.Name = "v"; viol.Topology = PackDomain{"host"}; viol.Cliques = {clq("worker", 1, 1, "zone")};
+  CHECK(be.ValidatePodCliqueSet(viol).has_value());
+}
+
+static void test_is_base_podgang_scheduled() {  // podclique/components/pod/syncflow_test.go:323-372, the four vectors
+  struct P { const char* name; int32_t minAvailable, scheduledReplicas; };
+  struct Case { const char* name; bool exists; std::vector<P> pclqs; bool scheduled, error; };
+  const std::vector<Case> cases = {
+    {"all PodCliques meet MinAvailable", true, {{"simple1-0-pcb", 2, 2}, {"simple1-0-pcc", 1, 3}}, true, false},
+    {"one PodClique below MinAvailable", true, {{"simple1-0-pcb", 2, 2}, {"simple1-0-pcc", 3, 2}}, false, false},
+    {"base PodGang missing", false, {}, false, true},
+    {"single PodClique", true, {{"simple1-0-pcb", 1, 1}}, true, false},
+  };
+  for (const auto& c : cases) {
+    PodGang base; base.Namespace = "default"; base.Name = "simple1-0";
+    std::map<std::string, int32_t> status;
+    for (const auto& p : c.pclqs) { PodGroup g; g.Name = p.name; g.MinReplicas = p.minAvailable; base.Spec.PodGroups.push_back(g); status[p.name] = p.scheduledReplicas; }
+    bool scheduled = true;
+    auto e = IsBasePodGangScheduled(c.exists ? &base : nullptr, status, &scheduled);
+    CHECK(e.has_value() == c.error);
+    CHECK(scheduled == c.scheduled);
+  }
+  // a PodGroup whose PodClique cannot be read is an error too (requeue), not "unscheduled"
+  PodGang base; base.Namespace = "default"; PodGroup g; g.Name = "x"; g.MinReplicas = 1; base.Spec.PodGroups.push_back(g);
+  bool scheduled = true;
+  CHECK(IsBasePodGangScheduled(&base, {}, &scheduled).has_value() && !scheduled);
+}
+
+static void test_pod_scheduling_gates() {  // podclique/components/pod/syncflow_test.go:40-125, the six vectors
+  struct Case { const char* name; const char* podGang; bool baseExists, baseReady, hasGate, inPodGang, removed; int skipped; bool error; };
+  const std::vector<Case> cases = {
+    {"base PodGang pod: gate removed immediately", "simple1-0", true, false, true, true, true, 0, false},
+    {"scaled PodGang pod, base not ready", "simple1-0-sga-2", true, false, true, true, false, 1, false},
+    {"scaled PodGang pod, base ready", "simple1-0-sga-2", true, true, true, true, true, 0, false},
+    {"scaled PodGang pod, base missing", "simple1-0-sga-3", false, false, true, true, false, 0, true},
+    {"pod not in PodGang yet", "simple1-0-sga-2", true, true, true, false, false, 1, false},
+    {"pod without gate", "simple1-0-sga-2", true, true, false, true, false, 0, false},
+  };
+  for (const auto& c : cases) {
+    const bool scaled = std::string(c.podGang).find("-sga-") != std::string::npos;
+    PodGang base; base.Namespace = "default"; base.Name = "simple1-0";
+    PodGroup g; g.Name = "simple1-0-pcb"; g.MinReplicas = 2; base.Spec.PodGroups.push_back(g);
+    std::map<std::string, int32_t> status = {{"simple1-0-pcb", c.baseReady ? 2 : 1}};
+    bool removed = true, skipped = true;
+    auto e = CheckPodSchedulingGate(c.hasGate, c.inPodGang, scaled ? "simple1-0" : "", c.baseExists ? &base : nullptr, status, &removed, &skipped);
+    CHECK(e.has_value() == c.error);
+    CHECK(removed == c.removed);
+    CHECK(int(skipped) == c.skipped);
+  }
+}
+
 static void test_encode() {
   GpuBackend be;
   CHECK(be.Name() == "gpu-scheduler");
@@ -275,6 +354,9 @@ int main(int argc, char** argv) {
   const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
   test_compute_expected_podgangs();
   test_topology_constraints();
+  test_hierarchy_violations();
+  test_is_base_podgang_scheduled();
+  test_pod_scheduling_gates();
   test_encode();
   if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); }
   else {  // without a CUDA device Init must fail loudly, never fall back
