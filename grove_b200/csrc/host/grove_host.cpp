@@ -305,10 +305,17 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     for (const auto& p : pg.Spec.PodGroups) if (has(p.Topology)) return true;
     return false;
   };
+  // The best-effort pods of a PodGang that is not scheduled yet follow the same route: it goes in as its minimum
+  // only, and its surplus as a remainder row gated behind it (base_gang) -- minimums of every gang before anybody's
+  // surplus, which is what the suites' step descriptions say happens (GS8 :583, GS10 :779, GS12 :1023).
+  auto hasSurplus = [](const PodGang& pg) { for (const auto& p : pg.Spec.PodGroups) if (int64_t(p.PodReferences.size()) > p.MinReplicas) return true; return false; };
   std::vector<const std::string*> order;
   for (const auto& kv : pending_) if (!bound_.count(kv.first)) order.push_back(&kv.first);
   const size_t nFull = order.size();
-  for (const auto& kv : pending_) if (bound_.count(kv.first) && !constrained(kv.second)) order.push_back(&kv.first);
+  for (const auto& kv : pending_) {
+    const bool scheduled = bound_.count(kv.first) != 0;
+    if (!constrained(kv.second) && (scheduled || hasSurplus(kv.second))) order.push_back(&kv.first);
+  }
   std::map<std::string, uint32_t> row;  // PodGang key -> gang row (PodGangs still to be scheduled only: what a base_gang can name)
   for (size_t i = 0; i < nFull; ++i) row.emplace(*order[i], uint32_t(i));
   std::map<std::string, uint32_t> nodeIndex;
@@ -317,7 +324,13 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     const std::string& key = *order[oi];
     const PodGang& pg = pending_.at(key);
     const bool remainder = oi >= nFull;
-    const std::vector<uint32_t>* done = remainder ? &bound_.at(key) : nullptr;   // pods already bound, per PodGroup
+    const bool split = !remainder && !constrained(pg) && hasSurplus(pg);          // this row carries the minimum only
+    std::vector<uint32_t> minOnly;                                                 // surplus row of an unscheduled PodGang: its minimum is row `row[key]`
+    const std::vector<uint32_t>* done = nullptr;                                   // pods covered elsewhere, per PodGroup
+    if (remainder) {
+      if (auto it = bound_.find(key); it != bound_.end()) done = &it->second;
+      else { for (const auto& p : pg.Spec.PodGroups) minOnly.push_back(uint32_t(std::max<int32_t>(0, p.MinReplicas))); done = &minOnly; }
+    }
     grove_gang_t g{};
     g.clique_off = uint32_t(out->cliques.size()); g.scope_off = uint32_t(out->scopes.size());
     g.anchor_node = GROVE_NONE_U32; g.base_gang = GROVE_NONE_U32; g.preferred = GROVE_LEVEL_NONE;
@@ -326,6 +339,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
     if (auto it = priorityClasses_.find(pg.Spec.PriorityClassName); it != priorityClasses_.end()) g.priority = it->second;
     if (!remainder && !pg.BasePodGangName.empty())   // a base that is already scheduled gates nothing
       if (auto it = row.find(pg.Namespace + "/" + pg.BasePodGangName); it != row.end()) g.base_gang = it->second;
+    if (remainder && !minOnly.empty()) g.base_gang = row.at(key);   // surplus of a PodGang whose minimum is in this very pass
     if (remainder) {  // stay close to where the gang landed
       if (auto it = lastNode_.find(key); it != lastNode_.end()) if (auto nt = nodeIndex.find(it->second); nt != nodeIndex.end()) g.anchor_node = nt->second;
     } else if (pg.Spec.ReuseReservationRef) {  // locality hint: score distance against where that PodGang was placed
@@ -367,6 +381,7 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
           return mkerr("ERR_SYNC_PODGANG", "Encode", "PodGroup " + p.Name + ": MinReplicas / PodReferences out of range");
         c.min_replicas = uint8_t(p.MinReplicas); c.replicas = uint8_t(p.PodReferences.size());
         if (remainder) { c.min_replicas = 0; c.replicas = uint8_t(left(gi)); }
+        if (split) c.replicas = c.min_replicas;
         uint8_t cpref;
         if (auto e = levelOf(p.Topology, &c.level, &cpref)) return e;
         c.scope = GROVE_CLIQUE_SCOPE_PREF(uint32_t(si), cpref);
@@ -439,6 +454,7 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
       case GROVE_GANG_GATED_SKIP: s.ScheduledReason = "Gated"; break;
       default: s.ScheduledReason = "Pending"; break;
     }
+    if (t.remainder[g] && statuses->count(t.gangNames[g])) continue;   // the minimum row of the same PodGang already spoke
     (*statuses)[t.gangNames[g]] = s;
   }
   // a scheduled PodGang leaves the pending set once every PodReference is bound; until then its unbound pods are retried

@@ -37,7 +37,12 @@ class Gang:
 
 
 class E2ESim:
-    def __init__(self, n_nodes, cordoned):
+    def __init__(self, n_nodes, cordoned, split_surplus=False, same_pass_unlock=True):
+        # same_pass_unlock: a scaled PodGang rides in the same pass as its unscheduled base, gated by base_gang (the
+        # engine unlocks it the round after the base is admitted).  False: it only shows up in the pass AFTER its base
+        # was scheduled -- the operator removes the pods' gates in a later reconcile (pod/syncflow.go:255-312) -- and a
+        # step repeats passes until nothing changes, as the suites wait for the cluster to settle.
+        self.split_surplus, self.same_pass_unlock = split_surplus, same_pass_unlock
         self.nodes = synth.e2e_cluster(n_nodes)
         self.cordoned = list(range(n_nodes - cordoned, n_nodes))
         synth.cordon(self.nodes, self.cordoned)
@@ -86,30 +91,50 @@ class E2ESim:
         return sum(g.n_bound() for g in self.gangs)
 
     def tables(self):
-        """(gangs, cliques, scopes), rows = [(gang, [(scope index, clique index) per table clique], remainder?)]"""
+        """(gangs, cliques, scopes), rows = [(gang, [(scope index, clique index) per table clique], remainder?)]
+
+        split_surplus (the encoding GpuBackend::Encode uses for PodGangs without pack constraints): a PodGang that is
+        not scheduled yet goes in as its minimum only; its best-effort pods follow as a remainder row gated behind it
+        (base_gang), after every minimum row -- "minimums of every gang before anybody's surplus", what the step
+        descriptions of GS8 / GS10 / GS12 say happens (which pods, not only how many)."""
         b, rows, row_of = T.GangTableBuilder(), [], {}
         for g in self.gangs:            # PodGangs that still have to get their minimum, in creation order
             if g.scheduled:
                 continue
             base = None
             if g.base is not None and not g.base.scheduled:
+                if not self.same_pass_unlock:
+                    continue
                 base = row_of[id(g.base)]
-            row_of[id(g)] = b.add_gang(g.scopes, base=base)
+            scopes = g.scopes
+            if self.split_surplus:
+                scopes = [(lvl, [dict(c, replicas=c["min"]) for c in cl]) for lvl, cl in g.scopes]
+            row_of[id(g)] = b.add_gang(scopes, base=base)
             rows.append((g, [(si, ci) for si, (_, cl) in enumerate(g.scopes) for ci in range(len(cl))], False))
-        for g in self.gangs:            # then the Pending pods of scheduled PodGangs
-            if not g.scheduled or g.n_bound() == g.total():
+        for g in self.gangs:            # then the pods beyond the minimum: Pending pods of scheduled PodGangs, surplus of the others
+            if g.n_bound() == g.total() or (not g.scheduled and (not self.split_surplus or id(g) not in row_of)):
                 continue
             scopes, index = [], []
             for si, (lvl, cl) in enumerate(g.scopes):
-                rem = [(ci, dict(c, min=0, replicas=c["replicas"] - g.bound[si][ci])) for ci, c in enumerate(cl) if c["replicas"] > g.bound[si][ci]]
+                have = [g.bound[si][ci] if g.scheduled else c["min"] for ci, c in enumerate(cl)]
+                rem = [(ci, dict(c, min=0, replicas=c["replicas"] - have[ci])) for ci, c in enumerate(cl) if c["replicas"] > have[ci]]
                 if rem:
                     scopes.append((lvl, [c for _, c in rem])); index += [(si, ci) for ci, _ in rem]
-            b.add_gang(scopes)
-            rows.append((g, index, True))
+            if scopes:
+                b.add_gang(scopes, base=None if g.scheduled else row_of[id(g)])
+                rows.append((g, index, True))
         return b.build(), rows
 
     def step(self, place):
-        """one scheduling pass: place(nodes, gangs, cliques, scopes) -> dict(status, placements, nodes_after)"""
+        """scheduling passes until the cluster settles (one pass when scaled gangs unlock inside the pass)"""
+        while True:
+            before = (self.running(), sum(g.scheduled for g in self.gangs))
+            self.one_pass(place)
+            if self.same_pass_unlock or (self.running(), sum(g.scheduled for g in self.gangs)) == before:
+                return
+
+    def one_pass(self, place):
+        """place(nodes, gangs, cliques, scopes) -> dict(status, placements, nodes_after)"""
         (g, c, s), rows = self.tables()
         if len(g) == 0:
             return None
@@ -118,7 +143,8 @@ class E2ESim:
             st = r["status"][row]
             if st["state"] != T.GANG_ADMITTED:
                 continue
-            gang.scheduled = True
+            if not remainder:
+                gang.scheduled = True
             pl = r["placements"][st["placement_off"]: st["placement_off"] + st["n_pods"]]
             for q in pl["clique"]:
                 si, ci = index[int(q) - int(g["clique_off"][row])]

@@ -344,5 +344,6 @@ def test_e2e_sequences_match_the_oracle_step_by_step(built_lib, oracle):
                 assert np.array_equal(out[k], ref[k]), k
             return out
         for name in GS:
-            sim = replay(place, GS[name])
-            assert sim.running() == sim.pods(), name
+            for kw in (dict(), dict(split_surplus=True, same_pass_unlock=False)):   # surplus with the gang / minimums first
+                sim = replay(place, GS[name], **kw)
+                assert sim.running() == sim.pods(), name
