@@ -65,11 +65,11 @@ struct RoundBufs {
   uint32_t* ent_node;    // [P]
   uint16_t* ent_meta;    // [P] clique_rel | score << 8
   uint32_t* active_all;  // [G] active gangs of every rank (replicated decision)
-  uint32_t* claim;       // [n]
-  uint8_t* taken;        // [n] node received a commit in this round
+  uint32_t* claim;       // [n] (tag << 24 | order rank) of the best proposal for the node; tags decrease per (round, sub-round)
+  uint8_t* taken;        // [n] stamp of the last round that committed pods on the node
   uint8_t* cur;          // [G] next alternative a gang will propose
   uint8_t* prop;         // [G] sub-round (1-based) of the gang's last proposal
-  uint32_t* flags;       // [GROVE_SUBROUNDS] any proposal in sub-round s
+  uint32_t* flags;       // [GROVE_SUBROUNDS] number of the last round with a proposal in sub-round s
   // exchange buffer of the round (also the all-reduce payload of the sharded cycle), u32 words:
   uint32_t* alt_node;    // [K][P] entry i of alternative a of gang g at a*P + pod_off[g] + i
   uint32_t* alt_meta;    // [K][P] clique_rel | score << 8

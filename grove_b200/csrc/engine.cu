@@ -719,7 +719,7 @@ int32_t grove_cycle_begin(grove_engine_t* e) {
   CU_TRY(e, e->d_taken.ensure(e->N)); CU_TRY(e, e->d_cur.ensure(G)); CU_TRY(e, e->d_prop.ensure(G)); CU_TRY(e, e->d_flags.ensure(GROVE_SUBROUNDS));
   CU_TRY(e, e->d_active_all.ensure(G));
   CU_TRY(e, e->d_xbuf.ensure(2 * size_t(e->K) * e->P + 4 * size_t(G) * e->K + G));
-  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // k_resolve withdraws its claims itself
+  CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));  // round-stamped; rounds count from 1
   CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
   CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
   // the Q x N matrices
@@ -839,13 +839,19 @@ static int32_t round_resolve(grove_engine* e, bool timed) {
   const uint32_t na_all = e->h_counters.p[5];
   if (na_all == 0) return GROVE_OK;
   Topo tp = make_topo(e); Tables tb = make_tables(e); RoundBufs rb = make_bufs(e);
-  CU_TRY(e, cudaMemsetAsync(e->d_taken.p, 0, e->N, e->stream));
-  CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));
-  CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));  // claims are sub-round tagged; reset once per round
+  // The per-round scratch is stamped instead of cleared.  claim[n] carries a tag in its top byte that DEcreases with
+  // every (round, sub-round), so a newer claim always beats a stale one through atomicMin; taken[n] holds the stamp of
+  // the round that committed on n; flags[sub] the number of the round that proposed.  The arrays are reset only when a
+  // stamp would wrap: every kClaimRounds rounds (claim: the top byte stays below 0x7F = "no claim") / 254 rounds (taken).
+  const uint32_t r0 = e->round_no - 1;   // rounds count from 1
+  if (r0 % kClaimRounds == 0) CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
+  if (r0 % 254u == 0) CU_TRY(e, cudaMemsetAsync(e->d_taken.p, 0, e->N, e->stream));
+  uint32_t tag_hi = 0x7Eu - (r0 % kClaimRounds) * GROVE_SUBROUNDS;   // tag of sub-round 0 of this round
+  uint32_t tk = r0 % 254u + 1u;                                       // 1..254
   uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
   const uint32_t want = (na_all * 32 + kResolveThreads - 1) / kResolveThreads;  // a warp per gang
   const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, std::min<uint32_t>(uint32_t(e->resolve_blocks_per_sm), e->tune_resolve_bps) * e->n_sm));
-  void* args[] = {&tp, &tb, &rb, &nres, &rn};
+  void* args[] = {&tp, &tb, &rb, &nres, &rn, &tag_hi, &tk};
   CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(kResolveThreads), args, 0, e->stream));
   if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
   e->launches += 1;

@@ -14,8 +14,12 @@ namespace grove {
 // claim and flags do and are read with ld.cg / volatile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kResolveThreads = 1024;  // few, fat CTAs: the grid barrier is what this kernel waits on
+constexpr uint32_t kClaimRounds = 0x7Eu / GROVE_SUBROUNDS;  // rounds whose (round, sub-round) tags fit below the "no claim" byte
 
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no) {
+// tag_hi: claim tag of this round's sub-round 0 (tags decrease: newer claims win atomicMin against stale ones);
+// tk: this round's stamp in taken[]; flags[] are stamped with the round number.  See round_resolve().
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb, RoundBufs rb, uint4* nres, uint32_t round_no,
+                                                            uint32_t tag_hi, uint32_t tk) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const uint32_t lane = threadIdx.x & 31;
@@ -45,27 +49,27 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb,
       if (pending) load_alt();
     }
     for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
-      const uint32_t order = order0 | ((GROVE_SUBROUNDS - 1u - sub) << 24);
+      const uint32_t order = order0 | ((tag_hi - sub) << 24);
       bool proposed = false;
       if (pending) {
         while (c < nalt) {  // first alternative that touches no node committed earlier in this round
           bool hit = false;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) hit |= __ldcg(rb.taken + nd[j]) != 0;
+          for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) hit |= __ldcg(rb.taken + nd[j]) == tk;
           if (!__any_sync(kFull, hit)) break;
           if (++c < nalt) load_alt();
         }
         if (c < nalt) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (nd[j] != GROVE_NONE_U32) atomicMin(rb.claim + nd[j], order);
-          if (lane == 0) rb.flags[sub] = 1u;
+          if (lane == 0) rb.flags[sub] = round_no;
           proposed = true;
         } else {
           pending = false;  // nothing left to propose: re-evaluated next round
         }
       }
       grid.sync();
-      if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
+      if (vflags[sub] != round_no) break;  // no proposal anywhere: the round is settled
       if (proposed) {
         bool win = true;
 #pragma unroll
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb,
             if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
             if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
             atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
-            rb.taken[nd[j]] = 1;
+            rb.taken[nd[j]] = uint8_t(tk);
             rb.ent_node[po + i] = nd[j]; rb.ent_meta[po + i] = uint16_t(meta);
           }
           if (lane == 0) {
@@ -108,9 +112,9 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb,
   }
   __syncwarp();
   for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
-    // claims carry the sub-round in their top bits so that a later sub-round always beats stale claims of
-    // an earlier one (atomicMin): nothing has to be withdrawn between sub-rounds
-    const uint32_t tag = (GROVE_SUBROUNDS - 1u - sub) << 24;
+    // claims carry the (round, sub-round) in their top bits so that a later sub-round always beats stale claims of
+    // an earlier one (atomicMin): nothing has to be withdrawn between sub-rounds or rounds
+    const uint32_t tag = (tag_hi - sub) << 24;
     // ---- propose ----
     for (uint32_t ai = gw; ai < na; ai += nw) {
       const uint32_t g = rb.active_all[ai];
@@ -120,17 +124,17 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb,
       while (c < nalt) {  // first alternative that touches no node committed earlier in this round
         cnt = rb.alt_n[size_t(g) * K + c];
         bool hit = false;
-        for (uint32_t i = lane; i < cnt; i += 32) hit |= __ldcg(rb.taken + rb.alt_node[size_t(c) * P + po + i]) != 0;
+        for (uint32_t i = lane; i < cnt; i += 32) hit |= __ldcg(rb.taken + rb.alt_node[size_t(c) * P + po + i]) == tk;
         if (!__any_sync(kFull, hit)) break;
         ++c;
       }
       if (lane == 0) rb.cur[g] = uint8_t(c);
       if (c >= nalt) continue;  // nothing left to propose: re-evaluated next round
       for (uint32_t i = lane; i < cnt; i += 32) atomicMin(rb.claim + rb.alt_node[size_t(c) * P + po + i], order);
-      if (lane == 0) { rb.prop[g] = uint8_t(sub + 1); rb.flags[sub] = 1u; }
+      if (lane == 0) { rb.prop[g] = uint8_t(sub + 1); rb.flags[sub] = round_no; }
     }
     grid.sync();
-    if (vflags[sub] == 0) break;  // no proposal anywhere: the round is settled
+    if (vflags[sub] != round_no) break;  // no proposal anywhere: the round is settled
     // ---- decide ----
     for (uint32_t ai = gw; ai < na; ai += nw) {
       const uint32_t g = rb.active_all[ai];
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Topo tp, Tables tb,
         if (q.req_cpu_milli) atomicSub(r + 0, q.req_cpu_milli);
         if (q.req_mem_mib) atomicSub(r + 1, q.req_mem_mib);
         atomicSub(r + 2, uint32_t(q.req_gpu) | (1u << 16));
-        rb.taken[nd] = 1;
+        rb.taken[nd] = uint8_t(tk);
         rb.ent_node[po + i] = nd; rb.ent_meta[po + i] = uint16_t(meta);
       }
       if (lane == 0) {

@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(1024) k_prepare(Tables tb, RoundBufs rb, uint3
     for (uint32_t i = 0; i < ncl; ++i) {
       rb.rows[orr + i] = coff + i;
       const uint32_t sg = tb.cinfo[coff + i].sig;
-      if (atomicExch(rb.sig_stamp + sg, round_no) != round_no) rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
+      // thousands of cliques share a few signatures: look before exchanging, so that only the first few arrivals per
+      // signature pay a same-address atomic
+      if (__ldcg(rb.sig_stamp + sg) != round_no && atomicExch(rb.sig_stamp + sg, round_no) != round_no)
+        rb.sig_list[atomicAdd(rb.counters + 4, 1u)] = sg;
     }
   }
 }
