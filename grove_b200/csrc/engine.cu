@@ -111,6 +111,7 @@ struct grove_engine {
   cudaStream_t stream = nullptr;
   cudaStream_t stream_score = nullptr;  // K2 runs beside K3 (they only share the fit data)
   cudaEvent_t ev_fit = nullptr, ev_score = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+  cudaEvent_t ev_nodes_up = nullptr, ev_tables_up = nullptr;  // the last upload out of the pinned node staging buffer / gang tables
   cudaEvent_t ev[10]{};
 
   // ---- topology (static until labels change) ----
@@ -368,6 +369,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaStreamCreateWithPriority(&e->stream_score, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaEventCreateWithFlags(&e->ev_fit, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_score, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_nodes_up, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_tables_up, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&e->ev_s0) != cudaSuccess || cudaEventCreate(&e->ev_s1) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
@@ -383,6 +385,8 @@ void grove_engine_destroy(grove_engine_t* e) {
   if (e->ev_s0) cudaEventDestroy(e->ev_s0);
   if (e->ev_s1) cudaEventDestroy(e->ev_s1);
   if (e->ev_fit) cudaEventDestroy(e->ev_fit);
+  if (e->ev_nodes_up) cudaEventDestroy(e->ev_nodes_up);
+  if (e->ev_tables_up) cudaEventDestroy(e->ev_tables_up);
   if (e->ev_score) cudaEventDestroy(e->ev_score);
   if (e->stream_score) cudaStreamDestroy(e->stream_score);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -393,8 +397,8 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
   if (n == 0 || n > GROVE_MAX_NODES) return fail(e, GROVE_ERR_INVALID_ARG, "node count out of range");
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));  // an earlier upload may still be reading the staging buffer
   if (host_nodes) {
+    CU_TRY(e, cudaEventSynchronize(e->ev_nodes_up));  // an earlier upload may still be reading the staging buffer
     CU_TRY(e, e->d_nodes_in.ensure(n));
     CU_TRY(e, e->h_stage_nodes.ensure(n));
     // one pass over the caller's snapshot by a few threads: copy to the pinned staging buffer (the caller's array is
@@ -416,6 +420,7 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
     }
     if (!cached || differs) { int32_t rc = build_topology(e, host_nodes, n); if (rc) return rc; }
     CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p, e->h_stage_nodes.p, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaEventRecord(e->ev_nodes_up, e->stream));
   } else {
     if (!e->nodes_loaded || n != e->N) return fail(e, GROVE_ERR_STATE, "device load needs a prior host load with the same labels");
     CU_TRY(e, cudaMemcpyAsync(e->d_nodes_in.p, dev_nodes, sizeof(grove_node_t) * n, cudaMemcpyDeviceToDevice, e->stream));
@@ -538,7 +543,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   int32_t rc = validate(e, gangs, n_gangs, cliques, n_cliques, scopes, n_scopes);
   if (rc) return rc;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));  // an earlier upload may still be reading the pinned tables
+  CU_TRY(e, cudaEventSynchronize(e->ev_tables_up));  // an earlier upload may still be reading the pinned tables
   e->G = n_gangs; e->Q = n_cliques; e->S = n_scopes;
   CU_TRY(e, e->gangs.assign(gangs, n_gangs));
   CU_TRY(e, e->cliques.assign(cliques, n_cliques));
@@ -557,6 +562,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   if (n_gangs) CU_TRY(e, cudaMemcpyAsync(e->d_gangs.p, e->gangs.data(), sizeof(grove_gang_t) * n_gangs, cudaMemcpyHostToDevice, e->stream));
   if (n_cliques) CU_TRY(e, cudaMemcpyAsync(e->d_cliques.p, e->cliques.data(), sizeof(grove_clique_t) * n_cliques, cudaMemcpyHostToDevice, e->stream));
   if (n_scopes) CU_TRY(e, cudaMemcpyAsync(e->d_scopes.p, e->scopes.data(), sizeof(grove_scope_t) * n_scopes, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaEventRecord(e->ev_tables_up, e->stream));
   return GROVE_OK;  // the uploads read engine-owned pinned memory: nothing of the caller's is referenced any more
 }
 
