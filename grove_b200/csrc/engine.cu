@@ -582,43 +582,79 @@ static int32_t build_ginfo(grove_engine* e) {
     }
   }
   e->sigs.clear();
-  // order rank = position by (priority desc, index asc): a stable bucket pass over the distinct priorities
-  std::vector<uint32_t> ord(G);
+  const auto t_m0 = std::chrono::steady_clock::now();
+  // order rank = position by (priority desc, index asc), and the anchors.  PriorityClasses are few: every thread counts
+  // the distinct priorities of its gang range, one thread turns the counts into start offsets per (priority, thread),
+  // and every thread numbers its own range -- a stable counting sort without the sorted array.
+  bool bad_anchor = false;
   {
-    std::vector<int32_t> pr;          // distinct priorities (PriorityClasses are few)
-    std::vector<uint8_t> bkt(G, 0);   // bucket of each gang in first-seen order, remapped below
+    constexpr size_t kMaxPrio = 64;
+    const int T1 = G >= 2048 ? host_threads() : 1;
+    std::vector<std::vector<std::pair<int32_t, uint32_t>>> seen(T1);   // per thread: (priority, count) in first-seen order
+    std::vector<int32_t> prios;                                         // distinct, descending
+    std::vector<uint32_t> start;                                        // [thread][priority index] first rank
     bool many = false;
-    for (uint32_t g = 0; g < G && !many; ++g) {
-      const int32_t p = e->gangs[g].priority;
-      size_t i = 0;
-      while (i < pr.size() && pr[i] != p) ++i;
-      if (i == pr.size()) { if (pr.size() == 64) { many = true; break; } pr.push_back(p); }
-      bkt[g] = uint8_t(i);
+#pragma omp parallel num_threads(T1)
+    {
+      const int t = omp_get_thread_num();
+      const uint32_t g0 = uint32_t(uint64_t(G) * t / T1), g1 = uint32_t(uint64_t(G) * (t + 1) / T1);
+      auto& mine = seen[t];
+      bool over = false;
+      for (uint32_t g = g0; g < g1 && !over; ++g) {
+        const int32_t p = e->gangs[g].priority;
+        size_t i = 0;
+        while (i < mine.size() && mine[i].first != p) ++i;
+        if (i == mine.size()) { if (mine.size() == kMaxPrio) { over = true; break; } mine.push_back({p, 0u}); }
+        mine[i].second++;
+      }
+      if (over) {
+#pragma omp atomic write
+        many = true;
+      }
+#pragma omp barrier
+#pragma omp single
+      {
+        for (const auto& v : seen) for (const auto& pc : v) prios.push_back(pc.first);
+        std::sort(prios.begin(), prios.end(), std::greater<int32_t>());
+        prios.erase(std::unique(prios.begin(), prios.end()), prios.end());
+        if (prios.size() > kMaxPrio) many = true;
+        if (!many) {
+          start.assign(size_t(T1) * prios.size(), 0u);
+          uint32_t run = 0;
+          for (size_t k = 0; k < prios.size(); ++k)
+            for (int tt = 0; tt < T1; ++tt) {
+              start[size_t(tt) * prios.size() + k] = run;
+              for (const auto& pc : seen[tt]) if (pc.first == prios[k]) run += pc.second;
+            }
+        }
+      }  // implicit barrier
+      bool bad = false;
+      uint32_t next[kMaxPrio];
+      if (!many) for (size_t k = 0; k < prios.size(); ++k) next[k] = start[size_t(t) * prios.size() + k];
+      for (uint32_t gi = g0; gi < g1; ++gi) {
+        const grove_gang_t& g = e->gangs[gi];
+        if (!many) {
+          size_t k = 0;
+          while (prios[k] != g.priority) ++k;
+          e->ginfo[gi].order = next[k]++;
+        }
+        if (g.anchor_node != GROVE_NONE_U32 && g.anchor_node >= e->N) { bad = true; continue; }
+        e->ginfo[gi].anchor = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
+      }
+      if (bad) {
+#pragma omp atomic write
+        bad_anchor = true;
+      }
     }
-    if (many) {
+    if (many) {  // more distinct priorities than a scheduler has PriorityClasses: plain stable sort
+      std::vector<uint32_t> ord(G);
       std::iota(ord.begin(), ord.end(), 0u);
       std::stable_sort(ord.begin(), ord.end(), [e](uint32_t a, uint32_t b) { return e->gangs[a].priority > e->gangs[b].priority; });
-    } else if (pr.size() <= 1) {
-      std::iota(ord.begin(), ord.end(), 0u);
-    } else {
-      std::vector<uint8_t> rank_of(pr.size());  // first-seen bucket -> position in descending priority order
-      std::vector<uint32_t> idx(pr.size());
-      std::iota(idx.begin(), idx.end(), 0u);
-      std::sort(idx.begin(), idx.end(), [&pr](uint32_t a, uint32_t b) { return pr[a] > pr[b]; });
-      for (size_t r = 0; r < idx.size(); ++r) rank_of[idx[r]] = uint8_t(r);
-      std::vector<uint32_t> cnt(pr.size() + 1, 0);
-      for (uint32_t g = 0; g < G; ++g) cnt[rank_of[bkt[g]] + 1]++;
-      for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
-      for (uint32_t g = 0; g < G; ++g) ord[cnt[rank_of[bkt[g]]]++] = g;
+      for (uint32_t r = 0; r < G; ++r) e->ginfo[ord[r]].order = r;
     }
   }
+  if (bad_anchor) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
   const auto t_m1 = std::chrono::steady_clock::now();
-  for (uint32_t r = 0; r < G; ++r) e->ginfo[ord[r]].order = r;
-  for (uint32_t gi = 0; gi < G; ++gi) {
-    const grove_gang_t& g = e->gangs[gi];
-    if (g.anchor_node != GROVE_NONE_U32 && g.anchor_node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
-    e->ginfo[gi].anchor = g.anchor_node != GROVE_NONE_U32 ? e->inv[g.anchor_node] : fmix32(gi) % e->N;
-  }
   // per-clique derived data + signature interning.  PodCliques stamped from one template (PCS / PCSG
   // replicas) share requests, selector class and binding depth: they share one fit-bitmap row.  Gang
   // ranges are processed by a few host threads with thread-local signature tables, merged afterwards.
@@ -705,7 +741,7 @@ static int32_t build_ginfo(grove_engine* e) {
   if (std::getenv("GROVE_DEBUG_HOST")) {
     const auto t_b2 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
-    std::fprintf(stderr, "build_ginfo: tables %ld us (order %ld, anchors %ld, cliques %ld, merge %ld), upload %ld us\n", us(t_b0, t_b1), us(t_b0, t_m1), us(t_m1, t_m2), us(t_m2, t_m3), us(t_m3, t_b1), us(t_b1, t_b2));
+    std::fprintf(stderr, "build_ginfo: tables %ld us (init %ld, order %ld, anchors %ld, cliques %ld, merge %ld), upload %ld us\n", us(t_b0, t_b1), us(t_b0, t_m0), us(t_m0, t_m1), us(t_m1, t_m2), us(t_m2, t_m3), us(t_m3, t_b1), us(t_b1, t_b2));
   }
   return GROVE_OK;
 }

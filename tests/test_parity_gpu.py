@@ -347,3 +347,22 @@ def test_e2e_sequences_match_the_oracle_step_by_step(built_lib, oracle):
             for kw in (dict(), dict(split_surplus=True, same_pass_unlock=False)):   # surplus with the gang / minimums first
                 sim = replay(place, GS[name], **kw)
                 assert sim.running() == sim.pods(), name
+
+
+def test_more_priorities_than_priority_classes(built_lib, oracle):
+    """order ranks come from a counting sort over the distinct priorities (few PriorityClasses) and fall back to a
+    stable sort beyond 64 of them; both must order conflicts like the oracle"""
+    from grove_b200.engine import PlacementEngine
+    rng = np.random.default_rng(11)
+    for n_prio, G in ((3, 3000), (64, 2500), (65, 300), (500, 2600)):
+        nodes = synth.kwok_nodes(1200, [240, 48, 8, 1])
+        b = T.GangTableBuilder()
+        for _ in range(G):
+            b.add_gang([(2, [dict(cpu=16000, mem=65536, gpu=4, min=2)])], level=1, priority=int(rng.integers(0, n_prio)) - n_prio // 2,
+                       anchor=int(rng.integers(0, 1200)))
+        g, c, s = b.build()
+        ref = oracle.run_cycle(nodes, 4, g, c, s, threads=8)
+        with PlacementEngine(4) as e:
+            e.load_nodes(nodes); e.submit_gangs(g, c, s); e.run_cycle()
+            assert np.array_equal(e.gang_status(), ref["status"]), n_prio
+            assert np.array_equal(e.placements(), ref["placements"]), n_prio
