@@ -332,7 +332,7 @@ def run_churn(args):
     sampler = ClockSampler(0)
     sampler.start()
     t_tick, t_cycle, adm, launches, pend, h2d, d2h = [], [], 0, 0, [], 0, 0
-    cpu_t, cpu_adm, same = 0.0, 0, True
+    cpu_t, cpu_adm, same, kept = 0.0, 0, True, []
     idx = recs = None
     with PlacementEngine(ch.n_levels) as e:
         e.load_nodes(ch.nodes)
@@ -352,13 +352,17 @@ def run_churn(args):
                 t_tick.append(dt * 1e3); t_cycle.append(st["ms_total"]); adm += st["gangs_admitted"]
                 launches += st["kernel_launches"]; pend.append(len(g))
                 h2d += g.nbytes + c.nbytes + s.nbytes + (0 if idx is None else idx.nbytes + recs.nbytes); d2h += pl.nbytes + gs.nbytes
-            if not args.no_cpu_baseline and args.warmup <= tick < args.warmup + 5:   # bounded sample: five ticks on the host cores
-                from oracle import oracle_py as O
-                tc = time.perf_counter()
-                r = O.run_cycle(before, ch.n_levels, g, c, s, threads=os.cpu_count() or 1)
-                cpu_t += time.perf_counter() - tc; cpu_adm += r["stats"]["gangs_admitted"]
-                same &= bool(np.array_equal(r["placements"], pl) and np.array_equal(r["status"], gs))
+            if not args.no_cpu_baseline and args.warmup <= tick < args.warmup + 5:   # bounded CPU sample: five ticks, replayed below
+                kept.append((before.copy(), g, c, s, pl.copy(), gs.copy()))
             idx, recs = ch.end_tick(specs, tabs, gs, pl, e.nodes())
+    # the CPU leg runs AFTER the timed ticks: the oracle's OpenMP team (all cores) and the engine's (8 threads) share one
+    # libgomp, and alternating team sizes makes it re-create its threads -- tens of milliseconds that belong to neither
+    for before, g, c, s, pl, gs in kept:
+        from oracle import oracle_py as O
+        tc = time.perf_counter()
+        r = O.run_cycle(before, ch.n_levels, g, c, s, threads=os.cpu_count() or 1)
+        cpu_t += time.perf_counter() - tc; cpu_adm += r["stats"]["gangs_admitted"]
+        same &= bool(np.array_equal(r["placements"], pl) and np.array_equal(r["status"], gs))
     clocks = sampler.stop()
     ms_tick, ms_cyc = float(np.mean(t_tick)), float(np.mean(t_cycle))
     line = {

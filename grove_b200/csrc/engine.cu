@@ -32,7 +32,7 @@ struct DevBuf {
   // of every table per cycle; falls back to the exact size when the padded one does not fit
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
-    const size_t want = std::max<size_t>(std::max<size_t>(n, 1), cap + cap / 2);
+    const size_t want = std::max<size_t>(std::max<size_t>(n, (64u << 10) / sizeof(T)), cap + cap / 2);
     release();
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
     if (e == cudaSuccess) { cap = want; return e; }
@@ -50,7 +50,8 @@ struct PinBuf {
   ~PinBuf() { if (p) cudaFreeHost(p); }
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
-    const size_t want = std::max<size_t>(std::max<size_t>(n, 1), cap + cap / 2);
+    // pinned allocations cost milliseconds: start at 256 KB and double, so a growing pending set re-allocates rarely
+    const size_t want = std::max<size_t>(std::max<size_t>(n, (256u << 10) / sizeof(T)), cap * 2);
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
