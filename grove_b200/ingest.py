@@ -127,3 +127,87 @@ def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=Non
                    base=row_of[base] if base in row_of else None)
     g, c, s = b.build()
     return g, c, s, names
+
+
+# ------------------------------------------------------------------------------------------------
+# The producer: PodCliqueSet -> PodGang manifests (the Python counterpart of ComputeExpectedPodGangs in
+# grove_b200/csrc/host; /root/reference operator/internal/controller/podcliqueset/components/podgang/syncflow.go:145-371,
+# names from operator/api/common/namegen.go:70-117, PodGroups from .../podgang/podgang.go:165-186).
+# ------------------------------------------------------------------------------------------------
+def podgangs_from_pcs(pcs: dict, topology_levels, tas_enabled: bool = True):
+    """PodCliqueSet (the compact dict of tests/golden/workloads.json: name, replicas, packDomain, cliques[],
+    podCliqueScalingGroups[]) -> (PodGang manifests, requests by PodGroup name, {scaled gang: base gang}).
+
+    topology_levels: ordered [(domain, node label key)], broadest first (ClusterTopology.spec.levels).
+    Base PodGang per PCS replica = standalone cliques + PCSG replicas [0, minAvailable) (one
+    TopologyConstraintGroupConfig per such replica when the PCSG has a constraint); a scaled PodGang per PCSG
+    replica >= minAvailable, carrying the PCSG's constraint or else the PCS's.  Defaults as the webhooks set them:
+    clique minAvailable = replicas, PCSG replicas = minAvailable = 1.
+    """
+    key_of = dict(topology_levels)
+
+    def constraint(domain):  # createTopologyPackConstraint: unknown domain or TAS off -> no constraint; Required only
+        if not tas_enabled or domain is None or domain not in key_of:
+            return None
+        return {"packConstraint": {"required": key_of[domain]}}
+
+    ns = pcs.get("namespace", "default")
+    cliques = {c["name"]: c for c in pcs["cliques"]}
+    groups = pcs.get("podCliqueScalingGroups") or []
+    grouped = {n for g in groups for n in g["cliqueNames"]}
+    requests, base_of, gangs = {}, {}, []
+
+    def podgroup(fqn, tmpl):
+        c = cliques[tmpl]
+        replicas = int(c.get("replicas") or 1)
+        mn = c.get("minAvailable")
+        requests[fqn] = dict(c.get("requests") or {})
+        pg = dict(name=fqn, minReplicas=int(replicas if mn is None else mn),
+                  podReferences=sorted(({"namespace": ns, "name": f"{fqn}-{i}"} for i in range(replicas)), key=lambda r: r["name"]))
+        tc = constraint(c.get("packDomain"))
+        if tc:
+            pg["topologyConstraint"] = tc
+        return pg
+
+    def manifest(name, podgroups, tc, configs=()):
+        spec = {"podgroups": podgroups}
+        if tc:
+            spec["topologyConstraint"] = tc
+        if configs:
+            spec["topologyConstraintGroupConfigs"] = list(configs)
+        if pcs.get("priorityClassName"):
+            spec["priorityClassName"] = pcs["priorityClassName"]
+        return {"apiVersion": "scheduler.grove.io/v1alpha1", "kind": "PodGang", "metadata": {"name": name, "namespace": ns}, "spec": spec}
+
+    for r in range(int(pcs.get("replicas") or 0)):
+        pgs = [podgroup(f"{pcs['name']}-{r}-{c['name']}", c["name"]) for c in pcs["cliques"] if c["name"] not in grouped]
+        configs = []
+        for g in groups:
+            fqn = f"{pcs['name']}-{r}-{g['name']}"
+            for ri in range(int(g.get("minAvailable") or 1)):
+                names = []
+                for cn in g["cliqueNames"]:
+                    if cn not in cliques:
+                        raise ValueError(f"PodCliqueScalingGroup {g['name']!r} references a PodClique {cn!r} that does not exist in the PodCliqueSet")
+                    pgs.append(podgroup(f"{fqn}-{ri}-{cn}", cn)); names.append(f"{fqn}-{ri}-{cn}")
+                tc = constraint(g.get("packDomain"))
+                if tas_enabled and g.get("packDomain") is not None:   # the config is emitted even when the domain went stale
+                    configs.append({"name": f"{fqn}-{ri}", "podGroupNames": names, **({"topologyConstraint": tc} if tc else {})})
+        gangs.append(manifest(f"{pcs['name']}-{r}", pgs, constraint(pcs.get("packDomain")), configs))
+    for r in range(int(pcs.get("replicas") or 0)):
+        for g in groups:
+            fqn = f"{pcs['name']}-{r}-{g['name']}"
+            replicas, mn = int(g.get("replicas") or 1), int(g.get("minAvailable") or 1)
+            for idx, pr in enumerate(range(mn, replicas)):
+                pgs = [podgroup(f"{fqn}-{pr}-{cn}", cn) for cn in g["cliqueNames"]]
+                tc = constraint(g["packDomain"] if g.get("packDomain") is not None else pcs.get("packDomain"))
+                name = f"{fqn}-{idx}"
+                gangs.append(manifest(name, pgs, tc)); base_of[name] = f"{pcs['name']}-{r}"
+    return gangs, requests, base_of
+
+
+def tables_from_pcs(pcs: dict, topology_levels, tas_enabled: bool = True, class_mask=0xFFFF):
+    """PodCliqueSet -> (gangs, cliques, scopes, clique_names, PodGang manifests): the producer, then the encoder."""
+    gangs, requests, base_of = podgangs_from_pcs(pcs, topology_levels, tas_enabled)
+    g, c, s, names = podgangs_from_manifests(gangs, requests, [k for _, k in topology_levels], class_mask=class_mask, base_of=base_of)
+    return g, c, s, names, gangs
