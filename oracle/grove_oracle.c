@@ -17,7 +17,11 @@
  *   * all-or-nothing admission               operator/internal/controller/podclique/components/pod/syncflow.go:319-358
  *   * scaled gangs gated behind their base gang                              ibid. :255-314
  *   * the outcome properties of the live-cluster e2e suites GS1-GS12 / TAS2-TAS17
- *     (operator/e2e/tests/gang_scheduling_test.go, topology_test.go).
+ *     (operator/e2e/tests/gang_scheduling_test.go, topology_test.go), the step-by-step pod counts of the
+ *     multi-step suites GS2-GS12 (tests/test_oracle_e2e_sequences.py), and the reference's own workload
+ *     files run end to end (tests/test_workload_fixtures.py)
+ *   * Preferred = best effort, widening level by level up to Required        podgang.go:110-117
+ *     (no reference test exercises it: tests/test_oracle_preferred.py restates the API comment).
  * Everything below those (which node, which domain among feasible ones, the score value) is
  * defined by DESIGN.md "Placement semantics"; this file is its executable form, written as plain
  * scalar loops that derive every ordering from the score matrix itself (no piece iterator, no
