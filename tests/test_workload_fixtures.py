@@ -171,3 +171,37 @@ def test_simple1_is_config_c1():
     assert len(g) == len(g1) == 1
     assert sorted(zip(c["min_replicas"].tolist(), c["replicas"].tolist())) == sorted(zip(c1["min_replicas"].tolist(), c1["replicas"].tolist()))
     assert sorted(n for _, n in names) == ["simple1-0-pca", "simple1-0-pcd", "simple1-0-sga-0-pcb", "simple1-0-sga-0-pcc"]
+
+
+def test_tas17_two_topologies_on_one_cluster(oracle):
+    """topology_test.go:1192-1370 on the reference's own files and its own node manifests: 28 nodes, the last 14
+    relabelled as GB200 (no kubernetes.io/rack, example.com/nvl-block + example.com/nvlink-domain instead); the domain
+    name "block" means kubernetes.io/rack in h100-topology and example.com/nvl-block in gb200-topology.  Each workload
+    must land on the segment that carries ITS topology's labels, packed in one block of that topology."""
+    kwok = json.load(open(os.path.join(HERE, "golden", "kwok_nodes_60.json")))
+    K = kwok["label_keys"]
+    ms = json.loads(json.dumps(kwok["manifests_e2e"][:28]))
+    for idx, m in enumerate(ms[14:]):
+        lab = m["metadata"]["labels"]
+        del lab[K["rack"]]
+        lab["example.com/nvl-block"] = f"block-{idx // 7}"
+        lab["example.com/nvlink-domain"] = f"nvl-domain-{idx}"
+    topologies = {
+        "e2e/yaml/tas-multi-topology-h100.yaml": [("block", K["rack"]), ("host", K["host"])],
+        "e2e/yaml/tas-multi-topology-gb200.yaml": [("block", "example.com/nvl-block"), ("rack", "example.com/nvlink-domain"), ("host", K["host"])],
+    }
+    used = {}
+    for path, levels in topologies.items():
+        pcs = pcs_of(path)
+        nodes, names, *_ = ingest.nodes_from_manifests(ms, [k for _, k in levels], used=used)
+        g, c, s, _, gangs = ingest.tables_from_pcs(pcs, levels)
+        assert gangs[0]["spec"]["topologyConstraint"]["packConstraint"]["required"] == levels[0][1]
+        r = oracle.run_cycle(nodes, len(levels), g, c, s)
+        assert (r["status"]["state"] == T.GANG_ADMITTED).all() and len(r["placements"]) == 2
+        where = [int(n) for n in r["placements"]["node"]]
+        segment = range(0, 14) if "h100" in path else range(14, 28)
+        assert all(n in segment for n in where), (path, where)
+        assert len({ms[n]["metadata"]["labels"][levels[0][1]] for n in where}) == 1     # one block of ITS topology
+        for n in where:
+            u = used.setdefault(names[n], {"memory": "0Mi", "pods": 0})
+            u["memory"] = f"{ingest.parse_mem_mib(u['memory']) + 10}Mi"; u["pods"] += 1
