@@ -225,6 +225,18 @@ Err IsBasePodGangScheduled(const PodGang* base, const std::map<std::string, int3
   return std::nullopt;
 }
 
+Condition ComputePodCliqueScheduledCondition(int32_t scheduledReplicas, int32_t minAvailable) {
+  const std::string counts = "expected at least: " + std::to_string(minAvailable) + ", found: " + std::to_string(scheduledReplicas);
+  if (scheduledReplicas < minAvailable) return {"PodCliqueScheduled", "False", "InsufficientScheduledPods", "Insufficient scheduled pods. " + counts};
+  return {"PodCliqueScheduled", "True", "SufficientScheduledPods", "Sufficient scheduled pods found. " + counts};
+}
+
+std::map<std::string, int32_t> CountScheduledReplicas(const std::vector<Binding>& bindings) {
+  std::map<std::string, int32_t> n;
+  for (const auto& b : bindings) n[b.PodName.substr(0, b.PodName.rfind('-'))]++;
+  return n;
+}
+
 Err CheckPodSchedulingGate(bool podHasGate, bool podListedInPodGang, const std::string& basePodGangName, const PodGang* base,
                            const std::map<std::string, int32_t>& scheduledReplicas, bool* removed, bool* skipped) {
   *removed = false; *skipped = false;

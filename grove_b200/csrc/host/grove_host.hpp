@@ -138,6 +138,13 @@ std::vector<FieldError> ValidateHierarchicalTopologyConstraints(const PodCliqueS
 // (podclique/reconcilestatus.go:134-141).
 Err IsBasePodGangScheduled(const PodGang* base, const std::map<std::string, int32_t>& scheduledReplicas, bool* scheduled);
 
+// What the bindings turn into on the way back (podclique/reconcilestatus.go:134-141, 255-274): ScheduledReplicas = pods of
+// the PodClique with PodScheduled=True, and the PodCliqueScheduled condition on it.
+struct Condition { std::string Type, Status, Reason, Message; };
+Condition ComputePodCliqueScheduledCondition(int32_t scheduledReplicas, int32_t minAvailable);
+// bindings of one cycle -> ScheduledReplicas per PodClique (pod names are <pclq fqn>-<ordinal>)
+std::map<std::string, int32_t> CountScheduledReplicas(const std::vector<struct Binding>& bindings);
+
 // Which pods reach a scheduler at all (checkAndRemovePodSchedulingGates, pod/syncflow.go:255-312): a pod loses its
 // grove.io/podgang-pending-creation gate when it carries the gate, is already listed in its PodGang's PodReferences,
 // and its PodGang is a base PodGang or its base PodGang is scheduled.  basePodGangName empty = the pod's PodGang is a

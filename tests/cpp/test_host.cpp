@@ -233,6 +233,22 @@ static void test_pod_scheduling_gates() {  // podclique/components/pod/syncflow_
   }
 }
 
+static void test_scheduled_condition_and_counts() {  // podclique/reconcilestatus.go:134-141, 255-274
+  auto c = ComputePodCliqueScheduledCondition(2, 3);
+  CHECK(c.Type == "PodCliqueScheduled" && c.Status == "False" && c.Reason == "InsufficientScheduledPods");
+  CHECK(c.Message == "Insufficient scheduled pods. expected at least: 3, found: 2");
+  c = ComputePodCliqueScheduledCondition(3, 3);
+  CHECK(c.Status == "True" && c.Reason == "SufficientScheduledPods" && c.Message == "Sufficient scheduled pods found. expected at least: 3, found: 3");
+  const std::vector<Binding> b = {{"default", "w-0-pc-a-0", "n0"}, {"default", "w-0-pc-a-1", "n1"}, {"default", "w-0-sg-x-0-pc-c-10", "n2"}};
+  const auto n = CountScheduledReplicas(b);
+  CHECK(n.size() == 2 && n.at("w-0-pc-a") == 2 && n.at("w-0-sg-x-0-pc-c") == 1);
+  // together with the gang predicate: bindings -> ScheduledReplicas -> is the base PodGang scheduled?
+  PodGang base; base.Namespace = "default"; base.Name = "w-0";
+  for (auto [name, mn] : std::vector<std::pair<const char*, int>>{{"w-0-pc-a", 2}, {"w-0-sg-x-0-pc-c", 1}}) { PodGroup g; g.Name = name; g.MinReplicas = mn; base.Spec.PodGroups.push_back(g); }
+  bool scheduled = false;
+  CHECK(!IsBasePodGangScheduled(&base, n, &scheduled) && scheduled);
+}
+
 static void test_encode() {
   GpuBackend be;
   CHECK(be.Name() == "gpu-scheduler");
@@ -357,6 +373,7 @@ int main(int argc, char** argv) {
   test_hierarchy_violations();
   test_is_base_podgang_scheduled();
   test_pod_scheduling_gates();
+  test_scheduled_condition_and_counts();
   test_encode();
   if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); }
   else {  // without a CUDA device Init must fail loudly, never fall back
