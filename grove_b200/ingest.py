@@ -14,7 +14,6 @@ counterpart used by tools and tests.
 """
 from __future__ import annotations
 
-import numpy as np
 
 from . import tables as T
 

@@ -5,7 +5,6 @@ import os
 import re
 import subprocess
 
-import numpy as np
 import pytest
 
 from grove_b200 import tables as T
