@@ -91,11 +91,13 @@ def _preferred(tc, level_keys):
     return None if pref is None or (req is not None and pref <= req) else pref
 
 
-def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=None, class_mask=0xFFFF, base_of=None):
+def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=None, class_mask=0xFFFF, base_of=None, placed_on=None):
     """PodGang manifests -> (gangs, cliques, scopes, clique_names) with clique_names[row] = (gang name, PodGroup name).
 
     Cliques of one TopologyConstraintGroupConfig are made adjacent (one scope each); PodGroups in no group form
     the implicit first scope.  base_of: optional {scaled gang name: base gang name} (gating, syncflow.go:319-358).
+    placed_on: optional {PodGang name: node index} of earlier placements; spec.reuseReservationRef (podgang.go:66-71,
+    a locality hint) resolves through it to the gang's anchor node.
     """
     b = T.GangTableBuilder()
     names, row_of = [], {pg["metadata"]["name"]: i for i, pg in enumerate(podgangs)}
@@ -120,7 +122,8 @@ def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=Non
             scopes.append((_level(gc.get("topologyConstraint"), level_keys), [clique(groups[n]) for n in gc["podGroupNames"]],
                            _preferred(gc.get("topologyConstraint"), level_keys)))
         base = (base_of or {}).get(pg["metadata"]["name"])
-        b.add_gang(scopes, level=_level(spec.get("topologyConstraint"), level_keys),
+        anchor = (placed_on or {}).get((spec.get("reuseReservationRef") or {}).get("name"))
+        b.add_gang(scopes, level=_level(spec.get("topologyConstraint"), level_keys), anchor=anchor,
                    preferred=_preferred(spec.get("topologyConstraint"), level_keys),
                    priority=(priority_classes or {}).get(spec.get("priorityClassName", ""), 0),
                    base=row_of[base] if base in row_of else None)
@@ -210,3 +213,31 @@ def tables_from_pcs(pcs: dict, topology_levels, tas_enabled: bool = True, class_
     gangs, requests, base_of = podgangs_from_pcs(pcs, topology_levels, tas_enabled)
     g, c, s, names = podgangs_from_manifests(gangs, requests, [k for _, k in topology_levels], class_mask=class_mask, base_of=base_of)
     return g, c, s, names, gangs
+
+
+# ------------------------------------------------------------------------------------------------
+# The way back: a cycle's outputs in the shapes the API objects carry them.
+# ------------------------------------------------------------------------------------------------
+def bindings(placements, podgangs, clique_names, node_names):
+    """placement entries -> [(pod namespace, pod name, node name)]: the r-th entry of a clique binds the r-th
+    PodReference of its PodGroup (podgang.go:75-91; sorted by name by the operator, podgang.go:175-177)."""
+    refs = {(pg["metadata"]["name"], g["name"]): g["podReferences"] for pg in podgangs for g in pg["spec"]["podgroups"]}
+    seen, out = {}, []
+    for q, n in zip(placements["clique"].tolist(), placements["node"].tolist()):
+        r = seen.get(q, 0); seen[q] = r + 1
+        ref = refs[clique_names[q]][r]
+        out.append((ref.get("namespace", "default"), ref["name"], node_names[n]))
+    return out
+
+
+def podgang_status(row) -> dict:
+    """one grove_gang_status_t -> PodGang.status (podgang.go:141-190): phase, placementScore (1.0 = best), and the
+    Scheduled condition with the reason a user sees on an unschedulable gang"""
+    state = int(row["state"])
+    reason = {T.GANG_ADMITTED: "Scheduled", T.GANG_REJECTED: "Unschedulable", T.GANG_BASE_REJECTED: "BaseNotScheduled",
+              T.GANG_GATED_SKIP: "Gated"}.get(state, "Pending")
+    st = {"phase": "Starting" if state == T.GANG_ADMITTED else "Pending",
+          "conditions": [{"type": "Scheduled", "status": "True" if state == T.GANG_ADMITTED else "False", "reason": reason}]}
+    if state == T.GANG_ADMITTED and int(row["score_den"]):
+        st["placementScore"] = int(row["score_num"]) / int(row["score_den"])
+    return st

@@ -125,3 +125,27 @@ def test_preferred_keys_become_preferred_levels(kwok, oracle):
     with pytest.raises(ValueError):
         bad = _podgang("x", [("a", 1, 1, None)]); bad["spec"]["topologyConstraint"] = {"packConstraint": {"preferred": "example.com/nope"}}
         ingest.podgangs_from_manifests([bad], {}, [Z, B, R, H])
+
+
+def test_reuse_reservation_ref_bindings_and_status(kwok, oracle):
+    """spec.reuseReservationRef -> anchor; placements -> (pod, node) bindings; status rows -> PodGang.status"""
+    Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
+    nodes, node_names, *_ = ingest.nodes_from_manifests(kwok["manifests_e2e"][:28], [Z, B, R, H])
+    first = _podgang("first", [("a", 2, 2, None)], gang_key=R)
+    again = _podgang("again", [("w", 3, 3, None)], gang_key=R)
+    again["spec"]["reuseReservationRef"] = {"namespace": "default", "name": "first"}
+    huge = _podgang("huge", [("x", 9, 9, H)])           # nine 40 MiB pods on one 150 MiB host: unschedulable
+    req = {"a": {"memory": "40Mi"}, "w": {"memory": "40Mi"}, "x": {"memory": "40Mi"}}
+    g, c, s, names = ingest.podgangs_from_manifests([first], req, [Z, B, R, H])
+    r = oracle.run_cycle(nodes, 4, g, c, s)
+    b1 = ingest.bindings(r["placements"], [first], names, node_names)
+    assert [p for _, p, _ in b1] == ["a-0", "a-1"] and all(n.startswith("kwok-node-") for _, _, n in b1)
+    landed = int(r["placements"]["node"][0])
+    g, c, s, names = ingest.podgangs_from_manifests([again, huge], req, [Z, B, R, H], placed_on={"first": landed})
+    assert g["anchor_node"].tolist() == [landed, T.NONE_U32]
+    r2 = oracle.run_cycle(r["nodes_after"], 4, g, c, s)
+    b2 = ingest.bindings(r2["placements"], [again, huge], names, node_names)
+    assert len(b2) == 3 and {int(nodes["dom"][node_names.index(n), 2]) for _, _, n in b2} == {int(nodes["dom"][landed, 2])}   # same rack as "first"
+    st = [ingest.podgang_status(row) for row in r2["status"]]
+    assert st[0]["phase"] == "Starting" and st[0]["conditions"][0]["status"] == "True" and 0 < st[0]["placementScore"] <= 1.0
+    assert st[1] == {"phase": "Pending", "conditions": [{"type": "Scheduled", "status": "False", "reason": "Unschedulable"}]}
