@@ -164,7 +164,9 @@ def config_c4(n=50000, g=10000, seed=SEED_BASE + 4, max_used_pct=90):
     3 selector classes, 3 priority classes.  A quarter of the gangs are base gangs
     (router x2 + 2 scaling groups x (leader x1 + worker x4)), the rest scaled gangs (one scaling-group
     replica each) gated behind a base gang: the hierarchical PodCliqueScalingGroup structure of
-    syncflow.go:189-333.  Gang Required=block, scaling-group scope Required=rack, leaders Required=host."""
+    syncflow.go:189-333.  Gang Required=block, scaling-group scope Required=rack, leaders Required=host.
+    Every PodGang of a PodCliqueSet carries the set's PriorityClassName (podgang/podgang.go:158), so a
+    scaled gang has its base gang's priority."""
     nodes = kwok_nodes(n, [2520, 126, 18, 1])
     pre_use(nodes, seed, max_used_pct)
     cls = _rand_below(seed, 20, n, 3)
@@ -186,7 +188,7 @@ def config_c4(n=50000, g=10000, seed=SEED_BASE + 4, max_used_pct=90):
                        level=1, priority=int(pr[gi]))
         else:
             base = (gi - n_base) % n_base
-            b.add_gang([(2, [lead, work])], level=1, priority=int(pr[gi]), base=base)
+            b.add_gang([(2, [lead, work])], level=1, priority=int(pr[base]), base=base)
     return dict(name="C4", n_levels=4, nodes=nodes, tables=b.build())
 
 

@@ -15,8 +15,6 @@ NONE_U32 = 0xFFFFFFFF
 MAX_GANG_PODS = 128
 MAX_GANG_CLIQUES = 32
 MAX_GANG_SCOPES = 32
-MAX_ALTERNATIVES = 8
-SUBROUNDS = 8
 
 NODE_SCHEDULABLE = 0x1
 NODE_CLASS_SHIFT = 8
@@ -43,22 +41,23 @@ gang_dt = np.dtype([
 ])
 placement_dt = np.dtype([("clique", "<u4"), ("node", "<u4")])
 status_dt = np.dtype([
-    ("state", "u1"), ("score_num", "u1"), ("score_den", "u1"), ("round", "u1"), ("n_pods", "<u4"),
-    ("placement_off", "<u4"), ("top_domain_lo", "<u4"),
+    ("state", "u1"), ("level", "u1"), ("reserved0", "<u2"), ("score_num", "<u2"), ("score_den", "<u2"),
+    ("n_pods", "<u4"), ("placement_off", "<u4"), ("domain_node", "<u4"), ("reserved1", "<u4", (3,)),
 ])
+scope_status_dt = np.dtype([("level", "u1"), ("reserved", "u1", (3,)), ("domain_node", "<u4")])
 config_dt = np.dtype([
-    ("abi_version", "<u4"), ("device", "<i4"), ("n_levels", "<u4"), ("max_rounds", "<u4"),
-    ("rank", "<u4"), ("world", "<u4"), ("alternatives", "<u4"), ("reserved", "<u4"),
+    ("abi_version", "<u4"), ("device", "<i4"), ("n_levels", "<u4"), ("window", "<u4"),
+    ("rank", "<u4"), ("world", "<u4"), ("reserved", "<u4", (2,)),
 ])
 stats_dt = np.dtype([
     ("rounds", "<u4"), ("gangs_admitted", "<u4"), ("gangs_rejected", "<u4"), ("pods_bound", "<u4"),
-    ("pairs_evaluated", "<u8"), ("kernel_launches", "<u8"), ("ms_fit", "<f4"), ("ms_score", "<f4"),
+    ("pairs_evaluated", "<u8"), ("kernel_launches", "<u8"), ("evaluations", "<u8"), ("ms_fit", "<f4"), ("ms_score", "<f4"),
     ("ms_admit", "<f4"), ("ms_commit", "<f4"), ("ms_total", "<f4"), ("reserved", "<f4"),
 ])
 
 assert node_dt.itemsize == 32 and clique_dt.itemsize == 16 and scope_dt.itemsize == 8
-assert gang_dt.itemsize == 32 and placement_dt.itemsize == 8 and status_dt.itemsize == 16
-assert config_dt.itemsize == 32 and stats_dt.itemsize == 56
+assert gang_dt.itemsize == 32 and placement_dt.itemsize == 8 and status_dt.itemsize == 32 and scope_status_dt.itemsize == 8
+assert config_dt.itemsize == 32 and stats_dt.itemsize == 64
 
 
 def make_nodes(n: int) -> np.ndarray:

@@ -18,11 +18,17 @@
  *                                    operator/internal/scheduler/types.go:45-47
  *                                    payload = PodGangSpec, scheduler/api/core/v1alpha1/podgang.go:51-131
  *   grove_run_cycle                  the scheduling cycle itself (absent from the
- *                                    reference tree; KAI-Scheduler v0.14.0, operator/go.mod:11)
+ *                                    reference tree; KAI-Scheduler v0.14.0, operator/go.mod:11).
+ *                                    Result = the SEQUENTIAL pass: gangs one at a time in (priority desc,
+ *                                    submission index asc) order, each against the state the earlier ones left
+ *                                    (PriorityClassName, podgang.go:62-64); the engine reaches it by parallel
+ *                                    relaxation, bit-identical to oracle/grove_oracle_seq.c
  *   grove_get_placements             Pod.spec.nodeName bindings, counted back by
  *                                    operator/internal/controller/podclique/reconcilestatus.go:134-141
  *   grove_get_gang_status            PodGangStatus{Phase,PlacementScore},
  *                                    scheduler/api/core/v1alpha1/podgang.go:141-150,182-190
+ *   grove_get_scope_domains          the topology domain chosen for every TopologyConstraintGroupConfig
+ *                                    (podgang.go:120-131) -- what a binder needs to explain a placement
  *
  * cgo rules honoured: plain pointers + sizes only, every input array is copied
  * before the call returns (no Go pointer is retained), outputs go to
@@ -41,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GROVE_ABI_VERSION 1u
+#define GROVE_ABI_VERSION 2u
 
 #define GROVE_MAX_LEVELS 4u          /* topology levels, index 0 = broadest (GREP-244 README.md:143) */
 #define GROVE_LEVEL_NONE 0xFFu       /* "no pack constraint at this scope" */
@@ -51,12 +57,6 @@ extern "C" {
 #define GROVE_MAX_GANG_CLIQUES 32u
 #define GROVE_MAX_GANG_SCOPES 32u
 #define GROVE_MAX_NODES (1u << 24)
-#ifndef GROVE_MAX_ALTERNATIVES
-#define GROVE_MAX_ALTERNATIVES 8u    /* feasible placements kept per gang per round */
-#endif
-#ifndef GROVE_SUBROUNDS
-#define GROVE_SUBROUNDS 8u           /* conflict-resolution passes over the alternatives per round */
-#endif
 
 /* error codes (all entry points return 0 on success, <0 on error) */
 #define GROVE_OK 0
@@ -114,11 +114,14 @@ typedef struct grove_gang {
   uint32_t scope_off;     /* into the scopes array */
   uint16_t n_cliques;
   uint16_t n_scopes;
-  int32_t priority;       /* PriorityClass value; higher goes first */
+  int32_t priority;       /* PriorityClass value (PodGangSpec.PriorityClassName resolved, podgang.go:62-64):
+                             gangs are placed strictly in (priority desc, submission index asc) order */
   uint32_t anchor_node;   /* caller's node index to score distance against (ReuseReservationRef hint,
                              podgang.go:66-71), or GROVE_NONE_U32 = engine derives hash(gang index) % N */
   uint32_t base_gang;     /* scaled gang: index of its base gang in this submission (gated behind it,
-                             pod/syncflow.go:319-358), or GROVE_NONE_U32 */
+                             pod/syncflow.go:319-358), or GROVE_NONE_U32.  Considered at its own turn: admitted
+                             only if the base gang was admitted EARLIER in this cycle's order, else
+                             GROVE_GANG_BASE_REJECTED (it waits for the next cycle, like its gated pods do) */
   uint8_t level;          /* PodGangSpec.TopologyConstraint Required level index, or GROVE_LEVEL_NONE */
   uint8_t preferred;      /* PackConstraint.Preferred level index (podgang.go:110-117): best effort, tried before
                              falling back level by level up to `level`; deeper than `level`; or GROVE_LEVEL_NONE */
@@ -135,41 +138,56 @@ typedef struct grove_placement {
 
 #define GROVE_GANG_PENDING 0u       /* never seen by a cycle */
 #define GROVE_GANG_ADMITTED 1u      /* all MinReplicas bound (Scheduled=True) */
-#define GROVE_GANG_REJECTED 2u      /* no feasible domain: Unschedulable, nothing bound */
+#define GROVE_GANG_REJECTED 2u      /* no feasible domain at its turn: Unschedulable, nothing bound */
 #define GROVE_GANG_GATED_SKIP 3u    /* GROVE_GANG_GATED set */
-#define GROVE_GANG_BASE_REJECTED 4u /* base gang was not admitted */
+#define GROVE_GANG_BASE_REJECTED 4u /* base gang not admitted before this gang's turn */
 typedef struct grove_gang_status {
   uint8_t state;
-  uint8_t score_num;       /* PlacementScore = score_num / score_den, (0,1]; 0/0 when not admitted */
-  uint8_t score_den;
-  uint8_t round;           /* optimistic round in which the gang was resolved */
+  uint8_t level;           /* level of the domain the whole gang was packed into (its Required level, or the deeper
+                              Preferred level that held), GROVE_LEVEL_NONE = the whole cluster / not admitted */
+  uint16_t reserved0;
+  uint16_t score_num;      /* PlacementScore = score_num / score_den (podgang.go:187-189): over the gang, its scopes and
+                              its cliques that carry a pack constraint, (levels honoured) / (levels asked for), where
+                              asked = Preferred if set else Required; 1/1 when nothing was asked or everything held;
+                              0/0 when not admitted */
+  uint16_t score_den;
   uint32_t n_pods;         /* pods bound (>= sum MinReplicas when admitted) */
   uint32_t placement_off;  /* first entry in grove_get_placements output */
-  uint32_t top_domain_lo;  /* caller-order is not contiguous: first SORTED node index of chosen gang domain, or NONE */
+  uint32_t domain_node;    /* caller index of the first node (topology order) of that gang domain, or GROVE_NONE_U32 */
+  uint32_t reserved1[3];
 } grove_gang_status_t;
+
+/* chosen domain of one scope (same indexing as the scopes array of the submission) */
+typedef struct grove_scope_status {
+  uint8_t level;           /* level of the domain the scope's cliques share; GROVE_LEVEL_NONE = no own domain (packed in
+                              the gang's domain) or gang not admitted */
+  uint8_t reserved[3];
+  uint32_t domain_node;    /* caller index of the first node (topology order) of that domain, or GROVE_NONE_U32 */
+} grove_scope_status_t;
 
 typedef struct grove_config {
   uint32_t abi_version;  /* GROVE_ABI_VERSION */
   int32_t device;        /* CUDA ordinal */
   uint32_t n_levels;     /* 1..GROVE_MAX_LEVELS */
-  uint32_t max_rounds;   /* 0 = default (unbounded until every gang is resolved) */
-  uint32_t rank;         /* gang-row sharding: this handle evaluates gangs g with g % world == rank */
-  uint32_t world;        /* 0 or 1 = unsharded */
-  uint32_t alternatives; /* 1..GROVE_MAX_ALTERNATIVES, 0 = default (GROVE_MAX_ALTERNATIVES) */
-  uint32_t reserved;
+  uint32_t window;       /* gangs beyond the settled prefix that relax concurrently; 0 = default.  A tuning knob:
+                            results do not depend on it */
+  uint32_t rank;         /* multi-GPU: this handle's rank ... */
+  uint32_t world;        /* ... of `world` handles driving the same cycle; 0 or 1 = single GPU */
+  uint32_t reserved[2];
 } grove_config_t;
 
 typedef struct grove_cycle_stats {
-  uint32_t rounds;
+  uint32_t rounds;           /* relaxation rounds the engine took (an implementation figure, not a result) */
   uint32_t gangs_admitted;
-  uint32_t gangs_rejected;
+  uint32_t gangs_rejected;   /* REJECTED + BASE_REJECTED */
   uint32_t pods_bound;
-  uint64_t pairs_evaluated;  /* (clique,node) pairs through fit+score, all rounds */
+  uint64_t pairs_evaluated;  /* (clique,node) pairs through fit+score (K1/K2 over the cycle-start snapshot) */
   uint64_t kernel_launches;
-  float ms_fit;              /* CUDA-event device time per kernel family, summed over rounds */
-  float ms_score;
-  float ms_admit;
-  float ms_commit;
+  uint64_t evaluations;      /* gang evaluations (K3) over all rounds; >= gangs considered */
+  float ms_fit;              /* CUDA-event device time: K1 + capacity tables */
+  float ms_score;            /* K2 (beside the relaxation, on its own stream) */
+  float ms_admit;            /* relaxation rounds: evaluate / publish / detect / settle */
+  float ms_commit;           /* output compaction */
   float ms_total;            /* first launch -> last kernel done */
   float reserved;
 } grove_cycle_stats_t;
@@ -192,46 +210,20 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
                            const grove_clique_t* cliques, uint32_t n_cliques,
                            const grove_scope_t* scopes, uint32_t n_scopes);
 
-/* blocking: fit -> score -> admit -> commit, optimistic rounds until every gang is resolved */
+/* blocking: fit -> score -> admit -> commit; on return every gang is decided */
 int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats);
 
 int32_t grove_get_placements(grove_engine_t* e, grove_placement_t* out, uint32_t cap, uint32_t* n_out);
 int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint32_t cap);
+int32_t grove_get_scope_domains(grove_engine_t* e, grove_scope_status_t* out, uint32_t cap);
 
 /* ---- device-resident variants (inputs already in HBM; used by bench.py `value`) -------------- */
 /* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load */
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);
 
-/* ---- multi-GPU stepping: one handle per rank (cfg.rank / cfg.world) -------------------------------
- * Gang rows are dealt g % world to ranks; the node table and the gang states are replicated.  A round
- * has two halves: each rank EVALUATES its own gangs (fit -> score -> up to `alternatives` feasible
- * placements per gang) into an exchange buffer that is zero for gangs it does not own; after one
- * all-reduce SUM over that buffer every rank RESOLVES the conflicts and commits identically.  Results
- * are bit-identical for every world size.  The buffer is a DEVICE pointer owned by the engine, int32
- * words; the host (torch.distributed / NCCL) reduces it in place:
- *
- *   grove_cycle_begin
- *   loop: grove_round_eval(&buf,&n,&go); if (!go) break;     all-reduce SUM over buf[n]
- *         grove_round_resolve(&remaining);
- *   grove_cycle_end(&stats)
- *
- * Every call is synchronous (its kernels are complete on return).  With world <= 1 the same sequence
- * is valid without the reduction, and grove_run_cycle is the fused form of it. */
-int32_t grove_cycle_begin(grove_engine_t* e);
-int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, uint32_t* go);
-int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining);
-int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats);
-/* The CUDA stream (cudaStream_t) every engine kernel runs on.  A host that enqueues its reduction ON THIS
- * STREAM (ncclAllReduce(..., stream), or torch.cuda.ExternalStream) may switch the stepping calls to
- * stream-ordered completion with grove_set_stream_ordered(e, 1): they then return without waiting for their
- * kernels, and eval -> all-reduce -> resolve are ordered by the stream alone (no host synchronisation). */
-int32_t grove_engine_stream(grove_engine_t* e, void** stream);
-int32_t grove_set_stream_ordered(grove_engine_t* e, int32_t on);
-
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */
 int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap);
-/* matrices as the last round left them (create the engine with max_rounds = 1 to read round 1):
- * fit bitmap row (ceil(n/32) words) and score row (n bytes) of one clique */
+/* K1 / K2 output over the cycle-start snapshot: fit bitmap row (ceil(n/32) words) and score row (n bytes) of one clique */
 int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* words, uint32_t cap_words);
 int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* bytes, uint32_t cap_bytes);
 #ifdef __cplusplus

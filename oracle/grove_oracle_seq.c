@@ -1,16 +1,27 @@
 /*
- * grove_oracle.c -- CPU restatement of the gang-placement cycle.  TEST INFRASTRUCTURE ONLY.
+ * grove_oracle_seq.c -- CPU restatement of the gang-placement cycle: the SEQUENTIAL, priority-ordered pass.
+ * TEST INFRASTRUCTURE ONLY.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libgrove_place.so) never links, loads or calls it.
+ *
+ * What it is: gangs are taken ONE AT A TIME in (priority desc, submission index asc) order
+ * (PodGangSpec.PriorityClassName, scheduler/api/core/v1alpha1/podgang.go:62-64);
+ * each is evaluated against the node state the earlier ones left, packed all-or-nothing, and its
+ * resources are subtracted before the next gang is looked at.  There are no rounds, no alternatives and
+ * no concurrency in here: this is the definition the CUDA engine (which reaches the same answer by
+ * parallel relaxation) is compared with bit for bit.
  *
  * PARITY STATUS: "parity unpinned" at node level.  The reference tree (ai-dynamo/grove @ 08ad3b37)
  * contains no scheduler: placement is done by KAI-Scheduler v0.14.0 (operator/go.mod:11), which is
  * not vendored, and there is no Go toolchain in this image.  What the reference does pin -- and
  * what tests/test_oracle_e2e_properties.py checks this file against -- is
  *   * the input schema             scheduler/api/core/v1alpha1/podgang.go:51-131
+ *   * priority order of gangs                                                 podgang.go:62-64
  *   * MinReplicas = gang guarantee, surplus best effort                      podgang.go:80-83
  *   * Required pack constraint = all pods of the scope share one label value podgang.go:101-109
+ *   * Preferred = best effort, widening level by level up to Required        podgang.go:110-117
+ *   * PlacementScore 1.0 = best possible placement                           podgang.go:187-189
  *   * nodes lacking the label are not candidates      docs/proposals/244-topology-aware-scheduling/README.md:65
  *   * level index 0 is the broadest                                          ibid. :143
  *   * scope nesting gang >= group-config >= pod-group   operator/internal/webhook/admission/pcs/validation/topologyconstraints.go:195-202
@@ -19,13 +30,11 @@
  *   * the outcome properties of the live-cluster e2e suites GS1-GS12 / TAS2-TAS17
  *     (operator/e2e/tests/gang_scheduling_test.go, topology_test.go), the step-by-step pod counts of the
  *     multi-step suites GS2-GS12 (tests/test_oracle_e2e_sequences.py), and the reference's own workload
- *     files run end to end (tests/test_workload_fixtures.py)
- *   * Preferred = best effort, widening level by level up to Required        podgang.go:110-117
- *     (no reference test exercises it: tests/test_oracle_preferred.py restates the API comment).
- * Everything below those (which node, which domain among feasible ones, the score value) is
- * defined by DESIGN.md "Placement semantics"; this file is its executable form, written as plain
- * scalar loops that derive every ordering from the score matrix itself (no piece iterator, no
- * warp tricks) so that it shares no code or shortcut with the CUDA path.
+ *     files run end to end (tests/test_workload_fixtures.py).
+ * Everything below those (which node, which domain among feasible ones) is defined by DESIGN.md
+ * "Placement semantics"; this file is its executable form, written as plain scalar loops that derive
+ * every ordering from the score row itself (no piece iterator, no warp tricks, no capacity tables) so
+ * that it shares no code or shortcut with the CUDA path.
  *
  * Build: make -C oracle   (gcc -O2 -fopenmp -shared)
  */
@@ -41,15 +50,14 @@
 #define VDEPTH_SHIFT 16u /* internal: valid label depth in flags bits 16..19 */
 
 typedef struct oracle_stats {
-  uint32_t rounds;
   uint32_t gangs_admitted;
-  uint32_t gangs_rejected;
+  uint32_t gangs_rejected;   /* REJECTED + BASE_REJECTED */
   uint32_t pods_bound;
-  uint64_t pairs_evaluated;
-  double seconds_eval;   /* fit+score+admit per-gang evaluation, all rounds */
+  uint32_t threads;          /* OpenMP threads used for the per-gang fit/score rows (the gang loop is sequential) */
+  uint64_t pairs_evaluated;  /* (clique,node) pairs through fit+score */
   double seconds_total;
-  uint32_t non_tree_labels; /* raw label ids that appeared under more than one parent */
-  uint32_t threads;
+  uint32_t non_tree_labels;  /* raw label ids that appeared under more than one parent */
+  uint32_t reserved;
 } oracle_stats_t;
 
 typedef struct topo {
@@ -164,25 +172,10 @@ typedef struct ctx {
   const grove_gang_t* gangs;
   const grove_clique_t* cliques;
   const grove_scope_t* scopes;
-  uint32_t* order;   /* gang -> rank by (priority desc, index asc) */
   uint32_t* anchor;  /* gang -> sorted node index */
-  uint32_t* pod_off; /* gang -> first slot */
 } ctx_t;
 
-typedef struct entry { uint32_t node; uint8_t clique_rel; uint8_t score; } entry_t;
-
-/* Exchange buffer of one round (int32 words; also the all-reduce payload of the multi-rank protocol):
- *   [0, K*P)          alt_node   entry i of alternative a of gang g at a*P + pod_off[g] + i (sorted node index)
- *   [K*P, 2*K*P)      alt_meta   clique_rel | score << 8
- *   then G*K words each: alt_n (entries incl. surplus), alt_score (min score over MinReplicas pods),
- *   alt_top (first sorted node of the gang domain); then G words nalt. */
-typedef struct xlay { size_t node, meta, n, score, top, nalt, words; uint32_t K; } xlay_t;
-static xlay_t xlayout(uint32_t K, uint32_t P, uint32_t G) {
-  xlay_t x; x.K = K;
-  x.node = 0; x.meta = (size_t)K * P; x.n = 2 * (size_t)K * P; x.score = x.n + (size_t)G * K; x.top = x.score + (size_t)G * K;
-  x.nalt = x.top + (size_t)G * K; x.words = x.nalt + G;
-  return x;
-}
+typedef struct entry { uint32_t node; uint8_t clique_rel; } entry_t;
 
 static uint32_t fmix32(uint32_t x) {
   x = x * 0x9E3779B1u + 0x7F4A7C15u;
@@ -238,15 +231,29 @@ static int level_span(uint32_t req, uint32_t pref, int lvl, int* first) {
 }
 static inline uint32_t scope_pref(const grove_scope_t* s) { return s->preferred1 ? (uint32_t)s->preferred1 - 1u : GROVE_LEVEL_NONE; }
 
+/* PlacementScore bookkeeping (podgang.go:187-189): a unit that carries a pack
+ * constraint asked for `want` = Preferred if set else Required; it was packed at level `got`
+ * (-1 = no domain of its own).  Levels count from 1 (level index + 1): credit min(got, want) + 1 of want + 1. */
+typedef struct score { uint32_t num, den; } score_t;
+static void score_unit(score_t* sc, uint32_t req, uint32_t pref, int got) {
+  if (req == GROVE_LEVEL_NONE && pref == GROVE_LEVEL_NONE) return;
+  const int want = pref != GROVE_LEVEL_NONE ? (int)pref : (int)req;
+  sc->den += (uint32_t)want + 1u;
+  sc->num += (uint32_t)((got < want ? got : want) + 1);
+}
+
 typedef struct geval {
   const ctx_t* C;
   uint32_t g;
   uint32_t a;
-  uint8_t* Trow[GROVE_MAX_GANG_CLIQUES]; /* score rows of this gang's cliques, round-start state */
+  uint8_t* Trow[GROVE_MAX_GANG_CLIQUES]; /* score rows of this gang's cliques against the current state */
   uint32_t ndepth[GROVE_MAX_GANG_CLIQUES];
   entry_t st[GROVE_MAX_GANG_PODS];
   uint32_t np;
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
+  int c_got[GROVE_MAX_GANG_CLIQUES];   /* level each clique / scope was packed at (-1: the parent range) */
+  int s_got[GROVE_MAX_GANG_SCOPES];
+  uint32_t s_lo[GROVE_MAX_GANG_SCOPES];
 } geval_t;
 
 /* how many more pods of clique cr fit on node n given the pods this gang already put there */
@@ -285,7 +292,7 @@ static uint32_t take(geval_t* E, uint32_t cr, uint32_t lo, uint32_t hi, uint32_t
       uint32_t c = cap_now(E, cr, n);
       uint32_t t = c < (want - placed) ? c : (want - placed);
       for (uint32_t j = 0; j < t; ++j) {
-        E->st[E->np].node = n; E->st[E->np].clique_rel = (uint8_t)cr; E->st[E->np].score = (uint8_t)s;
+        E->st[E->np].node = n; E->st[E->np].clique_rel = (uint8_t)cr;
         E->np++;
       }
       placed += t;
@@ -337,7 +344,7 @@ static cand_t* subdomains(const geval_t* E, uint32_t l, uint32_t lo, uint32_t hi
   return v;
 }
 
-/* cliques of one scope inside range E_=[lo,hi) whose level is `lvl` (-1 = ROOT) */
+/* cliques of one scope inside range [lo,hi) whose level is `lvl` (-1 = ROOT) */
 static int place_scope(geval_t* E, const grove_scope_t* s, uint32_t lo, uint32_t hi, int lvl) {
   const grove_gang_t* g = &E->C->gangs[E->g];
   uint32_t mark = E->np;
@@ -353,6 +360,7 @@ static int place_scope(geval_t* E, const grove_scope_t* s, uint32_t lo, uint32_t
       } else {
         ok = fill_min(E, cr, lo, hi);
       }
+      if (ok) E->c_got[cr] = l;
     }
     if (!ok) { E->np = mark; return 0; }
   }
@@ -369,43 +377,25 @@ static int place_in(geval_t* E, uint32_t lo, uint32_t hi, int lvl) {
     for (int l = first; l >= base && !ok; --l) {
       if (l > lvl) {
         uint32_t nc; cand_t* v = subdomains(E, (uint32_t)l, lo, hi, &nc);
-        for (uint32_t k = 0; k < nc && !ok; ++k) ok = place_scope(E, s, v[k].lo, v[k].hi, l);
+        for (uint32_t k = 0; k < nc && !ok; ++k) { ok = place_scope(E, s, v[k].lo, v[k].hi, l); if (ok) E->s_lo[si] = v[k].lo; }
         free(v);
       } else {
         ok = place_scope(E, s, lo, hi, lvl);
+        if (ok) E->s_lo[si] = lo;
       }
+      if (ok) E->s_got[si] = l;
     }
     if (!ok) { E->np = 0; return 0; }
   }
   return 1;
 }
 
-/* surplus beyond MinReplicas (best effort, podgang.go:80-83) and publication of one alternative */
-static void emit_alt(geval_t* E, const xlay_t* X, int32_t* xb, uint32_t P, uint32_t pod_off, uint32_t a, uint32_t top_lo) {
-  const ctx_t* C = E->C;
-  const grove_gang_t* g = &C->gangs[E->g];
-  uint32_t min_score = C->T.L + 1;
-  for (uint32_t i = 0; i < E->np; ++i) if (E->st[i].score < min_score) min_score = E->st[i].score;
-  for (uint32_t cr = 0; cr < g->n_cliques; ++cr) {
-    const grove_clique_t* q = &C->cliques[g->clique_off + cr];
-    uint32_t extra = q->replicas > q->min_replicas ? (uint32_t)(q->replicas - q->min_replicas) : 0;
-    if (extra) take(E, cr, E->Hlo[cr], E->Hhi[cr], extra);
-  }
-  for (uint32_t i = 0; i < E->np; ++i) {
-    xb[X->node + (size_t)a * P + pod_off + i] = (int32_t)E->st[i].node;
-    xb[X->meta + (size_t)a * P + pod_off + i] = (int32_t)((uint32_t)E->st[i].clique_rel | ((uint32_t)E->st[i].score << 8));
-  }
-  xb[X->n + (size_t)E->g * X->K + a] = (int32_t)E->np;
-  xb[X->score + (size_t)E->g * X->K + a] = (int32_t)min_score;
-  xb[X->top + (size_t)E->g * X->K + a] = (int32_t)top_lo;
-}
-
-/* one gang against the round-start state: its first K feasible gang-level domains in score order, each
- * packed independently ("alternatives"); a gang without a gang-level constraint has one candidate (the
- * whole cluster).  With a Preferred level the candidate list is the Preferred level's domains in score
- * order, then each wider level's, down to the Required level (or the whole cluster). */
-static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, const xlay_t* X, int32_t* xb, uint32_t P) {
-  geval_t* E = malloc(sizeof(geval_t));
+/* One gang against the current node state: its first feasible gang-level domain in score order (the whole
+ * cluster when it has no gang-level constraint).  With a Preferred level the candidate list is the Preferred
+ * level's domains in score order, then each wider level's, down to the Required level (or the whole
+ * cluster).  On success E->st[0..np) holds the pods (MinReplicas of every clique in scope/clique order, then
+ * the best-effort surplus, podgang.go:80-83) and *n_min the MinReplicas part.  Returns 1 if feasible. */
+static int eval_gang(geval_t* E, const ctx_t* C, uint32_t gi, uint8_t* const* Trow, int* g_got, uint32_t* g_lo, uint32_t* n_min) {
   memset(E, 0, sizeof(*E));
   const grove_gang_t* g = &C->gangs[gi];
   E->C = C; E->g = gi; E->a = C->anchor[gi];
@@ -417,20 +407,25 @@ static void eval_gang(const ctx_t* C, uint32_t gi, uint8_t* const* Trow, const x
     }
   }
   for (uint32_t cr = 0; cr < g->n_cliques; ++cr) E->Trow[cr] = Trow[cr];
-  uint32_t na = 0;
-  int first, base = level_span(g->level, g->preferred, -1, &first);
-  for (int l = first; l >= base && na < X->K; --l) {
+  int ok = 0, first, base = level_span(g->level, g->preferred, -1, &first);
+  for (int l = first; l >= base && !ok; --l) {
     if (l < 0) {
-      if (place_in(E, 0, C->T.n, -1)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, 0);
+      ok = place_in(E, 0, C->T.n, -1);
+      if (ok) { *g_got = -1; *g_lo = 0; }
     } else {
       uint32_t nc; cand_t* v = subdomains(E, (uint32_t)l, 0, C->T.n, &nc);
-      for (uint32_t k = 0; k < nc && na < X->K; ++k)
-        if (place_in(E, v[k].lo, v[k].hi, l)) emit_alt(E, X, xb, P, C->pod_off[gi], na++, v[k].lo);
+      for (uint32_t k = 0; k < nc && !ok; ++k) { ok = place_in(E, v[k].lo, v[k].hi, l); if (ok) { *g_got = l; *g_lo = v[k].lo; } }
       free(v);
     }
   }
-  xb[X->nalt + gi] = (int32_t)na;
-  free(E);
+  if (!ok) return 0;
+  *n_min = E->np;
+  for (uint32_t cr = 0; cr < g->n_cliques; ++cr) {
+    const grove_clique_t* q = &C->cliques[g->clique_off + cr];
+    uint32_t extra = q->replicas > q->min_replicas ? (uint32_t)(q->replicas - q->min_replicas) : 0;
+    if (extra) take(E, cr, E->Hlo[cr], E->Hhi[cr], extra);
+  }
+  return 1;
 }
 
 static double now_s(void) {
@@ -485,266 +480,154 @@ int32_t oracle_validate(const grove_gang_t* gangs, uint32_t G, const grove_cliqu
 }
 
 /*
- * One scheduling cycle.  Optimistic rounds (DESIGN.md "Cycle"):
- *   round: every active gang is evaluated against the round-start node state (fit -> score -> its
- *   first K feasible domains, each packed = K alternatives); then up to GROVE_SUBROUNDS sub-rounds
- *   resolve conflicts without re-evaluating: every undecided gang proposes its first alternative
- *   that touches no node committed earlier in this round, proposals claim their nodes with the gang's
- *   order rank (min wins), a gang that holds every node it claimed commits.  Gangs left undecided are
- *   re-evaluated next round; a gang with no feasible domain is rejected for the cycle.
- *
- * Written as steps over a shard context so that the multi-rank protocol (gang rows dealt g % world
- * to ranks, node table and gang state replicated -- DESIGN.md section 7) can be exercised on CPU:
- *   begin; repeat { eval (own gangs -> exchange buffer) -> [all-reduce SUM] -> resolve (replicated) }; end.
- * oracle_run_cycle is the same steps with world = 1 and no reduction.
+ * One scheduling cycle, sequentially (DESIGN.md section 1 "Cycle").
+ *   for every gang in (priority desc, index asc) order:
+ *     gated                                  -> GATED_SKIP
+ *     base gang not ADMITTED so far          -> BASE_REJECTED   (pod/syncflow.go:319-358: a scaled gang's pods stay
+ *                                                                gated until the base gang is scheduled; it waits
+ *                                                                for a later cycle)
+ *     fit row + score row of each clique over all nodes (K1, K2 semantics) against the CURRENT state,
+ *     first feasible domain in score order   -> ADMITTED, resources subtracted
+ *     none                                   -> REJECTED, nothing bound
+ * Outputs are in caller node indices.  out_fit/out_score (nullable) receive the rows of all cliques against
+ * the cycle-START state in SORTED node order (row stride words = ceil(n/32) and n bytes): what K1 and K2 of
+ * the engine produce.  out_scopes (nullable): S records.  `threads` parallelises the per-gang row computation
+ * over nodes; the gang loop is sequential by definition.
  */
-#define CLAIM_NONE 0x7F7F7F7F /* > any order rank (< 2^24) */
-
-typedef struct oshard {
-  ctx_t C;
-  uint32_t n, L, G, Q, S, P, K;
-  xlay_t X;
-  const grove_node_t* nodes_in;
-  uint32_t rank, world, max_rounds;
-  uint8_t* state; uint8_t* rnd;
-  uint32_t* active; uint32_t na_local;        /* this rank's share of the round */
-  uint32_t* active_all; uint32_t na_all;      /* every rank's (replicated decision) */
-  int32_t* fin_node; int32_t* fin_meta; uint32_t* fin_n; uint8_t* fin_score; uint32_t* fin_top;
-  uint32_t round, unresolved;
-  uint64_t pairs;
-  double t0, t_eval;
-  uint32_t* out_fit; uint8_t* out_score;
-} oshard_t;
-
-static void shard_free(oshard_t* h) {
-  if (!h) return;
-  free(h->active); free(h->active_all); free(h->rnd); free(h->state);
-  free(h->fin_node); free(h->fin_meta); free(h->fin_n); free(h->fin_score); free(h->fin_top);
-  free(h->C.order); free(h->C.anchor); free(h->C.pod_off);
-  topo_free(&h->C.T);
-  free(h);
-}
-
-void oracle_shard_abort(oshard_t* h) { shard_free(h); }
-
-int32_t oracle_shard_begin(const grove_node_t* nodes_in, uint32_t n, uint32_t L, const grove_gang_t* gangs, uint32_t G,
-                           const grove_clique_t* cliques, uint32_t Q, const grove_scope_t* scopes, uint32_t S,
-                           uint32_t max_rounds, uint32_t alternatives, int32_t threads, uint32_t rank, uint32_t world,
-                           uint32_t* out_fit, uint8_t* out_score, oshard_t** out) {
+int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
+                         const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
+                         const grove_scope_t* scopes, uint32_t S, int32_t threads,
+                         grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
+                         grove_gang_status_t* out_status, grove_scope_status_t* out_scopes, grove_node_t* out_nodes, uint32_t* out_perm,
+                         uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
   int32_t rc = oracle_validate(gangs, G, cliques, Q, scopes, S, L, n);
   if (rc != GROVE_OK) return rc;
-  if (n == 0 || n > GROVE_MAX_NODES || !out) return GROVE_ERR_INVALID_ARG;
-  if (alternatives == 0) alternatives = GROVE_MAX_ALTERNATIVES;
-  if (alternatives > GROVE_MAX_ALTERNATIVES) return GROVE_ERR_INVALID_ARG;
-  if (world == 0) world = 1;
-  if (rank >= world) return GROVE_ERR_INVALID_ARG;
+  if (n == 0 || n > GROVE_MAX_NODES) return GROVE_ERR_INVALID_ARG;
 #ifdef _OPENMP
   if (threads > 0) omp_set_num_threads(threads);
 #endif
-  oshard_t* h = calloc(1, sizeof(oshard_t));
-  if (!h) return GROVE_ERR_OOM;
-  h->t0 = now_s();
-  if (topo_build(&h->C.T, nodes_in, n, L)) { shard_free(h); return GROVE_ERR_OOM; }
-  h->n = n; h->L = L; h->G = G; h->Q = Q; h->S = S; h->nodes_in = nodes_in; h->K = alternatives;
-  h->rank = rank; h->world = world; h->max_rounds = max_rounds; h->out_fit = out_fit; h->out_score = out_score;
-  ctx_t* C = &h->C;
+  const double t0 = now_s();
+  ctx_t Cx; memset(&Cx, 0, sizeof(Cx));
+  ctx_t* C = &Cx;
+  if (topo_build(&C->T, nodes_in, n, L)) { topo_free(&C->T); return GROVE_ERR_OOM; }
   C->G = G; C->Q = Q; C->S = S; C->gangs = gangs; C->cliques = cliques; C->scopes = scopes;
-  C->order = malloc(sizeof(uint32_t) * (G ? G : 1));
   C->anchor = malloc(sizeof(uint32_t) * (G ? G : 1));
-  C->pod_off = malloc(sizeof(uint32_t) * (G + 1));
   ord_t* ov = malloc(sizeof(ord_t) * (G ? G : 1));
-  for (uint32_t g = 0; g < G; ++g) { ov[g].pr = gangs[g].priority; ov[g].g = g; }
-  qsort(ov, G, sizeof(ord_t), cmp_ord);
-  for (uint32_t r = 0; r < G; ++r) C->order[ov[r].g] = r;
-  free(ov);
-  uint32_t po = 0;
   for (uint32_t g = 0; g < G; ++g) {
+    ov[g].pr = gangs[g].priority; ov[g].g = g;
     C->anchor[g] = gangs[g].anchor_node != GROVE_NONE_U32 ? C->T.inv[gangs[g].anchor_node] : fmix32(g) % n;
-    C->pod_off[g] = po;
-    for (uint32_t c = 0; c < gangs[g].n_cliques; ++c) po += cliques[gangs[g].clique_off + c].replicas;
   }
-  C->pod_off[G] = po; h->P = po;
-  h->X = xlayout(h->K, h->P, G);
-  h->state = calloc(G ? G : 1, 1);
-  h->rnd = calloc(G ? G : 1, 1);
-  h->active = malloc(sizeof(uint32_t) * (G ? G : 1));
-  h->active_all = malloc(sizeof(uint32_t) * (G ? G : 1));
-  h->fin_node = calloc(po ? po : 1, sizeof(int32_t)); h->fin_meta = calloc(po ? po : 1, sizeof(int32_t));
-  h->fin_n = calloc(G ? G : 1, sizeof(uint32_t)); h->fin_score = calloc(G ? G : 1, 1); h->fin_top = calloc(G ? G : 1, sizeof(uint32_t));
-  for (uint32_t g = 0; g < G; ++g) {
-    if (gangs[g].flags & GROVE_GANG_GATED) h->state[g] = GROVE_GANG_GATED_SKIP; else h->unresolved++;
-  }
-  *out = h;
-  return GROVE_OK;
-}
-
-uint32_t oracle_shard_xbuf_words(const oshard_t* h) { return (uint32_t)h->X.words; }
-
-/* Step 1: decide who is active (replicated state => identical on every rank), evaluate this rank's
- * share into the exchange buffer (zero elsewhere).  *go = 0 when the cycle is over. */
-int32_t oracle_shard_eval(oshard_t* h, int32_t* xb, uint32_t* go) {
-  ctx_t* C = &h->C;
-  const grove_gang_t* gangs = C->gangs; const grove_clique_t* cliques = C->cliques; const grove_scope_t* scopes = C->scopes;
-  const uint32_t G = h->G, n = h->n;
-  *go = 0; h->na_local = 0; h->na_all = 0;
-  if (h->unresolved == 0 || (h->max_rounds && h->round >= h->max_rounds)) return GROVE_OK;
-  h->round++;
-  const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
-  /* scaled gangs become active once their base gang is admitted (pod/syncflow.go:319-358) */
-  int changed = 1;
-  while (changed) { /* propagate base rejections transitively */
-    changed = 0;
-    for (uint32_t g = 0; g < G; ++g) {
-      if (h->state[g] != GROVE_GANG_PENDING || gangs[g].base_gang == GROVE_NONE_U32) continue;
-      uint8_t bs = h->state[gangs[g].base_gang];
-      if (bs == GROVE_GANG_REJECTED || bs == GROVE_GANG_BASE_REJECTED || bs == GROVE_GANG_GATED_SKIP) {
-        h->state[g] = GROVE_GANG_BASE_REJECTED; h->rnd[g] = r8; h->unresolved--; changed = 1;
+  qsort(ov, G, sizeof(ord_t), cmp_ord);
+  const uint32_t words = (n + 31) / 32;
+  uint64_t pairs = 0;
+  /* K1 / K2 over the cycle-start snapshot, every clique (debug / parity rows) */
+  if (out_fit || out_score) {
+    for (uint32_t gi = 0; gi < G; ++gi) {
+      const grove_gang_t* g = &gangs[gi];
+      for (uint32_t si = 0; si < g->n_scopes; ++si) {
+        const grove_scope_t* s = &scopes[g->scope_off + si];
+        for (uint32_t i = 0; i < s->n_cliques; ++i) {
+          const uint32_t qi = g->clique_off + s->first_clique + i;
+          const grove_clique_t* q = &cliques[qi];
+          const uint32_t ndp = need_depth(g, s, q);
+          if (out_fit) memset(out_fit + (size_t)qi * words, 0, sizeof(uint32_t) * words);
+          for (uint32_t nn = 0; nn < n; ++nn) {
+            const int f = fit(&C->T.nodes[nn], q, ndp);
+            if (f && out_fit) out_fit[(size_t)qi * words + (nn >> 5)] |= 1u << (nn & 31);
+            if (out_score) out_score[(size_t)qi * n + nn] = f ? (uint8_t)(closeness(&C->T, nn, C->anchor[gi]) + 1) : 0;
+          }
+        }
       }
     }
   }
-  for (uint32_t g = 0; g < G; ++g) {
-    if (h->state[g] != GROVE_GANG_PENDING) continue;
-    if (gangs[g].base_gang != GROVE_NONE_U32 && h->state[gangs[g].base_gang] != GROVE_GANG_ADMITTED) continue;
-    h->active_all[h->na_all++] = g;
-    if (g % h->world == h->rank) h->active[h->na_local++] = g;
-  }
-  if (h->na_all == 0) { /* dependency cycle: nothing can ever become active */
-    for (uint32_t g = 0; g < G; ++g)
-      if (h->state[g] == GROVE_GANG_PENDING) { h->state[g] = GROVE_GANG_BASE_REJECTED; h->rnd[g] = r8; h->unresolved--; }
-    return GROVE_OK;
-  }
-  *go = 1;
-  memset(xb, 0, sizeof(int32_t) * h->X.words);
-  const uint32_t words = (n + 31) / 32;
-  uint64_t pairs = 0;
-  double te0 = now_s();
-  const uint32_t na = h->na_local;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : pairs)
-  for (uint32_t ai = 0; ai < na; ++ai) {
-    uint32_t gi = h->active[ai];
+  uint8_t* state = calloc(G ? G : 1, 1);
+  /* placements are kept per gang and emitted in submission order at the end */
+  uint32_t* pod_off = malloc(sizeof(uint32_t) * (G + 1));
+  uint32_t po = 0;
+  for (uint32_t g = 0; g < G; ++g) { pod_off[g] = po; for (uint32_t c = 0; c < gangs[g].n_cliques; ++c) po += cliques[gangs[g].clique_off + c].replicas; }
+  pod_off[G] = po;
+  entry_t* fin = malloc(sizeof(entry_t) * (po ? po : 1));
+  uint32_t* fin_n = calloc(G ? G : 1, sizeof(uint32_t));
+  grove_gang_status_t* gst = calloc(G ? G : 1, sizeof(grove_gang_status_t));
+  grove_scope_status_t* sst = malloc(sizeof(grove_scope_status_t) * (S ? S : 1));
+  for (uint32_t i = 0; i < S; ++i) { memset(&sst[i], 0, sizeof(sst[i])); sst[i].level = GROVE_LEVEL_NONE; sst[i].domain_node = GROVE_NONE_U32; }
+  geval_t* E = malloc(sizeof(geval_t));
+  uint8_t* Trow[GROVE_MAX_GANG_CLIQUES];
+  for (uint32_t c = 0; c < GROVE_MAX_GANG_CLIQUES; ++c) Trow[c] = malloc(n);
+
+  for (uint32_t r = 0; r < G; ++r) {
+    const uint32_t gi = ov[r].g;
     const grove_gang_t* g = &gangs[gi];
-    uint8_t* Trow[GROVE_MAX_GANG_CLIQUES];
-    uint32_t* Frow = malloc(sizeof(uint32_t) * words);
+    gst[gi].level = GROVE_LEVEL_NONE; gst[gi].domain_node = GROVE_NONE_U32;
+    if (g->flags & GROVE_GANG_GATED) { state[gi] = GROVE_GANG_GATED_SKIP; continue; }
+    if (g->base_gang != GROVE_NONE_U32 && state[g->base_gang] != GROVE_GANG_ADMITTED) { state[gi] = GROVE_GANG_BASE_REJECTED; continue; }
     for (uint32_t si = 0; si < g->n_scopes; ++si) {
       const grove_scope_t* s = &scopes[g->scope_off + si];
       for (uint32_t i = 0; i < s->n_cliques; ++i) {
-        uint32_t cr = s->first_clique + i;
+        const uint32_t cr = s->first_clique + i;
         const grove_clique_t* q = &cliques[g->clique_off + cr];
-        uint32_t ndp = need_depth(g, s, q);
-        Trow[cr] = malloc(n);
-        memset(Frow, 0, sizeof(uint32_t) * words);
-        /* K1: fit bitmap row; K2: score row = fit ? closeness + 1 : 0 (one pass over the node table) */
-        for (uint32_t nn = 0; nn < n; ++nn) {
-          const int f = fit(&C->T.nodes[nn], q, ndp);
-          if (f) Frow[nn >> 5] |= 1u << (nn & 31);
-          Trow[cr][nn] = f ? (uint8_t)(closeness(&C->T, nn, C->anchor[gi]) + 1) : 0;
-        }
+        const uint32_t ndp = need_depth(g, s, q);
+        uint8_t* row = Trow[cr];
+        const uint32_t a = C->anchor[gi];
+        /* K1: fit; K2: score = fit ? closeness + 1 : 0 (one pass over the node table) */
+#pragma omp parallel for schedule(static) if (n >= 4096)
+        for (uint32_t nn = 0; nn < n; ++nn)
+          row[nn] = fit(&C->T.nodes[nn], q, ndp) ? (uint8_t)(closeness(&C->T, nn, a) + 1) : 0;
         pairs += n;
-        if (h->round == 1 && h->out_fit) memcpy(h->out_fit + (size_t)(g->clique_off + cr) * words, Frow, sizeof(uint32_t) * words);
-        if (h->round == 1 && h->out_score) memcpy(h->out_score + (size_t)(g->clique_off + cr) * n, Trow[cr], n);
       }
     }
-    eval_gang(C, gi, Trow, &h->X, xb, h->P);
-    for (uint32_t cr = 0; cr < g->n_cliques; ++cr) free(Trow[cr]);
-    free(Frow);
+    int g_got = -1; uint32_t g_lo = 0, n_min = 0;
+    if (!eval_gang(E, C, gi, Trow, &g_got, &g_lo, &n_min)) { state[gi] = GROVE_GANG_REJECTED; continue; }
+    state[gi] = GROVE_GANG_ADMITTED;
+    /* commit: the next gang sees what is left */
+    for (uint32_t i = 0; i < E->np; ++i) {
+      const grove_clique_t* q = &cliques[g->clique_off + E->st[i].clique_rel];
+      grove_node_t* node = &C->T.nodes[E->st[i].node];
+      node->free_cpu_milli -= q->req_cpu_milli; node->free_mem_mib -= q->req_mem_mib;
+      node->free_gpu -= q->req_gpu; node->free_pods -= 1;
+      fin[pod_off[gi] + i] = E->st[i];
+    }
+    fin_n[gi] = E->np;
+    /* PlacementScore and the chosen domains */
+    score_t sc = {0, 0};
+    score_unit(&sc, g->level, g->preferred, g_got);
+    for (uint32_t si = 0; si < g->n_scopes; ++si) {
+      const grove_scope_t* s = &scopes[g->scope_off + si];
+      score_unit(&sc, s->level, scope_pref(s), E->s_got[si]);
+      /* a scope packed at the gang's own level has no domain of its own */
+      if (E->s_got[si] > g_got) { sst[g->scope_off + si].level = (uint8_t)E->s_got[si]; sst[g->scope_off + si].domain_node = C->T.perm[E->s_lo[si]]; }
+      for (uint32_t i = 0; i < s->n_cliques; ++i) {
+        const uint32_t cr = s->first_clique + i;
+        const grove_clique_t* q = &cliques[g->clique_off + cr];
+        score_unit(&sc, q->level, GROVE_CLIQUE_PREFERRED(q->scope), E->c_got[cr]);
+      }
+    }
+    if (sc.den == 0) { sc.num = 1; sc.den = 1; }
+    gst[gi].score_num = (uint16_t)sc.num; gst[gi].score_den = (uint16_t)sc.den;
+    if (g_got >= 0) { gst[gi].level = (uint8_t)g_got; gst[gi].domain_node = C->T.perm[g_lo]; }
   }
-  h->pairs += pairs;
-  h->t_eval += now_s() - te0;
-  return GROVE_OK;
-}
 
-/* Step 2 (exchange buffer summed over ranks): conflict resolution and commits, identical on every rank */
-int32_t oracle_shard_resolve(oshard_t* h, const int32_t* xb, uint32_t* remaining) {
-  ctx_t* C = &h->C;
-  const xlay_t* X = &h->X;
-  const uint32_t n = h->n, P = h->P, K = h->K;
-  const uint8_t r8 = (uint8_t)(h->round > 255 ? 255 : h->round);
-  uint8_t* taken = calloc(n, 1);
-  int32_t* claim = malloc(sizeof(int32_t) * n);
-  uint32_t* cur = calloc(h->na_all ? h->na_all : 1, sizeof(uint32_t));
-  uint8_t* prop = calloc(h->na_all ? h->na_all : 1, 1);
-  for (uint32_t ai = 0; ai < h->na_all; ++ai) {
-    uint32_t g = h->active_all[ai];
-    if (xb[X->nalt + g] == 0) { h->state[g] = GROVE_GANG_REJECTED; h->rnd[g] = r8; h->unresolved--; }
-  }
-  for (uint32_t sub = 0; sub < GROVE_SUBROUNDS; ++sub) {
-    for (uint32_t i = 0; i < n; ++i) claim[i] = CLAIM_NONE;
-    uint32_t nprop = 0;
-    for (uint32_t ai = 0; ai < h->na_all; ++ai) {
-      uint32_t g = h->active_all[ai];
-      prop[ai] = 0;
-      if (h->state[g] != GROVE_GANG_PENDING) continue;
-      const uint32_t nalt = (uint32_t)xb[X->nalt + g], po = C->pod_off[g];
-      while (cur[ai] < nalt) { /* first alternative that touches no node committed earlier in this round */
-        const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a];
-        int hit = 0;
-        for (uint32_t i = 0; i < cnt && !hit; ++i) hit = taken[(uint32_t)xb[X->node + (size_t)a * P + po + i]];
-        if (!hit) break;
-        cur[ai]++;
-      }
-      if (cur[ai] >= nalt) continue; /* nothing left to propose: re-evaluated next round */
-      prop[ai] = 1; nprop++;
-      const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a];
-      for (uint32_t i = 0; i < cnt; ++i) {
-        uint32_t nd = (uint32_t)xb[X->node + (size_t)a * P + po + i];
-        if ((int32_t)C->order[g] < claim[nd]) claim[nd] = (int32_t)C->order[g];
-      }
-    }
-    if (nprop == 0) break;
-    for (uint32_t ai = 0; ai < h->na_all; ++ai) {
-      if (!prop[ai]) continue;
-      uint32_t g = h->active_all[ai];
-      const uint32_t a = cur[ai], cnt = (uint32_t)xb[X->n + (size_t)g * K + a], po = C->pod_off[g];
-      int win = 1;
-      for (uint32_t i = 0; i < cnt && win; ++i) win = claim[(uint32_t)xb[X->node + (size_t)a * P + po + i]] == (int32_t)C->order[g];
-      if (!win) continue;
-      for (uint32_t i = 0; i < cnt; ++i) {
-        uint32_t nd = (uint32_t)xb[X->node + (size_t)a * P + po + i];
-        int32_t meta = xb[X->meta + (size_t)a * P + po + i];
-        const grove_clique_t* q = &C->cliques[C->gangs[g].clique_off + ((uint32_t)meta & 0xFFu)];
-        grove_node_t* node = &C->T.nodes[nd];
-        node->free_cpu_milli -= q->req_cpu_milli; node->free_mem_mib -= q->req_mem_mib;
-        node->free_gpu -= q->req_gpu; node->free_pods -= 1;
-        taken[nd] = 1;
-        h->fin_node[po + i] = (int32_t)nd; h->fin_meta[po + i] = meta;
-      }
-      h->fin_n[g] = cnt; h->fin_score[g] = (uint8_t)xb[X->score + (size_t)g * K + a]; h->fin_top[g] = (uint32_t)xb[X->top + (size_t)g * K + a];
-      h->state[g] = GROVE_GANG_ADMITTED; h->rnd[g] = r8; h->unresolved--;
-    }
-  }
-  free(taken); free(claim); free(cur); free(prop);
-  if (remaining) *remaining = h->unresolved;
-  return GROVE_OK;
-}
-
-/* Step 3: outputs in caller node indices; frees the context */
-int32_t oracle_shard_end(oshard_t* h, grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
-                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm, oracle_stats_t* stats) {
-  ctx_t* C = &h->C;
-  const uint32_t G = h->G, n = h->n;
   uint32_t np = 0, adm = 0, rej = 0;
   for (uint32_t g = 0; g < G; ++g) {
-    grove_gang_status_t st; memset(&st, 0, sizeof(st));
-    st.state = h->state[g]; st.round = h->rnd[g]; st.top_domain_lo = GROVE_NONE_U32; st.placement_off = np;
-    if (h->state[g] == GROVE_GANG_ADMITTED) {
+    gst[g].state = state[g]; gst[g].placement_off = np; gst[g].n_pods = 0;
+    if (state[g] == GROVE_GANG_ADMITTED) {
       adm++;
-      uint32_t cnt = h->fin_n[g];
-      st.score_num = h->fin_score[g]; st.score_den = (uint8_t)(h->L + 1);
-      st.n_pods = cnt; st.top_domain_lo = h->fin_top[g];
-      for (uint32_t i = 0; i < cnt; ++i) {
+      gst[g].n_pods = fin_n[g];
+      for (uint32_t i = 0; i < fin_n[g]; ++i) {
         if (out_pl && np < cap_pl) {
-          out_pl[np].clique = C->gangs[g].clique_off + ((uint32_t)h->fin_meta[C->pod_off[g] + i] & 0xFFu);
-          out_pl[np].node = C->T.perm[(uint32_t)h->fin_node[C->pod_off[g] + i]];
+          out_pl[np].clique = gangs[g].clique_off + fin[pod_off[g] + i].clique_rel;
+          out_pl[np].node = C->T.perm[fin[pod_off[g] + i].node];
         }
         np++;
       }
-    } else if (h->state[g] == GROVE_GANG_REJECTED || h->state[g] == GROVE_GANG_BASE_REJECTED) rej++;
-    if (out_status) out_status[g] = st;
+    } else if (state[g] == GROVE_GANG_REJECTED || state[g] == GROVE_GANG_BASE_REJECTED) rej++;
+    if (out_status) out_status[g] = gst[g];
   }
   if (n_pl) *n_pl = np;
+  if (out_scopes) memcpy(out_scopes, sst, sizeof(grove_scope_status_t) * S);
   if (out_nodes)
     for (uint32_t i = 0; i < n; ++i) {
-      grove_node_t nd = h->nodes_in[C->T.perm[i]];
+      grove_node_t nd = nodes_in[C->T.perm[i]];
       nd.free_cpu_milli = C->T.nodes[i].free_cpu_milli; nd.free_mem_mib = C->T.nodes[i].free_mem_mib;
       nd.free_gpu = C->T.nodes[i].free_gpu; nd.free_pods = C->T.nodes[i].free_pods;
       out_nodes[C->T.perm[i]] = nd;
@@ -752,8 +635,8 @@ int32_t oracle_shard_end(oshard_t* h, grove_placement_t* out_pl, uint32_t cap_pl
   if (out_perm) memcpy(out_perm, C->T.perm, sizeof(uint32_t) * n);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->rounds = h->round; stats->gangs_admitted = adm; stats->gangs_rejected = rej; stats->pods_bound = np;
-    stats->pairs_evaluated = h->pairs; stats->seconds_eval = h->t_eval; stats->seconds_total = now_s() - h->t0;
+    stats->gangs_admitted = adm; stats->gangs_rejected = rej; stats->pods_bound = np;
+    stats->pairs_evaluated = pairs; stats->seconds_total = now_s() - t0;
     stats->non_tree_labels = C->T.non_tree;
 #ifdef _OPENMP
     stats->threads = (uint32_t)omp_get_max_threads();
@@ -761,34 +644,10 @@ int32_t oracle_shard_end(oshard_t* h, grove_placement_t* out_pl, uint32_t cap_pl
     stats->threads = 1;
 #endif
   }
-  int32_t ret = (out_pl && np > cap_pl) ? GROVE_ERR_LIMIT : GROVE_OK;
-  shard_free(h);
-  return ret;
-}
-
-/* Outputs are in caller node indices.  out_fit/out_score (nullable) receive the round-1 rows of all
- * cliques in SORTED node order (row stride words = ceil(n/32) and n bytes). */
-int32_t oracle_run_cycle(const grove_node_t* nodes_in, uint32_t n, uint32_t L,
-                         const grove_gang_t* gangs, uint32_t G, const grove_clique_t* cliques, uint32_t Q,
-                         const grove_scope_t* scopes, uint32_t S, uint32_t max_rounds, uint32_t alternatives, int32_t threads,
-                         grove_placement_t* out_pl, uint32_t cap_pl, uint32_t* n_pl,
-                         grove_gang_status_t* out_status, grove_node_t* out_nodes, uint32_t* out_perm,
-                         uint32_t* out_fit, uint8_t* out_score, oracle_stats_t* stats) {
-  oshard_t* h = NULL;
-  int32_t rc = oracle_shard_begin(nodes_in, n, L, gangs, G, cliques, Q, scopes, S, max_rounds, alternatives, threads, 0, 1,
-                                  out_fit, out_score, &h);
-  if (rc != GROVE_OK) return rc;
-  int32_t* xb = malloc(sizeof(int32_t) * (h->X.words ? h->X.words : 1));
-  if (!xb) { shard_free(h); return GROVE_ERR_OOM; }
-  for (;;) {
-    uint32_t go = 0;
-    oracle_shard_eval(h, xb, &go);
-    if (!go) break;
-    oracle_shard_resolve(h, xb, NULL);
-  }
-  rc = oracle_shard_end(h, out_pl, cap_pl, n_pl, out_status, out_nodes, out_perm, stats);
-  free(xb);
-  return rc;
+  for (uint32_t c = 0; c < GROVE_MAX_GANG_CLIQUES; ++c) free(Trow[c]);
+  free(E); free(state); free(pod_off); free(fin); free(fin_n); free(gst); free(sst); free(ov); free(C->anchor);
+  topo_free(&C->T);
+  return (out_pl && np > cap_pl) ? GROVE_ERR_LIMIT : GROVE_OK;
 }
 
 /* topology preprocessing alone, for tests of the engine's host-side sort: perm + tree-ified dom ids */

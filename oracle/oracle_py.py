@@ -17,15 +17,15 @@ _LIB = None
 
 class OracleStats(C.Structure):
     _fields_ = [
-        ("rounds", C.c_uint32), ("gangs_admitted", C.c_uint32), ("gangs_rejected", C.c_uint32),
-        ("pods_bound", C.c_uint32), ("pairs_evaluated", C.c_uint64), ("seconds_eval", C.c_double),
-        ("seconds_total", C.c_double), ("non_tree_labels", C.c_uint32), ("threads", C.c_uint32),
+        ("gangs_admitted", C.c_uint32), ("gangs_rejected", C.c_uint32), ("pods_bound", C.c_uint32),
+        ("threads", C.c_uint32), ("pairs_evaluated", C.c_uint64), ("seconds_total", C.c_double),
+        ("non_tree_labels", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libgrove_oracle.so")
-    src = os.path.join(_HERE, "grove_oracle.c")
+    src = os.path.join(_HERE, "grove_oracle_seq.c")
     hdr = os.path.join(_HERE, "..", "include", "grove_place.h")
     stale = (not os.path.exists(so)) or any(
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
@@ -48,8 +48,9 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, want_matrices=False, alternatives=0):
-    """Returns dict(placements, status, nodes_after, perm, stats[, fit, score])."""
+def run_cycle(nodes, n_levels, gangs, cliques, scopes, threads=1, want_matrices=False):
+    """The sequential priority-ordered pass.  Returns dict(placements, status, scope_status, nodes_after, perm,
+    stats[, fit, score]); fit / score are the K1 / K2 rows over the cycle-start snapshot (sorted node order)."""
     from grove_b200 import tables as T
 
     n, G, Q, S = len(nodes), len(gangs), len(cliques), len(scopes)
@@ -60,6 +61,7 @@ def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, 
     cap = int(cliques["replicas"].astype(np.int64).sum()) if Q else 0
     pl = np.zeros(max(cap, 1), dtype=T.placement_dt)
     st = np.zeros(max(G, 1), dtype=T.status_dt)
+    ss = np.zeros(max(S, 1), dtype=T.scope_status_dt)
     nodes_after = np.zeros(max(n, 1), dtype=T.node_dt)
     perm = np.zeros(max(n, 1), dtype=np.uint32)
     words = (n + 31) // 32
@@ -69,12 +71,12 @@ def run_cycle(nodes, n_levels, gangs, cliques, scopes, max_rounds=0, threads=1, 
     stats = OracleStats()
     rc = lib().oracle_run_cycle(
         _p(nodes), C.c_uint32(n), C.c_uint32(n_levels), _p(gangs), C.c_uint32(G), _p(cliques), C.c_uint32(Q),
-        _p(scopes), C.c_uint32(S), C.c_uint32(max_rounds), C.c_uint32(alternatives), C.c_int32(threads), _p(pl), C.c_uint32(len(pl)),
-        C.byref(n_pl), _p(st), _p(nodes_after), _p(perm), _p(fit), _p(score), C.byref(stats))
+        _p(scopes), C.c_uint32(S), C.c_int32(threads), _p(pl), C.c_uint32(len(pl)),
+        C.byref(n_pl), _p(st), _p(ss), _p(nodes_after), _p(perm), _p(fit), _p(score), C.byref(stats))
     if rc != 0:
         raise RuntimeError(f"oracle_run_cycle failed: {rc}")
-    out = dict(placements=pl[: n_pl.value].copy(), status=st[:G].copy(), nodes_after=nodes_after[:n].copy(),
-               perm=perm[:n].copy(),
+    out = dict(placements=pl[: n_pl.value].copy(), status=st[:G].copy(), scope_status=ss[:S].copy(),
+               nodes_after=nodes_after[:n].copy(), perm=perm[:n].copy(),
                stats={k: getattr(stats, k) for k, _ in OracleStats._fields_})
     if want_matrices:
         out["fit"], out["score"] = fit, score
@@ -94,60 +96,3 @@ def topology(nodes, n_levels):
     if rc != 0:
         raise RuntimeError(f"oracle_topology failed: {rc}")
     return perm, dom, ndom[:n_levels].copy(), nt.value
-
-
-class OracleStepper:
-    """CPU stand-in for PlacementEngine's stepping interface (same protocol, numpy buffers), used by the
-    world_size-2 gloo test of grove_b200.sharded.run_sharded_cycle."""
-
-    def __init__(self, nodes, n_levels, gangs, cliques, scopes, rank, world, threads=1, alternatives=0):
-        from grove_b200 import tables as T
-        self.T = T
-        self.nodes = np.ascontiguousarray(nodes, dtype=T.node_dt)
-        self.gangs = np.ascontiguousarray(gangs, dtype=T.gang_dt)
-        self.cliques = np.ascontiguousarray(cliques, dtype=T.clique_dt)
-        self.scopes = np.ascontiguousarray(scopes, dtype=T.scope_dt)
-        self.L, self.rank, self.world, self.threads, self.alternatives = n_levels, rank, world, threads, alternatives
-        self.h = None
-        L = lib()
-        for f in ("oracle_shard_begin", "oracle_shard_eval", "oracle_shard_resolve", "oracle_shard_end"):
-            getattr(L, f).restype = C.c_int32
-        L.oracle_shard_xbuf_words.restype = C.c_uint32
-
-    def _chk(self, rc):
-        if rc != 0:
-            raise RuntimeError(f"oracle shard step failed: {rc}")
-
-    def cycle_begin(self):
-        self.h = C.c_void_p()
-        self._chk(lib().oracle_shard_begin(
-            _p(self.nodes), C.c_uint32(len(self.nodes)), C.c_uint32(self.L), _p(self.gangs), C.c_uint32(len(self.gangs)),
-            _p(self.cliques), C.c_uint32(len(self.cliques)), _p(self.scopes), C.c_uint32(len(self.scopes)),
-            C.c_uint32(0), C.c_uint32(self.alternatives), C.c_int32(self.threads), C.c_uint32(self.rank),
-            C.c_uint32(self.world), None, None, C.byref(self.h)))
-        self.n_x = lib().oracle_shard_xbuf_words(self.h)
-        self.xbuf = np.zeros(max(self.n_x, 1), dtype=np.int32)
-
-    def round_eval(self):
-        go = C.c_uint32(0)
-        self._chk(lib().oracle_shard_eval(self.h, _p(self.xbuf), C.byref(go)))
-        return self.xbuf, self.n_x, bool(go.value)
-
-    def round_resolve(self):
-        r = C.c_uint32(0)
-        self._chk(lib().oracle_shard_resolve(self.h, _p(self.xbuf), C.byref(r)))
-        return r.value
-
-    def cycle_end(self):
-        T = self.T
-        cap = int(self.cliques["replicas"].astype(np.int64).sum())
-        pl = np.zeros(max(cap, 1), dtype=T.placement_dt)
-        st = np.zeros(max(len(self.gangs), 1), dtype=T.status_dt)
-        after = np.zeros(len(self.nodes), dtype=T.node_dt)
-        n_pl = C.c_uint32(0)
-        stats = OracleStats()
-        self._chk(lib().oracle_shard_end(self.h, _p(pl), C.c_uint32(len(pl)), C.byref(n_pl), _p(st), _p(after),
-                                         None, C.byref(stats)))
-        self.h = None
-        self.result = dict(placements=pl[: n_pl.value].copy(), status=st[: len(self.gangs)].copy(), nodes_after=after)
-        return {k: getattr(stats, k) for k, _ in OracleStats._fields_}

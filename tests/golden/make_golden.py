@@ -3,7 +3,7 @@
 The reference (/root/reference, ai-dynamo/grove @ 08ad3b37) is Go, contains no scheduler and cannot
 be built or imported here, so there is no reference OUTPUT to record.  These fixtures are small
 snapshots in the shapes of the reference's e2e suites and BASELINE.json configs together with the
-oracle's answer at the commit that generated them; they pin (a) the oracle against silent drift and
+sequential oracle's answer (oracle/grove_oracle_seq.c) at the commit that generated them; they pin (a) the oracle against silent drift and
 (b) the CUDA path on the GPU box, where neither /root/reference nor this generator needs to run.
 
     python tests/golden/make_golden.py
@@ -47,9 +47,9 @@ def main():
     for name, nodes, L, (g, c, s) in cases():
         r = O.run_cycle(nodes, L, g, c, s, threads=4)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), nodes=nodes, n_levels=L, gangs=g, cliques=c, scopes=s,
-                            placements=r["placements"], status=r["status"], nodes_after=r["nodes_after"],
-                            rounds=r["stats"]["rounds"])
-        print(name, len(nodes), len(g), r["stats"]["rounds"], r["stats"]["gangs_admitted"], r["stats"]["pods_bound"])
+                            placements=r["placements"], status=r["status"], scope_status=r["scope_status"],
+                            nodes_after=r["nodes_after"])
+        print(name, len(nodes), len(g), r["stats"]["gangs_admitted"], r["stats"]["pods_bound"])
 
 
 if __name__ == "__main__":

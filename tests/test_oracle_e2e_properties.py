@@ -306,11 +306,19 @@ def test_kwok_label_arithmetic_is_not_a_tree(oracle):
 
 
 def test_placement_score_range_and_meaning(oracle):
+    """podgang.go:187-189: 1.0 = the best possible placement.  Best possible = every pack constraint held at the level
+    it asked for (Preferred if set, else Required), wherever in the cluster the gang landed."""
     nodes = synth.e2e_cluster(28)
     b = T.GangTableBuilder()
     same_host = b.add_gang([(None, [clq(40, 2, level=HOST)])], anchor=3)
-    spread = b.add_gang([(None, [clq(80, 20)])], anchor=3)
+    far = b.add_gang([(None, [clq(40, 2, level=HOST)])], anchor=27)          # perfectly packed far from anybody else: still 1.0
+    loose = b.add_gang([(None, [clq(80, 20)])], anchor=3)                     # nothing asked: 1.0
+    pref_ok = b.add_gang([(None, [clq(40, 3)])], preferred=RACK, anchor=10)   # fits the Preferred rack: 1.0
+    pref_wide = b.add_gang([(None, [clq(80, 6)])], preferred=HOST, level=BLOCK, anchor=14)  # one pod per node: falls back
     r, _ = run(oracle, nodes, b)
     st = r["status"]
-    assert st["score_den"][same_host] == 5 and st["score_num"][same_host] == 5  # on the anchor host: 1.0
-    assert 1 <= st["score_num"][spread] < 5  # spans racks/blocks: lower score, still in (0,1]
+    assert (st["state"] == T.GANG_ADMITTED).all()
+    for gi in (same_host, far, loose, pref_ok):
+        assert st["score_num"][gi] == st["score_den"][gi] > 0
+    assert 0 < st["score_num"][pref_wide] < st["score_den"][pref_wide]
+    assert st["level"][pref_wide] < HOST and st["level"][pref_ok] == RACK

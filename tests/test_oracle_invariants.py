@@ -35,6 +35,8 @@ def check(nodes, L, tabs, r):
     assert (nodes["flags"][pl["node"]] & T.NODE_SCHEDULABLE).all()
     assert ((q["class_mask"] >> cls) & 1).all()
     # ---- per gang
+    rank = np.empty(len(g), dtype=np.int64)
+    rank[np.lexsort((np.arange(len(g)), -g["priority"].astype(np.int64)))] = np.arange(len(g))
     for gi in range(len(g)):
         state = st["state"][gi]
         gg = g[gi]
@@ -45,7 +47,7 @@ def check(nodes, L, tabs, r):
         if gg["base_gang"] != T.NONE_U32:
             bstate = st["state"][gg["base_gang"]]
             if state == T.GANG_ADMITTED:
-                assert bstate == T.GANG_ADMITTED and st["round"][gg["base_gang"]] <= st["round"][gi]
+                assert bstate == T.GANG_ADMITTED and rank[gg["base_gang"]] < rank[gi]   # the base gang had its turn first
             if bstate != T.GANG_ADMITTED:
                 assert state == T.GANG_BASE_REJECTED
         if state != T.GANG_ADMITTED:
@@ -53,7 +55,11 @@ def check(nodes, L, tabs, r):
         mine = pl[st["placement_off"][gi]: st["placement_off"][gi] + st["n_pods"][gi]]
         rel = mine["clique"].astype(np.int64) - int(gg["clique_off"])
         assert ((rel >= 0) & (rel < gg["n_cliques"])).all()
-        assert st["score_den"][gi] == L + 1 and 0 < st["score_num"][gi] <= L + 1      # PlacementScore in (0, 1]
+        assert 0 < st["score_den"][gi] and st["score_num"][gi] <= st["score_den"][gi]  # PlacementScore in [0, 1]
+        asked = [(gg["level"], gg["preferred"])] + [(x["level"], x["preferred1"] - 1 if x["preferred1"] else T.LEVEL_NONE) for x in s[gg["scope_off"]: gg["scope_off"] + gg["n_scopes"]]]
+        asked += [(x["level"], (x["scope"] >> 5) - 1 if x["scope"] >> 5 else T.LEVEL_NONE) for x in c[gg["clique_off"]: gg["clique_off"] + gg["n_cliques"]]]
+        if all(p == T.LEVEL_NONE for _, p in asked):     # nothing Preferred: every Required level held => 1.0
+            assert st["score_num"][gi] == st["score_den"][gi]
         dom = lambda sel, lvl: set(nodes["dom"][mine["node"][sel], lvl].tolist())
         for ci in range(gg["n_cliques"]):
             cq = c[gg["clique_off"] + ci]
@@ -82,12 +88,11 @@ def test_cycle_invariants_on_random_snapshots(oracle, block):
             check(nodes, L, tabs, r)
 
 
-def test_cycle_invariants_with_one_alternative_and_bigger_cases(oracle):
+def test_cycle_invariants_on_bigger_cases(oracle):
     for seed in (2000, 2001, 4000, 4001):
         nodes, L, tabs = random_case(seed, big=True, pref=seed >= 4000)
-        for K in (0, 1):
-            r = oracle.run_cycle(nodes, L, *tabs, threads=8, alternatives=K)
-            check(nodes, L, tabs, r)
+        r = oracle.run_cycle(nodes, L, *tabs, threads=8)
+        check(nodes, L, tabs, r)
 
 
 def test_results_do_not_depend_on_threads(oracle):
