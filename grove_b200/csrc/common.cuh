@@ -1,4 +1,4 @@
-// common.cuh -- shared structs of the placement kernels (device views of the tables, per-round buffers).
+// common.cuh -- shared structs of the placement kernels (device views of the tables, relaxation state).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -10,6 +10,10 @@ namespace grove {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kMaxPieces = 2 * GROVE_MAX_LEVELS + 3;
+constexpr uint32_t kClaimSlots = 8;           // inline claim slots per node (one 128 B line); more spill to the overflow list
+constexpr uint32_t kClaimEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kStale = 0x80u;            // nlive8 bit: committed state changed since the capacity tables were built
+constexpr uint32_t kTagRounds = 254u;         // rounds per stamp epoch (stamps carry a round tag in their top byte)
 
 struct GangInfo {     // 48 B, built on the host at submit time
   uint32_t anchor;    // sorted node index
@@ -28,7 +32,7 @@ struct CliqueInfo {   // 16 B
 };
 
 struct Topo {
-  const uint4* nres;       // [npad] dynamic: free_cpu, free_mem, free_gpu | free_pods << 16, flags | vdepth << 16
+  const uint4* nres;       // [npad] committed state: free_cpu, free_mem, free_gpu | free_pods << 16, flags | vdepth << 16
   const uint4* ndom;       // [npad] static: tree-ified domain index per level
   const uint32_t* dom_lo[GROVE_MAX_LEVELS];
   const uint32_t* dom_hi[GROVE_MAX_LEVELS];
@@ -46,48 +50,91 @@ struct Tables {
   const grove_scope_t* scopes;
   const GangInfo* ginfo;
   const CliqueInfo* cinfo;
-  const uint4* sigs;     // [S] req_cpu, req_mem, req_gpu, class_mask | need_depth << 16
-  uint32_t G, Q, S;
+  const uint4* sigs;        // [S] req_cpu, req_mem, req_gpu, class_mask | need_depth << 16
+  const uint32_t* by_rank;  // [G] gang index at each order rank
+  uint32_t G, Q, S, NS;     // NS = scopes in the submission
 };
 
-struct RoundBufs {
-  uint8_t* state;        // [G] GROVE_GANG_*
-  uint8_t* round;        // [G]
-  uint32_t* active;      // [G] gangs evaluated this round
-  uint32_t* rows;        // [Q] clique rows evaluated this round
-  uint32_t* counters;    // [0] n_active [1] n_rows [2] unresolved [3] base rejections propagated [4] n_sigs
-                         // [5] active gangs over all ranks [6] gangs resolved by this round's apply
-  uint32_t* sig_stamp;   // [S] last round in which the signature was active
-  uint32_t* sig_list;    // [S] signatures needed this round
-  uint8_t* spec_score;   // [G]
-  uint16_t* spec_n;      // [G] entries incl. surplus
-  uint32_t* spec_top;    // [G]
-  uint32_t* ent_node;    // [P]
-  uint16_t* ent_meta;    // [P] clique_rel | score << 8
-  uint32_t* active_all;  // [G] active gangs of every rank (replicated decision)
-  uint32_t* claim;       // [n] (tag << 24 | order rank) of the best proposal for the node; tags decrease per (round, sub-round)
-  uint8_t* taken;        // [n] stamp of the last round that committed pods on the node
-  uint8_t* cur;          // [G] next alternative a gang will propose
-  uint8_t* prop;         // [G] sub-round (1-based) of the gang's last proposal
-  uint32_t* flags;       // [GROVE_SUBROUNDS] number of the last round with a proposal in sub-round s
-  // exchange buffer of the round (also the all-reduce payload of the sharded cycle), u32 words:
-  uint32_t* alt_node;    // [K][P] entry i of alternative a of gang g at a*P + pod_off[g] + i
-  uint32_t* alt_meta;    // [K][P] clique_rel | score << 8
-  uint32_t* alt_n;       // [G][K] entries incl. surplus
-  uint32_t* alt_score;   // [G][K] min score over the MinReplicas entries (written by k_alt_scores)
-  uint32_t* alt_nmin;    // [G][K] entries of the MinReplicas phase (the rest is best-effort surplus)
-  uint32_t* alt_top;     // [G][K]
-  uint32_t* nalt;        // [G]
-  uint32_t K, P;
-  uint32_t* F;           // [S][words] fit bitmap, one row per signature
-  uint8_t* T;            // [Q][npad]
-  const uint8_t* cap8;   // [S][npad] pods of the signature that fit on the node now (saturating), or null
-  const uint32_t* capsum; // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
-  const uint32_t* capmax; // [S][cap_stride] per-domain max of cap8
-  uint32_t caps_in_attempts;  // 1: the scalar evaluator packs from cap8 bytes, 0: from fit words + node records
-  uint32_t width0;            // candidates attempted in the very first step of a gang (1..32), warp-per-gang form
-  uint32_t width1;            // candidates per warp in the first attempt window of the CTA-per-gang forms (1..32)
-  uint32_t* dbg;              // [G][8] optional: successes, plausible, attempts, winning candidate, cycles, chunks
+// Control words of the relaxation (device memory; the host reads them back once per round or not at all)
+enum Ctl : uint32_t {
+  kFront = 0,      // settled prefix: every gang of rank < front is final
+  kHi,             // window end: gangs of rank in [front, hi) relax
+  kRound,          // relaxation round, from 1
+  kNEval,          // gangs in eval_list this round
+  kMinDirty,       // lowest rank that has to be (re-)evaluated after this round (becomes the next front)
+  kChanged,        // gangs whose tentative result changed this round
+  kEvals,          // evaluations so far (stat)
+  kOvfCount,       // entries in the claim overflow list
+  kRemAny,         // stamp (tag | rank): lowest rank that withdrew a claim this round
+  kDone,           // 1 when front == G
+  kTablesAt,       // front at the last capacity-table build
+  kRefresh,        // 1: rebuild the capacity tables before the next evaluation
+  kCtaDone,        // last-CTA-done counter of k_settle
+  kFoldAny,        // a settle pass folded claims into the committed state
+  kCtlWords = 16
 };
+
+// Relaxation state.  A gang's tentative result ("cur") lives in its own slots of the entry arrays and becomes final
+// in place; "nxt" is the scratch an evaluation writes before k_apply compares and publishes it.
+struct Relax {
+  uint32_t* ctl;            // [kCtlWords]
+  uint8_t* state;           // [G] final GROVE_GANG_* (PENDING until settled)
+  uint8_t* tstate;          // [G] tentative state of the last evaluation (0 = never evaluated)
+  uint8_t* dirty;           // [G] must be re-evaluated next round
+  uint32_t* chg_round;      // [G] last round in which the gang's tentative result changed
+  uint32_t* eval_list;      // [G]
+  // tentative / final result per gang
+  uint32_t* ent_node;       // [P]
+  uint16_t* ent_meta;       // [P] clique_rel
+  uint16_t* cur_n;          // [G] entries incl. surplus
+  uint32_t* cur_info;       // [G] gang level got (0xFF none) | score_num << 8 | score_den << 20
+  uint32_t* cur_glo;        // [G] first sorted node of the gang domain
+  uint32_t* extent;         // [G] nodes of the gang's visiting order its last evaluation may have read
+  uint8_t* sc_lvl;          // [NS] level each scope was packed at (0xFF: no own domain)
+  uint32_t* sc_lo;          // [NS]
+  // scratch of this round's evaluations
+  uint32_t* nxt_node;       // [P]
+  uint16_t* nxt_meta;       // [P]
+  uint16_t* nxt_n;          // [G]
+  uint8_t* nxt_tstate;      // [G]
+  uint32_t* nxt_info;       // [G]
+  uint32_t* nxt_glo;        // [G]
+  uint32_t* nxt_extent;     // [G]
+  uint8_t* nxt_sc_lvl;      // [NS]
+  uint32_t* nxt_sc_lo;      // [NS]
+  // claims of the tentative results: what gangs of higher rank subtract from the committed state
+  uint4* claims;            // [npad][kClaimSlots] x = rank (kClaimEmpty = free), y = cpu, z = mem, w = gpu | pods << 16
+  uint32_t* nlive;          // [npad / 4] one byte per node: live inline claims | kStale
+  uint32_t* has_ovf;        // [words] node has entries in the overflow list
+  uint32_t* ovf_node;       // [P]
+  uint4* ovf_claim;         // [P]
+  // change stamps of the round: (tag << 24) | lowest rank; a stale tag = no stamp
+  uint32_t* add_stamp;      // [npad] a gang newly claimed this node
+  uint32_t* rem_stamp;      // [words] a gang withdrew a claim from this 32-node group
+  // capacity tables over the committed state as of the last build (upper bounds afterwards)
+  uint32_t* F;              // [S][words] fit bitmap, one row per signature
+  uint8_t* cap8;            // [S][npad] pods of the signature that fit on the node (saturating at 255)
+  uint32_t* capsum;         // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
+  uint32_t* capmax;         // [S][cap_stride] per-domain max of cap8
+  uint8_t* T;               // [Q][npad] K2 score matrix over the cycle-start snapshot
+  uint32_t P, window;
+  uint32_t* dbg;            // [G][8] optional per-gang evaluation statistics
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(kFull, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+
+// stamp of round r for rank k: newer rounds carry SMALLER tags, so atomicMin lets a newer stamp beat a stale one
+__device__ __forceinline__ uint32_t stamp_tag(uint32_t round) { return kTagRounds - (round % kTagRounds); }  // 1..254
+__device__ __forceinline__ uint32_t make_stamp(uint32_t round, uint32_t rank) { return (stamp_tag(round) << 24) | rank; }
+__device__ __forceinline__ bool stamp_below(uint32_t s, uint32_t round, uint32_t rank) {
+  return (s >> 24) == stamp_tag(round) && (s & 0xFFFFFFu) < rank;
+}
 
 }  // namespace grove

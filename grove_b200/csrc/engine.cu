@@ -1,7 +1,7 @@
 // engine.cu -- libgrove_place.so: host side of the placement engine and the C ABI of
 // include/grove_place.h.  Everything that computes a placement runs in the kernels of kernels.cuh;
 // the host sorts the topology once per label change, validates and uploads tables, and drives the
-// optimistic rounds.  There is no CPU fallback: without a CUDA device the engine cannot be created.
+// relaxation rounds (relax.cuh).  There is no CPU fallback: without a CUDA device the engine cannot be created.
 #include <omp.h>
 
 #include <algorithm>
@@ -110,7 +110,7 @@ struct grove_engine {
   grove_config_t cfg{};
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream_score = nullptr;  // K2 runs beside K3 (they only share the fit data)
+  cudaStream_t stream_score = nullptr;  // K2 runs beside the relaxation (they only share the fit data)
   cudaEvent_t ev_fit = nullptr, ev_score = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   cudaEvent_t ev_nodes_up = nullptr, ev_tables_up = nullptr;  // the last upload out of the pinned node staging buffer / gang tables
   cudaEvent_t ev[10]{};
@@ -138,6 +138,7 @@ struct grove_engine {
   PinBuf<uint8_t> h_state0;        // initial gang states of a cycle
   PinBuf<GangInfo> ginfo_pin;      // derived tables are built straight into pinned memory: their upload is a plain DMA
   PinBuf<CliqueInfo> cinfo_pin;
+  PinBuf<uint32_t> by_rank_pin;
   GangInfo* ginfo = nullptr;
   CliqueInfo* cinfo = nullptr;
   std::vector<uint4> sigs;
@@ -149,52 +150,48 @@ struct grove_engine {
   DevBuf<GangInfo> d_ginfo;
   DevBuf<CliqueInfo> d_cinfo;
   DevBuf<uint4> d_sigs;
-  DevBuf<uint32_t> d_sig_stamp, d_sig_list;
+  DevBuf<uint32_t> d_by_rank;
 
-  // ---- round state ----
-  DevBuf<uint8_t> d_state, d_round, d_spec_score, d_T;
-  DevBuf<uint16_t> d_spec_n, d_ent_meta;
-  DevBuf<uint32_t> d_active, d_rows, d_counters, d_spec_top, d_ent_node, d_claim, d_F, d_totals;
+  // ---- relaxation state (relax.cuh) ----
+  DevBuf<uint32_t> d_ctl, d_chg_round, d_eval_list, d_ent_node, d_cur_info, d_cur_glo, d_extent, d_sc_lo;
+  DevBuf<uint32_t> d_nxt_node, d_nxt_info, d_nxt_glo, d_nxt_extent, d_nxt_sc_lo;
+  DevBuf<uint32_t> d_nlive, d_has_ovf, d_ovf_node, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
+  DevBuf<uint16_t> d_ent_meta, d_cur_n, d_nxt_meta, d_nxt_n;
+  DevBuf<uint8_t> d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
+  DevBuf<uint4> d_claims, d_ovf_claim;
   DevBuf<grove_gang_status_t> d_status;
+  DevBuf<grove_scope_status_t> d_scope_status;
   DevBuf<grove_placement_t> d_out;
-  DevBuf<uint32_t> d_xbuf, d_active_all, d_flags, d_capsum, d_capmax;
-  DevBuf<uint8_t> d_taken, d_cur, d_prop;
-  uint32_t K = GROVE_MAX_ALTERNATIVES;
   bool any_preferred = false;  // some gang / scope / clique carries a Preferred level
-  uint32_t n_constrained = 0, n_unconstrained = 0;  // gangs with / without a gang-level Required or Preferred level
   uint32_t max_gang_pods = 0;
-  int resolve_blocks_per_sm = 0;
   uint32_t n_sm = 148;
-  DevBuf<uint8_t> d_cap8;
   uint32_t cap_off[GROVE_MAX_LEVELS]{}, cap_stride = 0;
-  bool prefilter = false;
   bool dbg_on = false;
   DevBuf<uint32_t> d_dbg;
-  int tune_prefilter = 2;   // 0 off, 1 tables for the pre-filter, 2 tables also feed the packing
-  uint32_t tune_width0 = 24;  // packing attempts per window in the warp-per-gang kernel
-  uint32_t tune_width1 = 32;  // packing attempts per warp in the first window of the CTA-per-gang kernels (doubles per window)
-  // admission kernel form by number of active gangs: >= 10 per SM a warp per gang (gangs in flight matter),
-  // >= 4 per SM a 4-warp CTA per gang, below that an 8-warp CTA per gang (latency of one gang matters)
-  uint32_t tune_warp_min = 1480, tune_wide_max = 592;
-  bool tune_overlap = true;      // K2 on a second stream beside K3 (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
-  uint32_t tune_resolve_bps = 8;  // k_resolve CTAs per SM at most (fewer CTAs = cheaper grid barriers)
+  uint32_t tune_window = 0;        // gangs beyond the settled prefix that relax concurrently (0: all)
+  uint32_t tune_refresh = 512;     // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
+  bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
+  bool tune_score = true;          // materialise the K2 score matrix every cycle
+  PinBuf<uint32_t> h_upd_idx;
+  PinBuf<grove_node_t> h_upd_recs;
+  cudaEvent_t ev_upd = nullptr;
   DevBuf<uint32_t> d_upd_idx;
   DevBuf<grove_node_t> d_upd_recs;
   DevBuf<grove_node_t> d_nodes_out;  // grove_get_nodes scratch
-  PinBuf<uint32_t> h_counters;
+  PinBuf<uint32_t> h_ctl;
   PinBuf<grove_gang_status_t> h_status;
+  PinBuf<grove_scope_status_t> h_scope_status;
   PinBuf<grove_placement_t> h_out;
   PinBuf<grove_node_t> h_stage_nodes;
   uint32_t n_out = 0;
-  bool have_results = false;
+  bool have_results = false, have_scopes = false;
   grove_cycle_stats_t last{};
 
-  // stepping state (multi-GPU)
-  uint32_t round_no = 0;
   bool in_cycle = false;
-  bool stream_ordered = false;  // stepping calls return without the trailing host sync
-  uint64_t pairs = 0, launches = 0;
+  uint64_t launches = 0;
 };
+
 
 #define CU_TRY(e, expr)                                                                       \
   do {                                                                                        \
@@ -303,29 +300,28 @@ static Topo make_topo(grove_engine* e) {
   return t;
 }
 
+
 static Tables make_tables(grove_engine* e) {
   Tables t{};
   t.gangs = e->d_gangs.p; t.cliques = e->d_cliques.p; t.scopes = e->d_scopes.p;
-  t.ginfo = e->d_ginfo.p; t.cinfo = e->d_cinfo.p; t.sigs = e->d_sigs.p; t.G = e->G; t.Q = e->Q; t.S = e->n_sigs;
+  t.ginfo = e->d_ginfo.p; t.cinfo = e->d_cinfo.p; t.sigs = e->d_sigs.p; t.by_rank = e->d_by_rank.p;
+  t.G = e->G; t.Q = e->Q; t.S = e->n_sigs; t.NS = e->S;
   return t;
 }
 
-static RoundBufs make_bufs(grove_engine* e) {
-  RoundBufs r{};
-  r.state = e->d_state.p; r.round = e->d_round.p; r.active = e->d_active.p; r.rows = e->d_rows.p;
-  r.counters = e->d_counters.p; r.spec_score = e->d_spec_score.p;
-  r.spec_n = e->d_spec_n.p; r.spec_top = e->d_spec_top.p; r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p;
-  r.sig_stamp = e->d_sig_stamp.p; r.sig_list = e->d_sig_list.p;
-  r.active_all = e->d_active_all.p; r.taken = e->d_taken.p; r.cur = e->d_cur.p; r.prop = e->d_prop.p; r.flags = e->d_flags.p;
-  {
-    const size_t KP = size_t(e->K) * e->P, GK = size_t(e->G) * e->K;
-    uint32_t* x = e->d_xbuf.p;
-    r.alt_node = x; r.alt_meta = x + KP; r.alt_n = x + 2 * KP; r.alt_score = x + 2 * KP + GK; r.alt_top = x + 2 * KP + 2 * GK;
-    r.alt_nmin = x + 2 * KP + 3 * GK; r.nalt = x + 2 * KP + 4 * GK; r.K = e->K; r.P = e->P;
-  }
-  r.claim = e->d_claim.p; r.F = e->d_F.p; r.T = e->d_T.p;
-  r.cap8 = e->prefilter ? e->d_cap8.p : nullptr; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p;
-  r.caps_in_attempts = e->tune_prefilter >= 2; r.width0 = e->tune_width0; r.width1 = e->tune_width1; r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
+static Relax make_relax(grove_engine* e) {
+  Relax r{};
+  r.ctl = e->d_ctl.p; r.state = e->d_state.p; r.tstate = e->d_tstate.p; r.dirty = e->d_dirty.p; r.chg_round = e->d_chg_round.p;
+  r.eval_list = e->d_eval_list.p;
+  r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p; r.cur_n = e->d_cur_n.p; r.cur_info = e->d_cur_info.p; r.cur_glo = e->d_cur_glo.p;
+  r.extent = e->d_extent.p; r.sc_lvl = e->d_sc_lvl.p; r.sc_lo = e->d_sc_lo.p;
+  r.nxt_node = e->d_nxt_node.p; r.nxt_meta = e->d_nxt_meta.p; r.nxt_n = e->d_nxt_n.p; r.nxt_tstate = e->d_nxt_tstate.p;
+  r.nxt_info = e->d_nxt_info.p; r.nxt_glo = e->d_nxt_glo.p; r.nxt_extent = e->d_nxt_extent.p; r.nxt_sc_lvl = e->d_nxt_sc_lvl.p; r.nxt_sc_lo = e->d_nxt_sc_lo.p;
+  r.claims = e->d_claims.p; r.nlive = e->d_nlive.p; r.has_ovf = e->d_has_ovf.p; r.ovf_node = e->d_ovf_node.p; r.ovf_claim = e->d_ovf_claim.p;
+  r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p;
+  r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
+  r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u);
+  r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
 }
 
@@ -342,7 +338,6 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (cfg->abi_version != GROVE_ABI_VERSION) return GROVE_ERR_INVALID_ARG;
   if (cfg->n_levels < 1 || cfg->n_levels > GROVE_MAX_LEVELS) return GROVE_ERR_INVALID_ARG;
   if (cfg->world > 1 && cfg->rank >= cfg->world) return GROVE_ERR_INVALID_ARG;
-  if (cfg->alternatives > GROVE_MAX_ALTERNATIVES) return GROVE_ERR_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GROVE_ERR_NO_DEVICE;  // no CPU fallback
   if (cfg->device < 0 || cfg->device >= ndev) return GROVE_ERR_NO_DEVICE;
@@ -350,30 +345,24 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   grove_engine* e = new (std::nothrow) grove_engine();
   if (!e) return GROVE_ERR_OOM;
   e->cfg = *cfg; e->L = cfg->n_levels;
-  e->K = cfg->alternatives ? cfg->alternatives : GROVE_MAX_ALTERNATIVES;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->resolve_blocks_per_sm, k_resolve, kResolveThreads, 0);
-  if (e->resolve_blocks_per_sm < 1) e->resolve_blocks_per_sm = 1;
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
-  e->tune_warp_min = 10 * e->n_sm; e->tune_wide_max = 4 * e->n_sm;
-  if (const char* v = std::getenv("GROVE_TUNE_WARP_MIN")) e->tune_warp_min = uint32_t(std::max(1, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_WIDE_MAX")) e->tune_wide_max = uint32_t(std::max(1, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_PREFILTER")) e->tune_prefilter = std::atoi(v);
-  if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
-
+  e->tune_window = cfg->window;
+  if (const char* v = std::getenv("GROVE_TUNE_WINDOW")) if (!cfg->window) e->tune_window = uint32_t(std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_REFRESH")) e->tune_refresh = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
-  if (const char* v = std::getenv("GROVE_TUNE_RESOLVE_BPS")) e->tune_resolve_bps = uint32_t(std::max(1, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_WIDTH0")) e->tune_width0 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
-  if (const char* v = std::getenv("GROVE_TUNE_ALTERNATIVES")) if (!cfg->alternatives) e->K = uint32_t(std::min<int>(GROVE_MAX_ALTERNATIVES, std::max(1, std::atoi(v))));
-  if (const char* v = std::getenv("GROVE_TUNE_WIDTH1")) e->tune_width1 = uint32_t(std::min(32, std::max(1, std::atoi(v))));
+  if (const char* v = std::getenv("GROVE_TUNE_SCORE")) e->tune_score = std::atoi(v) != 0;
+  if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
   int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the latency-bound admission gets the SMs first
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the latency-bound relaxation gets the SMs first
   if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaStreamCreateWithPriority(&e->stream_score, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaEventCreateWithFlags(&e->ev_fit, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_score, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_nodes_up, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_tables_up, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&e->ev_s0) != cudaSuccess || cudaEventCreate(&e->ev_s1) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
-  if (e->h_counters.ensure(8) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
+  if (e->h_ctl.ensure(kCtlWords) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
   *out = e;
   return GROVE_OK;
 }
@@ -382,17 +371,20 @@ void grove_engine_destroy(grove_engine_t* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  cudaStreamSynchronize(e->stream_score);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->ev_s0) cudaEventDestroy(e->ev_s0);
   if (e->ev_s1) cudaEventDestroy(e->ev_s1);
   if (e->ev_fit) cudaEventDestroy(e->ev_fit);
   if (e->ev_nodes_up) cudaEventDestroy(e->ev_nodes_up);
   if (e->ev_tables_up) cudaEventDestroy(e->ev_tables_up);
+  if (e->ev_upd) cudaEventDestroy(e->ev_upd);
   if (e->ev_score) cudaEventDestroy(e->ev_score);
   if (e->stream_score) cudaStreamDestroy(e->stream_score);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
+
 
 static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes, const void* dev_nodes, uint32_t n) {
   if (n == 0 || n > GROVE_MAX_NODES) return fail(e, GROVE_ERR_INVALID_ARG, "node count out of range");
@@ -449,21 +441,24 @@ int32_t grove_update_nodes(grove_engine_t* e, const uint32_t* idx, const grove_n
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
   if (n == 0) return GROVE_OK;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  std::vector<uint32_t> sidx(n);
+  CU_TRY(e, cudaEventSynchronize(e->ev_upd));  // an earlier update may still be reading the pinned staging buffers
+  CU_TRY(e, e->h_upd_idx.ensure(n)); CU_TRY(e, e->h_upd_recs.ensure(n));
   for (uint32_t i = 0; i < n; ++i) {
     if (idx[i] >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "node index out of range");
     if (std::memcmp(&e->raw_dom[size_t(idx[i]) * GROVE_MAX_LEVELS], recs[i].dom, sizeof(uint32_t) * GROVE_MAX_LEVELS) != 0)
       return fail(e, GROVE_ERR_INVALID_ARG, "grove_update_nodes cannot change labels; reload the snapshot");
-    sidx[i] = e->inv[idx[i]];
+    e->h_upd_idx.p[i] = e->inv[idx[i]];
   }
+  std::memcpy(e->h_upd_recs.p, recs, sizeof(grove_node_t) * n);   // nothing of the caller's is referenced after return
   CU_TRY(e, e->d_upd_idx.ensure(n)); CU_TRY(e, e->d_upd_recs.ensure(n));
-  CU_TRY(e, cudaMemcpyAsync(e->d_upd_idx.p, sidx.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
-  CU_TRY(e, cudaMemcpyAsync(e->d_upd_recs.p, recs, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_upd_idx.p, e->h_upd_idx.p, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_upd_recs.p, e->h_upd_recs.p, sizeof(grove_node_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaEventRecord(e->ev_upd, e->stream));
   k_update<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_upd_idx.p, e->d_upd_recs.p, e->d_vdepth.p, e->d_perm.p, e->d_nres.p, e->d_nodes_in.p, n);
   CU_TRY(e, cudaGetLastError());
-  CU_TRY(e, cudaStreamSynchronize(e->stream));  // sidx is a local, recs the caller's
-  return GROVE_OK;
+  return GROVE_OK;   // stream-ordered: the next call on this handle sees the update
 }
+
 
 int32_t grove_get_nodes(grove_engine_t* e, grove_node_t* out, uint32_t cap) {
   if (!e || !out) return GROVE_ERR_INVALID_ARG;
@@ -540,7 +535,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
                            uint32_t n_cliques, const grove_scope_t* scopes, uint32_t n_scopes) {
   if (!e || (n_gangs && (!gangs || !cliques || !scopes))) return GROVE_ERR_INVALID_ARG;
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
-  if (n_gangs >= (1u << 24)) return fail(e, GROVE_ERR_LIMIT, "too many gangs");  // order rank + sub-round tag share a claim word
+  if (n_gangs >= (1u << 24)) return fail(e, GROVE_ERR_LIMIT, "too many gangs");  // order rank + round tag share a stamp word
   int32_t rc = validate(e, gangs, n_gangs, cliques, n_cliques, scopes, n_scopes);
   if (rc) return rc;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
@@ -550,12 +545,8 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   CU_TRY(e, e->cliques.assign(cliques, n_cliques));
   CU_TRY(e, e->scopes.assign(scopes, n_scopes));
   e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
-  e->n_constrained = e->n_unconstrained = 0;
   bool pref = false;
-  for (uint32_t g = 0; g < n_gangs; ++g) {
-    (gangs[g].level == GROVE_LEVEL_NONE && gangs[g].preferred == GROVE_LEVEL_NONE ? e->n_unconstrained : e->n_constrained)++;
-    pref |= gangs[g].preferred != GROVE_LEVEL_NONE;
-  }
+  for (uint32_t g = 0; g < n_gangs && !pref; ++g) pref |= gangs[g].preferred != GROVE_LEVEL_NONE;
   for (uint32_t i = 0; i < n_scopes && !pref; ++i) pref |= scopes[i].preferred1 != 0;
   for (uint32_t i = 0; i < n_cliques && !pref; ++i) pref |= (cliques[i].scope >> 5) != 0;
   e->any_preferred = pref;
@@ -567,11 +558,12 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   return GROVE_OK;  // the uploads read engine-owned pinned memory: nothing of the caller's is referenced any more
 }
 
+
 // derived per-gang / per-clique tables: order rank, anchor (sorted index + ancestor ranges), entry slots
 static int32_t build_ginfo(grove_engine* e) {
   const uint32_t G = e->G, Q = e->Q;
   const auto t_b0 = std::chrono::steady_clock::now();
-  CU_TRY(e, e->ginfo_pin.ensure(G)); CU_TRY(e, e->cinfo_pin.ensure(Q));
+  CU_TRY(e, e->ginfo_pin.ensure(G)); CU_TRY(e, e->cinfo_pin.ensure(Q)); CU_TRY(e, e->by_rank_pin.ensure(std::max<uint32_t>(G, 1)));
   e->ginfo = e->ginfo_pin.p; e->cinfo = e->cinfo_pin.p;
   {  // ginfo zeroed, cinfo all-ones (gang == NONE marks a row no gang owns yet), by the engine's thread team
     const int T0 = G >= 2048 ? host_threads() : 1;
@@ -655,6 +647,11 @@ static int32_t build_ginfo(grove_engine* e) {
     }
   }
   if (bad_anchor) return fail(e, GROVE_ERR_INVALID_ARG, "anchor node out of range");
+  {  // the inverse: which gang has its turn at each rank
+    const int T2 = G >= 2048 ? host_threads() : 1;
+#pragma omp parallel for num_threads(T2) schedule(static)
+    for (uint32_t gi = 0; gi < G; ++gi) e->by_rank_pin.p[e->ginfo[gi].order] = gi;
+  }
   const auto t_m1 = std::chrono::steady_clock::now();
   // per-clique derived data + signature interning.  PodCliques stamped from one template (PCS / PCSG
   // replicas) share requests, selector class and binding depth: they share one fit-bitmap row.  Gang
@@ -730,7 +727,7 @@ static int32_t build_ginfo(grove_engine* e) {
     if (e->cinfo[qi].gang == GROVE_NONE_U32) return fail(e, GROVE_ERR_INVALID_ARG, "clique row owned by no gang");
   e->n_sigs = uint32_t(e->sigs.size());
   CU_TRY(e, e->d_ginfo.ensure(G)); CU_TRY(e, e->d_cinfo.ensure(Q)); CU_TRY(e, e->d_sigs.ensure(e->n_sigs));
-  CU_TRY(e, e->d_sig_stamp.ensure(e->n_sigs)); CU_TRY(e, e->d_sig_list.ensure(e->n_sigs));
+  CU_TRY(e, e->d_by_rank.ensure(std::max<uint32_t>(G, 1)));
   if (e->n_sigs) CU_TRY(e, cudaMemcpyAsync(e->d_sigs.p, e->sigs.data(), sizeof(uint4) * e->n_sigs, cudaMemcpyHostToDevice, e->stream));
   if (G) {
     CU_TRY(e, cudaMemcpyAsync(e->d_ginfo.p, e->ginfo, sizeof(GangInfo) * G, cudaMemcpyHostToDevice, e->stream));
@@ -738,6 +735,7 @@ static int32_t build_ginfo(grove_engine* e) {
     CU_TRY(e, cudaGetLastError());
   }
   if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo, sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
+  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_by_rank.p, e->by_rank_pin.p, sizeof(uint32_t) * G, cudaMemcpyHostToDevice, e->stream));
   e->ginfo_dirty = false;
   if (std::getenv("GROVE_DEBUG_HOST")) {
     const auto t_b2 = std::chrono::steady_clock::now();
@@ -747,257 +745,185 @@ static int32_t build_ginfo(grove_engine* e) {
   return GROVE_OK;
 }
 
-int32_t grove_cycle_begin(grove_engine_t* e) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
+// capacity tables over the committed state: K1 fit bitmap for every signature, per-node capacities, per-domain sum / max
+static int32_t build_cap_tables(grove_engine* e, const Topo& tp, const Tables& tb, const Relax& rx) {
+  if (!e->n_sigs) return GROVE_OK;
+  dim3 gfit(e->Npad / 1024, std::min<uint32_t>((e->n_sigs + kFitTile - 1) / kFitTile, 65535u));
+  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p);
+  k_cap8<<<dim3(e->Npad / 256, e->n_sigs), 256, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p);
+  if (e->cap_stride) k_capsum<<<dim3((e->cap_stride * 32 + 255) / 256, e->n_sigs), 256, 0, e->stream>>>(tp, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+  k_clear_stale<<<(e->Npad / 4 + 255) / 256, 256, 0, e->stream>>>(rx, e->Npad / 4);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 4;
+  return GROVE_OK;
+}
+
+static int32_t cycle_begin(grove_engine* e) {
   if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
   if (!e->gangs_loaded) return fail(e, GROVE_ERR_STATE, "no gangs submitted");
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   if (e->ginfo_dirty) { int32_t rc = build_ginfo(e); if (rc) return rc; }
-  const uint32_t G = e->G, Q = e->Q;
-  CU_TRY(e, e->d_state.ensure(G)); CU_TRY(e, e->d_round.ensure(G)); CU_TRY(e, e->d_active.ensure(G)); CU_TRY(e, e->d_rows.ensure(Q));
-  CU_TRY(e, e->d_counters.ensure(8)); CU_TRY(e, e->d_spec_score.ensure(G));
-  CU_TRY(e, e->d_spec_n.ensure(G)); CU_TRY(e, e->d_spec_top.ensure(G)); CU_TRY(e, e->d_ent_node.ensure(e->P)); CU_TRY(e, e->d_ent_meta.ensure(e->P));
-  CU_TRY(e, e->d_claim.ensure(e->N)); CU_TRY(e, e->d_totals.ensure(4));
-  CU_TRY(e, e->d_taken.ensure(e->N)); CU_TRY(e, e->d_cur.ensure(G)); CU_TRY(e, e->d_prop.ensure(G)); CU_TRY(e, e->d_flags.ensure(GROVE_SUBROUNDS));
-  CU_TRY(e, e->d_active_all.ensure(G));
-  CU_TRY(e, e->d_xbuf.ensure(2 * size_t(e->K) * e->P + 4 * size_t(G) * e->K + G));
-  CU_TRY(e, cudaMemsetAsync(e->d_flags.p, 0, sizeof(uint32_t) * GROVE_SUBROUNDS, e->stream));  // round-stamped; rounds count from 1
-  CU_TRY(e, e->d_status.ensure(G)); CU_TRY(e, e->d_out.ensure(e->P));
-  CU_TRY(e, e->h_status.ensure(G)); CU_TRY(e, e->h_out.ensure(e->P));
-  // the Q x N matrices
+  const uint32_t G = e->G, Q = e->Q, S = e->S, P = e->P, N = e->Npad;
+  const size_t g1 = std::max<uint32_t>(G, 1), p1 = std::max<uint32_t>(P, 1), s1 = std::max<uint32_t>(S, 1);
+  CU_TRY(e, e->d_ctl.ensure(kCtlWords));
+  CU_TRY(e, e->d_state.ensure(g1)); CU_TRY(e, e->d_tstate.ensure(g1)); CU_TRY(e, e->d_dirty.ensure(g1)); CU_TRY(e, e->d_chg_round.ensure(g1));
+  CU_TRY(e, e->d_eval_list.ensure(g1));
+  CU_TRY(e, e->d_ent_node.ensure(p1)); CU_TRY(e, e->d_ent_meta.ensure(p1)); CU_TRY(e, e->d_cur_n.ensure(g1)); CU_TRY(e, e->d_cur_info.ensure(g1));
+  CU_TRY(e, e->d_cur_glo.ensure(g1)); CU_TRY(e, e->d_extent.ensure(g1)); CU_TRY(e, e->d_sc_lvl.ensure(s1)); CU_TRY(e, e->d_sc_lo.ensure(s1));
+  CU_TRY(e, e->d_nxt_node.ensure(p1)); CU_TRY(e, e->d_nxt_meta.ensure(p1)); CU_TRY(e, e->d_nxt_n.ensure(g1)); CU_TRY(e, e->d_nxt_tstate.ensure(g1));
+  CU_TRY(e, e->d_nxt_info.ensure(g1)); CU_TRY(e, e->d_nxt_glo.ensure(g1)); CU_TRY(e, e->d_nxt_extent.ensure(g1));
+  CU_TRY(e, e->d_nxt_sc_lvl.ensure(s1)); CU_TRY(e, e->d_nxt_sc_lo.ensure(s1));
+  CU_TRY(e, e->d_claims.ensure(size_t(N) * kClaimSlots)); CU_TRY(e, e->d_nlive.ensure(N / 4)); CU_TRY(e, e->d_has_ovf.ensure(e->words));
+  CU_TRY(e, e->d_ovf_node.ensure(p1)); CU_TRY(e, e->d_ovf_claim.ensure(p1));
+  CU_TRY(e, e->d_add_stamp.ensure(N)); CU_TRY(e, e->d_rem_stamp.ensure(e->words));
+  CU_TRY(e, e->d_status.ensure(g1)); CU_TRY(e, e->d_scope_status.ensure(s1)); CU_TRY(e, e->d_out.ensure(p1));
+  CU_TRY(e, e->h_status.ensure(g1)); CU_TRY(e, e->h_scope_status.ensure(s1)); CU_TRY(e, e->h_out.ensure(p1));
+  CU_TRY(e, e->d_fin.ensure((G + kFinThreads - 1) / kFinThreads + 4)); CU_TRY(e, e->d_totals.ensure(4));
+  // the S x N tables and the Q x N score matrix
   {
-    const size_t fw = size_t(e->n_sigs) * e->words, tb = size_t(Q) * e->Npad;
-    if (e->d_F.ensure(fw) != cudaSuccess || e->d_T.ensure(tb) != cudaSuccess) {
+    const size_t fw = size_t(e->n_sigs) * e->words, cb = size_t(e->n_sigs) * N, tw = size_t(e->n_sigs) * std::max<uint32_t>(e->cap_stride, 1);
+    if (e->d_F.ensure(std::max<size_t>(fw, 1)) != cudaSuccess || e->d_cap8.ensure(std::max<size_t>(cb, 1)) != cudaSuccess ||
+        e->d_capsum.ensure(tw) != cudaSuccess || e->d_capmax.ensure(tw) != cudaSuccess ||
+        (e->tune_score && e->d_T.ensure(std::max<size_t>(size_t(Q) * N, 1)) != cudaSuccess)) {
       (void)cudaGetLastError();
-      return fail(e, GROVE_ERR_OOM, "fit/score matrices do not fit in device memory");
+      return fail(e, GROVE_ERR_OOM, "fit / capacity / score matrices do not fit in device memory");
     }
   }
-  // capacity tables for the candidate pre-filter: worth building only while signatures are few
-  e->prefilter = false;
-  if (e->tune_prefilter && e->n_sigs && uint64_t(e->n_sigs) * e->Npad <= (64ull << 20) && e->cap_stride > 0) {
-    const size_t tw = size_t(e->n_sigs) * e->cap_stride;
-    if (e->d_cap8.ensure(size_t(e->n_sigs) * e->Npad) == cudaSuccess && e->d_capsum.ensure(tw) == cudaSuccess &&
-        e->d_capmax.ensure(tw) == cudaSuccess) e->prefilter = true;
-    else (void)cudaGetLastError();
+  if (e->dbg_on) { CU_TRY(e, e->d_dbg.ensure(g1 * 8)); CU_TRY(e, cudaMemsetAsync(e->d_dbg.p, 0, g1 * 32, e->stream)); }
+  cudaStream_t st = e->stream;
+  CU_TRY(e, cudaMemsetAsync(e->d_state.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_tstate.p, 0, g1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_dirty.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_chg_round.p, 0, sizeof(uint32_t) * g1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_cur_n.p, 0, sizeof(uint16_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_cur_info.p, 0, sizeof(uint32_t) * g1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_cur_glo.p, 0, sizeof(uint32_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_extent.p, 0, sizeof(uint32_t) * g1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_sc_lvl.p, 0xFF, s1, st)); CU_TRY(e, cudaMemsetAsync(e->d_sc_lo.p, 0xFF, sizeof(uint32_t) * s1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_claims.p, 0xFF, sizeof(uint4) * size_t(N) * kClaimSlots, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_has_ovf.p, 0, sizeof(uint32_t) * e->words, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, st));
+  {
+    uint32_t* c = e->h_ctl.p;
+    std::memset(c, 0, sizeof(uint32_t) * kCtlWords);
+    const uint32_t W = e->tune_window ? e->tune_window : std::max(G, 1u);
+    c[kFront] = 0; c[kHi] = std::min(G, W); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
+    CU_TRY(e, cudaMemcpyAsync(e->d_ctl.p, c, sizeof(uint32_t) * kCtlWords, cudaMemcpyHostToDevice, st));
+    CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
   }
-  if (e->dbg_on) CU_TRY(e, e->d_dbg.ensure(size_t(G) * 8));
-  // initial states: gated gangs are skipped (pods still hold the scheduling gate, pod.go:70,164)
-  CU_TRY(e, e->h_state0.ensure(G));
-  uint8_t* st = e->h_state0.p;   // rewritten only by the next cycle_begin, long after this upload has been consumed
-  for (uint32_t g = 0; g < G; ++g) st[g] = (e->gangs[g].flags & GROVE_GANG_GATED) ? GROVE_GANG_GATED_SKIP : GROVE_GANG_PENDING;
-  if (G) CU_TRY(e, cudaMemcpyAsync(e->d_state.p, st, G, cudaMemcpyHostToDevice, e->stream));
-  if (G) CU_TRY(e, cudaMemsetAsync(e->d_round.p, 0, G, e->stream));
-  if (G) CU_TRY(e, cudaMemsetAsync(e->d_spec_n.p, 0, sizeof(uint16_t) * G, e->stream));
-  if (e->n_sigs) CU_TRY(e, cudaMemsetAsync(e->d_sig_stamp.p, 0, sizeof(uint32_t) * e->n_sigs, e->stream));
-  e->round_no = 0; e->pairs = 0; e->launches = 0; e->in_cycle = true; e->have_results = false;
+  e->launches = 0; e->in_cycle = true; e->have_results = false; e->have_scopes = false;
   std::memset(&e->last, 0, sizeof(e->last));
   return GROVE_OK;
 }
 
-static size_t xbuf_words(const grove_engine* e) { return 2 * size_t(e->K) * e->P + 4 * size_t(e->G) * e->K + e->G; }
-
-// K3 launches of one round.  kPref: some gang / scope / clique of the submission carries a Preferred level
-// (the level walks are compiled in); otherwise the loop-free Required-only instantiations run.
-extern "C++" {
-template <bool kPref>
-static void launch_admit(grove_engine* e, const Topo& tp, const Tables& tb, const RoundBufs& rb, uint32_t na, bool caps, bool small) {
-  if (e->n_constrained) {
-    if (na >= e->tune_warp_min) {  // throughput round: a warp per gang
-      const uint32_t nb = (na + kAdmitWarpGangs - 1) / kAdmitWarpGangs;
-      const int th = kAdmitWarpGangs * 32;
-      if (caps && small) k_admit_warp<true, kEntSmem, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit_warp<true, 0, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit_warp<false, kEntSmem, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-      else k_admit_warp<false, 0, kPref><<<nb, th, 0, e->stream>>>(tp, tb, rb);
-    } else if (na >= e->tune_wide_max) {  // middle: a 4-warp CTA per gang
-      if (caps && small) k_admit<kAdmitThreads, 0, kEntSmem, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit<kAdmitThreads, 0, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit<kAdmitThreads, 1, kEntSmem, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-      else k_admit<kAdmitThreads, 1, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb);
-    } else {                // latency round: an 8-warp CTA per gang
-      if (caps && small) k_admit<kAdmitThreadsWide, 0, kEntSmem, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else if (caps) k_admit<kAdmitThreadsWide, 0, 0, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else if (small) k_admit<kAdmitThreadsWide, 1, kEntSmem, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-      else k_admit<kAdmitThreadsWide, 1, 0, kPref><<<na, kAdmitThreadsWide, 0, e->stream>>>(tp, tb, rb);
-    }
-    e->launches += 1;
-  }
-  if (e->n_unconstrained) { k_admit<kAdmitThreads, 2, 0, kPref><<<na, kAdmitThreads, 0, e->stream>>>(tp, tb, rb); e->launches += 1; }
-}
-}  // extern "C++"
-
-// evaluation half of a round on this handle's share of the gangs: prepare -> fit -> (capacity tables)
-// -> score -> admit.  Counters land in h_counters.
-static int32_t round_eval(grove_engine* e, bool timed) {
-  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
-  e->round_no++;
-  if (e->G == 0) { std::memset(e->h_counters.p, 0, sizeof(uint32_t) * 8); return GROVE_OK; }  // empty submission: nothing to launch
-  CU_TRY(e, cudaMemsetAsync(e->d_counters.p, 0, sizeof(uint32_t) * 8, e->stream));
-  k_prepare<<<(e->G + 1023) / 1024, 1024, 0, e->stream>>>(tb, rb, e->round_no, e->cfg.rank, e->cfg.world);
-  CU_TRY(e, cudaGetLastError());
-  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  e->launches += 1;
-  const uint32_t na = e->h_counters.p[0], nr = e->h_counters.p[1], ns = e->h_counters.p[4];
-  if (e->cfg.world > 1 && e->h_counters.p[5])  // all-reduce SUM payload: everything this rank does not own stays zero
-    CU_TRY(e, cudaMemsetAsync(e->d_xbuf.p, 0, sizeof(uint32_t) * xbuf_words(e), e->stream));
-  if (na == 0) return GROVE_OK;
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  dim3 gfit(e->Npad / 1024, std::min<uint32_t>((ns + kFitTile - 1) / kFitTile, 65535u));
-  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, rb);
-  // fork: the score matrix goes to the second stream and overlaps the admission
-  cudaStream_t ss = e->tune_overlap ? e->stream_score : e->stream;
-  if (e->tune_overlap) {
-    CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream));
-    CU_TRY(e, cudaStreamWaitEvent(e->stream_score, e->ev_fit, 0));
-  }
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev_s0, ss));
-  k_score<<<dim3(1, std::min<uint32_t>(nr, 65535u)), 256, 0, ss>>>(tp, tb, rb, nr);  // one CTA per row
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev_s1, ss));
-  if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_score, e->stream_score));
-  if (e->prefilter && ns) {
-    k_cap8<<<dim3(e->Npad / 256, ns), 256, 0, e->stream>>>(tp, tb, rb, e->d_cap8.p);
-    k_capsum<<<dim3((e->cap_stride * 32 + 255) / 256, ns), 256, 0, e->stream>>>(tp, rb, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
-    e->launches += 2;
-  }
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
-  if (e->dbg_on) { cudaMemsetAsync(e->d_dbg.p, 0, size_t(e->G) * 32, e->stream); k_dbg_init<<<(e->G + 255) / 256, 256, 0, e->stream>>>(e->d_dbg.p, e->G); }
-  const bool caps = e->prefilter && e->tune_prefilter >= 2;
-  const bool small = e->max_gang_pods <= kEntSmem;  // per-lane entry stacks fit the shared-memory form
-  if (e->any_preferred) launch_admit<true>(e, tp, tb, rb, na, caps, small); else launch_admit<false>(e, tp, tb, rb, na, caps, small);
-  // join: scores of the alternatives need both the score matrix and the alternatives
-  if (e->tune_overlap) CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_score, 0));
-  k_alt_scores<<<(na * e->K * 32 + 255) / 256, 256, 0, e->stream>>>(tp, tb, rb);
-  CU_TRY(e, cudaGetLastError());
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
-  e->launches += 3;
-  e->pairs += uint64_t(nr) * e->N;
-  return GROVE_OK;
-}
-
-// resolution half: sub-rounds over the alternatives of every rank's active gangs (replicated), commits
-static int32_t round_resolve(grove_engine* e, bool timed) {
-  const uint32_t na_all = e->h_counters.p[5];
-  if (na_all == 0) return GROVE_OK;
-  Topo tp = make_topo(e); Tables tb = make_tables(e); RoundBufs rb = make_bufs(e);
-  // The per-round scratch is stamped instead of cleared.  claim[n] carries a tag in its top byte that DEcreases with
-  // every (round, sub-round), so a newer claim always beats a stale one through atomicMin; taken[n] holds the stamp of
-  // the round that committed on n; flags[sub] the number of the round that proposed.  The arrays are reset only when a
-  // stamp would wrap: every kClaimRounds rounds (claim: the top byte stays below 0x7F = "no claim") / 254 rounds (taken).
-  const uint32_t r0 = e->round_no - 1;   // rounds count from 1
-  if (r0 % kClaimRounds == 0) CU_TRY(e, cudaMemsetAsync(e->d_claim.p, 0x7F, sizeof(uint32_t) * e->N, e->stream));
-  if (r0 % 254u == 0) CU_TRY(e, cudaMemsetAsync(e->d_taken.p, 0, e->N, e->stream));
-  uint32_t tag_hi = 0x7Eu - (r0 % kClaimRounds) * GROVE_SUBROUNDS;   // tag of sub-round 0 of this round
-  uint32_t tk = r0 % 254u + 1u;                                       // 1..254
-  uint4* nres = e->d_nres.p; uint32_t rn = e->round_no;
-  const uint32_t want = (na_all * 32 + kResolveThreads - 1) / kResolveThreads;  // a warp per gang
-  const uint32_t blocks = std::max(1u, std::min<uint32_t>(want, std::min<uint32_t>(uint32_t(e->resolve_blocks_per_sm), e->tune_resolve_bps) * e->n_sm));
-  void* args[] = {&tp, &tb, &rb, &nres, &rn, &tag_hi, &tk};
-  CU_TRY(e, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_resolve), dim3(blocks), dim3(kResolveThreads), args, 0, e->stream));
-  if (timed) CU_TRY(e, cudaEventRecord(e->ev[4], e->stream));
-  e->launches += 1;
-  return GROVE_OK;
-}
-
-static int32_t finish_cycle(grove_engine* e, grove_cycle_stats_t* stats) {
-  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const RoundBufs rb = make_bufs(e);
-  k_finalize<<<1, 1024, 0, e->stream>>>(tp, tb, rb, e->d_status.p, e->d_totals.p);
-  if (e->G) k_emit<<<(e->G * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rb, e->d_perm.p, e->d_status.p, e->d_out.p);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 2;
-  CU_TRY(e, cudaMemcpyAsync(e->h_counters.p, e->d_totals.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (e->G) CU_TRY(e, cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(grove_gang_status_t) * e->G, cudaMemcpyDeviceToHost, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  e->n_out = e->h_counters.p[0];
-  if (e->n_out) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->n_out, cudaMemcpyDeviceToHost, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream));
-  e->last.rounds = e->round_no; e->last.gangs_admitted = e->h_counters.p[1]; e->last.gangs_rejected = e->h_counters.p[2];
-  e->last.pods_bound = e->n_out; e->last.pairs_evaluated = e->pairs; e->last.kernel_launches = e->launches;
-  e->have_results = true; e->in_cycle = false;
-  if (stats) *stats = e->last;
-  return GROVE_OK;
-}
-
-// what the prepare pass decided (identical on every rank: it sees the replicated gang state):
-//  1 = a round is on, 0 = the cycle is over
-static int32_t after_prepare(grove_engine* e, uint32_t* go) {
-  *go = 0;
-  const uint32_t unres = e->h_counters.p[2], glob = e->h_counters.p[5];
-  if (unres == 0) { if (!e->h_counters.p[3]) e->round_no--; return GROVE_OK; }  // nothing left (and nothing propagated): not a round
-  if (glob == 0) {  // dependency cycle / unreachable base: nothing can ever become active
-    k_reject_rest<<<(e->G + 255) / 256, 256, 0, e->stream>>>(make_tables(e), make_bufs(e), e->round_no);
+static int32_t finish_cycle(grove_engine* e) {
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const Relax rx = make_relax(e);
+  const uint32_t G = e->G;
+  e->n_out = 0;
+  if (G) {
+    const uint32_t ncta = (G + kFinThreads - 1) / kFinThreads;
+    CU_TRY(e, cudaMemsetAsync(e->d_fin.p + ncta, 0, sizeof(uint32_t) * 4, e->stream));
+    k_fin_count<<<ncta, kFinThreads, 0, e->stream>>>(tb, rx, e->d_fin.p);
+    k_fin_scan<<<1, 1024, 0, e->stream>>>(e->d_fin.p, ncta, e->d_totals.p);
+    k_fin_status<<<ncta, kFinThreads, 0, e->stream>>>(tb, rx, e->d_fin.p, e->d_perm.p, e->d_status.p);
+    k_emit<<<(G * 32 + 255) / 256, 256, 0, e->stream>>>(tb, rx, e->d_perm.p, e->d_status.p, e->d_out.p, e->d_scope_status.p);
     CU_TRY(e, cudaGetLastError());
-    e->launches += 1;
-    return GROVE_OK;
+    e->launches += 4;
+    CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_totals.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(grove_gang_status_t) * G, cudaMemcpyDeviceToHost, e->stream));
+    // the placement count is only known on the device: copy the upper bound's worth in the same breath when it is small,
+    // else wait for the count
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    e->n_out = e->h_ctl.p[0];
+    if (e->n_out) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->n_out, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    e->last.gangs_admitted = e->h_ctl.p[1]; e->last.gangs_rejected = e->h_ctl.p[2];
   }
-  *go = 1;
+  (void)tp;
+  e->last.pods_bound = e->n_out; e->last.kernel_launches = e->launches;
+  e->have_results = true; e->in_cycle = false;
   return GROVE_OK;
 }
+
+struct CycleGuard {   // every error exit of a cycle leaves the handle usable (in_cycle stayed set)
+  grove_engine* e; bool armed = true;
+  ~CycleGuard() { if (armed) { e->in_cycle = false; cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->stream_score); } }
+};
 
 int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
   if (!e) return GROVE_ERR_INVALID_ARG;
-  if (e->cfg.world > 1) return fail(e, GROVE_ERR_STATE, "sharded handle: drive the cycle with grove_round_* and reduce between the steps");
-  const auto t_h0 = std::chrono::steady_clock::now();
-  int32_t rc = grove_cycle_begin(e);
-  const auto t_h1 = std::chrono::steady_clock::now();
+  int32_t rc = cycle_begin(e);
   if (rc) return rc;
-  float ms_fit = 0, ms_score = 0, ms_admit = 0, ms_commit = 0;
+  CycleGuard guard{e};
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const Relax rx = make_relax(e);
+  const uint32_t G = e->G;
   CU_TRY(e, cudaEventRecord(e->ev[8], e->stream));
-  for (;;) {
-    if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) break;
-    rc = round_eval(e, true);
-    if (rc) { e->in_cycle = false; return rc; }
-    uint32_t go = 0;
-    rc = after_prepare(e, &go);
-    if (rc) { e->in_cycle = false; return rc; }
-    if (!go) break;
-    const uint32_t na = e->h_counters.p[0];
-    rc = round_resolve(e, true);
-    if (rc) { e->in_cycle = false; return rc; }
-    CU_TRY(e, cudaEventSynchronize(e->ev[4]));
-    float t;
-    cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); ms_fit += t;
-    cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1); ms_score += t;  // on its own stream, overlapping the admission
-    cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_admit += t;
-    cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_commit += t;
-    if (e->dbg_on) {  // GROVE_DEBUG_ADMIT: per-round admission statistics on stderr
-      std::vector<uint32_t> h(size_t(e->G) * 8); std::vector<uint32_t> act(na);
-      cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
-      cudaMemcpy(act.data(), e->d_active.p, na * 4, cudaMemcpyDeviceToHost);
-      uint64_t sp = 0, sa = 0, sk = 0, won = 0, maxa = 0, ss = 0, full = 0;
-      for (uint32_t i = 0; i < na; ++i) {
-        const uint32_t* d = &h[size_t(act[i]) * 8]; sp += d[1]; sa += d[2]; ss += d[0]; maxa = std::max<uint64_t>(maxa, d[2]);
-        if (d[0] >= e->K) full++;
-        if (d[3] != 0xFFFFFFFFu) { won++; sk += d[3]; }
-      }
-      std::fprintf(stderr, "round %u: active %u plausible/gang %.1f attempts/gang %.1f (max %llu) successes/gang %.1f gangs with K %llu feasible %llu mean first feasible k %.1f\n",
-                   e->round_no, na, double(sp) / na, double(sa) / na, (unsigned long long)maxa, double(ss) / na, (unsigned long long)full, (unsigned long long)won,
-                   won ? double(sk) / won : 0.0);
-      // the slowest gangs of the round (SM cycles of their admission) and what they did
-      std::vector<uint32_t> idx(na); std::iota(idx.begin(), idx.end(), 0u);
-      std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return h[size_t(act[a]) * 8 + 4] > h[size_t(act[b]) * 8 + 4]; });
-      uint64_t cyc = 0; for (uint32_t i = 0; i < na; ++i) cyc += h[size_t(act[i]) * 8 + 4];
-      std::fprintf(stderr, "  mean cycles/gang %.0f, median %u; slowest:", double(cyc) / na, h[size_t(act[idx[na / 2]]) * 8 + 4]);
-      for (uint32_t i = 0; i < std::min(na, 6u); ++i) {
-        const uint32_t g = act[idx[i]]; const uint32_t* d = &h[size_t(g) * 8];
-        std::fprintf(stderr, " [g%u lvl%u cliques%u: %u cyc, %u chunks, %u plaus, %u att, %u succ]", g, unsigned(e->gangs[g].level), unsigned(e->gangs[g].n_cliques), d[4], d[5], d[1], d[2], d[0]);
-      }
-      std::fprintf(stderr, "\n");
+  uint32_t rounds = 0;
+  if (G) {
+    // K1 + capacity tables over the cycle-start snapshot; K2 (score matrix) forks to the second stream
+    CU_TRY(e, cudaEventRecord(e->ev[0], e->stream));
+    rc = build_cap_tables(e, tp, tb, rx);
+    if (rc) return rc;
+    CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
+    if (e->tune_score && e->Q) {
+      cudaStream_t ss = e->tune_overlap ? e->stream_score : e->stream;
+      if (e->tune_overlap) { CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream)); CU_TRY(e, cudaStreamWaitEvent(e->stream_score, e->ev_fit, 0)); }
+      CU_TRY(e, cudaEventRecord(e->ev_s0, ss));
+      k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, ss>>>(tp, tb, e->d_F.p, e->d_T.p, e->Q);  // one CTA per row
+      CU_TRY(e, cudaEventRecord(e->ev_s1, ss));
+      if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_score, e->stream_score));
+      e->launches += 1;
     }
+    CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
+    const uint32_t W = rx.window;
+    const uint32_t per_sm = e->tune_eval_ctas ? e->tune_eval_ctas : 8u;
+    const uint32_t eval_ctas = std::max(1u, std::min((W + kEvalWarps - 1) / kEvalWarps, e->n_sm * per_sm));
+    const uint32_t warp_ctas = std::max(1u, std::min((W * 32 + 255) / 256, e->n_sm * 8u));
+    for (;;) {
+      k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
+      if (e->any_preferred) k_eval<true><<<eval_ctas, kEvalWarps * 32, 0, e->stream>>>(tp, tb, rx);
+      else k_eval<false><<<eval_ctas, kEvalWarps * 32, 0, e->stream>>>(tp, tb, rx);
+      k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
+      k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
+      k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
+      CU_TRY(e, cudaGetLastError());
+      CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
+      CU_TRY(e, cudaStreamSynchronize(e->stream));
+      e->launches += 5; ++rounds;
+      const uint32_t* c = e->h_ctl.p;
+      if (e->dbg_on) std::fprintf(stderr, "round %u: front %u hi %u evals so far %u ovf %u\n", rounds, c[kFront], c[kHi], c[kEvals], c[kOvfCount]);
+      if (c[kDone]) break;
+      if (c[kOvfCount] > e->P) return fail(e, GROVE_ERR_LIMIT, "claim overflow list exhausted");
+      if (c[kRefresh]) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; }
+      if (c[kRound] % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
+        CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
+        CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
+      }
+    }
+    e->last.evaluations = e->h_ctl.p[kEvals];
   }
+  CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));
+  if (e->tune_score && e->tune_overlap && G && e->Q) CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_score, 0));  // the cycle ends when K2 has too
+  rc = finish_cycle(e);
+  if (rc) return rc;
   CU_TRY(e, cudaEventRecord(e->ev[9], e->stream));
-  const auto t_h2 = std::chrono::steady_clock::now();
-  rc = finish_cycle(e, nullptr);
-  if (std::getenv("GROVE_DEBUG_HOST")) {
-    const auto t_h3 = std::chrono::steady_clock::now();
-    auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
-    std::fprintf(stderr, "host: begin %ld us, rounds %ld us, finish %ld us\n", us(t_h0, t_h1), us(t_h1, t_h2), us(t_h2, t_h3));
+  CU_TRY(e, cudaEventSynchronize(e->ev[9]));
+  guard.armed = false;
+  float t = 0;
+  if (G) {
+    cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->last.ms_fit = t;
+    if (e->tune_score && e->Q) { cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1); e->last.ms_score = t; }
+    cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); e->last.ms_admit = t;
   }
-  if (rc) { e->in_cycle = false; return rc; }
-  float tot = 0; cudaEventElapsedTime(&tot, e->ev[8], e->ev[9]);
-  e->last.ms_fit = ms_fit; e->last.ms_score = ms_score; e->last.ms_admit = ms_admit; e->last.ms_commit = ms_commit; e->last.ms_total = tot;
+  cudaEventElapsedTime(&t, e->ev[3], e->ev[9]); e->last.ms_commit = t;
+  cudaEventElapsedTime(&t, e->ev[8], e->ev[9]); e->last.ms_total = t;
+  e->last.rounds = rounds;
+  e->last.pairs_evaluated = e->tune_score ? uint64_t(e->Q) * e->N : uint64_t(e->n_sigs) * e->N;
+  if (e->dbg_on && G) {
+    std::vector<uint32_t> h(size_t(G) * 8);
+    cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
+    uint64_t ev = 0, pl = 0, at = 0, mx = 0;
+    for (uint32_t g = 0; g < G; ++g) { ev += h[g * 8]; pl += h[g * 8 + 1]; at += h[g * 8 + 2]; mx = std::max<uint64_t>(mx, h[g * 8]); }
+    std::fprintf(stderr, "cycle: %u rounds, %llu evaluations (max %llu per gang), plausible/eval %.1f, attempts/eval %.2f\n", rounds,
+                 (unsigned long long)ev, (unsigned long long)mx, ev ? double(pl) / ev : 0.0, ev ? double(at) / ev : 0.0);
+  }
   if (stats) *stats = e->last;
   return GROVE_OK;
 }
@@ -1020,48 +946,17 @@ int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint3
   return GROVE_OK;
 }
 
-// ---- stepping API (multi-GPU hosts reduce the returned buffer between the two calls of a round) ----
-int32_t grove_round_eval(grove_engine_t* e, void** d_words, uint32_t* n_words, uint32_t* go) {
-  if (!e || !d_words || !n_words || !go) return GROVE_ERR_INVALID_ARG;
-  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  CU_TRY(e, cudaSetDevice(e->cfg.device));
-  *go = 0; *d_words = e->d_xbuf.p; *n_words = uint32_t(xbuf_words(e));
-  if (e->cfg.max_rounds && e->round_no >= e->cfg.max_rounds) return GROVE_OK;
-  int32_t rc = round_eval(e, false);
-  if (rc) return rc;
-  rc = after_prepare(e, go);
-  if (rc) return rc;
-  if (!e->stream_ordered) CU_TRY(e, cudaStreamSynchronize(e->stream));
-  return GROVE_OK;
-}
-
-int32_t grove_round_resolve(grove_engine_t* e, uint32_t* remaining) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
-  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  CU_TRY(e, cudaSetDevice(e->cfg.device));
-  int32_t rc = round_resolve(e, false);
-  if (rc) return rc;
-  if (!e->stream_ordered) CU_TRY(e, cudaStreamSynchronize(e->stream));
-  if (remaining) *remaining = e->h_counters.p[2];  // unresolved before this round's commits (upper bound)
-  return GROVE_OK;
-}
-
-int32_t grove_cycle_end(grove_engine_t* e, grove_cycle_stats_t* stats) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
-  if (!e->in_cycle) return fail(e, GROVE_ERR_STATE, "grove_cycle_begin first");
-  CU_TRY(e, cudaSetDevice(e->cfg.device));
-  return finish_cycle(e, stats);
-}
-
-int32_t grove_engine_stream(grove_engine_t* e, void** stream) {
-  if (!e || !stream) return GROVE_ERR_INVALID_ARG;
-  *stream = e->stream;
-  return GROVE_OK;
-}
-
-int32_t grove_set_stream_ordered(grove_engine_t* e, int32_t on) {
-  if (!e) return GROVE_ERR_INVALID_ARG;
-  e->stream_ordered = on != 0;
+int32_t grove_get_scope_domains(grove_engine_t* e, grove_scope_status_t* out, uint32_t cap) {
+  if (!e || !out) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results) return fail(e, GROVE_ERR_STATE, "no completed cycle");
+  if (cap < e->S) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  if (!e->have_scopes && e->S) {   // fetched on demand: most callers only bind pods
+    CU_TRY(e, cudaSetDevice(e->cfg.device));
+    CU_TRY(e, cudaMemcpyAsync(e->h_scope_status.p, e->d_scope_status.p, sizeof(grove_scope_status_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    e->have_scopes = true;
+  }
+  std::memcpy(out, e->h_scope_status.p, sizeof(grove_scope_status_t) * e->S);
   return GROVE_OK;
 }
 
@@ -1074,13 +969,19 @@ int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint
   return GROVE_OK;
 }
 
+// K1 over the cycle-start snapshot is recomputed on request (the engine's own table follows the committed state)
 int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* words, uint32_t cap_words) {
   if (!e || !words) return GROVE_ERR_INVALID_ARG;
   if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
   const uint32_t w = (e->N + 31) / 32;
   if (cap_words < w) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  if (!e->tune_score) return fail(e, GROVE_ERR_STATE, "score matrix disabled (GROVE_TUNE_SCORE=0)");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
-  CU_TRY(e, cudaMemcpy(words, e->d_F.p + size_t(e->cinfo[clique].sig) * e->words, sizeof(uint32_t) * w, cudaMemcpyDeviceToHost));
+  // the fit row of the cycle-start snapshot is the support of the score row
+  std::vector<uint8_t> row(e->N);
+  CU_TRY(e, cudaMemcpy(row.data(), e->d_T.p + size_t(clique) * e->Npad, e->N, cudaMemcpyDeviceToHost));
+  std::memset(words, 0, sizeof(uint32_t) * w);
+  for (uint32_t n = 0; n < e->N; ++n) if (row[n]) words[n >> 5] |= 1u << (n & 31);
   return GROVE_OK;
 }
 
@@ -1088,6 +989,7 @@ int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* b
   if (!e || !bytes) return GROVE_ERR_INVALID_ARG;
   if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
   if (cap_bytes < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  if (!e->tune_score) return fail(e, GROVE_ERR_STATE, "score matrix disabled (GROVE_TUNE_SCORE=0)");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   CU_TRY(e, cudaMemcpy(bytes, e->d_T.p + size_t(clique) * e->Npad, e->N, cudaMemcpyDeviceToHost));
   return GROVE_OK;

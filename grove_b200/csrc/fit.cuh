@@ -11,11 +11,11 @@ namespace grove {
 // ------------------------------------------------------------------------------------------------
 constexpr int kFitTile = 128;
 
-__global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) {
+__global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, uint32_t* __restrict__ F) {
   __shared__ uint4 s_prm[kFitTile];
   __shared__ uint32_t s_row[kFitTile];
   __shared__ uint32_t s_out[kFitTile][32];
-  const uint32_t n_rows = rb.counters[4];                 // active signatures
+  const uint32_t n_rows = tb.S;                            // every signature of the submission
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t node = blockIdx.x * 1024 + tid;           // npad is a multiple of 1024
   const uint4 r = __ldg(tp.nres + node);
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) 
     if (tid < kFitTile) {
       uint4 p = make_uint4(kFull, kFull, kFull, 0);  // never fits
       uint32_t sg = 0;
-      if (r0 + tid < n_rows) { sg = rb.sig_list[r0 + tid]; p = tb.sigs[sg]; }
+      if (r0 + tid < n_rows) { sg = r0 + tid; p = tb.sigs[sg]; }
       s_prm[tid] = p; s_row[tid] = sg;
     }
     __syncthreads();
@@ -40,22 +40,22 @@ __global__ void __launch_bounds__(1024) k_fit(Topo tp, Tables tb, RoundBufs rb) 
       if (lane == 0) s_out[c][warp] = b;
     }
     __syncthreads();
-    for (int c = warp; c < cnt; c += 32) rb.F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
+    for (int c = warp; c < cnt; c += 32) F[size_t(s_row[c]) * tp.words + blockIdx.x * 32 + lane] = s_out[c][lane];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Capacity tables for K3's candidate pre-filter (only built while the active signatures are few):
+// Capacity tables for K3 (candidate pre-filter and packing):
 // cap8[sig][n] = whole pods of the signature that fit on node n (0 if unfit, saturating at 255) and
 // its per-domain sum / max.  "sum over the fill domain >= MinReplicas" is a necessary condition for a
 // clique to be packable there, so domains failing it can be skipped without changing any result.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cap8(Topo tp, Tables tb, RoundBufs rb, uint8_t* cap8) {
-  const uint32_t sg = rb.sig_list[blockIdx.y];
+__global__ void __launch_bounds__(256) k_cap8(Topo tp, Tables tb, const uint32_t* __restrict__ F, uint8_t* cap8) {
+  const uint32_t sg = blockIdx.y;
   const uint32_t n = blockIdx.x * 256 + threadIdx.x;
   if (n >= tp.npad) return;
   uint32_t c = 0;
-  if ((__ldg(rb.F + size_t(sg) * tp.words + (n >> 5)) >> (n & 31)) & 1u) {
+  if ((__ldg(F + size_t(sg) * tp.words + (n >> 5)) >> (n & 31)) & 1u) {
     const uint4 r = __ldg(tp.nres + n);
     const uint4 q = tb.sigs[sg];
     c = r.z >> 16;
@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(256) k_cap8(Topo tp, Tables tb, RoundBufs rb, 
 }
 
 // one warp per (active signature, non-unit domain)
-__global__ void __launch_bounds__(256) k_capsum(Topo tp, RoundBufs rb, const uint8_t* __restrict__ cap8,
+__global__ void __launch_bounds__(256) k_capsum(Topo tp, const uint8_t* __restrict__ cap8,
                                                 uint32_t* capsum, uint32_t* capmax) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t j = (blockIdx.x * 256 + threadIdx.x) >> 5;   // column in the table row
   if (j >= tp.cap_stride) return;
-  const uint32_t sg = rb.sig_list[blockIdx.y];
+  const uint32_t sg = blockIdx.y;
   uint32_t l = 0;
 #pragma unroll
   for (uint32_t k = 0; k < GROVE_MAX_LEVELS; ++k)

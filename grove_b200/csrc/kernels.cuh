@@ -1,13 +1,12 @@
 // kernels.cuh -- sm_100a kernels of the gang-placement cycle (umbrella include).
 //
-//   tables.cuh   k_gather / k_scatter / k_update / k_anchor / k_prepare   table (un)packing, round bookkeeping
+//   tables.cuh   k_gather / k_scatter / k_update / k_anchor               table (un)packing
 //   fit.cuh      k_fit  K1  node x clique-signature resource-fit bitmap   (Filter; oracle: fit())
 //                k_cap8 / k_capsum  per-signature pod capacities and their per-domain sum / max
 //   score.cuh    k_score K2 topology-distance score matrix, u8            (Score;  oracle: closeness())
-//                k_alt_scores       joins the K2 stream with K3: score of every alternative
-//   admit.cuh    k_admit_warp / k_admit  K3  per-gang all-or-nothing admission, K alternatives per gang
-//   resolve.cuh  k_resolve  conflict resolution + commit of one round (cooperative launch);
-//                k_finalize / k_emit  outputs
+//   admit.cuh    k_eval  K3  one gang against its view: all-or-nothing admission, warp-cooperative packing
+//   relax.cuh    k_select / k_apply / k_detect / k_settle  the relaxation that makes the evaluations of all gangs
+//                agree with the sequential, priority-ordered pass; k_fin_* / k_emit  outputs
 //
 // Semantics are DESIGN.md "Placement semantics"; the reference contract they restate is cited in
 // include/grove_place.h.  Integer / compare work only: no tensor cores, no floating point.
@@ -17,4 +16,4 @@
 #include "fit.cuh"
 #include "score.cuh"
 #include "admit.cuh"
-#include "resolve.cuh"
+#include "relax.cuh"

@@ -1,0 +1,334 @@
+// relax.cuh -- the relaxation that turns per-gang evaluations into the sequential cycle, and the output kernels.
+#pragma once
+#include "common.cuh"
+#include "admit.cuh"
+
+namespace grove {
+// ------------------------------------------------------------------------------------------------
+// The cycle's result is defined sequentially: gang of rank 0, then rank 1, ... each against the state the
+// earlier ones left.  Equivalently: the unique assignment in which EVERY gang's placement equals its
+// evaluation against (committed state - claims of all gangs that rank before it).  The engine iterates
+// towards that fixed point with all gangs of a window at once:
+//
+//   round:  k_select   gangs of the window [front, hi) that were never evaluated or whose view changed
+//           k_eval     (admit.cuh) each of them against its view -> "nxt" scratch            [reads claims]
+//           k_apply    a changed result withdraws the gang's old claims and publishes the new
+//                      ones; every withdrawal / addition leaves a stamp (round tag | rank)   [writes claims]
+//           k_detect   whose view changed?  a gang is dirty if a LOWER rank added a claim on a node it uses
+//                      (capacity it counted on is gone), withdrew a claim in front of its extent (capacity it did
+//                      not see is back), or its base gang's result changed.  front' = lowest dirty rank.
+//           k_settle   gangs of rank < front' are final: every rank before them is final and their last
+//                      evaluation saw exactly those claims.  Their claims are folded into the committed state.
+//
+// Why it is exact: by induction on rank, a gang that is not dirty while everything before it is final holds the
+// sequential answer.  Why it terminates: the lowest gang of the window is never dirty after its evaluation.
+// Monotonicity does the rest of the work: resources only shrink inside a cycle, so additions by lower ranks
+// can only matter on the nodes a gang actually uses, and infeasible candidates stay infeasible.
+// Nothing here decides a result by arrival order: claims are sums, stamps are minima.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_select(Tables tb, Relax rx) {
+  const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi];
+  const uint32_t p = front + blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  bool need = false; uint32_t g = 0;
+  if (p < hi) {
+    g = tb.by_rank[p];
+    need = rx.tstate[g] == 0 || rx.dirty[g];
+    if (need) rx.dirty[g] = 0;
+  }
+  const uint32_t b = __ballot_sync(kFull, need);
+  uint32_t base = 0;
+  if (lane == 0 && b) base = atomicAdd(rx.ctl + kNEval, __popc(b));
+  base = __shfl_sync(kFull, base, 0);
+  if (need) rx.eval_list[base + __popc(b & ((1u << lane) - 1u))] = g;
+}
+
+// ---- claims --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nlive_add(uint32_t* nlive, uint32_t n, int delta) {
+  const uint32_t sh = (n & 3u) * 8u;
+  if (delta > 0) atomicAdd(nlive + (n >> 2), 1u << sh); else atomicSub(nlive + (n >> 2), 1u << sh);
+}
+
+// withdraw ONE claim slot of `rank` on node n (the caller owns exactly one per entry run)
+__device__ __forceinline__ void claim_remove(const Relax& rx, uint32_t n, uint32_t rank) {
+  uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
+  for (uint32_t s = 0; s < kClaimSlots; ++s)
+    if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) { nlive_add(rx.nlive, n, -1); return; }
+  const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(rx.ctl + kOvfCount);
+  for (uint32_t i = 0; i < cnt; ++i)
+    if (rx.ovf_node[i] == n && atomicCAS(reinterpret_cast<uint32_t*>(rx.ovf_claim + i), rank, kClaimEmpty) == rank) return;
+}
+
+__device__ __forceinline__ void claim_add(const Relax& rx, uint32_t n, uint32_t rank, uint32_t cpu, uint32_t mem, uint32_t gpw) {
+  uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
+  for (uint32_t s = 0; s < kClaimSlots; ++s)
+    if (atomicCAS(line + 4 * s, kClaimEmpty, rank) == kClaimEmpty) {
+      line[4 * s + 1] = cpu; line[4 * s + 2] = mem; line[4 * s + 3] = gpw;
+      nlive_add(rx.nlive, n, +1);
+      return;
+    }
+  // more than kClaimSlots gangs lean on this node: overflow list (entries are never moved; dead ones stay dead)
+  const uint32_t i = atomicAdd(rx.ctl + kOvfCount, 1u);
+  rx.ovf_node[i] = n;
+  rx.ovf_claim[i] = make_uint4(rank, cpu, mem, gpw);
+  atomicOr(rx.has_ovf + (n >> 5), 1u << (n & 31u));
+}
+
+// entry i of a placement starts a run of pods of one clique on one node; returns its length (0 = not a head)
+__device__ __forceinline__ uint32_t run_length(const uint32_t* node, const uint16_t* meta, uint32_t i, uint32_t cnt) {
+  if (i && node[i - 1] == node[i] && meta[i - 1] == meta[i]) return 0;
+  uint32_t t = 1;
+  while (i + t < cnt && node[i + t] == node[i] && meta[i + t] == meta[i]) ++t;
+  return t;
+}
+
+// one warp per evaluated gang: publish a changed result
+__global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_eval = rx.ctl[kNEval], round = rx.ctl[kRound];
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < n_eval; ei += nw) {
+    const uint32_t g = rx.eval_list[ei];
+    const grove_gang_t gg = tb.gangs[g];
+    const uint32_t po = tb.ginfo[g].pod_off, rank = tb.ginfo[g].order;
+    const uint32_t ot = rx.tstate[g], nt = rx.nxt_tstate[g];
+    const uint32_t on = ot == GROVE_GANG_ADMITTED ? rx.cur_n[g] : 0u, nn = nt == GROVE_GANG_ADMITTED ? rx.nxt_n[g] : 0u;
+    bool diff = ot != nt || on != nn || rx.cur_info[g] != rx.nxt_info[g] || rx.cur_glo[g] != rx.nxt_glo[g];
+    if (!diff) {
+      for (uint32_t i = lane; i < nn; i += 32) diff |= rx.ent_node[po + i] != rx.nxt_node[po + i] || rx.ent_meta[po + i] != rx.nxt_meta[po + i];
+      for (uint32_t si = lane; si < gg.n_scopes; si += 32)
+        diff |= rx.sc_lvl[gg.scope_off + si] != rx.nxt_sc_lvl[gg.scope_off + si] || rx.sc_lo[gg.scope_off + si] != rx.nxt_sc_lo[gg.scope_off + si];
+    }
+    diff = __any_sync(kFull, diff);
+    if (lane == 0) rx.extent[g] = rx.nxt_extent[g];   // what the LATEST evaluation read, changed result or not
+    if (!diff) continue;
+    const uint32_t stamp = make_stamp(round, rank);
+    // withdraw the old claims
+    for (uint32_t i = lane; i < on; i += 32) {
+      if (!run_length(rx.ent_node + po, rx.ent_meta + po, i, on)) continue;
+      const uint32_t n = rx.ent_node[po + i];
+      claim_remove(rx, n, rank);
+      atomicMin(rx.rem_stamp + (n >> 5), stamp);
+    }
+    if (on && lane == 0) atomicMin(rx.ctl + kRemAny, stamp);
+    __syncwarp();
+    // publish the new ones
+    for (uint32_t i = lane; i < nn; i += 32) {
+      const uint32_t n = rx.nxt_node[po + i]; const uint16_t m = rx.nxt_meta[po + i];
+      const uint32_t t = run_length(rx.nxt_node + po, rx.nxt_meta + po, i, nn);
+      if (t) {
+        const grove_clique_t q = tb.cliques[gg.clique_off + m];
+        claim_add(rx, n, rank, t * q.req_cpu_milli, t * q.req_mem_mib, t * uint32_t(q.req_gpu) | (t << 16));
+        atomicMin(rx.add_stamp + n, stamp);
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nn; i += 32) { rx.ent_node[po + i] = rx.nxt_node[po + i]; rx.ent_meta[po + i] = rx.nxt_meta[po + i]; }
+    for (uint32_t si = lane; si < gg.n_scopes; si += 32) { rx.sc_lvl[gg.scope_off + si] = rx.nxt_sc_lvl[gg.scope_off + si]; rx.sc_lo[gg.scope_off + si] = rx.nxt_sc_lo[gg.scope_off + si]; }
+    if (lane == 0) {
+      rx.tstate[g] = uint8_t(nt); rx.cur_n[g] = uint16_t(nn); rx.cur_info[g] = rx.nxt_info[g]; rx.cur_glo[g] = rx.nxt_glo[g];
+      rx.chg_round[g] = round;
+      atomicAdd(rx.ctl + kChanged, 1u);
+    }
+  }
+}
+
+// one warp per gang of the window: did its view change this round?
+__global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi], round = rx.ctl[kRound];
+  const uint32_t rem_any = rx.ctl[kRemAny];
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t p = front + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < hi; p += nw) {
+    const uint32_t g = tb.by_rank[p];   // rank of g == p
+    const grove_gang_t gg = tb.gangs[g];
+    bool dirty = false;
+    // its base gang's result changed
+    if (gg.base_gang != GROVE_NONE_U32 && rx.chg_round[gg.base_gang] == round) dirty = true;
+    // a lower rank newly claimed a node this gang uses
+    if (!dirty && rx.tstate[g] == GROVE_GANG_ADMITTED) {
+      const uint32_t po = tb.ginfo[g].pod_off, cnt = rx.cur_n[g];
+      for (uint32_t i = lane; i < cnt; i += 32) dirty |= stamp_below(rx.add_stamp[rx.ent_node[po + i]], round, p);
+      dirty = __any_sync(kFull, dirty);
+    }
+    // a lower rank withdrew a claim among the nodes the last evaluation may have read
+    uint32_t left = rx.extent[g];
+    if (!dirty && left && stamp_below(rem_any, round, p)) {
+      const GangInfo info = tb.ginfo[g];
+      GangRegs gr;
+      gr.a = info.anchor; gr.L = tp.L; gr.n = tp.n; gr.rank = p;
+#pragma unroll
+      for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { gr.anc_lo[l] = info.anc_lo[l]; gr.anc_hi[l] = info.anc_hi[l]; }
+      uint32_t plo[kMaxPieces], phi[kMaxPieces];
+      const int npc = make_pieces(gr, 0, tp.n, tp.L, plo, phi);
+      for (int k = 0; k < npc && left && !dirty; ++k) {
+        const uint32_t len = min(phi[k] - plo[k], left);
+        left -= len;
+        const uint32_t g0 = plo[k] >> 5, g1 = (plo[k] + len - 1u) >> 5;
+        bool hit = false;
+        for (uint32_t w = g0 + lane; w <= g1; w += 32) hit |= stamp_below(rx.rem_stamp[w], round, p);
+        dirty = __any_sync(kFull, hit);
+      }
+    }
+    if (dirty && lane == 0) { rx.dirty[g] = 1; atomicMin(rx.ctl + kMinDirty, p); }
+  }
+}
+
+// one warp per gang that became final: fold its claims into the committed state.  The last CTA to finish advances
+// the window and resets the per-round control words.
+__global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres, uint32_t refresh_every) {
+  __shared__ bool s_last;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t front = rx.ctl[kFront], nf = rx.ctl[kMinDirty];
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  bool folded = false;
+  for (uint32_t p = front + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < nf; p += nw) {
+    const uint32_t g = tb.by_rank[p];
+    const uint32_t t = rx.tstate[g];
+    if (lane == 0) rx.state[g] = uint8_t(t);
+    if (t != GROVE_GANG_ADMITTED) continue;
+    const uint32_t po = tb.ginfo[g].pod_off, cnt = rx.cur_n[g], coff = tb.gangs[g].clique_off;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t len = run_length(rx.ent_node + po, rx.ent_meta + po, i, cnt);
+      if (!len) continue;
+      const uint32_t n = rx.ent_node[po + i];
+      const grove_clique_t q = tb.cliques[coff + rx.ent_meta[po + i]];
+      claim_remove(rx, n, p);
+      uint32_t* r = reinterpret_cast<uint32_t*>(nres + n);
+      if (q.req_cpu_milli) atomicSub(r + 0, len * q.req_cpu_milli);
+      if (q.req_mem_mib) atomicSub(r + 1, len * q.req_mem_mib);
+      atomicSub(r + 2, len * uint32_t(q.req_gpu) | (len << 16));
+      atomicOr(rx.nlive + (n >> 2), kStale << ((n & 3u) * 8u));   // the capacity tables no longer describe this node
+    }
+    folded |= cnt != 0;
+  }
+  if (__any_sync(kFull, folded) && lane == 0) rx.ctl[kFoldAny] = 1;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(rx.ctl + kCtaDone, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    const uint32_t G = tb.G;
+    const uint32_t h2 = min(G, nf + rx.window);
+    rx.ctl[kEvals] += rx.ctl[kNEval];
+    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kChanged] = 0;
+    rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
+    rx.ctl[kDone] = nf >= G ? 1u : 0u;
+    if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every && rx.ctl[kFoldAny]) rx.ctl[kRefresh] = 1;
+    __threadfence();
+  }
+}
+
+// after a capacity-table build: the tables describe every node again
+__global__ void k_clear_stale(Relax rx, uint32_t n_words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) rx.nlive[i] &= 0x7F7F7F7Fu;
+  if (i == 0) { rx.ctl[kTablesAt] = rx.ctl[kFront]; rx.ctl[kRefresh] = 0; rx.ctl[kFoldAny] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs: compact the admitted gangs' entries into caller order / caller node indices
+// ------------------------------------------------------------------------------------------------
+// pass 1: per-CTA pod totals; pass 2 (one CTA): exclusive scan of the totals; pass 3: statuses with global offsets
+constexpr int kFinThreads = 1024;
+
+__global__ void __launch_bounds__(kFinThreads) k_fin_count(Tables tb, Relax rx, uint32_t* cta_tot) {
+  __shared__ uint32_t s_w[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t g = blockIdx.x * kFinThreads + tid;
+  uint32_t cnt = 0, adm = 0, rej = 0;
+  if (g < tb.G) {
+    const uint8_t st = rx.state[g];
+    if (st == GROVE_GANG_ADMITTED) { cnt = rx.cur_n[g]; adm = 1; }
+    rej = st == GROVE_GANG_REJECTED || st == GROVE_GANG_BASE_REJECTED;
+  }
+  uint32_t v = cnt | 0;   // three sums through one reduction each
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { v += __shfl_xor_sync(kFull, v, o); adm += __shfl_xor_sync(kFull, adm, o); rej += __shfl_xor_sync(kFull, rej, o); }
+  if (lane == 0) { s_w[warp] = v; atomicAdd(cta_tot + gridDim.x + 1, adm); atomicAdd(cta_tot + gridDim.x + 2, rej); }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t t = s_w[lane];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if (lane == 0) cta_tot[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_fin_scan(uint32_t* cta_tot, uint32_t n_cta, uint32_t* totals) {
+  // n_cta <= 16384 gangs-per-CTA blocks; a single CTA scans them in chunks of 1024
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_run;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_cta; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = i < n_cta ? cta_tot[i] : 0u;
+    const uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) { const uint32_t w = s_w[lane]; const uint32_t s = warp_incl_scan(w, lane); s_w[lane] = s - w; }
+    __syncthreads();
+    const uint32_t excl = s_run + s_w[warp] + incl - v;
+    if (i < n_cta) cta_tot[i] = excl;
+    __syncthreads();
+    if (tid == 1023) s_run = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) { totals[0] = s_run; totals[1] = cta_tot[n_cta + 1]; totals[2] = cta_tot[n_cta + 2]; }
+}
+
+__global__ void __launch_bounds__(kFinThreads) k_fin_status(Tables tb, Relax rx, const uint32_t* __restrict__ cta_off,
+                                                          const uint32_t* __restrict__ perm, grove_gang_status_t* status) {
+  __shared__ uint32_t s_w[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t g = blockIdx.x * kFinThreads + tid;
+  uint32_t cnt = 0; uint8_t st = 0;
+  if (g < tb.G) { st = rx.state[g]; if (st == GROVE_GANG_ADMITTED) cnt = rx.cur_n[g]; }
+  const uint32_t incl = warp_incl_scan(cnt, lane);
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) { const uint32_t w = s_w[lane]; const uint32_t s = warp_incl_scan(w, lane); s_w[lane] = s - w; }
+  __syncthreads();
+  if (g < tb.G) {
+    grove_gang_status_t o;
+    o.state = st; o.level = GROVE_LEVEL_NONE; o.reserved0 = 0; o.score_num = 0; o.score_den = 0;
+    o.n_pods = cnt; o.placement_off = cta_off[blockIdx.x] + s_w[warp] + incl - cnt;
+    o.domain_node = GROVE_NONE_U32; o.reserved1[0] = o.reserved1[1] = o.reserved1[2] = 0;
+    if (st == GROVE_GANG_ADMITTED) {
+      const uint32_t info = rx.cur_info[g];
+      o.level = uint8_t(info & 0xFFu); o.score_num = uint16_t((info >> 8) & 0xFFFu); o.score_den = uint16_t(info >> 20);
+      if ((info & 0xFFu) != GROVE_LEVEL_NONE) o.domain_node = perm[rx.cur_glo[g]];
+    }
+    status[g] = o;
+  }
+}
+
+// one warp per gang: its entries -> caller node indices, at the offset k_fin_status assigned; its scopes' domains
+__global__ void k_emit(Tables tb, Relax rx, const uint32_t* __restrict__ perm, const grove_gang_status_t* __restrict__ status,
+                       grove_placement_t* out, grove_scope_status_t* scopes_out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= tb.G) return;
+  const grove_gang_status_t st = status[g];
+  const grove_gang_t gg = tb.gangs[g];
+  const bool adm = st.state == GROVE_GANG_ADMITTED;
+  for (uint32_t si = lane; si < gg.n_scopes; si += 32) {
+    grove_scope_status_t s;
+    s.level = GROVE_LEVEL_NONE; s.reserved[0] = s.reserved[1] = s.reserved[2] = 0; s.domain_node = GROVE_NONE_U32;
+    if (adm && rx.sc_lvl[gg.scope_off + si] != 0xFFu) { s.level = rx.sc_lvl[gg.scope_off + si]; s.domain_node = perm[rx.sc_lo[gg.scope_off + si]]; }
+    scopes_out[gg.scope_off + si] = s;
+  }
+  if (!adm) return;
+  const uint32_t po = tb.ginfo[g].pod_off;
+  for (uint32_t i = lane; i < st.n_pods; i += 32) {
+    grove_placement_t p;
+    p.clique = gg.clique_off + rx.ent_meta[po + i];
+    p.node = perm[rx.ent_node[po + i]];
+    out[st.placement_off + i] = p;
+  }
+}
+
+}  // namespace grove

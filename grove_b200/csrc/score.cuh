@@ -1,4 +1,4 @@
-// score.cuh -- K2: topology-distance score matrix, and the join kernel that scores the alternatives.
+// score.cuh -- K2: topology-distance score matrix.
 #pragma once
 #include "common.cuh"
 
@@ -13,17 +13,17 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {  // 4 bits -> 4 byte
   return (nib * 0x00204081u) & 0x01010101u;
 }
 
-__global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb, uint32_t n_rows) {
+__global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, const uint32_t* __restrict__ F, uint8_t* __restrict__ T, uint32_t n_rows) {
   const uint32_t cpr = tp.npad >> 4;  // 16-node chunks per row
   for (uint32_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
-    const uint32_t q = __ldg(rb.rows + r);
+    const uint32_t q = r;   // one row per clique of the submission
     const CliqueInfo ci = tb.cinfo[q];
     const GangInfo* gi = tb.ginfo + ci.gang;
     const uint4 alo = __ldg(reinterpret_cast<const uint4*>(gi->anc_lo));
     const uint4 ahi = __ldg(reinterpret_cast<const uint4*>(gi->anc_hi));
     const uint32_t lo[4] = {alo.x, alo.y, alo.z, alo.w}, hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
-    const uint32_t* Frow = rb.F + size_t(ci.sig) * tp.words;
-    uint8_t* Trow = rb.T + size_t(q) * tp.npad;
+    const uint32_t* Frow = F + size_t(ci.sig) * tp.words;
+    uint8_t* Trow = T + size_t(q) * tp.npad;
     for (uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch < cpr; ch += gridDim.x * blockDim.x) {
       const uint32_t n0 = ch << 4;
       const uint32_t bits = (__ldg(Frow + (n0 >> 5)) >> (n0 & 16)) & 0xFFFFu;
@@ -59,36 +59,6 @@ __global__ void __launch_bounds__(256) k_score(Topo tp, Tables tb, RoundBufs rb,
       *reinterpret_cast<uint4*>(Trow + n0) = out;
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Scores of the alternatives.  The score matrix (K2) and the admission (K3) only share the fit data, so
-// they run concurrently on two streams (K2 is HBM-write-bound, K3 is latency-bound: they overlap almost
-// perfectly); this kernel joins them: one warp per (active gang, alternative) looks up T[clique row][node]
-// for every entry, stores it next to the entry and reduces the minimum over the MinReplicas entries --
-// the PlacementScore numerator (podgang.go:187-189).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_alt_scores(Topo tp, Tables tb, RoundBufs rb) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t K = rb.K, P = rb.P;
-  const uint32_t ai = w / K, a = w - ai * K;
-  if (ai >= rb.counters[0]) return;
-  const uint32_t g = rb.active[ai];
-  if (a >= rb.nalt[g]) return;
-  const uint32_t po = tb.ginfo[g].pod_off, coff = tb.gangs[g].clique_off;
-  const uint32_t cnt = rb.alt_n[size_t(g) * K + a], nmin = rb.alt_nmin[size_t(g) * K + a];
-  uint32_t mn = tp.L + 1;
-  for (uint32_t i = lane; i < cnt; i += 32) {
-    const size_t o = size_t(a) * P + po + i;
-    const uint32_t cr = rb.alt_meta[o] & 0xFFu;
-    const uint32_t sc = rb.T[size_t(coff + cr) * tp.npad + rb.alt_node[o]];
-    rb.alt_meta[o] = cr | (sc << 8);
-    if (i < nmin) mn = min(mn, sc);
-  }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) mn = min(mn, __shfl_xor_sync(kFull, mn, d));
-  if (lane == 0) rb.alt_score[size_t(g) * K + a] = mn;
 }
 
 }  // namespace grove

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import tables as T
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrove_place.so")
 
@@ -23,8 +23,7 @@ ERRORS = {0: "OK", -1: "INVALID_ARG", -2: "NO_DEVICE", -3: "CUDA", -4: "LIMIT", 
 SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
-    "grove_get_placements", "grove_get_gang_status", "grove_load_nodes_device", "grove_cycle_begin",
-    "grove_round_eval", "grove_round_resolve", "grove_cycle_end", "grove_engine_stream", "grove_set_stream_ordered",
+    "grove_get_placements", "grove_get_gang_status", "grove_get_scope_domains", "grove_load_nodes_device",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -62,20 +61,19 @@ def _p(a):
 class PlacementEngine:
     """One scheduler session on one GPU (not thread-safe; one cycle in flight)."""
 
-    def __init__(self, n_levels: int, device: int = 0, max_rounds: int = 0, rank: int = 0, world: int = 1,
-                 alternatives: int = 0):
+    def __init__(self, n_levels: int, device: int = 0, window: int = 0, rank: int = 0, world: int = 1):
         self.lib = load_library()
         cfg = np.zeros(1, dtype=T.config_dt)
         cfg["abi_version"] = ABI_VERSION
-        cfg["device"], cfg["n_levels"], cfg["max_rounds"] = device, n_levels, max_rounds
-        cfg["rank"], cfg["world"], cfg["alternatives"] = rank, world, alternatives
+        cfg["device"], cfg["n_levels"], cfg["window"] = device, n_levels, window
+        cfg["rank"], cfg["world"] = rank, world
         self.h = C.c_void_p()
         rc = self.lib.grove_engine_create(_p(cfg), C.byref(self.h))
         if rc != 0:
             self.h = None
             raise GroveError(rc, "grove_engine_create failed (no CPU fallback exists)")
         self.n_levels = n_levels
-        self.n = self.G = self.Q = 0
+        self.n = self.G = self.Q = self.S = 0
         self._cap_pods = 0
         self._pl_buf = self._st_buf = None
 
@@ -120,42 +118,13 @@ class PlacementEngine:
         scopes = np.ascontiguousarray(scopes, dtype=T.scope_dt)
         self._check(self.lib.grove_submit_gangs(self.h, _p(gangs), C.c_uint32(len(gangs)), _p(cliques),
                                                 C.c_uint32(len(cliques)), _p(scopes), C.c_uint32(len(scopes))))
-        self.G, self.Q = len(gangs), len(cliques)
+        self.G, self.Q, self.S = len(gangs), len(cliques), len(scopes)
         self._cap_pods = int(cliques["replicas"].astype(np.int64).sum()) if len(cliques) else 0
 
     # ---- the cycle ----
     def run_cycle(self) -> dict:
         st = np.zeros(1, dtype=T.stats_dt)
         self._check(self.lib.grove_run_cycle(self.h, _p(st)))
-        return {k: st[k][0].item() for k in T.stats_dt.names}
-
-    # ---- stepping (multi-GPU hosts reduce the returned device buffers between the calls) ----
-    def cycle_begin(self):
-        self._check(self.lib.grove_cycle_begin(self.h))
-
-    def round_eval(self):
-        """-> (device pointer, int32 words, go)"""
-        p, n, go = C.c_void_p(), C.c_uint32(0), C.c_uint32(0)
-        self._check(self.lib.grove_round_eval(self.h, C.byref(p), C.byref(n), C.byref(go)))
-        return p.value, n.value, bool(go.value)
-
-    def stream(self) -> int:
-        """cudaStream_t of the engine (as an integer), e.g. for torch.cuda.ExternalStream"""
-        p = C.c_void_p()
-        self._check(self.lib.grove_engine_stream(self.h, C.byref(p)))
-        return p.value or 0
-
-    def set_stream_ordered(self, on: bool):
-        self._check(self.lib.grove_set_stream_ordered(self.h, C.c_int32(1 if on else 0)))
-
-    def round_resolve(self) -> int:
-        r = C.c_uint32(0)
-        self._check(self.lib.grove_round_resolve(self.h, C.byref(r)))
-        return r.value
-
-    def cycle_end(self) -> dict:
-        st = np.zeros(1, dtype=T.stats_dt)
-        self._check(self.lib.grove_cycle_end(self.h, _p(st)))
         return {k: st[k][0].item() for k in T.stats_dt.names}
 
     # ---- outputs ----
@@ -176,6 +145,12 @@ class PlacementEngine:
         self._check(self.lib.grove_get_gang_status(self.h, _p(self._st_buf), C.c_uint32(len(self._st_buf))))
         out = self._st_buf[: self.G]
         return out.copy() if copy else out
+
+    def scope_domains(self) -> np.ndarray:
+        """chosen topology domain of every scope (TopologyConstraintGroupConfig) of the submission"""
+        out = np.zeros(max(self.S, 1), dtype=T.scope_status_dt)
+        self._check(self.lib.grove_get_scope_domains(self.h, _p(out), C.c_uint32(len(out))))
+        return out[: self.S]
 
     def nodes(self) -> np.ndarray:
         out = np.zeros(self.n, dtype=T.node_dt)

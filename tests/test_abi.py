@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in declared_symbols():
         assert hasattr(lib, s), s
     lib.grove_abi_version.restype = C.c_uint32
-    assert lib.grove_abi_version() == 1
+    assert lib.grove_abi_version() == 2
 
 
 def test_library_is_sm100a_only(built_lib):
@@ -44,6 +44,7 @@ def test_struct_layouts_match_header(tmp_path):
     fields = {
         "grove_node_t": T.node_dt, "grove_clique_t": T.clique_dt, "grove_scope_t": T.scope_dt,
         "grove_gang_t": T.gang_dt, "grove_placement_t": T.placement_dt, "grove_gang_status_t": T.status_dt,
+        "grove_scope_status_t": T.scope_status_dt,
         "grove_config_t": T.config_dt, "grove_cycle_stats_t": T.stats_dt,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
