@@ -144,7 +144,7 @@ struct Ev {
     const uint32_t sm = sh.smask[cr];
     if (!(r.w & GROVE_NODE_SCHEDULABLE) || !((sm >> ((r.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) & 1u) || ((r.w >> 16) & 0xFu) < (sm >> 16)) return 0u;
     uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-    if (live & 0x7Fu) {   // claims of the gangs that rank before this one
+    if (live & 0x3Fu) {   // claims of the gangs that rank before this one
       const uint4* line = rb.claims + size_t(n) * kClaimSlots;
 #pragma unroll
       for (uint32_t s = 0; s < kClaimSlots; ++s) {
@@ -154,11 +154,9 @@ struct Ev {
         }
       }
     }
-    if ((__ldg(rb.has_ovf + (n >> 5)) >> (n & 31u)) & 1u) {
-      const uint32_t cnt = __ldcg(rb.ctl + kOvfCount);
-      for (uint32_t i = 0; i < cnt; ++i) {
-        if (__ldg(rb.ovf_node + i) != n) continue;
-        const uint4 c = __ldg(rb.ovf_claim + i);
+    if (live & kHasOvf) {   // more than kClaimSlots gangs leaned on this node at some point: its overflow chain
+      for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
+        const uint4 c = __ldg(rb.ovf_claim + i - 1);
         if (c.x < g.rank) { cpu -= min(cpu, c.y); mem -= min(mem, c.z); gpu -= min(gpu, c.w & 0xFFFFu); pods -= min(pods, c.w >> 16); }
       }
     }

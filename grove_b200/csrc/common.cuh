@@ -13,6 +13,7 @@ constexpr int kMaxPieces = 2 * GROVE_MAX_LEVELS + 3;
 constexpr uint32_t kClaimSlots = 8;           // inline claim slots per node (one 128 B line); more spill to the overflow list
 constexpr uint32_t kClaimEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kStale = 0x80u;            // nlive8 bit: committed state changed since the capacity tables were built
+constexpr uint32_t kHasOvf = 0x40u;           // nlive8 bit: the node has (had) claims in the overflow chain
 constexpr uint32_t kTagRounds = 254u;         // rounds per stamp epoch (stamps carry a round tag in their top byte)
 
 struct GangInfo {     // 48 B, built on the host at submit time
@@ -64,7 +65,7 @@ enum Ctl : uint32_t {
   kMinDirty,       // lowest rank that has to be (re-)evaluated after this round (becomes the next front)
   kChanged,        // gangs whose tentative result changed this round
   kEvals,          // evaluations so far (stat)
-  kOvfCount,       // entries in the claim overflow list
+  kOvfCount,       // entries handed out of the claim overflow pool
   kRemAny,         // stamp (tag | rank): lowest rank that withdrew a claim this round
   kDone,           // 1 when front == G
   kTablesAt,       // front at the last capacity-table build
@@ -104,10 +105,11 @@ struct Relax {
   uint32_t* nxt_sc_lo;      // [NS]
   // claims of the tentative results: what gangs of higher rank subtract from the committed state
   uint4* claims;            // [npad][kClaimSlots] x = rank (kClaimEmpty = free), y = cpu, z = mem, w = gpu | pods << 16
-  uint32_t* nlive;          // [npad / 4] one byte per node: live inline claims | kStale
-  uint32_t* has_ovf;        // [words] node has entries in the overflow list
-  uint32_t* ovf_node;       // [P]
-  uint4* ovf_claim;         // [P]
+  uint32_t* nlive;          // [npad / 4] one byte per node: live inline claims | kHasOvf | kStale
+  uint32_t* ovf_head;       // [npad] first entry + 1 of the node's overflow chain (0 = none)
+  uint32_t* ovf_next;       // [ovf_cap] next entry + 1
+  uint4* ovf_claim;         // [ovf_cap] same layout as a claim slot; dead entries (x = kClaimEmpty) are revived by later claims on the node
+  uint32_t ovf_cap;
   // change stamps of the round: (tag << 24) | lowest rank; a stale tag = no stamp
   uint32_t* add_stamp;      // [npad] a gang newly claimed this node
   uint32_t* rem_stamp;      // [words] a gang withdrew a claim from this 32-node group
@@ -117,7 +119,7 @@ struct Relax {
   uint32_t* capsum;         // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
   uint32_t* capmax;         // [S][cap_stride] per-domain max of cap8
   uint8_t* T;               // [Q][npad] K2 score matrix over the cycle-start snapshot
-  uint32_t P, window;
+  uint32_t P, window, entry;
   uint32_t* dbg;            // [G][8] optional per-gang evaluation statistics
 };
 

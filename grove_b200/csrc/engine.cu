@@ -155,7 +155,7 @@ struct grove_engine {
   // ---- relaxation state (relax.cuh) ----
   DevBuf<uint32_t> d_ctl, d_chg_round, d_eval_list, d_ent_node, d_cur_info, d_cur_glo, d_extent, d_sc_lo;
   DevBuf<uint32_t> d_nxt_node, d_nxt_info, d_nxt_glo, d_nxt_extent, d_nxt_sc_lo;
-  DevBuf<uint32_t> d_nlive, d_has_ovf, d_ovf_node, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
+  DevBuf<uint32_t> d_nlive, d_ovf_head, d_ovf_next, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
   DevBuf<uint16_t> d_ent_meta, d_cur_n, d_nxt_meta, d_nxt_n;
   DevBuf<uint8_t> d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
   DevBuf<uint4> d_claims, d_ovf_claim;
@@ -169,6 +169,7 @@ struct grove_engine {
   bool dbg_on = false;
   DevBuf<uint32_t> d_dbg;
   uint32_t tune_window = 0;        // gangs beyond the settled prefix that relax concurrently (0: all)
+  uint32_t tune_entry = 1024;      // gangs that may join the window per round (0: no limit)
   uint32_t tune_refresh = 512;     // rebuild the capacity tables once the settled prefix has advanced this many gangs
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
   bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
@@ -317,10 +318,11 @@ static Relax make_relax(grove_engine* e) {
   r.extent = e->d_extent.p; r.sc_lvl = e->d_sc_lvl.p; r.sc_lo = e->d_sc_lo.p;
   r.nxt_node = e->d_nxt_node.p; r.nxt_meta = e->d_nxt_meta.p; r.nxt_n = e->d_nxt_n.p; r.nxt_tstate = e->d_nxt_tstate.p;
   r.nxt_info = e->d_nxt_info.p; r.nxt_glo = e->d_nxt_glo.p; r.nxt_extent = e->d_nxt_extent.p; r.nxt_sc_lvl = e->d_nxt_sc_lvl.p; r.nxt_sc_lo = e->d_nxt_sc_lo.p;
-  r.claims = e->d_claims.p; r.nlive = e->d_nlive.p; r.has_ovf = e->d_has_ovf.p; r.ovf_node = e->d_ovf_node.p; r.ovf_claim = e->d_ovf_claim.p;
+  r.claims = e->d_claims.p; r.nlive = e->d_nlive.p; r.ovf_head = e->d_ovf_head.p; r.ovf_next = e->d_ovf_next.p; r.ovf_claim = e->d_ovf_claim.p;
+  r.ovf_cap = uint32_t(std::min<size_t>(e->d_ovf_claim.cap, 0xFFFFFFF0u));
   r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p;
   r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
-  r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u);
+  r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u); r.entry = e->tune_entry ? e->tune_entry : r.window;
   r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
 }
@@ -348,6 +350,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   { int sm = 0; if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sm > 0) e->n_sm = uint32_t(sm); }
   e->tune_window = cfg->window;
   if (const char* v = std::getenv("GROVE_TUNE_WINDOW")) if (!cfg->window) e->tune_window = uint32_t(std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_ENTRY")) e->tune_entry = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_REFRESH")) e->tune_refresh = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
@@ -774,8 +777,8 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, e->d_nxt_node.ensure(p1)); CU_TRY(e, e->d_nxt_meta.ensure(p1)); CU_TRY(e, e->d_nxt_n.ensure(g1)); CU_TRY(e, e->d_nxt_tstate.ensure(g1));
   CU_TRY(e, e->d_nxt_info.ensure(g1)); CU_TRY(e, e->d_nxt_glo.ensure(g1)); CU_TRY(e, e->d_nxt_extent.ensure(g1));
   CU_TRY(e, e->d_nxt_sc_lvl.ensure(s1)); CU_TRY(e, e->d_nxt_sc_lo.ensure(s1));
-  CU_TRY(e, e->d_claims.ensure(size_t(N) * kClaimSlots)); CU_TRY(e, e->d_nlive.ensure(N / 4)); CU_TRY(e, e->d_has_ovf.ensure(e->words));
-  CU_TRY(e, e->d_ovf_node.ensure(p1)); CU_TRY(e, e->d_ovf_claim.ensure(p1));
+  CU_TRY(e, e->d_claims.ensure(size_t(N) * kClaimSlots)); CU_TRY(e, e->d_nlive.ensure(N / 4)); CU_TRY(e, e->d_ovf_head.ensure(N));
+  CU_TRY(e, e->d_ovf_next.ensure(4 * p1 + 1024)); CU_TRY(e, e->d_ovf_claim.ensure(4 * p1 + 1024));
   CU_TRY(e, e->d_add_stamp.ensure(N)); CU_TRY(e, e->d_rem_stamp.ensure(e->words));
   CU_TRY(e, e->d_status.ensure(g1)); CU_TRY(e, e->d_scope_status.ensure(s1)); CU_TRY(e, e->d_out.ensure(p1));
   CU_TRY(e, e->h_status.ensure(g1)); CU_TRY(e, e->h_scope_status.ensure(s1)); CU_TRY(e, e->h_out.ensure(p1));
@@ -798,13 +801,14 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, cudaMemsetAsync(e->d_cur_glo.p, 0, sizeof(uint32_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_extent.p, 0, sizeof(uint32_t) * g1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_sc_lvl.p, 0xFF, s1, st)); CU_TRY(e, cudaMemsetAsync(e->d_sc_lo.p, 0xFF, sizeof(uint32_t) * s1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_claims.p, 0xFF, sizeof(uint4) * size_t(N) * kClaimSlots, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_has_ovf.p, 0, sizeof(uint32_t) * e->words, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_ovf_head.p, 0, sizeof(uint32_t) * N, st));
   CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, st));
   {
     uint32_t* c = e->h_ctl.p;
     std::memset(c, 0, sizeof(uint32_t) * kCtlWords);
     const uint32_t W = e->tune_window ? e->tune_window : std::max(G, 1u);
-    c[kFront] = 0; c[kHi] = std::min(G, W); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
+    const uint32_t E = e->tune_entry ? e->tune_entry : W;
+    c[kFront] = 0; c[kHi] = std::min(G, std::min(W, E)); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
     CU_TRY(e, cudaMemcpyAsync(e->d_ctl.p, c, sizeof(uint32_t) * kCtlWords, cudaMemcpyHostToDevice, st));
     CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
   }
@@ -890,7 +894,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       const uint32_t* c = e->h_ctl.p;
       if (e->dbg_on) std::fprintf(stderr, "round %u: front %u hi %u evals so far %u ovf %u\n", rounds, c[kFront], c[kHi], c[kEvals], c[kOvfCount]);
       if (c[kDone]) break;
-      if (c[kOvfCount] > e->P) return fail(e, GROVE_ERR_LIMIT, "claim overflow list exhausted");
+      if (c[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
       if (c[kRefresh]) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; }
       if (c[kRound] % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
         CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));

@@ -55,9 +55,8 @@ __device__ __forceinline__ void claim_remove(const Relax& rx, uint32_t n, uint32
   uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
   for (uint32_t s = 0; s < kClaimSlots; ++s)
     if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) { nlive_add(rx.nlive, n, -1); return; }
-  const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(rx.ctl + kOvfCount);
-  for (uint32_t i = 0; i < cnt; ++i)
-    if (rx.ovf_node[i] == n && atomicCAS(reinterpret_cast<uint32_t*>(rx.ovf_claim + i), rank, kClaimEmpty) == rank) return;
+  for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1])
+    if (atomicCAS(reinterpret_cast<uint32_t*>(rx.ovf_claim + i - 1), rank, kClaimEmpty) == rank) return;
 }
 
 __device__ __forceinline__ void claim_add(const Relax& rx, uint32_t n, uint32_t rank, uint32_t cpu, uint32_t mem, uint32_t gpw) {
@@ -68,11 +67,24 @@ __device__ __forceinline__ void claim_add(const Relax& rx, uint32_t n, uint32_t 
       nlive_add(rx.nlive, n, +1);
       return;
     }
-  // more than kClaimSlots gangs lean on this node: overflow list (entries are never moved; dead ones stay dead)
+  // more than kClaimSlots gangs lean on this node: its overflow chain.  A dead entry of the chain is revived first;
+  // otherwise a pool entry is pushed on the chain's head (entries never leave a chain during a cycle)
+  for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1]) {
+    uint32_t* e = reinterpret_cast<uint32_t*>(rx.ovf_claim + i - 1);
+    if (atomicCAS(e, kClaimEmpty, rank) == kClaimEmpty) { e[1] = cpu; e[2] = mem; e[3] = gpw; return; }
+  }
   const uint32_t i = atomicAdd(rx.ctl + kOvfCount, 1u);
-  rx.ovf_node[i] = n;
+  if (i >= rx.ovf_cap) return;   // pool exhausted: the host sees the count and fails the cycle
   rx.ovf_claim[i] = make_uint4(rank, cpu, mem, gpw);
-  atomicOr(rx.has_ovf + (n >> 5), 1u << (n & 31u));
+  uint32_t old = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n);
+  for (;;) {
+    rx.ovf_next[i] = old;
+    __threadfence();
+    const uint32_t seen = atomicCAS(rx.ovf_head + n, old, i + 1u);
+    if (seen == old) break;
+    old = seen;
+  }
+  atomicOr(rx.nlive + (n >> 2), kHasOvf << ((n & 3u) * 8u));
 }
 
 // entry i of a placement starts a run of pods of one clique on one node; returns its length (0 = not a head)
@@ -210,7 +222,9 @@ __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     const uint32_t G = tb.G;
-    const uint32_t h2 = min(G, nf + rx.window);
+    // the window: at most `window` gangs beyond the settled prefix, at most `entry` new ones per round (gangs that meet
+    // the claims of the ranks before them on their first evaluation pile up less on the same nodes)
+    const uint32_t h2 = min(G, min(nf + rx.window, max(rx.ctl[kHi], nf) + rx.entry));
     rx.ctl[kEvals] += rx.ctl[kNEval];
     rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kChanged] = 0;
     rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres
 // after a capacity-table build: the tables describe every node again
 __global__ void k_clear_stale(Relax rx, uint32_t n_words) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_words) rx.nlive[i] &= 0x7F7F7F7Fu;
+  if (i < n_words) rx.nlive[i] &= ~0x80808080u;
   if (i == 0) { rx.ctl[kTablesAt] = rx.ctl[kFront]; rx.ctl[kRefresh] = 0; rx.ctl[kFoldAny] = 0; }
 }
 

@@ -1,0 +1,31 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+cat > /tmp/c4run.py <<'PY'
+import numpy as np, time, os, sys
+from grove_b200 import synth
+from grove_b200.engine import PlacementEngine
+from oracle import oracle_py as O
+cfg = synth.config_c4()
+g, c, s = cfg["tables"]
+ref = None
+if os.environ.get("CHECK"):
+    t = time.time(); ref = O.run_cycle(cfg["nodes"], cfg["n_levels"], g, c, s, threads=16); print("oracle %.1fs" % (time.time() - t), ref["stats"]["gangs_admitted"], flush=True)
+with PlacementEngine(cfg["n_levels"]) as e:
+    e.load_nodes(cfg["nodes"]); e.submit_gangs(g, c, s)
+    for i in range(4):
+        e.load_nodes(cfg["nodes"])
+        st = e.run_cycle()
+    print(os.environ.get("TAG", ""), {k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items() if k in ("rounds", "evaluations", "gangs_admitted", "ms_fit", "ms_score", "ms_admit", "ms_total")}, flush=True)
+    if ref is not None:
+        print("identical:", np.array_equal(e.placements(), ref["placements"]), np.array_equal(e.gang_status(), ref["status"]), np.array_equal(e.scope_domains(), ref["scope_status"]), np.array_equal(e.nodes(), ref["nodes_after"]), flush=True)
+PY
+(
+CHECK=1 TAG=default timeout 300 python /tmp/c4run.py
+for E in 256 512 2048 4096 0; do TAG="entry=$E" GROVE_TUNE_ENTRY=$E timeout 120 python /tmp/c4run.py; done
+for W in 1024 2048 4096; do TAG="window=$W entry=512" GROVE_TUNE_WINDOW=$W GROVE_TUNE_ENTRY=512 timeout 120 python /tmp/c4run.py; done
+for R in 128 2048 100000; do TAG="refresh=$R" GROVE_TUNE_REFRESH=$R timeout 120 python /tmp/c4run.py; done
+TAG="noscore" GROVE_TUNE_SCORE=0 timeout 120 python /tmp/c4run.py
+GROVE_DEBUG_ADMIT=1 TAG=dbg timeout 120 python /tmp/c4run.py 2>&1 | tail -32
+) 2>&1 | tee gpurun_out/dev_sweep.log
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_random_parity_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/dev_tests.log
