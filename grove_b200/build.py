@@ -11,6 +11,7 @@ SOURCES = ["engine.cu"]
 DEPS = ["engine.cu", "kernels.cuh", "common.cuh", "tables.cuh", "fit.cuh", "score.cuh", "admit.cuh", "relax.cuh",
         os.path.join("..", "..", "include", "grove_place.h")]
 NVCC_FLAGS = [
+    "-DGROVE_INLINE_ALL",
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-fopenmp", "-shared", "-cudart", "shared", "-lgomp",
 ]

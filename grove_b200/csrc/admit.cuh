@@ -2,6 +2,12 @@
 #pragma once
 #include "common.cuh"
 
+#ifdef GROVE_INLINE_ALL
+#define GROVE_NI __forceinline__
+#else
+#define GROVE_NI __noinline__
+#endif
+
 namespace grove {
 // ------------------------------------------------------------------------------------------------
 // K3: gang admission.
@@ -99,9 +105,9 @@ struct PieceIt {
 
 __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_t gpu, uint32_t pods, const uint4& q) {
   uint32_t c = pods;
-  if (q.x) c = min(c, cpu / q.x);
-  if (q.y) c = min(c, mem / q.y);
-  if (q.z) c = min(c, gpu / q.z);
+  if (q.x) c = min(c, div_small(cpu, q.x));
+  if (q.y) c = min(c, div_small(mem, q.y));
+  if (q.z) c = min(c, div_small(gpu, q.z));
   return c;
 }
 
@@ -125,10 +131,12 @@ __device__ __forceinline__ uint32_t visit_pos(const GangRegs& g, uint32_t n) {
 template <bool kPref_>
 struct Ev {
   static constexpr bool kPref = kPref_;
+  static constexpr bool kStaged = false;
   const Topo& tp; const Relax& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
   uint32_t np;
   uint32_t tmask = 0;   // bit (n & 31) set for every node the gang has put a pod on: quick 'untouched' test
   uint32_t ext = 0;     // see the file comment
+  uint32_t t_stage = 0, t_pre = 0, t_pack = 0, n_stage = 0;
   __device__ Ev(const Topo& t, const Relax& r, GangShared& s, const GangRegs& gr, uint32_t ln)
       : tp(t), rb(r), sh(s), g(gr), lane(ln), np(0) {}
 
@@ -172,9 +180,11 @@ struct Ev {
   }
 
   __device__ __forceinline__ void note_read(uint32_t last) { ext = max(ext, visit_pos(g, last) + 1u); }
+  __device__ __forceinline__ void begin(uint32_t, uint32_t) { np = 0; tmask = 0; }       // a fresh attempt
+  __device__ __forceinline__ void rollback(uint32_t mark) { np = mark; }               // drop the pods placed after mark
 
   // up to `want` pods of clique cr on fit nodes of [lo,hi) in score order; returns pods placed
-  __device__ uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+  __device__ GROVE_NI uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
     if (want == 0 || hi <= lo) return 0;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     PieceIt pit; pit.init(g, lo, hi, g.L);
@@ -211,7 +221,7 @@ struct Ev {
   __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t mark = np;
-    if (take(cr, lo, hi, m) < m) { np = mark; return false; }
+    if (take(cr, lo, hi, m) < m) { rollback(mark); return false; }
     if (lane == 0) { sh.Hlo[cr] = lo; sh.Hhi[cr] = hi; }
     __syncwarp();
     return true;
@@ -219,7 +229,7 @@ struct Ev {
 
   // clique whose own Required level is a unit level (one node per domain, e.g. hostname):
   // first node of [lo,hi) in score order that takes all m pods
-  __device__ bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+  __device__ GROVE_NI bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
     const uint32_t m = sh.clq[cr].w & 0xFFu;
     const uint32_t* Frow = rb.F + size_t(sh.sig[cr]) * tp.words;
     PieceIt pit; pit.init(g, lo, hi, g.L);
@@ -248,6 +258,158 @@ struct Ev {
       }
     }
     if (last != GROVE_NONE_U32) note_read(last);
+    return false;
+  }
+};
+
+
+// ---- staged evaluator: the candidate range lives in shared memory -------------------------------------------
+// For a candidate of at most kStageMax nodes (a rack, a block) the warp first computes the gang's VIEW of every node
+// of the range -- committed state minus the claims of lower ranks -- into shared memory (two rounds of independent
+// loads), then packs from there: capacities are divisions on the staged record, pods the gang places are subtracted
+// from it in place (no entry-stack scans), a failed scope adds them back.  An attempt costs a few thousand cycles
+// instead of a chain of dependent L2 look-ups per 32 nodes.
+constexpr uint32_t kStageMax = 128;
+
+template <bool kPref_>
+struct EvS {
+  static constexpr bool kPref = kPref_;
+  static constexpr bool kStaged = true;   // node state in shared memory: an attempt costs less than the table look-ups that would skip it
+  const Topo& tp; const Relax& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
+  uint4* view;          // [kStageMax] cpu, mem, gpu | pods << 16, node flags | vdepth << 16
+  uint32_t t_stage = 0, t_pre = 0, t_pack = 0, n_stage = 0;   // GROVE_DEBUG_ADMIT: cycles staging / pre-filtering sub-domains / packing
+  uint32_t vlo = 0, vhi = 0;
+  uint32_t np;
+  uint32_t tmask = 0;
+  uint32_t ext = 0;
+  __device__ EvS(const Topo& t, const Relax& r, GangShared& s, const GangRegs& gr, uint32_t ln, uint4* v)
+      : tp(t), rb(r), sh(s), g(gr), lane(ln), view(v), np(0) {}
+
+  __device__ GROVE_NI void begin(uint32_t dl, uint32_t dh) {
+    np = 0; vlo = dl; vhi = dh;
+    const long long tb0 = rb.dbg ? clock64() : 0;
+    __syncwarp();
+    constexpr uint32_t kPer = kStageMax / 32;
+    // phase 1: node records and claim counters of the whole range, every load independent of the others
+    uint4 r[kPer]; uint32_t live[kPer];
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      const uint32_t n = dl + k * 32u + lane;
+      const bool in = n < dh;
+      r[k] = in ? __ldg(tp.nres + n) : make_uint4(0, 0, 0, 0);
+      live[k] = in ? (__ldg(rb.nlive + (n >> 2)) >> ((n & 3u) * 8u)) & 0xFFu : 0u;
+    }
+    // phase 2: the claim lines of the claimed nodes (again independent loads), then the rare overflow chains
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      const uint32_t n = dl + k * 32u + lane;
+      if (n >= dh) continue;
+      uint32_t cpu = r[k].x, mem = r[k].y, gpu = r[k].z & 0xFFFFu, pods = r[k].z >> 16;
+      if (live[k] & 0x3Fu) {
+        const uint4* line = rb.claims + size_t(n) * kClaimSlots;
+        uint4 c[kClaimSlots];
+#pragma unroll
+        for (uint32_t s = 0; s < kClaimSlots; ++s) c[s] = __ldg(line + s);
+#pragma unroll
+        for (uint32_t s = 0; s < kClaimSlots; ++s)
+          if (c[s].x < g.rank) { cpu -= min(cpu, c[s].y); mem -= min(mem, c[s].z); gpu -= min(gpu, c[s].w & 0xFFFFu); pods -= min(pods, c[s].w >> 16); }
+      }
+      if (live[k] & kHasOvf) {
+        for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
+          const uint4 c = __ldg(rb.ovf_claim + i - 1);
+          if (c.x < g.rank) { cpu -= min(cpu, c.y); mem -= min(mem, c.z); gpu -= min(gpu, c.w & 0xFFFFu); pods -= min(pods, c.w >> 16); }
+        }
+      }
+      view[k * 32u + lane] = make_uint4(cpu, mem, gpu | (pods << 16), r[k].w);
+    }
+    __syncwarp();
+    // the whole range has been read: it ends at the furthest position any of its nodes has in the visiting order
+    ext = max(ext, (g.a >= dl && g.a < dh) ? dh - dl : visit_pos(g, dh - 1u) + 1u);
+    if (rb.dbg) { t_stage += uint32_t(clock64() - tb0); ++n_stage; }
+  }
+
+  __device__ __forceinline__ uint32_t cap(uint32_t cr, uint32_t n) const {
+    const uint4 v = view[n - vlo];
+    const uint32_t sm = sh.smask[cr];
+    if (!(v.w & GROVE_NODE_SCHEDULABLE) || !((sm >> ((v.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) & 1u) || ((v.w >> 16) & 0xFu) < (sm >> 16)) return 0u;
+    return cap_from(v.x, v.y, v.z & 0xFFFFu, v.z >> 16, sh.clq[cr]);
+  }
+
+  // give back the pods placed after mark
+  __device__ GROVE_NI void rollback(uint32_t mark) {
+    __syncwarp();
+    for (uint32_t i = mark + lane; i < np; i += 32) {
+      const uint4 q = sh.clq[sh.ent_meta[i]];
+      uint32_t* v = reinterpret_cast<uint32_t*>(view + (sh.ent_node[i] - vlo));
+      if (q.x) atomicAdd(v + 0, q.x);
+      if (q.y) atomicAdd(v + 1, q.y);
+      atomicAdd(v + 2, q.z + (1u << 16));
+    }
+    np = mark;
+    __syncwarp();
+  }
+
+  __device__ GROVE_NI uint32_t take(uint32_t cr, uint32_t lo, uint32_t hi, uint32_t want) {
+    if (want == 0 || hi <= lo) return 0;
+    const uint4 q = sh.clq[cr];
+    PieceIt pit; pit.init(g, lo, hi, g.L);
+    uint32_t placed = 0;
+    for (uint32_t a, b; placed < want && pit.next(g, a, b);) {
+      for (uint32_t base = a & ~31u; base < b && placed < want; base += 32) {
+        const uint32_t n = base + lane;
+        const uint32_t c = (n >= a && n < b) ? cap(cr, n) : 0u;
+        const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
+        const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
+        const uint32_t tincl = warp_incl_scan(t, lane);
+        if (t) {
+          const uint32_t pos = np + tincl - t;
+          for (uint32_t j = 0; j < t; ++j) { sh.ent_node[pos + j] = n; sh.ent_meta[pos + j] = uint16_t(cr); }
+          uint4 v = view[n - vlo];
+          v.x -= t * q.x; v.y -= t * q.y; v.z -= t * q.z + (t << 16);
+          view[n - vlo] = v;
+        }
+        const uint32_t tot = __shfl_sync(kFull, tincl, 31);
+        np += tot; placed += tot;
+        __syncwarp();
+      }
+    }
+    return placed;
+  }
+
+  __device__ bool fill_min(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint32_t mark = np;
+    if (take(cr, lo, hi, m) < m) { rollback(mark); return false; }
+    if (lane == 0) { sh.Hlo[cr] = lo; sh.Hhi[cr] = hi; }
+    __syncwarp();
+    return true;
+  }
+
+  __device__ GROVE_NI bool find_unit(uint32_t cr, uint32_t lo, uint32_t hi) {
+    const uint32_t m = sh.clq[cr].w & 0xFFu;
+    const uint4 q = sh.clq[cr];
+    PieceIt pit; pit.init(g, lo, hi, g.L);
+    for (uint32_t a, b; pit.next(g, a, b);) {
+      for (uint32_t base = a & ~31u; base < b; base += 32) {
+        const uint32_t n = base + lane;
+        const bool in = n >= a && n < b;
+        const uint32_t c = in ? cap(cr, n) : 0u;
+        const uint32_t okb = __ballot_sync(kFull, in && c >= m);
+        if (okb) {
+          const uint32_t nn = base + (__ffs(okb) - 1);
+          for (uint32_t j = lane; j < m; j += 32) { sh.ent_node[np + j] = nn; sh.ent_meta[np + j] = uint16_t(cr); }
+          if (lane == 0) {
+            sh.Hlo[cr] = nn; sh.Hhi[cr] = nn + 1;
+            uint4 v = view[nn - vlo];
+            v.x -= m * q.x; v.y -= m * q.y; v.z -= m * q.z + (m << 16);
+            view[nn - vlo] = v;
+          }
+          np += m;
+          __syncwarp();
+          return true;
+        }
+      }
+    }
     return false;
   }
 };
@@ -320,7 +482,7 @@ __device__ __forceinline__ int level_span(uint32_t req, uint32_t pref, int lvl, 
 }
 
 template <class Ev>
-__device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
+__device__ GROVE_NI bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
   const uint32_t mark = ev.np;
   for (uint32_t i = 0; i < s.n_cliques; ++i) {
@@ -350,15 +512,15 @@ __device__ __forceinline__ bool place_scope(Ev& ev, const grove_scope_t& s, uint
       }
       if (ok && ev.lane == 0) ev.sh.c_got[cr] = int8_t(ql);
     } while (Ev::kPref && !ok && --ql >= base);
-    if (!ok) { ev.np = mark; return false; }
+    if (!ok) { ev.rollback(mark); return false; }
   }
   return true;
 }
 
 template <class Ev>
-__device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
+__device__ GROVE_NI bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
-  ev.np = 0; ev.tmask = 0;
+  ev.begin(lo, hi);
   for (uint32_t si = 0; si < n_scopes; ++si) {
     const grove_scope_t s = ev.sh.scopes[si];
     bool ok = false;
@@ -376,17 +538,20 @@ __device__ __forceinline__ bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo,
             const uint32_t d = db + ev.lane;
             uint32_t el = 0, eh = 0;
             bool plaus = false;
+            const long long tp0 = ev.rb.dbg ? clock64() : 0;
             if (d < d1) {
               el = __ldg(tp.dom_lo[sl] + d); eh = __ldg(tp.dom_hi[sl] + d);
               plaus = scope_plausible(tp, ev.rb, ev.sh, s, el, eh, sl, d);
             }
             uint32_t todo = __ballot_sync(kFull, plaus);
+            const long long tp1 = ev.rb.dbg ? clock64() : 0;
             while (todo && !ok) {
               const uint32_t src = __ffs(todo) - 1; todo &= todo - 1;
               const uint32_t l0 = __shfl_sync(kFull, el, src), h0 = __shfl_sync(kFull, eh, src);
               ok = place_scope(ev, s, l0, h0, sl);
               if (ok && ev.lane == 0) ev.sh.s_lo[si] = l0;
             }
+            if (ev.rb.dbg) { ev.t_pre += uint32_t(tp1 - tp0); ev.t_pack += uint32_t(clock64() - tp1); }
           }
         }
       } else {
@@ -409,20 +574,56 @@ __device__ __forceinline__ void score_unit(uint32_t req, uint32_t pref, int got,
   num += uint32_t(min(got, want) + 1);
 }
 
-constexpr int kEvalWarps = 4;   // gangs per CTA of k_eval (a warp each)
+// The candidate pre-filter per (gang shape, domain): one thread per domain of one level, the shape's representative gang
+// staged in shared memory.  Runs after every capacity-table build; k_eval then reads one bit per candidate.
+__global__ void __launch_bounds__(128) k_shape_plaus(Topo tp, Tables tb, Relax rx, const uint32_t* __restrict__ shape_rep) {
+  __shared__ GangShared sh;
+  const uint32_t shape = blockIdx.y, l = blockIdx.z;
+  const uint32_t gi = shape_rep[shape];
+  const grove_gang_t gg = tb.gangs[gi];
+  // candidate levels of the shape: Preferred (if any) down to Required; the whole cluster needs no table
+  int first;
+  const int base = level_span<true>(gg.level, gg.preferred, -1, first);
+  if (int(l) > first || int(l) < base || l >= tp.L) return;
+  for (uint32_t c = threadIdx.x; c < gg.n_cliques; c += blockDim.x) {
+    const grove_clique_t q = tb.cliques[gg.clique_off + c];
+    sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
+                           uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16) |
+                               (GROVE_CLIQUE_PREFERRED(q.scope) << 24));
+    sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
+  }
+  for (uint32_t si = threadIdx.x; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
+  __syncthreads();
+  const uint32_t d = blockIdx.x * 128 + threadIdx.x;
+  bool plaus = false;
+  if (d < tp.n_dom[l]) plaus = gang_plausible(tp, rx, sh, gg.n_scopes, __ldg(tp.dom_lo[l] + d), __ldg(tp.dom_hi[l] + d), int(l), d);
+  const uint32_t b = __ballot_sync(kFull, plaus);
+  if ((threadIdx.x & 31) == 0 && (d & ~31u) < ((tp.n_dom[l] + 31u) & ~31u))
+    const_cast<uint32_t*>(rx.shape_bits)[size_t(shape) * rx.pl_words + ((rx.pl_off[l] + d) >> 5)] = b;
+}
 
-// One evaluation per warp, grid-stride over the round's eval_list.  Writes the "nxt" scratch of the gang.
-template <bool kPref>
-__global__ void __launch_bounds__(kEvalWarps * 32) k_eval(Topo tp, Tables tb, Relax rx) {
-  __shared__ GangShared shs[kEvalWarps];
+// K3 launch forms: kW warps share ONE gang.  The candidates of the gang's level are pre-filtered 1024 at a time by all
+// warps (a lane each); the plausible ones are then attempted kW at a time, a warp each, and the lowest successful
+// candidate IN ORDER is the answer -- exactly what trying them one after the other gives, minus the waiting.  kW = 1
+// while a round has many gangs (what matters is gangs in flight), 4 / 8 when it has few (what matters is the
+// latency of the slowest gang: a round lasts as long as its slowest evaluation).
+// A launch only acts if lo_cnt <= gangs of the round < hi_cnt, so the host can enqueue every form without
+// knowing the count.  Writes the "nxt" scratch of the gang.
+template <bool kPref, int kW>
+__global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, uint32_t lo_cnt, uint32_t hi_cnt) {
+  __shared__ GangShared shs[kW];
+  __shared__ uint4 s_view[kW][kStageMax];
+  __shared__ uint32_t s_plaus[32];   // plausible candidates of the current 1024-candidate chunk, in order
+  __shared__ uint32_t s_win, s_ext, s_att, s_npl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_eval = rx.ctl[kNEval], front = rx.ctl[kFront];
+  if (rx.ctl[kDone] || n_eval < lo_cnt || n_eval >= hi_cnt) return;
   GangShared& sh = shs[warp];
-  for (uint32_t ei = blockIdx.x * kEvalWarps + warp; ei < n_eval; ei += gridDim.x * kEvalWarps) {
+  for (uint32_t ei = blockIdx.x; ei < n_eval; ei += gridDim.x) {
     const uint32_t gi = rx.eval_list[ei];
     const grove_gang_t gg = tb.gangs[gi];
     const GangInfo info = tb.ginfo[gi];
-    __syncwarp();
+    __syncthreads();   // the previous gang's shared state is no longer read
     // ---- gangs that need no packing
     uint32_t trivial = 0;
     if (gg.flags & GROVE_GANG_GATED) trivial = GROVE_GANG_GATED_SKIP;
@@ -435,17 +636,17 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval(Topo tp, Tables tb, Re
       if (bs != GROVE_GANG_ADMITTED) trivial = GROVE_GANG_BASE_REJECTED;
     }
     if (trivial) {
-      if (lane == 0) {
+      if (threadIdx.x == 0) {
         rx.nxt_tstate[gi] = uint8_t(trivial); rx.nxt_n[gi] = 0; rx.nxt_info[gi] = 0xFFu; rx.nxt_glo[gi] = GROVE_NONE_U32; rx.nxt_extent[gi] = 0;
       }
-      for (uint32_t si = lane; si < gg.n_scopes; si += 32) { rx.nxt_sc_lvl[gg.scope_off + si] = 0xFFu; rx.nxt_sc_lo[gg.scope_off + si] = GROVE_NONE_U32; }
+      for (uint32_t si = threadIdx.x; si < gg.n_scopes; si += kW * 32) { rx.nxt_sc_lvl[gg.scope_off + si] = 0xFFu; rx.nxt_sc_lo[gg.scope_off + si] = GROVE_NONE_U32; }
       continue;
     }
     GangRegs g;
     g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.rank = info.order;
 #pragma unroll
     for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-    for (uint32_t c = lane; c < gg.n_cliques; c += 32) {
+    for (uint32_t c = lane; c < gg.n_cliques; c += 32) {   // every warp keeps its own copy: attempts run independently
       const grove_clique_t q = tb.cliques[gg.clique_off + c];
       const CliqueInfo ci = tb.cinfo[gg.clique_off + c];
       sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
@@ -455,65 +656,128 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval(Topo tp, Tables tb, Re
       sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.c_got[c] = -1;
     }
     for (uint32_t si = lane; si < gg.n_scopes; si += 32) { sh.scopes[si] = tb.scopes[gg.scope_off + si]; sh.s_got[si] = -1; sh.s_lo[si] = 0; }
-    __syncwarp();
-    Ev<kPref> ev(tp, rx, sh, g, lane);
-    bool ok = false;
+    if (threadIdx.x == 0) { s_win = GROVE_NONE_U32; s_ext = 0; s_att = 0; s_npl = 0; }
+    __syncthreads();
+    Ev<kPref> ev(tp, rx, sh, g, lane);                         // candidates of any size, node state from L2
+    EvS<kPref> evs(tp, rx, sh, g, lane, s_view[warp]);         // candidates of <= kStageMax nodes, node state staged in shared memory
+    bool staged = false;  // the winning attempt ran on evs
+    bool won = false;     // this warp holds the answer
+    bool done = false;    // CTA-uniform
     int g_got = -1; uint32_t g_lo = 0;
+    const long long t0 = rx.dbg ? clock64() : 0;
     // candidate levels: the Preferred level first (if any), widened level by level up to the Required one
     // (gl == -1: the whole cluster as a single candidate)
     int gfirst;
     const int gbase = level_span<kPref>(gg.level, gg.preferred, -1, gfirst);
     int gl = gfirst;
-    uint32_t n_att = 0, n_plaus = 0;
     do {
       if (gl < 0) {
-        ok = place_in(ev, gg.n_scopes, 0, tp.n, -1);
-        ++n_att;
-        if (ok) { g_got = -1; g_lo = 0; }
+        staged = false;
+        if (warp == 0) {
+          won = place_in(ev, gg.n_scopes, 0, tp.n, -1);
+          if (won) { g_got = -1; g_lo = 0; if (lane == 0) s_win = 0; }
+          if (lane == 0) s_att += 1;
+        }
+        __syncthreads();
+        done = s_win != GROVE_NONE_U32;
       } else {
         // candidate domains of level gl in score order: up to kMaxPieces ranges of domain indices
-        uint32_t plo[kMaxPieces], phi[kMaxPieces];
-        const int npc = make_pieces(g, 0, tp.n, uint32_t(gl), plo, phi);
-        for (int p = 0; p < npc && !ok; ++p) {
-          const uint32_t d0 = __ldg(tp.next_dom[gl] + plo[p]), d1 = __ldg(tp.next_dom[gl] + phi[p]);
-          for (uint32_t db = d0; db < d1 && !ok; db += 32) {
-            const uint32_t d = db + lane;
-            uint32_t dl = 0, dh = 0;
-            bool plaus = false;
-            if (d < d1) {
-              dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
-              plaus = gang_plausible(tp, rx, sh, gg.n_scopes, dl, dh, gl, d);
-            }
-            uint32_t todo = __ballot_sync(kFull, plaus);
-            n_plaus += __popc(todo);
-            while (todo && !ok) {
-              const uint32_t src = __ffs(todo) - 1; todo &= todo - 1;
-              const uint32_t l0 = __shfl_sync(kFull, dl, src), h0 = __shfl_sync(kFull, dh, src);
-              ok = place_in(ev, gg.n_scopes, l0, h0, gl);
-              ++n_att;
-              if (ok) { g_got = gl; g_lo = l0; }
-            }
+        uint32_t r0[kMaxPieces], rcnt[kMaxPieces], D = 0;
+        {
+          uint32_t plo[kMaxPieces], phi[kMaxPieces];
+          const int npc = make_pieces(g, 0, tp.n, uint32_t(gl), plo, phi);
+          for (int p = 0; p < kMaxPieces; ++p) {
+            r0[p] = 0; rcnt[p] = 0;
+            if (p < npc) { r0[p] = __ldg(tp.next_dom[gl] + plo[p]); rcnt[p] = __ldg(tp.next_dom[gl] + phi[p]) - r0[p]; D += rcnt[p]; }
           }
         }
+        auto cand = [&](uint32_t k, uint32_t& dl, uint32_t& dh) -> uint32_t {   // k-th candidate in order -> its domain
+          uint32_t d = 0, rem = k;
+#pragma unroll
+          for (int p = 0; p < kMaxPieces; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
+          dl = __ldg(tp.dom_lo[gl] + d); dh = __ldg(tp.dom_hi[gl] + d);
+          return d;
+        };
+        // candidates are taken in chunks that grow (kW x 32, then up to 1024): most gangs succeed among the first few
+        for (uint32_t base = 0, nchunk = kW; base < D && !done; base += nchunk * 32, nchunk = min(32u, nchunk * 4u)) {
+          // pre-filter: nchunk runs of 32 candidates, dealt to the warps
+          for (uint32_t c = warp; c < 32; c += kW) {
+            if (c >= nchunk) { if (lane == 0) s_plaus[c] = 0; continue; }
+            const uint32_t k = base + c * 32 + lane;
+            bool plaus = false;
+            if (k < D) {
+              if (rx.shape_bits) {   // one bit per (shape, domain), refreshed with the capacity tables
+                uint32_t d = 0, rem = k;
+#pragma unroll
+                for (int p = 0; p < kMaxPieces; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
+                const uint32_t bit = rx.pl_off[gl] + d;
+                plaus = (__ldg(rx.shape_bits + size_t(info.pad) * rx.pl_words + (bit >> 5)) >> (bit & 31u)) & 1u;
+              } else {
+                uint32_t dl, dh; const uint32_t d = cand(k, dl, dh); plaus = gang_plausible(tp, rx, sh, gg.n_scopes, dl, dh, gl, d);
+              }
+            }
+            const uint32_t b = __ballot_sync(kFull, plaus);
+            if (lane == 0) s_plaus[c] = b;
+          }
+          __syncthreads();
+          uint32_t total = 0;
+#pragma unroll 4
+          for (uint32_t c = 0; c < 32; ++c) total += __popc(s_plaus[c]);
+          if (threadIdx.x == 0) s_npl += total;
+          // attempts: kW plausible candidates at a time, in order, a warp each
+          // while a round has many gangs the very first candidate is attempted by one warp alone: it usually succeeds,
+          // and the other warps' attempts would be thrown away
+          const bool solo = kW > 1 && base == 0 && n_eval >= 256;
+          for (uint32_t j0 = 0; j0 < total && !done; j0 += (solo && j0 == 0) ? 1u : uint32_t(kW)) {
+            const uint32_t j = j0 + warp;
+            bool ok = false; uint32_t dl = 0, dh = 0;
+            if (j < total && !(solo && j0 == 0 && warp != 0)) {
+              uint32_t rem = j, c = 0;   // the j-th set bit of the bitmap
+              for (; c < 32; ++c) { const uint32_t pc = __popc(s_plaus[c]); if (rem < pc) break; rem -= pc; }
+              uint32_t w = s_plaus[c];
+              for (uint32_t i = 0; i < rem; ++i) w &= w - 1;
+              const uint32_t k = base + c * 32 + (__ffs(w) - 1);
+              cand(k, dl, dh);
+              staged = dh - dl <= kStageMax;
+              ok = staged ? place_in(evs, gg.n_scopes, dl, dh, gl) : place_in(ev, gg.n_scopes, dl, dh, gl);
+              if (lane == 0) { atomicAdd(&s_att, 1u); if (ok) atomicMin(&s_win, j); }
+            }
+            __syncthreads();
+            const uint32_t win = s_win;
+            if (win != GROVE_NONE_U32) { done = true; won = ok && win == j; if (won) { g_got = gl; g_lo = dl; } }
+          }
+          __syncthreads();   // s_plaus is rewritten by the next chunk
+        }
       }
-    } while (kPref && !ok && --gl >= gbase);
-    if (rx.dbg && lane == 0) { rx.dbg[gi * 8 + 0] += 1; rx.dbg[gi * 8 + 1] += n_plaus; rx.dbg[gi * 8 + 2] += n_att; }
-
-    if (!ok) {
-      if (lane == 0) {
+    } while (kPref && !done && --gl >= gbase);
+    // what any of the attempts may have read (attempts past the winner only widen it)
+    if (lane == 0) atomicMax(&s_ext, max(ev.ext, evs.ext));
+    __syncthreads();
+    if (rx.dbg && threadIdx.x == 0) {
+      const uint32_t cyc = uint32_t(clock64() - t0);
+      rx.dbg[gi * 8 + 0] += 1; rx.dbg[gi * 8 + 1] += s_npl; rx.dbg[gi * 8 + 2] += s_att;
+      rx.dbg[gi * 8 + 3] = max(rx.dbg[gi * 8 + 3], cyc); rx.dbg[gi * 8 + 4] = cyc; rx.dbg[gi * 8 + 5] = s_att; rx.dbg[gi * 8 + 6] = s_npl; rx.dbg[gi * 8 + 7] = rx.ctl[kRound];
+      // warp 0's own phases, summed over the cycle: staging, sub-domain pre-filter, packing, attempts staged
+      atomicAdd(rx.dbg + tb.G * 8 + 0, evs.t_stage); atomicAdd(rx.dbg + tb.G * 8 + 1, evs.t_pre); atomicAdd(rx.dbg + tb.G * 8 + 2, evs.t_pack);
+      atomicAdd(rx.dbg + tb.G * 8 + 3, evs.n_stage); atomicAdd(rx.dbg + tb.G * 8 + 4, cyc); atomicAdd(rx.dbg + tb.G * 8 + 5, 1u);
+    }
+    if (!done) {
+      if (threadIdx.x == 0) {
         rx.nxt_tstate[gi] = GROVE_GANG_REJECTED; rx.nxt_n[gi] = 0; rx.nxt_info[gi] = 0xFFu; rx.nxt_glo[gi] = GROVE_NONE_U32;
-        rx.nxt_extent[gi] = ev.ext;
+        rx.nxt_extent[gi] = s_ext;
       }
-      for (uint32_t si = lane; si < gg.n_scopes; si += 32) { rx.nxt_sc_lvl[gg.scope_off + si] = 0xFFu; rx.nxt_sc_lo[gg.scope_off + si] = GROVE_NONE_U32; }
+      for (uint32_t si = threadIdx.x; si < gg.n_scopes; si += kW * 32) { rx.nxt_sc_lvl[gg.scope_off + si] = 0xFFu; rx.nxt_sc_lo[gg.scope_off + si] = GROVE_NONE_U32; }
       continue;
     }
+    if (!won) continue;   // warp-uniform: the winner finishes alone
     // surplus beyond MinReplicas (best effort, podgang.go:80-83), inside the domain each clique was packed into
     for (uint32_t cr = 0; cr < gg.n_cliques; ++cr) {
       const uint32_t w = sh.clq[cr].w;
       const uint32_t mn = w & 0xFFu, rp = (w >> 8) & 0xFFu;
-      if (rp > mn) ev.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn);
+      if (rp > mn) { if (staged) evs.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn); else ev.take(cr, sh.Hlo[cr], sh.Hhi[cr], rp - mn); }
     }
     __syncwarp();
+    const uint32_t n_ent = staged ? evs.np : ev.np;
     // PlacementScore: levels honoured / levels asked for, over the gang, its scopes and its cliques
     uint32_t num = 0, den = 0;
     if (lane == 0) score_unit(gg.level, gg.preferred, g_got, num, den);
@@ -528,7 +792,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval(Topo tp, Tables tb, Re
 #pragma unroll
     for (int o = 16; o; o >>= 1) { num += __shfl_xor_sync(kFull, num, o); den += __shfl_xor_sync(kFull, den, o); }
     if (den == 0) { num = 1; den = 1; }
-    for (uint32_t i = lane; i < ev.np; i += 32) {
+    for (uint32_t i = lane; i < n_ent; i += 32) {
       rx.nxt_node[info.pod_off + i] = sh.ent_node[i];
       rx.nxt_meta[info.pod_off + i] = sh.ent_meta[i];
     }
@@ -538,10 +802,10 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval(Topo tp, Tables tb, Re
       rx.nxt_sc_lo[gg.scope_off + si] = own ? sh.s_lo[si] : GROVE_NONE_U32;
     }
     if (lane == 0) {
-      rx.nxt_tstate[gi] = GROVE_GANG_ADMITTED; rx.nxt_n[gi] = uint16_t(ev.np);
+      rx.nxt_tstate[gi] = GROVE_GANG_ADMITTED; rx.nxt_n[gi] = uint16_t(n_ent);
       rx.nxt_info[gi] = (g_got >= 0 ? uint32_t(g_got) : 0xFFu) | (num << 8) | (den << 20);
       rx.nxt_glo[gi] = g_got >= 0 ? g_lo : GROVE_NONE_U32;
-      rx.nxt_extent[gi] = ev.ext;
+      rx.nxt_extent[gi] = max(max(ev.ext, evs.ext), s_ext);   // the surplus pass above may have read further
     }
   }
 }

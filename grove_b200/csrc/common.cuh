@@ -20,7 +20,7 @@ struct GangInfo {     // 48 B, built on the host at submit time
   uint32_t anchor;    // sorted node index
   uint32_t order;     // rank by (priority desc, index asc)
   uint32_t pod_off;   // first slot in the entry arrays
-  uint32_t pad;
+  uint32_t pad;       // gang shape id (gangs with identical structure share one candidate pre-filter row)
   uint32_t anc_lo[GROVE_MAX_LEVELS];  // node range of the anchor's domain per level; [a,a) if label absent
   uint32_t anc_hi[GROVE_MAX_LEVELS];
 };
@@ -119,6 +119,8 @@ struct Relax {
   uint32_t* capsum;         // [S][cap_stride] per-domain sum of cap8 (non-unit levels)
   uint32_t* capmax;         // [S][cap_stride] per-domain max of cap8
   uint8_t* T;               // [Q][npad] K2 score matrix over the cycle-start snapshot
+  const uint32_t* shape_bits; // [shapes][pl_words] candidate pre-filter per (gang shape, domain), bit pl_off[level] + d; null = not built
+  uint32_t pl_off[GROVE_MAX_LEVELS], pl_words;
   uint32_t P, window, entry;
   uint32_t* dbg;            // [G][8] optional per-gang evaluation statistics
 };

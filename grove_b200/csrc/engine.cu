@@ -151,6 +151,10 @@ struct grove_engine {
   DevBuf<CliqueInfo> d_cinfo;
   DevBuf<uint4> d_sigs;
   DevBuf<uint32_t> d_by_rank;
+  std::vector<uint32_t> shape_rep;     // one representative gang per distinct gang shape
+  uint32_t n_shapes = 0, pl_words = 0, pl_off[GROVE_MAX_LEVELS]{};
+  bool shape_tables = false;
+  DevBuf<uint32_t> d_shape_rep, d_shape_bits;
 
   // ---- relaxation state (relax.cuh) ----
   DevBuf<uint32_t> d_ctl, d_chg_round, d_eval_list, d_ent_node, d_cur_info, d_cur_glo, d_extent, d_sc_lo;
@@ -170,8 +174,10 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   uint32_t tune_window = 0;        // gangs beyond the settled prefix that relax concurrently (0: all)
   uint32_t tune_entry = 1024;      // gangs that may join the window per round (0: no limit)
-  uint32_t tune_refresh = 512;     // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_refresh = 1024;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
+  uint32_t tune_warp4 = 4096, tune_warp16 = 600;   // rounds with fewer gangs than this evaluate them with 4 / 8 warps each
   bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
   bool tune_score = true;          // materialise the K2 score matrix every cycle
   PinBuf<uint32_t> h_upd_idx;
@@ -322,6 +328,8 @@ static Relax make_relax(grove_engine* e) {
   r.ovf_cap = uint32_t(std::min<size_t>(e->d_ovf_claim.cap, 0xFFFFFFF0u));
   r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p;
   r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
+  r.shape_bits = e->shape_tables ? e->d_shape_bits.p : nullptr; r.pl_words = e->pl_words;
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) r.pl_off[l] = e->pl_off[l];
   r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u); r.entry = e->tune_entry ? e->tune_entry : r.window;
   r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
@@ -353,6 +361,9 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_ENTRY")) e->tune_entry = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_REFRESH")) e->tune_refresh = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_BATCH")) e->tune_batch = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_WARP4")) e->tune_warp4 = uint32_t(std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_WARP16")) e->tune_warp16 = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("GROVE_TUNE_SCORE")) e->tune_score = std::atoi(v) != 0;
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
@@ -721,6 +732,74 @@ static int32_t build_ginfo(grove_engine* e) {
 #pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t qi = 0; qi < Q; ++qi)
     if (e->cinfo[qi].gang != GROVE_NONE_U32) { e->cinfo[qi].sig = remap[e->cinfo[qi].pad][e->cinfo[qi].sig]; e->cinfo[qi].pad = 0; }
+  // Gang SHAPES: what the candidate pre-filter of a gang depends on is its structure (levels, scopes, per-clique
+  // signature / MinReplicas / level), not its anchor or rank.  PodGangs stamped from one template share a shape, so the
+  // pre-filter is evaluated once per (shape, candidate domain) per capacity-table build (k_shape_plaus) instead of once
+  // per (gang evaluation, candidate).  Interned like the signatures: thread-local tables over gang ranges, merged.
+  {
+    auto shape_hash = [e](uint32_t gi) {
+      const grove_gang_t& g = e->gangs[gi];
+      uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t(g.n_cliques) << 32 | uint64_t(g.n_scopes) << 16 | uint64_t(g.level) << 8 | g.preferred);
+      auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+      for (uint32_t si = 0; si < g.n_scopes; ++si) { const grove_scope_t& s = e->scopes[g.scope_off + si]; mix(uint64_t(s.first_clique) | uint64_t(s.n_cliques) << 16 | uint64_t(s.level) << 32 | uint64_t(s.preferred1) << 40); }
+      for (uint32_t c = 0; c < g.n_cliques; ++c) { const grove_clique_t& q = e->cliques[g.clique_off + c]; mix(uint64_t(e->cinfo[g.clique_off + c].sig) | uint64_t(q.min_replicas) << 32 | uint64_t(q.level) << 40 | uint64_t(q.scope) << 48); }
+      return h;
+    };
+    auto shape_equal = [e](uint32_t a, uint32_t b) {
+      const grove_gang_t& x = e->gangs[a]; const grove_gang_t& y = e->gangs[b];
+      if (x.n_cliques != y.n_cliques || x.n_scopes != y.n_scopes || x.level != y.level || x.preferred != y.preferred) return false;
+      for (uint32_t si = 0; si < x.n_scopes; ++si) {
+        const grove_scope_t& s = e->scopes[x.scope_off + si]; const grove_scope_t& t = e->scopes[y.scope_off + si];
+        if (s.first_clique != t.first_clique || s.n_cliques != t.n_cliques || s.level != t.level || s.preferred1 != t.preferred1) return false;
+      }
+      for (uint32_t c = 0; c < x.n_cliques; ++c) {
+        const grove_clique_t& q = e->cliques[x.clique_off + c]; const grove_clique_t& r = e->cliques[y.clique_off + c];
+        if (e->cinfo[x.clique_off + c].sig != e->cinfo[y.clique_off + c].sig || q.min_replicas != r.min_replicas || q.level != r.level || q.scope != r.scope) return false;
+      }
+      return true;
+    };
+    struct ShapeTab {   // open addressing on the hash; value = representative gang
+      std::vector<std::pair<uint64_t, uint32_t>> tab = std::vector<std::pair<uint64_t, uint32_t>>(256, {0, GROVE_NONE_U32});
+      std::vector<uint32_t> reps;
+      size_t used = 0;
+    };
+    auto intern = [&](ShapeTab& st, uint32_t gi, uint64_t h) -> uint32_t {   // -> index into st.reps
+      if (st.used * 2 >= st.tab.size()) {
+        std::vector<std::pair<uint64_t, uint32_t>> nt(st.tab.size() * 4, {0, GROVE_NONE_U32});
+        for (const auto& r : st.tab) if (r.second != GROVE_NONE_U32) { size_t k = r.first & (nt.size() - 1); while (nt[k].second != GROVE_NONE_U32) k = (k + 1) & (nt.size() - 1); nt[k] = r; }
+        st.tab.swap(nt);
+      }
+      size_t k = h & (st.tab.size() - 1);
+      while (st.tab[k].second != GROVE_NONE_U32 && !(st.tab[k].first == h && shape_equal(st.reps[st.tab[k].second], gi))) k = (k + 1) & (st.tab.size() - 1);
+      if (st.tab[k].second == GROVE_NONE_U32) { st.tab[k] = {h, uint32_t(st.reps.size())}; st.reps.push_back(gi); st.used++; }
+      return st.tab[k].second;
+    };
+    std::vector<ShapeTab> lsh(T);
+    std::vector<uint32_t> lid(G);
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num();
+      const uint32_t g0 = uint32_t(uint64_t(G) * t / T), g1 = uint32_t(uint64_t(G) * (t + 1) / T);
+      for (uint32_t gi = g0; gi < g1; ++gi) lid[gi] = intern(lsh[t], gi, shape_hash(gi));
+    }
+    ShapeTab gsh;
+    std::vector<std::vector<uint32_t>> smap(T);
+    for (int t = 0; t < T; ++t) { smap[t].resize(lsh[t].reps.size()); for (size_t k = 0; k < lsh[t].reps.size(); ++k) smap[t][k] = intern(gsh, lsh[t].reps[k], shape_hash(lsh[t].reps[k])); }
+    e->shape_rep = gsh.reps;
+    e->n_shapes = uint32_t(gsh.reps.size());
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num();
+      const uint32_t g0 = uint32_t(uint64_t(G) * t / T), g1 = uint32_t(uint64_t(G) * (t + 1) / T);
+      for (uint32_t gi = g0; gi < g1; ++gi) e->ginfo[gi].pad = smap[t][lid[gi]];
+    }
+    // bit layout of one shape's row: every level's domains, each level padded to a word
+    uint32_t bits = 0;
+    for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) { e->pl_off[l] = bits; if (l < e->L) bits += (e->n_dom[l] + 31u) & ~31u; }
+    e->pl_words = bits / 32;
+    // worth it while the rows stay small next to the work they save; otherwise every evaluation runs the pre-filter itself
+    e->shape_tables = e->n_shapes && uint64_t(e->n_shapes) * e->pl_words * 4 <= (256ull << 20) && e->n_shapes <= G / 2 + 16;
+  }
   uint32_t pod_off = 0;
   e->max_gang_pods = 0;
   for (uint32_t gi = 0; gi < G; ++gi) { e->ginfo[gi].pod_off = pod_off; pod_off += gang_pods[gi]; e->max_gang_pods = std::max(e->max_gang_pods, gang_pods[gi]); }
@@ -739,6 +818,11 @@ static int32_t build_ginfo(grove_engine* e) {
   }
   if (Q) CU_TRY(e, cudaMemcpyAsync(e->d_cinfo.p, e->cinfo, sizeof(CliqueInfo) * Q, cudaMemcpyHostToDevice, e->stream));
   if (G) CU_TRY(e, cudaMemcpyAsync(e->d_by_rank.p, e->by_rank_pin.p, sizeof(uint32_t) * G, cudaMemcpyHostToDevice, e->stream));
+  if (e->shape_tables) {
+    CU_TRY(e, e->d_shape_rep.ensure(e->n_shapes)); CU_TRY(e, e->d_shape_bits.ensure(size_t(e->n_shapes) * e->pl_words));
+    CU_TRY(e, cudaMemcpyAsync(e->d_shape_rep.p, e->shape_rep.data(), sizeof(uint32_t) * e->n_shapes, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));   // shape_rep is a pageable vector
+  }
   e->ginfo_dirty = false;
   if (std::getenv("GROVE_DEBUG_HOST")) {
     const auto t_b2 = std::chrono::steady_clock::now();
@@ -752,12 +836,20 @@ static int32_t build_ginfo(grove_engine* e) {
 static int32_t build_cap_tables(grove_engine* e, const Topo& tp, const Tables& tb, const Relax& rx) {
   if (!e->n_sigs) return GROVE_OK;
   dim3 gfit(e->Npad / 1024, std::min<uint32_t>((e->n_sigs + kFitTile - 1) / kFitTile, 65535u));
-  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p);
-  k_cap8<<<dim3(e->Npad / 256, e->n_sigs), 256, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p);
-  if (e->cap_stride) k_capsum<<<dim3((e->cap_stride * 32 + 255) / 256, e->n_sigs), 256, 0, e->stream>>>(tp, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p);
+  if (e->cap_stride) {
+    const uint64_t warps = uint64_t(e->n_sigs) * e->cap_stride;
+    k_capsum<<<uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, e->n_sm * 8u))), 256, 0, e->stream>>>(tp, e->n_sigs, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+  }
   k_clear_stale<<<(e->Npad / 4 + 255) / 256, 256, 0, e->stream>>>(rx, e->Npad / 4);
+  if (e->shape_tables) {   // the candidate pre-filter of every gang shape over every domain of its candidate levels
+    uint32_t mx = 0;
+    for (uint32_t l = 0; l < e->L; ++l) mx = std::max(mx, e->n_dom[l]);
+    k_shape_plaus<<<dim3((mx + 127) / 128, e->n_shapes, e->L), 128, 0, e->stream>>>(tp, tb, rx, e->d_shape_rep.p);
+    e->launches += 1;
+  }
   CU_TRY(e, cudaGetLastError());
-  e->launches += 4;
+  e->launches += 3;
   return GROVE_OK;
 }
 
@@ -793,7 +885,7 @@ static int32_t cycle_begin(grove_engine* e) {
       return fail(e, GROVE_ERR_OOM, "fit / capacity / score matrices do not fit in device memory");
     }
   }
-  if (e->dbg_on) { CU_TRY(e, e->d_dbg.ensure(g1 * 8)); CU_TRY(e, cudaMemsetAsync(e->d_dbg.p, 0, g1 * 32, e->stream)); }
+  if (e->dbg_on) { CU_TRY(e, e->d_dbg.ensure(g1 * 8 + 8)); CU_TRY(e, cudaMemsetAsync(e->d_dbg.p, 0, g1 * 32 + 32, e->stream)); }
   cudaStream_t st = e->stream;
   CU_TRY(e, cudaMemsetAsync(e->d_state.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_tstate.p, 0, g1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_dirty.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_chg_round.p, 0, sizeof(uint32_t) * g1, st));
@@ -877,29 +969,61 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     }
     CU_TRY(e, cudaEventRecord(e->ev[2], e->stream));
     const uint32_t W = rx.window;
-    const uint32_t per_sm = e->tune_eval_ctas ? e->tune_eval_ctas : 8u;
-    const uint32_t eval_ctas = std::max(1u, std::min((W + kEvalWarps - 1) / kEvalWarps, e->n_sm * per_sm));
+    const uint32_t per_sm = e->tune_eval_ctas ? e->tune_eval_ctas : 16u;
+    const uint32_t eval_ctas = std::max(1u, std::min(W, e->n_sm * per_sm));
+    // rounds with many gangs: a warp per gang; fewer: 4 warps; few: 8 warps per gang (admit.cuh)
+    const uint32_t t4 = e->tune_warp4, t16 = std::min(e->tune_warp16, e->tune_warp4);
     const uint32_t warp_ctas = std::max(1u, std::min((W * 32 + 255) / 256, e->n_sm * 8u));
+    // Rounds are enqueued `batch` at a time without waiting: every kernel returns at once when the cycle is over, so the
+    // host only looks at the control words between batches (to rebuild the capacity tables when the settled prefix has
+    // moved on, and to know when to stop).  GROVE_DEBUG_ADMIT looks after every round.
+    const uint32_t batch = e->dbg_on ? 1u : std::max(1u, e->tune_batch);
+    uint32_t next_round = 1;   // number of the next round to be enqueued (rounds advance one by one until the cycle is over)
     for (;;) {
-      k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
-      if (e->any_preferred) k_eval<true><<<eval_ctas, kEvalWarps * 32, 0, e->stream>>>(tp, tb, rx);
-      else k_eval<false><<<eval_ctas, kEvalWarps * 32, 0, e->stream>>>(tp, tb, rx);
-      k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
-      k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
-      k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
+      for (uint32_t b = 0; b < batch; ++b, ++next_round) {
+        if (next_round > 1 && next_round % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
+          CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
+          CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
+        }
+        k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
+        if (e->any_preferred) {
+          k_eval<true, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
+          k_eval<true, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
+          k_eval<true, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+        } else {
+          k_eval<false, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
+          k_eval<false, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
+          k_eval<false, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+        }
+        k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
+        k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
+        k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
+        e->launches += 7;
+      }
       CU_TRY(e, cudaGetLastError());
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
       CU_TRY(e, cudaStreamSynchronize(e->stream));
-      e->launches += 5; ++rounds;
       const uint32_t* c = e->h_ctl.p;
-      if (e->dbg_on) std::fprintf(stderr, "round %u: front %u hi %u evals so far %u ovf %u\n", rounds, c[kFront], c[kHi], c[kEvals], c[kOvfCount]);
+      rounds = c[kRound] - 1;
+      if (e->dbg_on) {
+        std::fprintf(stderr, "round %u: front %u hi %u evals so far %u ovf %u\n", rounds, c[kFront], c[kHi], c[kEvals], c[kOvfCount]);
+        std::vector<uint32_t> h(size_t(G) * 8); std::vector<uint8_t> ts(G);
+        cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ts.data(), e->d_tstate.p, G, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> idx;
+        for (uint32_t g = 0; g < G; ++g) if (h[size_t(g) * 8 + 7] == rounds) idx.push_back(g);
+        std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return h[size_t(a) * 8 + 4] > h[size_t(b) * 8 + 4]; });
+        uint64_t cyc = 0; for (uint32_t g : idx) cyc += h[size_t(g) * 8 + 4];
+        std::fprintf(stderr, "  %zu packed evals, mean %.0f cyc, median %u; slowest:", idx.size(), idx.empty() ? 0.0 : double(cyc) / idx.size(), idx.empty() ? 0u : h[size_t(idx[idx.size() / 2]) * 8 + 4]);
+        for (size_t i = 0; i < std::min<size_t>(idx.size(), 6); ++i) {
+          const uint32_t g = idx[i]; const uint32_t* d = &h[size_t(g) * 8];
+          std::fprintf(stderr, " [g%u rank%u st%u scopes%u: %u cyc, %u plaus, %u att]", g, e->ginfo[g].order, unsigned(ts[g]), unsigned(e->gangs[g].n_scopes), d[4], d[6], d[5]);
+        }
+        std::fprintf(stderr, "\n");
+      }
       if (c[kDone]) break;
       if (c[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
       if (c[kRefresh]) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; }
-      if (c[kRound] % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
-        CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
-        CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
-      }
     }
     e->last.evaluations = e->h_ctl.p[kEvals];
   }
@@ -921,8 +1045,11 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
   e->last.rounds = rounds;
   e->last.pairs_evaluated = e->tune_score ? uint64_t(e->Q) * e->N : uint64_t(e->n_sigs) * e->N;
   if (e->dbg_on && G) {
-    std::vector<uint32_t> h(size_t(G) * 8);
+    std::vector<uint32_t> h(size_t(G) * 8 + 8);
     cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
+    { const uint32_t* w = &h[size_t(G) * 8];
+      std::fprintf(stderr, "warp 0 of every evaluation: %u evals, %.0f cyc each; %u staged attempts: staging %.0f cyc, sub-domain pre-filter %.0f, packing %.0f per attempt\n",
+                   w[5], w[5] ? double(w[4]) / w[5] : 0.0, w[3], w[3] ? double(w[0]) / w[3] : 0.0, w[3] ? double(w[1]) / w[3] : 0.0, w[3] ? double(w[2]) / w[3] : 0.0); }
     uint64_t ev = 0, pl = 0, at = 0, mx = 0;
     for (uint32_t g = 0; g < G; ++g) { ev += h[g * 8]; pl += h[g * 8 + 1]; at += h[g * 8 + 2]; mx = std::max<uint64_t>(mx, h[g * 8]); }
     std::fprintf(stderr, "cycle: %u rounds, %llu evaluations (max %llu per gang), plausible/eval %.1f, attempts/eval %.2f\n", rounds,

@@ -28,6 +28,7 @@ namespace grove {
 // ------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_select(Tables tb, Relax rx) {
+  if (rx.ctl[kDone]) return;   // the host enqueues rounds ahead of knowing that the cycle is over
   const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi];
   const uint32_t p = front + blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
@@ -53,20 +54,34 @@ __device__ __forceinline__ void nlive_add(uint32_t* nlive, uint32_t n, int delta
 // withdraw ONE claim slot of `rank` on node n (the caller owns exactly one per entry run)
 __device__ __forceinline__ void claim_remove(const Relax& rx, uint32_t n, uint32_t rank) {
   uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
-  for (uint32_t s = 0; s < kClaimSlots; ++s)
-    if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) { nlive_add(rx.nlive, n, -1); return; }
+  // look first (one cache line), then take: an atomic per slot would be a chain of L2 round trips
+  uint32_t own = 0;
+#pragma unroll
+  for (uint32_t s = 0; s < kClaimSlots; ++s) own |= uint32_t(__ldcg(line + 4 * s) == rank) << s;
+  for (; own; own &= own - 1) {
+    const uint32_t s = __ffs(own) - 1;
+    if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) { nlive_add(rx.nlive, n, -1); return; }   // (another lane of this gang may have taken it)
+  }
   for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1])
     if (atomicCAS(reinterpret_cast<uint32_t*>(rx.ovf_claim + i - 1), rank, kClaimEmpty) == rank) return;
 }
 
 __device__ __forceinline__ void claim_add(const Relax& rx, uint32_t n, uint32_t rank, uint32_t cpu, uint32_t mem, uint32_t gpw) {
   uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
-  for (uint32_t s = 0; s < kClaimSlots; ++s)
-    if (atomicCAS(line + 4 * s, kClaimEmpty, rank) == kClaimEmpty) {
-      line[4 * s + 1] = cpu; line[4 * s + 2] = mem; line[4 * s + 3] = gpw;
-      nlive_add(rx.nlive, n, +1);
-      return;
+  for (int pass = 0; pass < 3; ++pass) {   // look first, then take; somebody else may win the slot: look again
+    uint32_t freeb = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < kClaimSlots; ++s) freeb |= uint32_t(__ldcg(line + 4 * s) == kClaimEmpty) << s;
+    if (!freeb) break;
+    for (; freeb; freeb &= freeb - 1) {
+      const uint32_t s = __ffs(freeb) - 1;
+      if (atomicCAS(line + 4 * s, kClaimEmpty, rank) == kClaimEmpty) {
+        line[4 * s + 1] = cpu; line[4 * s + 2] = mem; line[4 * s + 3] = gpw;
+        nlive_add(rx.nlive, n, +1);
+        return;
+      }
     }
+  }
   // more than kClaimSlots gangs lean on this node: its overflow chain.  A dead entry of the chain is revived first;
   // otherwise a pool entry is pushed on the chain's head (entries never leave a chain during a cycle)
   for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1]) {
@@ -98,6 +113,7 @@ __device__ __forceinline__ uint32_t run_length(const uint32_t* node, const uint1
 // one warp per evaluated gang: publish a changed result
 __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
   const uint32_t lane = threadIdx.x & 31;
+  if (rx.ctl[kDone]) return;
   const uint32_t n_eval = rx.ctl[kNEval], round = rx.ctl[kRound];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < n_eval; ei += nw) {
@@ -149,6 +165,7 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
 // one warp per gang of the window: did its view change this round?
 __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx) {
   const uint32_t lane = threadIdx.x & 31;
+  if (rx.ctl[kDone]) return;
   const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi], round = rx.ctl[kRound];
   const uint32_t rem_any = rx.ctl[kRemAny];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -192,6 +209,7 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx) {
 __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres, uint32_t refresh_every) {
   __shared__ bool s_last;
   const uint32_t lane = threadIdx.x & 31;
+  if (rx.ctl[kDone]) return;   // uniform over the grid: set only by the last CTA of an earlier launch
   const uint32_t front = rx.ctl[kFront], nf = rx.ctl[kMinDirty];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   bool folded = false;

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" || exit 1
-mkdir -p gpurun_out
 export PYTHONPATH="$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
 cat > /tmp/c4run.py <<'PY'
 import numpy as np, time, os, sys
 from grove_b200 import synth
@@ -11,7 +11,7 @@ cfg = synth.config_c4()
 g, c, s = cfg["tables"]
 ref = None
 if os.environ.get("CHECK"):
-    t = time.time(); ref = O.run_cycle(cfg["nodes"], cfg["n_levels"], g, c, s, threads=16); print("oracle %.1fs" % (time.time() - t), ref["stats"]["gangs_admitted"], flush=True)
+    ref = O.run_cycle(cfg["nodes"], cfg["n_levels"], g, c, s, threads=16)
 with PlacementEngine(cfg["n_levels"]) as e:
     e.load_nodes(cfg["nodes"]); e.submit_gangs(g, c, s)
     for i in range(4):
@@ -23,9 +23,12 @@ with PlacementEngine(cfg["n_levels"]) as e:
 PY
 (
 CHECK=1 TAG=default timeout 300 python /tmp/c4run.py
-for E in 256 512 2048 4096 0; do TAG="entry=$E" GROVE_TUNE_ENTRY=$E timeout 120 python /tmp/c4run.py; done
-for W in 1024 2048 4096; do TAG="window=$W entry=512" GROVE_TUNE_WINDOW=$W GROVE_TUNE_ENTRY=512 timeout 120 python /tmp/c4run.py; done
-for R in 128 2048 100000; do TAG="refresh=$R" GROVE_TUNE_REFRESH=$R timeout 120 python /tmp/c4run.py; done
-TAG="noscore" GROVE_TUNE_SCORE=0 timeout 120 python /tmp/c4run.py
-GROVE_DEBUG_ADMIT=1 TAG=dbg timeout 120 python /tmp/c4run.py 2>&1 | tail -32
-) 2>&1 | tee gpurun_out/dev_sweep.log
+TAG="w4=0 (1 warp always)" GROVE_TUNE_WARP4=0 GROVE_TUNE_WARP16=0 timeout 120 python /tmp/c4run.py
+TAG="w4=100000 w16=0 (4 warps always)" GROVE_TUNE_WARP4=100000 GROVE_TUNE_WARP16=0 timeout 120 python /tmp/c4run.py
+TAG="8 warps always" GROVE_TUNE_WARP4=100000 GROVE_TUNE_WARP16=100000 timeout 120 python /tmp/c4run.py
+TAG="w16=1500" GROVE_TUNE_WARP16=1500 timeout 120 python /tmp/c4run.py
+TAG="entry=2048 w16=1500" GROVE_TUNE_ENTRY=2048 GROVE_TUNE_WARP16=1500 timeout 120 python /tmp/c4run.py
+TAG="entry=2048 8 warps" GROVE_TUNE_ENTRY=2048 GROVE_TUNE_WARP4=100000 GROVE_TUNE_WARP16=100000 timeout 120 python /tmp/c4run.py
+TAG="entry=512 8 warps" GROVE_TUNE_ENTRY=512 GROVE_TUNE_WARP4=100000 GROVE_TUNE_WARP16=100000 timeout 120 python /tmp/c4run.py
+) 2>&1 | tee gpurun_out/dev_sweep2.log
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_random_parity_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/dev_tests.log

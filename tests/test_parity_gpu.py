@@ -220,7 +220,7 @@ def test_tuning_knobs_never_change_a_result(built_lib, oracle, env):
         print("ok")
     ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, **env})
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+    assert r.returncode == 0 and "ok" in r.stdout, (env, r.stderr[-1500:])
 
 
 def test_edge_cases(built_lib, oracle):
