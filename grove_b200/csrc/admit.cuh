@@ -602,6 +602,12 @@ __global__ void __launch_bounds__(128) k_shape_plaus(Topo tp, Tables tb, Relax r
     const_cast<uint32_t*>(rx.shape_bits)[size_t(shape) * rx.pl_words + ((rx.pl_off[l] + d) >> 5)] = b;
 }
 
+// entry i of the round's evaluation list: the heavy gangs from the head, the light ones from the tail (relax.cuh k_select)
+__device__ __forceinline__ uint32_t eval_list_at(const Relax& rx, uint32_t G, uint32_t i) {
+  const uint32_t nh = rx.ctl[kNHeavy];
+  return i < nh ? rx.eval_list[i] : rx.eval_list[G - 1u - (i - nh)];
+}
+
 // K3 launch forms: kW warps share ONE gang.  The candidates of the gang's level are pre-filtered 1024 at a time by all
 // warps (a lane each); the plausible ones are then attempted kW at a time, a warp each, and the lowest successful
 // candidate IN ORDER is the answer -- exactly what trying them one after the other gives, minus the waiting.  kW = 1
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
   if (rx.ctl[kDone] || n_eval < lo_cnt || n_eval >= hi_cnt) return;
   GangShared& sh = shs[warp];
   for (uint32_t ei = blockIdx.x; ei < n_eval; ei += gridDim.x) {
-    const uint32_t gi = rx.eval_list[ei];
+    const uint32_t gi = eval_list_at(rx, tb.G, ei);
     const grove_gang_t gg = tb.gangs[gi];
     const GangInfo info = tb.ginfo[gi];
     __syncthreads();   // the previous gang's shared state is no longer read
@@ -753,6 +759,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     // what any of the attempts may have read (attempts past the winner only widen it)
     if (lane == 0) atomicMax(&s_ext, max(ev.ext, evs.ext));
     __syncthreads();
+    if (threadIdx.x == 0) rx.last_att[gi] = uint8_t(min(255u, (s_att + kW - 1) / kW));
     if (rx.dbg && threadIdx.x == 0) {
       const uint32_t cyc = uint32_t(clock64() - t0);
       rx.dbg[gi * 8 + 0] += 1; rx.dbg[gi * 8 + 1] += s_npl; rx.dbg[gi * 8 + 2] += s_att;

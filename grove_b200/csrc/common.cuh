@@ -72,6 +72,8 @@ enum Ctl : uint32_t {
   kRefresh,        // 1: rebuild the capacity tables before the next evaluation
   kCtaDone,        // last-CTA-done counter of k_settle
   kFoldAny,        // a settle pass folded claims into the committed state
+  kNHeavy,         // gangs at the head / tail of eval_list (k_select)
+  kNLight,
   kCtlWords = 16
 };
 
@@ -83,7 +85,8 @@ struct Relax {
   uint8_t* tstate;          // [G] tentative state of the last evaluation (0 = never evaluated)
   uint8_t* dirty;           // [G] must be re-evaluated next round
   uint32_t* chg_round;      // [G] last round in which the gang's tentative result changed
-  uint32_t* eval_list;      // [G]
+  uint32_t* eval_list;      // [G] heavy gangs from the head, light ones from the tail (k_select)
+  uint8_t* last_att;        // [G] attempt rounds the gang's last evaluation needed
   // tentative / final result per gang
   uint32_t* ent_node;       // [P]
   uint16_t* ent_meta;       // [P] clique_rel

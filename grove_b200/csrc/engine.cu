@@ -161,7 +161,7 @@ struct grove_engine {
   DevBuf<uint32_t> d_nxt_node, d_nxt_info, d_nxt_glo, d_nxt_extent, d_nxt_sc_lo;
   DevBuf<uint32_t> d_nlive, d_ovf_head, d_ovf_next, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
   DevBuf<uint16_t> d_ent_meta, d_cur_n, d_nxt_meta, d_nxt_n;
-  DevBuf<uint8_t> d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
+  DevBuf<uint8_t> d_last_att, d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
   DevBuf<uint4> d_claims, d_ovf_claim;
   DevBuf<grove_gang_status_t> d_status;
   DevBuf<grove_scope_status_t> d_scope_status;
@@ -174,12 +174,16 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   uint32_t tune_window = 0;        // gangs beyond the settled prefix that relax concurrently (0: all)
   uint32_t tune_entry = 1024;      // gangs that may join the window per round (0: no limit)
-  uint32_t tune_refresh = 1024;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_refresh = 2048;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_warp_ctas = 2;     // CTAs per SM of the warp-per-gang bookkeeping kernels (apply / detect / settle)
   uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
   uint32_t tune_warp4 = 4096, tune_warp16 = 600;   // rounds with fewer gangs than this evaluate them with 4 / 8 warps each
   bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
-  bool tune_score = true;          // materialise the K2 score matrix every cycle
+  bool tune_score = false;         // K2 score matrix: false = materialised on request (grove_build_score_matrix / the row getters),
+                                   // true = every cycle, on the second stream beside the relaxation
+  bool score_valid = false;        // d_T holds the matrix of the last cycle's start snapshot
+  DevBuf<uint32_t> d_F0;           // K1 output over the cycle-start snapshot (the engine's own F follows the committed state)
   PinBuf<uint32_t> h_upd_idx;
   PinBuf<grove_node_t> h_upd_recs;
   cudaEvent_t ev_upd = nullptr;
@@ -319,7 +323,7 @@ static Tables make_tables(grove_engine* e) {
 static Relax make_relax(grove_engine* e) {
   Relax r{};
   r.ctl = e->d_ctl.p; r.state = e->d_state.p; r.tstate = e->d_tstate.p; r.dirty = e->d_dirty.p; r.chg_round = e->d_chg_round.p;
-  r.eval_list = e->d_eval_list.p;
+  r.eval_list = e->d_eval_list.p; r.last_att = e->d_last_att.p;
   r.ent_node = e->d_ent_node.p; r.ent_meta = e->d_ent_meta.p; r.cur_n = e->d_cur_n.p; r.cur_info = e->d_cur_info.p; r.cur_glo = e->d_cur_glo.p;
   r.extent = e->d_extent.p; r.sc_lvl = e->d_sc_lvl.p; r.sc_lo = e->d_sc_lo.p;
   r.nxt_node = e->d_nxt_node.p; r.nxt_meta = e->d_nxt_meta.p; r.nxt_n = e->d_nxt_n.p; r.nxt_tstate = e->d_nxt_tstate.p;
@@ -361,6 +365,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_ENTRY")) e->tune_entry = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_REFRESH")) e->tune_refresh = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_WARP_CTAS")) e->tune_warp_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_BATCH")) e->tune_batch = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WARP4")) e->tune_warp4 = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WARP16")) e->tune_warp16 = uint32_t(std::max(0, std::atoi(v)));
@@ -839,7 +844,7 @@ static int32_t build_cap_tables(grove_engine* e, const Topo& tp, const Tables& t
   k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p);
   if (e->cap_stride) {
     const uint64_t warps = uint64_t(e->n_sigs) * e->cap_stride;
-    k_capsum<<<uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, e->n_sm * 8u))), 256, 0, e->stream>>>(tp, e->n_sigs, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+    k_capsum<<<uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, e->n_sm * 32u))), 256, 0, e->stream>>>(tp, e->n_sigs, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
   }
   k_clear_stale<<<(e->Npad / 4 + 255) / 256, 256, 0, e->stream>>>(rx, e->Npad / 4);
   if (e->shape_tables) {   // the candidate pre-filter of every gang shape over every domain of its candidate levels
@@ -863,7 +868,7 @@ static int32_t cycle_begin(grove_engine* e) {
   const size_t g1 = std::max<uint32_t>(G, 1), p1 = std::max<uint32_t>(P, 1), s1 = std::max<uint32_t>(S, 1);
   CU_TRY(e, e->d_ctl.ensure(kCtlWords));
   CU_TRY(e, e->d_state.ensure(g1)); CU_TRY(e, e->d_tstate.ensure(g1)); CU_TRY(e, e->d_dirty.ensure(g1)); CU_TRY(e, e->d_chg_round.ensure(g1));
-  CU_TRY(e, e->d_eval_list.ensure(g1));
+  CU_TRY(e, e->d_eval_list.ensure(g1)); CU_TRY(e, e->d_last_att.ensure(g1));
   CU_TRY(e, e->d_ent_node.ensure(p1)); CU_TRY(e, e->d_ent_meta.ensure(p1)); CU_TRY(e, e->d_cur_n.ensure(g1)); CU_TRY(e, e->d_cur_info.ensure(g1));
   CU_TRY(e, e->d_cur_glo.ensure(g1)); CU_TRY(e, e->d_extent.ensure(g1)); CU_TRY(e, e->d_sc_lvl.ensure(s1)); CU_TRY(e, e->d_sc_lo.ensure(s1));
   CU_TRY(e, e->d_nxt_node.ensure(p1)); CU_TRY(e, e->d_nxt_meta.ensure(p1)); CU_TRY(e, e->d_nxt_n.ensure(g1)); CU_TRY(e, e->d_nxt_tstate.ensure(g1));
@@ -888,7 +893,7 @@ static int32_t cycle_begin(grove_engine* e) {
   if (e->dbg_on) { CU_TRY(e, e->d_dbg.ensure(g1 * 8 + 8)); CU_TRY(e, cudaMemsetAsync(e->d_dbg.p, 0, g1 * 32 + 32, e->stream)); }
   cudaStream_t st = e->stream;
   CU_TRY(e, cudaMemsetAsync(e->d_state.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_tstate.p, 0, g1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_dirty.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_chg_round.p, 0, sizeof(uint32_t) * g1, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_dirty.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_last_att.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_chg_round.p, 0, sizeof(uint32_t) * g1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_cur_n.p, 0, sizeof(uint16_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_cur_info.p, 0, sizeof(uint32_t) * g1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_cur_glo.p, 0, sizeof(uint32_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_extent.p, 0, sizeof(uint32_t) * g1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_sc_lvl.p, 0xFF, s1, st)); CU_TRY(e, cudaMemsetAsync(e->d_sc_lo.p, 0xFF, sizeof(uint32_t) * s1, st));
@@ -958,11 +963,16 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     rc = build_cap_tables(e, tp, tb, rx);
     if (rc) return rc;
     CU_TRY(e, cudaEventRecord(e->ev[1], e->stream));
+    CU_TRY(e, e->d_F0.ensure(std::max<size_t>(size_t(e->n_sigs) * e->words, 1)));
+    CU_TRY(e, cudaMemcpyAsync(e->d_F0.p, e->d_F.p, sizeof(uint32_t) * size_t(e->n_sigs) * e->words, cudaMemcpyDeviceToDevice, e->stream));
+    e->score_valid = false;
     if (e->tune_score && e->Q) {
       cudaStream_t ss = e->tune_overlap ? e->stream_score : e->stream;
-      if (e->tune_overlap) { CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream)); CU_TRY(e, cudaStreamWaitEvent(e->stream_score, e->ev_fit, 0)); }
+      if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream));
+      if (e->tune_overlap) CU_TRY(e, cudaStreamWaitEvent(ss, e->ev_fit, 0));
       CU_TRY(e, cudaEventRecord(e->ev_s0, ss));
-      k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, ss>>>(tp, tb, e->d_F.p, e->d_T.p, e->Q);  // one CTA per row
+      k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, ss>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q);  // one CTA per row
+      e->score_valid = true;
       CU_TRY(e, cudaEventRecord(e->ev_s1, ss));
       if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_score, e->stream_score));
       e->launches += 1;
@@ -973,7 +983,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     const uint32_t eval_ctas = std::max(1u, std::min(W, e->n_sm * per_sm));
     // rounds with many gangs: a warp per gang; fewer: 4 warps; few: 8 warps per gang (admit.cuh)
     const uint32_t t4 = e->tune_warp4, t16 = std::min(e->tune_warp16, e->tune_warp4);
-    const uint32_t warp_ctas = std::max(1u, std::min((W * 32 + 255) / 256, e->n_sm * 8u));
+    const uint32_t warp_ctas = std::max(1u, std::min((W * 32 + 255) / 256, e->n_sm * e->tune_warp_ctas));
     // Rounds are enqueued `batch` at a time without waiting: every kernel returns at once when the cycle is over, so the
     // host only looks at the control words between batches (to rebuild the capacity tables when the settled prefix has
     // moved on, and to know when to stop).  GROVE_DEBUG_ADMIT looks after every round.
@@ -986,14 +996,15 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
           CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
         }
         k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
+        // (a form whose range of round sizes this submission cannot reach is not launched at all)
         if (e->any_preferred) {
-          k_eval<true, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
-          k_eval<true, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
-          k_eval<true, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+          if (G >= t4) k_eval<true, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
+          if (G >= t16 && t4 > t16) k_eval<true, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
+          if (t16) k_eval<true, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
         } else {
-          k_eval<false, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
-          k_eval<false, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
-          k_eval<false, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+          if (G >= t4) k_eval<false, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
+          if (G >= t16 && t4 > t16) k_eval<false, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
+          if (t16) k_eval<false, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
         }
         k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
         k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
@@ -1043,7 +1054,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
   cudaEventElapsedTime(&t, e->ev[3], e->ev[9]); e->last.ms_commit = t;
   cudaEventElapsedTime(&t, e->ev[8], e->ev[9]); e->last.ms_total = t;
   e->last.rounds = rounds;
-  e->last.pairs_evaluated = e->tune_score ? uint64_t(e->Q) * e->N : uint64_t(e->n_sigs) * e->N;
+  e->last.pairs_evaluated = uint64_t(e->tune_score ? e->Q : e->n_sigs) * e->N;   // K1 works per signature, K2 per clique
   if (e->dbg_on && G) {
     std::vector<uint32_t> h(size_t(G) * 8 + 8);
     cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
@@ -1091,6 +1102,30 @@ int32_t grove_get_scope_domains(grove_engine_t* e, grove_scope_status_t* out, ui
   return GROVE_OK;
 }
 
+// K2 over the snapshot the last cycle started from: T[q][n] = fit ? 1 + closeness(n, anchor of q's gang) : 0.  The admission
+// derives its visiting order from the anchor's ancestor ranges and never reads this matrix, so it is materialised on
+// request (a scheduler that wants per-node scores -- the Score extension point -- asks for it); GROVE_TUNE_SCORE=1 builds
+// it every cycle instead, on a second stream beside the relaxation.  *ms (nullable) = device time of the kernel.
+int32_t grove_build_score_matrix(grove_engine_t* e, float* ms) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results) return fail(e, GROVE_ERR_STATE, "no completed cycle");
+  if (ms) *ms = 0.f;
+  if (e->Q == 0) return GROVE_OK;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  if (e->score_valid && !ms) return GROVE_OK;
+  if (e->d_T.ensure(size_t(e->Q) * e->Npad) != cudaSuccess) { (void)cudaGetLastError(); return fail(e, GROVE_ERR_OOM, "score matrix does not fit in device memory"); }
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e);
+  CU_TRY(e, cudaEventRecord(e->ev_s0, e->stream));
+  k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, e->stream>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q);  // one CTA per row
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaEventRecord(e->ev_s1, e->stream));
+  CU_TRY(e, cudaEventSynchronize(e->ev_s1));
+  float t = 0; cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1);
+  e->last.ms_score = t; e->score_valid = true;
+  if (ms) *ms = t;
+  return GROVE_OK;
+}
+
 // ---- introspection for parity tests ----
 int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap) {
   if (!e || !sorted_to_caller) return GROVE_ERR_INVALID_ARG;
@@ -1106,7 +1141,7 @@ int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* wo
   if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
   const uint32_t w = (e->N + 31) / 32;
   if (cap_words < w) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
-  if (!e->tune_score) return fail(e, GROVE_ERR_STATE, "score matrix disabled (GROVE_TUNE_SCORE=0)");
+  { int32_t rc = grove_build_score_matrix(e, nullptr); if (rc) return rc; }
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   // the fit row of the cycle-start snapshot is the support of the score row
   std::vector<uint8_t> row(e->N);
@@ -1120,7 +1155,7 @@ int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* b
   if (!e || !bytes) return GROVE_ERR_INVALID_ARG;
   if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
   if (cap_bytes < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
-  if (!e->tune_score) return fail(e, GROVE_ERR_STATE, "score matrix disabled (GROVE_TUNE_SCORE=0)");
+  { int32_t rc = grove_build_score_matrix(e, nullptr); if (rc) return rc; }
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   CU_TRY(e, cudaMemcpy(bytes, e->d_T.p + size_t(clique) * e->Npad, e->N, cudaMemcpyDeviceToHost));
   return GROVE_OK;

@@ -130,7 +130,7 @@ PodGang BuildPodGang(const PodCliqueSet& pcs, const PodGangInfo& info) {
 
 // ---- GpuBackend ----------------------------------------------------------------------------------------
 GpuBackend::GpuBackend(int device, std::string classLabelKey) : device_(device), classKey_(std::move(classLabelKey)) {}
-GpuBackend::~GpuBackend() { if (engine_) grove_engine_destroy(engine_); }
+GpuBackend::~GpuBackend() { Stop(); if (engine_) grove_engine_destroy(engine_); }
 
 Err GpuBackend::Init() {
   if (levels_.empty()) return std::nullopt;  // the engine is created once the topology is known (SyncTopology)
@@ -147,11 +147,13 @@ Err GpuBackend::Init() {
 Err GpuBackend::SyncTopology(const std::vector<TopologyLevel>& levels) {
   if (levels.empty() || levels.size() > GROVE_MAX_LEVELS)
     return mkerr("ERR_SYNC_TOPOLOGY", "SyncTopology", "the engine supports 1.." + std::to_string(GROVE_MAX_LEVELS) + " topology levels");
+  std::lock_guard<std::mutex> l(mu_);
   levels_ = levels;  // ordered broadest -> narrowest, as desiredKAITopologyLevels hands them over (kai/topology.go:103-135)
   return std::nullopt;
 }
-Err GpuBackend::OnTopologyDelete() { levels_.clear(); return std::nullopt; }
+Err GpuBackend::OnTopologyDelete() { std::lock_guard<std::mutex> l(mu_); levels_.clear(); return std::nullopt; }
 std::pair<bool, std::string> GpuBackend::CheckTopologyDrift(const std::vector<TopologyLevel>& levels) const {
+  std::lock_guard<std::mutex> l(mu_);
   if (levels.size() != levels_.size()) return {false, "level count differs"};
   for (size_t i = 0; i < levels.size(); ++i)
     if (levels[i].Key != levels_[i].Key) return {false, "level " + std::to_string(i) + " key " + levels_[i].Key + " != " + levels[i].Key};
@@ -209,6 +211,7 @@ Err GpuBackend::ValidatePodCliqueSet(const PodCliqueSet& pcs) const {
 }
 
 Err GpuBackend::SyncPodGang(const PodGang& podGang) {
+  std::lock_guard<std::mutex> l(mu_);   // called concurrently by the PodGang reconcilers (podgang/register.go:34-36)
   pending_[podGang.Namespace + "/" + podGang.Name] = podGang;  // a copy: the cache-owned object is neither mutated nor retained
   return std::nullopt;
 }
@@ -253,12 +256,37 @@ Err CheckPodSchedulingGate(bool podHasGate, bool podListedInPodGang, const std::
 }
 
 Err GpuBackend::OnPodGangDelete(const PodGang& podGang) {
+  std::lock_guard<std::mutex> l(mu_);
   const std::string key = podGang.Namespace + "/" + podGang.Name;
   pending_.erase(key); bound_.erase(key);
   return std::nullopt;
 }
 
+std::string GpuBackend::WhyNotEncodable(const PodGang& pg) {
+  if (pg.Spec.PodGroups.empty()) return "spec.podgroups: a PodGang needs at least one PodGroup";
+  if (pg.Spec.PodGroups.size() > GROVE_MAX_GANG_CLIQUES) return "spec.podgroups: more than " + std::to_string(GROVE_MAX_GANG_CLIQUES) + " PodGroups";
+  if (pg.Spec.TopologyConstraintGroupConfigs.size() + 1 > GROVE_MAX_GANG_SCOPES) return "spec.topologyConstraintGroupConfigs: more than " + std::to_string(GROVE_MAX_GANG_SCOPES - 1) + " group configs";
+  size_t pods = 0;
+  for (const auto& p : pg.Spec.PodGroups) {
+    if (p.MinReplicas < 0 || p.MinReplicas > 255) return "spec.podgroups[" + p.Name + "].minReplicas: must be within 0..255";
+    if (p.PodReferences.size() > 255) return "spec.podgroups[" + p.Name + "].podReferences: more than 255 pods";
+    if (size_t(p.MinReplicas) > p.PodReferences.size()) return "spec.podgroups[" + p.Name + "].minReplicas: exceeds the pods referenced";
+    pods += p.PodReferences.size();
+  }
+  if (pods > GROVE_MAX_GANG_PODS) return "spec.podgroups: more than " + std::to_string(GROVE_MAX_GANG_PODS) + " pods in one PodGang";
+  for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs)
+    for (const auto& n : gc.PodGroupNames)
+      if (std::none_of(pg.Spec.PodGroups.begin(), pg.Spec.PodGroups.end(), [&n](const PodGroup& p) { return p.Name == n; }))
+        return "spec.topologyConstraintGroupConfigs[" + gc.Name + "].podGroupNames: unknown PodGroup " + n;
+  return "";
+}
+
 Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
+  std::lock_guard<std::mutex> l(mu_);
+  return EncodeLocked(nodes, out);
+}
+
+Err GpuBackend::EncodeLocked(const std::vector<Node>& nodes, Tables* out) const {
   *out = Tables{};
   if (levels_.empty()) return mkerr("ERR_SYNC_PODGANG", "Encode", "no ClusterTopology levels synced");
   const uint32_t L = uint32_t(levels_.size());
@@ -296,9 +324,11 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
   auto levelOf = [this](const std::optional<TopologyConstraint>& tc, uint8_t* lvl, uint8_t* pref) -> Err {
     *lvl = GROVE_LEVEL_NONE; *pref = GROVE_LEVEL_NONE;
     if (!tc || !tc->PackConstraint) return std::nullopt;
-    auto find = [this](const std::string& key, const char* what, uint8_t* o) -> Err {
+    // a key that is no (longer a) level of the synced ClusterTopology is dropped, not an error: the operator does the same
+    // for a pack domain it cannot find (createTopologyPackConstraint, syncflow.go:349-371, logs and returns nil)
+    auto find = [this](const std::string& key, const char*, uint8_t* o) -> Err {
       for (size_t l = 0; l < levels_.size(); ++l) if (levels_[l].Key == key) { *o = uint8_t(l); return std::nullopt; }
-      return mkerr("ERR_SYNC_PODGANG", "Encode", std::string(what) + " topology key " + key + " is not a level of the synced ClusterTopology");
+      return std::nullopt;
     };
     if (tc->PackConstraint->Required) if (auto e = find(*tc->PackConstraint->Required, "Required", lvl)) return e;
     if (tc->PackConstraint->Preferred) if (auto e = find(*tc->PackConstraint->Preferred, "Preferred", pref)) return e;
@@ -321,10 +351,17 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
   // only, and its surplus as a remainder row gated behind it (base_gang) -- minimums of every gang before anybody's
   // surplus, which is what the suites' step descriptions say happens (GS8 :583, GS10 :779, GS12 :1023).
   auto hasSurplus = [](const PodGang& pg) { for (const auto& p : pg.Spec.PodGroups) if (int64_t(p.PodReferences.size()) > p.MinReplicas) return true; return false; };
+  // PodGangs the packed tables cannot hold are left out of the pass (and so is a scaled PodGang behind one); everybody else
+  // is scheduled as usual
+  for (const auto& kv : pending_) { const std::string why = WhyNotEncodable(kv.second); if (!why.empty()) out->skipped[kv.first] = why; }
+  for (const auto& kv : pending_)
+    if (!out->skipped.count(kv.first) && !kv.second.BasePodGangName.empty() && out->skipped.count(kv.second.Namespace + "/" + kv.second.BasePodGangName))
+      out->skipped[kv.first] = "base PodGang " + kv.second.BasePodGangName + " cannot be scheduled: " + out->skipped[kv.second.Namespace + "/" + kv.second.BasePodGangName];
   std::vector<const std::string*> order;
-  for (const auto& kv : pending_) if (!bound_.count(kv.first)) order.push_back(&kv.first);
+  for (const auto& kv : pending_) if (!bound_.count(kv.first) && !out->skipped.count(kv.first)) order.push_back(&kv.first);
   const size_t nFull = order.size();
   for (const auto& kv : pending_) {
+    if (out->skipped.count(kv.first)) continue;
     const bool scheduled = bound_.count(kv.first) != 0;
     if (!constrained(kv.second) && (scheduled || hasSurplus(kv.second))) order.push_back(&kv.first);
   }
@@ -425,12 +462,21 @@ Err GpuBackend::Encode(const std::vector<Node>& nodes, Tables* out) const {
 
 Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* bindings, std::map<std::string, PodGangStatus>* statuses,
                          grove_cycle_stats_t* stats) {
+  std::lock_guard<std::mutex> cycle(cycleMu_);   // the engine handle is not thread-safe: one cycle at a time
   bindings->clear(); statuses->clear();
-  if (pending_.empty()) return std::nullopt;
-  if (auto e = Init()) return e;
-  if (!engine_) return mkerr("ERR_SYNC_PODGANG", "RunCycle", "no ClusterTopology synced");
+  if (stats) *stats = grove_cycle_stats_t{};
   Tables t;
-  if (auto e = Encode(nodes, &t)) return e;
+  std::map<std::string, PodGang> snap;            // the PodGangs of this pass: reconcilers may add / delete others meanwhile
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    if (pending_.empty()) return std::nullopt;
+    if (auto e = Init()) return e;
+    if (!engine_) return mkerr("ERR_SYNC_PODGANG", "RunCycle", "no ClusterTopology synced");
+    if (auto e = EncodeLocked(nodes, &t)) return e;
+    snap = pending_;
+  }
+  for (const auto& kv : t.skipped) { PodGangStatus s; s.ScheduledReason = "Unschedulable"; s.ScheduledMessage = kv.second; (*statuses)[kv.first] = s; }
+  if (t.gangs.empty()) return std::nullopt;
   auto chk = [this](int32_t rc, const char* what) -> Err {
     if (rc == GROVE_OK) return std::nullopt;
     return mkerr("ERR_SYNC_PODGANG", what, std::string(grove_last_error(engine_)) + " (" + std::to_string(rc) + ")");
@@ -449,7 +495,7 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
   std::vector<uint32_t> seen(t.cliques.size(), 0);  // the r-th entry of a clique binds its r-th PodReference
   for (uint32_t i = 0; i < n; ++i) {
     const auto [grow, pgi] = t.cliqueOf[pl[i].clique];
-    const PodGang& pg = pending_.at(t.gangNames[grow]);
+    const PodGang& pg = snap.at(t.gangNames[grow]);
     const PodGroup& grp = pg.Spec.PodGroups[pgi];
     const NamespacedName& pod = grp.PodReferences[t.refBase[pl[i].clique] + seen[pl[i].clique]++];
     bindings->push_back({pod.Namespace, pod.Name, nodes[pl[i].node].Name});
@@ -471,19 +517,63 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
   }
   // a scheduled PodGang leaves the pending set once every PodReference is bound; until then its unbound pods are retried
   // as a remainder (Encode).  Remember where gangs landed for ReuseReservationRef hints.
+  auto constrained = [](const PodGang& pg) {
+    auto has = [](const std::optional<TopologyConstraint>& tc) { return tc && tc->PackConstraint && (tc->PackConstraint->Required || tc->PackConstraint->Preferred); };
+    if (has(pg.Spec.Topology)) return true;
+    for (const auto& gc : pg.Spec.TopologyConstraintGroupConfigs) if (has(gc.Topology)) return true;
+    for (const auto& p : pg.Spec.PodGroups) if (has(p.Topology)) return true;
+    return false;
+  };
+  std::lock_guard<std::mutex> l(mu_);
   for (uint32_t i = 0; i < gs.size(); ++i) {
     if (gs[i].state != GROVE_GANG_ADMITTED) continue;
     const std::string& key = t.gangNames[i];
-    const PodGang& pg = pending_.at(key);
+    auto pit = pending_.find(key);
+    if (pit == pending_.end()) continue;   // deleted while the cycle ran
+    const PodGang& pg = pit->second;
     if (gs[i].n_pods && !lastNode_.count(key)) lastNode_[key] = nodes[pl[gs[i].placement_off].node].Name;
     std::vector<uint32_t>& done = bound_[key];
     done.resize(pg.Spec.PodGroups.size(), 0u);
     for (uint32_t c = t.gangs[i].clique_off; c < t.gangs[i].clique_off + t.gangs[i].n_cliques; ++c) done[t.cliqueOf[c].second] += seen[c];
-    bool all = true;
-    for (size_t k = 0; k < done.size(); ++k) all &= done[k] >= pg.Spec.PodGroups[k].PodReferences.size();
+    bool all = true; uint32_t unbound = 0;
+    for (size_t k = 0; k < done.size(); ++k) {
+      all &= done[k] >= pg.Spec.PodGroups[k].PodReferences.size();
+      if (done[k] < pg.Spec.PodGroups[k].PodReferences.size()) unbound += uint32_t(pg.Spec.PodGroups[k].PodReferences.size()) - done[k];
+    }
+    // A PodGang WITH pack constraints is not resubmitted as a remainder (its best-effort pods would have to rejoin the
+    // domains chosen for the gang): it is scheduled, leaves the pending set, and the status says how many of its
+    // best-effort pods stayed Pending (such gangs used to sit in the pending set for ever)
+    if (!all && constrained(pg)) { (*statuses)[key].UnboundPods = unbound; all = true; }
     if (all) { pending_.erase(key); bound_.erase(key); }
   }
   return std::nullopt;
+}
+
+Err GpuBackend::Start(SnapshotFn snapshot, BindFn bind, std::chrono::milliseconds period) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (loop_.joinable()) return mkerr("ERR_SYNC_PODGANG", "Start", "cycle loop already running");
+  stop_ = false;
+  loop_ = std::thread([this, snapshot, bind, period] {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (cv_.wait_for(lk, period, [this] { return stop_; })) return;
+        if (pending_.empty()) continue;
+      }
+      std::vector<Binding> b; std::map<std::string, PodGangStatus> st; grove_cycle_stats_t cs{};
+      const std::vector<Node> nodes = snapshot();
+      if (auto e = RunCycle(nodes, &b, &st, &cs)) continue;   // the next tick retries (the reconciler's requeue)
+      cycles_.fetch_add(1);
+      bind(b, st, cs);
+    }
+  });
+  return std::nullopt;
+}
+
+void GpuBackend::Stop() {
+  { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+  cv_.notify_all();
+  if (loop_.joinable()) loop_.join();
 }
 
 }  // namespace grove::host

@@ -14,7 +14,13 @@
 // (operator/internal/errors/errors.go:41-86).
 #pragma once
 #include <cstdint>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <optional>
 #include <string>
 #include <vector>
@@ -58,7 +64,9 @@ struct PodGangStatus {                                                          
   PodGangPhase Phase = PodGangPhase::Pending;
   bool Scheduled = false;                 // condition PodGangConditionTypeScheduled :155
   std::string ScheduledReason;            // "" | "Unschedulable" | "BaseNotScheduled" | "Gated"
+  std::string ScheduledMessage;           // condition message (why a PodGang cannot be handed to the engine)
   std::optional<double> PlacementScore;   // :187-189
+  uint32_t UnboundPods = 0;               // best-effort pods (beyond MinReplicas) of a scheduled PodGang that found no node
 };
 struct PodGang {
   std::string Namespace, Name;
@@ -175,9 +183,11 @@ class Backend {                                                                 
   virtual void PreparePod(std::string* schedulerName) const = 0; // sets pod.spec.schedulerName
   virtual Err ValidatePodCliqueSet(const PodCliqueSet& pcs) const = 0;
 };
+struct GroupVersionResource { std::string Group, Version, Resource; };                // schema.GroupVersionResource
 class TopologyAwareSchedBackend {                                                     // :64-96
  public:
   virtual ~TopologyAwareSchedBackend() = default;
+  virtual GroupVersionResource TopologyGVR() const = 0;                               // :65-68
   virtual std::string TopologyResourceName(const std::string& clusterTopologyName) const = 0;
   virtual Err SyncTopology(const std::vector<TopologyLevel>& levels) = 0;
   virtual Err OnTopologyDelete() = 0;
@@ -195,6 +205,7 @@ struct Tables {
   std::vector<std::pair<uint32_t, uint32_t>> cliqueOf; // clique row -> (gang row, PodGroup index in Spec.PodGroups)
   std::vector<uint8_t> remainder;                       // gang row -> 1: unbound pods of an already scheduled PodGang (MinReplicas 0)
   std::vector<uint32_t> refBase;                        // clique row -> first PodReference its placement entries bind (remainders)
+  std::map<std::string, std::string> skipped;           // PodGang "<ns>/<name>" -> why it was left out of this pass
 };
 
 // The `gpu` scheduler backend: the third case of newBackendForProfile (manager/manager.go:35-52).
@@ -209,6 +220,9 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   Err OnPodGangDelete(const PodGang& podGang) override;
   void PreparePod(std::string* schedulerName) const override { *schedulerName = kName; }
   Err ValidatePodCliqueSet(const PodCliqueSet& pcs) const override;
+  // this backend keeps no topology CR of its own: the ordered level keys of the ClusterTopology ARE its topology
+  // (kai/topology.go:40-46 returns KAI's CRD here); the CT controller's dynamic watch lands on the ClusterTopology itself
+  GroupVersionResource TopologyGVR() const override { return {"grove.io", "v1alpha1", "clustertopologies"}; }
   std::string TopologyResourceName(const std::string& ct) const override { return ct; }
   Err SyncTopology(const std::vector<TopologyLevel>& levels) override;
   Err OnTopologyDelete() override;
@@ -219,9 +233,23 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   // one scheduling cycle: Encode -> grove_load_nodes / submit / run_cycle -> bindings + PodGang statuses
   Err RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* bindings, std::map<std::string, PodGangStatus>* statuses,
                grove_cycle_stats_t* stats = nullptr);
-  size_t Pending() const { return pending_.size(); }       // PodGangs with unbound pods (unscheduled, or scheduled with a remainder)
-  size_t Unscheduled() const { return pending_.size() - bound_.size(); }
-  void SetPriorityClass(const std::string& name, int32_t value) { priorityClasses_[name] = value; }
+  size_t Pending() const { std::lock_guard<std::mutex> l(mu_); return pending_.size(); }   // PodGangs with unbound pods (unscheduled, or scheduled with a remainder)
+  size_t Unscheduled() const { std::lock_guard<std::mutex> l(mu_); return pending_.size() - bound_.size(); }
+  void SetPriorityClass(const std::string& name, int32_t value) { std::lock_guard<std::mutex> l(mu_); priorityClasses_[name] = value; }
+  // why a PodGang cannot be handed to the engine (limits of the packed tables), or empty.  SyncPodGang accepts every
+  // PodGang -- the reference's reconciler would requeue forever on an error -- and RunCycle reports these as
+  // Unschedulable with this message instead of failing the pass for everybody.
+  static std::string WhyNotEncodable(const PodGang& pg);
+
+  // The cycle loop of the backend: SyncPodGang / OnPodGangDelete are called concurrently by
+  // the PodGang reconcilers (controller/podgang/register.go:34-36, MaxConcurrentReconciles) and only touch the pending
+  // set under the mutex; ONE thread takes node snapshots, runs cycles on the engine handle (not thread-safe) and hands
+  // bindings + statuses to the binder callback.
+  using SnapshotFn = std::function<std::vector<Node>()>;
+  using BindFn = std::function<void(const std::vector<Binding>&, const std::map<std::string, PodGangStatus>&, const grove_cycle_stats_t&)>;
+  Err Start(SnapshotFn snapshot, BindFn bind, std::chrono::milliseconds period);
+  void Stop();
+  uint64_t Cycles() const { return cycles_.load(); }
 
  private:
   int device_;
@@ -233,6 +261,13 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   std::map<std::string, std::vector<uint32_t>> bound_;  // scheduled PodGang still pending with unbound pods -> pods bound per PodGroup
   grove_engine_t* engine_ = nullptr;
   uint32_t engineLevels_ = 0;
+  mutable std::mutex mu_;        // pending set, bindings, levels: everything SyncPodGang / OnPodGangDelete / SyncTopology touch
+  std::mutex cycleMu_;           // one cycle at a time on the engine handle
+  std::thread loop_;
+  std::condition_variable cv_;
+  bool stop_ = false;
+  std::atomic<uint64_t> cycles_{0};
+  Err EncodeLocked(const std::vector<Node>& nodes, Tables* out) const;
 };
 
 }  // namespace grove::host

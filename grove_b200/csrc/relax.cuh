@@ -38,11 +38,20 @@ __global__ void __launch_bounds__(256) k_select(Tables tb, Relax rx) {
     need = rx.tstate[g] == 0 || rx.dirty[g];
     if (need) rx.dirty[g] = 0;
   }
-  const uint32_t b = __ballot_sync(kFull, need);
-  uint32_t base = 0;
-  if (lane == 0 && b) base = atomicAdd(rx.ctl + kNEval, __popc(b));
-  base = __shfl_sync(kFull, base, 0);
-  if (need) rx.eval_list[base + __popc(b & ((1u << lane) - 1u))] = g;
+  // longest first: a round lasts as long as its slowest evaluation, so the gangs that needed several attempts last
+  // time go to the head of the list (CTAs are handed out in list order), the others fill it from the tail
+  const bool heavy = need && rx.last_att[g] >= 3;
+  const uint32_t bh = __ballot_sync(kFull, heavy), bl = __ballot_sync(kFull, need && !heavy);
+  uint32_t base_h = 0, base_l = 0;
+  if (lane == 0) {
+    if (bh) base_h = atomicAdd(rx.ctl + kNHeavy, __popc(bh));
+    if (bl) base_l = atomicAdd(rx.ctl + kNLight, __popc(bl));
+    if (bh | bl) atomicAdd(rx.ctl + kNEval, __popc(bh | bl));
+  }
+  base_h = __shfl_sync(kFull, base_h, 0); base_l = __shfl_sync(kFull, base_l, 0);
+  const uint32_t below = (1u << lane) - 1u;
+  if (heavy) rx.eval_list[base_h + __popc(bh & below)] = g;
+  else if (need) rx.eval_list[tb.G - 1u - (base_l + __popc(bl & below))] = g;
 }
 
 // ---- claims --------------------------------------------------------------------------------------------
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
   const uint32_t n_eval = rx.ctl[kNEval], round = rx.ctl[kRound];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < n_eval; ei += nw) {
-    const uint32_t g = rx.eval_list[ei];
+    const uint32_t g = eval_list_at(rx, tb.G, ei);
     const grove_gang_t gg = tb.gangs[g];
     const uint32_t po = tb.ginfo[g].pod_off, rank = tb.ginfo[g].order;
     const uint32_t ot = rx.tstate[g], nt = rx.nxt_tstate[g];
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres
     // the claims of the ranks before them on their first evaluation pile up less on the same nodes)
     const uint32_t h2 = min(G, min(nf + rx.window, max(rx.ctl[kHi], nf) + rx.entry));
     rx.ctl[kEvals] += rx.ctl[kNEval];
-    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kChanged] = 0;
+    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kNHeavy] = 0; rx.ctl[kNLight] = 0; rx.ctl[kChanged] = 0;
     rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
     rx.ctl[kDone] = nf >= G ? 1u : 0u;
     if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every && rx.ctl[kFoldAny]) rx.ctl[kRefresh] = 1;

@@ -24,6 +24,7 @@ SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_get_scope_domains", "grove_load_nodes_device",
+    "grove_build_score_matrix",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -156,6 +157,12 @@ class PlacementEngine:
         out = np.zeros(self.n, dtype=T.node_dt)
         self._check(self.lib.grove_get_nodes(self.h, _p(out), C.c_uint32(self.n)))
         return out
+
+    def build_score_matrix(self) -> float:
+        """K2 over the last cycle's start snapshot; returns the kernel's device time in ms"""
+        ms = C.c_float(0)
+        self._check(self.lib.grove_build_score_matrix(self.h, C.byref(ms)))
+        return ms.value
 
     # ---- introspection (parity tests) ----
     def debug_perm(self) -> np.ndarray:

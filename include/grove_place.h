@@ -217,6 +217,12 @@ int32_t grove_get_placements(grove_engine_t* e, grove_placement_t* out, uint32_t
 int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint32_t cap);
 int32_t grove_get_scope_domains(grove_engine_t* e, grove_scope_status_t* out, uint32_t cap);
 
+/* K2: the topology-distance score matrix T[clique][node] = fit ? 1 + levels shared with the gang's anchor : 0 (u8) over the
+ * snapshot the last cycle started from -- what a scheduler's Score extension point would hand out.  The admission does
+ * not read it (its visiting order comes from the anchor's domain ranges), so it is built on request; GROVE_TUNE_SCORE=1
+ * builds it every cycle beside the admission.  *ms (nullable): device time of the kernel. */
+int32_t grove_build_score_matrix(grove_engine_t* e, float* ms);
+
 /* ---- device-resident variants (inputs already in HBM; used by bench.py `value`) -------------- */
 /* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load */
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);

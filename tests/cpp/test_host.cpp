@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 #include <set>
 
 #include "../../grove_b200/csrc/host/grove_host.hpp"
@@ -273,11 +275,24 @@ static void test_encode() {
   CHECK(t.cliques[0].class_mask == 0x2);  // only the "agent" class, whose taint the pods tolerate
   CHECK((t.nodes[0].flags & GROVE_NODE_SCHEDULABLE) && !(t.nodes[9].flags & GROVE_NODE_SCHEDULABLE));
   CHECK(t.nodes[0].dom[0] == t.nodes[9].dom[0] && t.nodes[0].dom[2] != t.nodes[7].dom[2] && t.nodes[0].free_mem_mib == 150);
-  // a Required key that is not a level of the synced topology is an error, like a stale ClusterTopology
+  // a Required key that is not (or no longer) a level of the synced topology is DROPPED, as the operator does for a pack
+  // domain it cannot find (createTopologyPackConstraint, syncflow.go:349-371): the pass goes on for everybody
   PodGang bad = BuildPodGang(pcs, infos[0]); bad.Name = "bad"; bad.Spec.Topology = TopologyConstraint{TopologyPackConstraint{std::string("example.com/nope"), std::nullopt}};
   CHECK(!be.SyncPodGang(bad));
-  CHECK(be.Encode(e2e_nodes(10), &t).has_value());
+  CHECK(!be.Encode(e2e_nodes(10), &t));
+  CHECK(t.gangs.size() == 2 && t.gangNames[0].find("bad") != std::string::npos && t.gangs[0].level == GROVE_LEVEL_NONE && t.gangs[1].level == 1);
   CHECK(!be.OnPodGangDelete(bad));
+  // a PodGang the packed tables cannot hold is left out of the pass with a reason; SyncPodGang itself accepts it (an error
+  // there would requeue the reconcile for ever), and the others are encoded as usual
+  PodGang huge = BuildPodGang(pcs, infos[0]); huge.Name = "huge";
+  for (int i = 0; i < 300; ++i) huge.Spec.PodGroups[0].PodReferences.push_back({"default", "huge-pod-" + std::to_string(i)});
+  CHECK(!GpuBackend::WhyNotEncodable(huge).empty() && GpuBackend::WhyNotEncodable(bad).empty());
+  CHECK(!be.SyncPodGang(huge));
+  CHECK(!be.Encode(e2e_nodes(10), &t));
+  CHECK(t.gangs.size() == 1 && t.skipped.size() == 1 && t.skipped.begin()->first.find("huge") != std::string::npos);
+  CHECK(t.skipped.begin()->second.find("podReferences") != std::string::npos);
+  CHECK(!be.OnPodGangDelete(huge));
+  CHECK(be.TopologyGVR().Resource == "clustertopologies" && be.TopologyGVR().Group == "grove.io");
   // Preferred keys (podgang.go:110-117) become Preferred levels; one that is not deeper than Required is dropped
   PodGang pref = BuildPodGang(pcs, infos[0]); pref.Name = "zz-pref";  // rows follow the PodGang key order: after workload1-0
   pref.Spec.Topology = TopologyConstraint{TopologyPackConstraint{std::nullopt, kLevels[2].Key}};
@@ -366,6 +381,58 @@ static void test_gpu_min_replicas_then_remainder() {
   CHECK(podNode.size() == 10 && nodes.size() == 10);
 }
 
+// The backend's cycle loop: several "reconcilers" call SyncPodGang concurrently
+// (controller/podgang/register.go:34-36) while ONE thread snapshots nodes, runs cycles and binds.  A PodGang the tables
+// cannot hold is reported Unschedulable with its reason and does not stop anybody else.
+static void test_gpu_cycle_loop_with_concurrent_reconcilers() {
+  GpuBackend be;
+  CHECK(!be.SyncTopology(kLevels));
+  CHECK(!be.Init());
+  PodGang::Requests rq; rq.mem_mib = 80; rq.nodeSelector = {{"node_role.e2e.grove.nvidia.com", "agent"}}; rq.tolerationKeys = {"node_role.e2e.grove.nvidia.com"};
+  std::mutex mu; std::map<std::string, std::string> podNode; std::map<std::string, PodGangStatus> last;
+  auto snapshot = [&] {
+    auto nodes = e2e_nodes(28, 0);
+    std::lock_guard<std::mutex> l(mu);
+    for (const auto& kv : podNode) for (auto& nd : nodes) if (nd.Name == kv.second) { nd.used_mem_mib += 80; nd.used_pods += 1; }
+    return nodes;
+  };
+  auto bind = [&](const std::vector<Binding>& b, const std::map<std::string, PodGangStatus>& st, const grove_cycle_stats_t&) {
+    std::lock_guard<std::mutex> l(mu);
+    for (const auto& x : b) { CHECK(!podNode.count(x.PodName)); podNode[x.PodName] = x.NodeName; }
+    for (const auto& kv : st) last[kv.first] = kv.second;
+  };
+  CHECK(!be.Start(snapshot, bind, std::chrono::milliseconds(2)));
+  CHECK(be.Start(snapshot, bind, std::chrono::milliseconds(2)).has_value());   // already running
+  std::vector<std::thread> reconcilers;
+  for (int t = 0; t < 4; ++t)
+    reconcilers.emplace_back([&, t] {
+      for (int k = 0; k < 3; ++k) {
+        PodCliqueSet pcs; pcs.Name = "wl-" + std::to_string(t) + "-" + std::to_string(k);
+        auto c = clq("pc", 2, 2); c.Requests = rq; pcs.Cliques.push_back(c);
+        std::vector<PodGangInfo> infos;
+        if (ComputeExpectedPodGangs(pcs, kLevels, true, &infos)) { ++g_fail; return; }
+        for (const auto& i : infos) if (be.SyncPodGang(BuildPodGang(pcs, i))) ++g_fail;
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      }
+    });
+  { PodCliqueSet pcs; pcs.Name = "huge"; auto c = clq("pc", 2, 2); c.Requests = rq; pcs.Cliques.push_back(c);
+    std::vector<PodGangInfo> infos; CHECK(!ComputeExpectedPodGangs(pcs, kLevels, true, &infos));
+    PodGang huge = BuildPodGang(pcs, infos[0]);
+    for (int i = 0; i < 300; ++i) huge.Spec.PodGroups[0].PodReferences.push_back({"default", "huge-pod-" + std::to_string(i)});
+    CHECK(!be.SyncPodGang(huge)); }
+  for (auto& t : reconcilers) t.join();
+  for (int spin = 0; spin < 2000 && be.Pending() > 1; ++spin) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  be.Stop();
+  std::lock_guard<std::mutex> l(mu);
+  CHECK(be.Pending() == 1 && be.Cycles() >= 1);                      // only the oversized PodGang is left
+  CHECK(podNode.size() == 24);                                       // 12 PodGangs x 2 pods, each bound exactly once
+  std::set<std::string> used; for (const auto& kv : podNode) used.insert(kv.second);
+  CHECK(used.size() == 24);                                          // 150 MiB nodes hold one 80 MiB pod each
+  bool seen_huge = false;
+  for (const auto& kv : last) if (kv.first.find("huge") != std::string::npos) { seen_huge = true; CHECK(!kv.second.Scheduled && kv.second.ScheduledReason == "Unschedulable" && !kv.second.ScheduledMessage.empty()); }
+  CHECK(seen_huge);
+}
+
 int main(int argc, char** argv) {
   const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
   test_compute_expected_podgangs();
@@ -375,7 +442,7 @@ int main(int argc, char** argv) {
   test_pod_scheduling_gates();
   test_scheduled_condition_and_counts();
   test_encode();
-  if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); }
+  if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); test_gpu_cycle_loop_with_concurrent_reconcilers(); }
   else {  // without a CUDA device Init must fail loudly, never fall back
     GpuBackend be; be.SyncTopology(kLevels);
     auto e = be.Init();

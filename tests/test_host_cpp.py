@@ -14,7 +14,7 @@ def host_test_bin(built_lib, tmp_path_factory):
     srcs = [os.path.join(ROOT, "tests", "cpp", "test_host.cpp"), os.path.join(ROOT, "grove_b200", "csrc", "host", "grove_host.cpp")]
     libdir = os.path.join(ROOT, "grove_b200")
     env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", out, *srcs, f"-L{libdir}", "-lgrove_place",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-o", out, *srcs, f"-L{libdir}", "-lgrove_place",
                            f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], env=env)
     return out
 
