@@ -75,7 +75,7 @@ def _podgang(name, groups, gang_key=None, configs=()):
     return {"apiVersion": "scheduler.grove.io/v1alpha1", "kind": "PodGang", "metadata": {"name": name, "namespace": "default"}, "spec": spec}
 
 
-def test_podgang_manifest_to_tables_and_oracle(kwok, oracle):
+def test_podgang_manifest_to_tables_and_oracle(kwok, placer):
     """tas-hierarchy.yaml as the operator would emit it: PCS block -> PCSG replica rack -> PCLQ host"""
     Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
     pg = _podgang("tas-hierarchy-0",
@@ -91,7 +91,7 @@ def test_podgang_manifest_to_tables_and_oracle(kwok, oracle):
     for i, m in enumerate(ms):
         m["metadata"]["labels"][B] = f"block-{i // 14}"
     nodes, node_names, *_ = ingest.nodes_from_manifests(ms, [Z, B, R, H])
-    r = oracle.run_cycle(nodes, 4, g, c, s)
+    r = placer.run_cycle(nodes, 4, g, c, s)
     assert r["status"]["state"][0] == T.GANG_ADMITTED and r["status"]["n_pods"][0] == 9
     pl = r["placements"]
     for row in range(1, 5):
@@ -103,7 +103,7 @@ def test_podgang_manifest_to_tables_and_oracle(kwok, oracle):
         ingest.podgangs_from_manifests([_podgang("x", [("a", 1, 1, "example.com/nope")])], {}, [Z, B, R, H])
 
 
-def test_preferred_keys_become_preferred_levels(kwok, oracle):
+def test_preferred_keys_become_preferred_levels(kwok, placer):
     """packConstraint.preferred (podgang.go:110-117) at PodGang, group-config and PodGroup level"""
     Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
     pg = _podgang("p", [("a", 2, 2, None), ("b", 3, 3, None), ("c", 1, 1, None)], configs=[("cfg", ("b", "c"), B)])
@@ -117,7 +117,7 @@ def test_preferred_keys_become_preferred_levels(kwok, oracle):
     assert (c["scope"] & 0x1F).tolist() == [0, 1, 1] and (c["scope"] >> 5).tolist() == [4, 0, 0]
     assert c["level"].tolist() == [T.LEVEL_NONE, 2, T.LEVEL_NONE]
     nodes, *_ = ingest.nodes_from_manifests(kwok["manifests_e2e"][:14], [Z, B, R, H])
-    r = oracle.run_cycle(nodes, 4, g, c, s)
+    r = placer.run_cycle(nodes, 4, g, c, s)
     assert r["status"]["state"][0] == T.GANG_ADMITTED
     pl = r["placements"]
     assert len(set(pl["node"][pl["clique"] == 0])) == 1                      # a: both pods on one host
@@ -127,7 +127,7 @@ def test_preferred_keys_become_preferred_levels(kwok, oracle):
         ingest.podgangs_from_manifests([bad], {}, [Z, B, R, H])
 
 
-def test_reuse_reservation_ref_bindings_and_status(kwok, oracle):
+def test_reuse_reservation_ref_bindings_and_status(kwok, placer):
     """spec.reuseReservationRef -> anchor; placements -> (pod, node) bindings; status rows -> PodGang.status"""
     Z, B, R, H = (kwok["label_keys"][k] for k in ("zone", "block", "rack", "host"))
     nodes, node_names, *_ = ingest.nodes_from_manifests(kwok["manifests_e2e"][:28], [Z, B, R, H])
@@ -137,13 +137,13 @@ def test_reuse_reservation_ref_bindings_and_status(kwok, oracle):
     huge = _podgang("huge", [("x", 9, 9, H)])           # nine 40 MiB pods on one 150 MiB host: unschedulable
     req = {"a": {"memory": "40Mi"}, "w": {"memory": "40Mi"}, "x": {"memory": "40Mi"}}
     g, c, s, names = ingest.podgangs_from_manifests([first], req, [Z, B, R, H])
-    r = oracle.run_cycle(nodes, 4, g, c, s)
+    r = placer.run_cycle(nodes, 4, g, c, s)
     b1 = ingest.bindings(r["placements"], [first], names, node_names)
     assert [p for _, p, _ in b1] == ["a-0", "a-1"] and all(n.startswith("kwok-node-") for _, _, n in b1)
     landed = int(r["placements"]["node"][0])
     g, c, s, names = ingest.podgangs_from_manifests([again, huge], req, [Z, B, R, H], placed_on={"first": landed})
     assert g["anchor_node"].tolist() == [landed, T.NONE_U32]
-    r2 = oracle.run_cycle(r["nodes_after"], 4, g, c, s)
+    r2 = placer.run_cycle(r["nodes_after"], 4, g, c, s)
     b2 = ingest.bindings(r2["placements"], [again, huge], names, node_names)
     assert len(b2) == 3 and {int(nodes["dom"][node_names.index(n), 2]) for _, _, n in b2} == {int(nodes["dom"][landed, 2])}   # same rack as "first"
     st = [ingest.podgang_status(row) for row in r2["status"]]

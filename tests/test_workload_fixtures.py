@@ -137,12 +137,12 @@ TAS = {   # file -> (nodes, expected running pods) as the suite sets up / waits 
 
 
 @pytest.mark.parametrize("path", sorted(TAS))
-def test_tas_workload_files_end_to_end(oracle, path):
+def test_tas_workload_files_end_to_end(placer, path):
     n_nodes, expect = TAS[path]
     g, c, s, names, gangs = ingest.tables_from_pcs(pcs_of(path), LEVELS, class_mask=synth.AGENT)
     assert int(c["replicas"].sum()) == (expect if expect else 10)
     nodes = synth.e2e_cluster(n_nodes)
-    r = oracle.run_cycle(nodes, synth.E2E_LEVELS, g, c, s)
+    r = placer.run_cycle(nodes, synth.E2E_LEVELS, g, c, s)
     assert check_pack_constraints(nodes, (g, c, s), r) == expect
     if expect:
         assert (r["status"]["state"] == T.GANG_ADMITTED).all()
@@ -150,11 +150,11 @@ def test_tas_workload_files_end_to_end(oracle, path):
         assert (r["status"]["state"] == T.GANG_REJECTED).all() and np.array_equal(r["nodes_after"], nodes)
 
 
-def test_tas8_shape_from_the_file(oracle):
+def test_tas8_shape_from_the_file(placer):
     """topology_test.go:508-578 on the file itself: 4 host groups, 2 rack groups, 1 block"""
     g, c, s, names, _ = ingest.tables_from_pcs(pcs_of("e2e/yaml/tas-hierarchy.yaml"), LEVELS, class_mask=synth.AGENT)
     nodes = synth.e2e_cluster(28)
-    pl = oracle.run_cycle(nodes, synth.E2E_LEVELS, g, c, s)["placements"]
+    pl = placer.run_cycle(nodes, synth.E2E_LEVELS, g, c, s)["placements"]
     assert len({int(n) for n in pl["node"]}) == 4                                             # each PodClique's two pods share a host
     by_replica = {}
     for q, n in zip(pl["clique"], pl["node"]):
@@ -173,7 +173,7 @@ def test_simple1_is_config_c1():
     assert sorted(n for _, n in names) == ["simple1-0-pca", "simple1-0-pcd", "simple1-0-sga-0-pcb", "simple1-0-sga-0-pcc"]
 
 
-def test_tas17_two_topologies_on_one_cluster(oracle):
+def test_tas17_two_topologies_on_one_cluster(placer):
     """topology_test.go:1192-1370 on the reference's own files and its own node manifests: 28 nodes, the last 14
     relabelled as GB200 (no kubernetes.io/rack, example.com/nvl-block + example.com/nvlink-domain instead); the domain
     name "block" means kubernetes.io/rack in h100-topology and example.com/nvl-block in gb200-topology.  Each workload
@@ -196,7 +196,7 @@ def test_tas17_two_topologies_on_one_cluster(oracle):
         nodes, names, *_ = ingest.nodes_from_manifests(ms, [k for _, k in levels], used=used)
         g, c, s, _, gangs = ingest.tables_from_pcs(pcs, levels)
         assert gangs[0]["spec"]["topologyConstraint"]["packConstraint"]["required"] == levels[0][1]
-        r = oracle.run_cycle(nodes, len(levels), g, c, s)
+        r = placer.run_cycle(nodes, len(levels), g, c, s)
         assert (r["status"]["state"] == T.GANG_ADMITTED).all() and len(r["placements"]) == 2
         where = [int(n) for n in r["placements"]["node"]]
         segment = range(0, 14) if "h100" in path else range(14, 28)
