@@ -664,6 +664,12 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     for (uint32_t si = lane; si < gg.n_scopes; si += 32) { sh.scopes[si] = tb.scopes[gg.scope_off + si]; sh.s_got[si] = -1; sh.s_lo[si] = 0; }
     if (threadIdx.x == 0) { s_win = GROVE_NONE_U32; s_ext = 0; s_att = 0; s_npl = 0; }
     __syncthreads();
+    // A candidate that failed in the gang's last evaluation fails again unless a claim was withdrawn inside it since: views only
+    // shrink otherwise (claims are added, settled claims move into the committed state).  So a re-evaluation skips the
+    // candidates in front of its last answer that no withdrawal touched -- gangs that meet a nearly full cluster would
+    // otherwise re-run dozens of failing attempts every round.  (Single candidate level only.)
+    const uint32_t round_now = rx.ctl[kRound];
+    const uint32_t le = rx.last_eval[gi];
     Ev<kPref> ev(tp, rx, sh, g, lane);                         // candidates of any size, node state from L2
     EvS<kPref> evs(tp, rx, sh, g, lane, s_view[warp]);         // candidates of <= kStageMax nodes, node state staged in shared memory
     bool staged = false;  // the winning attempt ran on evs
@@ -676,6 +682,8 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     int gfirst;
     const int gbase = level_span<kPref>(gg.level, gg.preferred, -1, gfirst);
     int gl = gfirst;
+    const uint32_t fu = (le && gfirst == gbase && gfirst >= 0) ? rx.fail_upto[gi] : 0u;
+    uint32_t k_won = 0;
     do {
       if (gl < 0) {
         staged = false;
@@ -721,6 +729,12 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
               } else {
                 uint32_t dl, dh; const uint32_t d = cand(k, dl, dh); plaus = gang_plausible(tp, rx, sh, gg.n_scopes, dl, dh, gl, d);
               }
+              if (plaus && k < fu) {   // failed last time: worth another attempt only if somebody withdrew a claim in there since
+                uint32_t dl, dh; cand(k, dl, dh);
+                bool again = false;
+                for (uint32_t w = dl >> 5; w <= (dh - 1u) >> 5; ++w) again |= __ldg(rx.rem_round + w) >= le;
+                plaus = again;
+              }
             }
             const uint32_t b = __ballot_sync(kFull, plaus);
             if (lane == 0) s_plaus[c] = b;
@@ -747,6 +761,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
               staged = dh - dl <= kStageMax;
               ok = staged ? place_in(evs, gg.n_scopes, dl, dh, gl) : place_in(ev, gg.n_scopes, dl, dh, gl);
               if (lane == 0) { atomicAdd(&s_att, 1u); if (ok) atomicMin(&s_win, j); }
+              if (ok) k_won = k;
             }
             __syncthreads();
             const uint32_t win = s_win;
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
       }
     } while (kPref && !done && --gl >= gbase);
     // what any of the attempts may have read (attempts past the winner only widen it)
-    if (lane == 0) atomicMax(&s_ext, max(ev.ext, evs.ext));
+    if (lane == 0) atomicMax(&s_ext, max(max(ev.ext, evs.ext), fu ? rx.extent[gi] : 0u));   // skipped candidates were read by the last evaluation
     __syncthreads();
     if (threadIdx.x == 0) rx.last_att[gi] = uint8_t(min(255u, (s_att + kW - 1) / kW));
     if (rx.dbg && threadIdx.x == 0) {
@@ -770,6 +785,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     }
     if (!done) {
       if (threadIdx.x == 0) {
+        rx.last_eval[gi] = round_now; rx.fail_upto[gi] = kFull;   // every candidate failed
         rx.nxt_tstate[gi] = GROVE_GANG_REJECTED; rx.nxt_n[gi] = 0; rx.nxt_info[gi] = 0xFFu; rx.nxt_glo[gi] = GROVE_NONE_U32;
         rx.nxt_extent[gi] = s_ext;
       }
@@ -809,6 +825,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
       rx.nxt_sc_lo[gg.scope_off + si] = own ? sh.s_lo[si] : GROVE_NONE_U32;
     }
     if (lane == 0) {
+      rx.last_eval[gi] = round_now; rx.fail_upto[gi] = g_got >= 0 ? k_won : 0u;
       rx.nxt_tstate[gi] = GROVE_GANG_ADMITTED; rx.nxt_n[gi] = uint16_t(n_ent);
       rx.nxt_info[gi] = (g_got >= 0 ? uint32_t(g_got) : 0xFFu) | (num << 8) | (den << 20);
       rx.nxt_glo[gi] = g_got >= 0 ? g_lo : GROVE_NONE_U32;

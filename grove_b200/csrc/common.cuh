@@ -116,6 +116,9 @@ struct Relax {
   // change stamps of the round: (tag << 24) | lowest rank; a stale tag = no stamp
   uint32_t* add_stamp;      // [npad] a gang newly claimed this node
   uint32_t* rem_stamp;      // [words] a gang withdrew a claim from this 32-node group
+  uint32_t* rem_round;      // [words] last round in which ANY gang withdrew a claim from the group
+  uint32_t* last_eval;      // [G] round of the gang's last evaluation (0 = never)
+  uint32_t* fail_upto;      // [G] candidates (in order) that came before the last evaluation's answer: all of them failed then
   // capacity tables over the committed state as of the last build (upper bounds afterwards)
   uint32_t* F;              // [S][words] fit bitmap, one row per signature
   uint8_t* cap8;            // [S][npad] pods of the signature that fit on the node (saturating at 255)

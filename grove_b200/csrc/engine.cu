@@ -159,7 +159,7 @@ struct grove_engine {
   // ---- relaxation state (relax.cuh) ----
   DevBuf<uint32_t> d_ctl, d_chg_round, d_eval_list, d_ent_node, d_cur_info, d_cur_glo, d_extent, d_sc_lo;
   DevBuf<uint32_t> d_nxt_node, d_nxt_info, d_nxt_glo, d_nxt_extent, d_nxt_sc_lo;
-  DevBuf<uint32_t> d_nlive, d_ovf_head, d_ovf_next, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
+  DevBuf<uint32_t> d_rem_round, d_last_eval, d_fail_upto, d_nlive, d_ovf_head, d_ovf_next, d_add_stamp, d_rem_stamp, d_F, d_capsum, d_capmax, d_fin, d_totals;
   DevBuf<uint16_t> d_ent_meta, d_cur_n, d_nxt_meta, d_nxt_n;
   DevBuf<uint8_t> d_last_att, d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
   DevBuf<uint4> d_claims, d_ovf_claim;
@@ -330,7 +330,7 @@ static Relax make_relax(grove_engine* e) {
   r.nxt_info = e->d_nxt_info.p; r.nxt_glo = e->d_nxt_glo.p; r.nxt_extent = e->d_nxt_extent.p; r.nxt_sc_lvl = e->d_nxt_sc_lvl.p; r.nxt_sc_lo = e->d_nxt_sc_lo.p;
   r.claims = e->d_claims.p; r.nlive = e->d_nlive.p; r.ovf_head = e->d_ovf_head.p; r.ovf_next = e->d_ovf_next.p; r.ovf_claim = e->d_ovf_claim.p;
   r.ovf_cap = uint32_t(std::min<size_t>(e->d_ovf_claim.cap, 0xFFFFFFF0u));
-  r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p;
+  r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p; r.rem_round = e->d_rem_round.p; r.last_eval = e->d_last_eval.p; r.fail_upto = e->d_fail_upto.p;
   r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
   r.shape_bits = e->shape_tables ? e->d_shape_bits.p : nullptr; r.pl_words = e->pl_words;
   for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) r.pl_off[l] = e->pl_off[l];
@@ -876,7 +876,8 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, e->d_nxt_sc_lvl.ensure(s1)); CU_TRY(e, e->d_nxt_sc_lo.ensure(s1));
   CU_TRY(e, e->d_claims.ensure(size_t(N) * kClaimSlots)); CU_TRY(e, e->d_nlive.ensure(N / 4)); CU_TRY(e, e->d_ovf_head.ensure(N));
   CU_TRY(e, e->d_ovf_next.ensure(4 * p1 + 1024)); CU_TRY(e, e->d_ovf_claim.ensure(4 * p1 + 1024));
-  CU_TRY(e, e->d_add_stamp.ensure(N)); CU_TRY(e, e->d_rem_stamp.ensure(e->words));
+  CU_TRY(e, e->d_add_stamp.ensure(N)); CU_TRY(e, e->d_rem_stamp.ensure(e->words)); CU_TRY(e, e->d_rem_round.ensure(e->words));
+  CU_TRY(e, e->d_last_eval.ensure(g1)); CU_TRY(e, e->d_fail_upto.ensure(g1));
   CU_TRY(e, e->d_status.ensure(g1)); CU_TRY(e, e->d_scope_status.ensure(s1)); CU_TRY(e, e->d_out.ensure(p1));
   CU_TRY(e, e->h_status.ensure(g1)); CU_TRY(e, e->h_scope_status.ensure(s1)); CU_TRY(e, e->h_out.ensure(p1));
   CU_TRY(e, e->d_fin.ensure((G + kFinThreads - 1) / kFinThreads + 4)); CU_TRY(e, e->d_totals.ensure(4));
@@ -900,6 +901,7 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, cudaMemsetAsync(e->d_claims.p, 0xFF, sizeof(uint4) * size_t(N) * kClaimSlots, st));
   CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_ovf_head.p, 0, sizeof(uint32_t) * N, st));
   CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_rem_round.p, 0, sizeof(uint32_t) * e->words, st)); CU_TRY(e, cudaMemsetAsync(e->d_last_eval.p, 0, sizeof(uint32_t) * g1, st));
   {
     uint32_t* c = e->h_ctl.p;
     std::memset(c, 0, sizeof(uint32_t) * kCtlWords);

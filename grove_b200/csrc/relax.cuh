@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
       const uint32_t n = rx.ent_node[po + i];
       claim_remove(rx, n, rank);
       atomicMin(rx.rem_stamp + (n >> 5), stamp);
+      atomicMax(rx.rem_round + (n >> 5), round);
     }
     if (on && lane == 0) atomicMin(rx.ctl + kRemAny, stamp);
     __syncwarp();
