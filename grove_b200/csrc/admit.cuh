@@ -613,19 +613,25 @@ __device__ __forceinline__ uint32_t eval_list_at(const Relax& rx, uint32_t G, ui
 // candidate IN ORDER is the answer -- exactly what trying them one after the other gives, minus the waiting.  kW = 1
 // while a round has many gangs (what matters is gangs in flight), 4 / 8 when it has few (what matters is the
 // latency of the slowest gang: a round lasts as long as its slowest evaluation).
-// A launch only acts if lo_cnt <= gangs of the round < hi_cnt, so the host can enqueue every form without
-// knowing the count.  Writes the "nxt" scratch of the gang.
-template <bool kPref, int kW>
-__global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, uint32_t lo_cnt, uint32_t hi_cnt) {
+// Two launches per round, side by side on two streams: the LIGHT gangs (the tail of the list: most gangs, answered by their
+// first or second candidate) a warp each -- every resident warp does useful work --, the HEAVY ones (the head: gangs whose
+// last evaluation needed many attempts) kW warps each.  A light evaluation that is still unanswered after `max_att` attempts
+// gives up (kEvalDeferred): the gang stays dirty and comes back as a heavy one next round, instead of holding the round up.
+// Writes the "nxt" scratch of the gang.
+constexpr uint32_t kEvalDeferred = 0xFFu;   // nxt_tstate: no result this round
+constexpr int kHeavyWarps = 8;
+template <bool kPref, int kW, bool kHeavy>
+__global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, uint32_t max_att) {
   __shared__ GangShared shs[kW];
   __shared__ uint4 s_view[kW][kStageMax];
   __shared__ uint32_t s_plaus[32];   // plausible candidates of the current 1024-candidate chunk, in order
   __shared__ uint32_t s_win, s_ext, s_att, s_npl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_eval = rx.ctl[kNEval], front = rx.ctl[kFront];
-  if (rx.ctl[kDone] || n_eval < lo_cnt || n_eval >= hi_cnt) return;
+  const uint32_t n_eval = rx.ctl[kNEval], n_heavy = rx.ctl[kNHeavy], front = rx.ctl[kFront];
+  if (rx.ctl[kDone]) return;
   GangShared& sh = shs[warp];
-  for (uint32_t ei = blockIdx.x; ei < n_eval; ei += gridDim.x) {
+  const uint32_t seg_lo = kHeavy ? 0u : n_heavy, seg_hi = kHeavy ? n_heavy : n_eval;
+  for (uint32_t ei = seg_lo + blockIdx.x; ei < seg_hi; ei += gridDim.x) {
     const uint32_t gi = eval_list_at(rx, tb.G, ei);
     const grove_gang_t gg = tb.gangs[gi];
     const GangInfo info = tb.ginfo[gi];
@@ -684,6 +690,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     int gl = gfirst;
     const uint32_t fu = (le && gfirst == gbase && gfirst >= 0) ? rx.fail_upto[gi] : 0u;
     uint32_t k_won = 0;
+    bool gave_up = false;
     do {
       if (gl < 0) {
         staged = false;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
           return d;
         };
         // candidates are taken in chunks that grow (kW x 32, then up to 1024): most gangs succeed among the first few
-        for (uint32_t base = 0, nchunk = kW; base < D && !done; base += nchunk * 32, nchunk = min(32u, nchunk * 4u)) {
+        for (uint32_t base = 0, nchunk = kW; base < D && !done && !gave_up; base += nchunk * 32, nchunk = min(32u, nchunk * 4u)) {
           // pre-filter: nchunk runs of 32 candidates, dealt to the warps
           for (uint32_t c = warp; c < 32; c += kW) {
             if (c >= nchunk) { if (lane == 0) s_plaus[c] = 0; continue; }
@@ -747,11 +754,11 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
           // attempts: kW plausible candidates at a time, in order, a warp each
           // while a round has many gangs the very first candidate is attempted by one warp alone: it usually succeeds,
           // and the other warps' attempts would be thrown away
-          const bool solo = kW > 1 && base == 0 && n_eval >= 256;
-          for (uint32_t j0 = 0; j0 < total && !done; j0 += (solo && j0 == 0) ? 1u : uint32_t(kW)) {
+          for (uint32_t j0 = 0; j0 < total && !done; j0 += uint32_t(kW)) {
+            if (!kHeavy && max_att && s_att >= max_att) { gave_up = true; break; }   // CTA-uniform (read after a barrier)
             const uint32_t j = j0 + warp;
             bool ok = false; uint32_t dl = 0, dh = 0;
-            if (j < total && !(solo && j0 == 0 && warp != 0)) {
+            if (j < total) {
               uint32_t rem = j, c = 0;   // the j-th set bit of the bitmap
               for (; c < 32; ++c) { const uint32_t pc = __popc(s_plaus[c]); if (rem < pc) break; rem -= pc; }
               uint32_t w = s_plaus[c];
@@ -770,11 +777,15 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
           __syncthreads();   // s_plaus is rewritten by the next chunk
         }
       }
-    } while (kPref && !done && --gl >= gbase);
+    } while (kPref && !done && !gave_up && --gl >= gbase);
     // what any of the attempts may have read (attempts past the winner only widen it)
     if (lane == 0) atomicMax(&s_ext, max(max(ev.ext, evs.ext), fu ? rx.extent[gi] : 0u));   // skipped candidates were read by the last evaluation
     __syncthreads();
-    if (threadIdx.x == 0) rx.last_att[gi] = uint8_t(min(255u, (s_att + kW - 1) / kW));
+    if (threadIdx.x == 0) rx.last_att[gi] = uint8_t(gave_up ? 255u : min(254u, s_att));
+    if (gave_up) {   // no result this round: k_apply keeps the gang dirty
+      if (threadIdx.x == 0) rx.nxt_tstate[gi] = uint8_t(kEvalDeferred);
+      continue;
+    }
     if (rx.dbg && threadIdx.x == 0) {
       const uint32_t cyc = uint32_t(clock64() - t0);
       rx.dbg[gi * 8 + 0] += 1; rx.dbg[gi * 8 + 1] += s_npl; rx.dbg[gi * 8 + 2] += s_att;

@@ -127,7 +127,7 @@ struct Relax {
   uint8_t* T;               // [Q][npad] K2 score matrix over the cycle-start snapshot
   const uint32_t* shape_bits; // [shapes][pl_words] candidate pre-filter per (gang shape, domain), bit pl_off[level] + d; null = not built
   uint32_t pl_off[GROVE_MAX_LEVELS], pl_words;
-  uint32_t P, window, entry;
+  uint32_t P, window, entry, heavy_att;   // heavy_att: attempts of its last evaluation from which a gang counts as heavy
   uint32_t* dbg;            // [G][8] optional per-gang evaluation statistics
 };
 

@@ -111,6 +111,7 @@ struct grove_engine {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_score = nullptr;  // K2 runs beside the relaxation (they only share the fit data)
+  cudaStream_t stream_heavy = nullptr;  // the heavy gangs of a round are evaluated beside the light ones
   cudaEvent_t ev_fit = nullptr, ev_score = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   cudaEvent_t ev_nodes_up = nullptr, ev_tables_up = nullptr;  // the last upload out of the pinned node staging buffer / gang tables
   cudaEvent_t ev[10]{};
@@ -178,7 +179,10 @@ struct grove_engine {
   uint32_t tune_warp_ctas = 2;     // CTAs per SM of the warp-per-gang bookkeeping kernels (apply / detect / settle)
   uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
-  uint32_t tune_warp4 = 4096, tune_warp16 = 600;   // rounds with fewer gangs than this evaluate them with 4 / 8 warps each
+  uint32_t tune_heavy_att = 4;     // a gang whose last evaluation made this many attempts is heavy: kW warps next time
+  uint32_t tune_max_att = 4;       // a light (one-warp) evaluation gives up after this many attempts and comes back heavy
+  uint32_t tune_heavy_ctas = 2;    // heavy-form CTAs per SM
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)
   bool tune_score = false;         // K2 score matrix: false = materialised on request (grove_build_score_matrix / the row getters),
                                    // true = every cycle, on the second stream beside the relaxation
@@ -334,7 +338,7 @@ static Relax make_relax(grove_engine* e) {
   r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
   r.shape_bits = e->shape_tables ? e->d_shape_bits.p : nullptr; r.pl_words = e->pl_words;
   for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) r.pl_off[l] = e->pl_off[l];
-  r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u); r.entry = e->tune_entry ? e->tune_entry : r.window;
+  r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u); r.entry = e->tune_entry ? e->tune_entry : r.window; r.heavy_att = e->tune_heavy_att;
   r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
   return r;
 }
@@ -367,8 +371,9 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WARP_CTAS")) e->tune_warp_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_BATCH")) e->tune_batch = uint32_t(std::max(1, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_WARP4")) e->tune_warp4 = uint32_t(std::max(0, std::atoi(v)));
-  if (const char* v = std::getenv("GROVE_TUNE_WARP16")) e->tune_warp16 = uint32_t(std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_HEAVY_ATT")) e->tune_heavy_att = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_MAX_ATT")) e->tune_max_att = uint32_t(std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_HEAVY_CTAS")) e->tune_heavy_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_OVERLAP")) e->tune_overlap = std::atoi(v) != 0;
   if (const char* v = std::getenv("GROVE_TUNE_SCORE")) e->tune_score = std::atoi(v) != 0;
   if (std::getenv("GROVE_DEBUG_ADMIT")) e->dbg_on = true;
@@ -376,9 +381,11 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the latency-bound relaxation gets the SMs first
   if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaStreamCreateWithPriority(&e->stream_score, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&e->stream_heavy, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (cudaEventCreateWithFlags(&e->ev_fit, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_score, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_nodes_up, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_tables_up, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&e->ev_s0) != cudaSuccess || cudaEventCreate(&e->ev_s1) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_ctl.ensure(kCtlWords) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
@@ -398,8 +405,11 @@ void grove_engine_destroy(grove_engine_t* e) {
   if (e->ev_nodes_up) cudaEventDestroy(e->ev_nodes_up);
   if (e->ev_tables_up) cudaEventDestroy(e->ev_tables_up);
   if (e->ev_upd) cudaEventDestroy(e->ev_upd);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_score) cudaEventDestroy(e->ev_score);
   if (e->stream_score) cudaStreamDestroy(e->stream_score);
+  if (e->stream_heavy) cudaStreamDestroy(e->stream_heavy);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -947,7 +957,7 @@ static int32_t finish_cycle(grove_engine* e) {
 
 struct CycleGuard {   // every error exit of a cycle leaves the handle usable (in_cycle stayed set)
   grove_engine* e; bool armed = true;
-  ~CycleGuard() { if (armed) { e->in_cycle = false; cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->stream_score); } }
+  ~CycleGuard() { if (armed) { e->in_cycle = false; cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->stream_score); cudaStreamSynchronize(e->stream_heavy); } }
 };
 
 int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
@@ -983,8 +993,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     const uint32_t W = rx.window;
     const uint32_t per_sm = e->tune_eval_ctas ? e->tune_eval_ctas : 16u;
     const uint32_t eval_ctas = std::max(1u, std::min(W, e->n_sm * per_sm));
-    // rounds with many gangs: a warp per gang; fewer: 4 warps; few: 8 warps per gang (admit.cuh)
-    const uint32_t t4 = e->tune_warp4, t16 = std::min(e->tune_warp16, e->tune_warp4);
+    const uint32_t heavy_ctas = std::max(1u, std::min(W, e->n_sm * e->tune_heavy_ctas));
     const uint32_t warp_ctas = std::max(1u, std::min((W * 32 + 255) / 256, e->n_sm * e->tune_warp_ctas));
     // Rounds are enqueued `batch` at a time without waiting: every kernel returns at once when the cycle is over, so the
     // host only looks at the control words between batches (to rebuild the capacity tables when the settled prefix has
@@ -998,20 +1007,22 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
           CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
         }
         k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
-        // (a form whose range of round sizes this submission cannot reach is not launched at all)
+        // heavy gangs (head of the list) on the second stream, kHeavyWarps warps each; light gangs (tail) a warp each
+        CU_TRY(e, cudaEventRecord(e->ev_fork, e->stream));
+        CU_TRY(e, cudaStreamWaitEvent(e->stream_heavy, e->ev_fork, 0));
         if (e->any_preferred) {
-          if (G >= t4) k_eval<true, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
-          if (G >= t16 && t4 > t16) k_eval<true, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
-          if (t16) k_eval<true, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+          k_eval<true, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
+          k_eval<true, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
         } else {
-          if (G >= t4) k_eval<false, 1><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, t4, kFull);
-          if (G >= t16 && t4 > t16) k_eval<false, 4><<<eval_ctas, 128, 0, e->stream>>>(tp, tb, rx, t16, t4);
-          if (t16) k_eval<false, 8><<<std::max(1u, std::min(eval_ctas, t16)), 256, 0, e->stream>>>(tp, tb, rx, 0, t16);
+          k_eval<false, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
+          k_eval<false, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
         }
+        CU_TRY(e, cudaEventRecord(e->ev_join, e->stream_heavy));
+        CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
         k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
         k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
         k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
-        e->launches += 7;
+        e->launches += 6;
       }
       CU_TRY(e, cudaGetLastError());
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));

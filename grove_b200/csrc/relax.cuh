@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_select(Tables tb, Relax rx) {
   }
   // longest first: a round lasts as long as its slowest evaluation, so the gangs that needed several attempts last
   // time go to the head of the list (CTAs are handed out in list order), the others fill it from the tail
-  const bool heavy = need && rx.last_att[g] >= 3;
+  const bool heavy = need && rx.last_att[g] >= rx.heavy_att;
   const uint32_t bh = __ballot_sync(kFull, heavy), bl = __ballot_sync(kFull, need && !heavy);
   uint32_t base_h = 0, base_l = 0;
   if (lane == 0) {
@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
     const grove_gang_t gg = tb.gangs[g];
     const uint32_t po = tb.ginfo[g].pod_off, rank = tb.ginfo[g].order;
     const uint32_t ot = rx.tstate[g], nt = rx.nxt_tstate[g];
+    if (nt == kEvalDeferred) {   // the light evaluation gave up: no result, the gang is evaluated again (as a heavy one) next round
+      if (lane == 0) { rx.dirty[g] = 1; atomicMin(rx.ctl + kMinDirty, rank); }
+      continue;
+    }
     const uint32_t on = ot == GROVE_GANG_ADMITTED ? rx.cur_n[g] : 0u, nn = nt == GROVE_GANG_ADMITTED ? rx.nxt_n[g] : 0u;
     bool diff = ot != nt || on != nn || rx.cur_info[g] != rx.nxt_info[g] || rx.cur_glo[g] != rx.nxt_glo[g];
     if (!diff) {

@@ -14,4 +14,4 @@ with PlacementEngine(cfg["n_levels"]) as e:
     e.load_nodes(cfg["nodes"]); st = e.run_cycle()
     print(st)
 PY
-GROVE_DEBUG_ADMIT=1 timeout 300 python /tmp/c4one.py 2>&1 | tee gpurun_out/dev_dbg.log | grep "warp 0\|cycle:"
+GROVE_DEBUG_ADMIT=1 timeout 300 python /tmp/c4one.py 2>&1 | tee gpurun_out/dev_dbg.log | grep "warp 0\|cycle:\|packed evals" | cut -c1-330

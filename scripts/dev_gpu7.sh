@@ -26,8 +26,9 @@ with PlacementEngine(cfg["n_levels"]) as e:
 PY
 (
 CHECK=1 TAG="default" timeout 300 python /tmp/c4run.py
-for w in 1 4 8; do TAG="warp_ctas=$w" GROVE_TUNE_WARP_CTAS=$w timeout 120 python /tmp/c4run.py; done
-for en in 768 1536 2048; do TAG="entry=$en" GROVE_TUNE_ENTRY=$en timeout 120 python /tmp/c4run.py; done
+for w in 2 3 6 8; do TAG="heavy_att=$w" GROVE_TUNE_HEAVY_ATT=$w timeout 120 python /tmp/c4run.py; done
+for w in 2 6 0; do TAG="max_att=$w" GROVE_TUNE_MAX_ATT=$w timeout 120 python /tmp/c4run.py; done
+for en in 1536 2048 4096; do TAG="entry=$en" GROVE_TUNE_ENTRY=$en timeout 120 python /tmp/c4run.py; done
 TAG="noscore" GROVE_TUNE_SCORE=0 timeout 120 python /tmp/c4run.py
 ) 2>&1 | tee gpurun_out/dev_sweep5.log
 timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_random_parity_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/dev_tests.log

@@ -189,10 +189,12 @@ def test_c5_churn_matches_oracle_tick_by_tick(built_lib, oracle):
 
 
 @pytest.mark.parametrize("env", [{"GROVE_TUNE_WINDOW": "97"}, {"GROVE_TUNE_REFRESH": "1"}, {"GROVE_TUNE_REFRESH": "1000000"},
-                                 {"GROVE_TUNE_EVAL_CTAS": "1", "GROVE_TUNE_SCORE": "0"}])
+                                 {"GROVE_TUNE_EVAL_CTAS": "1", "GROVE_TUNE_SCORE": "1"}, {"GROVE_TUNE_MAX_ATT": "1", "GROVE_TUNE_HEAVY_ATT": "1"},
+                                 {"GROVE_TUNE_MAX_ATT": "0", "GROVE_TUNE_HEAVY_ATT": "200"}])
 def test_tuning_knobs_never_change_a_result(built_lib, oracle, env):
     """window size, how often the capacity tables are rebuilt (every round / never: the evaluator then leans on the
-    per-node slow path), grid sizes, no score matrix: all must give the oracle's answer."""
+    per-node slow path), grid sizes, the score matrix built beside the relaxation, every gang heavy after one attempt / no gang ever heavy:
+    all must give the oracle's answer."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent('''
         import sys, numpy as np
