@@ -40,6 +40,7 @@ struct GangShared {
   uint16_t ent_meta[GROVE_MAX_GANG_PODS];  // clique_rel
   uint32_t Hlo[GROVE_MAX_GANG_CLIQUES], Hhi[GROVE_MAX_GANG_CLIQUES];
   uint32_t s_lo[GROVE_MAX_GANG_SCOPES];
+  float4 rcp[GROVE_MAX_GANG_CLIQUES];      // 1 / request per resource (0 where nothing is requested)
   int8_t c_got[GROVE_MAX_GANG_CLIQUES];    // level each clique / scope was packed at (-1: the whole cluster)
   int8_t s_got[GROVE_MAX_GANG_SCOPES];
 };
@@ -111,6 +112,19 @@ __device__ __forceinline__ uint32_t cap_from(uint32_t cpu, uint32_t mem, uint32_
   return c;
 }
 
+// floor(x / d) for the staged evaluator, exact below 256 and >= 256 above (callers never ask for more than 255 pods);
+// r = 1.0f / d.  Branch-free so that the three resources -- and the nodes a lane handles -- overlap: the estimate is
+// within one of the quotient (relative error of the product < 2^-22, quotients < 257), one signed remainder fixes it.
+__device__ __forceinline__ uint32_t div_rcp(uint32_t x, uint32_t d, float r) {
+  uint32_t q = __float2uint_rz(fminf(__uint2float_rz(x) * r, 256.0f));
+  const long long rem = (long long)x - (long long)((unsigned long long)q * d);
+  q += uint32_t(rem >= (long long)d) - uint32_t(rem < 0);
+  return d ? q : 0xFFFFu;
+}
+__device__ __forceinline__ uint32_t cap_from_rcp(uint32_t cpu, uint32_t mem, uint32_t gpu, uint32_t pods, const uint4& q, const float4& r) {
+  return min(min(div_rcp(cpu, q.x, r.x), div_rcp(mem, q.y, r.y)), min(div_rcp(gpu, q.z, r.z), pods));
+}
+
 // position of node n in the gang's node visiting order (descending closeness to the anchor, ties by ascending
 // rotated index): the anchor's deepest domain from the anchor upwards, then its lower part, then ring by ring
 __device__ __forceinline__ uint32_t visit_pos(const GangRegs& g, uint32_t n) {
@@ -179,6 +193,7 @@ struct Ev {
     return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
   }
 
+  __device__ __forceinline__ uint32_t scope_filter(const grove_scope_t&, uint32_t, uint32_t, bool, int) { return kFull; }   // staged evaluator only
   __device__ __forceinline__ void note_read(uint32_t last) { ext = max(ext, visit_pos(g, last) + 1u); }
   __device__ __forceinline__ void begin(uint32_t, uint32_t) { np = 0; tmask = 0; }       // a fresh attempt
   __device__ __forceinline__ void rollback(uint32_t mark) { np = mark; }               // drop the pods placed after mark
@@ -276,51 +291,86 @@ struct EvS {
   static constexpr bool kPref = kPref_;
   static constexpr bool kStaged = true;   // node state in shared memory: an attempt costs less than the table look-ups that would skip it
   const Topo& tp; const Relax& rb; GangShared& sh; const GangRegs& g; uint32_t lane;
-  uint4* view;          // [kStageMax] cpu, mem, gpu | pods << 16, node flags | vdepth << 16
+  int4* view;           // [kStageMax] cpu, mem, gpu, pods the gang may still take.  Signed: the claims of lower ranks may transiently exceed
+                        // the committed state (saturating subtraction claim by claim == clamping the sum at zero when it is read)
+  uint32_t* vflag;      // [kStageMax] node flags | vdepth << 16
+  uint8_t* rk;          // [kStageMax + 256] sub-domain filter scratch: the sub-domain (lane) each staged node belongs to, then
+                        // per-sub-domain sum and max (32 words each) of the pods of ONE clique that fit
   uint32_t t_stage = 0, t_pre = 0, t_pack = 0, n_stage = 0;   // GROVE_DEBUG_ADMIT: cycles staging / pre-filtering sub-domains / packing
   uint32_t vlo = 0, vhi = 0;
   uint32_t np;
   uint32_t tmask = 0;
   uint32_t ext = 0;
-  __device__ EvS(const Topo& t, const Relax& r, GangShared& s, const GangRegs& gr, uint32_t ln, uint4* v)
-      : tp(t), rb(r), sh(s), g(gr), lane(ln), view(v), np(0) {}
+  __device__ EvS(const Topo& t, const Relax& r, GangShared& s, const GangRegs& gr, uint32_t ln, int4* v, uint32_t* vf, uint8_t* cv)
+      : tp(t), rb(r), sh(s), g(gr), lane(ln), view(v), vflag(vf), rk(cv), np(0) {}
 
+  __device__ __forceinline__ void sub_claim(uint32_t n, const uint4& c) {
+    int* v = reinterpret_cast<int*>(view + (n - vlo));
+    if (c.y) atomicSub(v + 0, int(c.y));
+    if (c.z) atomicSub(v + 1, int(c.z));
+    if (c.w & 0xFFFFu) atomicSub(v + 2, int(c.w & 0xFFFFu));
+    atomicSub(v + 3, int(c.w >> 16));
+  }
+
+  // Stage the gang's view of [dl, dh): committed record minus the claims of the ranks before it.
+  //   1. the node records, a lane per node (coalesced 16 B loads), written to shared memory;
+  //   2. the claim lines of the 4-node groups somebody leans on (one byte per node says so): the whole warp reads four
+  //      lines per load instruction -- lane = (node of the group, slot), 512 contiguous bytes --, several groups in
+  //      flight, and every claim of a lower rank is subtracted from its node with a shared-memory atomic.
+  // One L2 round trip for the records and the claim counters, one for all the claim lines.
   __device__ GROVE_NI void begin(uint32_t dl, uint32_t dh) {
     np = 0; vlo = dl; vhi = dh;
     const long long tb0 = rb.dbg ? clock64() : 0;
     __syncwarp();
     constexpr uint32_t kPer = kStageMax / 32;
-    // phase 1: node records and claim counters of the whole range, every load independent of the others
-    uint4 r[kPer]; uint32_t live[kPer];
+    const uint32_t w0 = dl >> 2, w1 = (dh - 1u) >> 2;   // nlive words (4 nodes each) that overlap the range: at most 33
+    // every claim line of the range is asked into L1 right away (no register, no wait): by the time the claim counters say
+    // which ones matter, they are there, and step 2 costs L1 hits instead of one more L2 round trip per trip
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
       const uint32_t n = dl + k * 32u + lane;
-      const bool in = n < dh;
-      r[k] = in ? __ldg(tp.nres + n) : make_uint4(0, 0, 0, 0);
-      live[k] = in ? (__ldg(rb.nlive + (n >> 2)) >> ((n & 3u) * 8u)) & 0xFFu : 0u;
+      if (n < dh) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb.claims + size_t(n) * kClaimSlots));
     }
-    // phase 2: the claim lines of the claimed nodes (again independent loads), then the rare overflow chains
+    const uint32_t lv0 = w0 + lane <= w1 ? __ldg(rb.nlive + w0 + lane) : 0u;
+    uint4 r[kPer];
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
       const uint32_t n = dl + k * 32u + lane;
-      if (n >= dh) continue;
-      uint32_t cpu = r[k].x, mem = r[k].y, gpu = r[k].z & 0xFFFFu, pods = r[k].z >> 16;
-      if (live[k] & 0x3Fu) {
-        const uint4* line = rb.claims + size_t(n) * kClaimSlots;
-        uint4 c[kClaimSlots];
+      r[k] = n < dh ? __ldg(tp.nres + n) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-        for (uint32_t s = 0; s < kClaimSlots; ++s) c[s] = __ldg(line + s);
+    for (uint32_t k = 0; k < kPer; ++k) {
+      view[k * 32u + lane] = make_int4(int(r[k].x), int(r[k].y), int(r[k].z & 0xFFFFu), int(r[k].z >> 16));
+      vflag[k * 32u + lane] = r[k].w;
+    }
+    __syncwarp();
+    for (uint32_t wb = w0; wb <= w1; wb += 32) {
+      const uint32_t w = wb + lane;
+      const uint32_t lv = wb == w0 ? lv0 : (w <= w1 ? __ldg(rb.nlive + w) : 0u);
+      uint32_t m = __ballot_sync(kFull, (lv & 0x3F3F3F3Fu) != 0u);
+      while (m) {   // warp-uniform: four groups (16 claim lines) per trip
+        uint32_t nd[4]; uint4 c[4];
 #pragma unroll
-        for (uint32_t s = 0; s < kClaimSlots; ++s)
-          if (c[s].x < g.rank) { cpu -= min(cpu, c[s].y); mem -= min(mem, c[s].z); gpu -= min(gpu, c[s].w & 0xFFFFu); pods -= min(pods, c[s].w >> 16); }
+        for (int u = 0; u < 4; ++u) {
+          nd[u] = GROVE_NONE_U32;
+          if (m) { const uint32_t b = __ffs(m) - 1; m &= m - 1; nd[u] = ((wb + b) << 2) + (lane >> 3); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          c[u] = (nd[u] >= dl && nd[u] < dh) ? __ldg(rb.claims + size_t(nd[u]) * kClaimSlots + (lane & 7u)) : make_uint4(kClaimEmpty, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c[u].x < g.rank) sub_claim(nd[u], c[u]);
       }
-      if (live[k] & kHasOvf) {
+      // more than kClaimSlots gangs leaned on a node at some point: its overflow chain (rare)
+      for (uint32_t ov = lv & 0x40404040u; ov; ov &= ov - 1) {
+        const uint32_t n = (w << 2) + ((__ffs(ov) - 1u) >> 3);
+        if (n < dl || n >= dh) continue;
         for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
           const uint4 c = __ldg(rb.ovf_claim + i - 1);
-          if (c.x < g.rank) { cpu -= min(cpu, c.y); mem -= min(mem, c.z); gpu -= min(gpu, c.w & 0xFFFFu); pods -= min(pods, c.w >> 16); }
+          if (c.x < g.rank) sub_claim(n, c);
         }
       }
-      view[k * 32u + lane] = make_uint4(cpu, mem, gpu | (pods << 16), r[k].w);
     }
     __syncwarp();
     // the whole range has been read: it ends at the furthest position any of its nodes has in the visiting order
@@ -329,10 +379,48 @@ struct EvS {
   }
 
   __device__ __forceinline__ uint32_t cap(uint32_t cr, uint32_t n) const {
-    const uint4 v = view[n - vlo];
+    const int4 v = view[n - vlo];
+    const uint32_t f = vflag[n - vlo];
     const uint32_t sm = sh.smask[cr];
-    if (!(v.w & GROVE_NODE_SCHEDULABLE) || !((sm >> ((v.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) & 1u) || ((v.w >> 16) & 0xFu) < (sm >> 16)) return 0u;
-    return cap_from(v.x, v.y, v.z & 0xFFFFu, v.z >> 16, sh.clq[cr]);
+    const bool usable = (f & GROVE_NODE_SCHEDULABLE) && ((sm >> ((f >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) & 1u) && ((f >> 16) & 0xFu) >= (sm >> 16);
+    const uint32_t c = cap_from_rcp(uint32_t(max(v.x, 0)), uint32_t(max(v.y, 0)), uint32_t(max(v.z, 0)), uint32_t(max(v.w, 0)), sh.clq[cr], sh.rcp[cr]);
+    return usable ? c : 0u;
+  }
+
+  // Sub-domain filter on the staged view: which of the (at most 32) level-sl domains [el, eh) -- a lane each -- could take
+  // every clique of scope s on its own?  A necessary condition like the table look-ups of scope_plausible, but against what
+  // the gang really sees (the tables only know the committed state as of their last build): a candidate whose racks are
+  // taken by lower ranks' claims fails here instead of after an attempt per rack.
+  __device__ GROVE_NI uint32_t scope_filter(const grove_scope_t& s, uint32_t el, uint32_t eh, bool in, int sl) {
+    constexpr uint32_t kPer = kStageMax / 32;
+    uint32_t* rsum = reinterpret_cast<uint32_t*>(rk + kStageMax);
+    uint32_t* rmax = rsum + 32;
+    bool ok = in;
+    el = max(el, vlo); eh = min(eh, vhi);
+    __syncwarp();
+    reinterpret_cast<uint32_t*>(rk)[lane] = kFull;             // a node that lacks the label is in no sub-domain
+    __syncwarp();
+    if (in) for (uint32_t n = el; n < eh; ++n) rk[n - vlo] = uint8_t(lane);   // (stores: nothing waits on them)
+    for (uint32_t i = 0; i < s.n_cliques; ++i) {
+      const uint32_t cr = s.first_clique + i;
+      const uint32_t w = sh.clq[cr].w;
+      const uint32_t m = w & 0xFFu, ql = (w >> 16) & 0xFFu;
+      if (m == 0) continue;
+      rsum[lane] = 0; rmax[lane] = 0;
+      __syncwarp();
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t idx = k * 32u + lane;
+        const uint32_t c = vlo + idx < vhi ? cap(cr, vlo + idx) : 0u;
+        const uint32_t slot = rk[idx];
+        if (c && slot != 0xFFu) { atomicAdd(rsum + slot, c); atomicMax(rmax + slot, c); }
+      }
+      __syncwarp();
+      const bool one_node = ql != GROVE_LEVEL_NONE && int(ql) > sl && tp.unit[ql];   // all m pods on one node
+      ok = ok && (one_node ? rmax[lane] >= m : rsum[lane] >= m);
+      __syncwarp();
+    }
+    return __ballot_sync(kFull, ok);
   }
 
   // give back the pods placed after mark
@@ -340,10 +428,11 @@ struct EvS {
     __syncwarp();
     for (uint32_t i = mark + lane; i < np; i += 32) {
       const uint4 q = sh.clq[sh.ent_meta[i]];
-      uint32_t* v = reinterpret_cast<uint32_t*>(view + (sh.ent_node[i] - vlo));
-      if (q.x) atomicAdd(v + 0, q.x);
-      if (q.y) atomicAdd(v + 1, q.y);
-      atomicAdd(v + 2, q.z + (1u << 16));
+      int* v = reinterpret_cast<int*>(view + (sh.ent_node[i] - vlo));
+      if (q.x) atomicAdd(v + 0, int(q.x));
+      if (q.y) atomicAdd(v + 1, int(q.y));
+      if (q.z) atomicAdd(v + 2, int(q.z));
+      atomicAdd(v + 3, 1);
     }
     np = mark;
     __syncwarp();
@@ -358,14 +447,15 @@ struct EvS {
       for (uint32_t base = a & ~31u; base < b && placed < want; base += 32) {
         const uint32_t n = base + lane;
         const uint32_t c = (n >= a && n < b) ? cap(cr, n) : 0u;
+        if (!__any_sync(kFull, c != 0u)) continue;
         const uint32_t incl = warp_incl_scan(c, lane), excl = incl - c, rem = want - placed;
         const uint32_t t = excl >= rem ? 0u : min(c, rem - excl);
         const uint32_t tincl = warp_incl_scan(t, lane);
         if (t) {
           const uint32_t pos = np + tincl - t;
           for (uint32_t j = 0; j < t; ++j) { sh.ent_node[pos + j] = n; sh.ent_meta[pos + j] = uint16_t(cr); }
-          uint4 v = view[n - vlo];
-          v.x -= t * q.x; v.y -= t * q.y; v.z -= t * q.z + (t << 16);
+          int4 v = view[n - vlo];
+          v.x -= int(t * q.x); v.y -= int(t * q.y); v.z -= int(t * q.z); v.w -= int(t);
           view[n - vlo] = v;
         }
         const uint32_t tot = __shfl_sync(kFull, tincl, 31);
@@ -400,8 +490,8 @@ struct EvS {
           for (uint32_t j = lane; j < m; j += 32) { sh.ent_node[np + j] = nn; sh.ent_meta[np + j] = uint16_t(cr); }
           if (lane == 0) {
             sh.Hlo[cr] = nn; sh.Hhi[cr] = nn + 1;
-            uint4 v = view[nn - vlo];
-            v.x -= m * q.x; v.y -= m * q.y; v.z -= m * q.z + (m << 16);
+            int4 v = view[nn - vlo];
+            v.x -= int(m * q.x); v.y -= int(m * q.y); v.z -= int(m * q.z); v.w -= int(m);
             view[nn - vlo] = v;
           }
           np += m;
@@ -528,7 +618,37 @@ __device__ GROVE_NI bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32
     const int base = level_span<Ev::kPref>(s.level, s.preferred1 ? uint32_t(s.preferred1) - 1u : uint32_t(GROVE_LEVEL_NONE), lvl, first);
     int sl = first;
     do {
-      if (sl > lvl) {
+      bool filtered = false;
+      if constexpr (Ev::kStaged) {
+        if (sl > lvl) {
+          // the staged range holds at most kStageMax nodes: usually all its level-sl domains fit one warp pass.  A lane each:
+          // filter them ONCE against the staged view, then attempt the survivors in visiting order (piece by piece, ascending
+          // inside a piece -- the order of the general walk below)
+          const uint32_t d0 = __ldg(tp.next_dom[sl] + lo), d1 = __ldg(tp.next_dom[sl] + hi);
+          if (d1 - d0 <= 32u) {
+            filtered = true;
+            const long long tp0 = ev.rb.dbg ? clock64() : 0;
+            const bool in = d0 + ev.lane < d1;
+            uint32_t el = 0, eh = 0;
+            if (in) { el = __ldg(tp.dom_lo[sl] + d0 + ev.lane); eh = __ldg(tp.dom_hi[sl] + d0 + ev.lane); }
+            const uint32_t plaus = ev.scope_filter(s, el, eh, in, sl);
+            const long long tp1 = ev.rb.dbg ? clock64() : 0;
+            PieceIt pit; pit.init(ev.g, lo, hi, uint32_t(sl));
+            for (uint32_t pa, pb; !ok && plaus && pit.next(ev.g, pa, pb);) {
+              uint32_t todo = plaus & __ballot_sync(kFull, in && el >= pa && el < pb);
+              while (todo && !ok) {
+                const uint32_t src = __ffs(todo) - 1; todo &= todo - 1;
+                const uint32_t l0 = __shfl_sync(kFull, el, src), h0 = __shfl_sync(kFull, eh, src);
+                ok = place_scope(ev, s, l0, h0, sl);
+                if (ok && ev.lane == 0) ev.sh.s_lo[si] = l0;
+              }
+            }
+            if (ev.rb.dbg) { ev.t_pre += uint32_t(tp1 - tp0); ev.t_pack += uint32_t(clock64() - tp1); }
+          }
+        }
+      }
+      if (filtered) {
+      } else if (sl > lvl) {
         PieceIt pit; pit.init(ev.g, lo, hi, uint32_t(sl));
         for (uint32_t pa, pb; !ok && pit.next(ev.g, pa, pb);) {
           const uint32_t d0 = __ldg(tp.next_dom[sl] + pa), d1 = __ldg(tp.next_dom[sl] + pb);
@@ -621,9 +741,11 @@ __device__ __forceinline__ uint32_t eval_list_at(const Relax& rx, uint32_t G, ui
 constexpr uint32_t kEvalDeferred = 0xFFu;   // nxt_tstate: no result this round
 constexpr int kHeavyWarps = 8;
 template <bool kPref, int kW, bool kHeavy>
-__global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, uint32_t max_att) {
+__global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tables tb, Relax rx, uint32_t max_att) {
   __shared__ GangShared shs[kW];
-  __shared__ uint4 s_view[kW][kStageMax];
+  __shared__ int4 s_view[kW][kStageMax];
+  __shared__ uint32_t s_vflag[kW][kStageMax];
+  __shared__ __align__(16) uint8_t s_rk[kW][kStageMax + 256];
   __shared__ uint32_t s_plaus[32];   // plausible candidates of the current 1024-candidate chunk, in order
   __shared__ uint32_t s_win, s_ext, s_att, s_npl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -664,6 +786,8 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
       sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
                              uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16) |
                                  (GROVE_CLIQUE_PREFERRED(q.scope) << 24));
+      sh.rcp[c] = make_float4(q.req_cpu_milli ? 1.0f / float(q.req_cpu_milli) : 0.f, q.req_mem_mib ? 1.0f / float(q.req_mem_mib) : 0.f,
+                              q.req_gpu ? 1.0f / float(q.req_gpu) : 0.f, 0.f);
       sh.sig[c] = ci.sig; sh.smask[c] = uint32_t(q.class_mask) | (ci.need_depth << 16);
       sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.c_got[c] = -1;
     }
@@ -677,7 +801,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
     const uint32_t round_now = rx.ctl[kRound];
     const uint32_t le = rx.last_eval[gi];
     Ev<kPref> ev(tp, rx, sh, g, lane);                         // candidates of any size, node state from L2
-    EvS<kPref> evs(tp, rx, sh, g, lane, s_view[warp]);         // candidates of <= kStageMax nodes, node state staged in shared memory
+    EvS<kPref> evs(tp, rx, sh, g, lane, s_view[warp], s_vflag[warp], s_rk[warp]);         // candidates of <= kStageMax nodes, node state staged in shared memory
     bool staged = false;  // the winning attempt ran on evs
     bool won = false;     // this warp holds the answer
     bool done = false;    // CTA-uniform
@@ -722,8 +846,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
         // candidates are taken in chunks that grow (kW x 32, then up to 1024): most gangs succeed among the first few
         for (uint32_t base = 0, nchunk = kW; base < D && !done && !gave_up; base += nchunk * 32, nchunk = min(32u, nchunk * 4u)) {
           // pre-filter: nchunk runs of 32 candidates, dealt to the warps
-          for (uint32_t c = warp; c < 32; c += kW) {
-            if (c >= nchunk) { if (lane == 0) s_plaus[c] = 0; continue; }
+          for (uint32_t c = warp; c < nchunk; c += kW) {
             const uint32_t k = base + c * 32 + lane;
             bool plaus = false;
             if (k < D) {
@@ -748,8 +871,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
           }
           __syncthreads();
           uint32_t total = 0;
-#pragma unroll 4
-          for (uint32_t c = 0; c < 32; ++c) total += __popc(s_plaus[c]);
+          for (uint32_t c = 0; c < nchunk; ++c) total += __popc(s_plaus[c]);
           if (threadIdx.x == 0) s_npl += total;
           // attempts: kW plausible candidates at a time, in order, a warp each
           // while a round has many gangs the very first candidate is attempted by one warp alone: it usually succeeds,
@@ -760,7 +882,7 @@ __global__ void __launch_bounds__(kW * 32) k_eval(Topo tp, Tables tb, Relax rx, 
             bool ok = false; uint32_t dl = 0, dh = 0;
             if (j < total) {
               uint32_t rem = j, c = 0;   // the j-th set bit of the bitmap
-              for (; c < 32; ++c) { const uint32_t pc = __popc(s_plaus[c]); if (rem < pc) break; rem -= pc; }
+              for (; c + 1 < nchunk; ++c) { const uint32_t pc = __popc(s_plaus[c]); if (rem < pc) break; rem -= pc; }
               uint32_t w = s_plaus[c];
               for (uint32_t i = 0; i < rem; ++i) w &= w - 1;
               const uint32_t k = base + c * 32 + (__ffs(w) - 1);

@@ -1,0 +1,33 @@
+#!/bin/bash
+# dev loop: C4 timing (best of 6) + identity with the oracle, per-phase debug statistics, the parity tests
+cd "$GRAFT_REPO_ROOT" || exit 1
+export PYTHONPATH="$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+cat > /tmp/c4run.py <<'PY'
+import numpy as np, time, os, sys
+from grove_b200 import synth
+from grove_b200.engine import PlacementEngine
+from oracle import oracle_py as O
+cfg = synth.config_c4()
+g, c, s = cfg["tables"]
+ref = None
+if os.environ.get("CHECK"):
+    ref = O.run_cycle(cfg["nodes"], cfg["n_levels"], g, c, s, threads=16)
+with PlacementEngine(cfg["n_levels"]) as e:
+    e.load_nodes(cfg["nodes"]); e.submit_gangs(g, c, s)
+    best = None
+    for i in range(int(os.environ.get("REPS", "6"))):
+        e.load_nodes(cfg["nodes"])
+        st = e.run_cycle()
+        if best is None or st["ms_total"] < best["ms_total"]: best = st
+    st = best
+    print(os.environ.get("TAG", ""), {k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items() if k in ("rounds", "evaluations", "ms_fit", "ms_admit", "ms_total")}, flush=True)
+    if ref is not None:
+        print("identical:", np.array_equal(e.placements(), ref["placements"]), np.array_equal(e.gang_status(), ref["status"]), np.array_equal(e.scope_domains(), ref["scope_status"]), np.array_equal(e.nodes(), ref["nodes_after"]), flush=True)
+PY
+(
+CHECK=1 TAG="default" timeout 300 python /tmp/c4run.py
+for spec in $SWEEP; do TAG="$spec" env ${spec//,/ } timeout 120 python /tmp/c4run.py; done
+REPS=2 GROVE_DEBUG_ADMIT=1 timeout 300 python /tmp/c4run.py 2>&1 | grep "warp 0\|cycle:\|packed evals" | cut -c1-360 | tail -${DBG_LINES:-4}
+) 2>&1 | tee gpurun_out/s2_dev.log
+if [ -z "$NOTESTS" ]; then timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/s2_dev_tests.log; fi
