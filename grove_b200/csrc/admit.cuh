@@ -165,32 +165,36 @@ struct Ev {
     const uint4 r = __ldg(tp.nres + n);
     const uint32_t sm = sh.smask[cr];
     if (!(r.w & GROVE_NODE_SCHEDULABLE) || !((sm >> ((r.w >> GROVE_NODE_CLASS_SHIFT) & 0xFu)) & 1u) || ((r.w >> 16) & 0xFu) < (sm >> 16)) return 0u;
-    uint32_t cpu = r.x, mem = r.y, gpu = r.z & 0xFFFFu, pods = r.z >> 16;
-    if (live & 0x3Fu) {   // claims of the gangs that rank before this one
-      const uint4* line = rb.claims + size_t(n) * kClaimSlots;
+    int cpu = int(r.x), mem = int(r.y), gpu = int(r.z & 0xFFFFu), pods = int(r.z >> 16);
+    if (live & 0x7Fu) {   // claims: all of them, minus those of the gangs that rank after this one (see EvS::begin)
+      const int4 t = __ldg(rb.ctot + n);
+      cpu -= t.x; mem -= t.y; gpu -= t.z; pods -= t.w;
+      if (__ldg(rb.cmaxr + n) >= g.rank) {
+        if (live & 0x3Fu) {
+          const uint4* line = rb.claims + size_t(n) * kClaimSlots;
 #pragma unroll
-      for (uint32_t s = 0; s < kClaimSlots; ++s) {
-        const uint4 c = __ldg(line + s);
-        if (c.x < g.rank) {
-          cpu -= min(cpu, c.y); mem -= min(mem, c.z); gpu -= min(gpu, c.w & 0xFFFFu); pods -= min(pods, c.w >> 16);
+          for (uint32_t s = 0; s < kClaimSlots; ++s) {
+            const uint4 c = __ldg(line + s);
+            if (c.x >= g.rank && c.x != kClaimEmpty) { cpu += int(c.y); mem += int(c.z); gpu += int(c.w & 0xFFFFu); pods += int(c.w >> 16); }
+          }
         }
-      }
-    }
-    if (live & kHasOvf) {   // more than kClaimSlots gangs leaned on this node at some point: its overflow chain
-      for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
-        const uint4 c = __ldg(rb.ovf_claim + i - 1);
-        if (c.x < g.rank) { cpu -= min(cpu, c.y); mem -= min(mem, c.z); gpu -= min(gpu, c.w & 0xFFFFu); pods -= min(pods, c.w >> 16); }
+        if (live & kHasOvf) {
+          for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
+            const uint4 c = __ldg(rb.ovf_claim + i - 1);
+            if (c.x >= g.rank && c.x != kClaimEmpty) { cpu += int(c.y); mem += int(c.z); gpu += int(c.w & 0xFFFFu); pods += int(c.w >> 16); }
+          }
+        }
       }
     }
     if (own) {
       for (uint32_t i = 0; i < np; ++i) {
         if (sh.ent_node[i] == n) {
           const uint4 o = sh.clq[sh.ent_meta[i]];
-          cpu -= min(cpu, o.x); mem -= min(mem, o.y); gpu -= min(gpu, o.z); pods -= min(pods, 1u);
+          cpu -= int(o.x); mem -= int(o.y); gpu -= int(o.z); pods -= 1;
         }
       }
     }
-    return cap_from(cpu, mem, gpu, pods, sh.clq[cr]);
+    return cap_from(uint32_t(max(cpu, 0)), uint32_t(max(mem, 0)), uint32_t(max(gpu, 0)), uint32_t(max(pods, 0)), sh.clq[cr]);
   }
 
   __device__ __forceinline__ uint32_t scope_filter(const grove_scope_t&, uint32_t, uint32_t, bool, int) { return kFull; }   // staged evaluator only
@@ -297,6 +301,7 @@ struct EvS {
   uint8_t* rk;          // [kStageMax + 256] sub-domain filter scratch: the sub-domain (lane) each staged node belongs to, then
                         // per-sub-domain sum and max (32 words each) of the pods of ONE clique that fit
   uint32_t t_stage = 0, t_pre = 0, t_pack = 0, n_stage = 0;   // GROVE_DEBUG_ADMIT: cycles staging / pre-filtering sub-domains / packing
+  uint32_t t_st2 = 0, t_st3 = 0;                              // of the staging: claim lines, overflow chains
   uint32_t vlo = 0, vhi = 0;
   uint32_t np;
   uint32_t tmask = 0;
@@ -304,78 +309,55 @@ struct EvS {
   __device__ EvS(const Topo& t, const Relax& r, GangShared& s, const GangRegs& gr, uint32_t ln, int4* v, uint32_t* vf, uint8_t* cv)
       : tp(t), rb(r), sh(s), g(gr), lane(ln), view(v), vflag(vf), rk(cv), np(0) {}
 
-  __device__ __forceinline__ void sub_claim(uint32_t n, const uint4& c) {
-    int* v = reinterpret_cast<int*>(view + (n - vlo));
-    if (c.y) atomicSub(v + 0, int(c.y));
-    if (c.z) atomicSub(v + 1, int(c.z));
-    if (c.w & 0xFFFFu) atomicSub(v + 2, int(c.w & 0xFFFFu));
-    atomicSub(v + 3, int(c.w >> 16));
-  }
-
-  // Stage the gang's view of [dl, dh): committed record minus the claims of the ranks before it.
-  //   1. the node records, a lane per node (coalesced 16 B loads), written to shared memory;
-  //   2. the claim lines of the 4-node groups somebody leans on (one byte per node says so): the whole warp reads four
-  //      lines per load instruction -- lane = (node of the group, slot), 512 contiguous bytes --, several groups in
-  //      flight, and every claim of a lower rank is subtracted from its node with a shared-memory atomic.
-  // One L2 round trip for the records and the claim counters, one for all the claim lines.
+  // Stage the gang's view of [dl, dh): committed record minus the claims of the ranks before it.  A lane per node, four nodes a
+  // lane, ONE L2 round trip for almost every node: the record, the node's claim TOTAL (all ranks) and the highest rank that ever
+  // claimed it (relax.cuh ctot / cmaxr).  Gangs enter the window in rank order, so for most evaluations every claim on a node is
+  // of a lower rank and the view is record - total.  Only where a HIGHER rank may lean on the node (cmaxr >= rank) are its claim
+  // line and overflow chain read, to give those claims back.
   __device__ GROVE_NI void begin(uint32_t dl, uint32_t dh) {
     np = 0; vlo = dl; vhi = dh;
     const long long tb0 = rb.dbg ? clock64() : 0;
     __syncwarp();
     constexpr uint32_t kPer = kStageMax / 32;
-    const uint32_t w0 = dl >> 2, w1 = (dh - 1u) >> 2;   // nlive words (4 nodes each) that overlap the range: at most 33
-    // every claim line of the range is asked into L1 right away (no register, no wait): by the time the claim counters say
-    // which ones matter, they are there, and step 2 costs L1 hits instead of one more L2 round trip per trip
+    uint4 r[kPer]; int4 t[kPer]; uint32_t live[kPer], mr[kPer];
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
       const uint32_t n = dl + k * 32u + lane;
-      if (n < dh) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb.claims + size_t(n) * kClaimSlots));
+      const bool in = n < dh;
+      r[k] = in ? __ldg(tp.nres + n) : make_uint4(0, 0, 0, 0);
+      t[k] = in ? __ldg(rb.ctot + n) : make_int4(0, 0, 0, 0);
+      mr[k] = in ? __ldg(rb.cmaxr + n) : 0u;
+      live[k] = in ? (__ldg(rb.nlive + (n >> 2)) >> ((n & 3u) * 8u)) & 0x7Fu : 0u;
     }
-    const uint32_t lv0 = w0 + lane <= w1 ? __ldg(rb.nlive + w0 + lane) : 0u;
-    uint4 r[kPer];
+    const long long tc0 = rb.dbg ? clock64() : 0;
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
       const uint32_t n = dl + k * 32u + lane;
-      r[k] = n < dh ? __ldg(tp.nres + n) : make_uint4(0, 0, 0, 0);
-    }
+      int cpu = int(r[k].x) - t[k].x, mem = int(r[k].y) - t[k].y, gpu = int(r[k].z & 0xFFFFu) - t[k].z, pods = int(r[k].z >> 16) - t[k].w;
+      if (live[k] && mr[k] >= g.rank) {   // a gang of a higher rank may hold a claim here: it is invisible to this one
+        if (live[k] & 0x3Fu) {
+          const uint4* line = rb.claims + size_t(n) * kClaimSlots;
+          uint4 c[kClaimSlots];
 #pragma unroll
-    for (uint32_t k = 0; k < kPer; ++k) {
-      view[k * 32u + lane] = make_int4(int(r[k].x), int(r[k].y), int(r[k].z & 0xFFFFu), int(r[k].z >> 16));
+          for (uint32_t s = 0; s < kClaimSlots; ++s) c[s] = __ldg(line + s);
+#pragma unroll
+          for (uint32_t s = 0; s < kClaimSlots; ++s)
+            if (c[s].x >= g.rank && c[s].x != kClaimEmpty) { cpu += int(c[s].y); mem += int(c[s].z); gpu += int(c[s].w & 0xFFFFu); pods += int(c[s].w >> 16); }
+        }
+        if (live[k] & kHasOvf) {
+          for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
+            const uint4 c = __ldg(rb.ovf_claim + i - 1);
+            if (c.x >= g.rank && c.x != kClaimEmpty) { cpu += int(c.y); mem += int(c.z); gpu += int(c.w & 0xFFFFu); pods += int(c.w >> 16); }
+          }
+        }
+      }
+      view[k * 32u + lane] = make_int4(cpu, mem, gpu, pods);
       vflag[k * 32u + lane] = r[k].w;
-    }
-    __syncwarp();
-    for (uint32_t wb = w0; wb <= w1; wb += 32) {
-      const uint32_t w = wb + lane;
-      const uint32_t lv = wb == w0 ? lv0 : (w <= w1 ? __ldg(rb.nlive + w) : 0u);
-      uint32_t m = __ballot_sync(kFull, (lv & 0x3F3F3F3Fu) != 0u);
-      while (m) {   // warp-uniform: four groups (16 claim lines) per trip
-        uint32_t nd[4]; uint4 c[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          nd[u] = GROVE_NONE_U32;
-          if (m) { const uint32_t b = __ffs(m) - 1; m &= m - 1; nd[u] = ((wb + b) << 2) + (lane >> 3); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          c[u] = (nd[u] >= dl && nd[u] < dh) ? __ldg(rb.claims + size_t(nd[u]) * kClaimSlots + (lane & 7u)) : make_uint4(kClaimEmpty, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (c[u].x < g.rank) sub_claim(nd[u], c[u]);
-      }
-      // more than kClaimSlots gangs leaned on a node at some point: its overflow chain (rare)
-      for (uint32_t ov = lv & 0x40404040u; ov; ov &= ov - 1) {
-        const uint32_t n = (w << 2) + ((__ffs(ov) - 1u) >> 3);
-        if (n < dl || n >= dh) continue;
-        for (uint32_t i = __ldg(rb.ovf_head + n); i; i = __ldg(rb.ovf_next + i - 1)) {
-          const uint4 c = __ldg(rb.ovf_claim + i - 1);
-          if (c.x < g.rank) sub_claim(n, c);
-        }
-      }
     }
     __syncwarp();
     // the whole range has been read: it ends at the furthest position any of its nodes has in the visiting order
     ext = max(ext, (g.a >= dl && g.a < dh) ? dh - dl : visit_pos(g, dh - 1u) + 1u);
-    if (rb.dbg) { t_stage += uint32_t(clock64() - tb0); ++n_stage; }
+    if (rb.dbg) { const long long te = clock64(); t_stage += uint32_t(te - tb0); t_st2 += uint32_t(tc0 - tb0); t_st3 += uint32_t(te - tc0); ++n_stage; }
   }
 
   __device__ __forceinline__ uint32_t cap(uint32_t cr, uint32_t n) const {
@@ -915,6 +897,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
       // warp 0's own phases, summed over the cycle: staging, sub-domain pre-filter, packing, attempts staged
       atomicAdd(rx.dbg + tb.G * 8 + 0, evs.t_stage); atomicAdd(rx.dbg + tb.G * 8 + 1, evs.t_pre); atomicAdd(rx.dbg + tb.G * 8 + 2, evs.t_pack);
       atomicAdd(rx.dbg + tb.G * 8 + 3, evs.n_stage); atomicAdd(rx.dbg + tb.G * 8 + 4, cyc); atomicAdd(rx.dbg + tb.G * 8 + 5, 1u);
+      atomicAdd(rx.dbg + tb.G * 8 + 6, evs.t_st2); atomicAdd(rx.dbg + tb.G * 8 + 7, evs.t_st3);
     }
     if (!done) {
       if (threadIdx.x == 0) {

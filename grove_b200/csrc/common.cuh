@@ -113,6 +113,9 @@ struct Relax {
   uint32_t* ovf_next;       // [ovf_cap] next entry + 1
   uint4* ovf_claim;         // [ovf_cap] same layout as a claim slot; dead entries (x = kClaimEmpty) are revived by later claims on the node
   uint32_t ovf_cap;
+  int4* ctot;               // [npad] sum of ALL live claims on the node (inline + overflow): cpu, mem, gpu, pods
+  uint32_t* cmaxr;          // [npad] upper bound of the ranks that claim(ed) the node this cycle: a gang of a higher rank sees
+                            // committed - ctot and never reads the claim line
   // change stamps of the round: (tag << 24) | lowest rank; a stale tag = no stamp
   uint32_t* add_stamp;      // [npad] a gang newly claimed this node
   uint32_t* rem_stamp;      // [words] a gang withdrew a claim from this 32-node group

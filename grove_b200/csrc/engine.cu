@@ -164,6 +164,8 @@ struct grove_engine {
   DevBuf<uint16_t> d_ent_meta, d_cur_n, d_nxt_meta, d_nxt_n;
   DevBuf<uint8_t> d_last_att, d_state, d_tstate, d_dirty, d_sc_lvl, d_nxt_tstate, d_nxt_sc_lvl, d_cap8, d_T;
   DevBuf<uint4> d_claims, d_ovf_claim;
+  DevBuf<int4> d_ctot;
+  DevBuf<uint32_t> d_cmaxr;
   DevBuf<grove_gang_status_t> d_status;
   DevBuf<grove_scope_status_t> d_scope_status;
   DevBuf<grove_placement_t> d_out;
@@ -334,6 +336,7 @@ static Relax make_relax(grove_engine* e) {
   r.nxt_info = e->d_nxt_info.p; r.nxt_glo = e->d_nxt_glo.p; r.nxt_extent = e->d_nxt_extent.p; r.nxt_sc_lvl = e->d_nxt_sc_lvl.p; r.nxt_sc_lo = e->d_nxt_sc_lo.p;
   r.claims = e->d_claims.p; r.nlive = e->d_nlive.p; r.ovf_head = e->d_ovf_head.p; r.ovf_next = e->d_ovf_next.p; r.ovf_claim = e->d_ovf_claim.p;
   r.ovf_cap = uint32_t(std::min<size_t>(e->d_ovf_claim.cap, 0xFFFFFFF0u));
+  r.ctot = e->d_ctot.p; r.cmaxr = e->d_cmaxr.p;
   r.add_stamp = e->d_add_stamp.p; r.rem_stamp = e->d_rem_stamp.p; r.rem_round = e->d_rem_round.p; r.last_eval = e->d_last_eval.p; r.fail_upto = e->d_fail_upto.p;
   r.F = e->d_F.p; r.cap8 = e->d_cap8.p; r.capsum = e->d_capsum.p; r.capmax = e->d_capmax.p; r.T = e->d_T.p;
   r.shape_bits = e->shape_tables ? e->d_shape_bits.p : nullptr; r.pl_words = e->pl_words;
@@ -886,6 +889,7 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, e->d_nxt_sc_lvl.ensure(s1)); CU_TRY(e, e->d_nxt_sc_lo.ensure(s1));
   CU_TRY(e, e->d_claims.ensure(size_t(N) * kClaimSlots)); CU_TRY(e, e->d_nlive.ensure(N / 4)); CU_TRY(e, e->d_ovf_head.ensure(N));
   CU_TRY(e, e->d_ovf_next.ensure(4 * p1 + 1024)); CU_TRY(e, e->d_ovf_claim.ensure(4 * p1 + 1024));
+  CU_TRY(e, e->d_ctot.ensure(N)); CU_TRY(e, e->d_cmaxr.ensure(N));
   CU_TRY(e, e->d_add_stamp.ensure(N)); CU_TRY(e, e->d_rem_stamp.ensure(e->words)); CU_TRY(e, e->d_rem_round.ensure(e->words));
   CU_TRY(e, e->d_last_eval.ensure(g1)); CU_TRY(e, e->d_fail_upto.ensure(g1));
   CU_TRY(e, e->d_status.ensure(g1)); CU_TRY(e, e->d_scope_status.ensure(s1)); CU_TRY(e, e->d_out.ensure(p1));
@@ -910,6 +914,7 @@ static int32_t cycle_begin(grove_engine* e) {
   CU_TRY(e, cudaMemsetAsync(e->d_sc_lvl.p, 0xFF, s1, st)); CU_TRY(e, cudaMemsetAsync(e->d_sc_lo.p, 0xFF, sizeof(uint32_t) * s1, st));
   CU_TRY(e, cudaMemsetAsync(e->d_claims.p, 0xFF, sizeof(uint4) * size_t(N) * kClaimSlots, st));
   CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_ovf_head.p, 0, sizeof(uint32_t) * N, st));
+  CU_TRY(e, cudaMemsetAsync(e->d_ctot.p, 0, sizeof(int4) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_cmaxr.p, 0, sizeof(uint32_t) * N, st));
   CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, st));
   CU_TRY(e, cudaMemsetAsync(e->d_rem_round.p, 0, sizeof(uint32_t) * e->words, st)); CU_TRY(e, cudaMemsetAsync(e->d_last_eval.p, 0, sizeof(uint32_t) * g1, st));
   {
@@ -1073,7 +1078,8 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     cudaMemcpy(h.data(), e->d_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost);
     { const uint32_t* w = &h[size_t(G) * 8];
       std::fprintf(stderr, "warp 0 of every evaluation: %u evals, %.0f cyc each; %u staged attempts: staging %.0f cyc, sub-domain pre-filter %.0f, packing %.0f per attempt\n",
-                   w[5], w[5] ? double(w[4]) / w[5] : 0.0, w[3], w[3] ? double(w[0]) / w[3] : 0.0, w[3] ? double(w[1]) / w[3] : 0.0, w[3] ? double(w[2]) / w[3] : 0.0); }
+                   w[5], w[5] ? double(w[4]) / w[5] : 0.0, w[3], w[3] ? double(w[0]) / w[3] : 0.0, w[3] ? double(w[1]) / w[3] : 0.0, w[3] ? double(w[2]) / w[3] : 0.0);
+      std::fprintf(stderr, "  of the staging: claim lines %.0f cyc, overflow chains %.0f per attempt\n", w[3] ? double(w[6]) / w[3] : 0.0, w[3] ? double(w[7]) / w[3] : 0.0); }
     uint64_t ev = 0, pl = 0, at = 0, mx = 0;
     for (uint32_t g = 0; g < G; ++g) { ev += h[g * 8]; pl += h[g * 8 + 1]; at += h[g * 8 + 2]; mx = std::max<uint64_t>(mx, h[g * 8]); }
     std::fprintf(stderr, "cycle: %u rounds, %llu evaluations (max %llu per gang), plausible/eval %.1f, attempts/eval %.2f\n", rounds,

@@ -60,6 +60,15 @@ __device__ __forceinline__ void nlive_add(uint32_t* nlive, uint32_t n, int delta
   if (delta > 0) atomicAdd(nlive + (n >> 2), 1u << sh); else atomicSub(nlive + (n >> 2), 1u << sh);
 }
 
+// the per-node total of all live claims follows every claim that comes or goes (gpw = gpu | pods << 16, sign = +1 / -1)
+__device__ __forceinline__ void ctot_add(const Relax& rx, uint32_t n, int cpu, int mem, uint32_t gpw, int sign) {
+  int* t = reinterpret_cast<int*>(rx.ctot + n);
+  if (cpu) atomicAdd(t + 0, cpu);
+  if (mem) atomicAdd(t + 1, mem);
+  if (gpw & 0xFFFFu) atomicAdd(t + 2, sign * int(gpw & 0xFFFFu));
+  atomicAdd(t + 3, sign * int(gpw >> 16));
+}
+
 // withdraw ONE claim slot of `rank` on node n (the caller owns exactly one per entry run)
 __device__ __forceinline__ void claim_remove(const Relax& rx, uint32_t n, uint32_t rank) {
   uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
@@ -69,14 +78,26 @@ __device__ __forceinline__ void claim_remove(const Relax& rx, uint32_t n, uint32
   for (uint32_t s = 0; s < kClaimSlots; ++s) own |= uint32_t(__ldcg(line + 4 * s) == rank) << s;
   for (; own; own &= own - 1) {
     const uint32_t s = __ffs(own) - 1;
-    if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) { nlive_add(rx.nlive, n, -1); return; }   // (another lane of this gang may have taken it)
+    // the amounts are read while the slot is still ours: once it is free another gang may take and rewrite it
+    const uint32_t cpu = __ldcg(line + 4 * s + 1), mem = __ldcg(line + 4 * s + 2), gpw = __ldcg(line + 4 * s + 3);
+    if (atomicCAS(line + 4 * s, rank, kClaimEmpty) == rank) {   // (another lane of this gang may have taken it)
+      ctot_add(rx, n, -int(cpu), -int(mem), gpw, -1);
+      nlive_add(rx.nlive, n, -1);
+      return;
+    }
   }
-  for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1])
-    if (atomicCAS(reinterpret_cast<uint32_t*>(rx.ovf_claim + i - 1), rank, kClaimEmpty) == rank) return;
+  for (uint32_t i = *reinterpret_cast<volatile uint32_t*>(rx.ovf_head + n); i; i = rx.ovf_next[i - 1]) {
+    uint32_t* e = reinterpret_cast<uint32_t*>(rx.ovf_claim + i - 1);
+    if (__ldcg(e) != rank) continue;
+    const uint32_t cpu = __ldcg(e + 1), mem = __ldcg(e + 2), gpw = __ldcg(e + 3);
+    if (atomicCAS(e, rank, kClaimEmpty) == rank) { ctot_add(rx, n, -int(cpu), -int(mem), gpw, -1); return; }
+  }
 }
 
 __device__ __forceinline__ void claim_add(const Relax& rx, uint32_t n, uint32_t rank, uint32_t cpu, uint32_t mem, uint32_t gpw) {
   uint32_t* line = reinterpret_cast<uint32_t*>(rx.claims + size_t(n) * kClaimSlots);
+  ctot_add(rx, n, int(cpu), int(mem), gpw, +1);
+  atomicMax(rx.cmaxr + n, rank);
   for (int pass = 0; pass < 3; ++pass) {   // look first, then take; somebody else may win the slot: look again
     uint32_t freeb = 0;
 #pragma unroll
