@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdio>
 #include <array>
 #include <cstdlib>
@@ -207,6 +208,7 @@ struct grove_engine {
 
   bool in_cycle = false;
   uint64_t launches = 0;
+  std::vector<grove_victim_t> victims;   // of the last grove_run_cycle_preempt
 };
 
 
@@ -927,6 +929,7 @@ static int32_t cycle_begin(grove_engine* e) {
     CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
   }
   e->launches = 0; e->in_cycle = true; e->have_results = false; e->have_scopes = false;
+  e->victims.clear();
   std::memset(&e->last, 0, sizeof(e->last));
   return GROVE_OK;
 }
@@ -1142,6 +1145,171 @@ int32_t grove_build_score_matrix(grove_engine_t* e, float* ms) {
   float t = 0; cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1);
   e->last.ms_score = t; e->score_valid = true;
   if (ms) *ms = t;
+  return GROVE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reclaim pass (include/grove_place.h "preemption / reclaim").  Host orchestration around the same
+// device path: the gangs the ordinary pass rejected are re-submitted priority class by priority class (descending) against
+// the reclaim view of that class -- the evaluation of a gang does not depend on WHICH running gangs end up evicted, only on
+// what is free plus what is evictable, so a whole class is one ordinary cycle on the augmented node table; the victims
+// are then chosen gang by gang in order, exactly as the sequential statement says.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Res { int64_t cpu = 0, mem = 0, gpu = 0, pods = 0; };
+inline bool covers(const grove_node_t& n, const Res& r) {
+  return int64_t(n.free_cpu_milli) >= r.cpu && int64_t(n.free_mem_mib) >= r.mem && int64_t(n.free_gpu) >= r.gpu && int64_t(n.free_pods) >= r.pods;
+}
+inline void give(grove_node_t& n, const grove_holding_t& h) {
+  n.free_cpu_milli += h.cpu_milli; n.free_mem_mib += h.mem_mib; n.free_gpu = uint16_t(n.free_gpu + h.gpu); n.free_pods = uint16_t(n.free_pods + h.pods);
+}
+}  // namespace
+
+int32_t grove_run_cycle_preempt(grove_engine_t* e, const grove_running_gang_t* running, uint32_t n_running,
+                                const grove_holding_t* holdings, uint32_t n_holdings, grove_cycle_stats_t* stats) {
+  if (!e || (n_running && !running) || (n_holdings && !holdings)) return GROVE_ERR_INVALID_ARG;
+  for (uint32_t r = 0; r < n_running; ++r)
+    if (uint64_t(running[r].holding_off) + running[r].n_holdings > n_holdings) return fail(e, GROVE_ERR_INVALID_ARG, "running gang holdings out of range");
+  if (e->nodes_loaded) for (uint32_t h = 0; h < n_holdings; ++h)
+    if (holdings[h].node >= e->N) return fail(e, GROVE_ERR_INVALID_ARG, "holding on a node out of range");
+  grove_cycle_stats_t st0{};
+  int32_t rc = grove_run_cycle(e, &st0);
+  if (rc) return rc;
+  const uint32_t G = e->G, Q = e->Q, S = e->S, N = e->N;
+  // the ordinary pass's outputs and the submission itself (the handle is re-used for the class cycles)
+  std::vector<grove_gang_t> gangs(e->gangs.data(), e->gangs.data() + G);
+  std::vector<grove_clique_t> cliques(e->cliques.data(), e->cliques.data() + Q);
+  std::vector<grove_scope_t> scopes(e->scopes.data(), e->scopes.data() + S);
+  std::vector<grove_gang_status_t> status(e->h_status.p, e->h_status.p + G);
+  std::vector<grove_placement_t> place(e->h_out.p, e->h_out.p + e->n_out);
+  std::vector<grove_scope_status_t> sstat(std::max<uint32_t>(S, 1));
+  if (S) { rc = grove_get_scope_domains(e, sstat.data(), S); if (rc) return rc; }
+  std::vector<int32_t> classes;
+  for (uint32_t g = 0; g < G; ++g) if (status[g].state == GROVE_GANG_REJECTED) classes.push_back(gangs[g].priority);
+  std::sort(classes.begin(), classes.end(), std::greater<int32_t>());
+  classes.erase(std::unique(classes.begin(), classes.end()), classes.end());
+  int32_t min_run = INT32_MAX;
+  for (uint32_t r = 0; r < n_running; ++r) min_run = std::min(min_run, running[r].priority);
+  std::vector<grove_victim_t> victims;
+  std::vector<std::vector<grove_placement_t>> extra(G);   // placements of the preemptors, by gang
+  if (!classes.empty() && n_running && classes.front() > min_run) {
+    std::vector<grove_node_t> real(N), view(N);
+    rc = grove_get_nodes(e, real.data(), N);
+    if (rc) return rc;
+    std::vector<uint8_t> evicted(n_running, 0);
+    // running gangs by node (CSR), for the victim choice
+    std::vector<uint32_t> at_off(size_t(N) + 1, 0), at_run(n_holdings);
+    for (uint32_t r = 0; r < n_running; ++r) for (uint32_t h = 0; h < running[r].n_holdings; ++h) ++at_off[holdings[running[r].holding_off + h].node + 1];
+    for (uint32_t n = 0; n < N; ++n) at_off[n + 1] += at_off[n];
+    { std::vector<uint32_t> cur(at_off.begin(), at_off.end() - 1);
+      for (uint32_t r = 0; r < n_running; ++r) for (uint32_t h = 0; h < running[r].n_holdings; ++h) at_run[cur[holdings[running[r].holding_off + h].node]++] = r; }
+    for (int32_t p : classes) {
+      bool any = false;
+      view = real;
+      for (uint32_t r = 0; r < n_running; ++r) {
+        if (evicted[r] || running[r].priority >= p) continue;
+        any = true;
+        for (uint32_t h = 0; h < running[r].n_holdings; ++h) give(view[holdings[running[r].holding_off + h].node], holdings[running[r].holding_off + h]);
+      }
+      if (!any) continue;   // nothing to reclaim for this class (nor for the lower ones)
+      // the class's rejected gangs as a submission of their own: anchors pinned to what the ordinary pass used, no gating
+      // (a rejected gang's base gang, if any, was admitted before it)
+      std::vector<uint32_t> ids;
+      std::vector<grove_gang_t> sg; std::vector<grove_clique_t> sq; std::vector<grove_scope_t> ss;
+      for (uint32_t g = 0; g < G; ++g) {
+        if (status[g].state != GROVE_GANG_REJECTED || gangs[g].priority != p) continue;
+        grove_gang_t x = gangs[g];
+        if (x.anchor_node == GROVE_NONE_U32) x.anchor_node = e->perm[fmix32(g) % N];
+        x.base_gang = GROVE_NONE_U32;
+        x.clique_off = uint32_t(sq.size()); x.scope_off = uint32_t(ss.size());
+        sq.insert(sq.end(), cliques.begin() + gangs[g].clique_off, cliques.begin() + gangs[g].clique_off + gangs[g].n_cliques);
+        ss.insert(ss.end(), scopes.begin() + gangs[g].scope_off, scopes.begin() + gangs[g].scope_off + gangs[g].n_scopes);
+        ids.push_back(g); sg.push_back(x);
+      }
+      if (ids.empty()) continue;
+      rc = grove_load_nodes(e, view.data(), N); if (rc) return rc;
+      rc = grove_submit_gangs(e, sg.data(), uint32_t(sg.size()), sq.data(), uint32_t(sq.size()), ss.data(), uint32_t(ss.size())); if (rc) return rc;
+      grove_cycle_stats_t stp{};
+      rc = grove_run_cycle(e, &stp); if (rc) return rc;
+      st0.rounds += stp.rounds; st0.evaluations += stp.evaluations; st0.kernel_launches += stp.kernel_launches;
+      st0.ms_fit += stp.ms_fit; st0.ms_admit += stp.ms_admit; st0.ms_commit += stp.ms_commit; st0.ms_total += stp.ms_total;
+      std::vector<grove_scope_status_t> ssp(std::max<size_t>(ss.size(), 1));
+      if (!ss.empty()) { rc = grove_get_scope_domains(e, ssp.data(), uint32_t(ss.size())); if (rc) return rc; }
+      for (uint32_t k = 0; k < ids.size(); ++k) {   // sub-submission order == order rank (one priority)
+        const grove_gang_status_t& sp = e->h_status.p[k];
+        if (sp.state != GROVE_GANG_ADMITTED) continue;
+        const uint32_t g = ids[k];
+        // what the gang puts on each node, nodes in the order its placement first names them
+        std::vector<uint32_t> order; std::vector<Res> use;
+        for (uint32_t i = 0; i < sp.n_pods; ++i) {
+          const grove_placement_t pl = e->h_out.p[sp.placement_off + i];
+          const grove_clique_t& q = sq[pl.clique];
+          size_t j = 0;
+          for (; j < order.size(); ++j) if (order[j] == pl.node) break;
+          if (j == order.size()) { order.push_back(pl.node); use.emplace_back(); }
+          use[j].cpu += q.req_cpu_milli; use[j].mem += q.req_mem_mib; use[j].gpu += q.req_gpu; use[j].pods += 1;
+          extra[g].push_back(grove_placement_t{gangs[g].clique_off + (pl.clique - sg[k].clique_off), pl.node});
+        }
+        for (size_t j = 0; j < order.size(); ++j) {
+          const uint32_t n = order[j];
+          while (!covers(real[n], use[j])) {
+            uint32_t v = GROVE_NONE_U32;   // lowest priority first, then the highest running index
+            for (uint32_t a = at_off[n]; a < at_off[n + 1]; ++a) {
+              const uint32_t r = at_run[a];
+              if (evicted[r] || running[r].priority >= p) continue;
+              if (v == GROVE_NONE_U32 || running[r].priority < running[v].priority || (running[r].priority == running[v].priority && r > v)) v = r;
+            }
+            if (v == GROVE_NONE_U32) return fail(e, GROVE_ERR_STATE, "reclaim pass: a preemptor's node cannot be freed");
+            evicted[v] = 1;
+            for (uint32_t h = 0; h < running[v].n_holdings; ++h) give(real[holdings[running[v].holding_off + h].node], holdings[running[v].holding_off + h]);
+            victims.push_back(grove_victim_t{v, g});
+          }
+          real[n].free_cpu_milli -= uint32_t(use[j].cpu); real[n].free_mem_mib -= uint32_t(use[j].mem);
+          real[n].free_gpu = uint16_t(real[n].free_gpu - use[j].gpu); real[n].free_pods = uint16_t(real[n].free_pods - use[j].pods);
+        }
+        grove_gang_status_t o = sp;
+        o.reserved0 = GROVE_STATUS_PREEMPTOR;
+        status[g] = o;   // placement_off is assigned when the outputs are merged
+        for (uint32_t si = 0; si < gangs[g].n_scopes; ++si) sstat[gangs[g].scope_off + si] = ssp[sg[k].scope_off + si];
+        st0.gangs_admitted += 1; st0.gangs_rejected -= 1;
+      }
+    }
+    // the handle goes back to the caller's submission, on the node table that is really free now
+    rc = grove_load_nodes(e, real.data(), N); if (rc) return rc;
+    rc = grove_submit_gangs(e, gangs.data(), G, cliques.data(), Q, scopes.data(), S); if (rc) return rc;
+  }
+  // merged outputs: placements grouped by gang in submission order
+  CU_TRY(e, e->h_status.ensure(std::max<uint32_t>(G, 1))); CU_TRY(e, e->h_scope_status.ensure(std::max<uint32_t>(S, 1)));
+  size_t total = 0;
+  for (uint32_t g = 0; g < G; ++g) total += status[g].state == GROVE_GANG_ADMITTED ? status[g].n_pods : 0u;
+  CU_TRY(e, e->h_out.ensure(std::max<size_t>(total, 1)));
+  std::vector<grove_placement_t> merged; merged.reserve(total);
+  for (uint32_t g = 0; g < G; ++g) {
+    if (status[g].state != GROVE_GANG_ADMITTED) continue;
+    const uint32_t off = uint32_t(merged.size());
+    if (status[g].reserved0 & GROVE_STATUS_PREEMPTOR) merged.insert(merged.end(), extra[g].begin(), extra[g].end());
+    else merged.insert(merged.end(), place.begin() + status[g].placement_off, place.begin() + status[g].placement_off + status[g].n_pods);
+    status[g].placement_off = off;
+  }
+  std::memcpy(e->h_out.p, merged.data(), sizeof(grove_placement_t) * merged.size());
+  std::memcpy(e->h_status.p, status.data(), sizeof(grove_gang_status_t) * G);
+  if (S) std::memcpy(e->h_scope_status.p, sstat.data(), sizeof(grove_scope_status_t) * S);
+  e->n_out = uint32_t(merged.size());
+  st0.pods_bound = e->n_out;
+  e->last = st0;
+  e->victims = std::move(victims);
+  e->have_results = true; e->have_scopes = true; e->score_valid = false;
+  if (stats) *stats = st0;
+  return GROVE_OK;
+}
+
+int32_t grove_get_victims(grove_engine_t* e, grove_victim_t* out, uint32_t cap, uint32_t* n_out) {
+  if (!e || !n_out) return GROVE_ERR_INVALID_ARG;
+  if (!e->have_results) return fail(e, GROVE_ERR_STATE, "no completed cycle");
+  *n_out = uint32_t(e->victims.size());
+  if (!out) return GROVE_OK;
+  if (cap < e->victims.size()) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  std::memcpy(out, e->victims.data(), sizeof(grove_victim_t) * e->victims.size());
   return GROVE_OK;
 }
 

@@ -258,7 +258,7 @@ Err CheckPodSchedulingGate(bool podHasGate, bool podListedInPodGang, const std::
 Err GpuBackend::OnPodGangDelete(const PodGang& podGang) {
   std::lock_guard<std::mutex> l(mu_);
   const std::string key = podGang.Namespace + "/" + podGang.Name;
-  pending_.erase(key); bound_.erase(key);
+  pending_.erase(key); bound_.erase(key); running_.erase(key);
   return std::nullopt;
 }
 
@@ -485,7 +485,29 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
   if (auto e = chk(grove_submit_gangs(engine_, t.gangs.data(), uint32_t(t.gangs.size()), t.cliques.data(), uint32_t(t.cliques.size()),
                                       t.scopes.data(), uint32_t(t.scopes.size())), "grove_submit_gangs")) return e;
   grove_cycle_stats_t st{};
-  if (auto e = chk(grove_run_cycle(engine_, &st), "grove_run_cycle")) return e;
+  // running PodGangs -> the reclaim pass's tables (holdings on nodes that left the snapshot are dropped)
+  std::vector<grove_running_gang_t> run; std::vector<grove_holding_t> held; std::vector<std::string> runNames;
+  bool preempt = false;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    preempt = preemption_ && !running_.empty();
+    if (preempt) {
+      std::map<std::string, uint32_t> nodeIdx;
+      for (uint32_t i = 0; i < nodes.size(); ++i) nodeIdx[nodes[i].Name] = i;
+      for (const auto& kv : running_) {
+        if (snap.count(kv.first)) continue;   // still pending with a remainder: not evictable while it is being placed
+        grove_running_gang_t r{kv.second.priority, uint32_t(held.size()), 0u, 0u};
+        for (const auto& h : kv.second.held) {
+          auto it = nodeIdx.find(h.node);
+          if (it == nodeIdx.end()) continue;
+          held.push_back(grove_holding_t{it->second, h.cpu_milli, h.mem_mib, h.gpu, h.pods}); ++r.n_holdings;
+        }
+        run.push_back(r); runNames.push_back(kv.first);
+      }
+    }
+  }
+  if (preempt) { if (auto e = chk(grove_run_cycle_preempt(engine_, run.data(), uint32_t(run.size()), held.data(), uint32_t(held.size()), &st), "grove_run_cycle_preempt")) return e; }
+  else if (auto e = chk(grove_run_cycle(engine_, &st), "grove_run_cycle")) return e;
   if (stats) *stats = st;
   std::vector<grove_placement_t> pl(st.pods_bound + 1);
   uint32_t n = 0;
@@ -525,12 +547,36 @@ Err GpuBackend::RunCycle(const std::vector<Node>& nodes, std::vector<Binding>* b
     return false;
   };
   std::lock_guard<std::mutex> l(mu_);
+  if (preempt) {   // victims: DisruptionTarget on the PodGang (podgang.go:166-170), forgotten as running
+    uint32_t nv = 0;
+    if (auto e = chk(grove_get_victims(engine_, nullptr, 0, &nv), "grove_get_victims")) return e;
+    std::vector<grove_victim_t> vs(nv + 1);
+    if (auto e = chk(grove_get_victims(engine_, vs.data(), uint32_t(vs.size()), &nv), "grove_get_victims")) return e;
+    for (uint32_t i = 0; i < nv; ++i) {
+      PodGangStatus s; s.Phase = PodGangPhase::Running; s.Scheduled = true;
+      s.DisruptionTarget = true; s.DisruptionMessage = "preempted by higher priority PodGang " + t.gangNames[vs[i].preemptor];
+      (*statuses)[runNames[vs[i].running]] = s;
+      running_.erase(runNames[vs[i].running]);
+    }
+  }
   for (uint32_t i = 0; i < gs.size(); ++i) {
     if (gs[i].state != GROVE_GANG_ADMITTED) continue;
     const std::string& key = t.gangNames[i];
     auto pit = pending_.find(key);
     if (pit == pending_.end()) continue;   // deleted while the cycle ran
     const PodGang& pg = pit->second;
+    {   // what the PodGang holds from now on (a remainder adds to what its minimum took)
+      RunningGang& rg = running_[key];
+      rg.priority = t.gangs[i].priority;
+      for (uint32_t k = 0; k < gs[i].n_pods; ++k) {
+        const grove_placement_t& e = pl[gs[i].placement_off + k];
+        const grove_clique_t& q = t.cliques[e.clique];
+        const std::string& nn = nodes[e.node].Name;
+        auto it = std::find_if(rg.held.begin(), rg.held.end(), [&](const Held& h) { return h.node == nn; });
+        if (it == rg.held.end()) { rg.held.push_back(Held{nn}); it = rg.held.end() - 1; }
+        it->cpu_milli += q.req_cpu_milli; it->mem_mib += q.req_mem_mib; it->gpu = uint16_t(it->gpu + q.req_gpu); it->pods = uint16_t(it->pods + 1);
+      }
+    }
     if (gs[i].n_pods && !lastNode_.count(key)) lastNode_[key] = nodes[pl[gs[i].placement_off].node].Name;
     std::vector<uint32_t>& done = bound_[key];
     done.resize(pg.Spec.PodGroups.size(), 0u);

@@ -67,6 +67,8 @@ struct PodGangStatus {                                                          
   std::string ScheduledMessage;           // condition message (why a PodGang cannot be handed to the engine)
   std::optional<double> PlacementScore;   // :187-189
   uint32_t UnboundPods = 0;               // best-effort pods (beyond MinReplicas) of a scheduled PodGang that found no node
+  bool DisruptionTarget = false;          // condition PodGangConditionTypeDisruptionTarget :166-170, reason 1: "PodGang is preempted
+  std::string DisruptionMessage;          // by a higher priority PodGang" -- names the preemptor; the caller terminates the pods
 };
 struct PodGang {
   std::string Namespace, Name;
@@ -236,6 +238,12 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   size_t Pending() const { std::lock_guard<std::mutex> l(mu_); return pending_.size(); }   // PodGangs with unbound pods (unscheduled, or scheduled with a remainder)
   size_t Unscheduled() const { std::lock_guard<std::mutex> l(mu_); return pending_.size() - bound_.size(); }
   void SetPriorityClass(const std::string& name, int32_t value) { std::lock_guard<std::mutex> l(mu_); priorityClasses_[name] = value; }
+  // Preemption (podgang.go:166-170): with it on, a cycle is grove_run_cycle_preempt -- PodGangs this backend scheduled earlier
+  // are the RUNNING gangs (priority + what they hold per node, remembered from their bindings); a PodGang the ordinary pass
+  // rejects may evict running PodGangs of a lower priority.  Victims come back in `statuses` with DisruptionTarget set and
+  // are forgotten here: the caller deletes their pods (the node snapshot of the next cycle shows the resources as free).
+  void SetPreemption(bool on) { std::lock_guard<std::mutex> l(mu_); preemption_ = on; }
+  size_t Running() const { std::lock_guard<std::mutex> l(mu_); return running_.size(); }
   // why a PodGang cannot be handed to the engine (limits of the packed tables), or empty.  SyncPodGang accepts every
   // PodGang -- the reference's reconciler would requeue forever on an error -- and RunCycle reports these as
   // Unschedulable with this message instead of failing the pass for everybody.
@@ -259,6 +267,10 @@ class GpuBackend : public Backend, public TopologyAwareSchedBackend {
   std::map<std::string, int32_t> priorityClasses_;
   std::map<std::string, std::string> lastNode_;  // scheduled PodGang -> a node it landed on (ReuseReservationRef hint)
   std::map<std::string, std::vector<uint32_t>> bound_;  // scheduled PodGang still pending with unbound pods -> pods bound per PodGroup
+  struct Held { std::string node; uint32_t cpu_milli = 0, mem_mib = 0; uint16_t gpu = 0, pods = 0; };
+  struct RunningGang { int32_t priority = 0; std::vector<Held> held; };
+  std::map<std::string, RunningGang> running_;   // PodGangs scheduled by this backend and not deleted since
+  bool preemption_ = false;
   grove_engine_t* engine_ = nullptr;
   uint32_t engineLevels_ = 0;
   mutable std::mutex mu_;        // pending set, bindings, levels: everything SyncPodGang / OnPodGangDelete / SyncTopology touch

@@ -24,7 +24,7 @@ SYMBOLS = [
     "grove_abi_version", "grove_engine_create", "grove_engine_destroy", "grove_last_error",
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_get_scope_domains", "grove_load_nodes_device",
-    "grove_build_score_matrix",
+    "grove_build_score_matrix", "grove_run_cycle_preempt", "grove_get_victims",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -127,6 +127,24 @@ class PlacementEngine:
         st = np.zeros(1, dtype=T.stats_dt)
         self._check(self.lib.grove_run_cycle(self.h, _p(st)))
         return {k: st[k][0].item() for k in T.stats_dt.names}
+
+    def run_cycle_preempt(self, running: np.ndarray, holdings: np.ndarray) -> dict:
+        """ordinary pass + reclaim pass: `running` (T.running_dt) are the gangs admitted by earlier cycles, `holdings`
+        (T.holding_dt) what each holds per node; rejected gangs may evict running gangs of a lower priority"""
+        running = np.ascontiguousarray(running, dtype=T.running_dt)
+        holdings = np.ascontiguousarray(holdings, dtype=T.holding_dt)
+        st = np.zeros(1, dtype=T.stats_dt)
+        self._check(self.lib.grove_run_cycle_preempt(self.h, _p(running), C.c_uint32(len(running)), _p(holdings),
+                                                     C.c_uint32(len(holdings)), _p(st)))
+        return {k: st[k][0].item() for k in T.stats_dt.names}
+
+    def victims(self) -> np.ndarray:
+        """(running gang, preemptor gang) pairs of the last run_cycle_preempt: the caller sets DisruptionTarget on them"""
+        n = C.c_uint32(0)
+        self._check(self.lib.grove_get_victims(self.h, None, C.c_uint32(0), C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=T.victim_dt)
+        self._check(self.lib.grove_get_victims(self.h, _p(out), C.c_uint32(len(out)), C.byref(n)))
+        return out[: n.value]
 
     # ---- outputs ----
     def placements(self, copy: bool = True) -> np.ndarray:

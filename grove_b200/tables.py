@@ -40,6 +40,12 @@ gang_dt = np.dtype([
     ("preferred", "u1"), ("flags", "<u2"), ("reserved", "<u4"),
 ])
 placement_dt = np.dtype([("clique", "<u4"), ("node", "<u4")])
+
+# preemption / reclaim inputs and outputs (include/grove_place.h)
+holding_dt = np.dtype([("node", np.uint32), ("cpu_milli", np.uint32), ("mem_mib", np.uint32), ("gpu", np.uint16), ("pods", np.uint16)])
+running_dt = np.dtype([("priority", np.int32), ("holding_off", np.uint32), ("n_holdings", np.uint32), ("reserved", np.uint32)])
+victim_dt = np.dtype([("running", np.uint32), ("preemptor", np.uint32)])
+STATUS_PREEMPTOR = 0x1
 status_dt = np.dtype([
     ("state", "u1"), ("level", "u1"), ("reserved0", "<u2"), ("score_num", "<u2"), ("score_den", "<u2"),
     ("n_pods", "<u4"), ("placement_off", "<u4"), ("domain_node", "<u4"), ("reserved1", "<u4", (3,)),

@@ -217,6 +217,37 @@ int32_t grove_get_placements(grove_engine_t* e, grove_placement_t* out, uint32_t
 int32_t grove_get_gang_status(grove_engine_t* e, grove_gang_status_t* out, uint32_t cap);
 int32_t grove_get_scope_domains(grove_engine_t* e, grove_scope_status_t* out, uint32_t cap);
 
+/* ---- preemption / reclaim ------------------------------------------------------------------------
+ * The API reserves it (PodGangConditionTypeDisruptionTarget, podgang.go:166-170: "PodGang is preempted by a higher priority
+ * PodGang"; PriorityClassName podgang.go:62-64); the arithmetic is ours ("Reclaim pass").  RUNNING gangs
+ * (admitted by earlier cycles) are handed in with what they hold per node.  After the ordinary pass every REJECTED gang, in
+ * order rank, is evaluated once more against the RECLAIM VIEW of its priority p -- free resources plus everything held by
+ * running gangs of priority < p that are still standing.  If it fits, it is admitted (GROVE_STATUS_PREEMPTOR) and, node by
+ * node in the order of its placement, running gangs are evicted WHOLE (lowest priority first, then highest running index)
+ * until the node's free resources cover what it puts there; everything an evicted gang held anywhere returns to the free
+ * pool.  grove_get_victims lists (running gang, preemptor) pairs: the caller sets DisruptionTarget on them. */
+typedef struct grove_holding {
+  uint32_t node;          /* caller's node index */
+  uint32_t cpu_milli, mem_mib;
+  uint16_t gpu, pods;
+} grove_holding_t;
+typedef struct grove_running_gang {
+  int32_t priority;
+  uint32_t holding_off;   /* into the holdings array */
+  uint32_t n_holdings;
+  uint32_t reserved;
+} grove_running_gang_t;
+typedef struct grove_victim {
+  uint32_t running;       /* index into the running array */
+  uint32_t preemptor;     /* gang index of the submission */
+} grove_victim_t;
+#define GROVE_STATUS_PREEMPTOR 0x1u /* grove_gang_status_t.reserved0: admitted by the reclaim pass */
+/* ordinary pass + reclaim pass; outputs through the usual getters (statuses, placements, scope domains, node table = free
+ * resources after evictions and admissions) */
+int32_t grove_run_cycle_preempt(grove_engine_t* e, const grove_running_gang_t* running, uint32_t n_running,
+                                const grove_holding_t* holdings, uint32_t n_holdings, grove_cycle_stats_t* stats);
+int32_t grove_get_victims(grove_engine_t* e, grove_victim_t* out, uint32_t cap, uint32_t* n_out);
+
 /* K2: the topology-distance score matrix T[clique][node] = fit ? 1 + levels shared with the gang's anchor : 0 (u8) over the
  * snapshot the last cycle started from -- what a scheduler's Score extension point would hand out.  The admission does
  * not read it (its visiting order comes from the anchor's domain ranges), so it is built on request; GROVE_TUNE_SCORE=1

@@ -96,3 +96,93 @@ def topology(nodes, n_levels):
     if rc != 0:
         raise RuntimeError(f"oracle_topology failed: {rc}")
     return perm, dom, ndom[:n_levels].copy(), nt.value
+
+
+def _fmix32(x: int) -> int:
+    x = (x * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF
+    x ^= x >> 16; x = (x * 0x85EBCA6B) & 0xFFFFFFFF; x ^= x >> 13; x = (x * 0xC2B2AE35) & 0xFFFFFFFF; x ^= x >> 16
+    return x
+
+
+def run_cycle_preempt(nodes, n_levels, gangs, cliques, scopes, running, holdings, threads=1):
+    """The reclaim pass as its definition reads (include/grove_place.h "preemption / reclaim"; the API reserves the outcome,
+    PodGangConditionTypeDisruptionTarget podgang.go:166-170, the arithmetic is ours): the ordinary sequential pass, then every
+    REJECTED gang ONE AT A TIME in order rank against free + everything running gangs of a lower priority still hold; a gang that
+    fits evicts whole running gangs, node by node in the order of its placement, lowest priority first then highest running
+    index, until each node's free resources cover what it puts there.  Small cases only (a full oracle cycle per rejected
+    gang).  Returns the ordinary outputs merged with the preemptors', plus `victims` (running, preemptor)."""
+    from grove_b200 import tables as T
+
+    base = run_cycle(nodes, n_levels, gangs, cliques, scopes, threads=threads)
+    G, N = len(gangs), len(nodes)
+    status = base["status"].copy()
+    sstat = base["scope_status"].copy()
+    per_gang = {g: base["placements"][status["placement_off"][g]: status["placement_off"][g] + status["n_pods"][g]].copy()
+                for g in range(G) if status["state"][g] == T.GANG_ADMITTED}
+    real = base["nodes_after"].copy()
+    perm = base["perm"]
+    evicted = np.zeros(len(running), dtype=bool)
+    victims = []
+    on_node = {}
+    for r in range(len(running)):
+        for h in holdings[running["holding_off"][r]: running["holding_off"][r] + running["n_holdings"][r]]:
+            on_node.setdefault(int(h["node"]), []).append(r)
+
+    def give(tab, h):
+        n = int(h["node"])
+        tab["free_cpu_milli"][n] += h["cpu_milli"]; tab["free_mem_mib"][n] += h["mem_mib"]
+        tab["free_gpu"][n] += h["gpu"]; tab["free_pods"][n] += h["pods"]
+
+    for g in sorted(range(G), key=lambda i: (-int(gangs["priority"][i]), i)):
+        if status["state"][g] != T.GANG_REJECTED:
+            continue
+        p = int(gangs["priority"][g])
+        elig = [r for r in range(len(running)) if not evicted[r] and int(running["priority"][r]) < p]
+        if not elig:
+            continue
+        view = real.copy()
+        for r in elig:
+            for h in holdings[running["holding_off"][r]: running["holding_off"][r] + running["n_holdings"][r]]:
+                give(view, h)
+        sg = gangs[g: g + 1].copy()
+        co, so = int(sg["clique_off"][0]), int(sg["scope_off"][0])
+        sq = cliques[co: co + int(sg["n_cliques"][0])].copy()
+        ss = scopes[so: so + int(sg["n_scopes"][0])].copy()
+        if sg["anchor_node"][0] == T.NONE_U32:
+            sg["anchor_node"][0] = perm[_fmix32(g) % N]   # the anchor the ordinary pass derived for this gang
+        sg["base_gang"][0] = T.NONE_U32; sg["clique_off"][0] = 0; sg["scope_off"][0] = 0
+        out = run_cycle(view, n_levels, sg, sq, ss, threads=threads)
+        if out["status"]["state"][0] != T.GANG_ADMITTED:
+            continue
+        pl = out["placements"].copy()
+        use, order = {}, []
+        for e in pl:
+            n, q = int(e["node"]), sq[int(e["clique"])]
+            if n not in use:
+                use[n] = [0, 0, 0, 0]; order.append(n)
+            use[n][0] += int(q["req_cpu_milli"]); use[n][1] += int(q["req_mem_mib"]); use[n][2] += int(q["req_gpu"]); use[n][3] += 1
+        for n in order:
+            u = use[n]
+            while not (real["free_cpu_milli"][n] >= u[0] and real["free_mem_mib"][n] >= u[1] and real["free_gpu"][n] >= u[2] and real["free_pods"][n] >= u[3]):
+                cands = [r for r in on_node.get(n, []) if not evicted[r] and int(running["priority"][r]) < p]
+                v = min(cands, key=lambda r: (int(running["priority"][r]), -r))
+                evicted[v] = True
+                for h in holdings[running["holding_off"][v]: running["holding_off"][v] + running["n_holdings"][v]]:
+                    give(real, h)
+                victims.append((v, g))
+            real["free_cpu_milli"][n] -= u[0]; real["free_mem_mib"][n] -= u[1]; real["free_gpu"][n] -= u[2]; real["free_pods"][n] -= u[3]
+        pl["clique"] += co
+        per_gang[g] = pl
+        st = out["status"][0].copy()
+        st["reserved0"] = T.STATUS_PREEMPTOR
+        status[g] = st
+        sstat[so: so + len(ss)] = out["scope_status"]
+    merged = []
+    off = 0
+    for g in range(G):
+        if status["state"][g] == T.GANG_ADMITTED:
+            status["placement_off"][g] = off
+            merged.append(per_gang[g]); off += len(per_gang[g])
+    placements = np.concatenate(merged) if merged else np.zeros(0, dtype=T.placement_dt)
+    return dict(placements=placements, status=status, scope_status=sstat, nodes_after=real,
+                victims=np.array(victims, dtype=T.victim_dt) if victims else np.zeros(0, dtype=T.victim_dt), perm=perm)

@@ -30,4 +30,4 @@ CHECK=1 TAG="default" timeout 300 python /tmp/c4run.py
 for spec in $SWEEP; do TAG="$spec" env ${spec//,/ } timeout 120 python /tmp/c4run.py; done
 REPS=2 GROVE_DEBUG_ADMIT=1 timeout 300 python /tmp/c4run.py 2>&1 | grep "warp 0\|cycle:\|packed evals\|of the staging" | cut -c1-360 | tail -${DBG_LINES:-4}
 ) 2>&1 | tee gpurun_out/s2_dev.log
-if [ -z "$NOTESTS" ]; then timeout 900 python -m pytest tests -m gpu -x -q --timeout 200 2>&1 | tail -5 | tee gpurun_out/s2_dev_tests.log; fi
+if [ -z "$NOTESTS" ]; then timeout 900 python -m pytest ${TESTS:-tests} -m gpu -x -q --timeout 200 2>&1 | tail -5 | tee gpurun_out/s2_dev_tests.log; fi

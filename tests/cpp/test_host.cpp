@@ -381,6 +381,56 @@ static void test_gpu_min_replicas_then_remainder() {
   CHECK(podNode.size() == 10 && nodes.size() == 10);
 }
 
+// Preemption (podgang.go:166-170 DisruptionTarget, reason 1; PriorityClassName :62-64): six one-pod nodes full of a
+// low-priority PodGang; a high-priority PodGang of two pods is unschedulable without it, evicts it WHOLE, and the victim comes
+// back with the DisruptionTarget condition.  With preemption off the high-priority PodGang simply stays pending.
+static void test_gpu_preemption() {
+  for (const bool on : {false, true}) {
+    GpuBackend be;
+    CHECK(!be.SyncTopology(kLevels));
+    CHECK(!be.Init());
+    be.SetPreemption(on);
+    be.SetPriorityClass("low", 0); be.SetPriorityClass("high", 1000);
+    PodGang::Requests rq; rq.mem_mib = 80; rq.nodeSelector = {{"node_role.e2e.grove.nvidia.com", "agent"}}; rq.tolerationKeys = {"node_role.e2e.grove.nvidia.com"};
+    auto one = [&](const char* name, const char* prio, int replicas) {
+      PodCliqueSet pcs; pcs.Name = name; pcs.PriorityClassName = prio;
+      auto c = clq("w", replicas, replicas); c.Requests = rq; pcs.Cliques.push_back(c);
+      std::vector<PodGangInfo> infos; CHECK(!ComputeExpectedPodGangs(pcs, kLevels, true, &infos));
+      CHECK(infos.size() == 1);
+      return BuildPodGang(pcs, infos[0]);
+    };
+    std::map<std::string, std::string> podNode;
+    auto cycle = [&](std::map<std::string, PodGangStatus>* st) {
+      auto nodes = e2e_nodes(6);
+      for (const auto& kv : podNode) for (auto& nd : nodes) if (nd.Name == kv.second) { nd.used_mem_mib += 80; nd.used_pods += 1; }
+      std::vector<Binding> b;
+      CHECK(!be.RunCycle(nodes, &b, st));
+      for (const auto& x : b) podNode[x.PodName] = x.NodeName;
+      return b.size();
+    };
+    std::map<std::string, PodGangStatus> st;
+    const PodGang filler = one("filler", "low", 6);
+    CHECK(!be.SyncPodGang(filler));
+    CHECK(cycle(&st) == 6 && be.Running() == 1 && be.Pending() == 0);
+    const PodGang urgent = one("urgent", "high", 2);
+    CHECK(!be.SyncPodGang(urgent));
+    const size_t bound = cycle(&st);
+    const std::string fk = filler.Namespace + "/" + filler.Name, uk = urgent.Namespace + "/" + urgent.Name;
+    if (!on) {
+      CHECK(bound == 0 && st.at(uk).ScheduledReason == "Unschedulable" && !st.count(fk) && be.Running() == 1 && be.Pending() == 1);
+      continue;
+    }
+    CHECK(bound == 2 && st.at(uk).Scheduled && be.Pending() == 0);
+    CHECK(st.count(fk) && st.at(fk).DisruptionTarget && st.at(fk).DisruptionMessage.find(uk) != std::string::npos);
+    CHECK(be.Running() == 1);   // the victim is forgotten, the preemptor runs
+    // the two pods sit on nodes the victim held
+    std::set<std::string> fillerNodes, urgentNodes;
+    for (const auto& kv : podNode) (kv.first.find("urgent") != std::string::npos ? urgentNodes : fillerNodes).insert(kv.second);
+    CHECK(urgentNodes.size() == 2);
+    for (const auto& n : urgentNodes) CHECK(fillerNodes.count(n));
+  }
+}
+
 // The backend's cycle loop: several "reconcilers" call SyncPodGang concurrently
 // (controller/podgang/register.go:34-36) while ONE thread snapshots nodes, runs cycles and binds.  A PodGang the tables
 // cannot hold is reported Unschedulable with its reason and does not stop anybody else.
@@ -442,7 +492,7 @@ int main(int argc, char** argv) {
   test_pod_scheduling_gates();
   test_scheduled_condition_and_counts();
   test_encode();
-  if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); test_gpu_cycle_loop_with_concurrent_reconcilers(); }
+  if (gpu) { test_gpu_cycles(); test_gpu_min_replicas_then_remainder(); test_gpu_preemption(); test_gpu_cycle_loop_with_concurrent_reconcilers(); }
   else {  // without a CUDA device Init must fail loudly, never fall back
     GpuBackend be; be.SyncTopology(kLevels);
     auto e = be.Init();
