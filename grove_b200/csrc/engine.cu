@@ -209,6 +209,12 @@ struct grove_engine {
   bool in_cycle = false;
   uint64_t launches = 0;
   std::vector<grove_victim_t> victims;   // of the last grove_run_cycle_preempt
+  // node-range shard of this handle (cfg.rank of cfg.world; the whole table when world <= 1): sorted node indices, cut at
+  // top-level domain boundaries
+  uint32_t shard_lo = 0, shard_hi = 0;
+  bool score_pass_valid = false;   // the capacity tables + T describe the loaded snapshot (grove_run_score_pass)
+  uint32_t t_c0 = 0, t_cpr = 0;    // ... and T holds the 16-node chunks [t_c0, t_c0 + t_cpr) of every row
+  DevBuf<uint32_t> d_sig_sum;
 };
 
 
@@ -303,6 +309,19 @@ static int32_t build_topology(grove_engine* e, const grove_node_t* nodes, uint32
     CU_TRY(e, cudaStreamSynchronize(e->stream));  // nxt is reused
   }
   e->ginfo_dirty = true;
+  // this handle's node-range shard: the top-level domains dealt out in order, as evenly as their sizes allow; nodes that lack
+  // the top-level label (sorted last) go to the last rank
+  {
+    const uint32_t W = std::max<uint32_t>(e->cfg.world, 1u), R = e->cfg.world > 1 ? e->cfg.rank : 0u;
+    auto cut = [&](uint32_t r) -> uint32_t {   // first node of rank r's shard
+      if (r == 0) return 0u;
+      if (r >= W) return n;
+      const uint64_t target = uint64_t(n) * r / W;
+      for (uint32_t d = 0; d < e->n_dom[0]; ++d) if (e->dom_lo[0][d] >= target) return e->dom_lo[0][d];
+      return n;
+    };
+    e->shard_lo = cut(R); e->shard_hi = cut(R + 1);
+  }
   return GROVE_OK;
 }
 
@@ -455,7 +474,7 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
   k_gather<<<(e->Npad + 255) / 256, 256, 0, e->stream>>>(e->d_nodes_in.p, e->d_perm.p, e->d_vdepth.p, e->d_nres.p, e->N, e->Npad);
   CU_TRY(e, cudaGetLastError());
   if (dev_nodes) CU_TRY(e, cudaStreamSynchronize(e->stream));  // the caller's device buffer is free again on return
-  e->nodes_loaded = true;
+  e->nodes_loaded = true; e->score_pass_valid = false;
   return GROVE_OK;
 }
 
@@ -474,6 +493,7 @@ int32_t grove_update_nodes(grove_engine_t* e, const uint32_t* idx, const grove_n
   if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
   if (e->in_cycle) return fail(e, GROVE_ERR_STATE, "cycle in flight");
   if (n == 0) return GROVE_OK;
+  e->score_pass_valid = false;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   CU_TRY(e, cudaEventSynchronize(e->ev_upd));  // an earlier update may still be reading the pinned staging buffers
   CU_TRY(e, e->h_upd_idx.ensure(n)); CU_TRY(e, e->h_upd_recs.ensure(n));
@@ -578,7 +598,7 @@ int32_t grove_submit_gangs(grove_engine_t* e, const grove_gang_t* gangs, uint32_
   CU_TRY(e, e->gangs.assign(gangs, n_gangs));
   CU_TRY(e, e->cliques.assign(cliques, n_cliques));
   CU_TRY(e, e->scopes.assign(scopes, n_scopes));
-  e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false;
+  e->gangs_loaded = true; e->ginfo_dirty = true; e->have_results = false; e->score_pass_valid = false;
   bool pref = false;
   for (uint32_t g = 0; g < n_gangs && !pref; ++g) pref |= gangs[g].preferred != GROVE_LEVEL_NONE;
   for (uint32_t i = 0; i < n_scopes && !pref; ++i) pref |= scopes[i].preferred1 != 0;
@@ -929,7 +949,7 @@ static int32_t cycle_begin(grove_engine* e) {
     CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
   }
   e->launches = 0; e->in_cycle = true; e->have_results = false; e->have_scopes = false;
-  e->victims.clear();
+  e->victims.clear(); e->score_pass_valid = false;
   std::memset(&e->last, 0, sizeof(e->last));
   return GROVE_OK;
 }
@@ -991,7 +1011,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_fit, e->stream));
       if (e->tune_overlap) CU_TRY(e, cudaStreamWaitEvent(ss, e->ev_fit, 0));
       CU_TRY(e, cudaEventRecord(e->ev_s0, ss));
-      k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, ss>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q);  // one CTA per row
+      k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, ss>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q, 0u, e->Npad >> 4, size_t(e->Npad));  // one CTA per row
       e->score_valid = true;
       CU_TRY(e, cudaEventRecord(e->ev_s1, ss));
       if (e->tune_overlap) CU_TRY(e, cudaEventRecord(e->ev_score, e->stream_score));
@@ -1138,7 +1158,7 @@ int32_t grove_build_score_matrix(grove_engine_t* e, float* ms) {
   if (e->d_T.ensure(size_t(e->Q) * e->Npad) != cudaSuccess) { (void)cudaGetLastError(); return fail(e, GROVE_ERR_OOM, "score matrix does not fit in device memory"); }
   const Topo tp = make_topo(e); const Tables tb = make_tables(e);
   CU_TRY(e, cudaEventRecord(e->ev_s0, e->stream));
-  k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, e->stream>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q);  // one CTA per row
+  k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, e->stream>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q, 0u, e->Npad >> 4, size_t(e->Npad));  // one CTA per row
   CU_TRY(e, cudaGetLastError());
   CU_TRY(e, cudaEventRecord(e->ev_s1, e->stream));
   CU_TRY(e, cudaEventSynchronize(e->ev_s1));
@@ -1313,6 +1333,65 @@ int32_t grove_get_victims(grove_engine_t* e, grove_victim_t* out, uint32_t cap, 
   return GROVE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU score pass (BASELINE.json north_star: "the node-state table shards across GPUs only when the synthetic cluster
+// exceeds single-GPU capacity, with one NCCL all-reduce over NVLink of the per-shard gang-feasibility bitmasks").  The object
+// that outgrows a GPU is the Q x N score matrix, so THAT is what shards: every rank holds the (small) node table, builds K1 +
+// K2 for its node range only -- cut at top-level domain boundaries, so every candidate domain of a gang lies in one shard --
+// and contributes one int32[G + Q] vector of per-shard feasibility counts and capacity counts; their SUM over the ranks (the
+// one collective, issued by the caller on its own communicator) says which gangs cannot fit anywhere in the snapshot.
+// ---------------------------------------------------------------------------------------------
+int32_t grove_shard_range(grove_engine_t* e, uint32_t* lo, uint32_t* hi) {
+  if (!e || !lo || !hi) return GROVE_ERR_INVALID_ARG;
+  if (!e->nodes_loaded) return fail(e, GROVE_ERR_STATE, "no node snapshot loaded");
+  *lo = e->shard_lo; *hi = e->shard_hi;
+  return GROVE_OK;
+}
+
+int32_t grove_run_score_pass(grove_engine_t* e, float* ms) {
+  if (!e) return GROVE_ERR_INVALID_ARG;
+  if (ms) *ms = 0.f;
+  int32_t rc = cycle_begin(e);   // allocations, derived gang tables, state resets: the pass leaves the handle ready for a cycle
+  if (rc) return rc;
+  CycleGuard guard{e};
+  e->score_pass_valid = false; e->score_valid = false;
+  if (e->G == 0 || e->Q == 0) { e->in_cycle = false; guard.armed = false; return GROVE_OK; }
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e); const Relax rx = make_relax(e);
+  const uint32_t c0 = e->shard_lo >> 4, c1 = (e->shard_hi + 15u) >> 4, cpr = c1 > c0 ? c1 - c0 : 0u;
+  const size_t tstride = size_t(cpr) << 4;
+  if (e->d_T.ensure(std::max<size_t>(size_t(e->Q) * tstride, 1)) != cudaSuccess) { (void)cudaGetLastError(); return fail(e, GROVE_ERR_OOM, "score matrix shard does not fit in device memory"); }
+  CU_TRY(e, cudaEventRecord(e->ev_s0, e->stream));
+  rc = build_cap_tables(e, tp, tb, rx);   // K1: fit bitmap + capacities of every signature over the loaded snapshot
+  if (rc) return rc;
+  CU_TRY(e, e->d_F0.ensure(std::max<size_t>(size_t(e->n_sigs) * e->words, 1)));
+  CU_TRY(e, cudaMemcpyAsync(e->d_F0.p, e->d_F.p, sizeof(uint32_t) * size_t(e->n_sigs) * e->words, cudaMemcpyDeviceToDevice, e->stream));
+  if (cpr) k_score<<<dim3(1, std::min<uint32_t>(e->Q, 65535u)), 256, 0, e->stream>>>(tp, tb, e->d_F0.p, e->d_T.p, e->Q, c0, cpr, tstride);   // K2, this shard's columns
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaEventRecord(e->ev_s1, e->stream));
+  CU_TRY(e, cudaEventSynchronize(e->ev_s1));
+  float t = 0; cudaEventElapsedTime(&t, e->ev_s0, e->ev_s1);
+  if (ms) *ms = t;
+  e->last.ms_score = t;
+  e->in_cycle = false; guard.armed = false;
+  e->score_pass_valid = true; e->t_c0 = c0; e->t_cpr = cpr;
+  return GROVE_OK;
+}
+
+int32_t grove_shard_summary_device(grove_engine_t* e, void* d_out, uint32_t cap_words) {
+  if (!e || !d_out) return GROVE_ERR_INVALID_ARG;
+  if (!e->score_pass_valid) return fail(e, GROVE_ERR_STATE, "no score pass over the loaded snapshot");
+  if (cap_words < e->G + e->Q) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  const Topo tp = make_topo(e); const Tables tb = make_tables(e);
+  CU_TRY(e, e->d_sig_sum.ensure(std::max<uint32_t>(e->n_sigs, 1)));
+  if (e->n_sigs) k_sig_range_sum<<<e->n_sigs, 256, 0, e->stream>>>(tp, e->d_cap8.p, e->shard_lo, e->shard_hi, e->d_sig_sum.p);
+  k_shard_summary<<<std::max(1u, std::min((e->G * 32 + 255) / 256, e->n_sm * 8u)), 256, 0, e->stream>>>(tp, tb, e->d_cap8.p, e->d_capsum.p, e->d_sig_sum.p, e->shard_lo, e->shard_hi,
+                                                                                                   static_cast<int32_t*>(d_out));
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaStreamSynchronize(e->stream));   // the caller's collective runs on its own stream
+  return GROVE_OK;
+}
+
 // ---- introspection for parity tests ----
 int32_t grove_debug_get_perm(grove_engine_t* e, uint32_t* sorted_to_caller, uint32_t cap) {
   if (!e || !sorted_to_caller) return GROVE_ERR_INVALID_ARG;
@@ -1340,6 +1419,16 @@ int32_t grove_debug_get_fit_row(grove_engine_t* e, uint32_t clique, uint32_t* wo
 
 int32_t grove_debug_get_score_row(grove_engine_t* e, uint32_t clique, uint8_t* bytes, uint32_t cap_bytes) {
   if (!e || !bytes) return GROVE_ERR_INVALID_ARG;
+  if (e->score_pass_valid) {   // after a score pass: this handle's shard of the row, zeros outside it
+    if (clique >= e->Q) return fail(e, GROVE_ERR_STATE, "bad clique");
+    if (cap_bytes < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
+    CU_TRY(e, cudaSetDevice(e->cfg.device));
+    std::memset(bytes, 0, e->N);
+    const size_t first = size_t(e->t_c0) << 4, width = size_t(e->t_cpr) << 4;
+    const size_t cnt = first < e->N ? std::min<size_t>(width, e->N - first) : 0;
+    if (cnt) CU_TRY(e, cudaMemcpy(bytes + first, e->d_T.p + size_t(clique) * width, cnt, cudaMemcpyDeviceToHost));
+    return GROVE_OK;
+  }
   if (!e->have_results || clique >= e->Q) return fail(e, GROVE_ERR_STATE, "no completed cycle / bad clique");
   if (cap_bytes < e->N) return fail(e, GROVE_ERR_LIMIT, "output buffer too small");
   { int32_t rc = grove_build_score_matrix(e, nullptr); if (rc) return rc; }

@@ -25,6 +25,7 @@ SYMBOLS = [
     "grove_load_nodes", "grove_update_nodes", "grove_get_nodes", "grove_submit_gangs", "grove_run_cycle",
     "grove_get_placements", "grove_get_gang_status", "grove_get_scope_domains", "grove_load_nodes_device",
     "grove_build_score_matrix", "grove_run_cycle_preempt", "grove_get_victims",
+    "grove_shard_range", "grove_run_score_pass", "grove_shard_summary_device",
     "grove_debug_get_perm", "grove_debug_get_fit_row", "grove_debug_get_score_row",
 ]
 
@@ -181,6 +182,23 @@ class PlacementEngine:
         ms = C.c_float(0)
         self._check(self.lib.grove_build_score_matrix(self.h, C.byref(ms)))
         return ms.value
+
+    # ---- multi-GPU score pass (node-range shards; grove_b200/sharded.py drives it) ----
+    def shard_range(self) -> tuple[int, int]:
+        """topology-sorted node range [lo, hi) this handle builds K1 / K2 for (the whole table when world <= 1)"""
+        lo, hi = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.grove_shard_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def run_score_pass(self) -> float:
+        """K1 + K2 over the loaded snapshot for this handle's node range, no admission; returns device ms"""
+        ms = C.c_float(0)
+        self._check(self.lib.grove_run_score_pass(self.h, C.byref(ms)))
+        return ms.value
+
+    def shard_summary_into(self, dev_ptr: int, cap_words: int):
+        """int32[G + Q] feasibility / capacity counts of this shard into a DEVICE buffer (all-reduced by the caller)"""
+        self._check(self.lib.grove_shard_summary_device(self.h, C.c_void_p(dev_ptr), C.c_uint32(cap_words)))
 
     # ---- introspection (parity tests) ----
     def debug_perm(self) -> np.ndarray:

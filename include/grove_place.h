@@ -254,6 +254,20 @@ int32_t grove_get_victims(grove_engine_t* e, grove_victim_t* out, uint32_t cap, 
  * builds it every cycle beside the admission.  *ms (nullable): device time of the kernel. */
 int32_t grove_build_score_matrix(grove_engine_t* e, float* ms);
 
+/* ---- multi-GPU score pass (north_star: node-range shards + one all-reduce of per-shard feasibility) -------------
+ * A handle created with grove_config_t.world = W > 1 and rank = r builds K1 + K2 (fit / score matrix) only for ITS node range:
+ * the topology-sorted node table cut at top-level domain boundaries into W ranges of about equal size (every handle loads the
+ * whole -- small -- node table; the Q x N score matrix is what outgrows a GPU).  grove_run_score_pass: K1 + K2 over the loaded
+ * snapshot for the submitted gangs, no admission; *ms (nullable) = device time.  grove_shard_summary_device writes int32[G + Q]
+ * into the caller's DEVICE buffer: [g] = domains of gang g's Required level starting in the shard in which each of its cliques
+ * finds MinReplicas worth of capacity (0 for gangs without a Required level), [G + q] = pods of clique q that fit on the
+ * shard's nodes.  The caller sums the vectors of all ranks with ONE all-reduce (NCCL over NVLink; gloo in the CPU tests) and
+ * reads cluster-wide feasibility off the sum: a gang with a Required level and sum 0, or a clique whose summed capacity is
+ * below MinReplicas, cannot be admitted from this snapshot.  With world <= 1 the shard is the whole table. */
+int32_t grove_shard_range(grove_engine_t* e, uint32_t* lo, uint32_t* hi); /* topology-sorted node indices [lo, hi) */
+int32_t grove_run_score_pass(grove_engine_t* e, float* ms);
+int32_t grove_shard_summary_device(grove_engine_t* e, void* d_out, uint32_t cap_words);
+
 /* ---- device-resident variants (inputs already in HBM; used by bench.py `value`) -------------- */
 /* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load */
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);

@@ -186,3 +186,67 @@ def run_cycle_preempt(nodes, n_levels, gangs, cliques, scopes, running, holdings
     placements = np.concatenate(merged) if merged else np.zeros(0, dtype=T.placement_dt)
     return dict(placements=placements, status=status, scope_status=sstat, nodes_after=real,
                 victims=np.array(victims, dtype=T.victim_dt) if victims else np.zeros(0, dtype=T.victim_dt), perm=perm)
+
+
+def shard_cut(n, dom0_sorted, rank, world):
+    """first node (topology-sorted index) of rank's shard: the table cut at top-level domain boundaries, about n / world nodes
+    each (include/grove_place.h "multi-GPU score pass"); nodes without the top-level label stay with the last rank"""
+    if rank <= 0:
+        return 0
+    if rank >= world:
+        return n
+    target = n * rank // world
+    present = dom0_sorted != 0xFFFFFFFF
+    starts = np.nonzero(present & np.concatenate([[True], dom0_sorted[1:] != dom0_sorted[:-1]]))[0]
+    later = starts[starts >= target]
+    return int(later[0]) if len(later) else n
+
+
+def shard_summary(nodes, n_levels, gangs, cliques, scopes, lo, hi):
+    """numpy restatement of the shard summary of the multi-GPU score pass: int32[G + Q] over the topology-sorted node range
+    [lo, hi) -- [g]: domains of gang g's Required level starting in the range in which every clique of the gang finds MinReplicas
+    worth of capacity on its own; [G + q]: pods of clique q that fit on the range's nodes (a node counts at most 255)."""
+    from grove_b200 import tables as T
+
+    perm, dom, _, _ = topology(nodes, n_levels)
+    sn = np.ascontiguousarray(nodes, dtype=T.node_dt)[perm]
+    n, G, Q = len(sn), len(gangs), len(cliques)
+    absent = dom[:, :n_levels] == 0xFFFFFFFF
+    vdepth = np.where(absent.any(axis=1), absent.argmax(axis=1), n_levels)
+    sched = (sn["flags"] & T.NODE_SCHEDULABLE) != 0
+    ncls = (sn["flags"].astype(np.int64) >> T.NODE_CLASS_SHIFT) & 0xF
+    out = np.zeros(G + Q, dtype=np.int32)
+    caps = {}
+    for g in range(G):
+        gg = gangs[g]
+        co, so = int(gg["clique_off"]), int(gg["scope_off"])
+        rows = []
+        for c in range(int(gg["n_cliques"])):
+            q = cliques[co + c]
+            sc = scopes[so + (int(q["scope"]) & 0x1F)]
+            need = 0
+            for lv in (int(gg["level"]), int(sc["level"]), int(q["level"])):
+                if lv != T.LEVEL_NONE:
+                    need = max(need, lv + 1)
+            ok = sched & (((int(q["class_mask"]) >> ncls) & 1) != 0) & (vdepth >= need)
+            cap = sn["free_pods"].astype(np.int64)
+            for free, req in ((sn["free_cpu_milli"], int(q["req_cpu_milli"])), (sn["free_mem_mib"], int(q["req_mem_mib"])), (sn["free_gpu"], int(q["req_gpu"]))):
+                if req:
+                    cap = np.minimum(cap, free.astype(np.int64) // req)
+            cap = np.where(ok, np.minimum(cap, 255), 0)
+            rows.append(cap)
+            out[G + co + c] = int(cap[lo:hi].sum())
+        lv = int(gg["level"])
+        if lv != T.LEVEL_NONE:
+            ids = dom[:, lv].astype(np.int64)
+            has = ids != 0xFFFFFFFF
+            nd = int(ids[has].max()) + 1 if has.any() else 0
+            first = np.full(nd, n, dtype=np.int64)
+            np.minimum.at(first, ids[has], np.nonzero(has)[0])
+            good = (first >= lo) & (first < hi)
+            for c, cap in enumerate(rows):
+                m = int(cliques[co + c]["min_replicas"])
+                if m:
+                    good &= np.bincount(ids[has], weights=cap[has], minlength=nd) >= m
+            out[g] = int(good.sum())
+    return out
