@@ -77,6 +77,11 @@ enum Ctl : uint32_t {
   kCtlWords = 16
 };
 
+// Progress words in host-mapped memory, written by the last CTA of k_settle after every round (kLiveRound last, behind a
+// system-wide fence): the host learns that a round is over, whether the cycle is, and whether a table rebuild is due, by
+// reading memory -- no blocking call, no idle GPU between batches of rounds.
+enum Live : uint32_t { kLiveRound = 0, kLiveFront, kLiveDone, kLiveRefresh, kLiveOvf, kLiveEvals, kLiveWords = 8 };
+
 // Relaxation state.  A gang's tentative result ("cur") lives in its own slots of the entry arrays and becomes final
 // in place; "nxt" is the scratch an evaluation writes before k_apply compares and publishes it.
 struct Relax {
@@ -132,6 +137,7 @@ struct Relax {
   uint32_t pl_off[GROVE_MAX_LEVELS], pl_words;
   uint32_t P, window, entry, heavy_att;   // heavy_att: attempts of its last evaluation from which a gang counts as heavy
   uint32_t* dbg;            // [G][8] optional per-gang evaluation statistics
+  uint32_t* live;           // [kLiveWords] host-mapped: progress words the host polls (null: not available)
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {

@@ -180,7 +180,8 @@ struct grove_engine {
   uint32_t tune_entry = 1024;      // gangs that may join the window per round (0: no limit)
   uint32_t tune_refresh = 2048;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
   uint32_t tune_warp_ctas = 2;     // CTAs per SM of the warp-per-gang bookkeeping kernels (apply / detect / settle)
-  uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words
+  uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words (GROVE_TUNE_AHEAD=0 / GROVE_DEBUG_ADMIT)
+  uint32_t tune_ahead = 3;         // rounds kept in the queue while the host follows the relaxation through host-mapped progress words
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
   uint32_t tune_heavy_att = 4;     // a gang whose last evaluation made this many attempts is heavy: kW warps next time
   uint32_t tune_max_att = 4;       // a light (one-warp) evaluation gives up after this many attempts and comes back heavy
@@ -198,6 +199,8 @@ struct grove_engine {
   DevBuf<grove_node_t> d_upd_recs;
   DevBuf<grove_node_t> d_nodes_out;  // grove_get_nodes scratch
   PinBuf<uint32_t> h_ctl;
+  uint32_t* h_live = nullptr;      // host-mapped words the last CTA of k_settle writes every round (round, front, done, refresh, ...):
+  uint32_t* d_live = nullptr;      // the host follows the relaxation by reading memory, without a blocking call (grove_run_cycle)
   PinBuf<grove_gang_status_t> h_status;
   PinBuf<grove_scope_status_t> h_scope_status;
   PinBuf<grove_placement_t> h_out;
@@ -364,6 +367,7 @@ static Relax make_relax(grove_engine* e) {
   for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) r.pl_off[l] = e->pl_off[l];
   r.P = e->P; r.window = e->tune_window ? e->tune_window : (e->G ? e->G : 1u); r.entry = e->tune_entry ? e->tune_entry : r.window; r.heavy_att = e->tune_heavy_att;
   r.dbg = e->dbg_on ? e->d_dbg.p : nullptr;
+  r.live = e->d_live;
   return r;
 }
 
@@ -395,6 +399,7 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
   if (const char* v = std::getenv("GROVE_TUNE_EVAL_CTAS")) e->tune_eval_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_WARP_CTAS")) e->tune_warp_ctas = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_BATCH")) e->tune_batch = uint32_t(std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GROVE_TUNE_AHEAD")) e->tune_ahead = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_HEAVY_ATT")) e->tune_heavy_att = uint32_t(std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_MAX_ATT")) e->tune_max_att = uint32_t(std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("GROVE_TUNE_HEAVY_CTAS")) e->tune_heavy_ctas = uint32_t(std::max(1, std::atoi(v)));
@@ -413,6 +418,8 @@ int32_t grove_engine_create(const grove_config_t* cfg, grove_engine_t** out) {
       cudaEventCreate(&e->ev_s0) != cudaSuccess || cudaEventCreate(&e->ev_s1) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return GROVE_ERR_CUDA; }
   if (e->h_ctl.ensure(kCtlWords) != cudaSuccess) { delete e; return GROVE_ERR_OOM; }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&e->h_live), sizeof(uint32_t) * kLiveWords, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->d_live), e->h_live, 0) != cudaSuccess) { (void)cudaGetLastError(); e->h_live = nullptr; e->d_live = nullptr; }
   *out = e;
   return GROVE_OK;
 }
@@ -432,6 +439,7 @@ void grove_engine_destroy(grove_engine_t* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_score) cudaEventDestroy(e->ev_score);
+  if (e->h_live) cudaFreeHost(e->h_live);
   if (e->stream_score) cudaStreamDestroy(e->stream_score);
   if (e->stream_heavy) cudaStreamDestroy(e->stream_heavy);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -947,6 +955,7 @@ static int32_t cycle_begin(grove_engine* e) {
     c[kFront] = 0; c[kHi] = std::min(G, std::min(W, E)); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
     CU_TRY(e, cudaMemcpyAsync(e->d_ctl.p, c, sizeof(uint32_t) * kCtlWords, cudaMemcpyHostToDevice, st));
     CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
+    if (e->h_live) { std::memset(e->h_live, 0, sizeof(uint32_t) * kLiveWords); e->h_live[kLiveRound] = 1; }
   }
   e->launches = 0; e->in_cycle = true; e->have_results = false; e->have_scopes = false;
   e->victims.clear(); e->score_pass_valid = false;
@@ -1028,30 +1037,59 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     // moved on, and to know when to stop).  GROVE_DEBUG_ADMIT looks after every round.
     const uint32_t batch = e->dbg_on ? 1u : std::max(1u, e->tune_batch);
     uint32_t next_round = 1;   // number of the next round to be enqueued (rounds advance one by one until the cycle is over)
-    for (;;) {
-      for (uint32_t b = 0; b < batch; ++b, ++next_round) {
-        if (next_round > 1 && next_round % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
-          CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
-          CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
-        }
-        k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
-        // heavy gangs (head of the list) on the second stream, kHeavyWarps warps each; light gangs (tail) a warp each
-        CU_TRY(e, cudaEventRecord(e->ev_fork, e->stream));
-        CU_TRY(e, cudaStreamWaitEvent(e->stream_heavy, e->ev_fork, 0));
-        if (e->any_preferred) {
-          k_eval<true, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
-          k_eval<true, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
-        } else {
-          k_eval<false, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
-          k_eval<false, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
-        }
-        CU_TRY(e, cudaEventRecord(e->ev_join, e->stream_heavy));
-        CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
-        k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
-        k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
-        k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
-        e->launches += 6;
+    auto enqueue_round = [&]() -> int32_t {
+      if (next_round > 1 && next_round % kTagRounds == 0) {   // the stamp tags wrap: forget the stamps of the epoch that ends
+        CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
+        CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
       }
+      k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
+      // heavy gangs (head of the list) on the second stream, kHeavyWarps warps each; light gangs (tail) a warp each
+      CU_TRY(e, cudaEventRecord(e->ev_fork, e->stream));
+      CU_TRY(e, cudaStreamWaitEvent(e->stream_heavy, e->ev_fork, 0));
+      if (e->any_preferred) {
+        k_eval<true, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
+        k_eval<true, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
+      } else {
+        k_eval<false, kHeavyWarps, true><<<heavy_ctas, kHeavyWarps * 32, 0, e->stream_heavy>>>(tp, tb, rx, 0);
+        k_eval<false, 1, false><<<eval_ctas, 32, 0, e->stream>>>(tp, tb, rx, e->tune_max_att);
+      }
+      CU_TRY(e, cudaEventRecord(e->ev_join, e->stream_heavy));
+      CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+      k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
+      k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
+      k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
+      e->launches += 6;
+      ++next_round;
+      return GROVE_OK;
+    };
+    // Following the relaxation WITHOUT blocking calls: the last CTA of k_settle leaves (round, done, refresh, ...) in host-mapped
+    // memory; the host keeps `ahead` rounds enqueued beyond the one that runs and adds one more each time it sees a round end
+    // (or a table rebuild first, when the device asked for one).  The GPU never waits for the host; the only waste is the
+    // <= ahead rounds in the queue when the cycle ends, which return at once.
+    const bool polled = e->h_live && e->tune_ahead > 0 && !e->dbg_on;
+    if (polled) {
+      volatile uint32_t* lv = e->h_live;
+      uint32_t enq = 0, rebuild_at = 0;   // rounds enqueued; the last rebuild enqueued runs before round rebuild_at + 1
+      for (; enq < e->tune_ahead; ++enq) { rc = enqueue_round(); if (rc) return rc; }
+      CU_TRY(e, cudaGetLastError());
+      uint64_t spins = 0;
+      for (;;) {
+        const uint32_t completed = lv[kLiveRound] - 1u;
+        if (lv[kLiveDone] && completed >= 1u) break;
+        if (completed + e->tune_ahead > enq) {   // fewer than `ahead` rounds in flight: top the queue up
+          if (lv[kLiveRefresh] && completed > rebuild_at) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; rebuild_at = enq; }   // (the flag is fresh again once round rebuild_at + 1 has ended)
+          rc = enqueue_round(); if (rc) return rc;
+          ++enq; spins = 0;
+          continue;
+        }
+        if ((++spins & 0xFFFFu) == 0) {   // a failed launch / a sticky error must not leave the host spinning
+          const cudaError_t q = cudaStreamQuery(e->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) { e->err = std::string("relaxation: ") + cudaGetErrorString(q); return GROVE_ERR_CUDA; }
+        }
+      }
+    }
+    for (; !polled || next_round == 0;) {   // (the batch protocol: look at the control words between batches of rounds)
+      for (uint32_t b = 0; b < batch; ++b) { rc = enqueue_round(); if (rc) return rc; }
       CU_TRY(e, cudaGetLastError());
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
       CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1073,9 +1111,15 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
         }
         std::fprintf(stderr, "\n");
       }
-      if (c[kDone]) break;
       if (c[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
+      if (c[kDone]) break;
       if (c[kRefresh]) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; }
+    }
+    if (polled) {   // the cycle is over (the queue holds at most a few rounds that return at once): the final control words
+      CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
+      CU_TRY(e, cudaStreamSynchronize(e->stream));
+      if (e->h_ctl.p[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
+      rounds = e->h_ctl.p[kRound] - 1;
     }
     e->last.evaluations = e->h_ctl.p[kEvals];
   }

@@ -284,6 +284,12 @@ __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres
     rx.ctl[kDone] = nf >= G ? 1u : 0u;
     if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every && rx.ctl[kFoldAny]) rx.ctl[kRefresh] = 1;
     __threadfence();
+    if (rx.live) {
+      volatile uint32_t* lv = rx.live;
+      lv[kLiveFront] = nf; lv[kLiveDone] = nf >= G ? 1u : 0u; lv[kLiveRefresh] = rx.ctl[kRefresh]; lv[kLiveOvf] = rx.ctl[kOvfCount]; lv[kLiveEvals] = rx.ctl[kEvals];
+      __threadfence_system();
+      lv[kLiveRound] = rx.ctl[kRound];
+    }
   }
 }
 
