@@ -521,22 +521,23 @@ __device__ __forceinline__ bool scope_plausible(const Topo& tp, const Relax& rb,
   return all != 0;
 }
 
+// one scope of a gang inside the candidate [lo, hi) of level lvl
+__device__ __forceinline__ bool scope_ok(const Topo& tp, const Relax& rb, const GangShared& sh, const grove_scope_t& s,
+                                         uint32_t lo, uint32_t hi, int lvl, uint32_t dD) {
+  if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
+    const uint32_t d0 = __ldg(tp.next_dom[s.level] + lo), d1 = __ldg(tp.next_dom[s.level] + hi);
+    uint32_t any = 0;  // no early exit: children are independent table look-ups
+    for (uint32_t d = d0; d < d1; ++d)
+      any |= scope_plausible(tp, rb, sh, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), d);
+    return any != 0;
+  }
+  return scope_plausible(tp, rb, sh, s, lo, hi, lvl, dD);
+}
+
 __device__ bool gang_plausible(const Topo& tp, const Relax& rb, const GangShared& sh, uint32_t n_scopes,
                                uint32_t lo, uint32_t hi, int lvl, uint32_t dD) {
-  for (uint32_t si = 0; si < n_scopes; ++si) {
-    const grove_scope_t s = sh.scopes[si];
-    bool ok = false;
-    if (s.level != GROVE_LEVEL_NONE && int(s.level) > lvl) {
-      const uint32_t d0 = __ldg(tp.next_dom[s.level] + lo), d1 = __ldg(tp.next_dom[s.level] + hi);
-      uint32_t any = 0;  // no early exit: children are independent table look-ups
-      for (uint32_t d = d0; d < d1; ++d)
-        any |= scope_plausible(tp, rb, sh, s, __ldg(tp.dom_lo[s.level] + d), __ldg(tp.dom_hi[s.level] + d), int(s.level), d);
-      ok = any != 0;
-    } else {
-      ok = scope_plausible(tp, rb, sh, s, lo, hi, lvl, dD);
-    }
-    if (!ok) return false;
-  }
+  for (uint32_t si = 0; si < n_scopes; ++si)
+    if (!scope_ok(tp, rb, sh, sh.scopes[si], lo, hi, lvl, dD)) return false;
   return true;
 }
 
@@ -676,17 +677,20 @@ __device__ __forceinline__ void score_unit(uint32_t req, uint32_t pref, int got,
   num += uint32_t(min(got, want) + 1);
 }
 
-// The candidate pre-filter per (gang shape, domain): one thread per domain of one level, the shape's representative gang
-// staged in shared memory.  Runs after every capacity-table build; k_eval then reads one bit per candidate.
+// The candidate pre-filter per (gang shape, domain): a CTA per 32 domains of one level, FOUR threads per domain (they share the
+// gang's scopes: a base gang's scopes are independent chains of table look-ups), the shape's representative gang staged in
+// shared memory.  Runs after every capacity-table build; k_eval then reads one bit per candidate.
 __global__ void __launch_bounds__(128) k_shape_plaus(Topo tp, Tables tb, Relax rx, const uint32_t* __restrict__ shape_rep) {
   __shared__ GangShared sh;
+  __shared__ uint32_t s_bits;
   const uint32_t shape = blockIdx.y, l = blockIdx.z;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = threadIdx.x & 3u;
   const uint32_t gi = shape_rep[shape];
   const grove_gang_t gg = tb.gangs[gi];
   // candidate levels of the shape: Preferred (if any) down to Required; the whole cluster needs no table
   int first;
   const int base = level_span<true>(gg.level, gg.preferred, -1, first);
-  if (int(l) > first || int(l) < base || l >= tp.L) return;
+  if (int(l) > first || int(l) < base || l >= tp.L || blockIdx.x * 32u >= tp.n_dom[l]) return;
   for (uint32_t c = threadIdx.x; c < gg.n_cliques; c += blockDim.x) {
     const grove_clique_t q = tb.cliques[gg.clique_off + c];
     sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
@@ -695,13 +699,25 @@ __global__ void __launch_bounds__(128) k_shape_plaus(Topo tp, Tables tb, Relax r
     sh.sig[c] = tb.cinfo[gg.clique_off + c].sig;
   }
   for (uint32_t si = threadIdx.x; si < gg.n_scopes; si += blockDim.x) sh.scopes[si] = tb.scopes[gg.scope_off + si];
+  if (threadIdx.x == 0) s_bits = 0;
   __syncthreads();
-  const uint32_t d = blockIdx.x * 128 + threadIdx.x;
-  bool plaus = false;
-  if (d < tp.n_dom[l]) plaus = gang_plausible(tp, rx, sh, gg.n_scopes, __ldg(tp.dom_lo[l] + d), __ldg(tp.dom_hi[l] + d), int(l), d);
-  const uint32_t b = __ballot_sync(kFull, plaus);
-  if ((threadIdx.x & 31) == 0 && (d & ~31u) < ((tp.n_dom[l] + 31u) & ~31u))
-    const_cast<uint32_t*>(rx.shape_bits)[size_t(shape) * rx.pl_words + ((rx.pl_off[l] + d) >> 5)] = b;
+  const uint32_t j = threadIdx.x >> 2, d = blockIdx.x * 32 + j;   // lanes 4j .. 4j + 3 of a warp share domain d
+  bool plaus = d < tp.n_dom[l];
+  if (plaus) {
+    const uint32_t lo = __ldg(tp.dom_lo[l] + d), hi = __ldg(tp.dom_hi[l] + d);
+    for (uint32_t si = slot; si < gg.n_scopes && plaus; si += 4) plaus = scope_ok(tp, rx, sh, sh.scopes[si], lo, hi, int(l), d);
+  }
+  plaus = plaus & bool(__shfl_xor_sync(kFull, uint32_t(plaus), 1));
+  plaus = plaus & bool(__shfl_xor_sync(kFull, uint32_t(plaus), 2));
+  const uint32_t b = __ballot_sync(kFull, plaus && slot == 0);
+  if (lane == 0) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) bits |= ((b >> (4 * k)) & 1u) << k;
+    atomicOr(&s_bits, bits << (warp * 8));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) const_cast<uint32_t*>(rx.shape_bits)[size_t(shape) * rx.pl_words + ((rx.pl_off[l] + blockIdx.x * 32) >> 5)] = s_bits;
 }
 
 // entry i of the round's evaluation list: the heavy gangs from the head, the light ones from the tail (relax.cuh k_select)
@@ -731,7 +747,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
   __shared__ uint32_t s_plaus[32];   // plausible candidates of the current 1024-candidate chunk, in order
   __shared__ uint32_t s_win, s_ext, s_att, s_npl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_eval = rx.ctl[kNEval], n_heavy = rx.ctl[kNHeavy], front = rx.ctl[kFront];
+  const uint32_t n_eval = rx.ctl[kNEval], n_heavy = rx.ctl[kNHeavy];
   if (rx.ctl[kDone]) return;
   GangShared& sh = shs[warp];
   const uint32_t seg_lo = kHeavy ? 0u : n_heavy, seg_hi = kHeavy ? n_heavy : n_eval;
@@ -747,8 +763,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
       // considered at its own turn: the base gang must have been admitted before it (final, or tentatively so far)
       const uint32_t brank = tb.ginfo[gg.base_gang].order;
       uint32_t bs = GROVE_GANG_REJECTED;
-      if (brank < front) bs = rx.state[gg.base_gang];
-      else if (brank < info.order) bs = rx.tstate[gg.base_gang];   // 0 (not evaluated yet): treated as not admitted; its first result marks us dirty
+      if (brank < info.order) bs = rx.tstate[gg.base_gang];   // final for ranks below the front; 0 (not evaluated yet) counts as not admitted: its first result marks us dirty
       if (bs != GROVE_GANG_ADMITTED) trivial = GROVE_GANG_BASE_REJECTED;
     }
     if (trivial) {

@@ -70,14 +70,15 @@ enum Ctl : uint32_t {
   kDone,           // 1 when front == G
   kTablesAt,       // front at the last capacity-table build
   kRefresh,        // 1: rebuild the capacity tables before the next evaluation
-  kCtaDone,        // last-CTA-done counter of k_settle
-  kFoldAny,        // a settle pass folded claims into the committed state
+  kCtaDone,        // last-CTA-done counter of k_detect
+  kFoldAny,        // (unused)
   kNHeavy,         // gangs at the head / tail of eval_list (k_select)
   kNLight,
-  kCtlWords = 16
+  kFolded,         // ranks below this are folded into the committed state (k_fold): folded <= front
+  kCtlWords = 24
 };
 
-// Progress words in host-mapped memory, written by the last CTA of k_settle after every round (kLiveRound last, behind a
+// Progress words in host-mapped memory, written by the last CTA of k_detect after every round (kLiveRound last, behind a
 // system-wide fence): the host learns that a round is over, whether the cycle is, and whether a table rebuild is due, by
 // reading memory -- no blocking call, no idle GPU between batches of rounds.
 enum Live : uint32_t { kLiveRound = 0, kLiveFront, kLiveDone, kLiveRefresh, kLiveOvf, kLiveEvals, kLiveWords = 8 };

@@ -199,7 +199,7 @@ struct grove_engine {
   DevBuf<grove_node_t> d_upd_recs;
   DevBuf<grove_node_t> d_nodes_out;  // grove_get_nodes scratch
   PinBuf<uint32_t> h_ctl;
-  uint32_t* h_live = nullptr;      // host-mapped words the last CTA of k_settle writes every round (round, front, done, refresh, ...):
+  uint32_t* h_live = nullptr;      // host-mapped words the last CTA of k_detect writes every round (round, front, done, refresh, ...):
   uint32_t* d_live = nullptr;      // the host follows the relaxation by reading memory, without a blocking call (grove_run_cycle)
   PinBuf<grove_gang_status_t> h_status;
   PinBuf<grove_scope_status_t> h_scope_status;
@@ -884,16 +884,23 @@ static int32_t build_ginfo(grove_engine* e) {
 static int32_t build_cap_tables(grove_engine* e, const Topo& tp, const Tables& tb, const Relax& rx) {
   if (!e->n_sigs) return GROVE_OK;
   dim3 gfit(e->Npad / 1024, std::min<uint32_t>((e->n_sigs + kFitTile - 1) / kFitTile, 65535u));
-  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p);
-  if (e->cap_stride) {
-    const uint64_t warps = uint64_t(e->n_sigs) * e->cap_stride;
-    k_capsum<<<uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, e->n_sm * 32u))), 256, 0, e->stream>>>(tp, e->n_sigs, e->d_cap8.p, e->d_capsum.p, e->d_capmax.p);
+  if (e->cap_stride) {   // k_fit accumulates the per-domain sums / maxima with atomics
+    CU_TRY(e, cudaMemsetAsync(e->d_capsum.p, 0, sizeof(uint32_t) * size_t(e->n_sigs) * e->cap_stride, e->stream));
+    CU_TRY(e, cudaMemsetAsync(e->d_capmax.p, 0, sizeof(uint32_t) * size_t(e->n_sigs) * e->cap_stride, e->stream));
   }
+  k_fit<<<gfit, 1024, 0, e->stream>>>(tp, tb, e->d_F.p, e->d_cap8.p, e->cap_stride ? e->d_capsum.p : nullptr, e->cap_stride ? e->d_capmax.p : nullptr);
   k_clear_stale<<<(e->Npad / 4 + 255) / 256, 256, 0, e->stream>>>(rx, e->Npad / 4);
   if (e->shape_tables) {   // the candidate pre-filter of every gang shape over every domain of its candidate levels
+    // only the levels some shape takes its candidates from (Preferred down to Required): a CTA that has nothing to do still
+    // costs its launch, and the unit level alone would be tens of thousands of them
     uint32_t mx = 0;
-    for (uint32_t l = 0; l < e->L; ++l) mx = std::max(mx, e->n_dom[l]);
-    k_shape_plaus<<<dim3((mx + 127) / 128, e->n_shapes, e->L), 128, 0, e->stream>>>(tp, tb, rx, e->d_shape_rep.p);
+    for (uint32_t i = 0; i < e->n_shapes; ++i) {
+      const grove_gang_t& g = e->gangs[e->shape_rep[i]];
+      const int base = g.level != GROVE_LEVEL_NONE ? int(g.level) : -1;
+      const int first = g.preferred != GROVE_LEVEL_NONE && int(g.preferred) > base ? int(g.preferred) : base;
+      for (int l = std::max(base, 0); l <= first && l < int(e->L); ++l) mx = std::max(mx, e->n_dom[l]);
+    }
+    if (mx) k_shape_plaus<<<dim3((mx + 31) / 32, e->n_shapes, e->L), 128, 0, e->stream>>>(tp, tb, rx, e->d_shape_rep.p);
     e->launches += 1;
   }
   CU_TRY(e, cudaGetLastError());
@@ -1056,13 +1063,20 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       CU_TRY(e, cudaEventRecord(e->ev_join, e->stream_heavy));
       CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
       k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
-      k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx);
-      k_settle<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p, e->tune_refresh);
-      e->launches += 6;
+      k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx, e->tune_refresh);
+      e->launches += 5;
       ++next_round;
       return GROVE_OK;
     };
-    // Following the relaxation WITHOUT blocking calls: the last CTA of k_settle leaves (round, done, refresh, ...) in host-mapped
+    auto fold = [&]() -> int32_t {   // the final gangs' claims -> committed state (relax.cuh k_fold)
+      k_fold<<<warp_ctas, 256, 0, e->stream>>>(tb, rx, e->d_nres.p);
+      k_fold_mark<<<1, 1, 0, e->stream>>>(rx);
+      e->launches += 2;
+      CU_TRY(e, cudaGetLastError());
+      return GROVE_OK;
+    };
+    auto fold_and_rebuild = [&]() -> int32_t { int32_t r = fold(); return r ? r : build_cap_tables(e, tp, tb, rx); };
+    // Following the relaxation WITHOUT blocking calls: the last CTA of k_detect leaves (round, done, refresh, ...) in host-mapped
     // memory; the host keeps `ahead` rounds enqueued beyond the one that runs and adds one more each time it sees a round end
     // (or a table rebuild first, when the device asked for one).  The GPU never waits for the host; the only waste is the
     // <= ahead rounds in the queue when the cycle ends, which return at once.
@@ -1077,7 +1091,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
         const uint32_t completed = lv[kLiveRound] - 1u;
         if (lv[kLiveDone] && completed >= 1u) break;
         if (completed + e->tune_ahead > enq) {   // fewer than `ahead` rounds in flight: top the queue up
-          if (lv[kLiveRefresh] && completed > rebuild_at) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; rebuild_at = enq; }   // (the flag is fresh again once round rebuild_at + 1 has ended)
+          if (lv[kLiveRefresh] && completed > rebuild_at) { rc = fold_and_rebuild(); if (rc) return rc; rebuild_at = enq; }   // (the flag is fresh again once round rebuild_at + 1 has ended)
           rc = enqueue_round(); if (rc) return rc;
           ++enq; spins = 0;
           continue;
@@ -1113,7 +1127,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       }
       if (c[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
       if (c[kDone]) break;
-      if (c[kRefresh]) { rc = build_cap_tables(e, tp, tb, rx); if (rc) return rc; }
+      if (c[kRefresh]) { rc = fold_and_rebuild(); if (rc) return rc; }
     }
     if (polled) {   // the cycle is over (the queue holds at most a few rounds that return at once): the final control words
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
@@ -1121,6 +1135,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       if (e->h_ctl.p[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
       rounds = e->h_ctl.p[kRound] - 1;
     }
+    rc = fold(); if (rc) return rc;   // everything is final now: the committed state and the final states of the outputs
     e->last.evaluations = e->h_ctl.p[kEvals];
   }
   CU_TRY(e, cudaEventRecord(e->ev[3], e->stream));

@@ -5,7 +5,7 @@
 //                k_cap8 / k_capsum  per-signature pod capacities and their per-domain sum / max
 //   score.cuh    k_score K2 topology-distance score matrix, u8            (Score;  oracle: closeness())
 //   admit.cuh    k_eval  K3  one gang against its view: all-or-nothing admission, warp-cooperative packing
-//   relax.cuh    k_select / k_apply / k_detect / k_settle  the relaxation that makes the evaluations of all gangs
+//   relax.cuh    k_select / k_apply / k_detect / k_fold    the relaxation that makes the evaluations of all gangs
 //                agree with the sequential, priority-ordered pass; k_fin_* / k_emit  outputs
 //
 // Semantics are DESIGN.md "Placement semantics"; the reference contract they restate is cited in

@@ -17,8 +17,11 @@ namespace grove {
 //           k_detect   whose view changed?  a gang is dirty if a LOWER rank added a claim on a node it uses
 //                      (capacity it counted on is gone), withdrew a claim in front of its extent (capacity it did
 //                      not see is back), or its base gang's result changed.  front' = lowest dirty rank.
-//           k_settle   gangs of rank < front' are final: every rank before them is final and their last
-//                      evaluation saw exactly those claims.  Their claims are folded into the committed state.
+//                      Gangs of rank < front' are final: every rank before them is final and their last evaluation saw
+//                      exactly those claims.  The last CTA of k_detect advances the window.
+//   now and then (before a capacity-table rebuild, and when the cycle ends):
+//           k_fold     the claims of the final gangs are folded into the committed state (until then they simply stay
+//                      claims: every gang of the window ranks after them and subtracts them anyway).
 //
 // Why it is exact: by induction on rank, a gang that is not dirty while everything before it is final holds the
 // sequential answer.  Why it terminates: the lowest gang of the window is never dirty after its evaluation.
@@ -198,9 +201,10 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
 }
 
 // one warp per gang of the window: did its view change this round?
-__global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx) {
+__global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx, uint32_t refresh_every) {
+  __shared__ bool s_last;
   const uint32_t lane = threadIdx.x & 31;
-  if (rx.ctl[kDone]) return;
+  if (rx.ctl[kDone]) return;   // uniform over the grid: set only by the last CTA of an earlier launch
   const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi], round = rx.ctl[kRound];
   const uint32_t rem_any = rx.ctl[kRemAny];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -237,18 +241,40 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx) {
     }
     if (dirty && lane == 0) { rx.dirty[g] = 1; atomicMin(rx.ctl + kMinDirty, p); }
   }
+  // the last CTA to finish advances the window and resets the per-round control words
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(rx.ctl + kCtaDone, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    const uint32_t G = tb.G;
+    const uint32_t nf = *reinterpret_cast<volatile uint32_t*>(rx.ctl + kMinDirty);
+    // the window: at most `window` gangs beyond the settled prefix, at most `entry` new ones per round (gangs that meet
+    // the claims of the ranks before them on their first evaluation pile up less on the same nodes)
+    const uint32_t h2 = min(G, min(nf + rx.window, max(rx.ctl[kHi], nf) + rx.entry));
+    rx.ctl[kEvals] += rx.ctl[kNEval];
+    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kNHeavy] = 0; rx.ctl[kNLight] = 0; rx.ctl[kChanged] = 0;
+    rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
+    rx.ctl[kDone] = nf >= G ? 1u : 0u;
+    if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every) rx.ctl[kRefresh] = 1;
+    __threadfence();
+    if (rx.live) {
+      volatile uint32_t* lv = rx.live;
+      lv[kLiveFront] = nf; lv[kLiveDone] = nf >= G ? 1u : 0u; lv[kLiveRefresh] = rx.ctl[kRefresh]; lv[kLiveOvf] = rx.ctl[kOvfCount]; lv[kLiveEvals] = rx.ctl[kEvals];
+      __threadfence_system();
+      lv[kLiveRound] = rx.ctl[kRound];
+    }
+  }
 }
 
-// one warp per gang that became final: fold its claims into the committed state.  The last CTA to finish advances
-// the window and resets the per-round control words.
-__global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres, uint32_t refresh_every) {
-  __shared__ bool s_last;
+// one warp per gang that became final since the last fold: its claims move into the committed state.  Not every round: the
+// claims of final gangs are as good as committed for everybody who ranks after them, so the fold runs before a capacity-table
+// rebuild (the tables are built from the committed state) and when the cycle ends; k_fold_mark then moves the marker.
+__global__ void __launch_bounds__(256) k_fold(Tables tb, Relax rx, uint4* nres) {
   const uint32_t lane = threadIdx.x & 31;
-  if (rx.ctl[kDone]) return;   // uniform over the grid: set only by the last CTA of an earlier launch
-  const uint32_t front = rx.ctl[kFront], nf = rx.ctl[kMinDirty];
+  const uint32_t lo = rx.ctl[kFolded], hi = rx.ctl[kFront];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-  bool folded = false;
-  for (uint32_t p = front + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < nf; p += nw) {
+  for (uint32_t p = lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < hi; p += nw) {
     const uint32_t g = tb.by_rank[p];
     const uint32_t t = rx.tstate[g];
     if (lane == 0) rx.state[g] = uint8_t(t);
@@ -266,32 +292,9 @@ __global__ void __launch_bounds__(256) k_settle(Tables tb, Relax rx, uint4* nres
       atomicSub(r + 2, len * uint32_t(q.req_gpu) | (len << 16));
       atomicOr(rx.nlive + (n >> 2), kStale << ((n & 3u) * 8u));   // the capacity tables no longer describe this node
     }
-    folded |= cnt != 0;
-  }
-  if (__any_sync(kFull, folded) && lane == 0) rx.ctl[kFoldAny] = 1;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(rx.ctl + kCtaDone, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    const uint32_t G = tb.G;
-    // the window: at most `window` gangs beyond the settled prefix, at most `entry` new ones per round (gangs that meet
-    // the claims of the ranks before them on their first evaluation pile up less on the same nodes)
-    const uint32_t h2 = min(G, min(nf + rx.window, max(rx.ctl[kHi], nf) + rx.entry));
-    rx.ctl[kEvals] += rx.ctl[kNEval];
-    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kNHeavy] = 0; rx.ctl[kNLight] = 0; rx.ctl[kChanged] = 0;
-    rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
-    rx.ctl[kDone] = nf >= G ? 1u : 0u;
-    if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every && rx.ctl[kFoldAny]) rx.ctl[kRefresh] = 1;
-    __threadfence();
-    if (rx.live) {
-      volatile uint32_t* lv = rx.live;
-      lv[kLiveFront] = nf; lv[kLiveDone] = nf >= G ? 1u : 0u; lv[kLiveRefresh] = rx.ctl[kRefresh]; lv[kLiveOvf] = rx.ctl[kOvfCount]; lv[kLiveEvals] = rx.ctl[kEvals];
-      __threadfence_system();
-      lv[kLiveRound] = rx.ctl[kRound];
-    }
   }
 }
+__global__ void k_fold_mark(Relax rx) { rx.ctl[kFolded] = rx.ctl[kFront]; }
 
 // after a capacity-table build: the tables describe every node again
 __global__ void k_clear_stale(Relax rx, uint32_t n_words) {
