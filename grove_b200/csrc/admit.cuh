@@ -720,10 +720,13 @@ __global__ void __launch_bounds__(128) k_shape_plaus(Topo tp, Tables tb, Relax r
   if (threadIdx.x == 0) const_cast<uint32_t*>(rx.shape_bits)[size_t(shape) * rx.pl_words + ((rx.pl_off[l] + blockIdx.x * 32) >> 5)] = s_bits;
 }
 
-// entry i of the round's evaluation list: the heavy gangs from the head, the light ones from the tail (relax.cuh k_select)
-__device__ __forceinline__ uint32_t eval_list_at(const Relax& rx, uint32_t G, uint32_t i) {
-  const uint32_t nh = rx.ctl[kNHeavy];
-  return i < nh ? rx.eval_list[i] : rx.eval_list[G - 1u - (i - nh)];
+// entry i of the round's evaluations: the heavy gangs of the list (from its head), the light ones (from its tail), then the new
+// entrants of the window (ranks [kEntryLo, kHi): never evaluated, they need no list entry).  relax.cuh k_detect builds the list.
+__device__ __forceinline__ uint32_t eval_list_at(const Relax& rx, const Tables& tb, uint32_t i) {
+  const uint32_t nh = rx.ctl[kNHeavy], nl = rx.ctl[kNLight];
+  if (i < nh) return rx.eval_list[i];
+  if (i - nh < nl) return rx.eval_list[tb.G - 1u - (i - nh)];
+  return tb.by_rank[rx.ctl[kEntryLo] + (i - nh - nl)];
 }
 
 // K3 launch forms: kW warps share ONE gang.  The candidates of the gang's level are pre-filtered 1024 at a time by all
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
   GangShared& sh = shs[warp];
   const uint32_t seg_lo = kHeavy ? 0u : n_heavy, seg_hi = kHeavy ? n_heavy : n_eval;
   for (uint32_t ei = seg_lo + blockIdx.x; ei < seg_hi; ei += gridDim.x) {
-    const uint32_t gi = eval_list_at(rx, tb.G, ei);
+    const uint32_t gi = eval_list_at(rx, tb, ei);
     const grove_gang_t gg = tb.gangs[gi];
     const GangInfo info = tb.ginfo[gi];
     __syncthreads();   // the previous gang's shared state is no longer read

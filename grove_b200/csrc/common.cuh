@@ -61,7 +61,7 @@ enum Ctl : uint32_t {
   kFront = 0,      // settled prefix: every gang of rank < front is final
   kHi,             // window end: gangs of rank in [front, hi) relax
   kRound,          // relaxation round, from 1
-  kNEval,          // gangs in eval_list this round
+  kNEval,          // gangs evaluated this round: the list (heavy + light) and the new entrants
   kMinDirty,       // lowest rank that has to be (re-)evaluated after this round (becomes the next front)
   kChanged,        // gangs whose tentative result changed this round
   kEvals,          // evaluations so far (stat)
@@ -72,9 +72,12 @@ enum Ctl : uint32_t {
   kRefresh,        // 1: rebuild the capacity tables before the next evaluation
   kCtaDone,        // last-CTA-done counter of k_detect
   kFoldAny,        // (unused)
-  kNHeavy,         // gangs at the head / tail of eval_list (k_select)
+  kNHeavy,         // gangs at the head / tail of eval_list (written by k_detect of the round before)
   kNLight,
   kFolded,         // ranks below this are folded into the committed state (k_fold): folded <= front
+  kEntryLo,        // this round's new entrants are the ranks [kEntryLo, kHi): never evaluated, no list entry needed
+  kNHeavyNext,     // the NEXT round's list counters, filled by k_detect while this round's are still being read
+  kNLightNext,
   kCtlWords = 24
 };
 
@@ -91,7 +94,7 @@ struct Relax {
   uint8_t* tstate;          // [G] tentative state of the last evaluation (0 = never evaluated)
   uint8_t* dirty;           // [G] must be re-evaluated next round
   uint32_t* chg_round;      // [G] last round in which the gang's tentative result changed
-  uint32_t* eval_list;      // [G] heavy gangs from the head, light ones from the tail (k_select)
+  uint32_t* eval_list;      // [G] the gangs to re-evaluate: heavy ones from the head, light ones from the tail (k_detect)
   uint8_t* last_att;        // [G] attempt rounds the gang's last evaluation needed
   // tentative / final result per gang
   uint32_t* ent_node;       // [P]

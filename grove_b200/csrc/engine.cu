@@ -960,6 +960,7 @@ static int32_t cycle_begin(grove_engine* e) {
     const uint32_t W = e->tune_window ? e->tune_window : std::max(G, 1u);
     const uint32_t E = e->tune_entry ? e->tune_entry : W;
     c[kFront] = 0; c[kHi] = std::min(G, std::min(W, E)); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
+    c[kEntryLo] = 0; c[kNEval] = c[kHi];   // the first round evaluates the first window's worth of new entrants
     CU_TRY(e, cudaMemcpyAsync(e->d_ctl.p, c, sizeof(uint32_t) * kCtlWords, cudaMemcpyHostToDevice, st));
     CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
     if (e->h_live) { std::memset(e->h_live, 0, sizeof(uint32_t) * kLiveWords); e->h_live[kLiveRound] = 1; }
@@ -1049,7 +1050,6 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
         CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * e->Npad, e->stream));
         CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, e->stream));
       }
-      k_select<<<(W + 255) / 256, 256, 0, e->stream>>>(tb, rx);
       // heavy gangs (head of the list) on the second stream, kHeavyWarps warps each; light gangs (tail) a warp each
       CU_TRY(e, cudaEventRecord(e->ev_fork, e->stream));
       CU_TRY(e, cudaStreamWaitEvent(e->stream_heavy, e->ev_fork, 0));
@@ -1064,7 +1064,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
       k_apply<<<warp_ctas, 256, 0, e->stream>>>(tb, rx);
       k_detect<<<warp_ctas, 256, 0, e->stream>>>(tp, tb, rx, e->tune_refresh);
-      e->launches += 5;
+      e->launches += 4;
       ++next_round;
       return GROVE_OK;
     };

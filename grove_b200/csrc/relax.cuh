@@ -10,8 +10,8 @@ namespace grove {
 // evaluation against (committed state - claims of all gangs that rank before it).  The engine iterates
 // towards that fixed point with all gangs of a window at once:
 //
-//   round:  k_select   gangs of the window [front, hi) that were never evaluated or whose view changed
-//           k_eval     (admit.cuh) each of them against its view -> "nxt" scratch            [reads claims]
+//   round:  k_eval     (admit.cuh) the gangs of the window [front, hi) that were never evaluated (the new entrants) or whose
+//                      view changed (the list k_detect left), each against its view -> "nxt" scratch   [reads claims]
 //           k_apply    a changed result withdraws the gang's old claims and publishes the new
 //                      ones; every withdrawal / addition leaves a stamp (round tag | rank)   [writes claims]
 //           k_detect   whose view changed?  a gang is dirty if a LOWER rank added a claim on a node it uses
@@ -29,33 +29,6 @@ namespace grove {
 // can only matter on the nodes a gang actually uses, and infeasible candidates stay infeasible.
 // Nothing here decides a result by arrival order: claims are sums, stamps are minima.
 // ------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) k_select(Tables tb, Relax rx) {
-  if (rx.ctl[kDone]) return;   // the host enqueues rounds ahead of knowing that the cycle is over
-  const uint32_t front = rx.ctl[kFront], hi = rx.ctl[kHi];
-  const uint32_t p = front + blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31;
-  bool need = false; uint32_t g = 0;
-  if (p < hi) {
-    g = tb.by_rank[p];
-    need = rx.tstate[g] == 0 || rx.dirty[g];
-    if (need) rx.dirty[g] = 0;
-  }
-  // longest first: a round lasts as long as its slowest evaluation, so the gangs that needed several attempts last
-  // time go to the head of the list (CTAs are handed out in list order), the others fill it from the tail
-  const bool heavy = need && rx.last_att[g] >= rx.heavy_att;
-  const uint32_t bh = __ballot_sync(kFull, heavy), bl = __ballot_sync(kFull, need && !heavy);
-  uint32_t base_h = 0, base_l = 0;
-  if (lane == 0) {
-    if (bh) base_h = atomicAdd(rx.ctl + kNHeavy, __popc(bh));
-    if (bl) base_l = atomicAdd(rx.ctl + kNLight, __popc(bl));
-    if (bh | bl) atomicAdd(rx.ctl + kNEval, __popc(bh | bl));
-  }
-  base_h = __shfl_sync(kFull, base_h, 0); base_l = __shfl_sync(kFull, base_l, 0);
-  const uint32_t below = (1u << lane) - 1u;
-  if (heavy) rx.eval_list[base_h + __popc(bh & below)] = g;
-  else if (need) rx.eval_list[tb.G - 1u - (base_l + __popc(bl & below))] = g;
-}
 
 // ---- claims --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void nlive_add(uint32_t* nlive, uint32_t n, int delta) {
@@ -150,12 +123,13 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
   const uint32_t n_eval = rx.ctl[kNEval], round = rx.ctl[kRound];
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < n_eval; ei += nw) {
-    const uint32_t g = eval_list_at(rx, tb.G, ei);
+    const uint32_t g = eval_list_at(rx, tb, ei);
     const grove_gang_t gg = tb.gangs[g];
     const uint32_t po = tb.ginfo[g].pod_off, rank = tb.ginfo[g].order;
     const uint32_t ot = rx.tstate[g], nt = rx.nxt_tstate[g];
+    if (lane == 0) rx.dirty[g] = nt == kEvalDeferred;   // the only dirtiness that outlives a round: no result yet
     if (nt == kEvalDeferred) {   // the light evaluation gave up: no result, the gang is evaluated again (as a heavy one) next round
-      if (lane == 0) { rx.dirty[g] = 1; atomicMin(rx.ctl + kMinDirty, rank); }
+      if (lane == 0) atomicMin(rx.ctl + kMinDirty, rank);
       continue;
     }
     const uint32_t on = ot == GROVE_GANG_ADMITTED ? rx.cur_n[g] : 0u, nn = nt == GROVE_GANG_ADMITTED ? rx.nxt_n[g] : 0u;
@@ -211,7 +185,7 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx, ui
   for (uint32_t p = front + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < hi; p += nw) {
     const uint32_t g = tb.by_rank[p];   // rank of g == p
     const grove_gang_t gg = tb.gangs[g];
-    bool dirty = false;
+    bool dirty = rx.dirty[g] != 0;   // its evaluation gave up this round (k_apply)
     // its base gang's result changed
     if (gg.base_gang != GROVE_NONE_U32 && rx.chg_round[gg.base_gang] == round) dirty = true;
     // a lower rank newly claimed a node this gang uses
@@ -239,7 +213,13 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx, ui
         dirty = __any_sync(kFull, hit);
       }
     }
-    if (dirty && lane == 0) { rx.dirty[g] = 1; atomicMin(rx.ctl + kMinDirty, p); }
+    if (dirty && lane == 0) {
+      atomicMin(rx.ctl + kMinDirty, p);
+      // the next round's list.  Longest first: a round lasts as long as its slowest evaluation, so the gangs whose last evaluation
+      // needed several attempts get kHeavyWarps warps (head of the list), the others a warp each (tail)
+      if (rx.last_att[g] >= rx.heavy_att) rx.eval_list[atomicAdd(rx.ctl + kNHeavyNext, 1u)] = g;
+      else rx.eval_list[tb.G - 1u - atomicAdd(rx.ctl + kNLightNext, 1u)] = g;
+    }
   }
   // the last CTA to finish advances the window and resets the per-round control words
   __threadfence();
@@ -252,8 +232,12 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx, ui
     // the window: at most `window` gangs beyond the settled prefix, at most `entry` new ones per round (gangs that meet
     // the claims of the ranks before them on their first evaluation pile up less on the same nodes)
     const uint32_t h2 = min(G, min(nf + rx.window, max(rx.ctl[kHi], nf) + rx.entry));
+    const uint32_t old_hi = max(rx.ctl[kHi], nf);   // (nf <= hi always: the lowest dirty rank lies inside the window or is its end)
+    const uint32_t nh = rx.ctl[kNHeavyNext], nl = rx.ctl[kNLightNext];
     rx.ctl[kEvals] += rx.ctl[kNEval];
-    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kNEval] = 0; rx.ctl[kNHeavy] = 0; rx.ctl[kNLight] = 0; rx.ctl[kChanged] = 0;
+    rx.ctl[kFront] = nf; rx.ctl[kHi] = h2; rx.ctl[kMinDirty] = h2; rx.ctl[kChanged] = 0;
+    rx.ctl[kEntryLo] = old_hi; rx.ctl[kNHeavy] = nh; rx.ctl[kNLight] = nl; rx.ctl[kNEval] = nh + nl + (h2 - min(old_hi, h2));
+    rx.ctl[kNHeavyNext] = 0; rx.ctl[kNLightNext] = 0;
     rx.ctl[kRound] += 1; rx.ctl[kRemAny] = kFull; rx.ctl[kCtaDone] = 0;
     rx.ctl[kDone] = nf >= G ? 1u : 0u;
     if (nf < G && nf - rx.ctl[kTablesAt] >= refresh_every) rx.ctl[kRefresh] = 1;
