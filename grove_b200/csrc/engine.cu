@@ -178,13 +178,13 @@ struct grove_engine {
   DevBuf<uint32_t> d_dbg;
   uint32_t tune_window = 0;        // gangs beyond the settled prefix that relax concurrently (0: all)
   uint32_t tune_entry = 1024;      // gangs that may join the window per round (0: no limit)
-  uint32_t tune_refresh = 2048;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
-  uint32_t tune_warp_ctas = 2;     // CTAs per SM of the warp-per-gang bookkeeping kernels (apply / detect / settle)
+  uint32_t tune_refresh = 1536;    // rebuild the capacity tables once the settled prefix has advanced this many gangs
+  uint32_t tune_warp_ctas = 4;     // CTAs per SM of the warp-per-gang bookkeeping kernels (apply / detect / settle)
   uint32_t tune_batch = 3;         // rounds enqueued between two looks at the control words (GROVE_TUNE_AHEAD=0 / GROVE_DEBUG_ADMIT)
   uint32_t tune_ahead = 3;         // rounds kept in the queue while the host follows the relaxation through host-mapped progress words
   uint32_t tune_eval_ctas = 0;     // k_eval CTAs per SM
   uint32_t tune_heavy_att = 4;     // a gang whose last evaluation made this many attempts is heavy: kW warps next time
-  uint32_t tune_max_att = 4;       // a light (one-warp) evaluation gives up after this many attempts and comes back heavy
+  uint32_t tune_max_att = 3;       // a light (one-warp) evaluation gives up after this many attempts and comes back heavy
   uint32_t tune_heavy_ctas = 2;    // heavy-form CTAs per SM
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool tune_overlap = true;        // K2 on a second stream beside the relaxation (GROVE_TUNE_OVERLAP=0 serialises them, e.g. to time K2 alone)

@@ -17,28 +17,41 @@ from __future__ import annotations
 
 from . import tables as T
 
-_BIN = {"Ki": 2 ** 10, "Mi": 2 ** 20, "Gi": 2 ** 30, "Ti": 2 ** 40, "Pi": 2 ** 50}
-_DEC = {"k": 10 ** 3, "M": 10 ** 6, "G": 10 ** 9, "T": 10 ** 12}
+from fractions import Fraction
+
+# resource.Quantity suffixes (k8s.io/apimachinery/pkg/api/resource): binary SI, decimal SI, milli
+_BIN = {"Ki": 2 ** 10, "Mi": 2 ** 20, "Gi": 2 ** 30, "Ti": 2 ** 40, "Pi": 2 ** 50, "Ei": 2 ** 60}
+_DEC = {"m": Fraction(1, 1000), "k": 10 ** 3, "M": 10 ** 6, "G": 10 ** 9, "T": 10 ** 12, "P": 10 ** 15, "E": 10 ** 18}
 
 
-def parse_cpu_milli(q) -> int:
-    """Kubernetes CPU quantity -> millicores ("64" -> 64000, "500m" -> 500, 0.5 -> 500)."""
-    s = str(q).strip()
-    if s.endswith("m"):
-        return int(s[:-1])
-    return int(round(float(s) * 1000))
-
-
-def parse_mem_mib(q) -> int:
-    """Kubernetes memory quantity -> MiB, rounded down ("512Gi" -> 524288, "150Mi" -> 150)."""
+def _quantity(q) -> Fraction:
+    """a Kubernetes quantity as an exact number of base units ("1500m" -> 3/2, "1Gi" -> 2**30, "1e3" -> 1000)"""
     s = str(q).strip()
     for suf, mul in _BIN.items():
         if s.endswith(suf):
-            return int(float(s[: -len(suf)]) * mul) // 2 ** 20
+            return Fraction(s[: -len(suf)]) * mul
     for suf, mul in _DEC.items():
-        if s.endswith(suf):
-            return int(float(s[: -len(suf)]) * mul) // 2 ** 20
-    return int(float(s)) // 2 ** 20
+        if s.endswith(suf) and not s[: -len(suf)].endswith(("e", "E")):
+            return Fraction(s[: -len(suf)]) * mul
+    return Fraction(s)
+
+
+def _ceil(x: Fraction) -> int:
+    return -((-x.numerator) // x.denominator)
+
+
+def parse_cpu_milli(q, request: bool = False) -> int:
+    """Kubernetes CPU quantity -> millicores ("64" -> 64000, "500m" -> 500, 0.5 -> 500, "2k" -> 2000000).  A pod's request is
+    rounded UP, what a node offers DOWN (Kubernetes rounds requests up: under-counting them would over-commit nodes)."""
+    x = _quantity(q) * 1000
+    return _ceil(x) if request else x.numerator // x.denominator
+
+
+def parse_mem_mib(q, request: bool = False) -> int:
+    """Kubernetes memory quantity -> MiB ("512Gi" -> 524288, "150Mi" -> 150, "100M" -> 95 offered / 96 requested,
+    "500Ki" -> 0 offered / 1 requested)."""
+    x = _quantity(q) / 2 ** 20
+    return _ceil(x) if request else x.numerator // x.denominator
 
 
 def nodes_from_manifests(manifests, level_keys, class_key=None, used=None):
@@ -57,8 +70,8 @@ def nodes_from_manifests(manifests, level_keys, class_key=None, used=None):
         names.append(meta.get("name", f"node-{i}"))
         alloc = status.get("allocatable") or status.get("capacity") or {}
         u = (used or {}).get(names[-1], {})
-        nodes["free_cpu_milli"][i] = max(0, parse_cpu_milli(alloc.get("cpu", 0)) - parse_cpu_milli(u.get("cpu", 0)))
-        nodes["free_mem_mib"][i] = max(0, parse_mem_mib(alloc.get("memory", 0)) - parse_mem_mib(u.get("memory", 0)))
+        nodes["free_cpu_milli"][i] = max(0, parse_cpu_milli(alloc.get("cpu", 0)) - parse_cpu_milli(u.get("cpu", 0), request=True))
+        nodes["free_mem_mib"][i] = max(0, parse_mem_mib(alloc.get("memory", 0)) - parse_mem_mib(u.get("memory", 0), request=True))
         nodes["free_gpu"][i] = max(0, int(alloc.get("nvidia.com/gpu", 0)) - int(u.get("nvidia.com/gpu", 0)))
         nodes["free_pods"][i] = max(0, int(alloc.get("pods", 110)) - int(u.get("pods", 0)))
         labels = meta.get("labels", {}) or {}
@@ -110,7 +123,7 @@ def podgangs_from_manifests(podgangs, requests, level_keys, priority_classes=Non
         def clique(g):
             rq = requests.get(g["name"], {})
             names.append((pg["metadata"]["name"], g["name"]))
-            return dict(cpu=parse_cpu_milli(rq.get("cpu", 0)), mem=parse_mem_mib(rq.get("memory", 0)),
+            return dict(cpu=parse_cpu_milli(rq.get("cpu", 0), request=True), mem=parse_mem_mib(rq.get("memory", 0), request=True),
                         gpu=int(rq.get("nvidia.com/gpu", 0)), min=int(g["minReplicas"]), replicas=len(g["podReferences"]),
                         level=_level(g.get("topologyConstraint"), level_keys),
                         preferred=_preferred(g.get("topologyConstraint"), level_keys), class_mask=class_mask)

@@ -24,6 +24,16 @@ def test_quantities():
     assert ingest.parse_mem_mib("1G") == 953
 
 
+def test_quantities_round_requests_up_and_offers_down():
+    """resource.Quantity suffix set (m, k, M, G, T, P, E, Ki..Ei); a request is rounded up, what a node offers down (ADVICE
+    round 1: flooring requests under-counts them and over-commits nodes)"""
+    c, m = ingest.parse_cpu_milli, ingest.parse_mem_mib
+    assert c("2k") == 2_000_000 and c("1e3") == 1_000_000 and c("0.0005") == 0 and c("0.0005", request=True) == 1
+    assert m("100M") == 95 and m("100M", request=True) == 96
+    assert m("500Ki") == 0 and m("500Ki", request=True) == 1
+    assert m("1500m", request=True) == 1 and m("1Ei") == 2 ** 40 and m("1P") == 10 ** 15 // 2 ** 20 and m("2E") == 2 * 10 ** 18 // 2 ** 20
+
+
 def test_reference_kwok_manifests_match_the_synthetic_generator(kwok):
     """our label arithmetic (synth.kwok_nodes) == what the reference generator labels its nodes with"""
     keys = [kwok["label_keys"][k] for k in ("zone", "block", "rack", "host")]
