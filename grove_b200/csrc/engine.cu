@@ -943,27 +943,12 @@ static int32_t cycle_begin(grove_engine* e) {
     }
   }
   if (e->dbg_on) { CU_TRY(e, e->d_dbg.ensure(g1 * 8 + 8)); CU_TRY(e, cudaMemsetAsync(e->d_dbg.p, 0, g1 * 32 + 32, e->stream)); }
-  cudaStream_t st = e->stream;
-  CU_TRY(e, cudaMemsetAsync(e->d_state.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_tstate.p, 0, g1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_dirty.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_last_att.p, 0, g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_chg_round.p, 0, sizeof(uint32_t) * g1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_cur_n.p, 0, sizeof(uint16_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_cur_info.p, 0, sizeof(uint32_t) * g1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_cur_glo.p, 0, sizeof(uint32_t) * g1, st)); CU_TRY(e, cudaMemsetAsync(e->d_extent.p, 0, sizeof(uint32_t) * g1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_sc_lvl.p, 0xFF, s1, st)); CU_TRY(e, cudaMemsetAsync(e->d_sc_lo.p, 0xFF, sizeof(uint32_t) * s1, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_claims.p, 0xFF, sizeof(uint4) * size_t(N) * kClaimSlots, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_nlive.p, 0, N, st)); CU_TRY(e, cudaMemsetAsync(e->d_ovf_head.p, 0, sizeof(uint32_t) * N, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_ctot.p, 0, sizeof(int4) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_cmaxr.p, 0, sizeof(uint32_t) * N, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_add_stamp.p, 0xFF, sizeof(uint32_t) * N, st)); CU_TRY(e, cudaMemsetAsync(e->d_rem_stamp.p, 0xFF, sizeof(uint32_t) * e->words, st));
-  CU_TRY(e, cudaMemsetAsync(e->d_rem_round.p, 0, sizeof(uint32_t) * e->words, st)); CU_TRY(e, cudaMemsetAsync(e->d_last_eval.p, 0, sizeof(uint32_t) * g1, st));
   {
-    uint32_t* c = e->h_ctl.p;
-    std::memset(c, 0, sizeof(uint32_t) * kCtlWords);
     const uint32_t W = e->tune_window ? e->tune_window : std::max(G, 1u);
     const uint32_t E = e->tune_entry ? e->tune_entry : W;
-    c[kFront] = 0; c[kHi] = std::min(G, std::min(W, E)); c[kRound] = 1; c[kMinDirty] = c[kHi]; c[kRemAny] = kFull; c[kDone] = G == 0;
-    c[kEntryLo] = 0; c[kNEval] = c[kHi];   // the first round evaluates the first window's worth of new entrants
-    CU_TRY(e, cudaMemcpyAsync(e->d_ctl.p, c, sizeof(uint32_t) * kCtlWords, cudaMemcpyHostToDevice, st));
-    CU_TRY(e, cudaStreamSynchronize(st));   // h_ctl is reused for the read-backs
     if (e->h_live) { std::memset(e->h_live, 0, sizeof(uint32_t) * kLiveWords); e->h_live[kLiveRound] = 1; }
+    k_reset<<<e->n_sm * 4, 256, 0, e->stream>>>(make_relax(e), G, S, N, e->words, std::min(G, std::min(W, E)));
+    CU_TRY(e, cudaGetLastError());
   }
   e->launches = 0; e->in_cycle = true; e->have_results = false; e->have_scopes = false;
   e->victims.clear(); e->score_pass_valid = false;

@@ -30,6 +30,30 @@ namespace grove {
 // Nothing here decides a result by arrival order: claims are sums, stamps are minima.
 // ------------------------------------------------------------------------------------------------
 
+// The state a cycle starts from, in ONE launch (it used to be two dozen memsets and a blocking upload of the control words: a tenth
+// of a millisecond of launch latencies in front of every cycle)
+__global__ void __launch_bounds__(256) k_reset(Relax rx, uint32_t G, uint32_t NS, uint32_t npad, uint32_t words, uint32_t hi0) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const uint4 ones = make_uint4(kFull, kFull, kFull, kFull);
+  for (size_t i = tid; i < size_t(npad) * kClaimSlots; i += nt) rx.claims[i] = ones;
+  for (uint32_t i = tid; i < npad; i += nt) { rx.ctot[i] = make_int4(0, 0, 0, 0); rx.cmaxr[i] = 0; rx.ovf_head[i] = 0; rx.add_stamp[i] = kFull; }
+  for (uint32_t i = tid; i < npad / 4; i += nt) rx.nlive[i] = 0;
+  for (uint32_t i = tid; i < words; i += nt) { rx.rem_stamp[i] = kFull; rx.rem_round[i] = 0; }
+  for (uint32_t i = tid; i < G; i += nt) {
+    rx.state[i] = 0; rx.tstate[i] = 0; rx.dirty[i] = 0; rx.last_att[i] = 0; rx.cur_n[i] = 0;
+    rx.chg_round[i] = 0; rx.cur_info[i] = 0; rx.cur_glo[i] = 0; rx.extent[i] = 0; rx.last_eval[i] = 0;
+  }
+  for (uint32_t i = tid; i < NS; i += nt) { rx.sc_lvl[i] = 0xFFu; rx.sc_lo[i] = kFull; }
+  if (tid < kCtlWords) {
+    uint32_t v = 0;
+    if (tid == kHi || tid == kMinDirty || tid == kNEval) v = hi0;   // the first round evaluates the first window's worth of new entrants
+    if (tid == kRound) v = 1;
+    if (tid == kRemAny) v = kFull;
+    if (tid == kDone) v = G == 0;
+    rx.ctl[tid] = v;
+  }
+}
+
 // ---- claims --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void nlive_add(uint32_t* nlive, uint32_t n, int delta) {
   const uint32_t sh = (n & 3u) * 8u;

@@ -4,7 +4,8 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 export PYTHONPATH="$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -4 | tee $O/r2_gpu_tests.log
+rm -f $O/*.ncu-rep
+if [ -z "$SKIP_TESTS" ]; then timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -4 | tee $O/r2_gpu_tests.log; fi
 timeout 600 python bench.py --steps 20 --warmup 3 > $O/r2_bench_C4.json 2> $O/r2_bench_C4.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_reference.json 2> $O/r2_bench_reference.err
 timeout 600 python bench.py --config C5 --steps 30 --warmup 5 > $O/r2_bench_C5.json 2> $O/r2_bench_C5.err
@@ -50,3 +51,5 @@ python scripts/ncu_regions.py $O/r2_k_eval_heavy.ncu-rep admit.cuh 40 > $O/r2_nc
 python scripts/ncu_regions.py $O/r2_k_apply.ncu-rep relax.cuh 25 > $O/r2_ncu_k_apply_source_hotspots.txt 2>&1
 python scripts/ncu_regions.py $O/r2_k_detect.ncu-rep relax.cuh 25 > $O/r2_ncu_k_detect_source_hotspots.txt 2>&1
 ls -la $O/r2_*.ncu-rep | awk '{print $5, $9}'
+rm -f $O/r2_*.ncu-rep    # (gpurun brings back at most 64 MiB: the text / csv exports above are what is kept)
+du -sh $O
