@@ -481,7 +481,8 @@ static int32_t load_nodes_common(grove_engine* e, const grove_node_t* host_nodes
   }
   k_gather<<<(e->Npad + 255) / 256, 256, 0, e->stream>>>(e->d_nodes_in.p, e->d_perm.p, e->d_vdepth.p, e->d_nres.p, e->N, e->Npad);
   CU_TRY(e, cudaGetLastError());
-  if (dev_nodes) CU_TRY(e, cudaStreamSynchronize(e->stream));  // the caller's device buffer is free again on return
+  // (device source: read asynchronously on the engine's stream -- the header asks the caller to leave it alone until the next
+  // blocking call on the handle returns; a synchronize here would cost every device-resident cycle a host round trip)
   e->nodes_loaded = true; e->score_pass_valid = false;
   return GROVE_OK;
 }

@@ -269,7 +269,9 @@ int32_t grove_run_score_pass(grove_engine_t* e, float* ms);
 int32_t grove_shard_summary_device(grove_engine_t* e, void* d_out, uint32_t cap_words);
 
 /* ---- device-resident variants (inputs already in HBM; used by bench.py `value`) -------------- */
-/* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load */
+/* d_nodes: device pointer to n grove_node_t in caller order, labels identical to the last load.  Read ASYNCHRONOUSLY on the
+ * engine's stream: the buffer must stay valid and unchanged until the next blocking call on the handle (grove_run_cycle,
+ * grove_run_score_pass, grove_get_nodes) has returned. */
 int32_t grove_load_nodes_device(grove_engine_t* e, const void* d_nodes, uint32_t n);
 
 /* ---- introspection for the parity tests (sorted node order; see DESIGN.md "Data layout") ------ */
