@@ -141,6 +141,7 @@ struct grove_engine {
   PinBuf<GangInfo> ginfo_pin;      // derived tables are built straight into pinned memory: their upload is a plain DMA
   PinBuf<CliqueInfo> cinfo_pin;
   PinBuf<uint32_t> by_rank_pin;
+  PinBuf<uint32_t> shape_rep_pin;
   GangInfo* ginfo = nullptr;
   CliqueInfo* cinfo = nullptr;
   std::vector<uint4> sigs;
@@ -869,8 +870,9 @@ static int32_t build_ginfo(grove_engine* e) {
   if (G) CU_TRY(e, cudaMemcpyAsync(e->d_by_rank.p, e->by_rank_pin.p, sizeof(uint32_t) * G, cudaMemcpyHostToDevice, e->stream));
   if (e->shape_tables) {
     CU_TRY(e, e->d_shape_rep.ensure(e->n_shapes)); CU_TRY(e, e->d_shape_bits.ensure(size_t(e->n_shapes) * e->pl_words));
-    CU_TRY(e, cudaMemcpyAsync(e->d_shape_rep.p, e->shape_rep.data(), sizeof(uint32_t) * e->n_shapes, cudaMemcpyHostToDevice, e->stream));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));   // shape_rep is a pageable vector
+    CU_TRY(e, e->shape_rep_pin.ensure(e->n_shapes));   // (pinned: the upload is a plain DMA the host does not wait for; the buffer is
+    std::memcpy(e->shape_rep_pin.p, e->shape_rep.data(), sizeof(uint32_t) * e->n_shapes);   //  rewritten only after the cycle that reads it)
+    CU_TRY(e, cudaMemcpyAsync(e->d_shape_rep.p, e->shape_rep_pin.p, sizeof(uint32_t) * e->n_shapes, cudaMemcpyHostToDevice, e->stream));
   }
   e->ginfo_dirty = false;
   if (std::getenv("GROVE_DEBUG_HOST")) {
@@ -974,10 +976,14 @@ static int32_t finish_cycle(grove_engine* e) {
     CU_TRY(e, cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(grove_gang_status_t) * G, cudaMemcpyDeviceToHost, e->stream));
     // the placement count is only known on the device: copy the upper bound's worth in the same breath when it is small,
     // else wait for the count
+    const bool eager = size_t(e->P) * sizeof(grove_placement_t) <= (8u << 20);   // a few hundred KB at C4: cheaper than a second round trip
+    if (eager && e->P) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->P, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(e, cudaStreamSynchronize(e->stream));
     e->n_out = e->h_ctl.p[0];
-    if (e->n_out) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->n_out, cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    if (!eager) {
+      if (e->n_out) CU_TRY(e, cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(grove_placement_t) * e->n_out, cudaMemcpyDeviceToHost, e->stream));
+      CU_TRY(e, cudaStreamSynchronize(e->stream));
+    }
     e->last.gangs_admitted = e->h_ctl.p[1]; e->last.gangs_rejected = e->h_ctl.p[2];
   }
   (void)tp;
