@@ -17,8 +17,21 @@ for seed in (3001, 3007, 3012):   # Preferred levels at gang / scope / clique, i
     nodes, L, (g, c, s) = random_case(seed, pref=True)
     with PlacementEngine(L) as e:
         e.load_nodes(nodes); e.submit_gangs(g, c, s); st = e.run_cycle(); print("pref", st["rounds"], st["gangs_admitted"])
+# the reclaim pass and the sharded score pass
+sys.path.insert(0, 'tests')
+import numpy as np, torch
+from oracle import oracle_py as O
+from preempt_cases import churned_cluster
+from grove_b200.sharded import engine_summary
+nodes, L, (g, c, s), running, holdings = churned_cluster(O, 11, n=1260, g_running=200, g_pending=100)
+with PlacementEngine(L) as e:
+    e.load_nodes(nodes); e.submit_gangs(g, c, s); st = e.run_cycle_preempt(running, holdings); print("preempt", st["gangs_admitted"], len(e.victims()))
+for r in range(2):
+    with PlacementEngine(L, rank=r, world=2) as e:
+        e.load_nodes(nodes); e.submit_gangs(g, c, s); e.run_score_pass(); t = engine_summary(e, torch.device("cuda", 0))(r); print("shard", r, int(t.sum()))
 PY
-for tool in memcheck racecheck; do
+cd "${GRAFT_REPO_ROOT:-.}"; export PYTHONPATH="${GRAFT_REPO_ROOT:-.}"
+for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
-  tail -3 gpurun_out/sanitizer_$tool.log
+  tail -2 gpurun_out/sanitizer_$tool.log
 done
