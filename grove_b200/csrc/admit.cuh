@@ -759,6 +759,14 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
     const grove_gang_t gg = tb.gangs[gi];
     const GangInfo info = tb.ginfo[gi];
     __syncthreads();   // the previous gang's shared state is no longer read
+    // the gang's cliques and scopes (a lane each), the words of the re-evaluation shortcut and the base gang's rank are asked for
+    // BEFORE anything looks at them: one L2 round trip for all of them instead of one per question
+    const bool has_c = lane < gg.n_cliques, has_s = lane < gg.n_scopes;
+    const grove_clique_t q0 = has_c ? tb.cliques[gg.clique_off + lane] : grove_clique_t{};
+    const CliqueInfo ci0 = has_c ? tb.cinfo[gg.clique_off + lane] : CliqueInfo{};
+    const grove_scope_t sc0 = has_s ? tb.scopes[gg.scope_off + lane] : grove_scope_t{};
+    const uint32_t round_now = rx.ctl[kRound];
+    const uint32_t le = rx.last_eval[gi], fu_word = rx.fail_upto[gi], ext_word = rx.extent[gi];
     // ---- gangs that need no packing
     uint32_t trivial = 0;
     if (gg.flags & GROVE_GANG_GATED) trivial = GROVE_GANG_GATED_SKIP;
@@ -780,9 +788,10 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
     g.a = info.anchor; g.L = tp.L; g.n = tp.n; g.rank = info.order;
 #pragma unroll
     for (int l = 0; l < GROVE_MAX_LEVELS; ++l) { g.anc_lo[l] = info.anc_lo[l]; g.anc_hi[l] = info.anc_hi[l]; }
-    for (uint32_t c = lane; c < gg.n_cliques; c += 32) {   // every warp keeps its own copy: attempts run independently
-      const grove_clique_t q = tb.cliques[gg.clique_off + c];
-      const CliqueInfo ci = tb.cinfo[gg.clique_off + c];
+    if (has_c) {   // every warp keeps its own copy: attempts run independently (GROVE_MAX_GANG_CLIQUES = 32: a lane each)
+      const uint32_t c = lane;
+      const grove_clique_t q = q0;
+      const CliqueInfo ci = ci0;
       sh.clq[c] = make_uint4(q.req_cpu_milli, q.req_mem_mib, q.req_gpu,
                              uint32_t(q.min_replicas) | (uint32_t(q.replicas) << 8) | (uint32_t(q.level) << 16) |
                                  (GROVE_CLIQUE_PREFERRED(q.scope) << 24));
@@ -791,15 +800,13 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
       sh.sig[c] = ci.sig; sh.smask[c] = uint32_t(q.class_mask) | (ci.need_depth << 16);
       sh.Hlo[c] = 0; sh.Hhi[c] = 0; sh.c_got[c] = -1;
     }
-    for (uint32_t si = lane; si < gg.n_scopes; si += 32) { sh.scopes[si] = tb.scopes[gg.scope_off + si]; sh.s_got[si] = -1; sh.s_lo[si] = 0; }
+    if (has_s) { sh.scopes[lane] = sc0; sh.s_got[lane] = -1; sh.s_lo[lane] = 0; }
     if (threadIdx.x == 0) { s_win = GROVE_NONE_U32; s_ext = 0; s_att = 0; s_npl = 0; }
     __syncthreads();
     // A candidate that failed in the gang's last evaluation fails again unless a claim was withdrawn inside it since: views only
     // shrink otherwise (claims are added, settled claims move into the committed state).  So a re-evaluation skips the
     // candidates in front of its last answer that no withdrawal touched -- gangs that meet a nearly full cluster would
     // otherwise re-run dozens of failing attempts every round.  (Single candidate level only.)
-    const uint32_t round_now = rx.ctl[kRound];
-    const uint32_t le = rx.last_eval[gi];
     Ev<kPref> ev(tp, rx, sh, g, lane);                         // candidates of any size, node state from L2
     EvS<kPref> evs(tp, rx, sh, g, lane, s_view[warp], s_vflag[warp], s_rk[warp]);         // candidates of <= kStageMax nodes, node state staged in shared memory
     bool staged = false;  // the winning attempt ran on evs
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
     int gfirst;
     const int gbase = level_span<kPref>(gg.level, gg.preferred, -1, gfirst);
     int gl = gfirst;
-    const uint32_t fu = (le && gfirst == gbase && gfirst >= 0) ? rx.fail_upto[gi] : 0u;
+    const uint32_t fu = (le && gfirst == gbase && gfirst >= 0) ? fu_word : 0u;
     uint32_t k_won = 0;
     bool gave_up = false;
     do {
@@ -901,7 +908,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
       }
     } while (kPref && !done && !gave_up && --gl >= gbase);
     // what any of the attempts may have read (attempts past the winner only widen it)
-    if (lane == 0) atomicMax(&s_ext, max(max(ev.ext, evs.ext), fu ? rx.extent[gi] : 0u));   // skipped candidates were read by the last evaluation
+    if (lane == 0) atomicMax(&s_ext, max(max(ev.ext, evs.ext), fu ? ext_word : 0u));   // skipped candidates were read by the last evaluation
     __syncthreads();
     if (threadIdx.x == 0) rx.last_att[gi] = uint8_t(gave_up ? 255u : min(254u, s_att));
     if (gave_up) {   // no result this round: k_apply keeps the gang dirty

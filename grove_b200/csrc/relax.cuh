@@ -148,23 +148,31 @@ __global__ void __launch_bounds__(256) k_apply(Tables tb, Relax rx) {
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < n_eval; ei += nw) {
     const uint32_t g = eval_list_at(rx, tb, ei);
+    // every word the comparison needs is asked for at once (a chain of `||` would fetch them one L2 round trip after the other)
     const grove_gang_t gg = tb.gangs[g];
     const uint32_t po = tb.ginfo[g].pod_off, rank = tb.ginfo[g].order;
     const uint32_t ot = rx.tstate[g], nt = rx.nxt_tstate[g];
+    const uint32_t c_n = rx.cur_n[g], n_n = rx.nxt_n[g], c_info = rx.cur_info[g], n_info = rx.nxt_info[g], c_glo = rx.cur_glo[g], n_glo = rx.nxt_glo[g];
+    const uint32_t n_ext = rx.nxt_extent[g];
     if (lane == 0) rx.dirty[g] = nt == kEvalDeferred;   // the only dirtiness that outlives a round: no result yet
     if (nt == kEvalDeferred) {   // the light evaluation gave up: no result, the gang is evaluated again (as a heavy one) next round
       if (lane == 0) atomicMin(rx.ctl + kMinDirty, rank);
       continue;
     }
-    const uint32_t on = ot == GROVE_GANG_ADMITTED ? rx.cur_n[g] : 0u, nn = nt == GROVE_GANG_ADMITTED ? rx.nxt_n[g] : 0u;
-    bool diff = ot != nt || on != nn || rx.cur_info[g] != rx.nxt_info[g] || rx.cur_glo[g] != rx.nxt_glo[g];
+    const uint32_t on = ot == GROVE_GANG_ADMITTED ? c_n : 0u, nn = nt == GROVE_GANG_ADMITTED ? n_n : 0u;
+    bool diff = (ot != nt) | (on != nn) | (c_info != n_info) | (c_glo != n_glo);
     if (!diff) {
-      for (uint32_t i = lane; i < nn; i += 32) diff |= rx.ent_node[po + i] != rx.nxt_node[po + i] || rx.ent_meta[po + i] != rx.nxt_meta[po + i];
-      for (uint32_t si = lane; si < gg.n_scopes; si += 32)
-        diff |= rx.sc_lvl[gg.scope_off + si] != rx.nxt_sc_lvl[gg.scope_off + si] || rx.sc_lo[gg.scope_off + si] != rx.nxt_sc_lo[gg.scope_off + si];
+      for (uint32_t i = lane; i < nn; i += 32) {
+        const uint32_t a = rx.ent_node[po + i], b = rx.nxt_node[po + i]; const uint16_t c = rx.ent_meta[po + i], d = rx.nxt_meta[po + i];
+        diff |= (a != b) | (c != d);
+      }
+      for (uint32_t si = lane; si < gg.n_scopes; si += 32) {
+        const uint8_t a = rx.sc_lvl[gg.scope_off + si], b = rx.nxt_sc_lvl[gg.scope_off + si]; const uint32_t c = rx.sc_lo[gg.scope_off + si], d = rx.nxt_sc_lo[gg.scope_off + si];
+        diff |= (a != b) | (c != d);
+      }
     }
     diff = __any_sync(kFull, diff);
-    if (lane == 0) rx.extent[g] = rx.nxt_extent[g];   // what the LATEST evaluation read, changed result or not
+    if (lane == 0) rx.extent[g] = n_ext;   // what the LATEST evaluation read, changed result or not
     if (!diff) continue;
     const uint32_t stamp = make_stamp(round, rank);
     // withdraw the old claims
@@ -208,18 +216,22 @@ __global__ void __launch_bounds__(256) k_detect(Topo tp, Tables tb, Relax rx, ui
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t p = front + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < hi; p += nw) {
     const uint32_t g = tb.by_rank[p];   // rank of g == p
-    const grove_gang_t gg = tb.gangs[g];
+    // the gang's words are asked for at once (conditions one after the other would fetch them one L2 round trip each)
+    const uint32_t base = tb.gangs[g].base_gang;
+    const uint32_t po = tb.ginfo[g].pod_off;
+    const uint32_t ts = rx.tstate[g], cnt = rx.cur_n[g], ext = rx.extent[g];
     bool dirty = rx.dirty[g] != 0;   // its evaluation gave up this round (k_apply)
+    const uint32_t first_node = (ts == GROVE_GANG_ADMITTED && lane < cnt) ? rx.ent_node[po + lane] : GROVE_NONE_U32;
     // its base gang's result changed
-    if (gg.base_gang != GROVE_NONE_U32 && rx.chg_round[gg.base_gang] == round) dirty = true;
+    if (base != GROVE_NONE_U32 && rx.chg_round[base] == round) dirty = true;
     // a lower rank newly claimed a node this gang uses
-    if (!dirty && rx.tstate[g] == GROVE_GANG_ADMITTED) {
-      const uint32_t po = tb.ginfo[g].pod_off, cnt = rx.cur_n[g];
-      for (uint32_t i = lane; i < cnt; i += 32) dirty |= stamp_below(rx.add_stamp[rx.ent_node[po + i]], round, p);
-      dirty = __any_sync(kFull, dirty);
+    if (ts == GROVE_GANG_ADMITTED) {
+      if (first_node != GROVE_NONE_U32) dirty |= stamp_below(rx.add_stamp[first_node], round, p);
+      for (uint32_t i = lane + 32; i < cnt; i += 32) dirty |= stamp_below(rx.add_stamp[rx.ent_node[po + i]], round, p);
     }
+    dirty = __any_sync(kFull, dirty);
     // a lower rank withdrew a claim among the nodes the last evaluation may have read
-    uint32_t left = rx.extent[g];
+    uint32_t left = ext;
     if (!dirty && left && stamp_below(rem_any, round, p)) {
       const GangInfo info = tb.ginfo[g];
       GangRegs gr;
