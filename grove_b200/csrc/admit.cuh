@@ -593,6 +593,14 @@ __device__ GROVE_NI bool place_scope(Ev& ev, const grove_scope_t& s, uint32_t lo
 template <class Ev>
 __device__ GROVE_NI bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32_t hi, int lvl) {
   const Topo& tp = ev.tp;
+  // (staged evaluator) the first / end domain index of every deeper level inside [lo, hi): asked for BEFORE the staging so that
+  // the look-ups overlap it -- each scope with a narrower level would otherwise start with one more L2 round trip
+  uint32_t pd0[GROVE_MAX_LEVELS], pd1[GROVE_MAX_LEVELS];
+#pragma unroll
+  for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) {
+    pd0[l] = pd1[l] = 0;
+    if (Ev::kStaged && int(l) > lvl && l < tp.L) { pd0[l] = __ldg(tp.next_dom[l] + lo); pd1[l] = __ldg(tp.next_dom[l] + hi); }
+  }
   ev.begin(lo, hi);
   for (uint32_t si = 0; si < n_scopes; ++si) {
     const grove_scope_t s = ev.sh.scopes[si];
@@ -607,7 +615,9 @@ __device__ GROVE_NI bool place_in(Ev& ev, uint32_t n_scopes, uint32_t lo, uint32
           // the staged range holds at most kStageMax nodes: usually all its level-sl domains fit one warp pass.  A lane each:
           // filter them ONCE against the staged view, then attempt the survivors in visiting order (piece by piece, ascending
           // inside a piece -- the order of the general walk below)
-          const uint32_t d0 = __ldg(tp.next_dom[sl] + lo), d1 = __ldg(tp.next_dom[sl] + hi);
+          uint32_t d0 = 0, d1 = 0;
+#pragma unroll
+          for (uint32_t l = 0; l < GROVE_MAX_LEVELS; ++l) if (int(l) == sl) { d0 = pd0[l]; d1 = pd1[l]; }
           if (d1 - d0 <= 32u) {
             filtered = true;
             const long long tp0 = ev.rb.dbg ? clock64() : 0;
@@ -748,6 +758,7 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
   __shared__ uint32_t s_vflag[kW][kStageMax];
   __shared__ __align__(16) uint8_t s_rk[kW][kStageMax + 256];
   __shared__ uint32_t s_plaus[32];   // plausible candidates of the current 1024-candidate chunk, in order
+  __shared__ uint32_t s_cl[kW][32], s_ch[kW][32];   // node ranges of the first chunk's candidates (kW runs of 32)
   __shared__ uint32_t s_win, s_ext, s_att, s_npl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_eval = rx.ctl[kNEval], n_heavy = rx.ctl[kNHeavy];
@@ -857,17 +868,17 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
             const uint32_t k = base + c * 32 + lane;
             bool plaus = false;
             if (k < D) {
+              // the candidate's node range is fetched together with its pre-filter bit (the attempt would otherwise pay one more
+              // L2 round trip for it); the first chunk's ranges wait in shared memory
+              uint32_t dl, dh; const uint32_t d = cand(k, dl, dh);
               if (rx.shape_bits) {   // one bit per (shape, domain), refreshed with the capacity tables
-                uint32_t d = 0, rem = k;
-#pragma unroll
-                for (int p = 0; p < kMaxPieces; ++p) { if (rem < rcnt[p]) { d = r0[p] + rem; break; } rem -= rcnt[p]; }
                 const uint32_t bit = rx.pl_off[gl] + d;
                 plaus = (__ldg(rx.shape_bits + size_t(info.pad) * rx.pl_words + (bit >> 5)) >> (bit & 31u)) & 1u;
               } else {
-                uint32_t dl, dh; const uint32_t d = cand(k, dl, dh); plaus = gang_plausible(tp, rx, sh, gg.n_scopes, dl, dh, gl, d);
+                plaus = gang_plausible(tp, rx, sh, gg.n_scopes, dl, dh, gl, d);
               }
+              if (base == 0) { s_cl[c][lane] = dl; s_ch[c][lane] = dh; }
               if (plaus && k < fu) {   // failed last time: worth another attempt only if somebody withdrew a claim in there since
-                uint32_t dl, dh; cand(k, dl, dh);
                 bool again = false;
                 for (uint32_t w = dl >> 5; w <= (dh - 1u) >> 5; ++w) again |= __ldg(rx.rem_round + w) >= le;
                 plaus = again;
@@ -892,8 +903,8 @@ __global__ void __launch_bounds__(kW * 32, kW == 1 ? 16 : 2) k_eval(Topo tp, Tab
               for (; c + 1 < nchunk; ++c) { const uint32_t pc = __popc(s_plaus[c]); if (rem < pc) break; rem -= pc; }
               uint32_t w = s_plaus[c];
               for (uint32_t i = 0; i < rem; ++i) w &= w - 1;
-              const uint32_t k = base + c * 32 + (__ffs(w) - 1);
-              cand(k, dl, dh);
+              const uint32_t kl = __ffs(w) - 1, k = base + c * 32 + kl;
+              if (base == 0) { dl = s_cl[c][kl]; dh = s_ch[c][kl]; } else cand(k, dl, dh);
               staged = dh - dl <= kStageMax;
               ok = staged ? place_in(evs, gg.n_scopes, dl, dh, gl) : place_in(ev, gg.n_scopes, dl, dh, gl);
               if (lane == 0) { atomicAdd(&s_att, 1u); if (ok) atomicMin(&s_win, j); }
