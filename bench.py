@@ -206,6 +206,9 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU oracle)")
+    # one rank per GPU shares the box's cores: the engine's host thread team (table validation, derived tables) is sized to this
+    # rank's share, and one core per rank stays free for the thread that follows the relaxation
+    os.environ.setdefault("GROVE_HOST_THREADS", str(max(1, min(8, host_cores() // max(world, 1) - 1))))
     build.build()
     torch.cuda.set_device(local)
     dist = None
@@ -351,6 +354,7 @@ def run_sharded(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    os.environ.setdefault("GROVE_HOST_THREADS", str(max(1, min(8, host_cores() // max(world, 1) - 1))))
     build.build()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

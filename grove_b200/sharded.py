@@ -54,8 +54,12 @@ def engine_summary(engine, device):
     `device` (the buffer NCCL reduces in place)"""
     import torch
 
+    buf = {}
+
     def fn(_rank):
-        t = torch.zeros(engine.G + engine.Q, dtype=torch.int32, device=device)
-        engine.shard_summary_into(t.data_ptr(), t.numel())
-        return t
+        n = engine.G + engine.Q
+        if buf.get("n") != n:   # one buffer per submission size: the pass runs every cycle
+            buf["t"], buf["n"] = torch.empty(n, dtype=torch.int32, device=device), n
+        engine.shard_summary_into(buf["t"].data_ptr(), n)   # every word of the vector is written
+        return buf["t"]
     return fn
