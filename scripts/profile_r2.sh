@@ -10,10 +10,9 @@ timeout 600 python bench.py --steps 20 --warmup 3 > $O/r2_bench_C4.json 2> $O/r2
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_reference.json 2> $O/r2_bench_reference.err
 timeout 600 python bench.py --config C5 --steps 30 --warmup 5 > $O/r2_bench_C5.json 2> $O/r2_bench_C5.err
 for c in C1 C2 C3; do timeout 300 python bench.py --config $c --steps 20 --warmup 3 > $O/r2_bench_$c.json 2> $O/r2_bench_$c.err; done
-timeout 600 python bench.py --config C4X --steps 10 --warmup 3 > $O/r2_bench_C4X_n1.json 2> $O/r2_bench_C4X_n1.err
 python - <<'PY'
 import json
-for n in ("C4", "reference", "C5", "C1", "C2", "C3", "C4X_n1"):
+for n in ("C4", "reference", "C5", "C1", "C2", "C3"):
     try:
         d = json.loads(open(f"gpurun_out/r2_bench_{n}.json").read().strip().splitlines()[-1])
         print(n, round(d["ms_per_step"], 3), "ms", round(d["value"]), d["unit"], "e2e", round(d["e2e"]["ms_per_step"], 3) if "ms_per_step" in d["e2e"] else "", (d.get("cpu_baseline") or {}).get("outputs_identical_to_gpu"))
@@ -34,6 +33,7 @@ with PlacementEngine(cfg["n_levels"]) as e:
     ms = e.build_score_matrix()
     print(st, ms)
 PY
+if [ -n "$ONLY_BENCH" ]; then du -sh $O; exit 0; fi
 cap() { timeout 600 ncu --set full --import-source on --clock-control none -k regex:$1 --launch-skip $2 --launch-count 1 -o $O/r2_$3 -f python /tmp/c4one.py > $O/r2_$3.log 2>&1; }
 cap k_eval 13 k_eval_light     # round 7, a warp per gang
 cap k_eval 18 k_eval_heavy     # round 10, eight warps per gang
