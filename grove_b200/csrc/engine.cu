@@ -1088,6 +1088,9 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
           ++enq; spins = 0;
           continue;
         }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();   // (a polite spin: the sibling hyper-thread may be another rank's)
+#endif
         if ((++spins & 0xFFFFu) == 0) {   // a failed launch / a sticky error must not leave the host spinning
           const cudaError_t q = cudaStreamQuery(e->stream);
           if (q != cudaSuccess && q != cudaErrorNotReady) { e->err = std::string("relaxation: ") + cudaGetErrorString(q); return GROVE_ERR_CUDA; }
@@ -1267,6 +1270,20 @@ int32_t grove_run_cycle_preempt(grove_engine_t* e, const grove_running_gang_t* r
     std::vector<grove_node_t> real(N), view(N);
     rc = grove_get_nodes(e, real.data(), N);
     if (rc) return rc;
+    // whatever goes wrong from here on, the handle goes back to the caller's submission on the node table of the ordinary pass
+    // (its class cycles re-use the handle); the error of the failing call is what the caller sees
+    struct Restore {
+      grove_engine* e; const std::vector<grove_node_t>* nodes; const std::vector<grove_gang_t>* g; const std::vector<grove_clique_t>* c; const std::vector<grove_scope_t>* s; bool armed = true;
+      ~Restore() {
+        if (!armed) return;
+        const std::string keep = e->err;
+        grove_load_nodes(e, nodes->data(), uint32_t(nodes->size()));
+        grove_submit_gangs(e, g->data(), uint32_t(g->size()), c->data(), uint32_t(c->size()), s->data(), uint32_t(s->size()));
+        e->err = keep;
+      }
+    };
+    const std::vector<grove_node_t> real0 = real;
+    Restore restore{e, &real0, &gangs, &cliques, &scopes};
     std::vector<uint8_t> evicted(n_running, 0);
     // running gangs by node (CSR), for the victim choice
     std::vector<uint32_t> at_off(size_t(N) + 1, 0), at_run(n_holdings);
@@ -1346,6 +1363,7 @@ int32_t grove_run_cycle_preempt(grove_engine_t* e, const grove_running_gang_t* r
       }
     }
     // the handle goes back to the caller's submission, on the node table that is really free now
+    restore.armed = false;
     rc = grove_load_nodes(e, real.data(), N); if (rc) return rc;
     rc = grove_submit_gangs(e, gangs.data(), G, cliques.data(), Q, scopes.data(), S); if (rc) return rc;
   }

@@ -46,6 +46,7 @@ def test_struct_layouts_match_header(tmp_path):
         "grove_gang_t": T.gang_dt, "grove_placement_t": T.placement_dt, "grove_gang_status_t": T.status_dt,
         "grove_scope_status_t": T.scope_status_dt,
         "grove_config_t": T.config_dt, "grove_cycle_stats_t": T.stats_dt,
+        "grove_holding_t": T.holding_dt, "grove_running_gang_t": T.running_dt, "grove_victim_t": T.victim_dt,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for name, dt in fields.items():
