@@ -1073,6 +1073,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
     // (or a table rebuild first, when the device asked for one).  The GPU never waits for the host; the only waste is the
     // <= ahead rounds in the queue when the cycle ends, which return at once.
     const bool polled = e->h_live && e->tune_ahead > 0 && !e->dbg_on;
+    bool use_batch = !polled;   // the batch protocol below: also the way out should the progress words ever stop moving
     if (polled) {
       volatile uint32_t* lv = e->h_live;
       uint32_t enq = 0, rebuild_at = 0;   // rounds enqueued; the last rebuild enqueued runs before round rebuild_at + 1
@@ -1094,10 +1095,13 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
         if ((++spins & 0xFFFFu) == 0) {   // a failed launch / a sticky error must not leave the host spinning
           const cudaError_t q = cudaStreamQuery(e->stream);
           if (q != cudaSuccess && q != cudaErrorNotReady) { e->err = std::string("relaxation: ") + cudaGetErrorString(q); return GROVE_ERR_CUDA; }
+          // nothing left in flight on the engine's stream, yet the words say rounds are outstanding: do not trust them any
+          // further -- the control words themselves are read from here on
+          if (q == cudaSuccess && lv[kLiveRound] - 1u == completed && !lv[kLiveDone]) { use_batch = true; break; }
         }
       }
     }
-    for (; !polled || next_round == 0;) {   // (the batch protocol: look at the control words between batches of rounds)
+    for (; use_batch;) {   // (the batch protocol: look at the control words between batches of rounds)
       for (uint32_t b = 0; b < batch; ++b) { rc = enqueue_round(); if (rc) return rc; }
       CU_TRY(e, cudaGetLastError());
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
@@ -1124,7 +1128,7 @@ int32_t grove_run_cycle(grove_engine_t* e, grove_cycle_stats_t* stats) {
       if (c[kDone]) break;
       if (c[kRefresh]) { rc = fold_and_rebuild(); if (rc) return rc; }
     }
-    if (polled) {   // the cycle is over (the queue holds at most a few rounds that return at once): the final control words
+    if (polled && !use_batch) {   // the cycle is over (the queue holds at most a few rounds that return at once): the final control words
       CU_TRY(e, cudaMemcpyAsync(e->h_ctl.p, e->d_ctl.p, sizeof(uint32_t) * kCtlWords, cudaMemcpyDeviceToHost, e->stream));
       CU_TRY(e, cudaStreamSynchronize(e->stream));
       if (e->h_ctl.p[kOvfCount] > rx.ovf_cap) return fail(e, GROVE_ERR_LIMIT, "claim overflow pool exhausted");
