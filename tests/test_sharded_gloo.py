@@ -63,3 +63,27 @@ def test_all_reduced_shard_summaries(oracle, tmp_path, world):
     ref = oracle.run_cycle(nodes, L, g, c, s)
     assert bad.any() and not bad.all()
     assert (ref["status"]["state"][bad] != T.GANG_ADMITTED).all()   # a necessary condition: what it rules out is never admitted
+
+
+def test_infeasible_from_sum_reads_the_reduced_vector():
+    """gang 0: Required level, no feasible domain anywhere -> infeasible; gang 1: Required level, one feasible domain -> not;
+    gang 2: no Required level, a clique whose MinReplicas exceed the cluster's capacity -> infeasible; gang 3: neither"""
+    from grove_b200 import tables as T
+    from grove_b200.sharded import infeasible_from_sum
+    b = T.GangTableBuilder()
+    for lvl in (1, 1, None, None):
+        b.add_gang([(None, [dict(cpu=1000, mem=1, gpu=0, min=4), dict(cpu=1000, mem=1, gpu=0, min=0)])], level=lvl)
+    g, c, s = b.build()
+    total = np.array([0, 1, 0, 0,   9, 0,  9, 0,  3, 0,  4, 0], dtype=np.int64)   # [G feasible-domain counts | Q capacity counts]
+    assert infeasible_from_sum(total, g, c).tolist() == [True, False, True, False]
+
+
+def test_shard_cut_tiles_the_table_at_top_level_boundaries(oracle):
+    dom0 = np.repeat(np.arange(5, dtype=np.uint32), [7, 3, 10, 1, 9])          # five zones of uneven size, 30 nodes
+    dom0 = np.concatenate([dom0, np.full(2, 0xFFFFFFFF, dtype=np.uint32)])     # two nodes without the label, sorted last
+    n = len(dom0)
+    for world in (1, 2, 3, 4, 8):
+        cuts = [oracle.shard_cut(n, dom0, r, world) for r in range(world + 1)]
+        assert cuts[0] == 0 and cuts[-1] == n and cuts == sorted(cuts)
+        for cpos in cuts[1:-1]:
+            assert cpos == n or (dom0[cpos] != dom0[cpos - 1] and dom0[cpos] != 0xFFFFFFFF)
