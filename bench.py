@@ -16,9 +16,12 @@ and comes out admitted or rejected, with the result of the SEQUENTIAL priority-o
 `cpu_baseline`/--impl reference   the CPU oracle (a C restatement: the reference tree holds no scheduler and there is no Go
               toolchain) on this box's host cores.  The gang loop of the sequential pass cannot be parallelised; OpenMP
               threads split each gang's fit/score rows over the nodes.
---gpus N      N > 1: replicas only: one cluster is one sequential dependency chain of ~1.6 MB of state, so
+--gpus N      N > 1: replicas: one cluster is one sequential dependency chain of ~1.6 MB of state, so
               every rank schedules ITS OWN cluster snapshot (same shape, rank-specific seed), no data-path collective;
               value = gangs admitted by all ranks / max-over-ranks time, scaling "weak".
+--config C4X  the part of the path that DOES shard: the score pass (K1 + K2) on a cluster 4x C4, node-range shards, one rank per
+              GPU, ONE all-reduce of per-shard feasibility / capacity counts (NCCL); strong scaling, pairs scored per second.
+--config C5   steady-state churn (BASELINE.json config 5); C1..C3 the smaller configurations.
 """
 from __future__ import annotations
 
