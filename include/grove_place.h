@@ -145,7 +145,7 @@ typedef struct grove_gang_status {
   uint8_t state;
   uint8_t level;           /* level of the domain the whole gang was packed into (its Required level, or the deeper
                               Preferred level that held), GROVE_LEVEL_NONE = the whole cluster / not admitted */
-  uint16_t reserved0;
+  uint16_t reserved0;      /* flags: GROVE_STATUS_PREEMPTOR = admitted by the reclaim pass of grove_run_cycle_preempt; else 0 */
   uint16_t score_num;      /* PlacementScore = score_num / score_den (podgang.go:187-189): over the gang, its scopes and
                               its cliques that carry a pack constraint, (levels honoured) / (levels asked for), where
                               asked = Preferred if set else Required; 1/1 when nothing was asked or everything held;
